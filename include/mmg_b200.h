@@ -1,0 +1,254 @@
+/*
+ * mmg_b200.h — C-ABI of the B200-native referential-game hot path (libmmg_b200.so).
+ *
+ * Drop-in boundary: the reference (nyu-dl/MultimodalGame) has no FFI layer; its operator
+ * API for this path is the Python surface of model.py.  The host-side mirror of that surface lives in
+ * multimodalgame_b200/model.py (Sender / Receiver / Baseline / exchange / loss functions, same names and
+ * argument meaning); underneath it, every tensor operation of the training iteration is executed by the
+ * entry points declared here.  Each entry point cites the reference code it replaces (file:line into
+ * /root/reference).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types in any signature;
+ *   - all `void* d_*` / `float* d_*` arguments are DEVICE pointers into caller-owned storage (the caller
+ *     keeps them alive until the stream has drained); `h_*` arguments are HOST pointers (pinned for
+ *     asynchronous copies);
+ *   - nothing is allocated inside the library; `mmg_workspace_layout` tells the caller how much scratch
+ *     to provide and where each named array lives in it;
+ *   - every function returns 0 on success or a negative mmg_status; nothing throws across the ABI;
+ *     `mmg_last_error()` returns a static string describing the last failure on the calling thread;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), stream-ordered, no host sync
+ *     unless stated; the sequences are CUDA-graph capturable.
+ */
+#ifndef MMG_B200_H_
+#define MMG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMG_ABI_VERSION 1
+
+typedef enum mmg_status {
+    MMG_OK = 0,
+    MMG_ERR_INVALID = -1,      /* bad argument / unsupported dimension */
+    MMG_ERR_CUDA = -2,         /* a CUDA runtime call failed (see mmg_last_error) */
+    MMG_ERR_UNSUPPORTED = -3,  /* flag combination outside the fused path */
+    MMG_ERR_NO_DEVICE = -4     /* no CUDA device: the library never falls back to the CPU */
+} mmg_status;
+
+enum { MMG_OPT_RMSPROP = 0, MMG_OPT_ADAM = 1, MMG_OPT_SGD = 2 }; /* model.py:1111-1137 */
+
+/* Flags that shape the path.  Field names follow the reference's gflags (model.py:1641-1741). */
+typedef struct mmg_config {
+    int32_t batch;          /* rows handled by THIS rank (FLAGS.batch_size / world size)                  */
+    int32_t batch_global;   /* global batch: denominators of every mean (== batch on a single GPU)         */
+    int32_t img_feat_dim;   /* F   model.py:1693 */
+    int32_t img_h_dim;      /* Hi  model.py:1694 */
+    int32_t msg_dim;        /* M = rec_w_dim = sender_out_dim (asserted equal, model.py:1756) */
+    int32_t rec_hidden;     /* Hr  model.py:1697 */
+    int32_t n_classes;      /* D   rows of `desc` */
+    int32_t wv_dim;         /* WV  model.py:1674 */
+    int32_t baseline_hid;   /* Hb  model.py:1695 */
+    int32_t max_exchange;   /* T   model.py:1736 */
+    int32_t use_binary;     /* model.py:1701 */
+    int32_t fixed_exchange; /* model.py:1737 */
+    int32_t s_prob_prod;    /* model.py:1713 (eval only) */
+    int32_t optim_type;     /* MMG_OPT_* */
+    int32_t has_entropy_s, has_entropy_sen, has_entropy_rec; /* 0 when the flag is None (model.py:925) */
+    float entropy_s, entropy_sen, entropy_rec;                /* model.py:1730-1732 */
+    float first_rec;        /* model.py:1709 */
+    float learning_rate;    /* model.py:1728 */
+    float max_norm;         /* clip_grad_norm(..., max_norm=1.) model.py:1310 */
+    int32_t ignore_receiver; /* model.py:1703,470-472 */
+    int32_t reserved[7];
+} mmg_config;
+
+/* ---- parameter layout -------------------------------------------------------------------------------
+ * One flat fp32 buffer holds the four modules' parameters, in optimizer order (model.py:1308-1330):
+ * receiver | sender | baseline_rec | baseline_sen.  Every tensor keeps the reference's state_dict name,
+ * shape and row-major layout; offsets are multiples of 4 floats, padding stays zero.
+ * Gradients and optimizer state use the same layout. */
+enum {
+    MMG_P_REC_RNN_WIH = 0,  /* receiver.rnn.weight_ih   (3Hr, M)   gate order r,z,n  model.py:256 */
+    MMG_P_REC_RNN_WHH,      /* receiver.rnn.weight_hh   (3Hr, Hr) */
+    MMG_P_REC_RNN_BIH,      /* receiver.rnn.bias_ih     (3Hr)     */
+    MMG_P_REC_RNN_BHH,      /* receiver.rnn.bias_hh     (3Hr)     */
+    MMG_P_REC_WH_W,         /* receiver.w_h.weight      (Hr, Hr)   model.py:258 */
+    MMG_P_REC_WH_B,         /* receiver.w_h.bias        (Hr)      */
+    MMG_P_REC_WD_W,         /* receiver.w_d.weight      (Hr, WV)   model.py:259 (no bias) */
+    MMG_P_REC_W_W,          /* receiver.w.weight        (M, Hr)    model.py:260 */
+    MMG_P_REC_W_B,          /* receiver.w.bias          (M)       */
+    MMG_P_REC_Y1_W,         /* receiver.y1.weight       (Hr, Hr+WV) columns [h_z ; desc]  model.py:262,548 */
+    MMG_P_REC_Y1_B,         /* receiver.y1.bias         (Hr)      */
+    MMG_P_REC_Y2_W,         /* receiver.y2.weight       (1, Hr)    model.py:263 */
+    MMG_P_REC_Y2_B,         /* receiver.y2.bias         (1)       */
+    MMG_P_REC_S_W,          /* receiver.s.weight        (1, Hr)    model.py:265 */
+    MMG_P_REC_S_B,          /* receiver.s.bias          (1)       */
+    MMG_P_SEN_CODE_BIAS,    /* sender.code_bias         (M)        model.py:69 */
+    MMG_P_SEN_IMG_W,        /* sender.image_layer.weight (Hi, F)   model.py:67 */
+    MMG_P_SEN_IMG_B,        /* sender.image_layer.bias  (Hi)      */
+    MMG_P_SEN_CODE_W,       /* sender.code_layer.weight (Hi, M)    model.py:68 */
+    MMG_P_SEN_CODE_B,       /* sender.code_layer.bias   (Hi)      */
+    MMG_P_SEN_BIN_W,        /* sender.binary_layer.weight (M, Hi)  model.py:76 */
+    MMG_P_SEN_BIN_B,        /* sender.binary_layer.bias (M)       */
+    MMG_P_BR_L1_W,          /* baseline_rec.linear1.weight (Hb, M+Hr) columns [z ; h_z]  model.py:492,842 */
+    MMG_P_BR_L1_B,          /* baseline_rec.linear1.bias   (Hb)   */
+    MMG_P_BR_L2_W,          /* baseline_rec.linear2.weight (1, Hb) */
+    MMG_P_BR_L2_B,          /* baseline_rec.linear2.bias   (1)    */
+    MMG_P_BS_L1_W,          /* baseline_sen.linear1.weight (Hb, Hi+M) columns [h_x ; z_r]  model.py:492,835 */
+    MMG_P_BS_L1_B,          /* baseline_sen.linear1.bias   (Hb)   */
+    MMG_P_BS_L2_W,          /* baseline_sen.linear2.weight (1, Hb) */
+    MMG_P_BS_L2_B,          /* baseline_sen.linear2.bias   (1)    */
+    MMG_P_COUNT
+};
+enum { MMG_SEG_RECEIVER = 0, MMG_SEG_SENDER = 1, MMG_SEG_BASELINE_REC = 2, MMG_SEG_BASELINE_SEN = 3, MMG_SEG_COUNT = 4 };
+
+typedef struct mmg_param_layout {
+    int64_t offset[MMG_P_COUNT];     /* in floats from the start of the flat buffer */
+    int32_t rows[MMG_P_COUNT];
+    int32_t cols[MMG_P_COUNT];       /* 1 for vectors */
+    int32_t segment[MMG_P_COUNT];    /* MMG_SEG_* */
+    int64_t seg_begin[MMG_SEG_COUNT + 1];
+    int64_t total;                   /* floats, multiple of 4 */
+} mmg_param_layout;
+
+/* ---- workspace layout -------------------------------------------------------------------------------
+ * One caller-provided device buffer holds the per-iteration outputs (what `exchange()` returns,
+ * model.py:872-876), the activations saved for the backward pass and all scratch.  Offsets in BYTES.
+ * R = max_exchange * batch rows, ordered step-major: row = t * batch + b. */
+typedef struct mmg_workspace_layout {
+    int64_t total_bytes;
+    /* outputs of exchange(): fp32 unless noted */
+    int64_t sen_feats;   /* (T,B,M)   z: sender messages {0,1} or raw scores (continuous)   model.py:855 */
+    int64_t sen_probs;   /* (T,B,M)   model.py:856 (unused when !use_binary) */
+    int64_t rec_feats;   /* (T+1,B,M) slot 0 = first_rec fill (model.py:786); rec_feats[t] = slot t+1  model.py:857 */
+    int64_t rec_probs;   /* (T,B,M)   model.py:858 */
+    int64_t stop_feat;   /* (T,B)     model.py:853 */
+    int64_t stop_prob;   /* (T,B)     model.py:854 */
+    int64_t y;           /* (T,B,D)   model.py:859 */
+    int64_t stop_mask;   /* uint8 (T+1,B) raw chain min(prev, s) with row 0 = 1 (model.py:775,852)        */
+    int64_t bs;          /* (T,B)     baseline_sen scores  model.py:863 */
+    int64_t br;          /* (T,B)     baseline_rec scores  model.py:862 */
+    int64_t h_x;         /* (B,Hi)    sender.h_x           model.py:195 */
+    int64_t h_z;         /* (T+1,B,Hr) slot 0 = initial state (zeros or caller state); h_z after step t = slot t+1 */
+    int64_t h_w;         /* (T,B,Hr)  receiver.h_w         model.py:452 */
+    /* per-iteration results */
+    int64_t losses;      /* float[MMG_LOSS_COUNT] */
+    int64_t ystep;       /* int32 (B) step at which each example's prediction is read (model.py:893-896) */
+    int64_t outp;        /* (B,D) selected prediction scores (get_rec_outp) */
+    int64_t logs;        /* (B)   per-example log-likelihood (model.py:1274) */
+    int64_t argmax;      /* int32 (B) model.py:1268 */
+    int64_t stats;       /* double[stats_count]: batch statistics that a data-parallel run all-reduces (sum) */
+    int64_t stats_count;
+    int64_t grad_norms;  /* float[4] pre-clip global L2 norm per module (clip_grad_norm's return value) */
+    /* upstream gradients dLoss/d(output) consumed by mmg_backward (written by mmg_loss or by the caller) */
+    int64_t g_sen_probs; /* (T,B,M) */
+    int64_t g_rec_probs; /* (T,B,M) */
+    int64_t g_stop_prob; /* (T,B)   */
+    int64_t g_outp;      /* (B,D)   gradient w.r.t. y[ystep[b], b, :] */
+    int64_t g_bs;        /* (T,B)   */
+    int64_t g_br;        /* (T,B)   */
+    int64_t rng_state;   /* uint64[2]: {seed, iteration counter} of the on-device Philox sampler */
+} mmg_workspace_layout;
+
+enum {
+    MMG_LOSS_NLL = 0,        /* nll_loss         model.py:1271 */
+    MMG_LOSS_REC,            /* loss_rec         model.py:1296-1300 */
+    MMG_LOSS_SEN,            /* loss_sen         model.py:1301 */
+    MMG_LOSS_BAS_REC,        /* loss_bas_rec     model.py:1293 */
+    MMG_LOSS_BAS_SEN,        /* loss_bas_sen     model.py:1294 */
+    MMG_LOSS_BINARY_S,       /* loss_binary_s    model.py:1279 */
+    MMG_LOSS_BINARY_REC,     /* loss_binary_rec  model.py:1285 */
+    MMG_LOSS_BINARY_SEN,     /* loss_binary_sen  model.py:1291 */
+    MMG_LOSS_TOPK_CORRECT,   /* number of rows (this rank) whose target is in the top-k (model.py:1333-1338) */
+    MMG_LOSS_ACTIVE_STEPS,   /* T' = number of exchange steps the reference would have executed (model.py:866) */
+    MMG_LOSS_COUNT = 16
+};
+
+/* Inputs of one exchange.  `d_u_*` are optional float64 uniforms in the reference's draw order
+ * (sender (T,B,M) model.py:227, stop (T,B) model.py:420, receiver (T,B,M) model.py:460);
+ * when NULL, training draws come from the on-device Philox stream seeded through `rng_state`. */
+typedef struct mmg_inputs {
+    const float* d_x;          /* (B,F)  image features       exchange_args["data"]   model.py:761 */
+    const float* d_desc;       /* (D,WV) class descriptions   exchange_args["desc"]   model.py:764 */
+    const int64_t* d_target;   /* (B)    class labels         exchange_args["target"] model.py:763 (may be NULL for forward) */
+    const double* d_u_sen;
+    const double* d_u_stop;
+    const double* d_u_rec;
+    const float* d_corrupt_mask; /* (M) 0/1, eval-time bit flips (model.py:814-820) or NULL */
+    const float* d_h0;           /* (B,Hr) initial receiver state or NULL (zeros, model.py:336-337) */
+    int32_t top_k;               /* FLAGS.top_k_train */
+    int32_t train;               /* exchange_args["train"] model.py:767 */
+} mmg_inputs;
+
+int mmg_abi_version(void);
+const char* mmg_last_error(void);
+/* Number of CUDA devices visible; <0 on error.  The library refuses to run without one. */
+int mmg_device_count(void);
+
+/* Validate `cfg` and fill the parameter layout.  Replaces the shape bookkeeping of Sender/Receiver/Baseline
+ * .__init__ (model.py:53-88, 245-273, 484-494). */
+int mmg_param_layout_get(const mmg_config* cfg, mmg_param_layout* out);
+int mmg_workspace_layout_get(const mmg_config* cfg, mmg_workspace_layout* out);
+
+/* One-time initialisation of a workspace (zeroes it, seeds the sampler, writes the launch plans). */
+int mmg_workspace_init(const mmg_config* cfg, void* d_workspace, uint64_t seed, void* stream);
+
+/* Forward conversation: replaces exchange() (model.py:725-876) including Sender.forward (195-238),
+ * Receiver.forward (333-342,412-477), both Baseline.forward calls (496-516, train only), build_inp (519-551)
+ * and the stop-mask chain.  Runs all `max_exchange` steps; rows that the reference would have skipped after an
+ * early break (model.py:866) are masked.  Outputs land in the workspace. */
+int mmg_exchange_forward(const mmg_config* cfg, const float* d_params, const mmg_inputs* in,
+                         void* d_workspace, void* stream);
+
+/* Losses and their gradients w.r.t. the exchange outputs: replaces get_rec_outp (879-904), NLL +
+ * loglikelihood (1264-1275, 571-577), multistep_loss_binary x3 / calculate_loss_binary (907-968),
+ * multistep_loss_bas x2 (971-988), the mask wiring (1248-1262), loss assembly (1296-1305) and top-k accuracy
+ * (1333-1338).  phase 0: per-rank batch statistics -> workspace.stats (all-reduce them across ranks when
+ * batch_global > batch); phase 1: loss values + upstream gradients.  phase -1 runs both. */
+int mmg_loss(const mmg_config* cfg, const float* d_params, const mmg_inputs* in, void* d_workspace, int phase,
+             void* stream);
+
+/* Backward through both agents and both baselines given the upstream gradients in the workspace: replaces
+ * the four loss.backward() calls (model.py:1309,1316,1322,1328).  Writes the flat gradient buffer `d_grads`
+ * (same layout as the parameters; fully overwritten). */
+int mmg_backward(const mmg_config* cfg, const float* d_params, const mmg_inputs* in, void* d_workspace,
+                 float* d_grads, void* stream);
+
+/* Data-parallel helper: recompute the per-module sums of squares of `d_grads` after the ranks have all-reduced it
+ * (mmg_backward already leaves them in the workspace for the single-GPU case). */
+int mmg_grad_norm(const mmg_config* cfg, float* d_grads, void* d_workspace, void* stream);
+
+/* Per-module global-norm clip + optimizer step: replaces 4x clip_grad_norm(params, 1.) + optimizer.step()
+ * (model.py:1310-1311,1317-1318,1323-1324,1329-1330).  `d_state1` = RMSprop square_avg / Adam exp_avg_sq,
+ * `d_state2` = Adam exp_avg (may be NULL otherwise), `step` = 1-based update count (Adam bias correction).
+ * `grad_scale` multiplies gradients first (1/world for averaged all-reduce; 1 otherwise).
+ * Modules not trained by the flags (sender + baselines when !use_binary, model.py:1313) are left untouched. */
+int mmg_clip_update(const mmg_config* cfg, float* d_params, float* d_grads, float* d_state1, float* d_state2,
+                    int64_t step, float grad_scale, void* d_workspace, void* stream);
+
+/* Whole training iteration on device-resident inputs = forward + loss + backward + clip_update
+ * (model.py:1240-1339).  Single-GPU convenience used by the fused `train_step`. */
+int mmg_train_step(const mmg_config* cfg, float* d_params, float* d_grads, float* d_state1, float* d_state2,
+                   int64_t step, const mmg_inputs* in, void* d_workspace, void* stream);
+
+/* End-to-end variant with HOST buffers: copies x (B,F) / target (B) [/ desc (D,WV) when h_desc != NULL] from
+ * pinned host memory into the caller's device staging buffers, runs mmg_train_step and copies the
+ * MMG_LOSS_COUNT loss floats back to `h_losses`.  All asynchronous on `stream`; the caller synchronises. */
+int mmg_train_step_host(const mmg_config* cfg, float* d_params, float* d_grads, float* d_state1, float* d_state2,
+                        int64_t step, const float* h_x, const int64_t* h_target, const float* h_desc,
+                        float* d_x_stage, int64_t* d_target_stage, float* d_desc_stage, const mmg_inputs* in,
+                        void* d_workspace, float* h_losses, void* stream);
+
+/* Number of kernels the last call of each entry point enqueued (for launch accounting). */
+int mmg_launch_count(void);
+void mmg_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMG_B200_H_ */

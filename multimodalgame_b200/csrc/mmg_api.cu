@@ -1,0 +1,581 @@
+// Host side of the C-ABI (include/mmg_b200.h): layouts, argument validation, launch sequences.
+// No allocation, no host synchronisation (except mmg_device_count); every sequence is CUDA-graph capturable.
+#include "mmg_pre.cuh"
+#include "mmg_exchange_fwd.cuh"
+#include "mmg_exchange_bwd.cuh"
+#include "mmg_loss.cuh"
+#include "mmg_update.cuh"
+
+#include <stdio.h>
+#include <stdarg.h>
+
+namespace mmg {
+namespace host {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_launches = 0;
+void count_launch() { ++g_launches; }
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#ifndef MMG_CPU_EMU
+static int check_cuda(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(MMG_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return MMG_OK;
+}
+static const int kMaxSmem = 227 * 1024;
+#else
+static int check_cuda(const char*) { return MMG_OK; }
+static const int kMaxSmem = 227 * 1024;
+#endif
+
+static int validate(const mmg_config* c) {
+    if (c == nullptr) return fail(MMG_ERR_INVALID, "null config");
+    if (c->batch < 1 || c->batch_global < c->batch) return fail(MMG_ERR_INVALID, "batch=%d batch_global=%d", c->batch, c->batch_global);
+    if (c->img_feat_dim < 1 || c->img_h_dim < 1 || c->msg_dim < 1 || c->rec_hidden < 1 || c->n_classes < 1 ||
+        c->wv_dim < 1 || c->baseline_hid < 1 || c->max_exchange < 1)
+        return fail(MMG_ERR_INVALID, "all dimensions must be >= 1");
+    if (c->rec_hidden > 256) return fail(MMG_ERR_UNSUPPORTED, "rec_hidden=%d > 256 not supported by the fused path", c->rec_hidden);
+    if (c->msg_dim > 256) return fail(MMG_ERR_UNSUPPORTED, "msg_dim=%d > 256 not supported by the fused path", c->msg_dim);
+    if (c->img_h_dim > 2 * kChunk * kLd) return fail(MMG_ERR_UNSUPPORTED, "img_h_dim=%d too large", c->img_h_dim);
+    if (c->optim_type < 0 || c->optim_type > 2) return fail(MMG_ERR_INVALID, "optim_type=%d", c->optim_type);
+    if ((long long)c->max_exchange * c->batch > (1ll << 24)) return fail(MMG_ERR_UNSUPPORTED, "T*B too large");
+    return MMG_OK;
+}
+
+static void param_layout(const Dims& d, mmg_param_layout* L) {
+    const int Hr = d.Hr, M = d.M, WV = d.WV, Hi = d.Hi, F = d.F, Hb = d.Hb;
+    struct E { int id, rows, cols, seg; };
+    const E tab[MMG_P_COUNT] = {
+        {MMG_P_REC_RNN_WIH, 3 * Hr, M, 0}, {MMG_P_REC_RNN_WHH, 3 * Hr, Hr, 0}, {MMG_P_REC_RNN_BIH, 3 * Hr, 1, 0},
+        {MMG_P_REC_RNN_BHH, 3 * Hr, 1, 0}, {MMG_P_REC_WH_W, Hr, Hr, 0}, {MMG_P_REC_WH_B, Hr, 1, 0},
+        {MMG_P_REC_WD_W, Hr, WV, 0}, {MMG_P_REC_W_W, M, Hr, 0}, {MMG_P_REC_W_B, M, 1, 0},
+        {MMG_P_REC_Y1_W, Hr, Hr + WV, 0}, {MMG_P_REC_Y1_B, Hr, 1, 0}, {MMG_P_REC_Y2_W, 1, Hr, 0},
+        {MMG_P_REC_Y2_B, 1, 1, 0}, {MMG_P_REC_S_W, 1, Hr, 0}, {MMG_P_REC_S_B, 1, 1, 0},
+        {MMG_P_SEN_CODE_BIAS, M, 1, 1}, {MMG_P_SEN_IMG_W, Hi, F, 1}, {MMG_P_SEN_IMG_B, Hi, 1, 1},
+        {MMG_P_SEN_CODE_W, Hi, M, 1}, {MMG_P_SEN_CODE_B, Hi, 1, 1}, {MMG_P_SEN_BIN_W, M, Hi, 1},
+        {MMG_P_SEN_BIN_B, M, 1, 1},
+        {MMG_P_BR_L1_W, Hb, M + Hr, 2}, {MMG_P_BR_L1_B, Hb, 1, 2}, {MMG_P_BR_L2_W, 1, Hb, 2}, {MMG_P_BR_L2_B, 1, 1, 2},
+        {MMG_P_BS_L1_W, Hb, Hi + M, 3}, {MMG_P_BS_L1_B, Hb, 1, 3}, {MMG_P_BS_L2_W, 1, Hb, 3}, {MMG_P_BS_L2_B, 1, 1, 3}};
+    int64_t off = 0;
+    int cur_seg = -1;
+    for (int i = 0; i < MMG_P_COUNT; ++i) {
+        const E& e = tab[i];
+        if (e.seg != cur_seg) { cur_seg = e.seg; L->seg_begin[cur_seg] = off; }
+        L->offset[e.id] = off;
+        L->rows[e.id] = e.rows; L->cols[e.id] = e.cols; L->segment[e.id] = e.seg;
+        off += round_up64((int64_t)e.rows * e.cols, 4);
+    }
+    L->seg_begin[MMG_SEG_COUNT] = off;
+    L->total = off;
+}
+
+static int64_t take(int64_t& cur, int64_t bytes) {
+    const int64_t at = cur;
+    cur += round_up64(bytes, 256);
+    return at;
+}
+
+static void ws_layout(const Dims& d, Ws* w) {
+    memset(w, 0, sizeof(*w));
+    mmg_param_layout L;
+    param_layout(d, &L);
+    const int64_t R = d.R, B = d.B, f = sizeof(float);
+    int64_t c = 0;
+    mmg_workspace_layout& p = w->pub;
+    p.sen_feats = take(c, R * d.M * f);
+    p.sen_probs = take(c, R * d.M * f);
+    p.rec_feats = take(c, (R + B) * d.M * f);
+    p.rec_probs = take(c, R * d.M * f);
+    p.stop_feat = take(c, R * f);
+    p.stop_prob = take(c, R * f);
+    p.y = take(c, R * d.D * f);
+    p.stop_mask = take(c, R + B);
+    p.bs = take(c, R * f);
+    p.br = take(c, R * f);
+    p.h_x = take(c, B * d.Hi * f);
+    p.h_z = take(c, (R + B) * d.Hr * f);
+    p.h_w = take(c, R * d.Hr * f);
+    p.losses = take(c, MMG_LOSS_COUNT * f);
+    p.ystep = take(c, B * 4);
+    p.outp = take(c, B * d.D * f);
+    p.logs = take(c, B * f);
+    p.argmax = take(c, B * 4);
+    p.stats_count = stats_count(d);
+    p.stats = take(c, p.stats_count * 8);
+    p.grad_norms = take(c, 4 * f);
+    p.g_sen_probs = take(c, R * d.M * f);
+    p.g_rec_probs = take(c, R * d.M * f);
+    p.g_stop_prob = take(c, R * f);
+    p.g_outp = take(c, B * d.D * f);
+    p.g_bs = take(c, R * f);
+    p.g_br = take(c, R * f);
+    p.rng_state = take(c, 16);
+    w->code_in = take(c, R * d.M * f);
+    w->a_s = take(c, R * d.Hi * f);
+    w->gates = take(c, R * 4 * d.Hr * f);
+    w->y1h = take(c, R * d.Hr * f);
+    w->q = take(c, R * d.D * f);
+    w->wd = take(c, R * d.WV * f);
+    w->rowstat = take(c, 6 * R * f);
+    w->ntb = cdiv(d.Hb, kTile);
+    w->h1s = take(c, R * d.Hb * f);
+    w->h1r = take(c, R * d.Hb * f);
+    w->bs_part = take(c, R * w->ntb * f);
+    w->br_part = take(c, R * w->ntb * f);
+    int hs = d.F / 128;
+    if (hs < 1) hs = 1;
+    if (hs > kHxSplitMax) hs = kHxSplitMax;
+    w->hx_split = hs;
+    w->hx_part = take(c, (int64_t)hs * B * d.Hi * f);
+    w->fwd_image = take(c, (int64_t)make_fwd_image(d).total * f);
+    w->bwd_image = take(c, (int64_t)make_bwd_image(d).total * f);
+    w->d_lz = take(c, R * d.M * f);
+    w->d_as = take(c, R * d.Hi * f);
+    w->dhx = take(c, B * d.Hi * f);
+    w->dgi = take(c, R * d.G3 * f);
+    w->dgh = take(c, R * d.G3 * f);
+    w->d_lw = take(c, R * d.M * f);
+    w->d_hw = take(c, R * d.Hr * f);
+    w->d_ls = take(c, R * f);
+    w->g_h = take(c, B * d.Hr * f);
+    w->hsel = take(c, B * d.Hr * f);
+    w->dy1 = take(c, B * d.D * d.Hr * f);
+    w->dw2p = take(c, B * d.Hr * f);
+    int gs = (int)(R / 160);
+    if (gs < 1) gs = 1;
+    if (gs > kWgradSplitMax) gs = kWgradSplitMax;
+    w->wgrad_split = gs;
+    w->slabs = take(c, (int64_t)gs * L.total * f);
+    w->norm_part = take(c, 4 * kNormCtas * f);
+    w->opt_counters = take(c, 4 * 8);
+    p.total_bytes = c;
+}
+
+static WsPtrs resolve(const Ws& w, void* base) {
+    char* b = (char*)base;
+    WsPtrs r;
+    const mmg_workspace_layout& p = w.pub;
+#define F_(name) r.name = (float*)(b + p.name)
+    F_(sen_feats); F_(sen_probs); F_(rec_feats); F_(rec_probs); F_(stop_feat); F_(stop_prob); F_(y); F_(bs); F_(br);
+    F_(h_x); F_(h_z); F_(h_w); F_(losses); F_(outp); F_(logs); F_(grad_norms);
+    F_(g_sen_probs); F_(g_rec_probs); F_(g_stop_prob); F_(g_outp); F_(g_bs); F_(g_br);
+#undef F_
+    r.stop_mask = (unsigned char*)(b + p.stop_mask);
+    r.ystep = (int*)(b + p.ystep);
+    r.argmax = (int*)(b + p.argmax);
+    r.stats = (double*)(b + p.stats);
+    r.rng_state = (unsigned long long*)(b + p.rng_state);
+#define G_(name) r.name = (float*)(b + w.name)
+    G_(code_in); G_(a_s); G_(gates); G_(y1h); G_(q); G_(wd); G_(rowstat); G_(h1s); G_(h1r); G_(bs_part); G_(br_part);
+    G_(hx_part); G_(fwd_image); G_(bwd_image); G_(d_lz); G_(d_as); G_(dhx); G_(dgi); G_(dgh); G_(d_lw); G_(d_hw);
+    G_(d_ls); G_(g_h); G_(hsel); G_(dy1); G_(dw2p); G_(slabs); G_(norm_part);
+#undef G_
+    r.opt_counters = (long long*)(b + w.opt_counters);
+    r.hx_split = w.hx_split; r.wgrad_split = w.wgrad_split; r.ntb = w.ntb;
+    return r;
+}
+
+static ParamPtrs param_ptrs(const mmg_param_layout& L, const float* base) {
+    ParamPtrs P;
+    for (int i = 0; i < MMG_P_COUNT; ++i) P.p[i] = base + L.offset[i];
+    return P;
+}
+
+static ExchangeInputs resolve_inputs(const mmg_inputs* in) {
+    ExchangeInputs e;
+    e.x = in->d_x; e.desc = in->d_desc; e.target = (const long long*)in->d_target;
+    e.u_sen = in->d_u_sen; e.u_stop = in->d_u_stop; e.u_rec = in->d_u_rec;
+    e.corrupt_mask = in->d_corrupt_mask; e.h0 = in->d_h0; e.top_k = in->top_k; e.train = in->train;
+    return e;
+}
+
+struct Plan { int BT; int sender_smem; int fwd_smem_bytes; int bwd_smem_bytes; };
+
+static int choose_bt(int B) {
+    if (B <= 148) return 1;
+    if (B <= 2 * 148) return 2;
+    if (B <= 4 * 148) return 4;
+    return 8;
+}
+
+static int make_plan(const Dims& d, Plan* pl) {
+    const FwdImage fi = make_fwd_image(d);
+    const BwdImage bi = make_bwd_image(d);
+    pl->BT = choose_bt(d.B);
+    for (;;) {
+        const int st = fwd_state_floats(d, pl->BT);
+        const int full = (fi.total + st) * 4, recv_only = (fi.total - fi.sender_end + st) * 4;
+        int bw_rec = (bi.total - bi.sender_end + bwd_rec_state_floats(d, pl->BT)) * 4;
+        int bw_sen = (bi.sender_end + bwd_sen_state_floats(d, pl->BT)) * 4;
+        const int bw = bw_rec > bw_sen ? bw_rec : bw_sen;
+        if (recv_only <= kMaxSmem && bw <= kMaxSmem) {
+            pl->sender_smem = full <= kMaxSmem ? 1 : 0;
+            pl->fwd_smem_bytes = pl->sender_smem ? full : recv_only;
+            pl->bwd_smem_bytes = bw;
+            return MMG_OK;
+        }
+        if (pl->BT == 1) break;
+        pl->BT /= 2;
+    }
+    return fail(MMG_ERR_UNSUPPORTED, "receiver weights (%d floats) do not fit in shared memory", fi.total - fi.sender_end);
+}
+
+#ifndef MMG_CPU_EMU
+template <typename K>
+static int set_smem(K kernel, int bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return fail(MMG_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", bytes, cudaGetErrorString(e));
+    return MMG_OK;
+}
+#else
+template <typename K>
+static int set_smem(K, int) { return MMG_OK; }
+#endif
+
+template <int BT>
+static int launch_fwd(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const float* b_img, const Plan& pl,
+                      cudaStream_t st) {
+    int rc = set_smem(k_exchange_fwd<BT>, pl.fwd_smem_bytes);
+    if (rc) return rc;
+    MMG_LAUNCH(k_exchange_fwd<BT>, cdiv(d.B, BT), kLoopThreads, pl.fwd_smem_bytes, st, d, W, in, b_img, pl.sender_smem, 0);
+    return check_cuda("k_exchange_fwd");
+}
+template <int BT>
+static int launch_bwd(const Dims& d, const WsPtrs& W, const Plan& pl, cudaStream_t st) {
+    int rc = set_smem(k_exchange_bwd<BT>, pl.bwd_smem_bytes);
+    if (rc) return rc;
+    const int n_rec = cdiv(d.B, BT), n_sen = d.use_binary ? cdiv(d.B, BT) : 0;
+    MMG_LAUNCH(k_exchange_bwd<BT>, n_rec + n_sen, kLoopThreads, pl.bwd_smem_bytes, st, d, W, n_rec);
+    return check_cuda("k_exchange_bwd");
+}
+
+static void add_problem(WgTable& t, const Operand& A, const Operand& B, int M, int N, int K, long long c_off, int ldc,
+                        long long bias_off, int kind) {
+    WgProblem& p = t.p[t.count++];
+    p.A = A; p.B = B; p.M = M; p.N = N; p.K = K; p.c_off = c_off; p.ldc = ldc; p.bias_off = bias_off; p.kind = kind;
+    p.ntm = cdiv(M, kTile);
+    p.ntn = kind == WG_GEMM ? cdiv(N, kTile) : 1;
+    p.tile_begin = t.total_tiles;
+    t.total_tiles += p.ntm * p.ntn * t.nsplit;
+}
+
+static Operand km(const float* p, int ld) { return Operand{p, nullptr, nullptr, nullptr, ld, 0, 1, 0, 0, OP_PLAIN}; }
+
+static void build_wgrad_table(const Dims& d, const mmg_param_layout& L, const ParamPtrs& P, const WsPtrs& W,
+                              const ExchangeInputs& in, WgTable* t) {
+    t->count = 0; t->total_tiles = 0; t->nsplit = W.wgrad_split; t->slab_stride = L.total;
+    const int R = d.R, B = d.B, Hr = d.Hr, M = d.M, Hi = d.Hi;
+    const float* h_after = W.h_z + (size_t)B * Hr;       // h_z after step t, row-aligned with (t, b)
+    // receiver
+    add_problem(*t, km(W.dgi, d.G3), km(W.sen_feats, M), d.G3, M, R, L.offset[MMG_P_REC_RNN_WIH], M, L.offset[MMG_P_REC_RNN_BIH], WG_GEMM);
+    add_problem(*t, km(W.dgh, d.G3), km(W.h_z, Hr), d.G3, Hr, R, L.offset[MMG_P_REC_RNN_WHH], Hr, L.offset[MMG_P_REC_RNN_BHH], WG_GEMM);
+    add_problem(*t, km(W.d_lw, M), km(W.h_w, Hr), M, Hr, R, L.offset[MMG_P_REC_W_W], Hr, L.offset[MMG_P_REC_W_B], WG_GEMM);
+    add_problem(*t, km(W.d_hw, Hr), km(h_after, Hr), Hr, Hr, R, L.offset[MMG_P_REC_WH_W], Hr, L.offset[MMG_P_REC_WH_B], WG_GEMM);
+    add_problem(*t, km(W.d_hw, Hr), km(W.wd, d.WV), Hr, d.WV, R, L.offset[MMG_P_REC_WD_W], d.WV, -1, WG_GEMM);
+    add_problem(*t, km(W.d_ls, 1), km(h_after, Hr), 1, Hr, R, L.offset[MMG_P_REC_S_W], Hr, L.offset[MMG_P_REC_S_B], WG_GEMM);
+    add_problem(*t, km(W.g_h, Hr), km(W.hsel, Hr), Hr, Hr, B, L.offset[MMG_P_REC_Y1_W], Hr + d.WV, -1, WG_GEMM);
+    {
+        Operand bd = km(in.desc, d.WV);
+        bd.mod = d.D;                                        // row (b, d) -> desc[d]
+        add_problem(*t, km(W.dy1, Hr), bd, Hr, d.WV, B * d.D, L.offset[MMG_P_REC_Y1_W] + Hr, Hr + d.WV, L.offset[MMG_P_REC_Y1_B], WG_GEMM);
+    }
+    add_problem(*t, km(W.dw2p, Hr), km(W.dw2p, Hr), Hr, 1, B, L.offset[MMG_P_REC_Y2_W], 1, -1, WG_COLSUM);
+    add_problem(*t, km(W.g_outp, 1), km(W.g_outp, 1), 1, 1, B * d.D, L.offset[MMG_P_REC_Y2_B], 1, -1, WG_COLSUM);
+    if (d.use_binary) {
+        // sender
+        add_problem(*t, km(W.d_lz, M), km(W.a_s, Hi), M, Hi, R, L.offset[MMG_P_SEN_BIN_W], Hi, L.offset[MMG_P_SEN_BIN_B], WG_GEMM);
+        add_problem(*t, km(W.d_as, Hi), km(W.code_in, M), Hi, M, R, L.offset[MMG_P_SEN_CODE_W], M, L.offset[MMG_P_SEN_CODE_B], WG_GEMM);
+        add_problem(*t, km(W.d_as, Hi), km(W.d_as, Hi), M, 1, 1, L.offset[MMG_P_SEN_CODE_BIAS], 1, -1, WG_CODEBIAS);
+        add_problem(*t, km(W.dhx, Hi), km(in.x, d.F), Hi, d.F, B, L.offset[MMG_P_SEN_IMG_W], d.F, L.offset[MMG_P_SEN_IMG_B], WG_GEMM);
+        // baseline_sen: d pre = g_bs * linear2.weight * (hidden > 0); rows [h_x[b] ; z_r[t,b]]
+        {
+            Operand a = km(W.h1s, d.Hb);
+            a.kind = OP_RELUGRAD; a.g = W.g_bs; a.w2 = P.p[MMG_P_BS_L2_W];
+            Operand b = km(W.h_x, Hi);
+            b.mod = B; b.p2 = W.rec_feats; b.ld2 = M; b.split = Hi;
+            add_problem(*t, a, b, d.Hb, Hi + M, R, L.offset[MMG_P_BS_L1_W], Hi + M, L.offset[MMG_P_BS_L1_B], WG_GEMM);
+            add_problem(*t, km(W.g_bs, 1), km(W.h1s, d.Hb), 1, d.Hb, R, L.offset[MMG_P_BS_L2_W], d.Hb, L.offset[MMG_P_BS_L2_B], WG_GEMM);
+        }
+        // baseline_rec: rows [z[t,b] ; h_z after step t]
+        {
+            Operand a = km(W.h1r, d.Hb);
+            a.kind = OP_RELUGRAD; a.g = W.g_br; a.w2 = P.p[MMG_P_BR_L2_W];
+            Operand b = km(W.sen_feats, M);
+            b.p2 = h_after; b.ld2 = Hr; b.split = M;
+            add_problem(*t, a, b, d.Hb, M + Hr, R, L.offset[MMG_P_BR_L1_W], M + Hr, L.offset[MMG_P_BR_L1_B], WG_GEMM);
+            add_problem(*t, km(W.g_br, 1), km(W.h1r, d.Hb), 1, d.Hb, R, L.offset[MMG_P_BR_L2_W], d.Hb, L.offset[MMG_P_BR_L2_B], WG_GEMM);
+        }
+    }
+}
+
+static SegInfo seg_info(const mmg_param_layout& L, const Dims& d) {
+    SegInfo s;
+    for (int i = 0; i < 5; ++i) s.begin[i] = L.seg_begin[i];
+    s.trained[0] = 1;
+    s.trained[1] = s.trained[2] = s.trained[3] = d.use_binary ? 1 : 0;   // model.py:1313
+    // tensors that receive no gradient at all are skipped by torch.optim (their .grad stays None):
+    //  - the receiver message head (w_h, w_d, w) when no receiver-message loss exists this iteration
+    //    (`len(rec_feats[:-1]) == 0`, model.py:1284-1289: one-step conversations);
+    //  - the STOP head (s) when the exchange length is fixed (loss_binary_s not built, model.py:1278-1280,1299).
+    s.whead_begin = L.offset[MMG_P_REC_WH_W];
+    s.whead_end = L.offset[MMG_P_REC_W_B] + round_up64(L.rows[MMG_P_REC_W_B], 4);
+    s.shead_begin = L.offset[MMG_P_REC_S_W];
+    s.shead_end = L.offset[MMG_P_REC_S_B] + 4;
+    s.shead_active = d.fixed ? 0 : 1;
+    s.whead_stat = stat_idx(d, 1, 0, 0);
+    return s;
+}
+
+}  // namespace host
+}  // namespace mmg
+
+using namespace mmg;
+using namespace mmg::host;
+
+extern "C" {
+
+int mmg_abi_version(void) { return MMG_ABI_VERSION; }
+const char* mmg_last_error(void) { return g_err; }
+int mmg_launch_count(void) { return g_launches; }
+void mmg_launch_count_reset(void) { g_launches = 0; }
+
+int mmg_device_count(void) {
+#ifndef MMG_CPU_EMU
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { fail(MMG_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); return MMG_ERR_NO_DEVICE; }
+    return n;
+#else
+    return 1;
+#endif
+}
+
+int mmg_param_layout_get(const mmg_config* cfg, mmg_param_layout* out) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!out) return fail(MMG_ERR_INVALID, "null output");
+    param_layout(make_dims(*cfg), out);
+    return MMG_OK;
+}
+
+int mmg_workspace_layout_get(const mmg_config* cfg, mmg_workspace_layout* out) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!out) return fail(MMG_ERR_INVALID, "null output");
+    Ws w;
+    ws_layout(make_dims(*cfg), &w);
+    *out = w.pub;
+    return MMG_OK;
+}
+
+int mmg_workspace_init(const mmg_config* cfg, void* d_workspace, uint64_t seed, void* stream) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!d_workspace) return fail(MMG_ERR_INVALID, "null workspace");
+    const Dims d = make_dims(*cfg);
+    Ws w;
+    ws_layout(d, &w);
+    cudaStream_t st = (cudaStream_t)stream;
+#ifndef MMG_CPU_EMU
+    if (cudaMemsetAsync(d_workspace, 0, (size_t)w.pub.total_bytes, st) != cudaSuccess) return check_cuda("cudaMemsetAsync");
+#else
+    memset(d_workspace, 0, (size_t)w.pub.total_bytes);
+#endif
+    WsPtrs W = resolve(w, d_workspace);
+    MMG_LAUNCH(k_init_rng, 1, 32, 0, st, W.rng_state, (unsigned long long)seed);
+    return check_cuda("k_init_rng");
+}
+
+int mmg_exchange_forward(const mmg_config* cfg, const float* d_params, const mmg_inputs* in, void* d_workspace,
+                         void* stream) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!d_params || !in || !d_workspace || !in->d_x || !in->d_desc) return fail(MMG_ERR_INVALID, "null pointer argument");
+    const Dims d = make_dims(*cfg);
+    Plan pl;
+    if ((rc = make_plan(d, &pl))) return rc;
+    mmg_param_layout L;
+    param_layout(d, &L);
+    Ws w;
+    ws_layout(d, &w);
+    const WsPtrs W = resolve(w, d_workspace);
+    const ParamPtrs P = param_ptrs(L, d_params);
+    const ExchangeInputs ei = resolve_inputs(in);
+    cudaStream_t st = (cudaStream_t)stream;
+    // K_pre
+    const int n_hx = cdiv(d.B, kTile) * cdiv(d.Hi, kTile) * W.hx_split;
+    const int hx_kslice = round_up(cdiv(d.F, W.hx_split), 4);
+    const int n_pack = 64;
+    MMG_LAUNCH(k_pre, n_hx + n_pack, kGemmThreads, 0, st, d, P, W, ei, n_hx, hx_kslice);
+    if ((rc = check_cuda("k_pre"))) return rc;
+    // K_exchange_fwd
+    const float* b_img = P.p[MMG_P_SEN_IMG_B];
+    switch (pl.BT) {
+        case 1: rc = launch_fwd<1>(d, W, ei, b_img, pl, st); break;
+        case 2: rc = launch_fwd<2>(d, W, ei, b_img, pl, st); break;
+        case 4: rc = launch_fwd<4>(d, W, ei, b_img, pl, st); break;
+        default: rc = launch_fwd<8>(d, W, ei, b_img, pl, st); break;
+    }
+    if (rc) return rc;
+    if (in->train) {
+        const int tiles = 2 * cdiv(d.R, kTile) * W.ntb;
+        MMG_LAUNCH(k_baseline_fwd, tiles, kGemmThreads, 0, st, d, P, W);
+        if ((rc = check_cuda("k_baseline_fwd"))) return rc;
+    }
+    return MMG_OK;
+}
+
+int mmg_loss(const mmg_config* cfg, const float* d_params, const mmg_inputs* in, void* d_workspace, int phase,
+             void* stream) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!d_params || !in || !d_workspace || !in->d_target) return fail(MMG_ERR_INVALID, "null pointer argument");
+    const Dims d = make_dims(*cfg);
+    mmg_param_layout L;
+    param_layout(d, &L);
+    Ws w;
+    ws_layout(d, &w);
+    const WsPtrs W = resolve(w, d_workspace);
+    const ParamPtrs P = param_ptrs(L, d_params);
+    const ExchangeInputs ei = resolve_inputs(in);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (phase <= 0) {
+        MMG_LAUNCH(k_stats, 1, kStatsThreads, 0, st, d, P, W, ei);
+        if ((rc = check_cuda("k_stats"))) return rc;
+    }
+    if (phase != 0) {
+        int ctas = cdiv(d.R, kLossThreads / 32);
+        if (ctas > 4 * 148) ctas = 4 * 148;
+        const int smem = 3 * d.T * (int)sizeof(LossCoef) + 16;
+        MMG_LAUNCH(k_lossgrad, ctas, kLossThreads, smem, st, d, *cfg, W);
+        if ((rc = check_cuda("k_lossgrad"))) return rc;
+    }
+    return MMG_OK;
+}
+
+int mmg_backward(const mmg_config* cfg, const float* d_params, const mmg_inputs* in, void* d_workspace, float* d_grads,
+                 void* stream) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!d_params || !in || !d_workspace || !d_grads) return fail(MMG_ERR_INVALID, "null pointer argument");
+    const Dims d = make_dims(*cfg);
+    Plan pl;
+    if ((rc = make_plan(d, &pl))) return rc;
+    mmg_param_layout L;
+    param_layout(d, &L);
+    Ws w;
+    ws_layout(d, &w);
+    const WsPtrs W = resolve(w, d_workspace);
+    const ParamPtrs P = param_ptrs(L, d_params);
+    const ExchangeInputs ei = resolve_inputs(in);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (pl.BT) {
+        case 1: rc = launch_bwd<1>(d, W, pl, st); break;
+        case 2: rc = launch_bwd<2>(d, W, pl, st); break;
+        case 4: rc = launch_bwd<4>(d, W, pl, st); break;
+        default: rc = launch_bwd<8>(d, W, pl, st); break;
+    }
+    if (rc) return rc;
+    WgTable tab;
+    build_wgrad_table(d, L, P, W, ei, &tab);
+    MMG_LAUNCH(k_wgrad, tab.total_tiles, kGemmThreads, 0, st, d, tab, W.slabs, P.p[MMG_P_SEN_CODE_W],
+               P.p[MMG_P_SEN_CODE_BIAS], W.d_as);
+    if ((rc = check_cuda("k_wgrad"))) return rc;
+    const SegInfo seg = seg_info(L, d);
+    MMG_LAUNCH(k_reduce_norm, kNormCtas, kUpdThreads, 0, st, seg, W.slabs, (long long)L.total, W.wgrad_split, d_grads, 1.0f,
+               1, W.norm_part);
+    return check_cuda("k_reduce_norm");
+}
+
+int mmg_grad_norm(const mmg_config* cfg, float* d_grads, void* d_workspace, void* stream) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!d_workspace || !d_grads) return fail(MMG_ERR_INVALID, "null pointer argument");
+    const Dims d = make_dims(*cfg);
+    mmg_param_layout L;
+    param_layout(d, &L);
+    Ws w;
+    ws_layout(d, &w);
+    const WsPtrs W = resolve(w, d_workspace);
+    const SegInfo seg = seg_info(L, d);
+    MMG_LAUNCH(k_reduce_norm, kNormCtas, kUpdThreads, 0, (cudaStream_t)stream, seg, W.slabs, (long long)L.total,
+               W.wgrad_split, d_grads, 1.0f, 0, W.norm_part);
+    return check_cuda("k_reduce_norm");
+}
+
+int mmg_clip_update(const mmg_config* cfg, float* d_params, float* d_grads, float* d_state1, float* d_state2,
+                    int64_t step, float grad_scale, void* d_workspace, void* stream) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!d_params || !d_grads || !d_workspace) return fail(MMG_ERR_INVALID, "null pointer argument");
+    if (cfg->optim_type != MMG_OPT_SGD && !d_state1) return fail(MMG_ERR_INVALID, "optimizer state required");
+    if (cfg->optim_type == MMG_OPT_ADAM && !d_state2) return fail(MMG_ERR_INVALID, "Adam needs d_state2");
+    if (grad_scale != 1.0f) return fail(MMG_ERR_UNSUPPORTED, "grad_scale != 1: gradients are already normalised by batch_global");
+    const Dims d = make_dims(*cfg);
+    mmg_param_layout L;
+    param_layout(d, &L);
+    Ws w;
+    ws_layout(d, &w);
+    const WsPtrs W = resolve(w, d_workspace);
+    const SegInfo seg = seg_info(L, d);
+    OptHyper hp;
+    hp.optim = cfg->optim_type; hp.lr = cfg->learning_rate; hp.max_norm = cfg->max_norm; hp.step = step;
+    MMG_LAUNCH(k_update, kNormCtas, kUpdThreads, 0, (cudaStream_t)stream, seg, hp, d_params, d_grads, d_state1, d_state2,
+               W.norm_part, (int)kNormCtas, W.grad_norms, W.stats, W.opt_counters);
+    return check_cuda("k_update");
+}
+
+int mmg_train_step(const mmg_config* cfg, float* d_params, float* d_grads, float* d_state1, float* d_state2,
+                   int64_t step, const mmg_inputs* in, void* d_workspace, void* stream) {
+    int rc;
+    if (!in || !in->train) return fail(MMG_ERR_INVALID, "mmg_train_step needs in->train = 1");
+    if ((rc = mmg_exchange_forward(cfg, d_params, in, d_workspace, stream))) return rc;
+    if ((rc = mmg_loss(cfg, d_params, in, d_workspace, -1, stream))) return rc;
+    if ((rc = mmg_backward(cfg, d_params, in, d_workspace, d_grads, stream))) return rc;
+    return mmg_clip_update(cfg, d_params, d_grads, d_state1, d_state2, step, 1.0f, d_workspace, stream);
+}
+
+int mmg_train_step_host(const mmg_config* cfg, float* d_params, float* d_grads, float* d_state1, float* d_state2,
+                        int64_t step, const float* h_x, const int64_t* h_target, const float* h_desc,
+                        float* d_x_stage, int64_t* d_target_stage, float* d_desc_stage, const mmg_inputs* in,
+                        void* d_workspace, float* h_losses, void* stream) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!h_x || !h_target || !d_x_stage || !d_target_stage || !in || !h_losses) return fail(MMG_ERR_INVALID, "null pointer argument");
+#ifndef MMG_CPU_EMU
+    cudaStream_t st = (cudaStream_t)stream;
+    const Dims d = make_dims(*cfg);
+    if (cudaMemcpyAsync(d_x_stage, h_x, (size_t)d.B * d.F * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return check_cuda("H2D x");
+    if (cudaMemcpyAsync(d_target_stage, h_target, (size_t)d.B * sizeof(int64_t), cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return check_cuda("H2D target");
+    if (h_desc != nullptr) {
+        if (!d_desc_stage) return fail(MMG_ERR_INVALID, "d_desc_stage required with h_desc");
+        if (cudaMemcpyAsync(d_desc_stage, h_desc, (size_t)d.D * d.WV * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess)
+            return check_cuda("H2D desc");
+    }
+    mmg_inputs dev = *in;
+    dev.d_x = d_x_stage;
+    dev.d_target = d_target_stage;
+    if (h_desc != nullptr) dev.d_desc = d_desc_stage;
+    if ((rc = mmg_train_step(cfg, d_params, d_grads, d_state1, d_state2, step, &dev, d_workspace, stream))) return rc;
+    Ws w;
+    ws_layout(d, &w);
+    if (cudaMemcpyAsync(h_losses, (char*)d_workspace + w.pub.losses, MMG_LOSS_COUNT * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        return check_cuda("D2H losses");
+    return MMG_OK;
+#else
+    (void)d_params; (void)d_grads; (void)d_state1; (void)d_state2; (void)step; (void)h_desc; (void)d_desc_stage; (void)d_workspace; (void)stream;
+    return fail(MMG_ERR_UNSUPPORTED, "host-buffer entry point is not part of the emulation build");
+#endif
+}
+
+}  // extern "C"

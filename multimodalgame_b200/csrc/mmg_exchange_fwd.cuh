@@ -1,0 +1,431 @@
+// K_exchange_fwd — the whole T-step conversation (model.py:801-867) in ONE persistent kernel.
+//
+// One CTA owns BT examples for all T steps; examples are independent in the forward pass (desc and parameters are
+// shared), so no inter-CTA communication is needed.  The kernel-layout weight image written by K_pre (~190 KB at the
+// headline configuration) is staged ONCE into shared memory by the TMA unit (cp.async.bulk + mbarrier) and reused
+// for every step: no weight byte is re-read from HBM/L2 inside the recurrence and there is no host round trip for
+// sampling (the reference does 3 D2H + 3 H2D copies per step, model.py:225-231,418-420,458-464).
+//
+// Per step:  sender   a = tanh(h_x + code_layer(w_prev));  p_z = sigmoid(binary_layer(a));  z ~ Bernoulli(p_z)
+//            receiver h' = GRU(z, h);  s_p = sigmoid(s(h'));  y[d] = y2(relu(y1h(h') + y1d[d]))   (y1 split in halves)
+//                     q = softmax(y);  h_w = tanh(w_h(h') + sum_d q_d wdd[d]);  p_w = sigmoid(w(h_w));  w ~ Bernoulli
+// Mat-vecs read "packed" weights (see mmg_layout.h) as float4, split along the reduction dimension across warps when
+// the output is narrower than the CTA, and meet in shared memory.
+#pragma once
+#include "mmg_kernels.cuh"
+
+namespace mmg {
+
+enum { kLoopThreads = 256 };
+
+struct SplitPlan { int Nr, KS; };
+MMG_HOST_DEVICE SplitPlan make_split(int N, int K4) {
+    SplitPlan s;
+    s.Nr = round_up(N, 32);
+    s.KS = kLoopThreads / s.Nr;
+    if (s.KS < 1) s.KS = 1;
+    if (s.KS > K4) s.KS = K4;
+    if (s.KS < 1) s.KS = 1;
+    return s;
+}
+
+// part[(ks * BT + bt) * Nr + n] = sum_{k4 in slice ks} W4[k4][n] . v[bt][4 k4 .. 4 k4 + 3]
+template <int BT, bool kGlobalW>
+MMG_DEVICE void split_matvec(const float* Wp, int N, int K4, const float* v, int ldv, float* part, SplitPlan sp) {
+    const float4* W4 = reinterpret_cast<const float4*>(Wp);
+    for (int idx = threadIdx.x; idx < sp.Nr * sp.KS; idx += kLoopThreads) {
+        const int n = idx % sp.Nr, ks = idx / sp.Nr;
+        if (n >= N) continue;
+        const int kb = (ks * K4) / sp.KS, ke = ((ks + 1) * K4) / sp.KS;
+        float acc[BT];
+#pragma unroll
+        for (int bt = 0; bt < BT; ++bt) acc[bt] = 0.f;
+#pragma unroll 4
+        for (int k4 = kb; k4 < ke; ++k4) {
+            const float4 w = kGlobalW ? ldg4(W4 + (size_t)k4 * N + n) : W4[(size_t)k4 * N + n];
+#pragma unroll
+            for (int bt = 0; bt < BT; ++bt) {
+                const float4 x = *reinterpret_cast<const float4*>(v + bt * ldv + 4 * k4);
+                acc[bt] = fmaf(w.x, x.x, acc[bt]);
+                acc[bt] = fmaf(w.y, x.y, acc[bt]);
+                acc[bt] = fmaf(w.z, x.z, acc[bt]);
+                acc[bt] = fmaf(w.w, x.w, acc[bt]);
+            }
+        }
+#pragma unroll
+        for (int bt = 0; bt < BT; ++bt) part[(ks * BT + bt) * sp.Nr + n] = acc[bt];
+    }
+}
+template <int BT>
+MMG_DEVICE float gather_part(const float* part, SplitPlan sp, int bt, int n) {
+    float s = 0.f;
+    for (int ks = 0; ks < sp.KS; ++ks) s += part[(ks * BT + bt) * sp.Nr + n];
+    return s;
+}
+
+// Bernoulli draw `u < p` (model.py:227): injected float64 uniform, or the on-device Philox stream.
+MMG_DEVICE float draw_bit(const double* u, size_t uidx, float p, unsigned long long seed, unsigned long long iter,
+                          unsigned stream_id, unsigned row, unsigned col) {
+    if (u != nullptr) return (u[uidx] < (double)p) ? 1.f : 0.f;
+    float r[4];
+    philox_uniform4(seed, iter, stream_id, row * 65536u + (col >> 2), r);
+    return (r[col & 3] < p) ? 1.f : 0.f;
+}
+
+MMG_HOST_DEVICE int fwd_state_floats(const Dims& d, int BT) {
+    // hx, a, win, z, pz, h, head, yv, q, hwr, partA, partB, misc
+    const int HiP = align4(d.Hi), MP = d.M4 * 4, HrP = d.Hr4 * 4;
+    int n = BT * HiP * 2 + BT * MP * 3 + BT * HrP * 2 + BT * align4(d.NH) + BT * align4(d.D) * 2;
+    int pmax = round_up(d.Hi, 32);
+    if (round_up(d.G3, 32) > pmax) pmax = round_up(d.G3, 32);
+    if (round_up(d.NH, 32) > pmax) pmax = round_up(d.NH, 32);
+    if (pmax < kLoopThreads) pmax = kLoopThreads;
+    n += 2 * BT * pmax;
+    n += 4 * BT + 8;   // sprod, active, barrier
+    return n;
+}
+
+template <int BT>
+MMG_GLOBAL void __launch_bounds__(kLoopThreads, 1)
+k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int sender_smem, int row_offset) {
+    MMG_DYN_SMEM(smem_raw);
+    float* sm = reinterpret_cast<float*>(smem_raw);
+    const FwdImage im = make_fwd_image(d);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b0 = blockIdx.x * BT;
+    const int HiP = align4(d.Hi), MP = d.M4 * 4, HrP = d.Hr4 * 4, NHP = align4(d.NH), DP = align4(d.D);
+    const int img0 = sender_smem ? 0 : im.sender_end;
+    // ---- shared-memory carve-up ---------------------------------------------------------------------------
+    float* img = sm - img0;                       // img[off] valid for off >= img0
+    int o = im.total - img0;
+    float* hx = sm + o;   o += BT * HiP;
+    float* av = sm + o;   o += BT * HiP;
+    float* win = sm + o;  o += BT * MP;
+    float* zv = sm + o;   o += BT * MP;
+    float* pv = sm + o;   o += BT * MP;
+    float* hv = sm + o;   o += BT * HrP;
+    float* hwr = sm + o;  o += BT * HrP;
+    float* head = sm + o; o += BT * NHP;
+    float* yv = sm + o;   o += BT * DP;
+    float* qv = sm + o;   o += BT * DP;
+    int pmax = round_up(d.Hi, 32);
+    if (round_up(d.G3, 32) > pmax) pmax = round_up(d.G3, 32);
+    if (round_up(d.NH, 32) > pmax) pmax = round_up(d.NH, 32);
+    if (pmax < kLoopThreads) pmax = kLoopThreads;
+    float* partA = sm + o; o += BT * pmax;
+    float* partB = sm + o; o += BT * pmax;
+    float* sprod = sm + o; o += BT;
+    float* smask = sm + o; o += BT;
+    o = align4(o);
+    o += (o & 1);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + o);
+
+    const float* gimg = W.fwd_image;
+    const float* Wc = sender_smem ? img + im.wc : gimg + im.wc;
+    const float* Wb = sender_smem ? img + im.wb : gimg + im.wb;
+    const float* b_code = sender_smem ? img + im.b_code : gimg + im.b_code;
+    const float* hw0 = sender_smem ? img + im.hw0 : gimg + im.hw0;
+    const float* b_b = sender_smem ? img + im.b_b : gimg + im.b_b;
+    const float* Wih = img + im.wih;
+    const float* Whh = img + im.whh;
+    const float* Whead = img + im.whead;
+    const float* Ww = img + im.ww;
+    const float* b_ih = img + im.b_ih;
+    const float* b_hh = img + im.b_hh;
+    const float* b_head = img + im.b_head;
+    const float* w2 = img + im.w2;
+    const float* b_w = img + im.b_w;
+    const float* y1d = img + im.y1d;
+    const float* wdd = img + im.wdd;
+
+    const SplitPlan sp_code = make_split(d.Hi, d.M4), sp_bin = make_split(d.M, d.Hi4), sp_gi = make_split(d.G3, d.M4),
+                    sp_gh = make_split(d.G3, d.Hr4), sp_head = make_split(d.NH, d.Hr4), sp_w = make_split(d.M, d.Hr4);
+    const bool train = in.train != 0;
+    const bool binary = d.use_binary != 0;
+
+    // ---- prologue -------------------------------------------------------------------------------------------
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    MMG_SYNCTHREADS();
+    pdl_wait();
+    if (tid == 0) tma_stage(sm, gimg + img0, (uint32_t)(im.total - img0) * 4u, bar);
+    // h_x rows of this CTA: sum the split-K partials of K_pre in a fixed order, add the bias
+    for (int idx = tid; idx < BT * d.Hi; idx += kLoopThreads) {
+        const int bt = idx / d.Hi, n = idx % d.Hi, b = b0 + bt;
+        float v = 0.f;
+        if (b < d.B) {
+            v = ldg(b_img + n);
+            for (int s = 0; s < W.hx_split; ++s) v += W.hx_part[((size_t)s * d.B + b) * d.Hi + n];
+            W.h_x[(size_t)b * d.Hi + n] = v;
+        }
+        hx[bt * HiP + n] = v;
+    }
+    for (int idx = tid; idx < BT * HrP; idx += kLoopThreads) {
+        const int bt = idx / HrP, k = idx % HrP, b = b0 + bt;
+        float v = 0.f;
+        if (b < d.B && k < d.Hr) {
+            if (in.h0 != nullptr) v = in.h0[(size_t)b * d.Hr + k];
+            W.h_z[(size_t)b * d.Hr + k] = v;                         // slot 0 = state entering step 0
+        }
+        hv[idx] = v;
+        hwr[idx] = 0.f;
+    }
+    for (int idx = tid; idx < BT * MP; idx += kLoopThreads) {
+        const int bt = idx / MP, j = idx % MP, b = b0 + bt;
+        const float v = (j < d.M) ? d.first_rec : 0.f;                 // model.py:786
+        win[idx] = v; zv[idx] = 0.f; pv[idx] = 0.f;
+        if (b < d.B && j < d.M) W.rec_feats[(size_t)b * d.M + j] = v;  // slot 0
+    }
+    if (tid < BT) { sprod[tid] = 1.f; smask[tid] = 1.f; if (b0 + tid < d.B) W.stop_mask[b0 + tid] = 1; }
+    for (int idx = tid; idx < BT * HiP; idx += kLoopThreads) av[idx] = 0.f;
+#ifdef MMG_CPU_EMU
+    MMG_SYNCTHREADS();
+#endif
+    mbar_wait(bar, 0);
+    MMG_SYNCTHREADS();
+
+    unsigned long long seed = 0, iter = 0;
+    if (train && in.u_sen == nullptr) { seed = W.rng_state[0]; iter = W.rng_state[1]; }
+
+    for (int t = 0; t < d.T; ++t) {
+        // ---- S1: sender code term W_code . w_prev (model.py:207); step 0 uses the constant hw0 (199-200) ----
+        if (t > 0) {
+            if (sender_smem) split_matvec<BT, false>(Wc, d.Hi, d.M4, win, MP, partA, sp_code);
+            else             split_matvec<BT, true>(Wc, d.Hi, d.M4, win, MP, partA, sp_code);
+            // log-likelihood / entropy sums of the previous receiver message (rows of calculate_loss_binary)
+            if (binary && warp == kLoopThreads / 32 - 1) {
+                for (int bt = 0; bt < BT; ++bt) {
+                    float lp = 0.f, hh = 0.f;
+                    for (int j = lane; j < d.M; j += 32) {
+                        const float p = pv[bt * MP + j], f = win[bt * MP + j];
+                        const float l1 = logf(p + 1e-8f), l0 = logf(1.f - p + 1e-8f);
+                        lp += f * l1 + (1.f - f) * l0;
+                        hh += p * l1 + (1.f - p) * l0;
+                    }
+                    lp = warp_sum(lp); hh = warp_sum(hh);
+                    const int b = b0 + bt;
+                    if (lane == 0 && b < d.B) {
+                        W.rowstat[(size_t)2 * d.R + (size_t)(t - 1) * d.B + b] = lp;
+                        W.rowstat[(size_t)3 * d.R + (size_t)(t - 1) * d.B + b] = hh;
+                    }
+                }
+            }
+            MMG_SYNCTHREADS();
+        }
+        // ---- S2: a = tanh(h_x + h_w) (model.py:216) -------------------------------------------------------
+        for (int idx = tid; idx < BT * d.Hi; idx += kLoopThreads) {
+            const int bt = idx / d.Hi, n = idx % d.Hi, b = b0 + bt;
+            const float hw = (t == 0) ? hw0[n] : b_code[n] + gather_part<BT>(partA, sp_code, bt, n);
+            const float a = tanhf(hx[bt * HiP + n] + hw);
+            av[bt * HiP + n] = a;
+            if (b < d.B) W.a_s[((size_t)t * d.B + b) * d.Hi + n] = a;
+        }
+        if (t > 0) {
+            for (int idx = tid; idx < BT * d.M; idx += kLoopThreads) {
+                const int bt = idx / d.M, j = idx % d.M, b = b0 + bt;
+                if (b < d.B) W.code_in[((size_t)t * d.B + b) * d.M + j] = win[bt * MP + j];
+            }
+        }
+        MMG_SYNCTHREADS();
+        // ---- S3: binary_layer (model.py:216) -----------------------------------------------------------------
+        if (sender_smem) split_matvec<BT, false>(Wb, d.M, d.Hi4, av, HiP, partA, sp_bin);
+        else             split_matvec<BT, true>(Wb, d.M, d.Hi4, av, HiP, partA, sp_bin);
+        MMG_SYNCTHREADS();
+        // ---- S4: sender message (model.py:222-238, 814-820) ------------------------------------------------
+        for (int idx = tid; idx < BT * d.M; idx += kLoopThreads) {
+            const int bt = idx / d.M, j = idx % d.M, b = b0 + bt;
+            const float logit = b_b[j] + gather_part<BT>(partA, sp_bin, bt, j);
+            float p = 0.f, zval;
+            const size_t row = (size_t)t * d.B + b;
+            if (binary) {
+                p = sigmoidf_(logit);
+                if (train) zval = (b < d.B) ? draw_bit(in.u_sen, row * d.M + j, p, seed, iter, t * 4 + 0, b + row_offset, j) : 0.f;
+                else       zval = rintf(p);
+            } else {
+                zval = logit;
+            }
+            if (in.corrupt_mask != nullptr) zval = fabsf(zval - in.corrupt_mask[j]);
+            zv[bt * MP + j] = zval;
+            pv[bt * MP + j] = p;
+            if (b < d.B) {
+                W.sen_feats[row * d.M + j] = zval;
+                if (binary) W.sen_probs[row * d.M + j] = p;
+            }
+        }
+        MMG_SYNCTHREADS();
+        // ---- S5: GRU mat-vecs (model.py:340) -------------------------------------------------------------------
+        split_matvec<BT, false>(Wih, d.G3, d.M4, zv, MP, partA, sp_gi);
+        split_matvec<BT, false>(Whh, d.G3, d.Hr4, hv, HrP, partB, sp_gh);
+        if (binary && warp == kLoopThreads / 32 - 1) {
+            for (int bt = 0; bt < BT; ++bt) {
+                float lp = 0.f, hh = 0.f;
+                for (int j = lane; j < d.M; j += 32) {
+                    const float p = pv[bt * MP + j], f = zv[bt * MP + j];
+                    const float l1 = logf(p + 1e-8f), l0 = logf(1.f - p + 1e-8f);
+                    lp += f * l1 + (1.f - f) * l0;
+                    hh += p * l1 + (1.f - p) * l0;
+                }
+                lp = warp_sum(lp); hh = warp_sum(hh);
+                const int b = b0 + bt;
+                if (lane == 0 && b < d.B) {
+                    W.rowstat[(size_t)0 * d.R + (size_t)t * d.B + b] = lp;
+                    W.rowstat[(size_t)1 * d.R + (size_t)t * d.B + b] = hh;
+                }
+            }
+        }
+        MMG_SYNCTHREADS();
+        // ---- S6: GRU gates, gate order r,z,n; h' = n + u (h - n) --------------------------------------------
+        for (int idx = tid; idx < BT * d.Hr; idx += kLoopThreads) {
+            const int bt = idx / d.Hr, k = idx % d.Hr, b = b0 + bt;
+            const float gi_r = b_ih[k] + gather_part<BT>(partA, sp_gi, bt, k);
+            const float gi_u = b_ih[d.Hr + k] + gather_part<BT>(partA, sp_gi, bt, d.Hr + k);
+            const float gi_n = b_ih[2 * d.Hr + k] + gather_part<BT>(partA, sp_gi, bt, 2 * d.Hr + k);
+            const float gh_r = b_hh[k] + gather_part<BT>(partB, sp_gh, bt, k);
+            const float gh_u = b_hh[d.Hr + k] + gather_part<BT>(partB, sp_gh, bt, d.Hr + k);
+            const float gh_n = b_hh[2 * d.Hr + k] + gather_part<BT>(partB, sp_gh, bt, 2 * d.Hr + k);
+            const float r = sigmoidf_(gi_r + gh_r);
+            const float u = sigmoidf_(gi_u + gh_u);
+            const float nn = tanhf(gi_n + r * gh_n);
+            const float hp = hv[bt * HrP + k];
+            const float hn = nn + u * (hp - nn);
+            hv[bt * HrP + k] = hn;
+            if (b < d.B) {
+                const size_t row = (size_t)t * d.B + b;
+                float* g = W.gates + row * 4 * d.Hr;
+                g[k] = r; g[d.Hr + k] = u; g[2 * d.Hr + k] = nn; g[3 * d.Hr + k] = gh_n;
+                W.h_z[((size_t)(t + 1) * d.B + b) * d.Hr + k] = hn;
+            }
+        }
+        MMG_SYNCTHREADS();
+        // ---- S7: stacked heads [y1.weight[:, :Hr] ; w_h ; s] . h' (model.py:414,432,452) --------------------
+        split_matvec<BT, false>(Whead, d.NH, d.Hr4, hv, HrP, partA, sp_head);
+        MMG_SYNCTHREADS();
+        // ---- S8a: finalize heads, STOP bit (model.py:414-429, 852) --------------------------------------------
+        for (int idx = tid; idx < BT * d.NH; idx += kLoopThreads) {
+            const int bt = idx / d.NH, oo = idx % d.NH, b = b0 + bt;
+            const float v = b_head[oo] + gather_part<BT>(partA, sp_head, bt, oo);
+            head[bt * NHP + oo] = v;
+            const size_t row = (size_t)t * d.B + b;
+            if (oo < d.Hr) {
+                if (b < d.B) W.y1h[row * d.Hr + oo] = v;
+            } else if (oo == 2 * d.Hr) {
+                const float sp = sigmoidf_(v);
+                float sbit;
+                if (train) {
+                    sbit = (b < d.B) ? draw_bit(in.u_stop, row, sp, seed, iter, t * 4 + 1, b + row_offset, 0) : 0.f;
+                } else {
+                    const float prod = (t == 0 || !d.s_prob_prod) ? sp : sprod[bt] * sp;
+                    sprod[bt] = prod;
+                    sbit = rintf(prod);
+                }
+                const float m = fminf(smask[bt], sbit);
+                smask[bt] = m;
+                if (b < d.B) {
+                    W.stop_feat[row] = sbit;
+                    W.stop_prob[row] = sp;
+                    W.stop_mask[(size_t)(t + 1) * d.B + b] = (unsigned char)(m != 0.f);
+                    const float l1 = logf(sp + 1e-8f), l0 = logf(1.f - sp + 1e-8f);
+                    W.rowstat[(size_t)4 * d.R + row] = sbit * l1 + (1.f - sbit) * l0;
+                    W.rowstat[(size_t)5 * d.R + row] = sp * l1 + (1.f - sp) * l0;
+                }
+            }
+        }
+        MMG_SYNCTHREADS();
+        // ---- S8b: class scores y[d] = y2(relu(y1h + y1d[d])) (model.py:432-433) — one warp per (example, class)
+        for (int pair = warp; pair < BT * d.D; pair += kLoopThreads / 32) {
+            const int bt = pair / d.D, dd = pair % d.D, b = b0 + bt;
+            float s = 0.f;
+            for (int k = lane; k < d.Hr; k += 32)
+                s = fmaf(w2[k], fmaxf(0.f, head[bt * NHP + k] + y1d[dd * d.Hr + k]), s);
+            s = warp_sum(s);
+            if (lane == 0) {
+                s += img[im.misc];
+                yv[bt * DP + dd] = s;
+                if (b < d.B) W.y[((size_t)t * d.B + b) * d.D + dd] = s;
+            }
+        }
+        MMG_SYNCTHREADS();
+        // ---- S9: q = softmax(y) (model.py:441) — one warp per example -------------------------------------------
+        for (int bt = warp; bt < BT; bt += kLoopThreads / 32) {
+            const int b = b0 + bt;
+            float mx = -INFINITY;
+            for (int dd = lane; dd < d.D; dd += 32) mx = fmaxf(mx, yv[bt * DP + dd]);
+            mx = warp_max(mx);
+            float se = 0.f;
+            for (int dd = lane; dd < d.D; dd += 32) se += expf(yv[bt * DP + dd] - mx);
+            se = warp_sum(se);
+            const float inv = 1.f / se;
+            for (int dd = lane; dd < d.D; dd += 32) {
+                const float qq = expf(yv[bt * DP + dd] - mx) * inv;
+                qv[bt * DP + dd] = qq;
+                if (b < d.B) W.q[((size_t)t * d.B + b) * d.D + dd] = qq;
+            }
+        }
+        MMG_SYNCTHREADS();
+        // ---- S10: h_w = tanh(w_h(h') + w_d(q . desc)) (model.py:442-452); wd = q . desc saved for the backward --
+        for (int idx = tid; idx < BT * (d.Hr + d.WV); idx += kLoopThreads) {
+            if (idx < BT * d.Hr) {
+                const int bt = idx / d.Hr, k = idx % d.Hr, b = b0 + bt;
+                float s = 0.f;
+                for (int dd = 0; dd < d.D; ++dd) s = fmaf(qv[bt * DP + dd], wdd[dd * d.Hr + k], s);
+                const float hw = tanhf(head[bt * NHP + d.Hr + k] + s);
+                hwr[bt * HrP + k] = hw;
+                if (b < d.B) W.h_w[((size_t)t * d.B + b) * d.Hr + k] = hw;
+            } else if (train) {
+                const int i2 = idx - BT * d.Hr;
+                const int bt = i2 / d.WV, v = i2 % d.WV, b = b0 + bt;
+                if (b < d.B) {
+                    float s = 0.f;
+                    for (int dd = 0; dd < d.D; ++dd) s = fmaf(qv[bt * DP + dd], ldg(in.desc + (size_t)dd * d.WV + v), s);
+                    W.wd[((size_t)t * d.B + b) * d.WV + v] = s;
+                }
+            }
+        }
+        MMG_SYNCTHREADS();
+        // ---- S11: w(h_w) (model.py:454) ------------------------------------------------------------------------
+        split_matvec<BT, false>(Ww, d.M, d.Hr4, hwr, HrP, partA, sp_w);
+        MMG_SYNCTHREADS();
+        // ---- S12: receiver message (model.py:455-475) ---------------------------------------------------------
+        for (int idx = tid; idx < BT * d.M; idx += kLoopThreads) {
+            const int bt = idx / d.M, j = idx % d.M, b = b0 + bt;
+            const float logit = b_w[j] + gather_part<BT>(partA, sp_w, bt, j);
+            const size_t row = (size_t)t * d.B + b;
+            float p = 0.f, wv;
+            if (binary) {
+                p = sigmoidf_(logit);
+                if (train) wv = (b < d.B) ? draw_bit(in.u_rec, row * d.M + j, p, seed, iter, t * 4 + 2, b + row_offset, j) : 0.f;
+                else       wv = rintf(p);
+                if (d.ignore_receiver) wv = 0.f;
+            } else {
+                wv = logit;
+            }
+            win[bt * MP + j] = wv;
+            pv[bt * MP + j] = p;
+            if (b < d.B) {
+                W.rec_feats[((size_t)(t + 1) * d.B + b) * d.M + j] = wv;
+                if (binary) W.rec_probs[row * d.M + j] = p;
+            }
+        }
+        MMG_SYNCTHREADS();
+    }
+    // log-likelihood / entropy sums of the last receiver message
+    if (binary && warp == kLoopThreads / 32 - 1) {
+        for (int bt = 0; bt < BT; ++bt) {
+            float lp = 0.f, hh = 0.f;
+            for (int j = lane; j < d.M; j += 32) {
+                const float p = pv[bt * MP + j], f = win[bt * MP + j];
+                const float l1 = logf(p + 1e-8f), l0 = logf(1.f - p + 1e-8f);
+                lp += f * l1 + (1.f - f) * l0;
+                hh += p * l1 + (1.f - p) * l0;
+            }
+            lp = warp_sum(lp); hh = warp_sum(hh);
+            const int b = b0 + bt;
+            if (lane == 0 && b < d.B) {
+                W.rowstat[(size_t)2 * d.R + (size_t)(d.T - 1) * d.B + b] = lp;
+                W.rowstat[(size_t)3 * d.R + (size_t)(d.T - 1) * d.B + b] = hh;
+            }
+        }
+    }
+    pdl_launch_dependents();
+}
+
+}  // namespace mmg

@@ -1,0 +1,58 @@
+// Kernel-side shared declarations: resolved pointer tables and launch helpers.
+#pragma once
+#include "mmg_layout.h"
+#include "mmg_gemm.cuh"
+
+namespace mmg {
+
+struct ParamPtrs {            // one pointer per state_dict tensor (params, or grads / slabs with the same layout)
+    const float* p[MMG_P_COUNT];
+};
+
+struct WsPtrs {               // resolved workspace arrays (device pointers)
+    float *sen_feats, *sen_probs, *rec_feats, *rec_probs, *stop_feat, *stop_prob, *y, *bs, *br, *h_x, *h_z, *h_w;
+    unsigned char* stop_mask;
+    float *losses, *outp, *logs, *grad_norms;
+    int *ystep, *argmax;
+    double* stats;
+    float *g_sen_probs, *g_rec_probs, *g_stop_prob, *g_outp, *g_bs, *g_br;
+    unsigned long long* rng_state;
+    float *code_in, *a_s, *gates, *y1h, *q, *wd, *rowstat, *h1s, *h1r, *bs_part, *br_part;
+    float *hx_part, *fwd_image, *bwd_image;
+    float *d_lz, *d_as, *dhx, *dgi, *dgh, *d_lw, *d_hw, *d_ls, *g_h, *hsel, *dy1, *dw2p, *slabs, *norm_part;
+    long long* opt_counters;
+    int hx_split, wgrad_split, ntb;
+};
+
+struct ExchangeInputs {       // device pointers of one exchange (mmg_inputs resolved)
+    const float* x;
+    const float* desc;
+    const long long* target;
+    const double *u_sen, *u_stop, *u_rec;
+    const float* corrupt_mask;
+    const float* h0;
+    int top_k, train;
+};
+
+}  // namespace mmg
+
+// ---- launch macro --------------------------------------------------------------------------------------
+#ifndef MMG_CPU_EMU
+#define MMG_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
+    do {                                                                    \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);        \
+        mmg::host::count_launch();                                          \
+    } while (0)
+#else
+#define MMG_LAUNCH(kernel, grid, block, smem, stream, ...)                                   \
+    do {                                                                                      \
+        mmg::emu::launch(dim3(grid), dim3(block), (smem), [&]() { kernel(__VA_ARGS__); });    \
+        mmg::host::count_launch();                                                            \
+    } while (0)
+#endif
+
+namespace mmg {
+namespace host {
+void count_launch();
+}
+}  // namespace mmg

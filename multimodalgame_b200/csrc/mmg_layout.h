@@ -1,0 +1,153 @@
+// Internal layouts shared by host code and kernels: problem dimensions, the flat parameter layout, the
+// workspace map and the kernel-layout weight images staged into shared memory by the exchange kernels.
+#pragma once
+#include "../../include/mmg_b200.h"
+#include "mmg_platform.cuh"
+
+namespace mmg {
+
+struct Dims {
+    int B, Bg, F, Hi, M, Hr, D, WV, Hb, T;
+    int R;        // T * B rows, step-major
+    int G3;       // 3 * Hr
+    int M4, Hr4, Hi4;   // ceil(x / 4): float4 groups along a reduction dimension
+    int NH;       // stacked head rows: [y1.weight[:, :Hr] ; w_h.weight ; s.weight] = 2*Hr + 1
+    int use_binary, fixed, s_prob_prod, ignore_receiver;
+    float first_rec;
+};
+
+MMG_HOST_DEVICE Dims make_dims(const mmg_config& c) {
+    Dims d;
+    d.B = c.batch; d.Bg = c.batch_global; d.F = c.img_feat_dim; d.Hi = c.img_h_dim; d.M = c.msg_dim;
+    d.Hr = c.rec_hidden; d.D = c.n_classes; d.WV = c.wv_dim; d.Hb = c.baseline_hid; d.T = c.max_exchange;
+    d.R = d.T * d.B; d.G3 = 3 * d.Hr;
+    d.M4 = cdiv(d.M, 4); d.Hr4 = cdiv(d.Hr, 4); d.Hi4 = cdiv(d.Hi, 4);
+    d.NH = 2 * d.Hr + 1;
+    d.use_binary = c.use_binary; d.fixed = c.fixed_exchange; d.s_prob_prod = c.s_prob_prod;
+    d.ignore_receiver = c.ignore_receiver;
+    d.first_rec = c.first_rec;
+    return d;
+}
+
+// ---- weight images ------------------------------------------------------------------------------------
+// "Packed" matrix for a mat-vec out[o] = sum_r W(o, r) * v[r]:  P[(r/4) * Nout * 4 + o * 4 + (r % 4)],
+// zero padded along r.  Thread `o` then reads one float4 per 4 reduction elements and a warp reads 512
+// contiguous bytes: conflict-free shared-memory (or fully coalesced global) access.
+// All offsets in floats, every section a multiple of 4 floats (16 bytes) for the TMA bulk copies.
+struct FwdImage {
+    // sender part
+    int wc;      // code_layer.weight   out=Hi  red=M
+    int wb;      // binary_layer.weight out=M   red=Hi
+    int b_code;  // [Hi]
+    int hw0;     // [Hi] code_layer(sigmoid(code_bias)) incl. bias: the step-0 code term (model.py:199-200)
+    int b_b;     // [M]
+    int sender_end;
+    // receiver part
+    int wih;     // rnn.weight_ih  out=3Hr red=M
+    int whh;     // rnn.weight_hh  out=3Hr red=Hr
+    int whead;   // [y1.weight[:, :Hr] ; w_h.weight ; s.weight]  out=NH red=Hr
+    int ww;      // w.weight       out=M   red=Hr
+    int b_ih, b_hh;   // [3Hr] each
+    int b_head;  // [NH]  (0 for the y1 rows: y1.bias is folded into y1d; w_h.bias; s.bias)
+    int w2;      // [Hr] y2.weight
+    int b_w;     // [M]
+    int misc;    // [4]: y2.bias, -, -, -
+    int y1d;     // [D][Hr]  desc_d . y1.weight[:, Hr:]^T + y1.bias   (class half of y1, loop invariant)
+    int wdd;     // [D][Hr]  desc_d . w_d.weight^T
+    int total;
+};
+struct BwdImage {
+    int wbT;     // binary_layer.weight^T  out=Hi red=M      (sender rows)
+    int sender_end;
+    int wwT;     // w.weight^T             out=Hr red=M
+    int headT;   // [w_h.weight ; y1.weight[:, :Hr]]^T  out=Hr red=2Hr
+    int whhT;    // rnn.weight_hh^T        out=Hr red=3Hr
+    int ws;      // [Hr] s.weight
+    int w2;      // [Hr] y2.weight
+    int y1d;     // [D][Hr]
+    int total;
+};
+
+MMG_HOST_DEVICE int align4(int x) { return (x + 3) & ~3; }
+
+MMG_HOST_DEVICE FwdImage make_fwd_image(const Dims& d) {
+    FwdImage im; int o = 0;
+    im.wc = o; o += d.M4 * d.Hi * 4;
+    im.wb = o; o += d.Hi4 * d.M * 4;
+    im.b_code = o; o += align4(d.Hi);
+    im.hw0 = o; o += align4(d.Hi);
+    im.b_b = o; o += align4(d.M);
+    im.sender_end = o;
+    im.wih = o; o += d.M4 * d.G3 * 4;
+    im.whh = o; o += d.Hr4 * d.G3 * 4;
+    im.whead = o; o += d.Hr4 * d.NH * 4;
+    im.ww = o; o += d.Hr4 * d.M * 4;
+    im.b_ih = o; o += align4(d.G3);
+    im.b_hh = o; o += align4(d.G3);
+    im.b_head = o; o += align4(d.NH);
+    im.w2 = o; o += align4(d.Hr);
+    im.b_w = o; o += align4(d.M);
+    im.misc = o; o += 4;
+    im.y1d = o; o += align4(d.D * d.Hr);
+    im.wdd = o; o += align4(d.D * d.Hr);
+    im.total = o;
+    return im;
+}
+MMG_HOST_DEVICE BwdImage make_bwd_image(const Dims& d) {
+    BwdImage im; int o = 0;
+    im.wbT = o; o += d.M4 * d.Hi * 4;
+    im.sender_end = o;
+    im.wwT = o; o += d.M4 * d.Hr * 4;
+    im.headT = o; o += cdiv(2 * d.Hr, 4) * d.Hr * 4;
+    im.whhT = o; o += cdiv(d.G3, 4) * d.Hr * 4;
+    im.ws = o; o += align4(d.Hr);
+    im.w2 = o; o += align4(d.Hr);
+    im.y1d = o; o += align4(d.D * d.Hr);
+    im.total = o;
+    return im;
+}
+
+// ---- workspace ------------------------------------------------------------------------------------------
+enum { kHxSplitMax = 16, kWgradSplitMax = 8, kNormCtas = 128 };
+enum { kStatKinds = 3 };  // 0: sender messages, 1: receiver messages, 2: stop bit
+// stats (double): per (kind, t): n, sum w, sum w^2 (w = logs - baseline); then per t: baseline_rec SSE,
+// baseline_sen SSE, n_mask; then scalars: nll_sum, topk_correct.
+MMG_HOST_DEVICE int stats_count(const Dims& d) { return kStatKinds * d.T * 3 + 3 * d.T + 4; }
+MMG_HOST_DEVICE int stat_idx(const Dims& d, int kind, int t, int which) { return (kind * d.T + t) * 3 + which; }
+MMG_HOST_DEVICE int stat_bas(const Dims& d, int t, int which) { return kStatKinds * d.T * 3 + t * 3 + which; }
+MMG_HOST_DEVICE int stat_scalar(const Dims& d, int which) { return kStatKinds * d.T * 3 + 3 * d.T + which; }
+
+struct Ws {   // byte offsets into the workspace
+    mmg_workspace_layout pub;
+    // saved activations
+    int64_t code_in;   // (T,B,M)  sender code input: sigmoid(code_bias) at t=0, receiver message after
+    int64_t a_s;       // (T,B,Hi) sender tanh hidden
+    int64_t gates;     // (T,B,4,Hr) r, u, n, (W_hn h + b_hn)
+    int64_t y1h;       // (T,B,Hr) y1.weight[:, :Hr] . h_z
+    int64_t q;         // (T,B,D)  softmax(y)
+    int64_t wd;        // (T,B,WV) q . desc
+    int64_t rowstat;   // (6,T,B)  logp_z, H_z, logp_w, H_w, logp_s, H_s
+    int64_t h1s, h1r;  // (T,B,Hb) baseline hidden (post relu)
+    int64_t bs_part, br_part;  // (T,B,NTb) partial dots with linear2.weight per 64-column tile
+    // pre-pass
+    int64_t hx_part;   // (S,B,Hi)
+    int64_t fwd_image, bwd_image;
+    // backward deltas
+    int64_t d_lz;      // (T,B,M)  dL/d sender logits
+    int64_t d_as;      // (T,B,Hi) dL/d sender pre-tanh
+    int64_t dhx;       // (B,Hi)
+    int64_t dgi, dgh;  // (T,B,3Hr)
+    int64_t d_lw;      // (T,B,M)
+    int64_t d_hw;      // (T,B,Hr)
+    int64_t d_ls;      // (T,B)
+    int64_t g_h;       // (B,Hr)   sum_d dy1
+    int64_t hsel;      // (B,Hr)   h_z at the prediction step
+    int64_t dy1;       // (B,D,Hr)
+    int64_t dw2p;      // (B,Hr)
+    int64_t slabs;     // (kWgradSplitMax, P) split-K partial gradients
+    int64_t norm_part; // (4, kNormCtas) per-CTA partial sums of squares
+    int64_t opt_counters; // int64[4]: [0] = number of updates that reached the receiver message head (Adam bias correction)
+    int hx_split, wgrad_split, ntb;
+};
+
+}  // namespace mmg

@@ -1,0 +1,304 @@
+// K_baseline_fwd, K_stats, K_lossgrad.
+//
+// K_baseline_fwd: both Baseline MLPs (model.py:496-516) for all T*B rows at once.  The baselines only consume
+//   detached by-products of the conversation (model.py:835-843), so they leave the recurrent critical path and run
+//   as two tiled GEMMs with a fused relu + linear2 epilogue.
+// K_stats (1 CTA): get_rec_outp's stop-step selection (model.py:879-904), log_softmax / NLL / loglikelihood /
+//   argmax / top-k (1264-1275, 1333-1338), and the batch-global statistics every REINFORCE term needs: per
+//   (loss, step) the active-row count n_t (model.py:947,981) and the mean/variance of `logs - baseline` for
+//   torch.std (915).  In a data-parallel run these statistics are what the ranks all-reduce.
+// K_lossgrad: closed-form dLoss/d(probabilities) of calculate_loss_binary (907-927) and calculate_loss_bas (971-973)
+//   with the multistep weighting (930-988) and the mask wiring (1248-1262); CTA 0 also evaluates the loss values.
+#pragma once
+#include "mmg_kernels.cuh"
+
+namespace mmg {
+
+MMG_GLOBAL void __launch_bounds__(kGemmThreads)
+k_baseline_fwd(Dims d, ParamPtrs P, WsPtrs W) {
+    MMG_SHARED __attribute__((aligned(16))) float As[kChunk * kLd];
+    MMG_SHARED __attribute__((aligned(16))) float Bs[kChunk * kLd];
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int ntm = cdiv(d.R, kTile), ntn = W.ntb;
+    int t = blockIdx.x;
+    const int which = t / (ntm * ntn);     // 0: baseline_sen, 1: baseline_rec
+    t %= ntm * ntn;
+    const int nt = t % ntn, mt = t / ntn;
+    Operand A, Bo;
+    const float *b1, *w2;
+    float *hid, *part;
+    int K;
+    if (which == 0) {   // rows [h_x[b] ; z_r[t,b]]  (model.py:835-836), z_r[t] = rec_feats slot t
+        A = Operand{W.h_x, W.rec_feats, nullptr, nullptr, d.Hi, d.M, 0, d.B, d.Hi, OP_PLAIN};
+        Bo = Operand{P.p[MMG_P_BS_L1_W], nullptr, nullptr, nullptr, d.Hi + d.M, 0, 0, 0, 0, OP_PLAIN};
+        b1 = P.p[MMG_P_BS_L1_B]; w2 = P.p[MMG_P_BS_L2_W]; hid = W.h1s; part = W.bs_part; K = d.Hi + d.M;
+    } else {            // rows [z[t,b] ; h_z after step t]  (model.py:842-843)
+        A = Operand{W.sen_feats, W.h_z + (size_t)d.B * d.Hr, nullptr, nullptr, d.M, d.Hr, 0, 0, d.M, OP_PLAIN};
+        Bo = Operand{P.p[MMG_P_BR_L1_W], nullptr, nullptr, nullptr, d.M + d.Hr, 0, 0, 0, 0, OP_PLAIN};
+        b1 = P.p[MMG_P_BR_L1_B]; w2 = P.p[MMG_P_BR_L2_W]; hid = W.h1r; part = W.br_part; K = d.M + d.Hr;
+    }
+    float acc[4][4];
+    gemm_tile(A, Bo, d.R, d.Hb, mt * kTile, nt * kTile, 0, K, acc, nullptr, As, Bs);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int r = mt * kTile + ty * 4 + a;
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int n = nt * kTile + tx * 4 + c;
+            if (r < d.R && n < d.Hb) {
+                const float v = fmaxf(0.f, acc[a][c] + ldg(b1 + n));
+                hid[(size_t)r * d.Hb + n] = v;
+                dot = fmaf(v, ldg(w2 + n), dot);
+            }
+        }
+        dot = half_warp_sum(dot);
+        if (tx == 0 && r < d.R) part[(size_t)r * ntn + nt] = dot;
+    }
+}
+
+enum { kStatsThreads = 1024 };
+
+MMG_DEVICE unsigned char mask_at(const Dims& d, const WsPtrs& W, int slot, int b) {
+    return d.fixed ? (unsigned char)1 : W.stop_mask[(size_t)slot * d.B + b];
+}
+
+MMG_GLOBAL void __launch_bounds__(kStatsThreads)
+k_stats(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kStatsThreads / 32;
+    // ---- finalize baseline scores --------------------------------------------------------------------------
+    const float b2s = ldg(P.p[MMG_P_BS_L2_B]), b2r = ldg(P.p[MMG_P_BR_L2_B]);
+    for (int r = tid; r < d.R; r += kStatsThreads) {
+        float s = b2s, q = b2r;
+        for (int j = 0; j < W.ntb; ++j) { s += W.bs_part[(size_t)r * W.ntb + j]; q += W.br_part[(size_t)r * W.ntb + j]; }
+        W.bs[r] = s; W.br[r] = q;
+    }
+    // ---- per example: prediction step, log-softmax, log-likelihood, argmax, top-k, dNLL/d outp ------------------
+    MMG_SHARED double s_red[2][kStatsThreads / 32];
+    double nll_local = 0.0, correct_local = 0.0;
+    for (int b = tid; b < d.B; b += kStatsThreads) {
+        int ts = d.T - 1;
+        if (!d.fixed) {
+            for (int t = 0; t < d.T; ++t) if (W.stop_mask[(size_t)(t + 1) * d.B + b] == 0) { ts = t; break; }
+        }
+        W.ystep[b] = ts;
+        const float* yy = W.y + ((size_t)ts * d.B + b) * d.D;
+        float mx = -INFINITY; int am = 0;
+        for (int dd = 0; dd < d.D; ++dd) { const float v = yy[dd]; if (v > mx) { mx = v; am = dd; } }
+        float se = 0.f;
+        for (int dd = 0; dd < d.D; ++dd) se += expf(yy[dd] - mx);
+        const float lse = mx + logf(se);
+        const int tg = (int)in.target[b];
+        const float lt = yy[tg] - lse;
+        int rank = 0;
+        const float invB = 1.0f / (float)d.Bg;
+        for (int dd = 0; dd < d.D; ++dd) {
+            const float v = yy[dd];
+            W.outp[(size_t)b * d.D + dd] = v;
+            if (v > yy[tg]) ++rank;
+            W.g_outp[(size_t)b * d.D + dd] = (expf(v - lse) - (dd == tg ? 1.f : 0.f)) * invB;   // d nll / d outp
+        }
+        W.logs[b] = lt;
+        W.argmax[b] = am;
+        nll_local -= (double)lt;
+        if (rank < in.top_k) correct_local += 1.0;
+    }
+    nll_local = warp_sum_d(nll_local);
+    correct_local = warp_sum_d(correct_local);
+    if (lane == 0) { s_red[0][warp] = nll_local; s_red[1][warp] = correct_local; }
+    MMG_SYNCTHREADS();
+    if (tid == 0) {
+        double a = 0, c = 0;
+        for (int w = 0; w < nwarps; ++w) { a += s_red[0][w]; c += s_red[1][w]; }
+        W.stats[stat_scalar(d, 0)] = a;
+        W.stats[stat_scalar(d, 1)] = c;
+        W.stats[stat_scalar(d, 2)] = 0.0;
+        W.stats[stat_scalar(d, 3)] = 0.0;
+        if (in.train && in.u_sen == nullptr) W.rng_state[1] += 1ull;   // next iteration draws a fresh Philox stream
+    }
+    // ---- batch statistics per (loss kind, step): one warp per quantity ------------------------------------------
+    // kind 0: sender messages  (baseline bs[t], mask s_masks[t])      model.py:1258,1291
+    // kind 1: receiver message (baseline br[t], mask s_masks[t+1], t <= T-2)   model.py:1257,1285-1286
+    // kind 2: stop bit         (baseline br[t], mask s_masks[t])      model.py:1256,1279-1280
+    for (int qn = warp; qn < 4 * d.T; qn += nwarps) {
+        const int kind = qn / d.T, t = qn % d.T;
+        double n = 0, s1 = 0, s2 = 0, e1 = 0, e2 = 0;
+        for (int b = lane; b < d.B; b += 32) {
+            const float lg = W.logs[b];
+            if (kind < 3) {
+                const int slot = (kind == 1) ? t + 1 : t;
+                const bool valid = !(kind == 1 && t == d.T - 1) && !(kind == 2 && d.fixed);
+                if (valid && mask_at(d, W, slot, b)) {
+                    const float base = (kind == 0) ? W.bs[(size_t)t * d.B + b] : W.br[(size_t)t * d.B + b];
+                    const double w = (double)(lg - base);
+                    n += 1.0; s1 += w; s2 += w * w;
+                }
+            } else {
+                if (mask_at(d, W, t, b)) {
+                    const double er = (double)(W.br[(size_t)t * d.B + b] - lg), es = (double)(W.bs[(size_t)t * d.B + b] - lg);
+                    e1 += er * er; e2 += es * es;
+                }
+                if (mask_at(d, W, t + 1, b) && !d.fixed) n += 1.0;   // rows still active after step t
+                if (d.fixed) n += 1.0;
+            }
+        }
+        n = warp_sum_d(n); s1 = warp_sum_d(s1); s2 = warp_sum_d(s2); e1 = warp_sum_d(e1); e2 = warp_sum_d(e2);
+        if (lane == 0) {
+            if (kind < 3) {
+                W.stats[stat_idx(d, kind, t, 0)] = n; W.stats[stat_idx(d, kind, t, 1)] = s1; W.stats[stat_idx(d, kind, t, 2)] = s2;
+            } else {
+                W.stats[stat_bas(d, t, 0)] = e1; W.stats[stat_bas(d, t, 1)] = e2; W.stats[stat_bas(d, t, 2)] = n;
+            }
+        }
+    }
+}
+
+// Per (kind, t) coefficients derived from the (all-reduced) statistics.
+struct LossCoef { float cA, cE; };   // REINFORCE scale (step weight / n / max(1, std)), entropy scale (lambda * step weight / n)
+
+MMG_DEVICE void loss_coefs(const Dims& d, const mmg_config& cfg, const double* st, int kind, int t, LossCoef& out,
+                           double* n_out) {
+    const double n = st[stat_idx(d, kind, t, 0)];
+    *n_out = n;
+    out.cA = 0.f; out.cE = 0.f;
+    if (n <= 0.0) return;
+    const int steps = (kind == 1) ? d.T - 1 : d.T;                 // list lengths, model.py:967
+    double sw;
+    if (d.fixed) sw = 1.0 / (double)steps;
+    else {
+        double tot = 0;
+        for (int tt = 0; tt < steps; ++tt) tot += st[stat_idx(d, kind, tt, 0)];
+        sw = n / tot;                                              // model.py:960-961
+    }
+    double inv = 1.0;
+    if (n > 1.0) {                                                 // model.py:914-915, unbiased std
+        const double s1 = st[stat_idx(d, kind, t, 1)], s2 = st[stat_idx(d, kind, t, 2)];
+        double var = (s2 - s1 * s1 / n) / (n - 1.0);
+        if (var < 0) var = 0;
+        const double sd = (double)(float)sqrt(var);
+        inv = 1.0 / (sd > 1.0 ? sd : 1.0);
+    }
+    const int has_ent = kind == 0 ? cfg.has_entropy_sen : (kind == 1 ? cfg.has_entropy_rec : cfg.has_entropy_s);
+    const float lam = kind == 0 ? cfg.entropy_sen : (kind == 1 ? cfg.entropy_rec : cfg.entropy_s);
+    out.cA = (float)(sw / n * inv);
+    out.cE = has_ent ? (float)((double)lam * sw / n) : 0.f;
+}
+
+enum { kLossThreads = 256 };
+
+// d/dp of  -w * [f log(p+e) + (1-f) log(1-p+e)] * cA  +  cE * [p log(p+e) + (1-p) log(1-p+e)]
+MMG_DEVICE float binary_grad(float p, float f, float wcA, float cE) {
+    const float e = 1e-8f;
+    const float a = p + e, bb = 1.f - p + e;
+    float g = -wcA * (f / a - (1.f - f) / bb);
+    if (cE != 0.f) g += cE * (logf(a) + p / a - logf(bb) - (1.f - p) / bb);
+    return g;
+}
+
+MMG_GLOBAL void __launch_bounds__(kLossThreads)
+k_lossgrad(Dims d, mmg_config cfg, WsPtrs W) {
+    MMG_DYN_SMEM(smem_raw);
+    LossCoef* coef = reinterpret_cast<LossCoef*>(smem_raw);          // [3][T]
+    float* bas_scale = reinterpret_cast<float*>(coef + 3 * d.T);      // [2]: 2 / denominator for baseline MSE grads
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* st = W.stats;
+    for (int i = tid; i < 3 * d.T; i += kLossThreads) {
+        double n;
+        loss_coefs(d, cfg, st, i / d.T, i % d.T, coef[i], &n);
+    }
+    if (tid == 0) {
+        double tot = 0;   // sum_t n_t over s_masks[:-1] (model.py:983); fixed: B_global * T (mean over steps of batch means)
+        for (int t = 0; t < d.T; ++t) tot += st[stat_idx(d, 0, t, 0)];
+        if (d.fixed) tot = (double)d.Bg * d.T;
+        bas_scale[0] = tot > 0 ? (float)(1.0 / tot) : 0.f;
+    }
+    MMG_SYNCTHREADS();
+    const bool binary = d.use_binary != 0;
+    // ---- upstream gradients, one warp per (t, b) row -------------------------------------------------------------
+    const int rows_per_cta = kLossThreads / 32;
+    for (int row = blockIdx.x * rows_per_cta + warp; row < d.R; row += gridDim.x * rows_per_cta) {
+        const int t = row / d.B, b = row % d.B;
+        const float lg = W.logs[b];
+        const bool m_in = mask_at(d, W, t, b) != 0;           // active entering step t
+        const bool m_out = mask_at(d, W, t + 1, b) != 0;      // still active after step t
+        const float bsv = W.bs[row], brv = W.br[row];
+        if (binary) {
+            const LossCoef c0 = coef[0 * d.T + t], c1 = coef[1 * d.T + t];
+            const float w0 = m_in ? (lg - bsv) * c0.cA : 0.f, e0 = m_in ? c0.cE : 0.f;
+            const bool rec_on = m_out && (t < d.T - 1);
+            const float w1 = rec_on ? (lg - brv) * c1.cA : 0.f, e1 = rec_on ? c1.cE : 0.f;
+            for (int j = lane; j < d.M; j += 32) {
+                const size_t i = (size_t)row * d.M + j;
+                W.g_sen_probs[i] = m_in ? binary_grad(W.sen_probs[i], W.sen_feats[i], w0, e0) : 0.f;
+                W.g_rec_probs[i] = rec_on ? binary_grad(W.rec_probs[i], W.rec_feats[i + (size_t)d.B * d.M], w1, e1) : 0.f;
+            }
+            if (lane == 0) {
+                float gs = 0.f;
+                if (!d.fixed && m_in) {
+                    const LossCoef c2 = coef[2 * d.T + t];
+                    gs = binary_grad(W.stop_prob[row], W.stop_feat[row], (lg - brv) * c2.cA, c2.cE);
+                }
+                W.g_stop_prob[row] = gs;
+                W.g_bs[row] = m_in ? 2.f * (bsv - lg) * bas_scale[0] : 0.f;     // model.py:971-988
+                W.g_br[row] = m_in ? 2.f * (brv - lg) * bas_scale[0] : 0.f;
+            }
+        } else if (lane == 0) {
+            W.g_stop_prob[row] = 0.f; W.g_bs[row] = 0.f; W.g_br[row] = 0.f;
+        }
+    }
+    // ---- loss values (CTA 0): rank-local contributions; their sum over ranks is the global loss ------------------
+    if (blockIdx.x != 0) return;
+    MMG_SHARED double red[8][kLossThreads / 32];
+    double acc[8];
+    for (int i = 0; i < 8; ++i) acc[i] = 0;
+    // acc: 0 nll, 1 binary_sen, 2 binary_rec, 3 binary_s, 4 bas_rec, 5 bas_sen, 6 topk
+    for (int b = tid; b < d.B; b += kLossThreads) acc[0] -= (double)W.logs[b] / (double)d.Bg;
+    if (binary) {
+        for (int row = tid; row < d.R; row += kLossThreads) {
+            const int t = row / d.B, b = row % d.B;
+            const float lg = W.logs[b];
+            const bool m_in = mask_at(d, W, t, b) != 0, m_out = mask_at(d, W, t + 1, b) != 0;
+            const float bsv = W.bs[row], brv = W.br[row];
+            if (m_in) {
+                const LossCoef c0 = coef[0 * d.T + t];
+                acc[1] += (double)(-(lg - bsv) * c0.cA) * W.rowstat[(size_t)0 * d.R + row] + (double)c0.cE * W.rowstat[(size_t)1 * d.R + row];
+                if (!d.fixed) {
+                    const LossCoef c2 = coef[2 * d.T + t];
+                    acc[3] += (double)(-(lg - brv) * c2.cA) * W.rowstat[(size_t)4 * d.R + row] + (double)c2.cE * W.rowstat[(size_t)5 * d.R + row];
+                }
+                acc[4] += (double)(brv - lg) * (double)(brv - lg) * bas_scale[0];
+                acc[5] += (double)(bsv - lg) * (double)(bsv - lg) * bas_scale[0];
+            }
+            if (m_out && t < d.T - 1) {
+                const LossCoef c1 = coef[1 * d.T + t];
+                acc[2] += (double)(-(lg - brv) * c1.cA) * W.rowstat[(size_t)2 * d.R + row] + (double)c1.cE * W.rowstat[(size_t)3 * d.R + row];
+            }
+        }
+    }
+    for (int i = 0; i < 6; ++i) {
+        const double v = warp_sum_d(acc[i]);
+        if (lane == 0) red[i][warp] = v;
+    }
+    MMG_SYNCTHREADS();
+    if (tid == 0) {
+        double v[6];
+        for (int i = 0; i < 6; ++i) { v[i] = 0; for (int w = 0; w < kLossThreads / 32; ++w) v[i] += red[i][w]; }
+        float* L = W.losses;
+        L[MMG_LOSS_NLL] = (float)v[0];
+        L[MMG_LOSS_BINARY_SEN] = (float)v[1];
+        L[MMG_LOSS_BINARY_REC] = (float)v[2];
+        L[MMG_LOSS_BINARY_S] = (float)v[3];
+        L[MMG_LOSS_BAS_REC] = (float)v[4];
+        L[MMG_LOSS_BAS_SEN] = (float)v[5];
+        L[MMG_LOSS_REC] = (float)(v[0] + v[2] + (d.fixed ? 0.0 : v[3]));      // model.py:1296-1300
+        L[MMG_LOSS_SEN] = (float)v[1];                                          // model.py:1301
+        L[MMG_LOSS_TOPK_CORRECT] = (float)st[stat_scalar(d, 1)];
+        int tp = d.T;
+        if (!d.fixed) for (int t = 0; t < d.T; ++t) if (st[stat_bas(d, t, 2)] <= 0.0) { tp = t + 1; break; }
+        L[MMG_LOSS_ACTIVE_STEPS] = (float)tp;
+        if (st[stat_idx(d, 1, 0, 0)] > 0.0) W.opt_counters[0] += 1;   // updates seen by the receiver message head
+        for (int i = MMG_LOSS_ACTIVE_STEPS + 1; i < MMG_LOSS_COUNT; ++i) L[i] = 0.f;
+    }
+}
+
+}  // namespace mmg

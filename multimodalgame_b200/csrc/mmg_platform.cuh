@@ -1,0 +1,218 @@
+// Platform layer.  Product build: nvcc, sm_100a.  When MMG_CPU_EMU is defined (tests/emu only) the very same
+// kernel sources are compiled by g++ and every CUDA thread becomes an OS thread, so kernel logic (indexing,
+// barrier structure, shared-memory hazards under ThreadSanitizer) can be checked in the GPU-less build
+// container.  The emulated library is test infrastructure: the product package never loads it.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include <math.h>
+#include <string.h>
+
+#ifndef MMG_CPU_EMU
+// =====================================================================================================
+//                                              CUDA
+// =====================================================================================================
+#include <cuda_runtime.h>
+
+#define MMG_DEVICE __device__ __forceinline__
+#define MMG_HOST_DEVICE __host__ __device__ __forceinline__
+#define MMG_GLOBAL __global__
+#define MMG_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#define MMG_SHARED __shared__
+
+namespace mmg {
+
+MMG_DEVICE float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+MMG_DEVICE float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+MMG_DEVICE double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// sum over aligned groups of 16 lanes
+MMG_DEVICE float half_warp_sum(float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- mbarrier + TMA bulk copy (cp.async.bulk, SASS UBLKCP) ------------------------------------------
+MMG_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+MMG_DEVICE void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+MMG_DEVICE void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+MMG_DEVICE void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+MMG_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+MMG_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared bulk copy executed by the TMA unit; bytes % 16 == 0, both addresses 16-byte aligned
+MMG_DEVICE void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+// One thread stages `bytes` (multiple of 16) in <=32 KB pieces and arms the barrier with the total.
+MMG_DEVICE void tma_stage(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    mbar_expect_tx(bar, bytes);
+    const uint32_t kPiece = 32768;
+    for (uint32_t off = 0; off < bytes; off += kPiece) {
+        uint32_t n = bytes - off < kPiece ? bytes - off : kPiece;
+        tma_bulk_g2s((char*)smem_dst + off, (const char*)gmem_src + off, n, bar);
+    }
+}
+// Programmatic dependent launch: wait for the producer grid's memory to be visible / let dependents start.
+MMG_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+MMG_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+MMG_DEVICE float ldg(const float* p) { return __ldg(p); }
+MMG_DEVICE float4 ldg4(const float4* p) { return __ldg(p); }
+
+}  // namespace mmg
+
+#define MMG_SYNCTHREADS() __syncthreads()
+#define MMG_SYNCWARP() __syncwarp()
+
+#else
+// =====================================================================================================
+//                                   CPU emulation (tests only)
+// =====================================================================================================
+#include <algorithm>
+#include <atomic>
+#include <barrier>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+struct float4 {
+    float x, y, z, w;
+};
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+typedef void* cudaStream_t;
+typedef int cudaError_t;
+#define cudaSuccess 0
+
+#define MMG_DEVICE static inline
+#define MMG_HOST_DEVICE static inline
+#define MMG_GLOBAL static
+#define __launch_bounds__(...)
+#define __restrict__
+#define MMG_DYN_SMEM(name) unsigned char* name = mmg::emu::dyn_smem()
+#define MMG_SHARED static
+
+namespace mmg {
+namespace emu {
+struct BlockCtx {
+    std::barrier<>* block_bar;
+    std::vector<std::unique_ptr<std::barrier<>>>* warp_bars;
+    unsigned char* dyn;
+    double* shfl;  // [nthreads]
+};
+extern thread_local dim3 t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
+extern thread_local BlockCtx* t_ctx;
+unsigned char* dyn_smem();
+void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+void syncthreads();
+void syncwarp();
+double shfl_xor(double v, int lane_mask);
+}  // namespace emu
+}  // namespace mmg
+
+#define threadIdx (mmg::emu::t_threadIdx)
+#define blockIdx (mmg::emu::t_blockIdx)
+#define blockDim (mmg::emu::t_blockDim)
+#define gridDim (mmg::emu::t_gridDim)
+#define MMG_SYNCTHREADS() mmg::emu::syncthreads()
+#define MMG_SYNCWARP() mmg::emu::syncwarp()
+
+using std::max;
+using std::min;
+
+namespace mmg {
+MMG_DEVICE float warp_sum(float v) {
+    for (int o = 16; o > 0; o >>= 1) v += (float)emu::shfl_xor(v, o);
+    return v;
+}
+MMG_DEVICE float warp_max(float v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, (float)emu::shfl_xor(v, o));
+    return v;
+}
+MMG_DEVICE double warp_sum_d(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += emu::shfl_xor(v, o);
+    return v;
+}
+MMG_DEVICE float half_warp_sum(float v) {
+    for (int o = 8; o > 0; o >>= 1) v += (float)emu::shfl_xor(v, o);
+    return v;
+}
+MMG_DEVICE void mbar_init(uint64_t* bar, int) { *bar = 0; }
+MMG_DEVICE void mbar_fence_init() {}
+MMG_DEVICE void mbar_wait(uint64_t*, uint32_t) {}
+MMG_DEVICE void tma_stage(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t*) {
+    memcpy(smem_dst, gmem_src, bytes);
+}
+MMG_DEVICE void pdl_wait() {}
+MMG_DEVICE void pdl_launch_dependents() {}
+MMG_DEVICE float ldg(const float* p) { return *p; }
+MMG_DEVICE float4 ldg4(const float4* p) { return *p; }
+}  // namespace mmg
+#endif
+
+namespace mmg {
+MMG_HOST_DEVICE int cdiv(int a, int b) { return (a + b - 1) / b; }
+MMG_HOST_DEVICE int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+MMG_HOST_DEVICE int round_up(int a, int b) { return cdiv(a, b) * b; }
+MMG_HOST_DEVICE int64_t round_up64(int64_t a, int64_t b) { return cdiv64(a, b) * b; }
+
+MMG_DEVICE float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Philox4x32-10 counter-based generator (Salmon et al. 2011) for the on-device sampler.
+MMG_DEVICE void philox_round(uint32_t (&c)[4], uint32_t (&k)[2]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    const uint64_t p0 = (uint64_t)M0 * c[0], p1 = (uint64_t)M1 * c[2];
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    const uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
+}
+// 4 uniforms in (0,1) for counter (iter, a, b) under key `seed`
+MMG_DEVICE void philox_uniform4(uint64_t seed, uint64_t iter, uint32_t a, uint32_t b, float (&u)[4]) {
+    uint32_t c[4] = {(uint32_t)iter, (uint32_t)(iter >> 32), a, b};
+    uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    for (int i = 0; i < 10; ++i) philox_round(c, k);
+    for (int i = 0; i < 4; ++i) u[i] = ((float)(c[i] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+}
+}  // namespace mmg

@@ -1,0 +1,149 @@
+// K_pre — per-iteration pre-pass (one launch):
+//   role A (blocks [0, n_hx_tiles)): split-K tiles of the image-layer GEMM h_x = x . W_img^T (model.py:195).  x and
+//          W_img are loop invariant inside one conversation, so the reference's T recomputations collapse to one.
+//   role B (remaining blocks): (1) re-pack the loop weights from their state_dict layout into the kernel-layout
+//          images the exchange kernels stage into shared memory with TMA bulk copies; (2) the loop-invariant
+//          class halves  y1d = desc . y1.weight[:, Hr:]^T + y1.bias  and  wdd = desc . w_d.weight^T  (this is what
+//          removes build_inp's B*D x (Hr+WV) cartesian product, model.py:412,519-551); (3) the step-0 sender code
+//          term hw0 = code_layer(sigmoid(code_bias)) (model.py:199-200) and code_in[0] = sigmoid(code_bias).
+#pragma once
+#include "mmg_kernels.cuh"
+
+namespace mmg {
+
+MMG_DEVICE float packed_src(const float* W, int ld, int o, int r, int K) { return r < K ? ldg(W + (size_t)o * ld + r) : 0.f; }
+
+// value of fwd-image element e (sections produced by dot products are skipped by the caller)
+MMG_DEVICE float fwd_image_elem(const Dims& d, const FwdImage& im, const ParamPtrs& P, int e) {
+    if (e < im.wb) { int q = e - im.wc; int r = (q / (d.Hi * 4)) * 4 + (q & 3), o = (q >> 2) % d.Hi;
+        return packed_src(P.p[MMG_P_SEN_CODE_W], d.M, o, r, d.M); }
+    if (e < im.b_code) { int q = e - im.wb; int r = (q / (d.M * 4)) * 4 + (q & 3), o = (q >> 2) % d.M;
+        return packed_src(P.p[MMG_P_SEN_BIN_W], d.Hi, o, r, d.Hi); }
+    if (e < im.hw0) { int i = e - im.b_code; return i < d.Hi ? ldg(P.p[MMG_P_SEN_CODE_B] + i) : 0.f; }
+    if (e < im.b_b) return 0.f;  // hw0: dot role
+    if (e < im.sender_end) { int i = e - im.b_b; return i < d.M ? ldg(P.p[MMG_P_SEN_BIN_B] + i) : 0.f; }
+    if (e < im.whh) { int q = e - im.wih; int r = (q / (d.G3 * 4)) * 4 + (q & 3), o = (q >> 2) % d.G3;
+        return packed_src(P.p[MMG_P_REC_RNN_WIH], d.M, o, r, d.M); }
+    if (e < im.whead) { int q = e - im.whh; int r = (q / (d.G3 * 4)) * 4 + (q & 3), o = (q >> 2) % d.G3;
+        return packed_src(P.p[MMG_P_REC_RNN_WHH], d.Hr, o, r, d.Hr); }
+    if (e < im.ww) { int q = e - im.whead; int r = (q / (d.NH * 4)) * 4 + (q & 3), o = (q >> 2) % d.NH;
+        if (o < d.Hr) return packed_src(P.p[MMG_P_REC_Y1_W], d.Hr + d.WV, o, r, d.Hr);
+        if (o < 2 * d.Hr) return packed_src(P.p[MMG_P_REC_WH_W], d.Hr, o - d.Hr, r, d.Hr);
+        return packed_src(P.p[MMG_P_REC_S_W], d.Hr, 0, r, d.Hr); }
+    if (e < im.b_ih) { int q = e - im.ww; int r = (q / (d.M * 4)) * 4 + (q & 3), o = (q >> 2) % d.M;
+        return packed_src(P.p[MMG_P_REC_W_W], d.Hr, o, r, d.Hr); }
+    if (e < im.b_hh) { int i = e - im.b_ih; return i < d.G3 ? ldg(P.p[MMG_P_REC_RNN_BIH] + i) : 0.f; }
+    if (e < im.b_head) { int i = e - im.b_hh; return i < d.G3 ? ldg(P.p[MMG_P_REC_RNN_BHH] + i) : 0.f; }
+    if (e < im.w2) { int i = e - im.b_head;
+        if (i < d.Hr) return 0.f;
+        if (i < 2 * d.Hr) return ldg(P.p[MMG_P_REC_WH_B] + (i - d.Hr));
+        if (i == 2 * d.Hr) return ldg(P.p[MMG_P_REC_S_B]);
+        return 0.f; }
+    if (e < im.b_w) { int i = e - im.w2; return i < d.Hr ? ldg(P.p[MMG_P_REC_Y2_W] + i) : 0.f; }
+    if (e < im.misc) { int i = e - im.b_w; return i < d.M ? ldg(P.p[MMG_P_REC_W_B] + i) : 0.f; }
+    if (e < im.y1d) { int i = e - im.misc; return i == 0 ? ldg(P.p[MMG_P_REC_Y2_B]) : 0.f; }
+    return 0.f;  // y1d / wdd: dot role
+}
+
+MMG_DEVICE float bwd_image_elem(const Dims& d, const BwdImage& im, const ParamPtrs& P, int e) {
+    if (e < im.wwT) { int q = e - im.wbT; int r = (q / (d.Hi * 4)) * 4 + (q & 3), o = (q >> 2) % d.Hi;   // W(o=n, r=j) = bin_w[j][n]
+        return r < d.M ? ldg(P.p[MMG_P_SEN_BIN_W] + (size_t)r * d.Hi + o) : 0.f; }
+    if (e < im.headT) { int q = e - im.wwT; int r = (q / (d.Hr * 4)) * 4 + (q & 3), o = (q >> 2) % d.Hr;  // w_w[j][k]
+        return r < d.M ? ldg(P.p[MMG_P_REC_W_W] + (size_t)r * d.Hr + o) : 0.f; }
+    if (e < im.whhT) { int q = e - im.headT; int r = (q / (d.Hr * 4)) * 4 + (q & 3), o = (q >> 2) % d.Hr;
+        if (r < d.Hr) return ldg(P.p[MMG_P_REC_WH_W] + (size_t)r * d.Hr + o);
+        if (r < 2 * d.Hr) return ldg(P.p[MMG_P_REC_Y1_W] + (size_t)(r - d.Hr) * (d.Hr + d.WV) + o);
+        return 0.f; }
+    if (e < im.ws) { int q = e - im.whhT; int r = (q / (d.Hr * 4)) * 4 + (q & 3), o = (q >> 2) % d.Hr;
+        return r < d.G3 ? ldg(P.p[MMG_P_REC_RNN_WHH] + (size_t)r * d.Hr + o) : 0.f; }
+    if (e < im.w2) { int i = e - im.ws; return i < d.Hr ? ldg(P.p[MMG_P_REC_S_W] + i) : 0.f; }
+    if (e < im.y1d) { int i = e - im.w2; return i < d.Hr ? ldg(P.p[MMG_P_REC_Y2_W] + i) : 0.f; }
+    return 0.f;  // y1d: dot role
+}
+
+MMG_GLOBAL void __launch_bounds__(kGemmThreads)
+k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_kslice) {
+    MMG_SHARED __attribute__((aligned(16))) float As[kChunk * kLd];
+    MMG_SHARED __attribute__((aligned(16))) float Bs[kChunk * kLd];
+    const int tid = threadIdx.x;
+    if ((int)blockIdx.x < n_hx_tiles) {
+        // ---- role A: h_x split-K tile -------------------------------------------------------------------
+        const int ntn = cdiv(d.Hi, kTile), ntm = cdiv(d.B, kTile);
+        int t = blockIdx.x;
+        const int nt = t % ntn; t /= ntn;
+        const int mt = t % ntm; t /= ntm;
+        const int s = t;
+        Operand A = {in.x, nullptr, nullptr, nullptr, d.F, 0, 0, 0, 0, OP_PLAIN};
+        Operand Bo = {P.p[MMG_P_SEN_IMG_W], nullptr, nullptr, nullptr, d.F, 0, 0, 0, 0, OP_PLAIN};
+        float acc[4][4];
+        const int k0 = s * hx_kslice, k1 = min(d.F, k0 + hx_kslice);
+        gemm_tile(A, Bo, d.B, d.Hi, mt * kTile, nt * kTile, k0, k1, acc, nullptr, As, Bs);
+        const int tx = tid % 16, ty = tid / 16;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int b = mt * kTile + ty * 4 + a;
+            if (b >= d.B) continue;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int n = nt * kTile + tx * 4 + c;
+                if (n < d.Hi) W.hx_part[((size_t)s * d.B + b) * d.Hi + n] = acc[a][c];
+            }
+        }
+        return;
+    }
+    // ---- role B: images + class halves ------------------------------------------------------------------
+    const FwdImage fim = make_fwd_image(d);
+    const BwdImage bim = make_bwd_image(d);
+    const int nblk = gridDim.x - n_hx_tiles, blk = blockIdx.x - n_hx_tiles;
+    const int gthreads = nblk * kGemmThreads, gtid = blk * kGemmThreads + tid;
+    for (int e = gtid; e < fim.y1d; e += gthreads) {
+        if (e >= fim.hw0 && e < fim.b_b) continue;
+        W.fwd_image[e] = fwd_image_elem(d, fim, P, e);
+    }
+    for (int e = gtid; e < bim.y1d; e += gthreads) W.bwd_image[e] = bwd_image_elem(d, bim, P, e);
+    // dot role: one warp per output, lanes along the reduction
+    const int lane = tid & 31, gwarp = gtid >> 5, nwarps = gthreads >> 5;
+    const int n_y1d = d.D * d.Hr;
+    const int n_out = 2 * n_y1d + d.Hi + d.M;
+    const float* y1w = P.p[MMG_P_REC_Y1_W];
+    for (int o = gwarp; o < n_out; o += nwarps) {
+        if (o < n_y1d) {                       // y1d[dd][k] = y1.bias[k] + sum_v desc[dd][v] * y1.weight[k][Hr + v]
+            const int dd = o / d.Hr, k = o % d.Hr;
+            float s = 0.f;
+            for (int v = lane; v < d.WV; v += 32)
+                s = fmaf(ldg(in.desc + (size_t)dd * d.WV + v), ldg(y1w + (size_t)k * (d.Hr + d.WV) + d.Hr + v), s);
+            s = warp_sum(s);
+            if (lane == 0) {
+                s += ldg(P.p[MMG_P_REC_Y1_B] + k);
+                W.fwd_image[fim.y1d + o] = s;
+                W.bwd_image[bim.y1d + o] = s;
+            }
+        } else if (o < 2 * n_y1d) {            // wdd[dd][k] = sum_v desc[dd][v] * w_d.weight[k][v]
+            const int oo = o - n_y1d, dd = oo / d.Hr, k = oo % d.Hr;
+            float s = 0.f;
+            for (int v = lane; v < d.WV; v += 32)
+                s = fmaf(ldg(in.desc + (size_t)dd * d.WV + v), ldg(P.p[MMG_P_REC_WD_W] + (size_t)k * d.WV + v), s);
+            s = warp_sum(s);
+            if (lane == 0) W.fwd_image[fim.wdd + oo] = s;
+        } else if (o < 2 * n_y1d + d.Hi) {     // hw0[n] = code_layer.bias[n] + sum_j sigmoid(code_bias[j]) * code_layer.weight[n][j]
+            const int n = o - 2 * n_y1d;
+            float s = 0.f;
+            for (int j = lane; j < d.M; j += 32)
+                s = fmaf(sigmoidf_(ldg(P.p[MMG_P_SEN_CODE_BIAS] + j)), ldg(P.p[MMG_P_SEN_CODE_W] + (size_t)n * d.M + j), s);
+            s = warp_sum(s);
+            if (lane == 0) W.fwd_image[fim.hw0 + n] = s + ldg(P.p[MMG_P_SEN_CODE_B] + n);
+        } else {                               // code_in[0][b][j] = sigmoid(code_bias[j]) for every row b
+            const int j = o - 2 * n_y1d - d.Hi;
+            const float c0 = sigmoidf_(ldg(P.p[MMG_P_SEN_CODE_BIAS] + j));
+            for (int b = lane; b < d.B; b += 32) W.code_in[(size_t)b * d.M + j] = c0;
+        }
+    }
+    // pad tails of dot sections (keep the image fully defined for the bulk copies)
+    for (int e = gtid; e < fim.total; e += gthreads) {
+        if ((e >= fim.hw0 + d.Hi && e < fim.b_b) || (e >= fim.y1d + n_y1d && e < fim.wdd) || (e >= fim.wdd + n_y1d))
+            W.fwd_image[e] = 0.f;
+    }
+    for (int e = gtid + bim.y1d + n_y1d; e < bim.total; e += gthreads) W.bwd_image[e] = 0.f;
+}
+
+}  // namespace mmg

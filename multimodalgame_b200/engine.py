@@ -1,0 +1,207 @@
+"""GameEngine — owns the device buffers of one referential game (flat parameters / gradients / optimizer state /
+workspace) and drives the C-ABI entry points (include/mmg_b200.h).  PyTorch is used for device memory, streams and
+`torch.distributed` only; every tensor operation of the path runs in libmmg_b200.so.
+
+The reference keeps four `nn.Module`s and four `torch.optim` objects (model.py:1014-1142); here their parameters are
+views into one flat fp32 buffer so that clip + optimizer step is one kernel and a data-parallel run all-reduces one
+contiguous gradient buffer.
+"""
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import capi
+
+
+def make_config(batch, n_classes, img_feat_dim=4096, img_h_dim=100, baseline_hid_dim=500, sender_out_dim=50,
+                rec_hidden=128, rec_w_dim=50, wv_dim=100, max_exchange=3, fixed_exchange=True, use_binary=True,
+                entropy_s=None, entropy_sen=None, entropy_rec=None, first_rec=0.0, s_prob_prod=True,
+                learning_rate=1e-4, optim_type="RMSprop", ignore_receiver=False, batch_global=None, max_norm=1.0):
+    """Build the C config from reference flag names/defaults (model.py:1641-1741)."""
+    assert sender_out_dim == rec_w_dim, \
+        "Both sender and receiver should communicate with same dim vectors for now."   # model.py:1756
+    c = capi.Config()
+    c.batch = int(batch)
+    c.batch_global = int(batch_global if batch_global is not None else batch)
+    c.img_feat_dim, c.img_h_dim, c.msg_dim = int(img_feat_dim), int(img_h_dim), int(rec_w_dim)
+    c.rec_hidden, c.n_classes, c.wv_dim = int(rec_hidden), int(n_classes), int(wv_dim)
+    c.baseline_hid, c.max_exchange = int(baseline_hid_dim), int(max_exchange)
+    c.use_binary, c.fixed_exchange, c.s_prob_prod = int(bool(use_binary)), int(bool(fixed_exchange)), int(bool(s_prob_prod))
+    if optim_type not in capi.OPTIM:
+        raise NotImplementedError(optim_type)                                         # model.py:1137
+    c.optim_type = capi.OPTIM[optim_type]
+    c.has_entropy_s, c.entropy_s = int(entropy_s is not None), float(entropy_s or 0.0)
+    c.has_entropy_sen, c.entropy_sen = int(entropy_sen is not None), float(entropy_sen or 0.0)
+    c.has_entropy_rec, c.entropy_rec = int(entropy_rec is not None), float(entropy_rec or 0.0)
+    c.first_rec, c.learning_rate, c.max_norm = float(first_rec), float(learning_rate), float(max_norm)
+    c.ignore_receiver = int(bool(ignore_receiver))
+    return c
+
+
+def _is_vector(key):
+    return key.endswith("bias") or key.endswith("bias_ih") or key.endswith("bias_hh")
+
+
+class GameEngine(object):
+    def __init__(self, config, device=None, lib=None, seed=0):
+        self.lib = lib if lib is not None else capi.load()
+        self.cfg = config
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.layout = capi.ParamLayout()
+        self.lib.call("mmg_param_layout_get", C.byref(self.cfg), C.byref(self.layout))
+        self.wsl = capi.WorkspaceLayout()
+        self.lib.call("mmg_workspace_layout_get", C.byref(self.cfg), C.byref(self.wsl))
+        n = int(self.layout.total)
+        self.params = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.grads = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.state1 = torch.zeros(n, dtype=torch.float32, device=self.device)     # RMSprop square_avg / Adam exp_avg_sq
+        self.state2 = torch.zeros(n, dtype=torch.float32, device=self.device) if self.cfg.optim_type == 1 else None
+        self.workspace = torch.zeros(int(self.wsl.total_bytes), dtype=torch.uint8, device=self.device)
+        self.step = 0
+        self._keep = None
+        self.lib.call("mmg_workspace_init", C.byref(self.cfg), self.workspace.data_ptr(), C.c_uint64(seed), self._stream())
+        self._views = {}
+
+    # ---- plumbing ---------------------------------------------------------------------------------------------
+    def _stream(self):
+        if self.device.type == "cuda":
+            return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return C.c_void_p(0)
+
+    @property
+    def dims(self):
+        c = self.cfg
+        return dict(B=c.batch, F=c.img_feat_dim, Hi=c.img_h_dim, M=c.msg_dim, Hr=c.rec_hidden, D=c.n_classes,
+                    WV=c.wv_dim, Hb=c.baseline_hid, T=c.max_exchange)
+
+    def _flat_view(self, flat, idx):
+        off, rows, cols = int(self.layout.offset[idx]), int(self.layout.rows[idx]), int(self.layout.cols[idx])
+        v = flat[off:off + rows * cols]
+        agent, key = capi.PARAM_NAMES[idx]
+        return v if _is_vector(key) else v.view(rows, cols)
+
+    def named_views(self, flat=None):
+        """{agent: OrderedDict(state_dict key -> view into the flat buffer)} (reference key names)."""
+        flat = self.params if flat is None else flat
+        out = OrderedDict((a, OrderedDict()) for a in capi.SEGMENTS)
+        for idx, (agent, key) in enumerate(capi.PARAM_NAMES):
+            out[agent][key] = self._flat_view(flat, idx)
+        return out
+
+    def load_params(self, params):
+        """params: {agent: {key: tensor}} (e.g. four state_dicts)."""
+        views = self.named_views()
+        with torch.no_grad():
+            for agent in params:
+                for key, val in params[agent].items():
+                    views[agent][key].copy_(torch.as_tensor(val).to(self.device).reshape(views[agent][key].shape))
+
+    def ws(self, name, shape, dtype=torch.float32):
+        """Typed view of a named workspace array."""
+        k = (name, tuple(shape), dtype)
+        v = self._views.get(k)
+        if v is None:
+            off = int(getattr(self.wsl, name))
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+            v = self.workspace[off:off + nbytes].view(dtype).view(*shape)
+            self._views[k] = v
+        return v
+
+    def _inputs(self, x, desc, target, train, uniforms=None, corrupt_mask=None, h0=None, top_k=6):
+        dev = self.device
+        def prep(t, dtype):
+            if t is None:
+                return None
+            t = torch.as_tensor(t)
+            if t.dtype != dtype or t.device != dev or not t.is_contiguous():
+                t = t.to(device=dev, dtype=dtype).contiguous()
+            return t
+        keep = [prep(x, torch.float32), prep(desc, torch.float32), prep(target, torch.int64)]
+        us = [None, None, None]
+        if uniforms is not None:
+            us = [prep(u, torch.float64) for u in uniforms]
+        keep += us + [prep(corrupt_mask, torch.float32), prep(h0, torch.float32)]
+        d = self.dims
+        assert tuple(keep[0].shape) == (d["B"], d["F"]), (tuple(keep[0].shape), (d["B"], d["F"]))
+        assert tuple(keep[1].shape) == (d["D"], d["WV"]), tuple(keep[1].shape)
+        inp = capi.Inputs()
+        ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        inp.d_x, inp.d_desc, inp.d_target = ptr(keep[0]), ptr(keep[1]), ptr(keep[2])
+        inp.d_u_sen, inp.d_u_stop, inp.d_u_rec = ptr(keep[3]), ptr(keep[4]), ptr(keep[5])
+        inp.d_corrupt_mask, inp.d_h0 = ptr(keep[6]), ptr(keep[7])
+        inp.top_k, inp.train = int(top_k), int(bool(train))
+        self._keep = keep      # keep the tensors alive until the next call
+        return inp
+
+    # ---- the path ------------------------------------------------------------------------------------------------
+    def forward(self, x, desc, target=None, train=True, uniforms=None, corrupt_mask=None, h0=None, top_k=6):
+        self._inp = self._inputs(x, desc, target, train, uniforms, corrupt_mask, h0, top_k)
+        self.lib.call("mmg_exchange_forward", C.byref(self.cfg), self.params.data_ptr(), C.byref(self._inp),
+                      self.workspace.data_ptr(), self._stream())
+
+    def loss(self, phase=-1):
+        self.lib.call("mmg_loss", C.byref(self.cfg), self.params.data_ptr(), C.byref(self._inp),
+                      self.workspace.data_ptr(), int(phase), self._stream())
+
+    def backward(self):
+        self.lib.call("mmg_backward", C.byref(self.cfg), self.params.data_ptr(), C.byref(self._inp),
+                      self.workspace.data_ptr(), self.grads.data_ptr(), self._stream())
+
+    def grad_norm(self):
+        self.lib.call("mmg_grad_norm", C.byref(self.cfg), self.grads.data_ptr(), self.workspace.data_ptr(), self._stream())
+
+    def update(self):
+        self.step += 1
+        s2 = None if self.state2 is None else self.state2.data_ptr()
+        self.lib.call("mmg_clip_update", C.byref(self.cfg), self.params.data_ptr(), self.grads.data_ptr(),
+                      self.state1.data_ptr(), s2, C.c_int64(self.step), C.c_float(1.0), self.workspace.data_ptr(),
+                      self._stream())
+
+    def train_step(self, x, desc, target, uniforms=None, top_k=6):
+        """One fused training iteration (model.py:1240-1339) on device-resident inputs."""
+        self._inp = self._inputs(x, desc, target, True, uniforms, None, None, top_k)
+        self.step += 1
+        s2 = None if self.state2 is None else self.state2.data_ptr()
+        self.lib.call("mmg_train_step", C.byref(self.cfg), self.params.data_ptr(), self.grads.data_ptr(),
+                      self.state1.data_ptr(), s2, C.c_int64(self.step), C.byref(self._inp), self.workspace.data_ptr(),
+                      self._stream())
+
+    def train_step_dp(self, x, desc, target, group=None, uniforms=None, top_k=6):
+        """Data-parallel iteration: this rank's batch shard; batch statistics and gradients are all-reduced
+        (SURVEY.md §8e).  Two collectives per iteration: a few hundred doubles, then the flat gradient buffer."""
+        import torch.distributed as dist
+        self.forward(x, desc, target, True, uniforms, None, None, top_k)
+        self.loss(0)
+        dist.all_reduce(self.stats(), group=group)
+        self.loss(1)
+        self.backward()
+        dist.all_reduce(self.grads, group=group)
+        self.grad_norm()
+        self.update()
+
+    # ---- results -----------------------------------------------------------------------------------------------
+    def stats(self):
+        return self.ws("stats", (int(self.wsl.stats_count),), torch.float64)
+
+    def losses(self):
+        """dict of loss values (device->host copy; synchronises)."""
+        v = self.ws("losses", (capi.MMG_LOSS_COUNT,)).detach().cpu().tolist()
+        return dict(zip(capi.LOSS_NAMES, v))
+
+    def outputs(self):
+        """Views of everything `exchange()` returns (model.py:872-876), stacked over steps."""
+        d = self.dims
+        T, B, M, D, Hr, Hi = d["T"], d["B"], d["M"], d["D"], d["Hr"], d["Hi"]
+        return dict(
+            sen_feats=self.ws("sen_feats", (T, B, M)), sen_probs=self.ws("sen_probs", (T, B, M)),
+            rec_feats=self.ws("rec_feats", (T + 1, B, M))[1:], rec_probs=self.ws("rec_probs", (T, B, M)),
+            stop_feat=self.ws("stop_feat", (T, B, 1)), stop_prob=self.ws("stop_prob", (T, B, 1)),
+            y=self.ws("y", (T, B, D)), stop_mask=self.ws("stop_mask", (T + 1, B, 1), torch.uint8),
+            bs=self.ws("bs", (T, B, 1)), br=self.ws("br", (T, B, 1)), h_x=self.ws("h_x", (B, Hi)),
+            h_z=self.ws("h_z", (T + 1, B, Hr))[1:], h_w=self.ws("h_w", (T, B, Hr)),
+            outp=self.ws("outp", (B, D)), logs=self.ws("logs", (B, 1)), argmax=self.ws("argmax", (B,), torch.int32),
+            ystep=self.ws("ystep", (B,), torch.int32), grad_norms=self.ws("grad_norms", (4,)))

@@ -1,0 +1,255 @@
+"""Shared parity checker: drives a GameEngine (CUDA library on the GPU box; the CPU-emulated build of the same
+kernels in the build container) through the training iterations of a golden case and compares every output,
+loss, gradient and post-step parameter with the CPU oracle (oracle/game_oracle.py)."""
+import numpy as np
+import torch
+
+from multimodalgame_b200 import capi, engine as eng
+from oracle import game_oracle as go
+from tests import golden_util as gu
+
+
+def config_from(cfg, B=None, batch_global=None):
+    return eng.make_config(
+        batch=B or cfg.batch_size, n_classes=cfg.n_classes, img_feat_dim=cfg.img_feat_dim, img_h_dim=cfg.img_h_dim,
+        baseline_hid_dim=cfg.baseline_hid_dim, sender_out_dim=cfg.sender_out_dim, rec_hidden=cfg.rec_hidden,
+        rec_w_dim=cfg.rec_w_dim, wv_dim=cfg.wv_dim, max_exchange=cfg.max_exchange, fixed_exchange=cfg.fixed_exchange,
+        use_binary=cfg.use_binary, entropy_s=cfg.entropy_s, entropy_sen=cfg.entropy_sen, entropy_rec=cfg.entropy_rec,
+        first_rec=cfg.first_rec, s_prob_prod=cfg.s_prob_prod, learning_rate=cfg.learning_rate,
+        optim_type=cfg.optim_type, ignore_receiver=cfg.ignore_receiver, batch_global=batch_global)
+
+
+def stack_uniforms(us, cfg, B):
+    """list of per-step (u_z, u_s, u_w) -> three (T, B, .) float64 tensors, padded to max_exchange steps (the
+    reference stops drawing after an early break; the kernel runs every step, masked)."""
+    T, M = cfg.max_exchange, cfg.rec_w_dim
+    rng = np.random.RandomState(4242)
+    uz, us_, uw = [], [], []
+    for t in range(T):
+        a, b, c = us[t] if t < len(us) else (None, None, None)
+        uz.append(a if a is not None else rng.rand(B, M))
+        us_.append(b if b is not None else rng.rand(B, 1))
+        uw.append(c if c is not None else rng.rand(B, M))
+    f = lambda l: torch.from_numpy(np.ascontiguousarray(np.stack(l, 0)))
+    return f(uz), f(us_).reshape(T, B), f(uw)
+
+
+def assert_close(name, got, want, rtol=1e-4, atol=1e-4):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (name, got.shape, want.shape)
+    err = np.abs(got - want)
+    tol = atol + rtol * np.abs(want)
+    if not np.all(err <= tol):
+        i = np.unravel_index(np.argmax(err - tol), err.shape)
+        raise AssertionError("%s: max violation at %s got %.8g want %.8g (|err| %.3g, max|err| %.3g, %d/%d bad)" %
+                             (name, i, got[i], want[i], err[i], err.max(), int((err > tol).sum()), err.size))
+    return float(err.max()) if err.size else 0.0
+
+
+def check_margin(u, p, name, margin=2e-6):
+    """A sampled bit is only comparable if the uniform is not within rounding distance of the probability."""
+    gap = np.abs(np.asarray(u, np.float64) - np.asarray(p, np.float64)).min() if np.size(u) else 1.0
+    assert gap > margin, "%s: fixture has a uniform within %.1e of a probability (gap %.3g); pick another seed" % (
+        name, margin, gap)
+
+
+def run_train_case(case, lib, device, report=None, grad_rtol=2e-3):
+    """Returns dict of max errors.  `report` (list) receives human-readable lines."""
+    z, cfg = gu.load(case)
+    B = cfg.batch_size
+    params = gu.params_at(z, "P0")
+    oparams = go.clone_params(params)
+    ostate = go.new_opt_state(oparams)
+    e = eng.GameEngine(config_from(cfg), device=device, lib=lib)
+    e.load_params(params)
+    errs = {}
+    for it in range(int(z["iters"])):
+        x, desc, target = gu.batch_at(z, it)
+        us = gu.uniforms_at(z, it, cfg)
+        ex, res, grads = go.train_iteration(oparams, ostate, x, target, desc, cfg, us, return_grads=True)
+        Tp = len(ex["y"])     # steps the reference executed (early break)
+        uz, us_, uw = stack_uniforms(us, cfg, B)
+        e.forward(x, desc, target, train=True, uniforms=(uz, us_, uw), top_k=min(cfg.top_k_train, cfg.n_classes))
+        e.loss()
+        e.backward()
+        out = {k: v.detach().cpu().numpy() for k, v in e.outputs().items()}
+        tag = "%s/it%d/" % (case, it)
+        st = lambda key: np.stack([t.detach().numpy() for t in ex[key]], 0)
+        # --- forward: discrete outputs bit-exact, continuous within 1e-4 (north_star tolerance) ---
+        errs["h_x"] = assert_close(tag + "h_x", out["h_x"], ex["h_x"].detach().numpy())
+        if cfg.use_binary:
+            check_margin(uz[:Tp].numpy(), st("sen_probs"), tag + "u_z")
+            check_margin(uw[:Tp].numpy(), st("rec_probs"), tag + "u_w")
+            errs["sen_probs"] = assert_close(tag + "sen_probs", out["sen_probs"][:Tp], st("sen_probs"))
+            assert np.array_equal(out["sen_feats"][:Tp], st("sen_feats")), tag + "sen_feats bits differ"
+        else:
+            errs["sen_feats"] = assert_close(tag + "sen_feats", out["sen_feats"][:Tp], st("sen_feats"))
+        errs["h_z"] = assert_close(tag + "h_z", out["h_z"][:Tp], st("h_z"))
+        errs["stop_prob"] = assert_close(tag + "stop_prob", out["stop_prob"][:Tp], st("stop_prob"))
+        errs["y"] = assert_close(tag + "y", out["y"][:Tp], st("y"))
+        errs["h_w"] = assert_close(tag + "h_w", out["h_w"][:Tp], st("h_w"))
+        if cfg.use_binary:
+            errs["rec_probs"] = assert_close(tag + "rec_probs", out["rec_probs"][:Tp], st("rec_probs"))
+            assert np.array_equal(out["rec_feats"][:Tp], st("rec_feats")), tag + "rec_feats bits differ"
+        else:
+            errs["rec_feats"] = assert_close(tag + "rec_feats", out["rec_feats"][:Tp], st("rec_feats"))
+        check_margin(us_[:Tp].numpy().reshape(Tp, B, 1), st("stop_prob"), tag + "u_s")
+        assert np.array_equal(out["stop_feat"][:Tp], st("stop_feat")), tag + "stop bits differ"
+        # the reference forces the last mask to zero (model.py:870); the kernel keeps the raw chain
+        sm = st("stop_mask")
+        assert np.array_equal(out["stop_mask"][:Tp], sm[:Tp]), tag + "stop_mask chain differs"
+        errs["bs"] = assert_close(tag + "bs", out["bs"][:Tp], st("bs"))
+        errs["br"] = assert_close(tag + "br", out["br"][:Tp], st("br"))
+        # --- losses ---
+        assert np.array_equal(out["argmax"], res["argmax"].numpy()), tag + "argmax differs"
+        errs["outp"] = assert_close(tag + "outp", out["outp"], res["outp"].detach().numpy())
+        errs["logs"] = assert_close(tag + "logs", out["logs"], res["logs"].numpy())
+        L = e.losses()
+        for name in ("nll_loss", "loss_rec", "loss_sen", "loss_bas_rec", "loss_bas_sen", "loss_binary_s",
+                     "loss_binary_rec", "loss_binary_sen"):
+            if name in res:
+                errs[name] = assert_close(tag + name, L[name], float(res[name]), rtol=1e-4, atol=1e-4)
+        assert int(L["active_steps"]) == Tp, (tag, L["active_steps"], Tp)
+        assert abs(L["topk_correct"] / B - res["accuracy"]) < 1e-6, (tag, L["topk_correct"], res["accuracy"])
+        # --- gradients (pre-clip) against autograd of the oracle ---
+        gv = e.named_views(e.grads)
+        for a in grads:
+            gmax = max([float(g.abs().max()) for g in grads[a].values() if g is not None] + [1e-12])
+            for k, g in grads[a].items():
+                got = gv[a][k].detach().cpu().numpy()
+                if g is None:
+                    assert np.all(got == 0), tag + "grad %s.%s should be exactly zero" % (a, k)
+                    continue
+                if (a, k) == ("receiver", "y2.bias"):
+                    assert abs(float(got.reshape(-1)[0])) < 1e-5
+                    continue
+                errs["grad_" + a] = max(errs.get("grad_" + a, 0.0), assert_close(
+                    tag + "grad %s.%s" % (a, k), got, g.numpy(), rtol=grad_rtol, atol=2e-5 * gmax + 1e-9))
+        # --- clip + optimizer step ---
+        e.update()
+        gn = e.outputs()["grad_norms"].detach().cpu().numpy()
+        for i, a in enumerate(capi.SEGMENTS):
+            if a in res["grad_norms"]:
+                assert_close(tag + "grad_norm " + a, gn[i], res["grad_norms"][a], rtol=1e-3, atol=1e-6)
+        pv = e.named_views()
+        lr = cfg.learning_rate
+        for a in oparams:
+            for k, v in oparams[a].items():
+                got = pv[a][k].detach().cpu().numpy()
+                # RMSprop/Adam turn a tiny gradient difference into at most ~10*lr of parameter difference
+                # (see tests/test_oracle_golden.py on y2.bias); SGD is linear.
+                atol = 12 * lr * (it + 1) if (a, k) == ("receiver", "y2.bias") else 2e-2 * lr + 1e-7
+                if cfg.optim_type == "SGD":
+                    atol = lr * 1e-3 + 1e-7
+                elif a in grads and grads[a].get(k) is not None:
+                    # elements whose gradient is at rounding-noise level: the normalised step is noise too
+                    tiny = (grads[a][k].abs() < 1e-6).numpy()
+                    atol = np.where(tiny, 12 * lr * (it + 1), atol)
+                errs["param_" + a] = max(errs.get("param_" + a, 0.0), assert_close(
+                    tag + "param %s.%s" % (a, k), got, v.numpy(), rtol=1e-5, atol=atol))
+        # keep both trajectories glued together: continue from the oracle's parameters
+        e.load_params(oparams)
+        if report is not None:
+            report.append("%s it%d ok: %s" % (case, it, " ".join("%s=%.1e" % kv for kv in sorted(errs.items()))))
+    return errs
+
+
+def run_eval_case(case, lib, device):
+    """Eval-mode conversation (round(), running product of STOP probabilities, optional message corruption,
+    model.py:229,423-427,462,814-820) against the golden vectors produced by the reference."""
+    z, cfg = gu.load(case)
+    B = cfg.batch_size
+    params = gu.params_at(z, "P0")
+    e = eng.GameEngine(config_from(cfg), device=device, lib=lib)
+    e.load_params(params)
+    x, desc, target = torch.from_numpy(z["x"]), torch.from_numpy(z["desc"]), torch.from_numpy(z["target"])
+    region = str(z["corrupt_region"])
+    mask = None
+    if region:
+        mask = torch.zeros(cfg.rec_w_dim)
+        for r in region.split(","):
+            r = r.split(":")
+            idx = [int(r[0])] if len(r) == 1 else list(range(int(r[0]), int(r[1])))
+            mask[idx] = 1
+    e.forward(x, desc, target, train=False, corrupt_mask=mask)
+    out = {k: v.detach().cpu().numpy() for k, v in e.outputs().items()}
+    Tp = z["y"].shape[0]
+    # rounding decisions are only comparable away from p = 0.5
+    if cfg.use_binary:
+        assert np.abs(z["sen_probs"] - 0.5).min() > 1e-5 and np.abs(z["rec_probs"] - 0.5).min() > 1e-5
+        assert np.array_equal(out["sen_feats"][:Tp], z["sen_feats"]), case + " sen_feats"
+        assert np.array_equal(out["rec_feats"][:Tp], z["rec_feats"]), case + " rec_feats"
+        assert_close(case + " sen_probs", out["sen_probs"][:Tp], z["sen_probs"])
+        assert_close(case + " rec_probs", out["rec_probs"][:Tp], z["rec_probs"])
+    else:
+        assert_close(case + " sen_feats", out["sen_feats"][:Tp], z["sen_feats"])
+        assert_close(case + " rec_feats", out["rec_feats"][:Tp], z["rec_feats"])
+    assert np.array_equal(out["stop_feat"][:Tp], z["stop_feat"]), case + " stop_feat"
+    assert np.array_equal(out["stop_mask"][:Tp], z["stop_mask"][:Tp]), case + " stop_mask"
+    assert_close(case + " stop_prob", out["stop_prob"][:Tp], z["stop_prob"])
+    assert_close(case + " y", out["y"][:Tp], z["y"])
+    # prediction read at each example's stop step (model.py:648-654)
+    sm = out["stop_mask"][:, :, 0]
+    T = cfg.max_exchange
+    if cfg.fixed_exchange:
+        ystep = np.full(B, T - 1)
+    else:
+        ystep = np.array([next((t for t in range(T) if sm[t + 1, b] == 0), T - 1) for b in range(B)])
+    sel = out["y"][ystep, np.arange(B)]
+    assert_close(case + " outp", sel, z["outp"])
+
+
+def run_synth_case(cfg, lib, device, iters=1, seed=0, check_grads=True, tag="synth"):
+    """Synthetic inputs (oracle's init, N(0,1) features/descriptions) at arbitrary — including BASELINE.json's full —
+    sizes: fused `train_step` through the C-ABI vs the oracle, iteration by iteration."""
+    B = cfg.batch_size
+    params = go.init_params(cfg, seed=seed)
+    oparams = go.clone_params(params)
+    ostate = go.new_opt_state(oparams)
+    e = eng.GameEngine(config_from(cfg), device=device, lib=lib)
+    e.load_params(params)
+    rng = np.random.RandomState(seed)
+    worst = {}
+    for it in range(iters):
+        x, desc, target = go.synthetic_batch(cfg, seed=seed * 10 + it)
+        us = go.draw_uniforms(rng, cfg)
+        ex, res, grads = go.train_iteration(oparams, ostate, x, target, desc, cfg, us, return_grads=True)
+        Tp = len(ex["y"])
+        uz, us_, uw = stack_uniforms(us, cfg, B)
+        e.train_step(x, desc, target, uniforms=(uz, us_, uw), top_k=min(cfg.top_k_train, cfg.n_classes))
+        out = {k: v.detach().cpu().numpy() for k, v in e.outputs().items()}
+        st = lambda key: np.stack([t.detach().numpy() for t in ex[key]], 0)
+        t_ = "%s/it%d/" % (tag, it)
+        if cfg.use_binary:
+            check_margin(uz[:Tp].numpy(), st("sen_probs"), t_ + "u_z")
+            check_margin(uw[:Tp].numpy(), st("rec_probs"), t_ + "u_w")
+            assert np.array_equal(out["sen_feats"][:Tp], st("sen_feats")), t_ + "sen_feats bits differ"
+            assert np.array_equal(out["rec_feats"][:Tp], st("rec_feats")), t_ + "rec_feats bits differ"
+            worst["sen_probs"] = assert_close(t_ + "sen_probs", out["sen_probs"][:Tp], st("sen_probs"))
+            worst["rec_probs"] = assert_close(t_ + "rec_probs", out["rec_probs"][:Tp], st("rec_probs"))
+        check_margin(us_[:Tp].numpy().reshape(Tp, B, 1), st("stop_prob"), t_ + "u_s")
+        assert np.array_equal(out["stop_feat"][:Tp], st("stop_feat")), t_ + "stop bits differ"
+        assert np.array_equal(out["argmax"], res["argmax"].numpy()), t_ + "argmax differs"
+        worst["y"] = assert_close(t_ + "y", out["y"][:Tp], st("y"))
+        worst["h_x"] = assert_close(t_ + "h_x", out["h_x"], ex["h_x"].detach().numpy())
+        worst["bs"] = assert_close(t_ + "bs", out["bs"][:Tp], st("bs"))
+        worst["br"] = assert_close(t_ + "br", out["br"][:Tp], st("br"))
+        L = e.losses()
+        for name in ("nll_loss", "loss_rec", "loss_sen", "loss_bas_rec", "loss_bas_sen"):
+            worst[name] = assert_close(t_ + name, L[name], float(res[name].detach()), rtol=1e-4, atol=1e-4)
+        assert int(L["active_steps"]) == Tp
+        if check_grads:
+            gv = e.named_views(e.grads)
+            for a in grads:
+                nrm = res["grad_norms"][a]
+                coef = min(1.0, 1.0 / (nrm + 1e-6))           # e.grads holds the clipped gradient after the update
+                gmax = max([float(g.abs().max()) for g in grads[a].values() if g is not None] + [1e-12]) * coef
+                for k, g in grads[a].items():
+                    if g is None or (a, k) == ("receiver", "y2.bias"):
+                        continue
+                    worst["grad_" + a] = max(worst.get("grad_" + a, 0.0), assert_close(
+                        t_ + "grad %s.%s" % (a, k), gv[a][k].detach().cpu().numpy(), (g * coef).numpy(), rtol=2e-3,
+                        atol=3e-5 * gmax + 1e-9))
+        e.load_params(oparams)
+    return worst

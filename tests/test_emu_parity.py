@@ -1,0 +1,26 @@
+"""CPU (no GPU): the kernel sources compiled for the thread-per-OS-thread emulator (tests/emu) against the oracle.
+This checks kernel LOGIC (indexing, barrier structure, closed-form gradients) in the GPU-less build container;
+the real parity gate is tests/test_gpu_parity.py, which runs the same checks through the CUDA library."""
+import pytest
+
+from tests import emu_util, parity_util as pu
+
+CASES = ["fixed_small", "fixed_t1_noent", "continuous_t3", "adaptive_small", "adaptive_b1_adam", "adaptive_sgd"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_emulated_kernels_match_oracle(case):
+    pu.run_train_case(case, emu_util.emu_library(), "cpu")
+
+
+@pytest.mark.parametrize("case", ["eval_adaptive", "eval_adaptive_noprod", "eval_fixed_corrupt", "eval_continuous"])
+def test_emulated_eval_matches_reference_golden(case):
+    pu.run_eval_case(case, emu_util.emu_library(), "cpu")
+
+
+def test_emulated_synthetic_odd_dims():
+    from oracle import game_oracle as go
+    cfg = go.GameConfig(batch_size=7, img_feat_dim=131, img_h_dim=45, baseline_hid_dim=71, sender_out_dim=13,
+                        rec_hidden=27, rec_w_dim=13, wv_dim=19, n_classes=11, max_exchange=3, fixed_exchange=False,
+                        use_binary=True, entropy_s=0.05, entropy_sen=0.01, entropy_rec=0.02, top_k_train=2)
+    pu.run_synth_case(cfg, emu_util.emu_library(), "cpu", iters=2, seed=6, tag="odd")
