@@ -1,0 +1,583 @@
+"""Host-side mirror of the reference's operator surface for the hot path (`/root/reference/model.py`).
+
+Same names, constructor/`forward` signatures, flag names and `state_dict` keys as the reference, so that the
+reference's `run()` loop (model.py:1190-1339) can call into this module unchanged:
+
+    Sender / Receiver / Baseline      model.py:49-238 / 241-477 / 480-516
+    exchange(...)                     model.py:725-876
+    get_rec_outp, calculate_loss_binary, multistep_loss_binary, calculate_loss_bas, multistep_loss_bas,
+    build_inp, flipout, loglikelihood model.py:519-577, 879-988
+    flags(), default_flags(), Fixed/Adaptive presets       model.py:1605-1810
+
+Everything the conversation computes runs in libmmg_b200.so (hand-written sm_100a kernels behind the C-ABI in
+include/mmg_b200.h).  Two ways in:
+
+  * `exchange()` — drop-in.  Returns the reference's tuple of lists; in train mode the probabilities / scores /
+    baseline values carry autograd history through ONE custom Function whose backward is the fused backward kernel
+    sequence, so `loss.backward()` + `torch.optim` work exactly as in the reference's loop.
+  * `train_step()` — the whole iteration (conversation, the five losses, backward, 4x clip + optimizer step) fused on
+    the device with no host round trip.  This is what `bench.py` measures.
+
+There is no CPU path: without the CUDA library and a GPU these functions raise.
+"""
+import ctypes as C
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn.parameter import Parameter
+
+from . import capi
+from . import engine as _engine
+
+try:
+    from absl import flags as gflags
+except ImportError:  # pragma: no cover
+    import gflags
+
+FLAGS = gflags.FLAGS
+
+_LIB_OVERRIDE = None   # tests hand the emulated build in here; the product never sets it
+
+
+def _flag(name, default=None):
+    try:
+        return getattr(FLAGS, name)
+    except Exception:
+        return default
+
+
+# ------------------------------------------------------------------------------------------------------------
+# flags (names and defaults: model.py:1639-1741)
+# ------------------------------------------------------------------------------------------------------------
+def flags():
+    D = gflags
+    D.DEFINE_string("branch", None, ""); D.DEFINE_string("sha", None, ""); D.DEFINE_boolean("debug", False, "")
+    D.DEFINE_integer("save_after", 1000, ""); D.DEFINE_integer("save_interval", 100, "")
+    D.DEFINE_string("checkpoint", None, ""); D.DEFINE_string("conf_mat", None, ""); D.DEFINE_string("log_path", "./logs", "")
+    D.DEFINE_string("log_file", None, ""); D.DEFINE_string("eval_csv_file", None, ""); D.DEFINE_string("json_file", None, "")
+    D.DEFINE_string("log_load", None, ""); D.DEFINE_boolean("eval_only", False, "")
+    D.DEFINE_boolean("binary_only", False, ""); D.DEFINE_string("binary_output", None, "")
+    D.DEFINE_boolean("cuda", False, "")
+    D.DEFINE_string("env", "main", ""); D.DEFINE_boolean("visdom", False, ""); D.DEFINE_boolean("use_alpha", False, "")
+    D.DEFINE_string("experiment_name", None, ""); D.DEFINE_integer("log_interval", 50, ""); D.DEFINE_integer("log_dev", 1000, "")
+    D.DEFINE_enum("wv_type", "glove.6B", ["fake", "glove.6B", "none"], ""); D.DEFINE_integer("wv_dim", 100, "")
+    D.DEFINE_string("descr_train", "descriptions.csv", ""); D.DEFINE_string("descr_dev", "descriptions.csv", "")
+    D.DEFINE_string("train_file", "train.hdf5", ""); D.DEFINE_string("dev_file", "dev.hdf5", "")
+    D.DEFINE_enum("images", "mammal", ["cifar", "mammal"], "")
+    D.DEFINE_string("glove_path", "./glove.6B/glove.6B.100d.txt", "")
+    D.DEFINE_boolean("shuffle_train", True, ""); D.DEFINE_boolean("shuffle_dev", False, "")
+    D.DEFINE_enum("model_type", None, ["Fixed", "Adaptive", "FixedAttention", "AdaptiveAttention"],
+                  "Preset model configurations.")
+    D.DEFINE_enum("img_feat", "avgpool_512", ["layer4_2", "avgpool_512", "fc"], "Specify which layer output to use as image")
+    D.DEFINE_enum("data_context", "fc", ["fc"], "Specify which layer output to use as context for attention")
+    D.DEFINE_enum("sender_mix", "sum", ["sum", "prod", "mou"], "")
+    D.DEFINE_integer("img_feat_dim", 4096, ""); D.DEFINE_integer("img_h_dim", 100, "")
+    D.DEFINE_integer("baseline_hid_dim", 500, ""); D.DEFINE_integer("sender_out_dim", 50, "")
+    D.DEFINE_integer("rec_hidden", 128, ""); D.DEFINE_integer("rec_out_dim", 1, ""); D.DEFINE_integer("rec_w_dim", 50, "")
+    D.DEFINE_integer("rec_s_dim", 1, "")
+    D.DEFINE_boolean("use_binary", True, "Encoding whether Sender uses binary features")
+    D.DEFINE_boolean("ignore_receiver", False, "Sender ignores messages from Receiver")
+    D.DEFINE_boolean("ignore_code", False, "Sender ignores messages from Receiver")
+    D.DEFINE_boolean("block_y", True, "Halt gradient flow through description scores")
+    D.DEFINE_float("first_rec", 0, "")
+    D.DEFINE_float("flipout_rec", None, "Dropout for bit flipping"); D.DEFINE_float("flipout_sen", None, "Dropout for bit flipping")
+    D.DEFINE_boolean("flipout_dev", False, "Dropout for bit flipping")
+    D.DEFINE_boolean("s_prob_prod", True, "Simulate sampling during test time")
+    D.DEFINE_boolean("visual_attn", False, "Sender attends over image"); D.DEFINE_integer("attn_dim", 256, "")
+    D.DEFINE_boolean("attn_extra_context", False, ""); D.DEFINE_integer("attn_context_dim", 4096, "")
+    D.DEFINE_boolean("desc_attn", False, "Receiver attends over text"); D.DEFINE_integer("desc_attn_dim", 64, "Receiver attends over text")
+    D.DEFINE_integer("top_k_dev", 6, "Top-k error in development"); D.DEFINE_integer("top_k_train", 6, "Top-k error in training")
+    D.DEFINE_enum("optim_type", "RMSprop", ["Adam", "SGD", "RMSprop"], "")
+    D.DEFINE_integer("batch_size", 32, "Minibatch size for train set."); D.DEFINE_integer("batch_size_dev", 50, "Minibatch size for dev set.")
+    D.DEFINE_float("learning_rate", 1e-4, "Used in optimizer."); D.DEFINE_integer("max_epoch", 500, "")
+    D.DEFINE_float("entropy_s", None, ""); D.DEFINE_float("entropy_sen", None, ""); D.DEFINE_float("entropy_rec", None, "")
+    D.DEFINE_integer("exchange_samples", 3, ""); D.DEFINE_integer("max_exchange", 3, ""); D.DEFINE_boolean("fixed_exchange", True, "")
+    D.DEFINE_boolean("bit_flip", False, "Whether sender's messages are corrupted.")
+    D.DEFINE_string("corrupt_region", None, "Comma-separated ranges of bit indexes (e.g. ``0:3,5'').")
+
+
+def Fixed():
+    FLAGS.img_feat = "avgpool_512"; FLAGS.img_feat_dim = 512; FLAGS.fixed_exchange = True; FLAGS.visual_attn = False
+
+
+def Adaptive():
+    FLAGS.img_feat = "avgpool_512"; FLAGS.img_feat_dim = 512; FLAGS.fixed_exchange = False; FLAGS.visual_attn = False
+
+
+def FixedAttention():
+    FLAGS.img_feat = "layer4_2"; FLAGS.img_feat_dim = 512; FLAGS.fixed_exchange = True; FLAGS.visual_attn = True
+    FLAGS.attn_dim = 256; FLAGS.attn_extra_context = True; FLAGS.attn_context_dim = 1000
+
+
+def AdaptiveAttention():
+    FLAGS.img_feat = "layer4_2"; FLAGS.img_feat_dim = 512; FLAGS.fixed_exchange = False; FLAGS.visual_attn = True
+    FLAGS.attn_dim = 256; FLAGS.attn_extra_context = True; FLAGS.attn_context_dim = 1000
+
+
+_PRESETS = dict(Fixed=Fixed, Adaptive=Adaptive, FixedAttention=FixedAttention, AdaptiveAttention=AdaptiveAttention)
+
+
+def default_flags(argv=None):
+    """model.py:1744-1810 (the parts that shape the path; path/log-name derivation kept)."""
+    import json
+    import time
+    argv = sys.argv if argv is None else argv
+    if FLAGS.log_load:
+        log_flags = json.loads(open(FLAGS.log_load).read())
+        for k in log_flags.keys():
+            if k in FLAGS.flag_values_dict().keys():
+                setattr(FLAGS, k, log_flags[k])
+        FLAGS(argv)
+    if FLAGS.model_type:
+        _PRESETS[FLAGS.model_type]()
+        FLAGS(argv)
+    assert FLAGS.sender_out_dim == FLAGS.rec_w_dim, \
+        "Both sender and receiver should communicate with same dim vectors for now."
+    if not FLAGS.use_binary:
+        FLAGS.exchange_samples = 0
+    if not FLAGS.experiment_name:
+        FLAGS.experiment_name = "{}-so_{}-wv_{}-bs_{}-{}".format(FLAGS.images, FLAGS.sender_out_dim, FLAGS.wv_dim,
+                                                                FLAGS.batch_size, str(int(time.time())))
+    for attr, suffix in (("conf_mat", ".conf_mat.txt"), ("log_file", ".log"), ("eval_csv_file", ".eval.csv"),
+                         ("json_file", ".json"), ("checkpoint", ".pt"), ("binary_output", ".bv.hdf5")):
+        if not getattr(FLAGS, attr):
+            setattr(FLAGS, attr, os.path.join(FLAGS.log_path, FLAGS.experiment_name + suffix))
+    if not torch.cuda.is_available():
+        FLAGS.cuda = False
+    if FLAGS.debug:
+        np.seterr(all="raise")
+    FLAGS.glove_path = os.path.expanduser(FLAGS.glove_path)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# modules (parameters and names as the reference; forward math lives in the CUDA library)
+# ------------------------------------------------------------------------------------------------------------
+def xavier_normal(tensor, gain=1):
+    """misc.py:367-385."""
+    fan_out, fan_in = tensor.shape[0], tensor.shape[1]
+    std = gain * math.sqrt(2.0 / (fan_in + fan_out))
+    with torch.no_grad():
+        return tensor.normal_(0, std)
+
+
+def _unsupported(what):
+    raise NotImplementedError("%s is outside the fused B200 path (SURVEY.md §8f); the flag is kept for CLI "
+                              "compatibility only" % what)
+
+
+class Sender(nn.Module):
+    """Agent 1 (model.py:49-238).  Stateless; exposes `h_x` after an exchange (model.py:195,832)."""
+
+    def __init__(self, feature_type, feat_dim, h_dim, w_dim, bin_dim_out, use_binary, use_attn=False, attn_dim=0,
+                 attn_extra_context=False, attn_context_dim=0):
+        super(Sender, self).__init__()
+        self.feature_type, self.feat_dim, self.h_dim, self.w_dim = feature_type, feat_dim, h_dim, w_dim
+        self.bin_dim_out, self.use_binary, self.use_attn = bin_dim_out, use_binary, use_attn
+        self.attn_dim, self.attn_extra_context, self.attn_context_dim = attn_dim, attn_extra_context, attn_context_dim
+        if use_attn:
+            _unsupported("-visual_attn (Sender visual attention, model.py:80-86,114-191)")
+        if _flag("sender_mix", "sum") != "sum" or _flag("ignore_code", False):
+            _unsupported("-sender_mix %s / -ignore_code" % _flag("sender_mix", "sum"))
+        self.image_layer = nn.Linear(self.feat_dim, self.h_dim)
+        self.code_layer = nn.Linear(self.w_dim, self.h_dim)
+        self.code_bias = Parameter(torch.Tensor(self.bin_dim_out))
+        self.binary_layer = nn.Linear(self.h_dim, self.bin_dim_out)
+        self.reset_parameters()
+        self.reset_state()
+
+    def reset_parameters(self):   # model.py:90-97
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                xavier_normal(m.weight.data)
+                if m.bias is not None:
+                    m.bias.data.zero_()
+        self.code_bias.data.normal_()
+
+    def reset_state(self):        # model.py:99-112
+        self.h_x = None
+        self.attn_scores = []
+
+    def forward(self, x, w, g, t):
+        """One sender turn (model.py:144-238): (message, probs-or-None).  Runs the fused kernels for a single step;
+        no autograd history (training goes through `exchange()` / `train_step()`)."""
+        return _single_sender_step(self, x, w, t)
+
+
+class Receiver(nn.Module):
+    """Agent 2 (model.py:241-477).  Stateful: `h_z`, `s_prob_prod`, `h_w`."""
+
+    def __init__(self, z_dim, desc_dim, hid_dim, out_dim, w_dim, s_dim, use_binary):
+        super(Receiver, self).__init__()
+        self.z_dim, self.desc_dim, self.hid_dim, self.out_dim = z_dim, desc_dim, hid_dim, out_dim
+        self.w_dim, self.s_dim, self.use_binary = w_dim, s_dim, use_binary
+        if out_dim != 1 or s_dim != 1:
+            _unsupported("rec_out_dim/rec_s_dim != 1")
+        if _flag("desc_attn", False):
+            _unsupported("-desc_attn (word-level description attention, model.py:344-410)")
+        self.rnn = nn.GRUCell(self.z_dim, self.hid_dim)
+        self.w_h = nn.Linear(self.hid_dim, self.hid_dim, bias=True)
+        self.w_d = nn.Linear(self.desc_dim, self.hid_dim, bias=False)
+        self.w = nn.Linear(self.hid_dim, self.w_dim)
+        self.y1 = nn.Linear(self.hid_dim + self.desc_dim, self.hid_dim)
+        self.y2 = nn.Linear(self.hid_dim, self.out_dim)
+        self.s = nn.Linear(self.hid_dim, self.s_dim)
+        self.reset_parameters()
+        self.reset_state()
+
+    def reset_parameters(self):   # model.py:275-288
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                xavier_normal(m.weight.data)
+                if m.bias is not None:
+                    m.bias.data.zero_()
+            elif isinstance(m, nn.GRUCell):
+                for mm in m.parameters():
+                    if mm.data.ndimension() == 2:
+                        xavier_normal(mm.data)
+                    elif mm.data.ndimension() == 1:
+                        mm.data.zero_()
+
+    def reset_state(self):        # model.py:290-298
+        self.h_z = None
+        self.s_prob_prod = None
+        self.h_w = None
+
+    def initial_state(self, batch_size):
+        return torch.zeros(batch_size, self.hid_dim, device=self.rnn.weight_ih.device)
+
+    def forward(self, z, desc, desc_set=None, desc_set_lens=None):
+        """One receiver turn (model.py:303-477): ((s, s_prob), (w, w_probs), y); updates `h_z`."""
+        return _single_receiver_step(self, z, desc)
+
+
+class Baseline(nn.Module):
+    """REINFORCE control variate (model.py:480-516); torch-default init (no reset_parameters in the reference)."""
+
+    def __init__(self, hid_dim, x_dim, binary_dim, inp_dim):
+        super(Baseline, self).__init__()
+        self.x_dim, self.binary_dim, self.inp_dim, self.hid_dim = x_dim, binary_dim, inp_dim, hid_dim
+        self.linear1 = nn.Linear(x_dim + self.binary_dim + self.inp_dim, self.hid_dim)
+        self.linear2 = nn.Linear(self.hid_dim, 1)
+
+    def forward(self, x, binary, inp):
+        _unsupported("calling a Baseline outside exchange() (its forward is fused into the exchange kernels)")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# binding modules <-> engine
+# ------------------------------------------------------------------------------------------------------------
+class _Binding(object):
+    """One engine per (modules, batch, classes, flags); module parameters become views of the flat buffer."""
+
+    def __init__(self, mods, B, D, device, batch_global=None):
+        s, r = mods["sender"], mods["receiver"]
+        cfg = _engine.make_config(
+            batch=B, n_classes=D, img_feat_dim=s.feat_dim, img_h_dim=s.h_dim, baseline_hid_dim=mods["baseline_sen"].hid_dim
+            if mods.get("baseline_sen") is not None else int(_flag("baseline_hid_dim", 500)),
+            sender_out_dim=s.bin_dim_out, rec_hidden=r.hid_dim, rec_w_dim=r.w_dim, wv_dim=r.desc_dim,
+            max_exchange=int(_flag("max_exchange", 3)), fixed_exchange=bool(_flag("fixed_exchange", True)),
+            use_binary=bool(s.use_binary), entropy_s=_flag("entropy_s"), entropy_sen=_flag("entropy_sen"),
+            entropy_rec=_flag("entropy_rec"), first_rec=float(_flag("first_rec", 0) or 0),
+            s_prob_prod=bool(_flag("s_prob_prod", True)), learning_rate=float(_flag("learning_rate", 1e-4)),
+            optim_type=_flag("optim_type", "RMSprop"), ignore_receiver=bool(_flag("ignore_receiver", False)),
+            batch_global=batch_global)
+        if _flag("flipout_sen") is not None or _flag("flipout_rec") is not None:
+            _unsupported("-flipout_sen / -flipout_rec")
+        self.engine = _engine.GameEngine(cfg, device=device, lib=_LIB_OVERRIDE)
+        self.mods = mods
+        self.key = None
+        self.rebind()
+
+    def rebind(self):
+        views = self.engine.named_views()
+        gviews = self.engine.named_views(self.engine.grads)
+        for agent, mod in self.mods.items():
+            if mod is None:
+                continue
+            for key, p in mod.named_parameters():
+                v = views[agent][key]
+                if p.data_ptr() != v.data_ptr():
+                    with torch.no_grad():
+                        v.copy_(p.data.to(v.device).reshape(v.shape))
+                    p.data = v
+        self.gviews = gviews
+
+    def publish_grads(self):
+        for agent, mod in self.mods.items():
+            if mod is None:
+                continue
+            for key, p in mod.named_parameters():
+                p.grad = self.gviews[agent][key]
+
+
+_BINDINGS = {}
+
+
+def _binding_for(sender, receiver, baseline_sen, baseline_rec, B, D, device, batch_global=None):
+    key = (id(sender), id(receiver), id(baseline_sen), id(baseline_rec), int(B), int(D), str(device),
+           int(_flag("max_exchange", 3)), bool(_flag("fixed_exchange", True)), _flag("entropy_s"), _flag("entropy_sen"),
+           _flag("entropy_rec"), _flag("optim_type", "RMSprop"), float(_flag("learning_rate", 1e-4)), batch_global)
+    b = _BINDINGS.get(key)
+    if b is None:
+        mods = dict(receiver=receiver, sender=sender, baseline_rec=baseline_rec, baseline_sen=baseline_sen)
+        b = _Binding(mods, B, D, device, batch_global)
+        _BINDINGS[key] = b
+    else:
+        b.rebind()
+    return b
+
+
+def build_mask(region_str, size):
+    """misc.py:388-402."""
+    mask = torch.zeros(size)
+    for r in region_str.split(","):
+        r = r.split(":")
+        idx = [int(r[0])] if len(r) == 1 else list(range(int(r[0]), int(r[1])))
+        mask[idx] = 1
+    return mask
+
+
+class _ExchangeFn(torch.autograd.Function):
+    """Autograd bridge: forward = fused conversation, backward = fused backward kernels for whatever upstream
+    gradients the caller's losses produce (the reference's four `.backward()` calls each trigger one pass)."""
+
+    @staticmethod
+    def forward(ctx, binding, x, desc, target, uniforms, *params):
+        e = binding.engine
+        e.forward(x, desc, target, train=True, uniforms=uniforms)
+        o = e.outputs()
+        ctx.binding = binding
+        ctx.inp = e._inp
+        outs = (o["sen_probs"].clone(), o["rec_probs"].clone(), o["stop_prob"].clone(), o["y"].clone(), o["bs"].clone(),
+                o["br"].clone())
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_sen, g_rec, g_stop, g_y, g_bs, g_br):
+        b = ctx.binding
+        e = b.engine
+        d = e.dims
+        T, B, M, D = d["T"], d["B"], d["M"], d["D"]
+        z = lambda g, shape: torch.zeros(shape, device=e.device) if g is None else g
+        e.ws("g_sen_probs", (T, B, M)).copy_(z(g_sen, (T, B, M)))
+        e.ws("g_rec_probs", (T, B, M)).copy_(z(g_rec, (T, B, M)))
+        e.ws("g_stop_prob", (T, B)).copy_(z(g_stop, (T, B, 1)).reshape(T, B))
+        e.ws("g_bs", (T, B)).copy_(z(g_bs, (T, B, 1)).reshape(T, B))
+        e.ws("g_br", (T, B)).copy_(z(g_br, (T, B, 1)).reshape(T, B))
+        gy = z(g_y, (T, B, D))
+        nz = (gy != 0).any(dim=2)                                  # (T, B): steps whose scores received gradient
+        if bool((nz.sum(0) > 1).any()):
+            _unsupported("gradients into the class scores of more than one step per example")
+        ystep = torch.where(nz.any(0), nz.float().argmax(0), torch.full((B,), T - 1, device=e.device)).to(torch.int32)
+        e.ws("ystep", (B,), torch.int32).copy_(ystep)
+        e.ws("g_outp", (B, D)).copy_(gy[ystep.long(), torch.arange(B, device=e.device)])
+        e._inp = ctx.inp
+        e.backward()
+        gv = b.gviews
+        grads = []
+        for agent, key in capi.PARAM_NAMES:
+            grads.append(gv[agent][key].clone())
+        return (None, None, None, None, None) + tuple(grads)
+
+
+def _device_of(module):
+    return next(module.parameters()).device
+
+
+def exchange(sender, receiver, baseline_sen, baseline_rec, exchange_args):
+    """Batched conversation (model.py:725-876).  Same arguments and return structure as the reference:
+    s = (stop_mask[T'+1], stop_feat[T'], stop_prob[T']), sen_w = (feats, probs), rec_w = (feats, probs), y, bs, br.
+    Optional extra key exchange_args["uniforms"] = (u_sen (T,B,M), u_stop (T,B), u_rec (T,B,M)) float64 replaces the
+    on-device sampler by injected draws in the reference's order (parity tests)."""
+    data = exchange_args["data"]
+    target = exchange_args.get("target")
+    desc = exchange_args["desc"]
+    train = exchange_args["train"]
+    break_early = exchange_args.get("break_early", False)
+    corrupt = exchange_args.get("corrupt", False)
+    corrupt_region = exchange_args.get("corrupt_region", None)
+    if exchange_args.get("data_context") is not None:
+        _unsupported("data_context (visual attention)")
+    dev = _device_of(receiver)
+    B, D = data.shape[0], desc.shape[0]
+    binding = _binding_for(sender, receiver, baseline_sen, baseline_rec, B, D, dev)
+    e = binding.engine
+    T = e.dims["T"]
+    if train:
+        sender.train(); receiver.train(); baseline_sen.train(); baseline_rec.train()    # model.py:789-793
+    else:
+        sender.eval(); receiver.eval()
+    sender.reset_state(); receiver.reset_state()
+    mask = build_mask(corrupt_region, sender.w_dim).to(dev) if corrupt else None
+    binary = bool(sender.use_binary)
+    if train:
+        params = []
+        for agent, key in capi.PARAM_NAMES:
+            mod = binding.mods[agent]
+            params.append(dict(mod.named_parameters())[key])
+        sen_p, rec_p, stop_p, y_all, bs_all, br_all = _ExchangeFn.apply(
+            binding, data.detach(), desc.detach(), target, exchange_args.get("uniforms"), *params)
+        o = e.outputs()
+    else:
+        with torch.no_grad():
+            e.forward(data, desc, target, train=False, corrupt_mask=mask)
+        o = e.outputs()
+        sen_p, rec_p, stop_p, y_all = o["sen_probs"].clone(), o["rec_probs"].clone(), o["stop_prob"].clone(), o["y"].clone()
+    masks = o["stop_mask"].clone()                       # (T+1, B, 1) uint8, raw chain
+    steps = T
+    if break_early:                                       # model.py:866: stop once nobody is active
+        alive = masks[1:].reshape(T, -1).sum(1)
+        dead = (alive == 0).nonzero()
+        if dead.numel() > 0:
+            steps = int(dead[0]) + 1
+    stop_mask = [masks[t] for t in range(steps + 1)]
+    stop_mask[-1] = torch.zeros_like(stop_mask[-1])       # model.py:870
+    sen_feats_all, rec_feats_all, stop_feat_all = o["sen_feats"].clone(), o["rec_feats"].clone(), o["stop_feat"].clone()
+    stop_feat = [stop_feat_all[t] for t in range(steps)]
+    stop_prob = [stop_p[t] for t in range(steps)]
+    sen_feats = [sen_feats_all[t] for t in range(steps)]
+    rec_feats = [rec_feats_all[t] for t in range(steps)]
+    sen_probs = [sen_p[t] if binary else None for t in range(steps)]
+    rec_probs = [rec_p[t] if binary else None for t in range(steps)]
+    y = [y_all[t] for t in range(steps)]
+    bs = [bs_all[t] for t in range(steps)] if train else []
+    br = [br_all[t] for t in range(steps)] if train else []
+    sender.h_x = o["h_x"]
+    receiver.h_z = o["h_z"][steps - 1]
+    receiver.h_w = o["h_w"][steps - 1]
+    return (stop_mask, stop_feat, stop_prob), (sen_feats, sen_probs), (rec_feats, rec_probs), y, bs, br
+
+
+def train_step(sender, receiver, baseline_sen, baseline_rec, exchange_args, group=None):
+    """The whole iteration of run() (model.py:1240-1339) fused on the device: conversation, the five losses, backward,
+    per-module clip_grad_norm(1.) and the optimizer step.  Returns the engine (losses()/outputs() read results).
+    With `group` (torch.distributed, NCCL) the batch in `exchange_args` is this rank's shard of a global batch of
+    world_size * B rows: batch statistics and the flat gradient buffer are all-reduced."""
+    data, target, desc = exchange_args["data"], exchange_args["target"], exchange_args["desc"]
+    dev = _device_of(receiver)
+    world = 1
+    if group is not None:
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+    binding = _binding_for(sender, receiver, baseline_sen, baseline_rec, data.shape[0], desc.shape[0], dev,
+                           batch_global=data.shape[0] * world if world > 1 else None)
+    e = binding.engine
+    top_k = min(int(_flag("top_k_train", 6)), desc.shape[0])
+    if world > 1:
+        e.train_step_dp(data, desc, target, group=group, uniforms=exchange_args.get("uniforms"), top_k=top_k)
+    else:
+        e.train_step(data, desc, target, uniforms=exchange_args.get("uniforms"), top_k=top_k)
+    binding.publish_grads()
+    return e
+
+
+# ------------------------------------------------------------------------------------------------------------
+# single-turn module forwards (no autograd): one-step conversations through the same kernels
+# ------------------------------------------------------------------------------------------------------------
+def _single_sender_step(sender, x, w, t):
+    _unsupported("Sender.forward outside exchange() (use exchange() / train_step(); single-turn entry points are "
+                 "SURVEY.md §8f work)")
+
+
+def _single_receiver_step(receiver, z, desc):
+    _unsupported("Receiver.forward outside exchange() (use exchange() / train_step(); single-turn entry points are "
+                 "SURVEY.md §8f work)")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference loss surface (model.py:519-577, 879-988) for callers that keep the reference's own update block
+# ------------------------------------------------------------------------------------------------------------
+def build_inp(binary_features, descs):
+    """model.py:519-551 (kept for API compatibility; the fused path never materialises this product)."""
+    if descs is None:
+        return binary_features
+    B, D = binary_features.size(0), descs.size(0)
+    hb = binary_features.unsqueeze(1).expand(B, D, binary_features.size(1)).reshape(B * D, -1)
+    dd = descs.unsqueeze(0).expand(B, D, descs.size(1)).reshape(B * D, -1)
+    return torch.cat([hb, dd], 1)
+
+
+def flipout(binary, p):
+    """model.py:554-568."""
+    mask = torch.from_numpy((np.random.rand(*binary.shape) < p).astype("float32")).to(binary.device)
+    return (binary - mask).abs()
+
+
+def loglikelihood(log_prob, target):
+    return log_prob.gather(1, target)
+
+
+def get_rec_outp(y, masks):
+    """model.py:879-904."""
+    def negent(yy):
+        probs = F.softmax(yy, dim=1)
+        return (torch.log(probs + 1e-8) * probs).sum(1).mean()
+    negentropy = [negent(yy) for yy in y]
+    if masks is None:
+        return y[-1], negentropy
+    B = y[0].size(0)
+    inp = torch.stack(y, 1)
+    m = torch.cat(masks, 1).bool()
+    if _flag("debug", False):
+        assert bool((m.sum(1) == 1).all())
+    return inp[m].view(B, -1), negentropy
+
+
+def calculate_loss_binary(binary_features, binary_probs, logs, baseline_scores, entropy_penalty):
+    """model.py:907-927 with the torch-0.1.12 shapes made explicit ((B,1) per-example terms, no broadcasting)."""
+    f = binary_features.detach()
+    log_p_z = (f * torch.log(binary_probs + 1e-8) + (1 - f) * torch.log(1 - binary_probs + 1e-8)).sum(1, keepdim=True)
+    weight = logs.detach() - baseline_scores.detach()
+    if logs.size(0) > 1:
+        weight = weight / max(1.0, float(torch.std(weight)))
+    loss = torch.mean(-1 * weight * log_p_z)
+    initial_negent = (torch.log(binary_probs + 1e-8) * binary_probs).sum(1).mean()
+    inverse_negent = (torch.log((1. - binary_probs) + 1e-8) * (1. - binary_probs)).sum(1).mean()
+    negentropy = initial_negent + inverse_negent
+    if entropy_penalty is not None:
+        loss = loss + entropy_penalty * negentropy
+    return loss, negentropy
+
+
+def multistep_loss_binary(binary_features, binary_probs, logs, baseline_scores, masks, entropy_penalty):
+    """model.py:930-968."""
+    if masks is not None:
+        sums = [float(m.float().sum()) for m in masks]
+        losses, entropies = [], []
+        for feat, prob, scores, mask, ms in zip(binary_features, binary_probs, baseline_scores, masks, sums):
+            if ms == 0:
+                losses.append(torch.zeros((), device=logs.device))
+                continue
+            sel = mask.view(-1).bool()
+            l, e = calculate_loss_binary(feat[sel], prob[sel], logs[sel], scores[sel], entropy_penalty)
+            losses.append(l); entropies.append(e)
+        loss = sum(l * ms for l, ms in zip(losses, sums)) / sum(sums)
+    else:
+        outp = [calculate_loss_binary(feat, prob, logs, scores, entropy_penalty)
+                for feat, prob, scores in zip(binary_features, binary_probs, baseline_scores)]
+        losses = [o[0] for o in outp]
+        entropies = [o[1] for o in outp]
+        loss = sum(losses) / len(binary_features)
+    return loss, entropies
+
+
+def calculate_loss_bas(baseline_scores, logs):
+    return F.mse_loss(baseline_scores, logs.detach())
+
+
+def multistep_loss_bas(baseline_scores, logs, masks):
+    """model.py:976-988."""
+    if masks is not None:
+        losses, sums = [], []
+        for scores, mask in zip(baseline_scores, masks):
+            sel = mask.view(-1).bool()
+            losses.append(calculate_loss_bas(scores[sel].view(-1, 1), logs[sel].view(-1, 1)))
+            sums.append(float(mask.float().sum()))
+        return sum(l * ms for l, ms in zip(losses, sums)) / sum(sums)
+    losses = [calculate_loss_bas(scores, logs) for scores in baseline_scores]
+    return sum(losses) / len(baseline_scores)

@@ -200,10 +200,36 @@ def run_eval_case(case, lib, device):
     assert_close(case + " outp", sel, z["outp"])
 
 
+def _find_seed(cfg, seed, iters, margin=1e-6, tries=40):
+    """Sampled bits are only comparable when no injected uniform lies within rounding distance of its probability
+    (|u - p| > margin); with 1e5+ draws per iteration that needs a seed search.  Deterministic: first seed >= `seed`
+    whose ORACLE run keeps the margin."""
+    for s in range(seed, seed + tries):
+        params = go.init_params(cfg, seed=s)
+        state = go.new_opt_state(params)
+        rng = np.random.RandomState(s)
+        ok = True
+        for it in range(iters):
+            x, desc, target = go.synthetic_batch(cfg, seed=s * 10 + it)
+            us = go.draw_uniforms(rng, cfg)
+            ex, _ = go.train_iteration(params, state, x, target, desc, cfg, us)
+            for t in range(len(ex["y"])):
+                gaps = [np.abs(us[t][1] - ex["stop_prob"][t].detach().numpy()).min()]
+                if cfg.use_binary:
+                    gaps += [np.abs(us[t][0] - ex["sen_probs"][t].detach().numpy()).min(),
+                             np.abs(us[t][2] - ex["rec_probs"][t].detach().numpy()).min()]
+                if min(gaps) <= margin:
+                    ok = False
+        if ok:
+            return s
+    raise AssertionError("no seed with sampling margin found")
+
+
 def run_synth_case(cfg, lib, device, iters=1, seed=0, check_grads=True, tag="synth"):
     """Synthetic inputs (oracle's init, N(0,1) features/descriptions) at arbitrary — including BASELINE.json's full —
     sizes: fused `train_step` through the C-ABI vs the oracle, iteration by iteration."""
     B = cfg.batch_size
+    seed = _find_seed(cfg, seed, iters)
     params = go.init_params(cfg, seed=seed)
     oparams = go.clone_params(params)
     ostate = go.new_opt_state(oparams)
@@ -222,13 +248,13 @@ def run_synth_case(cfg, lib, device, iters=1, seed=0, check_grads=True, tag="syn
         st = lambda key: np.stack([t.detach().numpy() for t in ex[key]], 0)
         t_ = "%s/it%d/" % (tag, it)
         if cfg.use_binary:
-            check_margin(uz[:Tp].numpy(), st("sen_probs"), t_ + "u_z")
-            check_margin(uw[:Tp].numpy(), st("rec_probs"), t_ + "u_w")
+            check_margin(uz[:Tp].numpy(), st("sen_probs"), t_ + "u_z", 1e-6)
+            check_margin(uw[:Tp].numpy(), st("rec_probs"), t_ + "u_w", 1e-6)
             assert np.array_equal(out["sen_feats"][:Tp], st("sen_feats")), t_ + "sen_feats bits differ"
             assert np.array_equal(out["rec_feats"][:Tp], st("rec_feats")), t_ + "rec_feats bits differ"
             worst["sen_probs"] = assert_close(t_ + "sen_probs", out["sen_probs"][:Tp], st("sen_probs"))
             worst["rec_probs"] = assert_close(t_ + "rec_probs", out["rec_probs"][:Tp], st("rec_probs"))
-        check_margin(us_[:Tp].numpy().reshape(Tp, B, 1), st("stop_prob"), t_ + "u_s")
+        check_margin(us_[:Tp].numpy().reshape(Tp, B, 1), st("stop_prob"), t_ + "u_s", 1e-6)
         assert np.array_equal(out["stop_feat"][:Tp], st("stop_feat")), t_ + "stop bits differ"
         assert np.array_equal(out["argmax"], res["argmax"].numpy()), t_ + "argmax differs"
         worst["y"] = assert_close(t_ + "y", out["y"][:Tp], st("y"))
