@@ -3,10 +3,12 @@
 #include "mmg_pre.cuh"
 #include "mmg_exchange_fwd.cuh"
 #include "mmg_exchange_bwd.cuh"
+#include "mmg_fast.cuh"
 #include "mmg_loss.cuh"
 #include "mmg_update.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <stdarg.h>
 
 namespace mmg {
@@ -135,8 +137,14 @@ static void ws_layout(const Dims& d, Ws* w) {
     if (hs > kHxSplitMax) hs = kHxSplitMax;
     w->hx_split = hs;
     w->hx_part = take(c, (int64_t)hs * B * d.Hi * f);
-    w->fwd_image = take(c, (int64_t)make_fwd_image(d).total * f);
-    w->bwd_image = take(c, (int64_t)make_bwd_image(d).total * f);
+    int64_t fi = make_fwd_image(d).total, bi = make_bwd_image(d).total;
+    if (fast_dims(d)) {   // the fast-path images share the buffers
+        const int64_t ffi = make_fast_fwd_image(d.M, d.D).total, fbi = make_fast_bwd_image(d.M, d.D).total;
+        if (ffi > fi) fi = ffi;
+        if (fbi > bi) bi = fbi;
+    }
+    w->fwd_image = take(c, fi * f);
+    w->bwd_image = take(c, bi * f);
     w->d_lz = take(c, R * d.M * f);
     w->d_as = take(c, R * d.Hi * f);
     w->dhx = take(c, B * d.Hi * f);
@@ -155,6 +163,8 @@ static void ws_layout(const Dims& d, Ws* w) {
     w->wgrad_split = gs;
     w->slabs = take(c, (int64_t)gs * L.total * f);
     w->norm_part = take(c, 4 * kNormCtas * f);
+    w->loss_part = take(c, (int64_t)kLossCtasMax * 8 * 8);
+    w->tickets = take(c, 4 * 4);
     w->opt_counters = take(c, 4 * 8);
     p.total_bytes = c;
 }
@@ -178,6 +188,8 @@ static WsPtrs resolve(const Ws& w, void* base) {
     G_(hx_part); G_(fwd_image); G_(bwd_image); G_(d_lz); G_(d_as); G_(dhx); G_(dgi); G_(dgh); G_(d_lw); G_(d_hw);
     G_(d_ls); G_(g_h); G_(hsel); G_(dy1); G_(dw2p); G_(slabs); G_(norm_part);
 #undef G_
+    r.loss_part = (double*)(b + w.loss_part);
+    r.tickets = (unsigned*)(b + w.tickets);
     r.opt_counters = (long long*)(b + w.opt_counters);
     r.hx_split = w.hx_split; r.wgrad_split = w.wgrad_split; r.ntb = w.ntb;
     return r;
@@ -197,7 +209,7 @@ static ExchangeInputs resolve_inputs(const mmg_inputs* in) {
     return e;
 }
 
-struct Plan { int BT; int sender_smem; int fwd_smem_bytes; int bwd_smem_bytes; };
+struct Plan { int BT; int sender_smem; int fwd_smem_bytes; int bwd_smem_bytes; int fast; };
 
 static int choose_bt(int B) {
     if (B <= 148) return 1;
@@ -206,7 +218,36 @@ static int choose_bt(int B) {
     return 8;
 }
 
+static int g_force_generic = -1;   // MMG_FORCE_GENERIC=1 routes every shape through the generic kernels (tests)
+
+static bool make_fast_plan(const Dims& d, Plan* pl) {
+    if (g_force_generic < 0) {
+        const char* e = getenv("MMG_FORCE_GENERIC");
+        g_force_generic = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (g_force_generic || !fast_dims(d)) return false;
+    const FastFwdImage fi = make_fast_fwd_image(d.M, d.D);
+    const FastBwdImage bi = make_fast_bwd_image(d.M, d.D);
+    int bw_rec = (bi.total + fast_bwd_rec_state_floats(d.T, d.M, d.D)) * 4;
+    int bw_sen = fast_bwd_sen_state_floats(d.T, d.M) * 4;
+    pl->bwd_smem_bytes = bw_rec > bw_sen ? bw_rec : bw_sen;
+    if (pl->bwd_smem_bytes > kMaxSmem) return false;
+    int bt = d.B <= 148 ? 1 : (d.B <= 2 * 148 ? 2 : 4);
+    for (; bt >= 1; bt /= 2) {
+        const int st = fast_fwd_state_floats(bt, d.M, d.D);
+        const int full = (fi.total + st) * 4, recv_only = (fi.total - fi.sender_end + st) * 4;
+        if (d.M == 32 && full <= kMaxSmem) { pl->sender_smem = 1; pl->fwd_smem_bytes = full; break; }
+        if (recv_only <= kMaxSmem) { pl->sender_smem = 0; pl->fwd_smem_bytes = recv_only; break; }
+    }
+    if (bt < 1) return false;
+    pl->BT = bt;
+    pl->fast = 1;
+    return true;
+}
+
 static int make_plan(const Dims& d, Plan* pl) {
+    pl->fast = 0;
+    if (make_fast_plan(d, pl)) return MMG_OK;
     const FwdImage fi = make_fwd_image(d);
     const BwdImage bi = make_bwd_image(d);
     pl->BT = choose_bt(d.B);
@@ -255,6 +296,39 @@ static int launch_bwd(const Dims& d, const WsPtrs& W, const Plan& pl, cudaStream
     const int n_rec = cdiv(d.B, BT), n_sen = d.use_binary ? cdiv(d.B, BT) : 0;
     MMG_LAUNCH(k_exchange_bwd<BT>, n_rec + n_sen, kLoopThreads, pl.bwd_smem_bytes, st, d, W, n_rec);
     return check_cuda("k_exchange_bwd");
+}
+
+template <int BT, int M, bool SS>
+static int launch_fwd_fast_one(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const float* b_img, const Plan& pl,
+                               cudaStream_t st) {
+    auto kern = k_exchange_fwd_fast<BT, M, SS>;
+    int rc = set_smem(kern, pl.fwd_smem_bytes);
+    if (rc) return rc;
+    MMG_LAUNCH(kern, cdiv(d.B, BT), kFastThreads, pl.fwd_smem_bytes, st, d, W, in, b_img, 0);
+    return check_cuda("k_exchange_fwd_fast");
+}
+template <int M, bool SS>
+static int launch_fwd_fast_bt(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const float* b_img, const Plan& pl,
+                              cudaStream_t st) {
+    switch (pl.BT) {
+        case 1: return launch_fwd_fast_one<1, M, SS>(d, W, in, b_img, pl, st);
+        case 2: return launch_fwd_fast_one<2, M, SS>(d, W, in, b_img, pl, st);
+        default: return launch_fwd_fast_one<4, M, SS>(d, W, in, b_img, pl, st);
+    }
+}
+static int launch_fwd_fast(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const float* b_img, const Plan& pl,
+                           cudaStream_t st) {
+    if (d.M == 32) return pl.sender_smem ? launch_fwd_fast_bt<32, true>(d, W, in, b_img, pl, st)
+                                         : launch_fwd_fast_bt<32, false>(d, W, in, b_img, pl, st);
+    return launch_fwd_fast_bt<64, false>(d, W, in, b_img, pl, st);
+}
+template <int M>
+static int launch_bwd_fast_m(const Dims& d, const WsPtrs& W, const float* bin_w, const Plan& pl, cudaStream_t st) {
+    int rc = set_smem(k_exchange_bwd_fast<M>, pl.bwd_smem_bytes);
+    if (rc) return rc;
+    const int n_rec = d.B, n_sen = d.use_binary ? d.B : 0;
+    MMG_LAUNCH(k_exchange_bwd_fast<M>, n_rec + n_sen, kFastThreads, pl.bwd_smem_bytes, st, d, W, bin_w, n_rec);
+    return check_cuda("k_exchange_bwd_fast");
 }
 
 static void add_problem(WgTable& t, const Operand& A, const Operand& B, int M, int N, int K, long long c_off, int ldc,
@@ -414,11 +488,12 @@ int mmg_exchange_forward(const mmg_config* cfg, const float* d_params, const mmg
     const int n_hx = cdiv(d.B, kTile) * cdiv(d.Hi, kTile) * W.hx_split;
     const int hx_kslice = round_up(cdiv(d.F, W.hx_split), 4);
     const int n_pack = 64;
-    MMG_LAUNCH(k_pre, n_hx + n_pack, kGemmThreads, 0, st, d, P, W, ei, n_hx, hx_kslice);
+    MMG_LAUNCH(k_pre, n_hx + n_pack, kGemmThreads, 0, st, d, P, W, ei, n_hx, hx_kslice, pl.fast);
     if ((rc = check_cuda("k_pre"))) return rc;
     // K_exchange_fwd
     const float* b_img = P.p[MMG_P_SEN_IMG_B];
-    switch (pl.BT) {
+    if (pl.fast) rc = launch_fwd_fast(d, W, ei, b_img, pl, st);
+    else switch (pl.BT) {
         case 1: rc = launch_fwd<1>(d, W, ei, b_img, pl, st); break;
         case 2: rc = launch_fwd<2>(d, W, ei, b_img, pl, st); break;
         case 4: rc = launch_fwd<4>(d, W, ei, b_img, pl, st); break;
@@ -427,7 +502,8 @@ int mmg_exchange_forward(const mmg_config* cfg, const float* d_params, const mmg
     if (rc) return rc;
     if (in->train) {
         const int tiles = 2 * cdiv(d.R, kTile) * W.ntb;
-        MMG_LAUNCH(k_baseline_fwd, tiles, kGemmThreads, 0, st, d, P, W);
+        const int wd_tiles = pl.fast ? cdiv(d.R, kTile) * cdiv(d.WV, kTile) : 0;   // the generic kernel writes wd itself
+        MMG_LAUNCH(k_baseline_fwd, tiles + wd_tiles, kGemmThreads, 0, st, d, P, W, ei.desc, tiles);
         if ((rc = check_cuda("k_baseline_fwd"))) return rc;
     }
     return MMG_OK;
@@ -477,7 +553,9 @@ int mmg_backward(const mmg_config* cfg, const float* d_params, const mmg_inputs*
     const ParamPtrs P = param_ptrs(L, d_params);
     const ExchangeInputs ei = resolve_inputs(in);
     cudaStream_t st = (cudaStream_t)stream;
-    switch (pl.BT) {
+    if (pl.fast) rc = d.M == 32 ? launch_bwd_fast_m<32>(d, W, P.p[MMG_P_SEN_BIN_W], pl, st)
+                                : launch_bwd_fast_m<64>(d, W, P.p[MMG_P_SEN_BIN_W], pl, st);
+    else switch (pl.BT) {
         case 1: rc = launch_bwd<1>(d, W, pl, st); break;
         case 2: rc = launch_bwd<2>(d, W, pl, st); break;
         case 4: rc = launch_bwd<4>(d, W, pl, st); break;

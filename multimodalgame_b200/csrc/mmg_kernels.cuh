@@ -20,6 +20,8 @@ struct WsPtrs {               // resolved workspace arrays (device pointers)
     float *code_in, *a_s, *gates, *y1h, *q, *wd, *rowstat, *h1s, *h1r, *bs_part, *br_part;
     float *hx_part, *fwd_image, *bwd_image;
     float *d_lz, *d_as, *dhx, *dgi, *dgh, *d_lw, *d_hw, *d_ls, *g_h, *hsel, *dy1, *dw2p, *slabs, *norm_part;
+    double* loss_part;
+    unsigned* tickets;
     long long* opt_counters;
     int hx_split, wgrad_split, ntb;
 };

@@ -107,8 +107,80 @@ MMG_HOST_DEVICE BwdImage make_bwd_image(const Dims& d) {
     return im;
 }
 
+// ---- fast-path images (img_h_dim = 256, rec_hidden = 64, msg_dim in {32, 64}; mmg_fast.cuh) -------------------
+// Every matrix is stored in the order its consumer phase reads it: a warp's float4 loads are 512 contiguous bytes.
+enum { kFastThreads = 256, kFastHi = 256, kFastHr = 64, kFastMaxT = 32 };
+struct FastFwdImage {
+    int wc;      // code_layer.weight    [k4 < M/4][n < 256][4]
+    int wb;      // binary_layer.weight  row-major (M, 256): the state_dict layout
+    int b_code, hw0, b_b;
+    int sender_end;
+    int wih;     // rnn.weight_ih        [(g*(M/16) + q)][k < 64][part < 4][4],  column = part*(M/4) + 4q + c
+    int wfull;   // rows [y1.weight[:, :64] ; w_h.weight ; rnn.weight_hh[0:128]]  [k4 < 16][o < 256][4]
+    int wghn;    // rnn.weight_hh[128:192]  [q < 4][k < 64][part < 4][4],  column = part*16 + 4q + c
+    int ww;      // w.weight             [q][j < M][part < TPO][4],  TPO = 256/M, column = part*(64/TPO) + 4q + c
+    int b_ih;    // [192]
+    int b_full;  // [256]: 0 (y1.bias lives in y1d), w_h.bias, rnn.bias_hh[0:128]
+    int b_ghn;   // [64] rnn.bias_hh[128:192]
+    int ws;      // [64] s.weight
+    int b_w;     // [M]
+    int w2;      // [64] y2.weight
+    int misc;    // [4]: y2.bias, s.bias
+    int y1d;     // [D][64]   desc_d . y1.weight[:, 64:]^T + y1.bias
+    int wdd;     // [ceil(D/4)][64][4]   (desc_d . w_d.weight^T)[k] at ((d/4)*64 + k)*4 + d%4
+    int total;
+};
+MMG_HOST_DEVICE FastFwdImage make_fast_fwd_image(int M, int D) {
+    FastFwdImage im; int o = 0;
+    im.wc = o; o += M * kFastHi;
+    im.wb = o; o += M * kFastHi;
+    im.b_code = o; o += kFastHi;
+    im.hw0 = o; o += kFastHi;
+    im.b_b = o; o += M;
+    im.sender_end = o;
+    im.wih = o; o += 3 * M * kFastHr;
+    im.wfull = o; o += 256 * kFastHr;
+    im.wghn = o; o += kFastHr * kFastHr;
+    im.ww = o; o += M * kFastHr;
+    im.b_ih = o; o += 3 * kFastHr;
+    im.b_full = o; o += 256;
+    im.b_ghn = o; o += kFastHr;
+    im.ws = o; o += kFastHr;
+    im.b_w = o; o += M;
+    im.w2 = o; o += kFastHr;
+    im.misc = o; o += 4;
+    im.y1d = o; o += D * kFastHr;
+    im.wdd = o; o += ((D + 3) / 4) * 4 * kFastHr;
+    im.total = o;
+    return im;
+}
+struct FastBwdImage {
+    int wwT;     // w.weight^T            [j4 < M/4][k < 64][4]   element c = w.weight[4 j4 + c][k]
+    int whT;     // w_h.weight^T          [k4 < 16][k < 64][4]
+    int w1hT;    // y1.weight[:, :64]^T   [k4 < 16][k < 64][4]
+    int whhT;    // rnn.weight_hh^T       [q < 12][k < 64][part < 4][4]   element c = weight_hh[part*48 + 4q + c][k]
+    int ws, w2;  // [64] each
+    int y1d;     // [ceil(D/4)][64][4]
+    int total;
+};
+MMG_HOST_DEVICE FastBwdImage make_fast_bwd_image(int M, int D) {
+    FastBwdImage im; int o = 0;
+    im.wwT = o; o += M * kFastHr;
+    im.whT = o; o += kFastHr * kFastHr;
+    im.w1hT = o; o += kFastHr * kFastHr;
+    im.whhT = o; o += 3 * kFastHr * kFastHr;
+    im.ws = o; o += kFastHr;
+    im.w2 = o; o += kFastHr;
+    im.y1d = o; o += ((D + 3) / 4) * 4 * kFastHr;
+    im.total = o;
+    return im;
+}
+MMG_HOST_DEVICE bool fast_dims(const Dims& d) {
+    return d.Hi == kFastHi && d.Hr == kFastHr && (d.M == 32 || d.M == 64) && d.T <= kFastMaxT;
+}
+
 // ---- workspace ------------------------------------------------------------------------------------------
-enum { kHxSplitMax = 16, kWgradSplitMax = 8, kNormCtas = 128 };
+enum { kHxSplitMax = 16, kWgradSplitMax = 8, kNormCtas = 128, kLossCtasMax = 592 };
 enum { kStatKinds = 3 };  // 0: sender messages, 1: receiver messages, 2: stop bit
 // stats (double): per (kind, t): n, sum w, sum w^2 (w = logs - baseline); then per t: baseline_rec SSE,
 // baseline_sen SSE, n_mask; then scalars: nll_sum, topk_correct.
@@ -146,6 +218,8 @@ struct Ws {   // byte offsets into the workspace
     int64_t dw2p;      // (B,Hr)
     int64_t slabs;     // (kWgradSplitMax, P) split-K partial gradients
     int64_t norm_part; // (4, kNormCtas) per-CTA partial sums of squares
+    int64_t loss_part; // double (kLossCtasMax, 8) per-CTA loss partial sums, summed in CTA order by the last CTA
+    int64_t tickets;   // uint32[4] "last CTA done" counters (self-resetting)
     int64_t opt_counters; // int64[4]: [0] = number of updates that reached the receiver message head (Adam bias correction)
     int hx_split, wgrad_split, ntb;
 };

@@ -15,12 +15,32 @@
 namespace mmg {
 
 MMG_GLOBAL void __launch_bounds__(kGemmThreads)
-k_baseline_fwd(Dims d, ParamPtrs P, WsPtrs W) {
+k_baseline_fwd(Dims d, ParamPtrs P, WsPtrs W, const float* desc, int n_bas_tiles) {
     MMG_SHARED __attribute__((aligned(16))) float As[kChunk * kLd];
     MMG_SHARED __attribute__((aligned(16))) float Bs[kChunk * kLd];
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
     const int ntm = cdiv(d.R, kTile), ntn = W.ntb;
     int t = blockIdx.x;
+    if (t >= n_bas_tiles) {
+        // extra tiles (fast path): wd = q . desc for all T*B rows (model.py:442-449), saved for the w_d gradient
+        t -= n_bas_tiles;
+        const int nwv = cdiv(d.WV, kTile);
+        const int nt = t % nwv, mt = t / nwv;
+        const Operand A = Operand{W.q, nullptr, nullptr, nullptr, d.D, 0, 0, 0, 0, OP_PLAIN};
+        const Operand Bo = Operand{desc, nullptr, nullptr, nullptr, d.WV, 0, 1, 0, 0, OP_PLAIN};
+        float acc[4][4];
+        gemm_tile(A, Bo, d.R, d.WV, mt * kTile, nt * kTile, 0, d.D, acc, nullptr, As, Bs);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int r = mt * kTile + ty * 4 + a;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int v = nt * kTile + tx * 4 + c;
+                if (r < d.R && v < d.WV) W.wd[(size_t)r * d.WV + v] = acc[a][c];
+            }
+        }
+        return;
+    }
     const int which = t / (ntm * ntn);     // 0: baseline_sen, 1: baseline_rec
     t %= ntm * ntn;
     const int nt = t % ntn, mt = t / ntn;
@@ -199,7 +219,7 @@ MMG_GLOBAL void __launch_bounds__(kLossThreads)
 k_lossgrad(Dims d, mmg_config cfg, WsPtrs W) {
     MMG_DYN_SMEM(smem_raw);
     LossCoef* coef = reinterpret_cast<LossCoef*>(smem_raw);          // [3][T]
-    float* bas_scale = reinterpret_cast<float*>(coef + 3 * d.T);      // [2]: 2 / denominator for baseline MSE grads
+    float* bas_scale = reinterpret_cast<float*>(coef + 3 * d.T);      // [2]: 1 / denominator of the baseline MSE
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double* st = W.stats;
     for (int i = tid; i < 3 * d.T; i += kLossThreads) {
@@ -214,7 +234,9 @@ k_lossgrad(Dims d, mmg_config cfg, WsPtrs W) {
     }
     MMG_SYNCTHREADS();
     const bool binary = d.use_binary != 0;
-    // ---- upstream gradients, one warp per (t, b) row -------------------------------------------------------------
+    // ---- one warp per (t, b) row: upstream gradients + this row's share of every loss value ----------------------
+    // acc (lane 0): 0 binary_sen, 1 binary_rec, 2 binary_s, 3 bas_rec, 4 bas_sen — rank-local contributions
+    double acc[5] = {0, 0, 0, 0, 0};
     const int rows_per_cta = kLossThreads / 32;
     for (int row = blockIdx.x * rows_per_cta + warp; row < d.R; row += gridDim.x * rows_per_cta) {
         const int t = row / d.B, b = row % d.B;
@@ -227,17 +249,44 @@ k_lossgrad(Dims d, mmg_config cfg, WsPtrs W) {
             const float w0 = m_in ? (lg - bsv) * c0.cA : 0.f, e0 = m_in ? c0.cE : 0.f;
             const bool rec_on = m_out && (t < d.T - 1);
             const float w1 = rec_on ? (lg - brv) * c1.cA : 0.f, e1 = rec_on ? c1.cE : 0.f;
+            // log-likelihood and (neg)entropy sums of the two messages: the rows of calculate_loss_binary (model.py:907-921)
+            float lp0 = 0.f, hh0 = 0.f, lp1 = 0.f, hh1 = 0.f;
             for (int j = lane; j < d.M; j += 32) {
                 const size_t i = (size_t)row * d.M + j;
-                W.g_sen_probs[i] = m_in ? binary_grad(W.sen_probs[i], W.sen_feats[i], w0, e0) : 0.f;
-                W.g_rec_probs[i] = rec_on ? binary_grad(W.rec_probs[i], W.rec_feats[i + (size_t)d.B * d.M], w1, e1) : 0.f;
+                float gs = 0.f, gr = 0.f;
+                if (m_in) {
+                    const float p = W.sen_probs[i], f = W.sen_feats[i];
+                    const float l1 = logf(p + 1e-8f), l0 = logf(1.f - p + 1e-8f);
+                    lp0 += f * l1 + (1.f - f) * l0;
+                    hh0 += p * l1 + (1.f - p) * l0;
+                    gs = binary_grad(p, f, w0, e0);
+                }
+                if (rec_on) {
+                    const float p = W.rec_probs[i], f = W.rec_feats[i + (size_t)d.B * d.M];
+                    const float l1 = logf(p + 1e-8f), l0 = logf(1.f - p + 1e-8f);
+                    lp1 += f * l1 + (1.f - f) * l0;
+                    hh1 += p * l1 + (1.f - p) * l0;
+                    gr = binary_grad(p, f, w1, e1);
+                }
+                W.g_sen_probs[i] = gs;
+                W.g_rec_probs[i] = gr;
             }
+            lp0 = warp_sum(lp0); hh0 = warp_sum(hh0); lp1 = warp_sum(lp1); hh1 = warp_sum(hh1);
             if (lane == 0) {
                 float gs = 0.f;
-                if (!d.fixed && m_in) {
-                    const LossCoef c2 = coef[2 * d.T + t];
-                    gs = binary_grad(W.stop_prob[row], W.stop_feat[row], (lg - brv) * c2.cA, c2.cE);
+                if (m_in) {
+                    acc[0] += (double)(-(lg - bsv) * c0.cA) * lp0 + (double)c0.cE * hh0;
+                    if (!d.fixed) {
+                        const LossCoef c2 = coef[2 * d.T + t];
+                        const float sp = W.stop_prob[row], sf = W.stop_feat[row];
+                        const float l1 = logf(sp + 1e-8f), l0 = logf(1.f - sp + 1e-8f);
+                        acc[2] += (double)(-(lg - brv) * c2.cA) * (sf * l1 + (1.f - sf) * l0) + (double)c2.cE * (sp * l1 + (1.f - sp) * l0);
+                        gs = binary_grad(sp, sf, (lg - brv) * c2.cA, c2.cE);
+                    }
+                    acc[3] += (double)(brv - lg) * (double)(brv - lg) * bas_scale[0];
+                    acc[4] += (double)(bsv - lg) * (double)(bsv - lg) * bas_scale[0];
                 }
+                if (rec_on) acc[1] += (double)(-(lg - brv) * c1.cA) * lp1 + (double)c1.cE * hh1;
                 W.g_stop_prob[row] = gs;
                 W.g_bs[row] = m_in ? 2.f * (bsv - lg) * bas_scale[0] : 0.f;     // model.py:971-988
                 W.g_br[row] = m_in ? 2.f * (brv - lg) * bas_scale[0] : 0.f;
@@ -246,43 +295,37 @@ k_lossgrad(Dims d, mmg_config cfg, WsPtrs W) {
             W.g_stop_prob[row] = 0.f; W.g_bs[row] = 0.f; W.g_br[row] = 0.f;
         }
     }
-    // ---- loss values (CTA 0): rank-local contributions; their sum over ranks is the global loss ------------------
-    if (blockIdx.x != 0) return;
-    MMG_SHARED double red[8][kLossThreads / 32];
-    double acc[8];
-    for (int i = 0; i < 8; ++i) acc[i] = 0;
-    // acc: 0 nll, 1 binary_sen, 2 binary_rec, 3 binary_s, 4 bas_rec, 5 bas_sen, 6 topk
-    for (int b = tid; b < d.B; b += kLossThreads) acc[0] -= (double)W.logs[b] / (double)d.Bg;
-    if (binary) {
-        for (int row = tid; row < d.R; row += kLossThreads) {
-            const int t = row / d.B, b = row % d.B;
-            const float lg = W.logs[b];
-            const bool m_in = mask_at(d, W, t, b) != 0, m_out = mask_at(d, W, t + 1, b) != 0;
-            const float bsv = W.bs[row], brv = W.br[row];
-            if (m_in) {
-                const LossCoef c0 = coef[0 * d.T + t];
-                acc[1] += (double)(-(lg - bsv) * c0.cA) * W.rowstat[(size_t)0 * d.R + row] + (double)c0.cE * W.rowstat[(size_t)1 * d.R + row];
-                if (!d.fixed) {
-                    const LossCoef c2 = coef[2 * d.T + t];
-                    acc[3] += (double)(-(lg - brv) * c2.cA) * W.rowstat[(size_t)4 * d.R + row] + (double)c2.cE * W.rowstat[(size_t)5 * d.R + row];
-                }
-                acc[4] += (double)(brv - lg) * (double)(brv - lg) * bas_scale[0];
-                acc[5] += (double)(bsv - lg) * (double)(bsv - lg) * bas_scale[0];
-            }
-            if (m_out && t < d.T - 1) {
-                const LossCoef c1 = coef[1 * d.T + t];
-                acc[2] += (double)(-(lg - brv) * c1.cA) * W.rowstat[(size_t)2 * d.R + row] + (double)c1.cE * W.rowstat[(size_t)3 * d.R + row];
-            }
+    // ---- loss values: per-CTA partials, summed in CTA order by the last CTA to finish (deterministic) -------------
+    MMG_SHARED double red[5][kLossThreads / 32];
+    MMG_SHARED double nll_red[kLossThreads / 32];
+    MMG_SHARED int s_last;
+    if (lane == 0) for (int i = 0; i < 5; ++i) red[i][warp] = acc[i];
+    MMG_SYNCTHREADS();
+    if (tid == 0) {
+        for (int i = 0; i < 5; ++i) {
+            double v = 0;
+            for (int w = 0; w < kLossThreads / 32; ++w) v += red[i][w];
+            W.loss_part[(size_t)blockIdx.x * 8 + i] = v;
         }
+        s_last = (ticket_take(W.tickets) == gridDim.x - 1) ? 1 : 0;
     }
-    for (int i = 0; i < 6; ++i) {
-        const double v = warp_sum_d(acc[i]);
-        if (lane == 0) red[i][warp] = v;
-    }
+    MMG_SYNCTHREADS();
+    if (!s_last) return;
+    fence_acquire();
+    double nl = 0;
+    for (int b = tid; b < d.B; b += kLossThreads) nl -= (double)W.logs[b] / (double)d.Bg;
+    nl = warp_sum_d(nl);
+    if (lane == 0) nll_red[warp] = nl;
     MMG_SYNCTHREADS();
     if (tid == 0) {
         double v[6];
-        for (int i = 0; i < 6; ++i) { v[i] = 0; for (int w = 0; w < kLossThreads / 32; ++w) v[i] += red[i][w]; }
+        v[0] = 0;
+        for (int w = 0; w < kLossThreads / 32; ++w) v[0] += nll_red[w];
+        for (int i = 0; i < 5; ++i) {
+            double a = 0;
+            for (unsigned c = 0; c < gridDim.x; ++c) a += W.loss_part[(size_t)c * 8 + i];
+            v[i + 1] = a;
+        }
         float* L = W.losses;
         L[MMG_LOSS_NLL] = (float)v[0];
         L[MMG_LOSS_BINARY_SEN] = (float)v[1];
@@ -298,6 +341,7 @@ k_lossgrad(Dims d, mmg_config cfg, WsPtrs W) {
         L[MMG_LOSS_ACTIVE_STEPS] = (float)tp;
         if (st[stat_idx(d, 1, 0, 0)] > 0.0) W.opt_counters[0] += 1;   // updates seen by the receiver message head
         for (int i = MMG_LOSS_ACTIVE_STEPS + 1; i < MMG_LOSS_COUNT; ++i) L[i] = 0.f;
+        W.tickets[0] = 0;                                             // ready for the next launch
     }
 }
 

@@ -44,6 +44,21 @@ MMG_DEVICE float half_warp_sum(float v) {
     return v;
 }
 
+MMG_DEVICE float shfl_xor_f(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+// sum over aligned groups of N lanes (N power of two <= 32); every lane of the group receives the sum
+template <int N>
+MMG_DEVICE float group_sum(float v) {
+#pragma unroll
+    for (int o = N / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// "last CTA done" ticket: returns the number of CTAs that arrived before this one (release/acquire around it)
+MMG_DEVICE unsigned ticket_take(unsigned* counter) {
+    __threadfence();
+    return atomicAdd(counter, 1u);
+}
+MMG_DEVICE void fence_acquire() { __threadfence(); }
+
 // ---- mbarrier + TMA bulk copy (cp.async.bulk, SASS UBLKCP) ------------------------------------------
 MMG_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -178,6 +193,14 @@ MMG_DEVICE float half_warp_sum(float v) {
     for (int o = 8; o > 0; o >>= 1) v += (float)emu::shfl_xor(v, o);
     return v;
 }
+MMG_DEVICE float shfl_xor_f(float v, int m) { return (float)emu::shfl_xor(v, m); }
+template <int N>
+MMG_DEVICE float group_sum(float v) {
+    for (int o = N / 2; o > 0; o >>= 1) v += (float)emu::shfl_xor(v, o);
+    return v;
+}
+MMG_DEVICE unsigned ticket_take(unsigned* counter) { return __atomic_fetch_add(counter, 1u, __ATOMIC_SEQ_CST); }
+MMG_DEVICE void fence_acquire() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 MMG_DEVICE void mbar_init(uint64_t* bar, int) { *bar = 0; }
 MMG_DEVICE void mbar_fence_init() {}
 MMG_DEVICE void mbar_wait(uint64_t*, uint32_t) {}

@@ -7,7 +7,7 @@
 //          removes build_inp's B*D x (Hr+WV) cartesian product, model.py:412,519-551); (3) the step-0 sender code
 //          term hw0 = code_layer(sigmoid(code_bias)) (model.py:199-200) and code_in[0] = sigmoid(code_bias).
 #pragma once
-#include "mmg_kernels.cuh"
+#include "mmg_fast.cuh"
 
 namespace mmg {
 
@@ -62,7 +62,7 @@ MMG_DEVICE float bwd_image_elem(const Dims& d, const BwdImage& im, const ParamPt
 }
 
 MMG_GLOBAL void __launch_bounds__(kGemmThreads)
-k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_kslice) {
+k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_kslice, int fast) {
     MMG_SHARED __attribute__((aligned(16))) float As[kChunk * kLd];
     MMG_SHARED __attribute__((aligned(16))) float Bs[kChunk * kLd];
     const int tid = threadIdx.x;
@@ -94,13 +94,23 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
     // ---- role B: images + class halves ------------------------------------------------------------------
     const FwdImage fim = make_fwd_image(d);
     const BwdImage bim = make_bwd_image(d);
+    const FastFwdImage ffi = make_fast_fwd_image(d.M, d.D);
+    const FastBwdImage fbi = make_fast_bwd_image(d.M, d.D);
     const int nblk = gridDim.x - n_hx_tiles, blk = blockIdx.x - n_hx_tiles;
     const int gthreads = nblk * kGemmThreads, gtid = blk * kGemmThreads + tid;
-    for (int e = gtid; e < fim.y1d; e += gthreads) {
-        if (e >= fim.hw0 && e < fim.b_b) continue;
-        W.fwd_image[e] = fwd_image_elem(d, fim, P, e);
+    if (fast) {
+        for (int e = gtid; e < ffi.y1d; e += gthreads) {
+            if (e >= ffi.hw0 && e < ffi.b_b) continue;
+            W.fwd_image[e] = fast_fwd_image_elem(d, ffi, P, e);
+        }
+        for (int e = gtid; e < fbi.y1d; e += gthreads) W.bwd_image[e] = fast_bwd_image_elem(d, fbi, P, e);
+    } else {
+        for (int e = gtid; e < fim.y1d; e += gthreads) {
+            if (e >= fim.hw0 && e < fim.b_b) continue;
+            W.fwd_image[e] = fwd_image_elem(d, fim, P, e);
+        }
+        for (int e = gtid; e < bim.y1d; e += gthreads) W.bwd_image[e] = bwd_image_elem(d, bim, P, e);
     }
-    for (int e = gtid; e < bim.y1d; e += gthreads) W.bwd_image[e] = bwd_image_elem(d, bim, P, e);
     // dot role: one warp per output, lanes along the reduction
     const int lane = tid & 31, gwarp = gtid >> 5, nwarps = gthreads >> 5;
     const int n_y1d = d.D * d.Hr;
@@ -115,8 +125,13 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
             s = warp_sum(s);
             if (lane == 0) {
                 s += ldg(P.p[MMG_P_REC_Y1_B] + k);
-                W.fwd_image[fim.y1d + o] = s;
-                W.bwd_image[bim.y1d + o] = s;
+                if (fast) {
+                    W.fwd_image[ffi.y1d + o] = s;
+                    W.bwd_image[fbi.y1d + ((dd >> 2) * d.Hr + k) * 4 + (dd & 3)] = s;
+                } else {
+                    W.fwd_image[fim.y1d + o] = s;
+                    W.bwd_image[bim.y1d + o] = s;
+                }
             }
         } else if (o < 2 * n_y1d) {            // wdd[dd][k] = sum_v desc[dd][v] * w_d.weight[k][v]
             const int oo = o - n_y1d, dd = oo / d.Hr, k = oo % d.Hr;
@@ -124,21 +139,33 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
             for (int v = lane; v < d.WV; v += 32)
                 s = fmaf(ldg(in.desc + (size_t)dd * d.WV + v), ldg(P.p[MMG_P_REC_WD_W] + (size_t)k * d.WV + v), s);
             s = warp_sum(s);
-            if (lane == 0) W.fwd_image[fim.wdd + oo] = s;
+            if (lane == 0) {
+                if (fast) W.fwd_image[ffi.wdd + ((dd >> 2) * d.Hr + k) * 4 + (dd & 3)] = s;
+                else      W.fwd_image[fim.wdd + oo] = s;
+            }
         } else if (o < 2 * n_y1d + d.Hi) {     // hw0[n] = code_layer.bias[n] + sum_j sigmoid(code_bias[j]) * code_layer.weight[n][j]
             const int n = o - 2 * n_y1d;
             float s = 0.f;
             for (int j = lane; j < d.M; j += 32)
                 s = fmaf(sigmoidf_(ldg(P.p[MMG_P_SEN_CODE_BIAS] + j)), ldg(P.p[MMG_P_SEN_CODE_W] + (size_t)n * d.M + j), s);
             s = warp_sum(s);
-            if (lane == 0) W.fwd_image[fim.hw0 + n] = s + ldg(P.p[MMG_P_SEN_CODE_B] + n);
+            if (lane == 0) W.fwd_image[(fast ? ffi.hw0 : fim.hw0) + n] = s + ldg(P.p[MMG_P_SEN_CODE_B] + n);
         } else {                               // code_in[0][b][j] = sigmoid(code_bias[j]) for every row b
             const int j = o - 2 * n_y1d - d.Hi;
             const float c0 = sigmoidf_(ldg(P.p[MMG_P_SEN_CODE_BIAS] + j));
             for (int b = lane; b < d.B; b += 32) W.code_in[(size_t)b * d.M + j] = c0;
         }
     }
-    // pad tails of dot sections (keep the image fully defined for the bulk copies)
+    // pad tails of dot sections (keep the images fully defined for the bulk copies)
+    if (fast) {
+        const int dpad = ((d.D + 3) / 4) * 4;
+        for (int e = gtid; e < (dpad - d.D) * d.Hr; e += gthreads) {
+            const int dd = d.D + e / d.Hr, k = e % d.Hr;
+            W.fwd_image[ffi.wdd + ((dd >> 2) * d.Hr + k) * 4 + (dd & 3)] = 0.f;
+            W.bwd_image[fbi.y1d + ((dd >> 2) * d.Hr + k) * 4 + (dd & 3)] = 0.f;
+        }
+        return;
+    }
     for (int e = gtid; e < fim.total; e += gthreads) {
         if ((e >= fim.hw0 + d.Hi && e < fim.b_b) || (e >= fim.y1d + n_y1d && e < fim.wdd) || (e >= fim.wdd + n_y1d))
             W.fwd_image[e] = 0.f;

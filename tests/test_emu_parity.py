@@ -24,3 +24,14 @@ def test_emulated_synthetic_odd_dims():
                         rec_hidden=27, rec_w_dim=13, wv_dim=19, n_classes=11, max_exchange=3, fixed_exchange=False,
                         use_binary=True, entropy_s=0.05, entropy_sen=0.01, entropy_rec=0.02, top_k_train=2)
     pu.run_synth_case(cfg, emu_util.emu_library(), "cpu", iters=2, seed=6, tag="odd")
+
+
+@pytest.mark.parametrize("M,fixed,binary", [(32, False, True), (64, True, True), (32, True, False)])
+def test_emulated_fast_path_dims(M, fixed, binary):
+    """img_h_dim=256 / rec_hidden=64 / msg_dim in {32,64} route through the specialised kernels (mmg_fast.cuh)."""
+    from oracle import game_oracle as go
+    cfg = go.GameConfig(batch_size=3, img_feat_dim=40, img_h_dim=256, baseline_hid_dim=24, sender_out_dim=M,
+                        rec_hidden=64, rec_w_dim=M, wv_dim=12, n_classes=6, max_exchange=3, fixed_exchange=fixed,
+                        use_binary=binary, entropy_s=None if fixed else 0.05, entropy_sen=0.01, entropy_rec=0.02,
+                        top_k_train=2)
+    pu.run_synth_case(cfg, emu_util.emu_library(), "cpu", iters=2, seed=9, tag="fast%d" % M)
