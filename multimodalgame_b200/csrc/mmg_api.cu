@@ -46,7 +46,7 @@ static int validate(const mmg_config* c) {
         return fail(MMG_ERR_INVALID, "all dimensions must be >= 1");
     if (c->rec_hidden > 256) return fail(MMG_ERR_UNSUPPORTED, "rec_hidden=%d > 256 not supported by the fused path", c->rec_hidden);
     if (c->msg_dim > 256) return fail(MMG_ERR_UNSUPPORTED, "msg_dim=%d > 256 not supported by the fused path", c->msg_dim);
-    if (c->img_h_dim > 2 * kChunk * kLd) return fail(MMG_ERR_UNSUPPORTED, "img_h_dim=%d too large", c->img_h_dim);
+    if (c->img_h_dim > (int)kGemmSmemFloats * 64) return fail(MMG_ERR_UNSUPPORTED, "img_h_dim=%d too large", c->img_h_dim);
     if (c->optim_type < 0 || c->optim_type > 2) return fail(MMG_ERR_INVALID, "optim_type=%d", c->optim_type);
     if ((long long)c->max_exchange * c->batch > (1ll << 24)) return fail(MMG_ERR_UNSUPPORTED, "T*B too large");
     return MMG_OK;
@@ -157,12 +157,10 @@ static void ws_layout(const Dims& d, Ws* w) {
     w->hsel = take(c, B * d.Hr * f);
     w->dy1 = take(c, B * d.D * d.Hr * f);
     w->dw2p = take(c, B * d.Hr * f);
-    int gs = (int)(R / 160);
-    if (gs < 1) gs = 1;
-    if (gs > kWgradSplitMax) gs = kWgradSplitMax;
-    w->wgrad_split = gs;
-    w->slabs = take(c, (int64_t)gs * L.total * f);
-    w->norm_part = take(c, 4 * kNormCtas * f);
+    w->dcode_part = take(c, B * d.M * f);
+    w->wgrad_split = kWgradSplitMax;
+    w->slabs = take(c, (int64_t)(kWgradSplitMax - 1) * L.total * f);
+    w->norm_part = take(c, 4 * kNormCtasMax * f);
     w->loss_part = take(c, (int64_t)kLossCtasMax * 8 * 8);
     w->tickets = take(c, 4 * 4);
     w->opt_counters = take(c, 4 * 8);
@@ -186,7 +184,7 @@ static WsPtrs resolve(const Ws& w, void* base) {
 #define G_(name) r.name = (float*)(b + w.name)
     G_(code_in); G_(a_s); G_(gates); G_(y1h); G_(q); G_(wd); G_(rowstat); G_(h1s); G_(h1r); G_(bs_part); G_(br_part);
     G_(hx_part); G_(fwd_image); G_(bwd_image); G_(d_lz); G_(d_as); G_(dhx); G_(dgi); G_(dgh); G_(d_lw); G_(d_hw);
-    G_(d_ls); G_(g_h); G_(hsel); G_(dy1); G_(dw2p); G_(slabs); G_(norm_part);
+    G_(d_ls); G_(g_h); G_(hsel); G_(dy1); G_(dw2p); G_(dcode_part); G_(slabs); G_(norm_part);
 #undef G_
     r.loss_part = (double*)(b + w.loss_part);
     r.tickets = (unsigned*)(b + w.tickets);
@@ -323,71 +321,111 @@ static int launch_fwd_fast(const Dims& d, const WsPtrs& W, const ExchangeInputs&
     return launch_fwd_fast_bt<64, false>(d, W, in, b_img, pl, st);
 }
 template <int M>
-static int launch_bwd_fast_m(const Dims& d, const WsPtrs& W, const float* bin_w, const Plan& pl, cudaStream_t st) {
+static int launch_bwd_fast_m(const Dims& d, const WsPtrs& W, const float* bin_w, const float* code_w, const Plan& pl,
+                             cudaStream_t st) {
     int rc = set_smem(k_exchange_bwd_fast<M>, pl.bwd_smem_bytes);
     if (rc) return rc;
     const int n_rec = d.B, n_sen = d.use_binary ? d.B : 0;
-    MMG_LAUNCH(k_exchange_bwd_fast<M>, n_rec + n_sen, kFastThreads, pl.bwd_smem_bytes, st, d, W, bin_w, n_rec);
+    MMG_LAUNCH(k_exchange_bwd_fast<M>, n_rec + n_sen, kFastThreads, pl.bwd_smem_bytes, st, d, W, bin_w, code_w, n_rec);
     return check_cuda("k_exchange_bwd_fast");
 }
 
-static void add_problem(WgTable& t, const Operand& A, const Operand& B, int M, int N, int K, long long c_off, int ldc,
-                        long long bias_off, int kind) {
-    WgProblem& p = t.p[t.count++];
-    p.A = A; p.B = B; p.M = M; p.N = N; p.K = K; p.c_off = c_off; p.ldc = ldc; p.bias_off = bias_off; p.kind = kind;
-    p.ntm = cdiv(M, kTile);
-    p.ntn = kind == WG_GEMM ? cdiv(N, kTile) : 1;
-    p.tile_begin = t.total_tiles;
-    t.total_tiles += p.ntm * p.ntn * t.nsplit;
-}
-
 static Operand km(const float* p, int ld) { return Operand{p, nullptr, nullptr, nullptr, ld, 0, 1, 0, 0, OP_PLAIN}; }
+static Operand ones() { return Operand{nullptr, nullptr, nullptr, nullptr, 0, 0, 1, 0, 0, OP_ONES}; }
+
+struct WgBuilder {
+    WgTable* t;
+    SplitTable* st;
+    const mmg_param_layout* L;
+    int w_id[kMaxWgProblems], b_id[kMaxWgProblems];
+    // C (M x N) = A^T B goes to tensor `w_id` at column offset `col`; colsum(A) (optional) to tensor `b_id`
+    void add(const Operand& A, const Operand& B, int M, int N, int K, int wid, int col, int bid, int kind = WG_GEMM,
+             const float* sig_rows = nullptr) {
+        WgProblem& p = t->p[t->count];
+        w_id[t->count] = wid; b_id[t->count] = bid;
+        ++t->count;
+        p.A = A; p.B = B; p.M = M; p.N = N; p.K = K;
+        p.c_off = L->offset[wid] + col; p.ldc = N == 1 ? 1 : L->cols[wid];   // N == 1: column sums land contiguously
+        p.bias_off = bid >= 0 ? L->offset[bid] : -1;
+        p.sig_rows = sig_rows; p.kind = kind;
+        int ns = kind == WG_GEMM ? cdiv(K, kWgradKSlice) : 1;
+        if (ns < 1) ns = 1;
+        if (ns > kWgradSplitMax) ns = kWgradSplitMax;
+        if (ns > st->nsplit[wid]) st->nsplit[wid] = ns;
+    }
+    void finish() {
+        t->total_tiles = 0;
+        for (int i = 0; i < t->count; ++i) {
+            WgProblem& p = t->p[i];
+            p.nsplit = st->nsplit[w_id[i]];                  // problems sharing a tensor share its split factor
+            if (b_id[i] >= 0) st->nsplit[b_id[i]] = p.nsplit;
+            p.ntm = cdiv(p.M, kTile);
+            p.ntn = p.kind == WG_GEMM ? cdiv(p.N, kTile) : 1;
+            p.tile_begin = t->total_tiles;
+            t->total_tiles += p.ntm * p.ntn * p.nsplit;
+        }
+    }
+};
 
 static void build_wgrad_table(const Dims& d, const mmg_param_layout& L, const ParamPtrs& P, const WsPtrs& W,
-                              const ExchangeInputs& in, WgTable* t) {
-    t->count = 0; t->total_tiles = 0; t->nsplit = W.wgrad_split; t->slab_stride = L.total;
+                              const ExchangeInputs& in, int fast, WgTable* t, SplitTable* st) {
+    t->count = 0; t->total_tiles = 0; t->slab_stride = L.total;
+    for (int i = 0; i < MMG_P_COUNT; ++i) {
+        st->begin[i] = L.offset[i]; st->numel[i] = L.rows[i] * L.cols[i]; st->nsplit[i] = 1;
+    }
+    st->begin[MMG_P_COUNT] = L.total;
+    WgBuilder b{t, st, &L, {}, {}};
     const int R = d.R, B = d.B, Hr = d.Hr, M = d.M, Hi = d.Hi;
     const float* h_after = W.h_z + (size_t)B * Hr;       // h_z after step t, row-aligned with (t, b)
     // receiver
-    add_problem(*t, km(W.dgi, d.G3), km(W.sen_feats, M), d.G3, M, R, L.offset[MMG_P_REC_RNN_WIH], M, L.offset[MMG_P_REC_RNN_BIH], WG_GEMM);
-    add_problem(*t, km(W.dgh, d.G3), km(W.h_z, Hr), d.G3, Hr, R, L.offset[MMG_P_REC_RNN_WHH], Hr, L.offset[MMG_P_REC_RNN_BHH], WG_GEMM);
-    add_problem(*t, km(W.d_lw, M), km(W.h_w, Hr), M, Hr, R, L.offset[MMG_P_REC_W_W], Hr, L.offset[MMG_P_REC_W_B], WG_GEMM);
-    add_problem(*t, km(W.d_hw, Hr), km(h_after, Hr), Hr, Hr, R, L.offset[MMG_P_REC_WH_W], Hr, L.offset[MMG_P_REC_WH_B], WG_GEMM);
-    add_problem(*t, km(W.d_hw, Hr), km(W.wd, d.WV), Hr, d.WV, R, L.offset[MMG_P_REC_WD_W], d.WV, -1, WG_GEMM);
-    add_problem(*t, km(W.d_ls, 1), km(h_after, Hr), 1, Hr, R, L.offset[MMG_P_REC_S_W], Hr, L.offset[MMG_P_REC_S_B], WG_GEMM);
-    add_problem(*t, km(W.g_h, Hr), km(W.hsel, Hr), Hr, Hr, B, L.offset[MMG_P_REC_Y1_W], Hr + d.WV, -1, WG_GEMM);
+    b.add(km(W.dgi, d.G3), km(W.sen_feats, M), d.G3, M, R, MMG_P_REC_RNN_WIH, 0, MMG_P_REC_RNN_BIH);
+    b.add(km(W.dgh, d.G3), km(W.h_z, Hr), d.G3, Hr, R, MMG_P_REC_RNN_WHH, 0, MMG_P_REC_RNN_BHH);
+    b.add(km(W.d_lw, M), km(W.h_w, Hr), M, Hr, R, MMG_P_REC_W_W, 0, MMG_P_REC_W_B);
+    b.add(km(W.d_hw, Hr), km(h_after, Hr), Hr, Hr, R, MMG_P_REC_WH_W, 0, MMG_P_REC_WH_B);
+    b.add(km(W.d_hw, Hr), km(W.wd, d.WV), Hr, d.WV, R, MMG_P_REC_WD_W, 0, -1);
+    b.add(km(W.d_ls, 1), km(h_after, Hr), 1, Hr, R, MMG_P_REC_S_W, 0, MMG_P_REC_S_B);
+    b.add(km(W.g_h, Hr), km(W.hsel, Hr), Hr, Hr, B, MMG_P_REC_Y1_W, 0, -1);
     {
         Operand bd = km(in.desc, d.WV);
         bd.mod = d.D;                                        // row (b, d) -> desc[d]
-        add_problem(*t, km(W.dy1, Hr), bd, Hr, d.WV, B * d.D, L.offset[MMG_P_REC_Y1_W] + Hr, Hr + d.WV, L.offset[MMG_P_REC_Y1_B], WG_GEMM);
+        b.add(km(W.dy1, Hr), bd, Hr, d.WV, B * d.D, MMG_P_REC_Y1_W, Hr, MMG_P_REC_Y1_B);
     }
-    add_problem(*t, km(W.dw2p, Hr), km(W.dw2p, Hr), Hr, 1, B, L.offset[MMG_P_REC_Y2_W], 1, -1, WG_COLSUM);
-    add_problem(*t, km(W.g_outp, 1), km(W.g_outp, 1), 1, 1, B * d.D, L.offset[MMG_P_REC_Y2_B], 1, -1, WG_COLSUM);
+    b.add(km(W.dw2p, Hr), ones(), Hr, 1, B, MMG_P_REC_Y2_W, 0, -1);          // y2.weight (1, Hr): sum over examples
+    b.add(km(W.g_outp, 1), ones(), 1, 1, B * d.D, MMG_P_REC_Y2_B, 0, -1);
     if (d.use_binary) {
         // sender
-        add_problem(*t, km(W.d_lz, M), km(W.a_s, Hi), M, Hi, R, L.offset[MMG_P_SEN_BIN_W], Hi, L.offset[MMG_P_SEN_BIN_B], WG_GEMM);
-        add_problem(*t, km(W.d_as, Hi), km(W.code_in, M), Hi, M, R, L.offset[MMG_P_SEN_CODE_W], M, L.offset[MMG_P_SEN_CODE_B], WG_GEMM);
-        add_problem(*t, km(W.d_as, Hi), km(W.d_as, Hi), M, 1, 1, L.offset[MMG_P_SEN_CODE_BIAS], 1, -1, WG_CODEBIAS);
-        add_problem(*t, km(W.dhx, Hi), km(in.x, d.F), Hi, d.F, B, L.offset[MMG_P_SEN_IMG_W], d.F, L.offset[MMG_P_SEN_IMG_B], WG_GEMM);
+        b.add(km(W.d_lz, M), km(W.a_s, Hi), M, Hi, R, MMG_P_SEN_BIN_W, 0, MMG_P_SEN_BIN_B);
+        b.add(km(W.d_as, Hi), km(W.code_in, M), Hi, M, R, MMG_P_SEN_CODE_W, 0, MMG_P_SEN_CODE_B);
+        if (fast) b.add(km(W.dcode_part, M), ones(), M, 1, B, MMG_P_SEN_CODE_BIAS, 0, -1, WG_GEMM, P.p[MMG_P_SEN_CODE_BIAS]);
+        else      b.add(km(W.d_as, Hi), km(W.d_as, Hi), M, 1, 1, MMG_P_SEN_CODE_BIAS, 0, -1, WG_CODEBIAS);
+        b.add(km(W.dhx, Hi), km(in.x, d.F), Hi, d.F, B, MMG_P_SEN_IMG_W, 0, MMG_P_SEN_IMG_B);
         // baseline_sen: d pre = g_bs * linear2.weight * (hidden > 0); rows [h_x[b] ; z_r[t,b]]
         {
             Operand a = km(W.h1s, d.Hb);
             a.kind = OP_RELUGRAD; a.g = W.g_bs; a.w2 = P.p[MMG_P_BS_L2_W];
-            Operand b = km(W.h_x, Hi);
-            b.mod = B; b.p2 = W.rec_feats; b.ld2 = M; b.split = Hi;
-            add_problem(*t, a, b, d.Hb, Hi + M, R, L.offset[MMG_P_BS_L1_W], Hi + M, L.offset[MMG_P_BS_L1_B], WG_GEMM);
-            add_problem(*t, km(W.g_bs, 1), km(W.h1s, d.Hb), 1, d.Hb, R, L.offset[MMG_P_BS_L2_W], d.Hb, L.offset[MMG_P_BS_L2_B], WG_GEMM);
+            Operand bb = km(W.h_x, Hi);
+            bb.mod = B; bb.p2 = W.rec_feats; bb.ld2 = M; bb.split = Hi;
+            b.add(a, bb, d.Hb, Hi + M, R, MMG_P_BS_L1_W, 0, MMG_P_BS_L1_B);
+            b.add(km(W.g_bs, 1), km(W.h1s, d.Hb), 1, d.Hb, R, MMG_P_BS_L2_W, 0, MMG_P_BS_L2_B);
         }
         // baseline_rec: rows [z[t,b] ; h_z after step t]
         {
             Operand a = km(W.h1r, d.Hb);
             a.kind = OP_RELUGRAD; a.g = W.g_br; a.w2 = P.p[MMG_P_BR_L2_W];
-            Operand b = km(W.sen_feats, M);
-            b.p2 = h_after; b.ld2 = Hr; b.split = M;
-            add_problem(*t, a, b, d.Hb, M + Hr, R, L.offset[MMG_P_BR_L1_W], M + Hr, L.offset[MMG_P_BR_L1_B], WG_GEMM);
-            add_problem(*t, km(W.g_br, 1), km(W.h1r, d.Hb), 1, d.Hb, R, L.offset[MMG_P_BR_L2_W], d.Hb, L.offset[MMG_P_BR_L2_B], WG_GEMM);
+            Operand bb = km(W.sen_feats, M);
+            bb.p2 = h_after; bb.ld2 = Hr; bb.split = M;
+            b.add(a, bb, d.Hb, M + Hr, R, MMG_P_BR_L1_W, 0, MMG_P_BR_L1_B);
+            b.add(km(W.g_br, 1), km(W.h1r, d.Hb), 1, d.Hb, R, MMG_P_BR_L2_W, 0, MMG_P_BR_L2_B);
         }
     }
+    b.finish();
+}
+
+static int upd_ctas(int64_t total) {
+    int64_t n = cdiv64(total / 4, kUpdThreads);
+    if (n > kNormCtasMax) n = kNormCtasMax;
+    if (n < 1) n = 1;
+    return (int)n;
 }
 
 static SegInfo seg_info(const mmg_param_layout& L, const Dims& d) {
@@ -553,8 +591,8 @@ int mmg_backward(const mmg_config* cfg, const float* d_params, const mmg_inputs*
     const ParamPtrs P = param_ptrs(L, d_params);
     const ExchangeInputs ei = resolve_inputs(in);
     cudaStream_t st = (cudaStream_t)stream;
-    if (pl.fast) rc = d.M == 32 ? launch_bwd_fast_m<32>(d, W, P.p[MMG_P_SEN_BIN_W], pl, st)
-                                : launch_bwd_fast_m<64>(d, W, P.p[MMG_P_SEN_BIN_W], pl, st);
+    if (pl.fast) rc = d.M == 32 ? launch_bwd_fast_m<32>(d, W, P.p[MMG_P_SEN_BIN_W], P.p[MMG_P_SEN_CODE_W], pl, st)
+                                : launch_bwd_fast_m<64>(d, W, P.p[MMG_P_SEN_BIN_W], P.p[MMG_P_SEN_CODE_W], pl, st);
     else switch (pl.BT) {
         case 1: rc = launch_bwd<1>(d, W, pl, st); break;
         case 2: rc = launch_bwd<2>(d, W, pl, st); break;
@@ -563,12 +601,13 @@ int mmg_backward(const mmg_config* cfg, const float* d_params, const mmg_inputs*
     }
     if (rc) return rc;
     WgTable tab;
-    build_wgrad_table(d, L, P, W, ei, &tab);
-    MMG_LAUNCH(k_wgrad, tab.total_tiles, kGemmThreads, 0, st, d, tab, W.slabs, P.p[MMG_P_SEN_CODE_W],
+    SplitTable stab;
+    build_wgrad_table(d, L, P, W, ei, pl.fast, &tab, &stab);
+    MMG_LAUNCH(k_wgrad, tab.total_tiles, kGemmThreads, 0, st, d, tab, d_grads, W.slabs, P.p[MMG_P_SEN_CODE_W],
                P.p[MMG_P_SEN_CODE_BIAS], W.d_as);
     if ((rc = check_cuda("k_wgrad"))) return rc;
     const SegInfo seg = seg_info(L, d);
-    MMG_LAUNCH(k_reduce_norm, kNormCtas, kUpdThreads, 0, st, seg, W.slabs, (long long)L.total, W.wgrad_split, d_grads, 1.0f,
+    MMG_LAUNCH(k_reduce_norm, upd_ctas(L.total), kUpdThreads, 0, st, seg, stab, W.slabs, (long long)L.total, d_grads, 1.0f,
                1, W.norm_part);
     return check_cuda("k_reduce_norm");
 }
@@ -584,8 +623,10 @@ int mmg_grad_norm(const mmg_config* cfg, float* d_grads, void* d_workspace, void
     ws_layout(d, &w);
     const WsPtrs W = resolve(w, d_workspace);
     const SegInfo seg = seg_info(L, d);
-    MMG_LAUNCH(k_reduce_norm, kNormCtas, kUpdThreads, 0, (cudaStream_t)stream, seg, W.slabs, (long long)L.total,
-               W.wgrad_split, d_grads, 1.0f, 0, W.norm_part);
+    SplitTable stab;
+    memset(&stab, 0, sizeof(stab));
+    MMG_LAUNCH(k_reduce_norm, upd_ctas(L.total), kUpdThreads, 0, (cudaStream_t)stream, seg, stab, W.slabs, (long long)L.total,
+               d_grads, 1.0f, 0, W.norm_part);
     return check_cuda("k_reduce_norm");
 }
 
@@ -606,8 +647,9 @@ int mmg_clip_update(const mmg_config* cfg, float* d_params, float* d_grads, floa
     const SegInfo seg = seg_info(L, d);
     OptHyper hp;
     hp.optim = cfg->optim_type; hp.lr = cfg->learning_rate; hp.max_norm = cfg->max_norm; hp.step = step;
-    MMG_LAUNCH(k_update, kNormCtas, kUpdThreads, 0, (cudaStream_t)stream, seg, hp, d_params, d_grads, d_state1, d_state2,
-               W.norm_part, (int)kNormCtas, W.grad_norms, W.stats, W.opt_counters);
+    const int nc = upd_ctas(L.total);
+    MMG_LAUNCH(k_update, nc, kUpdThreads, 0, (cudaStream_t)stream, seg, hp, d_params, d_grads, d_state1, d_state2,
+               W.norm_part, nc, W.grad_norms, W.stats, W.opt_counters);
     return check_cuda("k_update");
 }
 

@@ -486,11 +486,11 @@ MMG_HOST_DEVICE int fast_bwd_rec_state_floats(int T, int M, int D) {
     // dlw (T,M) | dhw (T,64) | inj (T,64) | gat (T,5,64) | dgh (2,192) | gv (64) | gout (DP) | dls (T) | barrier
     return T * M + 2 * T * kFastHr + 5 * T * kFastHr + 2 * 3 * kFastHr + kFastHr + align4(D) + align4(T) + 8;
 }
-MMG_HOST_DEVICE int fast_bwd_sen_state_floats(int T, int M) { return T * M + 8; }
+MMG_HOST_DEVICE int fast_bwd_sen_state_floats(int T, int M) { return T * M + 2 * kFastHi + 8; }
 
 template <int M>
 MMG_GLOBAL void __launch_bounds__(kFastThreads, 1)
-k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, int n_rec_ctas) {
+k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, int n_rec_ctas) {
     constexpr int HI = kFastHi, HR = kFastHr, NT = kFastThreads, M4 = M / 4;
     MMG_DYN_SMEM(smem_raw);
     float* sm = reinterpret_cast<float*>(smem_raw);
@@ -515,6 +515,8 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, int n_rec_ctas) {
             dlz[idx] = dl;
         }
         MMG_SYNCTHREADS();
+        float* das0 = sm + T * M;                                     // (256) d a at t = 0
+        float* cred = das0 + HI;                                      // (256 / M, M) partial sums
         float dhx = 0.f;
 #pragma unroll 2
         for (int t = 0; t < T; ++t) {
@@ -529,9 +531,31 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, int n_rec_ctas) {
             }
             const float das = acc * (1.f - a * a);                    // through tanh (model.py:216)
             W.d_as[i] = das;
+            if (t == 0) das0[n] = das;
             dhx += das;                                               // h_x is shared by all steps (model.py:195)
         }
         W.dhx[(size_t)b * HI + n] = dhx;
+        // d code_layer-input at t = 0 (the code is sigmoid(code_bias) for every example, model.py:199-200):
+        // dcode_part[b][j] = sum_n d_a[0][n] code_layer.weight[n][j]; K_wgrad sums over b and applies d sigmoid.
+        MMG_SYNCTHREADS();
+        {
+            const int j = tid % M, part = tid / M;                    // NT / M parts, each HI * M / NT rows
+            constexpr int RPP = HI * M / NT;
+            float acc = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < RPP; ++r) {
+                const int nn = part * RPP + r;
+                acc = fmaf(das0[nn], ldg(code_w + (size_t)nn * M + j), acc);
+            }
+            cred[part * M + j] = acc;
+        }
+        MMG_SYNCTHREADS();
+        if (tid < M) {
+            float v = 0.f;
+#pragma unroll
+            for (int p = 0; p < NT / M; ++p) v += cred[p * M + tid];
+            W.dcode_part[(size_t)b * M + tid] = v;
+        }
         return;
     }
 

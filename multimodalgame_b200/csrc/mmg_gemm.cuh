@@ -1,6 +1,8 @@
 // Generic fp32 FFMA tile GEMM used for every non-recurrent product of the path: the image-layer GEMM, the two
 // baseline MLPs and all weight gradients.  C[i][j] = sum_k A(k, i) * B(k, j) over k in [k0, k1).
-// 64x64 output tile per 256-thread CTA, 4x4 register micro-tile per thread, 16-deep shared-memory chunks.
+// 64x64 output tile per 256-thread CTA, 4x4 register micro-tile per thread, 16-deep chunks, shared memory double
+// buffered through a register prefetch: the global loads of chunk c+1 are in flight while chunk c is multiplied, one
+// barrier per chunk.  Operand rows are fetched as float4 (LDG.128 -> STS.128) whenever the layout allows it.
 // fp32 on the CUDA cores on purpose: parity with the reference is 1e-4 on logits and bit-exact on sampled
 // bits, which TF32 tensor-core products (10-bit mantissa) do not meet at K=2048.
 #pragma once
@@ -9,7 +11,8 @@
 namespace mmg {
 
 enum { kTile = 64, kChunk = 16, kLd = kTile + 4, kGemmThreads = 256 };
-enum { OP_PLAIN = 0, OP_RELUGRAD = 1 };
+enum { kGemmSmemFloats = 4 * kChunk * kLd };     // [buffer 0/1][A, B][kChunk][kLd]
+enum { OP_PLAIN = 0, OP_RELUGRAD = 1, OP_ONES = 2 };
 
 // Operand descriptor.  Element (k, i): k = reduction index, i = output index (row of C for A, column for B).
 struct Operand {
@@ -23,10 +26,11 @@ struct Operand {
     int mod;            // > 0: row index taken modulo `mod` (applies to the primary source only)
     int split;          // concat boundary: kmajor ? (i >= split -> p2[k * ld2 + i - split])
                         //                         : (k >= split -> p2[i * ld2 + k - split]); 0 = none
-    int kind;
+    int kind;           // OP_PLAIN; OP_RELUGRAD: (p > 0) ? g[k] * w2[i] : 0; OP_ONES: 1 (column sums as a GEMM)
 };
 
 MMG_DEVICE float operand_load(const Operand& op, int k, int i) {
+    if (op.kind == OP_ONES) return 1.f;
     float v;
     if (op.kmajor) {
         if (op.split > 0 && i >= op.split) {
@@ -47,25 +51,98 @@ MMG_DEVICE float operand_load(const Operand& op, int k, int i) {
     return v;
 }
 
-// Load a kChunk x kTile chunk of an operand into shared memory S[kk][ii] (row stride kLd), zero filled outside
-// [0,K) x [0,N).  Thread->element mapping follows the operand's contiguous direction for coalescing.
-MMG_DEVICE void load_chunk(const Operand& op, float* S, int kbase, int kend, int ibase, int ilim, int tid) {
+MMG_DEVICE bool aligned16(const void* p) { return (((size_t)p) & 15) == 0; }
+
+// Per-thread fetch pattern of one 16 x 64 chunk (4 elements per thread):
+//   mode 0 (scalar, k-major rows): (kk, ii) = (tid/64 + 4 l, tid % 64)
+//   mode 1 (scalar, k contiguous): (kk, ii) = (tid % 16, tid/16 + 16 l)
+//   mode 2 (float4 along i):       (kk, ii) = (tid/16, 4 (tid % 16) + c)
+//   mode 3 (float4 along k):       (kk, ii) = (4 (tid % 4) + c, tid/4)
+MMG_DEVICE int operand_mode(const Operand& op, int k0) {
+    if (op.kind == OP_ONES) return 0;
+    const bool ok2 = op.p2 == nullptr || op.split == 0 || ((op.split & 3) == 0 && (op.ld2 & 3) == 0 && aligned16(op.p2));
+    if ((op.ld & 3) != 0 || !aligned16(op.p) || !ok2) return op.kmajor ? 0 : 1;
+    if (op.kmajor) {
+        if (op.kind == OP_RELUGRAD && !aligned16(op.w2)) return 0;
+        return 2;
+    }
+    return (k0 & 3) == 0 ? 3 : 1;
+}
+
+MMG_DEVICE float4 chunk_fetch(const Operand& op, int mode, int kbase, int kend, int ibase, int ilim, int tid) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (mode == 2) {
+        const int k = kbase + (tid >> 4), i = ibase + 4 * (tid & 15);
+        if (k < kend && i + 3 < ilim) {
+            float4 r;
+            if (op.split > 0 && i >= op.split) {
+                r = ldg4(reinterpret_cast<const float4*>(op.p2 + (size_t)k * op.ld2 + (i - op.split)));
+            } else {
+                const int row = op.mod > 0 ? k % op.mod : k;
+                r = ldg4(reinterpret_cast<const float4*>(op.p + (size_t)row * op.ld + i));
+            }
+            if (op.kind == OP_RELUGRAD) {
+                const float g = ldg(op.g + k);
+                const float4 w = ldg4(reinterpret_cast<const float4*>(op.w2 + i));
+                r.x = r.x > 0.f ? g * w.x : 0.f; r.y = r.y > 0.f ? g * w.y : 0.f;
+                r.z = r.z > 0.f ? g * w.z : 0.f; r.w = r.w > 0.f ? g * w.w : 0.f;
+            }
+            return r;
+        }
+        if (k < kend) {
 #pragma unroll
-    for (int l = 0; l < (kChunk * kTile) / kGemmThreads; ++l) {
-        int idx = tid + l * kGemmThreads;
-        int kk, ii;
-        if (op.kmajor) { kk = idx / kTile; ii = idx % kTile; }
-        else           { kk = idx % kChunk; ii = idx / kChunk; }
-        int k = kbase + kk, i = ibase + ii;
-        float v = (k < kend && i < ilim) ? operand_load(op, k, i) : 0.f;
-        S[kk * kLd + ii] = v;
+            for (int c = 0; c < 4; ++c) if (i + c < ilim) v[c] = operand_load(op, k, i + c);
+        }
+    } else if (mode == 3) {
+        const int k = kbase + 4 * (tid & 3), i = ibase + (tid >> 2);
+        if (i < ilim) {
+            if (k + 3 < kend && !(op.split > 0 && k + 3 >= op.split && k < op.split)) {
+                if (op.split > 0 && k >= op.split)
+                    return ldg4(reinterpret_cast<const float4*>(op.p2 + (size_t)i * op.ld2 + (k - op.split)));
+                const int row = op.mod > 0 ? i % op.mod : i;
+                return ldg4(reinterpret_cast<const float4*>(op.p + (size_t)row * op.ld + k));
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (k + c < kend) v[c] = operand_load(op, k + c, i);
+        }
+    } else if (mode == 0) {
+        const int i = ibase + (tid & 63);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const int k = kbase + (tid >> 6) + 4 * l;
+            if (k < kend && i < ilim) v[l] = operand_load(op, k, i);
+        }
+    } else {
+        const int k = kbase + (tid & 15);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const int i = ibase + (tid >> 4) + 16 * l;
+            if (k < kend && i < ilim) v[l] = operand_load(op, k, i);
+        }
+    }
+    return make_float4(v[0], v[1], v[2], v[3]);
+}
+
+MMG_DEVICE void chunk_store(float* S, int mode, const float4& r, int tid) {
+    if (mode == 2) {
+        *reinterpret_cast<float4*>(S + (tid >> 4) * kLd + 4 * (tid & 15)) = r;
+    } else if (mode == 3) {
+        float* q = S + (4 * (tid & 3)) * kLd + (tid >> 2);
+        q[0] = r.x; q[kLd] = r.y; q[2 * kLd] = r.z; q[3 * kLd] = r.w;
+    } else if (mode == 0) {
+        float* q = S + (tid >> 6) * kLd + (tid & 63);
+        q[0] = r.x; q[4 * kLd] = r.y; q[8 * kLd] = r.z; q[12 * kLd] = r.w;
+    } else {
+        float* q = S + (tid & 15) * kLd + (tid >> 4);
+        q[0] = r.x; q[16] = r.y; q[32] = r.z; q[48] = r.w;
     }
 }
 
 // Accumulates the 4x4 micro-tile of thread (ty = tid / 16, tx = tid % 16): rows i = ty*4.., cols j = tx*4..
 // `colsum` (optional, threads < kTile): sum_k A(k, m0 + tid) as a by-product (bias gradients).
+// `smem`: kGemmSmemFloats floats, 16-byte aligned.
 MMG_DEVICE void gemm_tile(const Operand& A, const Operand& Bm, int Mdim, int Ndim, int m0, int n0, int k0, int k1,
-                          float (&acc)[4][4], float* colsum, float* As, float* Bs) {
+                          float (&acc)[4][4], float* colsum, float* smem) {
     const int tid = threadIdx.x;
     const int tx = tid % 16, ty = tid / 16;
 #pragma unroll
@@ -73,26 +150,45 @@ MMG_DEVICE void gemm_tile(const Operand& A, const Operand& Bm, int Mdim, int Ndi
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
     float cs = 0.f;
-    for (int kb = k0; kb < k1; kb += kChunk) {
-        load_chunk(A, As, kb, k1, m0, Mdim, tid);
-        load_chunk(Bm, Bs, kb, k1, n0, Ndim, tid);
+    if (k0 < k1) {
+        const int modeA = operand_mode(A, k0), modeB = operand_mode(Bm, k0);
+        float4 ra = chunk_fetch(A, modeA, k0, k1, m0, Mdim, tid);
+        float4 rb = chunk_fetch(Bm, modeB, k0, k1, n0, Ndim, tid);
+        chunk_store(smem, modeA, ra, tid);
+        chunk_store(smem + kChunk * kLd, modeB, rb, tid);
         MMG_SYNCTHREADS();
+        int buf = 0;
+        for (int kb = k0; kb < k1; kb += kChunk) {
+            const bool more = kb + kChunk < k1;
+            if (more) {
+                ra = chunk_fetch(A, modeA, kb + kChunk, k1, m0, Mdim, tid);
+                rb = chunk_fetch(Bm, modeB, kb + kChunk, k1, n0, Ndim, tid);
+            }
+            const float* As = smem + buf * 2 * kChunk * kLd;
+            const float* Bs = As + kChunk * kLd;
 #pragma unroll
-        for (int kk = 0; kk < kChunk; ++kk) {
-            const float4 a4 = *reinterpret_cast<const float4*>(As + kk * kLd + ty * 4);
-            const float4 b4 = *reinterpret_cast<const float4*>(Bs + kk * kLd + tx * 4);
-            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-            const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+            for (int kk = 0; kk < kChunk; ++kk) {
+                const float4 a4 = *reinterpret_cast<const float4*>(As + kk * kLd + ty * 4);
+                const float4 b4 = *reinterpret_cast<const float4*>(Bs + kk * kLd + tx * 4);
+                const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+                const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+                for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+                    for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+            }
+            if (colsum != nullptr && tid < kTile) {
+#pragma unroll
+                for (int kk = 0; kk < kChunk; ++kk) cs += As[kk * kLd + tid];
+            }
+            if (more) {
+                float* Sn = smem + (buf ^ 1) * 2 * kChunk * kLd;
+                chunk_store(Sn, modeA, ra, tid);
+                chunk_store(Sn + kChunk * kLd, modeB, rb, tid);
+            }
+            MMG_SYNCTHREADS();
+            buf ^= 1;
         }
-        if (colsum != nullptr && tid < kTile) {
-#pragma unroll
-            for (int kk = 0; kk < kChunk; ++kk) cs += As[kk * kLd + tid];
-        }
-        MMG_SYNCTHREADS();
     }
     if (colsum != nullptr && tid < kTile) *colsum = cs;
 }

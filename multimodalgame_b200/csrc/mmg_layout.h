@@ -180,7 +180,7 @@ MMG_HOST_DEVICE bool fast_dims(const Dims& d) {
 }
 
 // ---- workspace ------------------------------------------------------------------------------------------
-enum { kHxSplitMax = 16, kWgradSplitMax = 8, kNormCtas = 128, kLossCtasMax = 592 };
+enum { kHxSplitMax = 16, kWgradSplitMax = 16, kNormCtasMax = 592, kLossCtasMax = 592 };
 enum { kStatKinds = 3 };  // 0: sender messages, 1: receiver messages, 2: stop bit
 // stats (double): per (kind, t): n, sum w, sum w^2 (w = logs - baseline); then per t: baseline_rec SSE,
 // baseline_sen SSE, n_mask; then scalars: nll_sum, topk_correct.
@@ -216,8 +216,9 @@ struct Ws {   // byte offsets into the workspace
     int64_t hsel;      // (B,Hr)   h_z at the prediction step
     int64_t dy1;       // (B,D,Hr)
     int64_t dw2p;      // (B,Hr)
-    int64_t slabs;     // (kWgradSplitMax, P) split-K partial gradients
-    int64_t norm_part; // (4, kNormCtas) per-CTA partial sums of squares
+    int64_t dcode_part; // (B,M)   per-example d code_layer-input at t = 0 (fast path), summed into d code_bias
+    int64_t slabs;     // (kWgradSplitMax - 1, P) split-K partial gradients (split 0 lands in the gradient buffer itself)
+    int64_t norm_part; // (4, kNormCtasMax) per-CTA partial sums of squares
     int64_t loss_part; // double (kLossCtasMax, 8) per-CTA loss partial sums, summed in CTA order by the last CTA
     int64_t tickets;   // uint32[4] "last CTA done" counters (self-resetting)
     int64_t opt_counters; // int64[4]: [0] = number of updates that reached the receiver message head (Adam bias correction)

@@ -16,8 +16,7 @@ namespace mmg {
 
 MMG_GLOBAL void __launch_bounds__(kGemmThreads)
 k_baseline_fwd(Dims d, ParamPtrs P, WsPtrs W, const float* desc, int n_bas_tiles) {
-    MMG_SHARED __attribute__((aligned(16))) float As[kChunk * kLd];
-    MMG_SHARED __attribute__((aligned(16))) float Bs[kChunk * kLd];
+    MMG_SHARED __attribute__((aligned(16))) float gs[kGemmSmemFloats];
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
     const int ntm = cdiv(d.R, kTile), ntn = W.ntb;
     int t = blockIdx.x;
@@ -29,7 +28,7 @@ k_baseline_fwd(Dims d, ParamPtrs P, WsPtrs W, const float* desc, int n_bas_tiles
         const Operand A = Operand{W.q, nullptr, nullptr, nullptr, d.D, 0, 0, 0, 0, OP_PLAIN};
         const Operand Bo = Operand{desc, nullptr, nullptr, nullptr, d.WV, 0, 1, 0, 0, OP_PLAIN};
         float acc[4][4];
-        gemm_tile(A, Bo, d.R, d.WV, mt * kTile, nt * kTile, 0, d.D, acc, nullptr, As, Bs);
+        gemm_tile(A, Bo, d.R, d.WV, mt * kTile, nt * kTile, 0, d.D, acc, nullptr, gs);
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int r = mt * kTile + ty * 4 + a;
@@ -58,7 +57,7 @@ k_baseline_fwd(Dims d, ParamPtrs P, WsPtrs W, const float* desc, int n_bas_tiles
         b1 = P.p[MMG_P_BR_L1_B]; w2 = P.p[MMG_P_BR_L2_W]; hid = W.h1r; part = W.br_part; K = d.M + d.Hr;
     }
     float acc[4][4];
-    gemm_tile(A, Bo, d.R, d.Hb, mt * kTile, nt * kTile, 0, K, acc, nullptr, As, Bs);
+    gemm_tile(A, Bo, d.R, d.Hb, mt * kTile, nt * kTile, 0, K, acc, nullptr, gs);
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const int r = mt * kTile + ty * 4 + a;

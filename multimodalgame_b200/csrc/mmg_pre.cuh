@@ -63,8 +63,7 @@ MMG_DEVICE float bwd_image_elem(const Dims& d, const BwdImage& im, const ParamPt
 
 MMG_GLOBAL void __launch_bounds__(kGemmThreads)
 k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_kslice, int fast) {
-    MMG_SHARED __attribute__((aligned(16))) float As[kChunk * kLd];
-    MMG_SHARED __attribute__((aligned(16))) float Bs[kChunk * kLd];
+    MMG_SHARED __attribute__((aligned(16))) float gs[kGemmSmemFloats];
     const int tid = threadIdx.x;
     if ((int)blockIdx.x < n_hx_tiles) {
         // ---- role A: h_x split-K tile -------------------------------------------------------------------
@@ -77,7 +76,7 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
         Operand Bo = {P.p[MMG_P_SEN_IMG_W], nullptr, nullptr, nullptr, d.F, 0, 0, 0, 0, OP_PLAIN};
         float acc[4][4];
         const int k0 = s * hx_kslice, k1 = min(d.F, k0 + hx_kslice);
-        gemm_tile(A, Bo, d.B, d.Hi, mt * kTile, nt * kTile, k0, k1, acc, nullptr, As, Bs);
+        gemm_tile(A, Bo, d.B, d.Hi, mt * kTile, nt * kTile, k0, k1, acc, nullptr, gs);
         const int tx = tid % 16, ty = tid / 16;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {

@@ -1,9 +1,11 @@
 // K_wgrad, K_reduce_norm, K_update.
 //
 // K_wgrad: every weight / bias gradient of the four modules as ONE grouped launch of 64x64 fp32 tiles
-//   C = A^T . B reduced over the T*B (or B, or B*D) rows, split-K into `nsplit` slabs for parallelism; slabs are
-//   summed in a fixed order by K_reduce_norm, so gradients are bit-reproducible run to run (no float atomics).
-// K_reduce_norm: slabs -> flat gradient, plus per-CTA partial sums of squares per module.
+//   C = A^T . B reduced over the T*B (or B, or B*D) rows.  Each tensor picks its own split-K factor so that every CTA
+//   multiplies a K-slice of ~128 rows (balanced single wave); split 0 writes straight into the flat gradient buffer,
+//   splits 1.. into arena slabs that K_reduce_norm adds in a fixed order, so gradients are bit-reproducible run to run
+//   (no float atomics).  Column sums (bias-like gradients) run through the same tiles with a constant-one operand.
+// K_reduce_norm: gradient += slabs, plus per-CTA partial sums of squares per module (float4 streams).
 // K_update: torch.nn.utils.clip_grad_norm(params, 1.) per module (model.py:1310,1317,1323,1329) fused with the
 //   optimizer step (RMSprop default, model.py:1725; Adam / SGD, 1111-1137).
 #pragma once
@@ -11,8 +13,8 @@
 
 namespace mmg {
 
-enum { WG_GEMM = 0, WG_COLSUM = 1, WG_CODEBIAS = 2 };
-enum { kMaxWgProblems = 20 };
+enum { WG_GEMM = 0, WG_CODEBIAS = 2 };
+enum { kMaxWgProblems = 20, kWgradKSlice = 128 };
 
 struct WgProblem {
     Operand A, B;
@@ -20,19 +22,20 @@ struct WgProblem {
     long long c_off;      // float offset of C[0][0] inside the flat layout (includes any column offset)
     int ldc;
     long long bias_off;   // float offset of colsum(A) output, or -1
+    const float* sig_rows; // non-null: row i of C is scaled by s (1 - s), s = sigmoid(sig_rows[i])  (d sigmoid(code_bias))
     int kind;
+    int nsplit;
     int tile_begin, ntm, ntn;
 };
 struct WgTable {
     WgProblem p[kMaxWgProblems];
-    int count, total_tiles, nsplit;
-    long long slab_stride;   // floats between consecutive slabs (= flat layout total)
+    int count, total_tiles;
+    long long slab_stride;   // floats between consecutive arena slabs (= flat layout total)
 };
 
 MMG_GLOBAL void __launch_bounds__(kGemmThreads)
-k_wgrad(Dims d, WgTable tab, float* slabs, const float* code_w, const float* code_bias, const float* d_as) {
-    MMG_SHARED __attribute__((aligned(16))) float As[kChunk * kLd];
-    MMG_SHARED __attribute__((aligned(16))) float Bs[kChunk * kLd];
+k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, const float* code_bias, const float* d_as) {
+    MMG_SHARED __attribute__((aligned(16))) float gs[kGemmSmemFloats];
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
     int tile = blockIdx.x, pi = 0;
     while (pi + 1 < tab.count && tile >= tab.p[pi + 1].tile_begin) ++pi;
@@ -42,46 +45,41 @@ k_wgrad(Dims d, WgTable tab, float* slabs, const float* code_w, const float* cod
     const int s = tile / per_split;
     tile %= per_split;
     const int nt = tile % pr.ntn, mt = tile / pr.ntn;
-    float* slab = slabs + (size_t)s * tab.slab_stride;
-    const int ks = cdiv(pr.K, tab.nsplit);
+    float* slab = s == 0 ? grads : arena + (size_t)(s - 1) * tab.slab_stride;
+    const int ks = round_up(cdiv(pr.K, pr.nsplit), 4);
     const int k0 = s * ks, k1 = min(pr.K, k0 + ks);
 
     if (pr.kind == WG_GEMM) {
         float acc[4][4];
         float cs = 0.f;
         const bool want_bias = pr.bias_off >= 0 && nt == 0;
-        gemm_tile(pr.A, pr.B, pr.M, pr.N, mt * kTile, nt * kTile, k0, k1, acc, want_bias ? &cs : nullptr, As, Bs);
+        gemm_tile(pr.A, pr.B, pr.M, pr.N, mt * kTile, nt * kTile, k0, k1, acc, want_bias ? &cs : nullptr, gs);
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int i = mt * kTile + ty * 4 + a;
             if (i >= pr.M) continue;
+            float rs = 1.f;
+            if (pr.sig_rows != nullptr) { const float c0 = sigmoidf_(ldg(pr.sig_rows + i)); rs = c0 * (1.f - c0); }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int j = nt * kTile + tx * 4 + c;
-                if (j < pr.N) slab[pr.c_off + (size_t)i * pr.ldc + j] = acc[a][c];
+                if (j < pr.N) slab[pr.c_off + (size_t)i * pr.ldc + j] = acc[a][c] * rs;
             }
         }
         if (want_bias && tid < kTile && mt * kTile + tid < pr.M) slab[pr.bias_off + mt * kTile + tid] = cs;
-    } else if (pr.kind == WG_COLSUM) {
-        // C[i] = sum_k A(k, i): 4 row-interleaved partial sums per column, combined through shared memory
-        const int c = tid % kTile, qd = tid / kTile, i = mt * kTile + c;
-        float sacc = 0.f;
-        if (i < pr.M) for (int k = k0 + qd; k < k1; k += kGemmThreads / kTile) sacc += operand_load(pr.A, k, i);
-        As[qd * kTile + c] = sacc;
-        MMG_SYNCTHREADS();
-        if (tid < kTile && i < pr.M) slab[pr.c_off + i] = As[c] + As[kTile + c] + As[2 * kTile + c] + As[3 * kTile + c];
     } else {
+        // generic-path only (the fast backward kernel emits per-example partials instead):
         // d code_bias[j] = c0 (1 - c0) sum_n code_layer.weight[n][j] * (sum_b d_as[t=0][b][n])   (model.py:199-200)
-        float* v = As;   // Hi <= kChunk * kLd * 2 checked on the host (As and Bs are contiguous only by luck: use As + loop)
+        float* v = gs;
         for (int j0 = 0; j0 < d.M; j0 += kGemmThreads) {
             const int j = j0 + tid;
             float accj = 0.f;
-            for (int nb = 0; nb < d.Hi; nb += kChunk * kLd) {
-                const int nlim = min(d.Hi - nb, kChunk * kLd);
+            for (int nb = 0; nb < d.Hi; nb += kGemmSmemFloats) {
+                const int nlim = min(d.Hi - nb, (int)kGemmSmemFloats);
                 MMG_SYNCTHREADS();
                 for (int n = tid; n < nlim; n += kGemmThreads) {
                     float sv = 0.f;
-                    if (s == 0) for (int b = 0; b < d.B; ++b) sv += d_as[(size_t)b * d.Hi + nb + n];
+                    for (int b = 0; b < d.B; ++b) sv += d_as[(size_t)b * d.Hi + nb + n];
                     v[n] = sv;
                 }
                 MMG_SYNCTHREADS();
@@ -97,38 +95,61 @@ k_wgrad(Dims d, WgTable tab, float* slabs, const float* code_w, const float* cod
 
 enum { kUpdThreads = 256 };
 
-MMG_DEVICE int seg_of(const long long* seg_begin, long long i) {
-    return i < seg_begin[1] ? 0 : (i < seg_begin[2] ? 1 : (i < seg_begin[3] ? 2 : 3));
-}
-
 struct SegInfo {
     long long begin[5];
     int trained[4];
     long long whead_begin, whead_end, shead_begin, shead_end;
     int shead_active, whead_stat;
 };
+// Per state_dict tensor: where it lives, how many floats are real (the rest of its 4-float slot is padding) and how
+// many split-K partials K_wgrad produced for it.
+struct SplitTable {
+    long long begin[MMG_P_COUNT + 1];
+    int numel[MMG_P_COUNT];
+    int nsplit[MMG_P_COUNT];
+};
 
+MMG_DEVICE int seg_of(const long long* seg_begin, long long i) {
+    return i < seg_begin[1] ? 0 : (i < seg_begin[2] ? 1 : (i < seg_begin[3] ? 2 : 3));
+}
+MMG_DEVICE int tensor_of(const SplitTable& st, long long i) {
+    int lo = 0, hi = MMG_P_COUNT - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (st.begin[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// grads (+)= slabs, scaled; per-CTA partial sums of squares per module -> norm_part[module * gridDim.x + cta].
+// do_reduce = 0: gradients are final already (after the data-parallel all-reduce), only the norms are computed.
 MMG_GLOBAL void __launch_bounds__(kUpdThreads)
-k_reduce_norm(SegInfo seg, const float* slabs, long long slab_stride, int nsplit, float* grads, float scale,
+k_reduce_norm(SegInfo seg, SplitTable st, const float* arena, long long slab_stride, float* grads, float scale,
               int do_reduce, float* norm_part) {
     MMG_SHARED float red[4][kUpdThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long total = seg.begin[4];
-    const long long chunk = round_up64(cdiv64(total, (long long)gridDim.x), 4);
-    const long long lo = (long long)blockIdx.x * chunk, hi = min(total, lo + chunk);
     float ss[4] = {0.f, 0.f, 0.f, 0.f};
-    for (long long i = lo + tid; i < hi; i += kUpdThreads) {
+    for (long long i = 4 * ((long long)blockIdx.x * kUpdThreads + tid); i < total; i += 4ll * gridDim.x * kUpdThreads) {
         const int sg = seg_of(seg.begin, i);
-        float g;
+        float4 g = *reinterpret_cast<const float4*>(grads + i);
         if (do_reduce) {
-            g = 0.f;
-            if (seg.trained[sg]) for (int s = 0; s < nsplit; ++s) g += slabs[(size_t)s * slab_stride + i];
-            g *= scale;
-            grads[i] = g;
-        } else {
-            g = grads[i];
+            const int tn = tensor_of(st, i);
+            const long long valid = st.begin[tn] + st.numel[tn] - i;   // real floats in this group (>= 1)
+            if (!seg.trained[sg]) {
+                g = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                for (int s = 1; s < st.nsplit[tn]; ++s) {
+                    const float4 a = *reinterpret_cast<const float4*>(arena + (size_t)(s - 1) * slab_stride + i);
+                    g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
+                }
+                if (valid < 4) { if (valid < 2) g.y = 0.f; if (valid < 3) g.z = 0.f; g.w = 0.f; }
+            }
+            g.x *= scale; g.y *= scale; g.z *= scale; g.w *= scale;
+            *reinterpret_cast<float4*>(grads + i) = g;
         }
-        ss[sg] = fmaf(g, g, ss[sg]);
+        ss[sg] = fmaf(g.x, g.x, ss[sg]); ss[sg] = fmaf(g.y, g.y, ss[sg]);
+        ss[sg] = fmaf(g.z, g.z, ss[sg]); ss[sg] = fmaf(g.w, g.w, ss[sg]);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -163,8 +184,6 @@ k_update(SegInfo seg, OptHyper hp, float* params, float* grads, float* state1, f
     }
     MMG_SYNCTHREADS();
     const long long total = seg.begin[4];
-    const long long chunk = round_up64(cdiv64(total, (long long)gridDim.x), 4);
-    const long long lo = (long long)blockIdx.x * chunk, hi = min(total, lo + chunk);
     float bc1 = 1.f, bc2s = 1.f, bc1w = 1.f, bc2sw = 1.f;
     const bool whead_active = stats[seg.whead_stat] > 0.0;
     if (hp.optim == MMG_OPT_ADAM) {
@@ -174,28 +193,45 @@ k_update(SegInfo seg, OptHyper hp, float* params, float* grads, float* state1, f
         bc1w = 1.f - powf(0.9f, ws);
         bc2sw = sqrtf(1.f - powf(0.999f, ws));
     }
-    for (long long i = lo + tid; i < hi; i += kUpdThreads) {
+    // all range boundaries are multiples of 4 floats, so a float4 group never straddles a module or a head
+    for (long long i = 4 * ((long long)blockIdx.x * kUpdThreads + tid); i < total; i += 4ll * gridDim.x * kUpdThreads) {
         const int sg = seg_of(seg.begin, i);
         if (!seg.trained[sg]) continue;
         const bool in_whead = i >= seg.whead_begin && i < seg.whead_end;
         if (in_whead && !whead_active) continue;
         if (i >= seg.shead_begin && i < seg.shead_end && !seg.shead_active) continue;
-        const float g = grads[i] * coef[sg];
-        grads[i] = g;
-        float p = params[i];
+        float4 g4 = *reinterpret_cast<const float4*>(grads + i);
+        float4 p4 = *reinterpret_cast<const float4*>(params + i);
+        const float cf = coef[sg];
+        float g[4] = {g4.x * cf, g4.y * cf, g4.z * cf, g4.w * cf};
+        float p[4] = {p4.x, p4.y, p4.z, p4.w};
         if (hp.optim == MMG_OPT_RMSPROP) {            // alpha 0.99, eps 1e-8, no momentum
-            const float v = 0.99f * state1[i] + 0.01f * g * g;
-            state1[i] = v;
-            p -= hp.lr * g / (sqrtf(v) + 1e-8f);
+            float4 v4 = *reinterpret_cast<const float4*>(state1 + i);
+            float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                v[c] = 0.99f * v[c] + 0.01f * g[c] * g[c];
+                p[c] -= hp.lr * g[c] / (sqrtf(v[c]) + 1e-8f);
+            }
+            *reinterpret_cast<float4*>(state1 + i) = make_float4(v[0], v[1], v[2], v[3]);
         } else if (hp.optim == MMG_OPT_ADAM) {        // betas (0.9, 0.999), eps 1e-8
-            const float m = 0.9f * state2[i] + 0.1f * g;
-            const float v = 0.999f * state1[i] + 0.001f * g * g;
-            state2[i] = m; state1[i] = v;
-            p -= (hp.lr / (in_whead ? bc1w : bc1)) * m / (sqrtf(v) / (in_whead ? bc2sw : bc2s) + 1e-8f);
+            float4 v4 = *reinterpret_cast<const float4*>(state1 + i);
+            float4 m4 = *reinterpret_cast<const float4*>(state2 + i);
+            float v[4] = {v4.x, v4.y, v4.z, v4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                m[c] = 0.9f * m[c] + 0.1f * g[c];
+                v[c] = 0.999f * v[c] + 0.001f * g[c] * g[c];
+                p[c] -= (hp.lr / (in_whead ? bc1w : bc1)) * m[c] / (sqrtf(v[c]) / (in_whead ? bc2sw : bc2s) + 1e-8f);
+            }
+            *reinterpret_cast<float4*>(state1 + i) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(state2 + i) = make_float4(m[0], m[1], m[2], m[3]);
         } else {
-            p -= hp.lr * g;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) p[c] -= hp.lr * g[c];
         }
-        params[i] = p;
+        *reinterpret_cast<float4*>(grads + i) = make_float4(g[0], g[1], g[2], g[3]);
+        *reinterpret_cast<float4*>(params + i) = make_float4(p[0], p[1], p[2], p[3]);
     }
 }
 
