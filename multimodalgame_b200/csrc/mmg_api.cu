@@ -232,7 +232,7 @@ static bool make_fast_plan(const Dims& d, Plan* pl) {
     if (pl->bwd_smem_bytes > kMaxSmem) return false;
     int bt = d.B <= 148 ? 1 : (d.B <= 2 * 148 ? 2 : 4);
     for (; bt >= 1; bt /= 2) {
-        const int st = fast_fwd_state_floats(bt, d.M, d.D);
+        const int st = fast_fwd_state_floats(bt, d.M, d.D, d.T);
         const int full = (fi.total + st) * 4, recv_only = (fi.total - fi.sender_end + st) * 4;
         if (d.M == 32 && full <= kMaxSmem) { pl->sender_smem = 1; pl->fwd_smem_bytes = full; break; }
         if (recv_only <= kMaxSmem) { pl->sender_smem = 0; pl->fwd_smem_bytes = recv_only; break; }
@@ -326,7 +326,7 @@ static int launch_bwd_fast_m(const Dims& d, const WsPtrs& W, const float* bin_w,
     int rc = set_smem(k_exchange_bwd_fast<M>, pl.bwd_smem_bytes);
     if (rc) return rc;
     const int n_rec = d.B, n_sen = d.use_binary ? d.B : 0;
-    MMG_LAUNCH(k_exchange_bwd_fast<M>, n_rec + n_sen, kFastThreads, pl.bwd_smem_bytes, st, d, W, bin_w, code_w, n_rec);
+    MMG_LAUNCH(k_exchange_bwd_fast<M>, n_rec + n_sen, kFastBwdThreads, pl.bwd_smem_bytes, st, d, W, bin_w, code_w, n_rec);
     return check_cuda("k_exchange_bwd_fast");
 }
 

@@ -28,22 +28,23 @@ MMG_DEVICE float dot4(const float4& a, const float4& b, float acc) {
 // ---- image packing (called by k_pre) ---------------------------------------------------------------------------
 MMG_DEVICE float fast_fwd_image_elem(const Dims& d, const FastFwdImage& im, const ParamPtrs& P, int e) {
     const int M = d.M;
-    if (e < im.wb) { const int q = e - im.wc; const int k4 = q >> 10, n = (q >> 2) & 255, c = q & 3;
-        return ldg(P.p[MMG_P_SEN_CODE_W] + (size_t)n * M + 4 * k4 + c); }
+    if (e < im.wb) { const int q = e - im.wc; const int c = q & 3, f4 = q >> 2, half = f4 & 1, n = (f4 >> 1) & 255, qq = f4 >> 9;
+        return ldg(P.p[MMG_P_SEN_CODE_W] + (size_t)n * M + half * (M / 2) + 4 * qq + c); }
     if (e < im.b_code) return ldg(P.p[MMG_P_SEN_BIN_W] + (e - im.wb));
     if (e < im.hw0) return ldg(P.p[MMG_P_SEN_CODE_B] + (e - im.b_code));
     if (e < im.b_b) return 0.f;                                   // hw0: dot role
     if (e < im.sender_end) return ldg(P.p[MMG_P_SEN_BIN_B] + (e - im.b_b));
-    if (e < im.wfull) { const int q = e - im.wih; const int c = q & 3, f4 = q >> 2, part = f4 & 3, k = (f4 >> 2) & 63, gq = f4 >> 8;
-        const int MQ = M / 16, g = gq / MQ, qq = gq % MQ;
-        return ldg(P.p[MMG_P_REC_RNN_WIH] + (size_t)(g * 64 + k) * M + part * (M / 4) + 4 * qq + c); }
-    if (e < im.wghn) { const int q = e - im.wfull; const int c = q & 3, f4 = q >> 2, o = f4 & 255, k4 = f4 >> 8, col = 4 * k4 + c;
+    if (e < im.wfull) { const int q = e - im.wih; const int c = q & 3, f4 = q >> 2, part = f4 & 7, k = (f4 >> 3) & 63, gq = f4 >> 9;
+        const int MQ = M / 32, g = gq / MQ, qq = gq % MQ;
+        return ldg(P.p[MMG_P_REC_RNN_WIH] + (size_t)(g * 64 + k) * M + part * (M / 8) + 4 * qq + c); }
+    if (e < im.wghn) { const int q = e - im.wfull; const int c = q & 3, f4 = q >> 2, half = f4 & 1, o = (f4 >> 1) & 255, qq = f4 >> 9;
+        const int col = half * 32 + 4 * qq + c;
         if (o < 64) return ldg(P.p[MMG_P_REC_Y1_W] + (size_t)o * (64 + d.WV) + col);
         if (o < 128) return ldg(P.p[MMG_P_REC_WH_W] + (size_t)(o - 64) * 64 + col);
         return ldg(P.p[MMG_P_REC_RNN_WHH] + (size_t)(o - 128) * 64 + col); }
-    if (e < im.ww) { const int q = e - im.wghn; const int c = q & 3, f4 = q >> 2, part = f4 & 3, k = (f4 >> 2) & 63, qq = f4 >> 8;
-        return ldg(P.p[MMG_P_REC_RNN_WHH] + (size_t)(128 + k) * 64 + part * 16 + 4 * qq + c); }
-    if (e < im.b_ih) { const int q = e - im.ww; const int c = q & 3, f4 = q >> 2, TPO = 256 / M, KPT = 64 / TPO;
+    if (e < im.ww) { const int q = e - im.wghn; const int c = q & 3, f4 = q >> 2, part = f4 & 7, k = (f4 >> 3) & 63, qq = f4 >> 9;
+        return ldg(P.p[MMG_P_REC_RNN_WHH] + (size_t)(128 + k) * 64 + part * 8 + 4 * qq + c); }
+    if (e < im.b_ih) { const int q = e - im.ww; const int c = q & 3, f4 = q >> 2, TPO = kFastThreads / M, KPT = 64 / TPO;
         const int part = f4 % TPO, j = (f4 / TPO) % M, qq = f4 / (TPO * M);
         return ldg(P.p[MMG_P_REC_W_W] + (size_t)j * 64 + part * KPT + 4 * qq + c); }
     if (e < im.b_full) return ldg(P.p[MMG_P_REC_RNN_BIH] + (e - im.b_ih));
@@ -75,22 +76,27 @@ MMG_DEVICE float fast_bwd_image_elem(const Dims& d, const FastBwdImage& im, cons
 }
 
 // ---- forward -----------------------------------------------------------------------------------------------------
-MMG_HOST_DEVICE int fast_fwd_state_floats(int BT, int M, int D) {
-    // hx, av (256 each) | win, zv (M each) | hv, y1hv, whv, hwv (64 each) | ghv (192) | yv (DP) | sprod, smask | barrier
-    return BT * (2 * kFastHi + 2 * M + 4 * kFastHr + 3 * kFastHr + align4(D)) + align4(2 * BT) + 8;
+// 512 threads (16 warps) per CTA: the step is instruction-issue bound, so each phase is spread over all four
+// schedulers with 4 warps each; K-splits inside a phase meet through 1-4 shuffles.
+MMG_HOST_DEVICE int fast_uni_stride(int M) { return 2 * M + 4; }       // per (example, step): z draws, w draws, stop draw
+MMG_HOST_DEVICE int fast_fwd_state_floats(int BT, int M, int D, int T) {
+    // hx, av (256 each) | win, zv (M each) | hv, y1hv, whv, hwv (64 each) | ghv (192) | yv (DP) | ev (16 warps x DP)
+    // | uniforms (T x stride) | sprod, smask | barrier
+    return BT * (2 * kFastHi + 2 * M + 4 * kFastHr + 3 * kFastHr + align4(D) + (kFastThreads / 32) * align4(D) +
+                 T * fast_uni_stride(M)) + align4(2 * BT) + 8;
 }
 
 template <int BT, int M, bool kSenderSmem>
 MMG_GLOBAL void __launch_bounds__(kFastThreads, 1)
 k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int row_offset) {
-    constexpr int HI = kFastHi, HR = kFastHr, NT = kFastThreads;
-    constexpr int M4 = M / 4, MQ = M / 16, TPO = NT / M, KPT = HR / TPO, OPW = M / 8;
+    constexpr int HI = kFastHi, HR = kFastHr, NT = kFastThreads, NW = NT / 32;
+    constexpr int MQ = M / 32, TPO = NT / M, KPT = HR / TPO, OPW = M / NW, UST = 2 * M + 4;
     MMG_DYN_SMEM(smem_raw);
     float* sm = reinterpret_cast<float*>(smem_raw);
     const FastFwdImage im = make_fast_fwd_image(M, d.D);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b0 = blockIdx.x * BT;
-    const int D = d.D, DP = align4(D), B = d.B;
+    const int D = d.D, DP = align4(D), B = d.B, T = d.T;
     const int img0 = kSenderSmem ? 0 : im.sender_end;
     float* img = sm - img0;
     int o = im.total - img0;
@@ -104,6 +110,8 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
     float* hwv = sm + o;   o += BT * HR;
     float* ghv = sm + o;   o += BT * 3 * HR;
     float* yv = sm + o;    o += BT * DP;
+    float* ev = sm + o;    o += BT * NW * DP;
+    float* uni = sm + o;   o += BT * T * UST;
     float* sprod = sm + o; o += BT;
     float* smask = sm + o; o += BT;
     o = align4(o);
@@ -130,36 +138,63 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
     const float* wdd = img + im.wdd;
     const bool train = in.train != 0;
     const bool binary = d.use_binary != 0;
+    const bool own_draws = train && in.u_sen == nullptr;   // on-device Philox stream (else: injected float64 uniforms)
 
     // ---- prologue ----------------------------------------------------------------------------------------------
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     MMG_SYNCTHREADS();
     pdl_wait();
     if (tid == 0) tma_stage(sm, gimg + img0, (uint32_t)(im.total - img0) * 4u, bar);
-    // h_x rows of this CTA: split-K partials of K_pre summed in a fixed order + bias (model.py:195)
+    {   // h_x rows of this CTA: split-K partials of K_pre summed in a fixed order + bias (model.py:195)
+        const int n = tid >> 1, half = tid & 1;
 #pragma unroll
-    for (int bt = 0; bt < BT; ++bt) {
-        const int b = b0 + bt, n = tid;
-        float v = 0.f;
-        if (b < B) {
-            v = ldg(b_img + n);
-            for (int s = 0; s < W.hx_split; ++s) v += W.hx_part[((size_t)s * B + b) * HI + n];
-            W.h_x[(size_t)b * HI + n] = v;
-        }
-        hx[bt * HI + n] = v;
-        if (n < HR) {
-            float h = 0.f;
-            if (b < B) {
-                if (in.h0 != nullptr) h = in.h0[(size_t)b * HR + n];
-                W.h_z[(size_t)b * HR + n] = h;                        // slot 0 = state entering step 0
+        for (int bt = 0; bt < BT; ++bt) {
+            const int b = b0 + bt;
+            float v = 0.f;
+            if (b < B) for (int s = half; s < W.hx_split; s += 2) v += W.hx_part[((size_t)s * B + b) * HI + n];
+            v = group_sum<2>(v);
+            if (b < B) v += ldg(b_img + n);
+            if (half == 0) {
+                hx[bt * HI + n] = v;
+                if (b < B) W.h_x[(size_t)b * HI + n] = v;
             }
-            hv[bt * HR + n] = h;
+            if (tid < HR) {
+                float h = 0.f;
+                if (b < B) {
+                    if (in.h0 != nullptr) h = in.h0[(size_t)b * HR + tid];
+                    W.h_z[(size_t)b * HR + tid] = h;                    // slot 0 = state entering step 0
+                }
+                hv[bt * HR + tid] = h;
+            }
+            if (tid < M) {
+                win[bt * M + tid] = d.first_rec;                        // model.py:786
+                if (b < B) W.rec_feats[(size_t)b * M + tid] = d.first_rec;   // slot 0
+            }
+            if (tid == 0) { sprod[bt] = 1.f; smask[bt] = 1.f; if (b < B) W.stop_mask[b] = 1; }
         }
-        if (n < M) {
-            win[bt * M + n] = d.first_rec;                            // model.py:786
-            if (b < B) W.rec_feats[(size_t)b * M + n] = d.first_rec;  // slot 0
+    }
+    if (own_draws) {
+        // every Bernoulli draw of this CTA's conversations up front (same Philox counters as the generic kernel:
+        // stream = 4 t + {0 sender, 1 stop, 2 receiver}, counter = row * 65536 + column / 4)
+        const unsigned long long seed = W.rng_state[0], iter = W.rng_state[1];
+        constexpr int GPS = 2 * (M / 4) + 1;                             // 4-wide groups per (example, step)
+        for (int idx = tid; idx < BT * T * GPS; idx += NT) {
+            const int g = idx % GPS, t = (idx / GPS) % T, bt = idx / (GPS * T);
+            const unsigned row = (unsigned)(b0 + bt + row_offset);
+            float r[4];
+            float* dst = uni + (bt * T + t) * UST;
+            if (g < M / 4) {
+                philox_uniform4(seed, iter, t * 4 + 0, row * 65536u + g, r);
+                dst += 4 * g;
+            } else if (g < 2 * (M / 4)) {
+                philox_uniform4(seed, iter, t * 4 + 2, row * 65536u + (g - M / 4), r);
+                dst += M + 4 * (g - M / 4);
+            } else {
+                philox_uniform4(seed, iter, t * 4 + 1, row * 65536u, r);
+                dst += 2 * M;
+            }
+            dst[0] = r[0]; dst[1] = r[1]; dst[2] = r[2]; dst[3] = r[3];
         }
-        if (n == 0) { sprod[bt] = 1.f; smask[bt] = 1.f; if (b < B) W.stop_mask[b] = 1; }
     }
 #ifdef MMG_CPU_EMU
     MMG_SYNCTHREADS();
@@ -167,58 +202,59 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
     mbar_wait(bar, 0);
     MMG_SYNCTHREADS();
 
-    unsigned long long seed = 0, iter = 0;
-    if (train && in.u_sen == nullptr) { seed = W.rng_state[0]; iter = W.rng_state[1]; }
-
     // Heads phase: everything that only needs h' — class-score / message-head pre-activations, the STOP bit and
     // W_hh . h' + b_hh for the NEXT step's gates.  `t < 0`: prologue call, only the W_hh part is kept.
     auto heads = [&](int t) {
-        {   // rows [y1h ; w_h ; gh_r ; gh_u]: one output per thread, K = 64
-            float acc[BT];
-            const float bias = b_full[tid];
-#pragma unroll
-            for (int bt = 0; bt < BT; ++bt) acc[bt] = bias;
-#pragma unroll
-            for (int k4 = 0; k4 < HR / 4; ++k4) {
-                const float4 w = Wfull4[k4 * NT + tid];
-#pragma unroll
-                for (int bt = 0; bt < BT; ++bt)
-                    acc[bt] = dot4(w, *reinterpret_cast<const float4*>(hv + bt * HR + 4 * k4), acc[bt]);
-            }
-#pragma unroll
-            for (int bt = 0; bt < BT; ++bt) {
-                const int b = b0 + bt;
-                if (tid < HR) {
-                    if (t >= 0) {
-                        y1hv[bt * HR + tid] = acc[bt];
-                        if (b < B) W.y1h[((size_t)t * B + b) * HR + tid] = acc[bt];
-                    }
-                } else if (tid < 2 * HR) {
-                    whv[bt * HR + tid - HR] = acc[bt];
-                } else {
-                    ghv[bt * 3 * HR + tid - 2 * HR] = acc[bt];
-                }
-            }
-        }
-        {   // rows gh_n: 4 threads per output, 16 reduction elements each
-            const int k = tid >> 2, part = tid & 3;
+        {   // rows [y1h ; w_h ; gh_r ; gh_u]: two threads per output, 32 reduction elements each
+            const int oo = tid >> 1, half = tid & 1;
             float acc[BT];
 #pragma unroll
             for (int bt = 0; bt < BT; ++bt) acc[bt] = 0.f;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 w = Wghn4[(q * HR + k) * 4 + part];
+            for (int q = 0; q < 8; ++q) {
+                const float4 w = Wfull4[(q * 256 + oo) * 2 + half];
 #pragma unroll
                 for (int bt = 0; bt < BT; ++bt)
-                    acc[bt] = dot4(w, *reinterpret_cast<const float4*>(hv + bt * HR + part * 16 + 4 * q), acc[bt]);
+                    acc[bt] = dot4(w, *reinterpret_cast<const float4*>(hv + bt * HR + half * 32 + 4 * q), acc[bt]);
+            }
+            const float bias = b_full[oo];
+#pragma unroll
+            for (int bt = 0; bt < BT; ++bt) {
+                const float v = group_sum<2>(acc[bt]) + bias;
+                const int b = b0 + bt;
+                if (half == 0) {
+                    if (oo < HR) {
+                        if (t >= 0) {
+                            y1hv[bt * HR + oo] = v;
+                            if (b < B) W.y1h[((size_t)t * B + b) * HR + oo] = v;
+                        }
+                    } else if (oo < 2 * HR) {
+                        whv[bt * HR + oo - HR] = v;
+                    } else {
+                        ghv[bt * 3 * HR + oo - 2 * HR] = v;
+                    }
+                }
+            }
+        }
+        {   // rows gh_n: 8 threads per output, 8 reduction elements each
+            const int k = tid >> 3, part = tid & 7;
+            float acc[BT];
+#pragma unroll
+            for (int bt = 0; bt < BT; ++bt) acc[bt] = 0.f;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float4 w = Wghn4[(q * HR + k) * 8 + part];
+#pragma unroll
+                for (int bt = 0; bt < BT; ++bt)
+                    acc[bt] = dot4(w, *reinterpret_cast<const float4*>(hv + bt * HR + part * 8 + 4 * q), acc[bt]);
             }
 #pragma unroll
             for (int bt = 0; bt < BT; ++bt) {
-                const float v = group_sum<4>(acc[bt]);
+                const float v = group_sum<8>(acc[bt]);
                 if (part == 0) ghv[bt * 3 * HR + 2 * HR + k] = b_ghn[k] + v;
             }
         }
-        if (t >= 0 && warp == NT / 32 - 1) {   // STOP bit (model.py:414-429, 852)
+        if (t >= 0 && warp == NW - 1) {   // STOP bit (model.py:414-429, 852)
 #pragma unroll
             for (int bt = 0; bt < BT; ++bt) {
                 float v = wsv[lane] * hv[bt * HR + lane] + wsv[lane + 32] * hv[bt * HR + lane + 32];
@@ -229,7 +265,9 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
                     const float sp = sigmoidf_(v + img[im.misc + 1]);
                     float sbit;
                     if (train) {
-                        sbit = (b < B) ? draw_bit(in.u_stop, row, sp, seed, iter, t * 4 + 1, b + row_offset, 0) : 0.f;
+                        if (b >= B) sbit = 0.f;
+                        else if (own_draws) sbit = (uni[(bt * T + t) * UST + 2 * M] < sp) ? 1.f : 0.f;
+                        else sbit = (in.u_stop[row] < (double)sp) ? 1.f : 0.f;
                     } else {
                         const float prod = (t == 0 || !d.s_prob_prod) ? sp : sprod[bt] * sp;
                         sprod[bt] = prod;
@@ -248,39 +286,36 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
     };
 
     heads(-1);                                   // gh for step 0 from the initial state
-    const float4 w2a = w2_4[lane & 7], w2b = w2_4[8 + (lane & 7)];
+    const float4 w2q = w2_4[lane & 15];
     const float y2b = img[im.misc];
     MMG_SYNCTHREADS();
 
-    for (int t = 0; t < d.T; ++t) {
-        // ---- P1: sender hidden a = tanh(h_x + code_layer(w_prev)) (model.py:199-216) ------------------------------
+    for (int t = 0; t < T; ++t) {
+        // ---- P1: sender hidden a = tanh(h_x + code_layer(w_prev)) (model.py:199-216): 2 threads per unit ----------
         {
+            const int n = tid >> 1, half = tid & 1;
             float acc[BT];
-            if (t == 0) {
-                const float v = hw0[tid];
 #pragma unroll
-                for (int bt = 0; bt < BT; ++bt) acc[bt] = v;
-            } else {
-                const float v = b_code[tid];
+            for (int bt = 0; bt < BT; ++bt) acc[bt] = 0.f;
+            if (t > 0) {
 #pragma unroll
-                for (int bt = 0; bt < BT; ++bt) acc[bt] = v;
-#pragma unroll
-                for (int k4 = 0; k4 < M4; ++k4) {
-                    const float4 w = kSenderSmem ? Wc4[k4 * HI + tid] : ldg4(Wc4 + k4 * HI + tid);
+                for (int q = 0; q < M / 8; ++q) {
+                    const float4 w = kSenderSmem ? Wc4[(q * HI + n) * 2 + half] : ldg4(Wc4 + (q * HI + n) * 2 + half);
 #pragma unroll
                     for (int bt = 0; bt < BT; ++bt)
-                        acc[bt] = dot4(w, *reinterpret_cast<const float4*>(win + bt * M + 4 * k4), acc[bt]);
+                        acc[bt] = dot4(w, *reinterpret_cast<const float4*>(win + bt * M + half * (M / 2) + 4 * q), acc[bt]);
                 }
             }
+            const float base = (t == 0) ? hw0[n] : b_code[n];
 #pragma unroll
             for (int bt = 0; bt < BT; ++bt) {
                 const int b = b0 + bt;
-                const float a = tanhf(hx[bt * HI + tid] + acc[bt]);
-                av[bt * HI + tid] = a;
-                if (b < B) {
-                    W.a_s[((size_t)t * B + b) * HI + tid] = a;
-                    if (t > 0 && tid < M) W.code_in[((size_t)t * B + b) * M + tid] = win[bt * M + tid];
+                const float a = tanhf(hx[bt * HI + n] + (base + group_sum<2>(acc[bt])));
+                if (half == 0) {
+                    av[bt * HI + n] = a;
+                    if (b < B) W.a_s[((size_t)t * B + b) * HI + n] = a;
                 }
+                if (t > 0 && tid < M && b < B) W.code_in[((size_t)t * B + b) * M + tid] = win[bt * M + tid];
             }
         }
         MMG_SYNCTHREADS();
@@ -316,8 +351,13 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
                     float p = 0.f, zval;
                     if (binary) {
                         p = sigmoidf_(logit);
-                        if (train) zval = (b < B) ? draw_bit(in.u_sen, row * M + j, p, seed, iter, t * 4 + 0, b + row_offset, j) : 0.f;
-                        else       zval = rintf(p);
+                        if (train) {
+                            if (b >= B) zval = 0.f;
+                            else if (own_draws) zval = (uni[(bt * T + t) * UST + j] < p) ? 1.f : 0.f;
+                            else zval = (in.u_sen[row * M + j] < (double)p) ? 1.f : 0.f;
+                        } else {
+                            zval = rintf(p);
+                        }
                     } else {
                         zval = logit;
                     }
@@ -333,7 +373,7 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
         MMG_SYNCTHREADS();
         // ---- P3: GRU step (model.py:340), gate order r,z,n; W_hh . h + b_hh is already in ghv ----------------------
         {
-            const int k = tid >> 2, part = tid & 3;
+            const int k = tid >> 3, part = tid & 7;
             float g[BT][3];
 #pragma unroll
             for (int bt = 0; bt < BT; ++bt) { g[bt][0] = 0.f; g[bt][1] = 0.f; g[bt][2] = 0.f; }
@@ -341,24 +381,26 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
             for (int gate = 0; gate < 3; ++gate)
 #pragma unroll
                 for (int q = 0; q < MQ; ++q) {
-                    const float4 w = Wih4[((gate * MQ + q) * HR + k) * 4 + part];
+                    const float4 w = Wih4[((gate * MQ + q) * HR + k) * 8 + part];
 #pragma unroll
                     for (int bt = 0; bt < BT; ++bt)
-                        g[bt][gate] = dot4(w, *reinterpret_cast<const float4*>(zv + bt * M + part * (M / 4) + 4 * q), g[bt][gate]);
+                        g[bt][gate] = dot4(w, *reinterpret_cast<const float4*>(zv + bt * M + part * (M / 8) + 4 * q), g[bt][gate]);
                 }
 #pragma unroll
             for (int bt = 0; bt < BT; ++bt) {
-                const float gi_r = group_sum<4>(g[bt][0]) + b_ih[k];
-                const float gi_u = group_sum<4>(g[bt][1]) + b_ih[HR + k];
-                const float gi_n = group_sum<4>(g[bt][2]) + b_ih[2 * HR + k];
+                const float gi_r = group_sum<8>(g[bt][0]) + b_ih[k];
+                const float gi_u = group_sum<8>(g[bt][1]) + b_ih[HR + k];
+                const float gi_n = group_sum<8>(g[bt][2]) + b_ih[2 * HR + k];
+                const float gh_r = ghv[bt * 3 * HR + k], gh_u = ghv[bt * 3 * HR + HR + k], gh_n = ghv[bt * 3 * HR + 2 * HR + k];
+                // one sigmoid instruction stream serves both gates: lane part 0 evaluates r, lane part 1 evaluates u
+                const float sg = sigmoidf_((part & 1) ? (gi_u + gh_u) : (gi_r + gh_r));
+                const float r = shfl_xor_f(sg, part), u = shfl_xor_f(sg, part ^ 1);
+                const float nn = tanhf(gi_n + r * gh_n);
+                const float hp = hv[bt * HR + k];
+                const float hn = nn + u * (hp - nn);
+                MMG_SYNCWARP();                      // every lane of the group has read hv[k] before it is overwritten
                 if (part == 0) {
                     const int b = b0 + bt;
-                    const float gh_r = ghv[bt * 3 * HR + k], gh_u = ghv[bt * 3 * HR + HR + k], gh_n = ghv[bt * 3 * HR + 2 * HR + k];
-                    const float r = sigmoidf_(gi_r + gh_r);
-                    const float u = sigmoidf_(gi_u + gh_u);
-                    const float nn = tanhf(gi_n + r * gh_n);
-                    const float hp = hv[bt * HR + k];
-                    const float hn = nn + u * (hp - nn);
                     hv[bt * HR + k] = hn;
                     if (b < B) {
                         const size_t row = (size_t)t * B + b;
@@ -373,32 +415,25 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
         // ---- P4: heads of h' + STOP bit + W_hh . h' for the next step ------------------------------------------------
         heads(t);
         MMG_SYNCTHREADS();
-        // ---- P5: class scores y[d] = y2(relu(y1h + y1d[d])) (model.py:432-433): 8 lanes per class -----------------
+        // ---- P5: class scores y[d] = y2(relu(y1h + y1d[d])) (model.py:432-433): 16 lanes per class ----------------
         {
-            const int sub = lane & 7, cw = lane >> 3;
-            float4 ya[BT], yb[BT];
+            const int sub = lane & 15, cw = lane >> 4;
+            float4 ya[BT];
 #pragma unroll
-            for (int bt = 0; bt < BT; ++bt) {
-                ya[bt] = *reinterpret_cast<const float4*>(y1hv + bt * HR + 4 * sub);
-                yb[bt] = *reinterpret_cast<const float4*>(y1hv + bt * HR + 32 + 4 * sub);
-            }
-            for (int c0 = 0; c0 < D; c0 += 32) {
-                const int cls = c0 + warp * 4 + cw;
+            for (int bt = 0; bt < BT; ++bt) ya[bt] = *reinterpret_cast<const float4*>(y1hv + bt * HR + 4 * sub);
+            for (int c0 = 0; c0 < D; c0 += 2 * NW) {
+                const int cls = c0 + warp * 2 + cw;
                 const bool valid = cls < D;
-                float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-                if (valid) { r0 = y1d4[cls * 16 + sub]; r1 = y1d4[cls * 16 + 8 + sub]; }
+                float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) r0 = y1d4[cls * 16 + sub];
 #pragma unroll
                 for (int bt = 0; bt < BT; ++bt) {
                     float s = 0.f;
-                    s = fmaf(w2a.x, fmaxf(0.f, ya[bt].x + r0.x), s);
-                    s = fmaf(w2a.y, fmaxf(0.f, ya[bt].y + r0.y), s);
-                    s = fmaf(w2a.z, fmaxf(0.f, ya[bt].z + r0.z), s);
-                    s = fmaf(w2a.w, fmaxf(0.f, ya[bt].w + r0.w), s);
-                    s = fmaf(w2b.x, fmaxf(0.f, yb[bt].x + r1.x), s);
-                    s = fmaf(w2b.y, fmaxf(0.f, yb[bt].y + r1.y), s);
-                    s = fmaf(w2b.z, fmaxf(0.f, yb[bt].z + r1.z), s);
-                    s = fmaf(w2b.w, fmaxf(0.f, yb[bt].w + r1.w), s);
-                    s = group_sum<8>(s);
+                    s = fmaf(w2q.x, fmaxf(0.f, ya[bt].x + r0.x), s);
+                    s = fmaf(w2q.y, fmaxf(0.f, ya[bt].y + r0.y), s);
+                    s = fmaf(w2q.z, fmaxf(0.f, ya[bt].z + r0.z), s);
+                    s = fmaf(w2q.w, fmaxf(0.f, ya[bt].w + r0.w), s);
+                    s = group_sum<16>(s);
                     if (sub == 0 && valid) {
                         s += y2b;
                         yv[bt * DP + cls] = s;
@@ -410,31 +445,36 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
         }
         MMG_SYNCTHREADS();
         // ---- P6: q = softmax(y) (detached, model.py:441); h_w = tanh(w_h(h') + sum_d q_d wdd[d]) (442-452) ----------
+        // every warp evaluates the D exponentials once into its own strip of shared memory (no block barrier)
         {
-            const int k = tid >> 2, part = tid & 3;
+            const int k = tid >> 3, part = tid & 7;
 #pragma unroll
             for (int bt = 0; bt < BT; ++bt) {
                 const int b = b0 + bt;
+                float* e = ev + (bt * NW + warp) * DP;
                 float mx = -INFINITY;
                 for (int dd = lane; dd < D; dd += 32) mx = fmaxf(mx, yv[bt * DP + dd]);
                 mx = warp_max(mx);
-                float acc = 0.f, se = 0.f;
-                for (int dd = part; dd < D; dd += 4) {
-                    const float e = expf(yv[bt * DP + dd] - mx);
-                    se += e;
-                    acc = fmaf(e, wdd[((dd >> 2) * HR + k) * 4 + part], acc);
+                float se = 0.f;
+                for (int dd = lane; dd < D; dd += 32) {
+                    const float x = expf(yv[bt * DP + dd] - mx);
+                    e[dd] = x;
+                    se += x;
                 }
-                acc = group_sum<4>(acc);
-                se = group_sum<4>(se);
+                se = warp_sum(se);
                 const float inv = 1.f / se;
-                if (train && b < B)
-                    for (int dd = tid; dd < D; dd += NT)
-                        W.q[((size_t)t * B + b) * D + dd] = expf(yv[bt * DP + dd] - mx) * inv;
+                MMG_SYNCWARP();
+                if (train && warp == 0 && b < B)
+                    for (int dd = lane; dd < D; dd += 32) W.q[((size_t)t * B + b) * D + dd] = e[dd] * inv;
+                float acc = 0.f;
+                for (int dd = part; dd < D; dd += 8) acc = fmaf(e[dd], wdd[((dd >> 3) * HR + k) * 8 + part], acc);
+                acc = group_sum<8>(acc);
                 if (part == 0) {
                     const float hw = tanhf(whv[bt * HR + k] + acc * inv);
                     hwv[bt * HR + k] = hw;
                     if (b < B) W.h_w[((size_t)t * B + b) * HR + k] = hw;
                 }
+                MMG_SYNCWARP();
             }
         }
         MMG_SYNCTHREADS();
@@ -461,8 +501,13 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
                     float p = 0.f, wv;
                     if (binary) {
                         p = sigmoidf_(logit);
-                        if (train) wv = (b < B) ? draw_bit(in.u_rec, row * M + j, p, seed, iter, t * 4 + 2, b + row_offset, j) : 0.f;
-                        else       wv = rintf(p);
+                        if (train) {
+                            if (b >= B) wv = 0.f;
+                            else if (own_draws) wv = (uni[(bt * T + t) * UST + M + j] < p) ? 1.f : 0.f;
+                            else wv = (in.u_rec[row * M + j] < (double)p) ? 1.f : 0.f;
+                        } else {
+                            wv = rintf(p);
+                        }
                         if (d.ignore_receiver) wv = 0.f;
                     } else {
                         wv = logit;
@@ -483,15 +528,15 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
 // ---- backward ------------------------------------------------------------------------------------------------------
 // One example per CTA.  CTAs [0, n_rec): receiver (BPTT); the rest: sender (no recurrence, model.py:807-811).
 MMG_HOST_DEVICE int fast_bwd_rec_state_floats(int T, int M, int D) {
-    // dlw (T,M) | dhw (T,64) | inj (T,64) | gat (T,5,64) | dgh (2,192) | gv (64) | gout (DP) | dls (T) | barrier
-    return T * M + 2 * T * kFastHr + 5 * T * kFastHr + 2 * 3 * kFastHr + kFastHr + align4(D) + align4(T) + 8;
+    // dlw (T,M) | dhw (T,64) | inj (T,64) | gat (T,5,64) | hws, y1hs (T,64 each) | dgh (2,192) | gv (64) | gout (DP) | dls (T) | barrier
+    return T * M + 2 * T * kFastHr + 5 * T * kFastHr + 2 * T * kFastHr + 2 * 3 * kFastHr + kFastHr + align4(D) + align4(T) + 8;
 }
-MMG_HOST_DEVICE int fast_bwd_sen_state_floats(int T, int M) { return T * M + 2 * kFastHi + 8; }
+MMG_HOST_DEVICE int fast_bwd_sen_state_floats(int T, int M) { return T * M + 2 * kFastHi + T * kFastHi + 8; }
 
 template <int M>
-MMG_GLOBAL void __launch_bounds__(kFastThreads, 1)
+MMG_GLOBAL void __launch_bounds__(kFastBwdThreads, 1)
 k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, int n_rec_ctas) {
-    constexpr int HI = kFastHi, HR = kFastHr, NT = kFastThreads, M4 = M / 4;
+    constexpr int HI = kFastHi, HR = kFastHr, NT = kFastBwdThreads, M4 = M / 4;
     MMG_DYN_SMEM(smem_raw);
     float* sm = reinterpret_cast<float*>(smem_raw);
     const int tid = threadIdx.x;
@@ -506,6 +551,10 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
         float wb[M];                                                   // column n of binary_layer.weight
 #pragma unroll
         for (int j = 0; j < M; ++j) wb[j] = ldg(bin_w + (size_t)j * HI + n);
+        float* das0 = sm + T * M;                                     // (256) d a at t = 0
+        float* cred = das0 + HI;                                      // (256 / M, M) partial sums
+        float* as_s = cred + HI;                                      // (T, 256) saved tanh outputs of this example
+        for (int t = 0; t < T; ++t) as_s[t * HI + n] = W.a_s[((size_t)t * B + b) * HI + n];
         for (int idx = tid; idx < T * M; idx += NT) {
             const int t = idx / M, j = idx % M;
             const size_t i = ((size_t)t * B + b) * M + j;
@@ -515,13 +564,11 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
             dlz[idx] = dl;
         }
         MMG_SYNCTHREADS();
-        float* das0 = sm + T * M;                                     // (256) d a at t = 0
-        float* cred = das0 + HI;                                      // (256 / M, M) partial sums
         float dhx = 0.f;
 #pragma unroll 2
         for (int t = 0; t < T; ++t) {
             const size_t i = ((size_t)t * B + b) * HI + n;
-            const float a = W.a_s[i];
+            const float a = as_s[t * HI + n];
             float acc = 0.f;
 #pragma unroll
             for (int j4 = 0; j4 < M4; ++j4) {
@@ -568,6 +615,8 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
     float* dhw = sm + o;  o += T * HR;
     float* inj = sm + o;  o += T * HR;
     float* gat = sm + o;  o += 5 * T * HR;          // per step: r, u, n, gh_n, h_prev
+    float* hws = sm + o;  o += T * HR;              // h_w of every step
+    float* y1hs = sm + o; o += T * HR;              // y1h of every step (the prediction step is only known after the load)
     float* dghv = sm + o; o += 2 * 3 * HR;
     float* gv = sm + o;   o += HR;
     float* gout = sm + o; o += DP;
@@ -605,6 +654,8 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
     for (int idx = tid; idx < T * HR; idx += NT) {
         const int t = idx >> 6, k = idx & 63;
         gat[t * 5 * HR + 4 * HR + k] = W.h_z[((size_t)t * B + b) * HR + k];   // slot t = state entering step t
+        hws[idx] = W.h_w[((size_t)t * B + b) * HR + k];
+        y1hs[idx] = W.y1h[((size_t)t * B + b) * HR + k];
     }
     for (int t = tid; t < T; t += NT) {
         const size_t row = (size_t)t * B + b;
@@ -627,14 +678,14 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
 #pragma unroll
         for (int j4 = 0; j4 < M4; ++j4) acc = dot4(WwT4[j4 * HR + k], *reinterpret_cast<const float4*>(dlw + t * M + 4 * j4), acc);
         const size_t i = ((size_t)t * B + b) * HR + k;
-        const float hw = W.h_w[i];
+        const float hw = hws[t * HR + k];
         const float v = acc * (1.f - hw * hw);                        // through tanh (model.py:452)
         W.d_hw[i] = v;
         dhw[t * HR + k] = v;
     }
     {
         // y[d] = y2.bias + sum_k w2[k] relu(y1h[k] + y1d[d][k])   (model.py:432-433)
-        const float yh = W.y1h[((size_t)ys * B + b) * HR + k], wk = w2[k];
+        const float yh = y1hs[ys * HR + k], wk = w2[k];
         float G = 0.f, dw2 = 0.f;
         for (int dd = part; dd < D; dd += 4) {
             const float g = gout[dd];

@@ -92,38 +92,50 @@ k_stats(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in) {
         for (int j = 0; j < W.ntb; ++j) { s += W.bs_part[(size_t)r * W.ntb + j]; q += W.br_part[(size_t)r * W.ntb + j]; }
         W.bs[r] = s; W.br[r] = q;
     }
-    // ---- per example: prediction step, log-softmax, log-likelihood, argmax, top-k, dNLL/d outp ------------------
+    // ---- per example (one warp each, lanes over classes): prediction step, log-softmax, log-likelihood, argmax,
+    //      top-k, dNLL/d outp ------------------------------------------------------------------------------------------
     MMG_SHARED double s_red[2][kStatsThreads / 32];
     double nll_local = 0.0, correct_local = 0.0;
-    for (int b = tid; b < d.B; b += kStatsThreads) {
+    const float invB = 1.0f / (float)d.Bg;
+    for (int b = warp; b < d.B; b += nwarps) {
         int ts = d.T - 1;
-        if (!d.fixed) {
-            for (int t = 0; t < d.T; ++t) if (W.stop_mask[(size_t)(t + 1) * d.B + b] == 0) { ts = t; break; }
+        if (!d.fixed) {   // first step whose outgoing mask is 0 (model.py:893-896); the last mask is forced to 0 (870)
+            float first = (float)(d.T - 1);
+            for (int t = lane; t < d.T; t += 32)
+                if (W.stop_mask[(size_t)(t + 1) * d.B + b] == 0) first = fminf(first, (float)t);
+            ts = (int)(-warp_max(-first));
         }
-        W.ystep[b] = ts;
         const float* yy = W.y + ((size_t)ts * d.B + b) * d.D;
-        float mx = -INFINITY; int am = 0;
-        for (int dd = 0; dd < d.D; ++dd) { const float v = yy[dd]; if (v > mx) { mx = v; am = dd; } }
-        float se = 0.f;
-        for (int dd = 0; dd < d.D; ++dd) se += expf(yy[dd] - mx);
-        const float lse = mx + logf(se);
         const int tg = (int)in.target[b];
-        const float lt = yy[tg] - lse;
-        int rank = 0;
-        const float invB = 1.0f / (float)d.Bg;
-        for (int dd = 0; dd < d.D; ++dd) {
+        const float ytg = yy[tg];
+        float mx = -INFINITY;
+        for (int dd = lane; dd < d.D; dd += 32) mx = fmaxf(mx, yy[dd]);
+        mx = warp_max(mx);
+        float am = 3.0e9f, se = 0.f, rank = 0.f;
+        for (int dd = lane; dd < d.D; dd += 32) {
+            const float v = yy[dd];
+            if (v == mx) am = fminf(am, (float)dd);          // first index of the maximum, like a serial `>` scan
+            se += expf(v - mx);
+            if (v > ytg) rank += 1.f;
+        }
+        am = -warp_max(-am);
+        se = warp_sum(se);
+        rank = warp_sum(rank);
+        const float lse = mx + logf(se);
+        const float lt = ytg - lse;
+        for (int dd = lane; dd < d.D; dd += 32) {
             const float v = yy[dd];
             W.outp[(size_t)b * d.D + dd] = v;
-            if (v > yy[tg]) ++rank;
             W.g_outp[(size_t)b * d.D + dd] = (expf(v - lse) - (dd == tg ? 1.f : 0.f)) * invB;   // d nll / d outp
         }
-        W.logs[b] = lt;
-        W.argmax[b] = am;
-        nll_local -= (double)lt;
-        if (rank < in.top_k) correct_local += 1.0;
+        if (lane == 0) {
+            W.ystep[b] = ts;
+            W.logs[b] = lt;
+            W.argmax[b] = (int)am;
+            nll_local -= (double)lt;
+            if ((int)rank < in.top_k) correct_local += 1.0;
+        }
     }
-    nll_local = warp_sum_d(nll_local);
-    correct_local = warp_sum_d(correct_local);
     if (lane == 0) { s_red[0][warp] = nll_local; s_red[1][warp] = correct_local; }
     MMG_SYNCTHREADS();
     if (tid == 0) {
@@ -316,13 +328,22 @@ k_lossgrad(Dims d, mmg_config cfg, WsPtrs W) {
     nl = warp_sum_d(nl);
     if (lane == 0) nll_red[warp] = nl;
     MMG_SYNCTHREADS();
+    // per-CTA partials: thread c sums CTAs c, c + 256, ...; then a fixed shuffle tree and 8 warp totals
+    double part[5] = {0, 0, 0, 0, 0};
+    for (unsigned c = tid; c < gridDim.x; c += kLossThreads)
+        for (int i = 0; i < 5; ++i) part[i] += W.loss_part[(size_t)c * 8 + i];
+    for (int i = 0; i < 5; ++i) {
+        const double v = warp_sum_d(part[i]);
+        if (lane == 0) red[i][warp] = v;
+    }
+    MMG_SYNCTHREADS();
     if (tid == 0) {
         double v[6];
         v[0] = 0;
         for (int w = 0; w < kLossThreads / 32; ++w) v[0] += nll_red[w];
         for (int i = 0; i < 5; ++i) {
             double a = 0;
-            for (unsigned c = 0; c < gridDim.x; ++c) a += W.loss_part[(size_t)c * 8 + i];
+            for (int w = 0; w < kLossThreads / 32; ++w) a += red[i][w];
             v[i + 1] = a;
         }
         float* L = W.losses;
