@@ -132,6 +132,7 @@ static void ws_layout(const Dims& d, Ws* w) {
     w->h1r = take(c, R * d.Hb * f);
     w->bs_part = take(c, R * w->ntb * f);
     w->br_part = take(c, R * w->ntb * f);
+    w->ubs = take(c, B * d.Hb * f);
     int hs = d.F / 128;
     if (hs < 1) hs = 1;
     if (hs > kHxSplitMax) hs = kHxSplitMax;
@@ -182,7 +183,7 @@ static WsPtrs resolve(const Ws& w, void* base) {
     r.stats = (double*)(b + p.stats);
     r.rng_state = (unsigned long long*)(b + p.rng_state);
 #define G_(name) r.name = (float*)(b + w.name)
-    G_(code_in); G_(a_s); G_(gates); G_(y1h); G_(q); G_(wd); G_(rowstat); G_(h1s); G_(h1r); G_(bs_part); G_(br_part);
+    G_(code_in); G_(a_s); G_(gates); G_(y1h); G_(q); G_(wd); G_(rowstat); G_(h1s); G_(h1r); G_(bs_part); G_(br_part); G_(ubs);
     G_(hx_part); G_(fwd_image); G_(bwd_image); G_(d_lz); G_(d_as); G_(dhx); G_(dgi); G_(dgh); G_(d_lw); G_(d_hw);
     G_(d_ls); G_(g_h); G_(hsel); G_(dy1); G_(dw2p); G_(dcode_part); G_(slabs); G_(norm_part);
 #undef G_
@@ -232,10 +233,18 @@ static bool make_fast_plan(const Dims& d, Plan* pl) {
     if (pl->bwd_smem_bytes > kMaxSmem) return false;
     int bt = d.B <= 148 ? 1 : (d.B <= 2 * 148 ? 2 : 4);
     for (; bt >= 1; bt /= 2) {
-        const int st = fast_fwd_state_floats(bt, d.M, d.D, d.T);
-        const int full = (fi.total + st) * 4, recv_only = (fi.total - fi.sender_end + st) * 4;
-        if (d.M == 32 && full <= kMaxSmem) { pl->sender_smem = 1; pl->fwd_smem_bytes = full; break; }
-        if (recv_only <= kMaxSmem) { pl->sender_smem = 0; pl->fwd_smem_bytes = recv_only; break; }
+        int st = fast_fwd_state_floats(bt, d.M, d.D, d.T);
+#ifdef MMG_PHASE_TIMING
+        st += d.T * 64 + 8;
+#endif
+        // msg_dim 32: every loop matrix in registers; msg_dim 64: receiver in registers, sender section in shared memory
+        const int tail = fi.total - fi.b_ih;
+        const int need = ((d.M == 32 ? 0 : fi.sender_end) + tail + st) * 4;
+        if (need <= kMaxSmem) {
+            pl->sender_smem = d.M == 32 ? 0 : 1;
+            pl->fwd_smem_bytes = need > (int)kGemmSmemFloats * 4 ? need : (int)kGemmSmemFloats * 4;   // side-role GEMM tiles
+            break;
+        }
     }
     if (bt < 1) return false;
     pl->BT = bt;
@@ -296,29 +305,31 @@ static int launch_bwd(const Dims& d, const WsPtrs& W, const Plan& pl, cudaStream
     return check_cuda("k_exchange_bwd");
 }
 
+struct FastFwdArgs { const float* b_img; const float* bs_w1; const float* bs_b1; };
 template <int BT, int M, bool SS>
-static int launch_fwd_fast_one(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const float* b_img, const Plan& pl,
+static int launch_fwd_fast_one(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const FastFwdArgs& fa, const Plan& pl,
                                cudaStream_t st) {
     auto kern = k_exchange_fwd_fast<BT, M, SS>;
     int rc = set_smem(kern, pl.fwd_smem_bytes);
     if (rc) return rc;
-    MMG_LAUNCH(kern, cdiv(d.B, BT), kFastThreads, pl.fwd_smem_bytes, st, d, W, in, b_img, 0);
+    const int n_conv = cdiv(d.B, BT);
+    const int n_side = in.train ? cdiv(d.B, kTile) * cdiv(d.Hb, kTile) : 0;     // baseline pre-activation tiles
+    MMG_LAUNCH(kern, n_conv + n_side, kFastThreads, pl.fwd_smem_bytes, st, d, W, in, fa.b_img, 0, fa.bs_w1, fa.bs_b1, n_conv);
     return check_cuda("k_exchange_fwd_fast");
 }
 template <int M, bool SS>
-static int launch_fwd_fast_bt(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const float* b_img, const Plan& pl,
+static int launch_fwd_fast_bt(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const FastFwdArgs& fa, const Plan& pl,
                               cudaStream_t st) {
     switch (pl.BT) {
-        case 1: return launch_fwd_fast_one<1, M, SS>(d, W, in, b_img, pl, st);
-        case 2: return launch_fwd_fast_one<2, M, SS>(d, W, in, b_img, pl, st);
-        default: return launch_fwd_fast_one<4, M, SS>(d, W, in, b_img, pl, st);
+        case 1: return launch_fwd_fast_one<1, M, SS>(d, W, in, fa, pl, st);
+        case 2: return launch_fwd_fast_one<2, M, SS>(d, W, in, fa, pl, st);
+        default: return launch_fwd_fast_one<4, M, SS>(d, W, in, fa, pl, st);
     }
 }
-static int launch_fwd_fast(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const float* b_img, const Plan& pl,
+static int launch_fwd_fast(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const FastFwdArgs& fa, const Plan& pl,
                            cudaStream_t st) {
-    if (d.M == 32) return pl.sender_smem ? launch_fwd_fast_bt<32, true>(d, W, in, b_img, pl, st)
-                                         : launch_fwd_fast_bt<32, false>(d, W, in, b_img, pl, st);
-    return launch_fwd_fast_bt<64, false>(d, W, in, b_img, pl, st);
+    if (d.M == 32) return launch_fwd_fast_bt<32, true>(d, W, in, fa, pl, st);
+    return launch_fwd_fast_bt<64, false>(d, W, in, fa, pl, st);
 }
 template <int M>
 static int launch_bwd_fast_m(const Dims& d, const WsPtrs& W, const float* bin_w, const float* code_w, const Plan& pl,
@@ -348,7 +359,7 @@ struct WgBuilder {
         p.c_off = L->offset[wid] + col; p.ldc = N == 1 ? 1 : L->cols[wid];   // N == 1: column sums land contiguously
         p.bias_off = bid >= 0 ? L->offset[bid] : -1;
         p.sig_rows = sig_rows; p.kind = kind;
-        int ns = kind == WG_GEMM ? cdiv(K, kWgradKSlice) : 1;
+        int ns = kind != WG_CODEBIAS ? cdiv(K, kWgradKSlice) : 1;
         if (ns < 1) ns = 1;
         if (ns > kWgradSplitMax) ns = kWgradSplitMax;
         if (ns > st->nsplit[wid]) st->nsplit[wid] = ns;
@@ -360,7 +371,7 @@ struct WgBuilder {
             p.nsplit = st->nsplit[w_id[i]];                  // problems sharing a tensor share its split factor
             if (b_id[i] >= 0) st->nsplit[b_id[i]] = p.nsplit;
             p.ntm = cdiv(p.M, kTile);
-            p.ntn = p.kind == WG_GEMM ? cdiv(p.N, kTile) : 1;
+            p.ntn = p.kind == WG_GEMM ? cdiv(p.N, kTile) : (p.kind == WG_ROWVEC ? cdiv(p.N, kRowvecCols) : 1);
             p.tile_begin = t->total_tiles;
             t->total_tiles += p.ntm * p.ntn * p.nsplit;
         }
@@ -383,7 +394,7 @@ static void build_wgrad_table(const Dims& d, const mmg_param_layout& L, const Pa
     b.add(km(W.d_lw, M), km(W.h_w, Hr), M, Hr, R, MMG_P_REC_W_W, 0, MMG_P_REC_W_B);
     b.add(km(W.d_hw, Hr), km(h_after, Hr), Hr, Hr, R, MMG_P_REC_WH_W, 0, MMG_P_REC_WH_B);
     b.add(km(W.d_hw, Hr), km(W.wd, d.WV), Hr, d.WV, R, MMG_P_REC_WD_W, 0, -1);
-    b.add(km(W.d_ls, 1), km(h_after, Hr), 1, Hr, R, MMG_P_REC_S_W, 0, MMG_P_REC_S_B);
+    b.add(km(W.d_ls, 1), km(h_after, Hr), 1, Hr, R, MMG_P_REC_S_W, 0, MMG_P_REC_S_B, WG_ROWVEC);
     b.add(km(W.g_h, Hr), km(W.hsel, Hr), Hr, Hr, B, MMG_P_REC_Y1_W, 0, -1);
     {
         Operand bd = km(in.desc, d.WV);
@@ -403,10 +414,19 @@ static void build_wgrad_table(const Dims& d, const mmg_param_layout& L, const Pa
         {
             Operand a = km(W.h1s, d.Hb);
             a.kind = OP_RELUGRAD; a.g = W.g_bs; a.w2 = P.p[MMG_P_BS_L2_W];
-            Operand bb = km(W.h_x, Hi);
-            bb.mod = B; bb.p2 = W.rec_feats; bb.ld2 = M; bb.split = Hi;
-            b.add(a, bb, d.Hb, Hi + M, R, MMG_P_BS_L1_W, 0, MMG_P_BS_L1_B);
-            b.add(km(W.g_bs, 1), km(W.h1s, d.Hb), 1, d.Hb, R, MMG_P_BS_L2_W, 0, MMG_P_BS_L2_B);
+            if (fast) {
+                // h_x is shared by the T rows of an example: sum the relu-gradient over t first (K = B instead of T*B),
+                // the z_r columns keep the full row range
+                Operand at = a;
+                at.kind = OP_RELUGRAD_TSUM; at.mod = d.T; at.ld2 = B;
+                b.add(at, km(W.h_x, Hi), d.Hb, Hi, B, MMG_P_BS_L1_W, 0, MMG_P_BS_L1_B);
+                b.add(a, km(W.rec_feats, M), d.Hb, M, R, MMG_P_BS_L1_W, Hi, -1);
+            } else {
+                Operand bb = km(W.h_x, Hi);
+                bb.mod = B; bb.p2 = W.rec_feats; bb.ld2 = M; bb.split = Hi;
+                b.add(a, bb, d.Hb, Hi + M, R, MMG_P_BS_L1_W, 0, MMG_P_BS_L1_B);
+            }
+            b.add(km(W.g_bs, 1), km(W.h1s, d.Hb), 1, d.Hb, R, MMG_P_BS_L2_W, 0, MMG_P_BS_L2_B, WG_ROWVEC);
         }
         // baseline_rec: rows [z[t,b] ; h_z after step t]
         {
@@ -415,7 +435,7 @@ static void build_wgrad_table(const Dims& d, const mmg_param_layout& L, const Pa
             Operand bb = km(W.sen_feats, M);
             bb.p2 = h_after; bb.ld2 = Hr; bb.split = M;
             b.add(a, bb, d.Hb, M + Hr, R, MMG_P_BR_L1_W, 0, MMG_P_BR_L1_B);
-            b.add(km(W.g_br, 1), km(W.h1r, d.Hb), 1, d.Hb, R, MMG_P_BR_L2_W, 0, MMG_P_BR_L2_B);
+            b.add(km(W.g_br, 1), km(W.h1r, d.Hb), 1, d.Hb, R, MMG_P_BR_L2_W, 0, MMG_P_BR_L2_B, WG_ROWVEC);
         }
     }
     b.finish();
@@ -530,7 +550,7 @@ int mmg_exchange_forward(const mmg_config* cfg, const float* d_params, const mmg
     if ((rc = check_cuda("k_pre"))) return rc;
     // K_exchange_fwd
     const float* b_img = P.p[MMG_P_SEN_IMG_B];
-    if (pl.fast) rc = launch_fwd_fast(d, W, ei, b_img, pl, st);
+    if (pl.fast) rc = launch_fwd_fast(d, W, ei, FastFwdArgs{b_img, P.p[MMG_P_BS_L1_W], P.p[MMG_P_BS_L1_B]}, pl, st);
     else switch (pl.BT) {
         case 1: rc = launch_fwd<1>(d, W, ei, b_img, pl, st); break;
         case 2: rc = launch_fwd<2>(d, W, ei, b_img, pl, st); break;
@@ -541,7 +561,7 @@ int mmg_exchange_forward(const mmg_config* cfg, const float* d_params, const mmg
     if (in->train) {
         const int tiles = 2 * cdiv(d.R, kTile) * W.ntb;
         const int wd_tiles = pl.fast ? cdiv(d.R, kTile) * cdiv(d.WV, kTile) : 0;   // the generic kernel writes wd itself
-        MMG_LAUNCH(k_baseline_fwd, tiles + wd_tiles, kGemmThreads, 0, st, d, P, W, ei.desc, tiles);
+        MMG_LAUNCH(k_baseline_fwd, tiles + wd_tiles, kGemmThreads, 0, st, d, P, W, ei.desc, tiles, pl.fast);
         if ((rc = check_cuda("k_baseline_fwd"))) return rc;
     }
     return MMG_OK;

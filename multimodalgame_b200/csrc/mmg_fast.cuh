@@ -15,6 +15,13 @@
 #pragma once
 #include "mmg_exchange_fwd.cuh"
 
+#if defined(MMG_PHASE_TIMING) && !defined(MMG_CPU_EMU)
+// debug build only (scripts/phase_timing.py): per-phase clock stamps of CTA 0 into the g_sen_probs scratch
+#define MMG_STAMP(p) do { if (lane == 0) stamps[(t * 8 + (p)) * 8 + warp] = (unsigned)clock64(); } while (0)
+#else
+#define MMG_STAMP(p) do { } while (0)
+#endif
+
 namespace mmg {
 
 MMG_DEVICE float dot4(const float4& a, const float4& b, float acc) {
@@ -28,31 +35,28 @@ MMG_DEVICE float dot4(const float4& a, const float4& b, float acc) {
 // ---- image packing (called by k_pre) ---------------------------------------------------------------------------
 MMG_DEVICE float fast_fwd_image_elem(const Dims& d, const FastFwdImage& im, const ParamPtrs& P, int e) {
     const int M = d.M;
-    if (e < im.wb) { const int q = e - im.wc; const int c = q & 3, f4 = q >> 2, half = f4 & 1, n = (f4 >> 1) & 255, qq = f4 >> 9;
-        return ldg(P.p[MMG_P_SEN_CODE_W] + (size_t)n * M + half * (M / 2) + 4 * qq + c); }
+    if (e < im.wb) { const int q = e - im.wc; const int k4 = q >> 10, n = (q >> 2) & 255, c = q & 3;
+        return ldg(P.p[MMG_P_SEN_CODE_W] + (size_t)n * M + 4 * k4 + c); }
     if (e < im.b_code) return ldg(P.p[MMG_P_SEN_BIN_W] + (e - im.wb));
     if (e < im.hw0) return ldg(P.p[MMG_P_SEN_CODE_B] + (e - im.b_code));
     if (e < im.b_b) return 0.f;                                   // hw0: dot role
     if (e < im.sender_end) return ldg(P.p[MMG_P_SEN_BIN_B] + (e - im.b_b));
-    if (e < im.wfull) { const int q = e - im.wih; const int c = q & 3, f4 = q >> 2, part = f4 & 7, k = (f4 >> 3) & 63, gq = f4 >> 9;
-        const int MQ = M / 32, g = gq / MQ, qq = gq % MQ;
-        return ldg(P.p[MMG_P_REC_RNN_WIH] + (size_t)(g * 64 + k) * M + part * (M / 8) + 4 * qq + c); }
-    if (e < im.wghn) { const int q = e - im.wfull; const int c = q & 3, f4 = q >> 2, half = f4 & 1, o = (f4 >> 1) & 255, qq = f4 >> 9;
+    if (e < im.whead) { const int q = e - im.wih; const int c = q & 3, f4 = q >> 2, part = f4 & 3, k = (f4 >> 2) & 63, gq = f4 >> 8;
+        const int MQ = M / 16, g = gq / MQ, qq = gq % MQ;
+        return ldg(P.p[MMG_P_REC_RNN_WIH] + (size_t)(g * 64 + k) * M + part * (M / 4) + 4 * qq + c); }
+    if (e < im.wgh) { const int q = e - im.whead; const int c = q & 3, f4 = q >> 2, half = f4 & 1, o = (f4 >> 1) & 127, qq = f4 >> 8;
         const int col = half * 32 + 4 * qq + c;
         if (o < 64) return ldg(P.p[MMG_P_REC_Y1_W] + (size_t)o * (64 + d.WV) + col);
-        if (o < 128) return ldg(P.p[MMG_P_REC_WH_W] + (size_t)(o - 64) * 64 + col);
-        return ldg(P.p[MMG_P_REC_RNN_WHH] + (size_t)(o - 128) * 64 + col); }
-    if (e < im.ww) { const int q = e - im.wghn; const int c = q & 3, f4 = q >> 2, part = f4 & 7, k = (f4 >> 3) & 63, qq = f4 >> 9;
-        return ldg(P.p[MMG_P_REC_RNN_WHH] + (size_t)(128 + k) * 64 + part * 8 + 4 * qq + c); }
-    if (e < im.b_ih) { const int q = e - im.ww; const int c = q & 3, f4 = q >> 2, TPO = kFastThreads / M, KPT = 64 / TPO;
-        const int part = f4 % TPO, j = (f4 / TPO) % M, qq = f4 / (TPO * M);
+        return ldg(P.p[MMG_P_REC_WH_W] + (size_t)(o - 64) * 64 + col); }
+    if (e < im.ww) { const int q = e - im.wgh; const int c = q & 3, f4 = q >> 2, part = f4 & 3, k = (f4 >> 2) & 63, gq = f4 >> 8;
+        const int g = gq >> 2, qq = gq & 3;
+        return ldg(P.p[MMG_P_REC_RNN_WHH] + (size_t)(g * 64 + k) * 64 + part * 16 + 4 * qq + c); }
+    if (e < im.b_ih) { const int q = e - im.ww; const int c = q & 3, f4 = q >> 2, LPO = kFastThreads / M, KPT = 64 / LPO;
+        const int part = f4 % LPO, j = (f4 / LPO) % M, qq = f4 / (LPO * M);
         return ldg(P.p[MMG_P_REC_W_W] + (size_t)j * 64 + part * KPT + 4 * qq + c); }
-    if (e < im.b_full) return ldg(P.p[MMG_P_REC_RNN_BIH] + (e - im.b_ih));
-    if (e < im.b_ghn) { const int o = e - im.b_full;
-        if (o < 64) return 0.f;
-        if (o < 128) return ldg(P.p[MMG_P_REC_WH_B] + (o - 64));
-        return ldg(P.p[MMG_P_REC_RNN_BHH] + (o - 128)); }
-    if (e < im.ws) return ldg(P.p[MMG_P_REC_RNN_BHH] + 128 + (e - im.b_ghn));
+    if (e < im.b_hh) return ldg(P.p[MMG_P_REC_RNN_BIH] + (e - im.b_ih));
+    if (e < im.b_wh) return ldg(P.p[MMG_P_REC_RNN_BHH] + (e - im.b_hh));
+    if (e < im.ws) return ldg(P.p[MMG_P_REC_WH_B] + (e - im.b_wh));
     if (e < im.b_w) return ldg(P.p[MMG_P_REC_S_W] + (e - im.ws));
     if (e < im.w2) return ldg(P.p[MMG_P_REC_W_B] + (e - im.b_w));
     if (e < im.misc) return ldg(P.p[MMG_P_REC_Y2_W] + (e - im.w2));
@@ -76,30 +80,77 @@ MMG_DEVICE float fast_bwd_image_elem(const Dims& d, const FastBwdImage& im, cons
 }
 
 // ---- forward -----------------------------------------------------------------------------------------------------
-// 512 threads (16 warps) per CTA: the step is instruction-issue bound, so each phase is spread over all four
-// schedulers with 4 warps each; K-splits inside a phase meet through 1-4 shuffles.
+// Phase timing on B200 showed the step is bound by the DEPENDENT chain inside each phase (every instruction of a warp
+// waits for the previous one), not by issue slots, so this kernel keeps every chain short: 4 independent accumulators
+// per dot product, at most 3 shuffle stages per reduction, MUFU-based sigmoid/tanh/exp, loop-invariant addresses
+// hoisted into registers, and the two products that are not on the critical path (W_hh . h' for the NEXT step, the
+// STOP head) issued inside phases whose own chain leaves the pipes idle.
+// With the chains short, the next wall is shared-memory bandwidth: ~200 KB of weights per step through a 128 B/clk
+// pipe is ~1600 cycles.  The weights are loop constants, so each thread keeps ITS slice of every matrix in registers
+// (kRegRecv: GRU + heads + message head, 112 registers; kRegSend: sender, 64 registers at msg_dim 32) and shared memory
+// only carries the per-step vectors and the class tables.
 MMG_HOST_DEVICE int fast_uni_stride(int M) { return 2 * M + 4; }       // per (example, step): z draws, w draws, stop draw
 MMG_HOST_DEVICE int fast_fwd_state_floats(int BT, int M, int D, int T) {
-    // hx, av (256 each) | win, zv (M each) | hv, y1hv, whv, hwv (64 each) | ghv (192) | yv (DP) | ev (16 warps x DP)
+    // hx, av (256 each) | win, zv (M each) | hv, y1hv, whv, hwv (64 each) | ghv (192) | yv (DP) | wmax (8)
     // | uniforms (T x stride) | sprod, smask | barrier
-    return BT * (2 * kFastHi + 2 * M + 4 * kFastHr + 3 * kFastHr + align4(D) + (kFastThreads / 32) * align4(D) +
-                 T * fast_uni_stride(M)) + align4(2 * BT) + 8;
+    return BT * (2 * kFastHi + 2 * M + 4 * kFastHr + 3 * kFastHr + align4(D) + 8 + T * fast_uni_stride(M)) +
+           align4(2 * BT) + 8;
 }
 
-template <int BT, int M, bool kSenderSmem>
+MMG_DEVICE void fma4(const float4& w, const float4& x, float4& acc) {
+    acc.x = fmaf(w.x, x.x, acc.x); acc.y = fmaf(w.y, x.y, acc.y);
+    acc.z = fmaf(w.z, x.z, acc.z); acc.w = fmaf(w.w, x.w, acc.w);
+}
+MMG_DEVICE float hsum4(const float4& a) { return (a.x + a.y) + (a.z + a.w); }
+MMG_DEVICE float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+MMG_DEVICE float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+#ifdef MMG_NO_SAVE
+#define MMG_SAVE_OK(b) ((b) < 0)
+#else
+#define MMG_SAVE_OK(b) ((b) < B)
+#endif
+
+template <int BT, int M, bool kRegSend>
 MMG_GLOBAL void __launch_bounds__(kFastThreads, 1)
-k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int row_offset) {
+k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int row_offset, const float* bs_w1,
+                    const float* bs_b1, int n_conv_ctas) {
     constexpr int HI = kFastHi, HR = kFastHr, NT = kFastThreads, NW = NT / 32;
-    constexpr int MQ = M / 32, TPO = NT / M, KPT = HR / TPO, OPW = M / NW, UST = 2 * M + 4;
+    constexpr int M4 = M / 4, MQ = M / 16, LPO = NT / M, KPT = HR / LPO, KB = HI / LPO, UST = 2 * M + 4;
     MMG_DYN_SMEM(smem_raw);
     float* sm = reinterpret_cast<float*>(smem_raw);
+    if ((int)blockIdx.x >= n_conv_ctas) {
+        // Side role on SMs the conversations leave idle: U[b] = baseline_sen.linear1[:, :Hi] . h_x[b] + bias
+        // (model.py:835-836).  h_x is the same for all T steps of an example, so this 9/10 of the sender-side baseline
+        // GEMM is done once per example, concurrently with the exchange loop.
+        pdl_wait();
+        const int ntn = cdiv(d.Hb, kTile);
+        const int tile = (int)blockIdx.x - n_conv_ctas, nt = tile % ntn, mt = tile / ntn;
+        Operand A = Operand{W.hx_part, nullptr, b_img, nullptr, HI, d.B, 0, W.hx_split, 0, OP_SUMSLABS};
+        Operand Bo = Operand{bs_w1, nullptr, nullptr, nullptr, HI + M, 0, 0, 0, 0, OP_PLAIN};
+        float acc[4][4];
+        gemm_tile(A, Bo, d.B, d.Hb, mt * kTile, nt * kTile, 0, HI, acc, nullptr, sm);
+        const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int b = mt * kTile + ty * 4 + a;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int n = nt * kTile + tx * 4 + c;
+                if (b < d.B && n < d.Hb) W.ubs[(size_t)b * d.Hb + n] = acc[a][c] + ldg(bs_b1 + n);
+            }
+        }
+        return;
+    }
     const FastFwdImage im = make_fast_fwd_image(M, d.D);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b0 = blockIdx.x * BT;
     const int D = d.D, DP = align4(D), B = d.B, T = d.T;
-    const int img0 = kSenderSmem ? 0 : im.sender_end;
-    float* img = sm - img0;
-    int o = im.total - img0;
+    // shared-memory image: [sender section (unless it lives in registers)] [tail: biases, class tables]
+    const int snd = kRegSend ? 0 : im.sender_end;
+    float* simg_s = sm;                                           // sender section at its image offsets
+    float* img = sm + snd - im.b_ih;                              // img[off] valid for off >= im.b_ih
+    int o = snd + im.total - im.b_ih;
     float* hx = sm + o;    o += BT * HI;
     float* av = sm + o;    o += BT * HI;
     float* win = sm + o;   o += BT * M;
@@ -110,68 +161,88 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
     float* hwv = sm + o;   o += BT * HR;
     float* ghv = sm + o;   o += BT * 3 * HR;
     float* yv = sm + o;    o += BT * DP;
-    float* ev = sm + o;    o += BT * NW * DP;
+    float* wmax = sm + o;  o += BT * 8;
     float* uni = sm + o;   o += BT * T * UST;
     float* sprod = sm + o; o += BT;
     float* smask = sm + o; o += BT;
     o = align4(o);
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + o);
+#if defined(MMG_PHASE_TIMING) && !defined(MMG_CPU_EMU)
+    unsigned* stamps = reinterpret_cast<unsigned*>(sm + o + 4);     // (T, 8 phases, 8 warps), debug build only
+#endif
 
     const float* gimg = W.fwd_image;
-    const float* simg = kSenderSmem ? img : gimg;                 // sender sections: shared memory or L2
-    const float4* Wc4 = reinterpret_cast<const float4*>(simg + im.wc);
-    const float4* Wb4 = reinterpret_cast<const float4*>(simg + im.wb);
-    const float* b_code = simg + im.b_code;
-    const float* hw0 = simg + im.hw0;
-    const float* b_b = simg + im.b_b;
-    const float4* Wih4 = reinterpret_cast<const float4*>(img + im.wih);
-    const float4* Wfull4 = reinterpret_cast<const float4*>(img + im.wfull);
-    const float4* Wghn4 = reinterpret_cast<const float4*>(img + im.wghn);
-    const float4* Ww4 = reinterpret_cast<const float4*>(img + im.ww);
-    const float* b_ih = img + im.b_ih;
-    const float* b_full = img + im.b_full;
-    const float* b_ghn = img + im.b_ghn;
-    const float* wsv = img + im.ws;
-    const float* b_w = img + im.b_w;
-    const float4* w2_4 = reinterpret_cast<const float4*>(img + im.w2);
-    const float4* y1d4 = reinterpret_cast<const float4*>(img + im.y1d);
-    const float* wdd = img + im.wdd;
+    const float* simg = kRegSend ? gimg : simg_s;                 // sender section: read once from L2, or shared memory
     const bool train = in.train != 0;
     const bool binary = d.use_binary != 0;
     const bool own_draws = train && in.u_sen == nullptr;   // on-device Philox stream (else: injected float64 uniforms)
+
+    // per-thread roles, fixed for the whole kernel (addresses hoisted out of the step loop)
+    const int k4t = tid >> 2, p4 = tid & 3;                       // (hidden unit, K-quarter) pairs: GRU, W_hh, mix
+    const int jo = tid / LPO, po = tid % LPO;                     // (message bit, K-slice) pairs: both message heads
+    const int oh = tid >> 1, hh = tid & 1;                        // (head row, K-half) pairs: y1h / w_h rows
+    const int sub = lane & 7, cw = lane >> 3;                     // (K-eighth, class within warp): class scores
+    const float4* wc_t = reinterpret_cast<const float4*>(simg + im.wc) + tid;                 // + k4 * HI
+    const float4* wb_t = reinterpret_cast<const float4*>(simg + im.wb) + jo * (HI / 4) + po;  // + i * LPO
+    const float4* wih_t = reinterpret_cast<const float4*>(gimg + im.wih) + k4t * 4 + p4;      // + (g*MQ+q) * 256
+    const float4* whd_t = reinterpret_cast<const float4*>(gimg + im.whead) + oh * 2 + hh;     // + q * 256
+    const float4* wgh_t = reinterpret_cast<const float4*>(gimg + im.wgh) + k4t * 4 + p4;      // + (g*4+q) * 256
+    const float4* ww_t = reinterpret_cast<const float4*>(gimg + im.ww) + jo * LPO + po;       // + q * M * LPO
+    const float4* y1d_t = reinterpret_cast<const float4*>(img + im.y1d) + sub;                // + cls*16 (+8)
+    const float* wdd_t = img + im.wdd + k4t * 4 + p4;                                          // + (d/4) * 256
 
     // ---- prologue ----------------------------------------------------------------------------------------------
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     MMG_SYNCTHREADS();
     pdl_wait();
-    if (tid == 0) tma_stage(sm, gimg + img0, (uint32_t)(im.total - img0) * 4u, bar);
-    {   // h_x rows of this CTA: split-K partials of K_pre summed in a fixed order + bias (model.py:195)
-        const int n = tid >> 1, half = tid & 1;
+    if (tid == 0) tma_stage2(sm, gimg, (uint32_t)snd * 4u, sm + snd, gimg + im.b_ih, (uint32_t)(im.total - im.b_ih) * 4u, bar);
+    // this thread's slice of every loop matrix -> registers (coalesced 16-byte loads from the L2-resident image)
+    float4 rc[kRegSend ? M4 : 1], rb[kRegSend ? KB / 4 : 1], ri[3 * MQ], rh[8], rg[12], rw[KPT / 4];
+    if constexpr (kRegSend) {
 #pragma unroll
-        for (int bt = 0; bt < BT; ++bt) {
-            const int b = b0 + bt;
-            float v = 0.f;
-            if (b < B) for (int s = half; s < W.hx_split; s += 2) v += W.hx_part[((size_t)s * B + b) * HI + n];
-            v = group_sum<2>(v);
-            if (b < B) v += ldg(b_img + n);
-            if (half == 0) {
-                hx[bt * HI + n] = v;
-                if (b < B) W.h_x[(size_t)b * HI + n] = v;
+        for (int k4 = 0; k4 < M4; ++k4) rc[k4] = ldg4(wc_t + k4 * HI);
+#pragma unroll
+        for (int i = 0; i < KB / 4; ++i) rb[i] = ldg4(wb_t + i * LPO);
+    }
+#pragma unroll
+    for (int i = 0; i < 3 * MQ; ++i) ri[i] = ldg4(wih_t + i * NT);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) rh[q] = ldg4(whd_t + q * NT);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) rg[i] = ldg4(wgh_t + i * NT);
+#pragma unroll
+    for (int q = 0; q < KPT / 4; ++q) rw[q] = ldg4(ww_t + q * M * LPO);
+    // h_x rows of this CTA: split-K partials of K_pre summed in a fixed order + bias (model.py:195)
+#pragma unroll
+    for (int bt = 0; bt < BT; ++bt) {
+        const int b = b0 + bt, n = tid;
+        float v = 0.f;
+        if (b < B) {
+            float v0 = ldg(b_img + n), v1 = 0.f;
+            int s = 0;
+            for (; s + 1 < W.hx_split; s += 2) {
+                v0 += W.hx_part[((size_t)s * B + b) * HI + n];
+                v1 += W.hx_part[((size_t)(s + 1) * B + b) * HI + n];
             }
-            if (tid < HR) {
-                float h = 0.f;
-                if (b < B) {
-                    if (in.h0 != nullptr) h = in.h0[(size_t)b * HR + tid];
-                    W.h_z[(size_t)b * HR + tid] = h;                    // slot 0 = state entering step 0
-                }
-                hv[bt * HR + tid] = h;
-            }
-            if (tid < M) {
-                win[bt * M + tid] = d.first_rec;                        // model.py:786
-                if (b < B) W.rec_feats[(size_t)b * M + tid] = d.first_rec;   // slot 0
-            }
-            if (tid == 0) { sprod[bt] = 1.f; smask[bt] = 1.f; if (b < B) W.stop_mask[b] = 1; }
+            if (s < W.hx_split) v0 += W.hx_part[((size_t)s * B + b) * HI + n];
+            v = v0 + v1;
+            W.h_x[(size_t)b * HI + n] = v;
         }
+        hx[bt * HI + n] = v;
+        if (n < HR) {
+            float h = 0.f;
+            if (b < B) {
+                if (in.h0 != nullptr) h = in.h0[(size_t)b * HR + n];
+                W.h_z[(size_t)b * HR + n] = h;                        // slot 0 = state entering step 0
+            }
+            hv[bt * HR + n] = h;
+        }
+        if (n < M) {
+            win[bt * M + n] = d.first_rec;                            // model.py:786
+            if (b < B) W.rec_feats[(size_t)b * M + n] = d.first_rec;  // slot 0
+        }
+        if (n == 0) { sprod[bt] = 1.f; smask[bt] = 1.f; if (b < B) W.stop_mask[b] = 1; }
+        for (int dd = D + n; dd < DP; dd += NT) yv[bt * DP + dd] = -INFINITY;   // padded classes never win the softmax
     }
     if (own_draws) {
         // every Bernoulli draw of this CTA's conversations up front (same Philox counters as the generic kernel:
@@ -202,155 +273,94 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
     mbar_wait(bar, 0);
     MMG_SYNCTHREADS();
 
-    // Heads phase: everything that only needs h' — class-score / message-head pre-activations, the STOP bit and
-    // W_hh . h' + b_hh for the NEXT step's gates.  `t < 0`: prologue call, only the W_hh part is kept.
-    auto heads = [&](int t) {
-        {   // rows [y1h ; w_h ; gh_r ; gh_u]: two threads per output, 32 reduction elements each
-            const int oo = tid >> 1, half = tid & 1;
-            float acc[BT];
+    const float b_b_t = (simg + im.b_b)[jo], b_w_t = (img + im.b_w)[jo];
+    const float hw0_v = (simg + im.hw0)[tid], b_code_t = (simg + im.b_code)[tid];
+    const float bih_r = (img + im.b_ih)[k4t], bih_u = (img + im.b_ih)[HR + k4t], bih_n = (img + im.b_ih)[2 * HR + k4t];
+    const float bhh_r = (img + im.b_hh)[k4t], bhh_u = (img + im.b_hh)[HR + k4t], bhh_n = (img + im.b_hh)[2 * HR + k4t];
+    const float bhd_t = oh < HR ? 0.f : (img + im.b_wh)[oh - HR];
+    const float ws_a = (img + im.ws)[lane], ws_b = (img + im.ws)[lane + 32];
+    const float4 w2a = lds4(img + im.w2 + 4 * sub), w2b = lds4(img + im.w2 + 32 + 4 * sub);
+    const float y2b = img[im.misc], s_bias = img[im.misc + 1];
+
+    // W_hh . h + b_hh for the NEXT GRU step (needs only h): thread (k, quarter) -> three gate rows, 16 columns each
+    auto gh_phase = [&]() {
+        float4 acc[BT][3];
 #pragma unroll
-            for (int bt = 0; bt < BT; ++bt) acc[bt] = 0.f;
+        for (int bt = 0; bt < BT; ++bt) { acc[bt][0] = zero4(); acc[bt][1] = zero4(); acc[bt][2] = zero4(); }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 w = Wfull4[(q * 256 + oo) * 2 + half];
-#pragma unroll
-                for (int bt = 0; bt < BT; ++bt)
-                    acc[bt] = dot4(w, *reinterpret_cast<const float4*>(hv + bt * HR + half * 32 + 4 * q), acc[bt]);
-            }
-            const float bias = b_full[oo];
+        for (int q = 0; q < 4; ++q) {
+            const float4 w0 = rg[q], w1 = rg[4 + q], w2 = rg[8 + q];
 #pragma unroll
             for (int bt = 0; bt < BT; ++bt) {
-                const float v = group_sum<2>(acc[bt]) + bias;
-                const int b = b0 + bt;
-                if (half == 0) {
-                    if (oo < HR) {
-                        if (t >= 0) {
-                            y1hv[bt * HR + oo] = v;
-                            if (b < B) W.y1h[((size_t)t * B + b) * HR + oo] = v;
-                        }
-                    } else if (oo < 2 * HR) {
-                        whv[bt * HR + oo - HR] = v;
-                    } else {
-                        ghv[bt * 3 * HR + oo - 2 * HR] = v;
-                    }
-                }
+                const float4 h = lds4(hv + bt * HR + p4 * 16 + 4 * q);
+                fma4(w0, h, acc[bt][0]); fma4(w1, h, acc[bt][1]); fma4(w2, h, acc[bt][2]);
             }
         }
-        {   // rows gh_n: 8 threads per output, 8 reduction elements each
-            const int k = tid >> 3, part = tid & 7;
-            float acc[BT];
 #pragma unroll
-            for (int bt = 0; bt < BT; ++bt) acc[bt] = 0.f;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const float4 w = Wghn4[(q * HR + k) * 8 + part];
-#pragma unroll
-                for (int bt = 0; bt < BT; ++bt)
-                    acc[bt] = dot4(w, *reinterpret_cast<const float4*>(hv + bt * HR + part * 8 + 4 * q), acc[bt]);
-            }
-#pragma unroll
-            for (int bt = 0; bt < BT; ++bt) {
-                const float v = group_sum<8>(acc[bt]);
-                if (part == 0) ghv[bt * 3 * HR + 2 * HR + k] = b_ghn[k] + v;
-            }
-        }
-        if (t >= 0 && warp == NW - 1) {   // STOP bit (model.py:414-429, 852)
-#pragma unroll
-            for (int bt = 0; bt < BT; ++bt) {
-                float v = wsv[lane] * hv[bt * HR + lane] + wsv[lane + 32] * hv[bt * HR + lane + 32];
-                v = warp_sum(v);
-                const int b = b0 + bt;
-                if (lane == 0) {
-                    const size_t row = (size_t)t * B + b;
-                    const float sp = sigmoidf_(v + img[im.misc + 1]);
-                    float sbit;
-                    if (train) {
-                        if (b >= B) sbit = 0.f;
-                        else if (own_draws) sbit = (uni[(bt * T + t) * UST + 2 * M] < sp) ? 1.f : 0.f;
-                        else sbit = (in.u_stop[row] < (double)sp) ? 1.f : 0.f;
-                    } else {
-                        const float prod = (t == 0 || !d.s_prob_prod) ? sp : sprod[bt] * sp;
-                        sprod[bt] = prod;
-                        sbit = rintf(prod);
-                    }
-                    const float m = fminf(smask[bt], sbit);
-                    smask[bt] = m;
-                    if (b < B) {
-                        W.stop_feat[row] = sbit;
-                        W.stop_prob[row] = sp;
-                        W.stop_mask[(size_t)(t + 1) * B + b] = (unsigned char)(m != 0.f);
-                    }
-                }
+        for (int bt = 0; bt < BT; ++bt) {
+            const float r = group_sum<4>(hsum4(acc[bt][0])), u = group_sum<4>(hsum4(acc[bt][1])), n = group_sum<4>(hsum4(acc[bt][2]));
+            if (p4 == 0) {
+                ghv[bt * 3 * HR + k4t] = r + bhh_r;
+                ghv[bt * 3 * HR + HR + k4t] = u + bhh_u;
+                ghv[bt * 3 * HR + 2 * HR + k4t] = n + bhh_n;
             }
         }
     };
 
-    heads(-1);                                   // gh for step 0 from the initial state
-    const float4 w2q = w2_4[lane & 15];
-    const float y2b = img[im.misc];
+    gh_phase();                                   // gates' recurrent half for step 0 from the initial state
     MMG_SYNCTHREADS();
 
     for (int t = 0; t < T; ++t) {
-        // ---- P1: sender hidden a = tanh(h_x + code_layer(w_prev)) (model.py:199-216): 2 threads per unit ----------
+        // ---- P1: sender hidden a = tanh(h_x + code_layer(w_prev)) (model.py:199-216): one thread per unit -----------
+        MMG_STAMP(0);
         {
-            const int n = tid >> 1, half = tid & 1;
-            float acc[BT];
+            float4 acc[BT];
 #pragma unroll
-            for (int bt = 0; bt < BT; ++bt) acc[bt] = 0.f;
+            for (int bt = 0; bt < BT; ++bt) acc[bt] = zero4();
             if (t > 0) {
 #pragma unroll
-                for (int q = 0; q < M / 8; ++q) {
-                    const float4 w = kSenderSmem ? Wc4[(q * HI + n) * 2 + half] : ldg4(Wc4 + (q * HI + n) * 2 + half);
+                for (int k4 = 0; k4 < M4; ++k4) {
+                    float4 w;
+                    if constexpr (kRegSend) w = rc[k4]; else w = wc_t[k4 * HI];
 #pragma unroll
-                    for (int bt = 0; bt < BT; ++bt)
-                        acc[bt] = dot4(w, *reinterpret_cast<const float4*>(win + bt * M + half * (M / 2) + 4 * q), acc[bt]);
+                    for (int bt = 0; bt < BT; ++bt) fma4(w, lds4(win + bt * M + 4 * k4), acc[bt]);
                 }
             }
-            const float base = (t == 0) ? hw0[n] : b_code[n];
+            const float base = (t == 0) ? hw0_v : b_code_t;
 #pragma unroll
             for (int bt = 0; bt < BT; ++bt) {
                 const int b = b0 + bt;
-                const float a = tanhf(hx[bt * HI + n] + (base + group_sum<2>(acc[bt])));
-                if (half == 0) {
-                    av[bt * HI + n] = a;
-                    if (b < B) W.a_s[((size_t)t * B + b) * HI + n] = a;
+                const float a = fast_tanh(hx[bt * HI + tid] + (base + hsum4(acc[bt])));
+                av[bt * HI + tid] = a;
+                if (MMG_SAVE_OK(b)) {
+                    W.a_s[((size_t)t * B + b) * HI + tid] = a;
+                    if (t > 0 && tid < M) W.code_in[((size_t)t * B + b) * M + tid] = win[bt * M + tid];
                 }
-                if (t > 0 && tid < M && b < B) W.code_in[((size_t)t * B + b) * M + tid] = win[bt * M + tid];
             }
         }
+        MMG_STAMP(1);
         MMG_SYNCTHREADS();
-        // ---- P2: binary_layer + sender message (model.py:216-238, 814-820): warp w owns outputs [w*OPW, (w+1)*OPW) --
+        // ---- P2: binary_layer + sender message (model.py:216-238, 814-820): LPO lanes per message bit ---------------
         {
-            float4 a0[BT], a1[BT];
+            float4 acc[BT];
 #pragma unroll
-            for (int bt = 0; bt < BT; ++bt) {
-                a0[bt] = *reinterpret_cast<const float4*>(av + bt * HI + 4 * lane);
-                a1[bt] = *reinterpret_cast<const float4*>(av + bt * HI + 128 + 4 * lane);
-            }
-            float s[BT][OPW];
+            for (int bt = 0; bt < BT; ++bt) acc[bt] = zero4();
 #pragma unroll
-            for (int oo = 0; oo < OPW; ++oo) {
-                const int j = warp * OPW + oo;
-                const float4 w0 = kSenderSmem ? Wb4[j * (HI / 4) + lane] : ldg4(Wb4 + j * (HI / 4) + lane);
-                const float4 w1 = kSenderSmem ? Wb4[j * (HI / 4) + 32 + lane] : ldg4(Wb4 + j * (HI / 4) + 32 + lane);
+            for (int i = 0; i < KB / 4; ++i) {
+                float4 w;
+                if constexpr (kRegSend) w = rb[i]; else w = wb_t[i * LPO];
 #pragma unroll
-                for (int bt = 0; bt < BT; ++bt) s[bt][oo] = dot4(w1, a1[bt], dot4(w0, a0[bt], 0.f));
+                for (int bt = 0; bt < BT; ++bt) fma4(w, lds4(av + bt * HI + 4 * (i * LPO + po)), acc[bt]);
             }
 #pragma unroll
             for (int bt = 0; bt < BT; ++bt) {
-                float mine = 0.f;
-#pragma unroll
-                for (int oo = 0; oo < OPW; ++oo) {
-                    const float v = warp_sum(s[bt][oo]);
-                    if (lane == oo) mine = v;
-                }
-                if (lane < OPW) {
-                    const int j = warp * OPW + lane, b = b0 + bt;
-                    const float logit = b_b[j] + mine;
+                const float logit = b_b_t + group_sum<LPO>(hsum4(acc[bt]));
+                if (po == 0) {
+                    const int j = jo, b = b0 + bt;
                     const size_t row = (size_t)t * B + b;
                     float p = 0.f, zval;
                     if (binary) {
-                        p = sigmoidf_(logit);
+                        p = fast_sigmoid(logit);
                         if (train) {
                             if (b >= B) zval = 0.f;
                             else if (own_draws) zval = (uni[(bt * T + t) * UST + j] < p) ? 1.f : 0.f;
@@ -363,144 +373,201 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
                     }
                     if (in.corrupt_mask != nullptr) zval = fabsf(zval - in.corrupt_mask[j]);
                     zv[bt * M + j] = zval;
-                    if (b < B) {
+                    if (MMG_SAVE_OK(b)) {
                         W.sen_feats[row * M + j] = zval;
                         if (binary) W.sen_probs[row * M + j] = p;
                     }
                 }
             }
         }
+        MMG_STAMP(2);
         MMG_SYNCTHREADS();
         // ---- P3: GRU step (model.py:340), gate order r,z,n; W_hh . h + b_hh is already in ghv ----------------------
         {
-            const int k = tid >> 3, part = tid & 7;
-            float g[BT][3];
+            float4 g[BT][3];
 #pragma unroll
-            for (int bt = 0; bt < BT; ++bt) { g[bt][0] = 0.f; g[bt][1] = 0.f; g[bt][2] = 0.f; }
+            for (int bt = 0; bt < BT; ++bt) { g[bt][0] = zero4(); g[bt][1] = zero4(); g[bt][2] = zero4(); }
 #pragma unroll
-            for (int gate = 0; gate < 3; ++gate)
-#pragma unroll
-                for (int q = 0; q < MQ; ++q) {
-                    const float4 w = Wih4[((gate * MQ + q) * HR + k) * 8 + part];
-#pragma unroll
-                    for (int bt = 0; bt < BT; ++bt)
-                        g[bt][gate] = dot4(w, *reinterpret_cast<const float4*>(zv + bt * M + part * (M / 8) + 4 * q), g[bt][gate]);
-                }
-#pragma unroll
-            for (int bt = 0; bt < BT; ++bt) {
-                const float gi_r = group_sum<8>(g[bt][0]) + b_ih[k];
-                const float gi_u = group_sum<8>(g[bt][1]) + b_ih[HR + k];
-                const float gi_n = group_sum<8>(g[bt][2]) + b_ih[2 * HR + k];
-                const float gh_r = ghv[bt * 3 * HR + k], gh_u = ghv[bt * 3 * HR + HR + k], gh_n = ghv[bt * 3 * HR + 2 * HR + k];
-                // one sigmoid instruction stream serves both gates: lane part 0 evaluates r, lane part 1 evaluates u
-                const float sg = sigmoidf_((part & 1) ? (gi_u + gh_u) : (gi_r + gh_r));
-                const float r = shfl_xor_f(sg, part), u = shfl_xor_f(sg, part ^ 1);
-                const float nn = tanhf(gi_n + r * gh_n);
-                const float hp = hv[bt * HR + k];
-                const float hn = nn + u * (hp - nn);
-                MMG_SYNCWARP();                      // every lane of the group has read hv[k] before it is overwritten
-                if (part == 0) {
-                    const int b = b0 + bt;
-                    hv[bt * HR + k] = hn;
-                    if (b < B) {
-                        const size_t row = (size_t)t * B + b;
-                        float* gg = W.gates + row * 4 * HR;
-                        gg[k] = r; gg[HR + k] = u; gg[2 * HR + k] = nn; gg[3 * HR + k] = gh_n;
-                        W.h_z[((size_t)(t + 1) * B + b) * HR + k] = hn;
-                    }
-                }
-            }
-        }
-        MMG_SYNCTHREADS();
-        // ---- P4: heads of h' + STOP bit + W_hh . h' for the next step ------------------------------------------------
-        heads(t);
-        MMG_SYNCTHREADS();
-        // ---- P5: class scores y[d] = y2(relu(y1h + y1d[d])) (model.py:432-433): 16 lanes per class ----------------
-        {
-            const int sub = lane & 15, cw = lane >> 4;
-            float4 ya[BT];
-#pragma unroll
-            for (int bt = 0; bt < BT; ++bt) ya[bt] = *reinterpret_cast<const float4*>(y1hv + bt * HR + 4 * sub);
-            for (int c0 = 0; c0 < D; c0 += 2 * NW) {
-                const int cls = c0 + warp * 2 + cw;
-                const bool valid = cls < D;
-                float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) r0 = y1d4[cls * 16 + sub];
+            for (int q = 0; q < MQ; ++q) {
+                const float4 w0 = ri[q], w1 = ri[MQ + q], w2 = ri[2 * MQ + q];
 #pragma unroll
                 for (int bt = 0; bt < BT; ++bt) {
-                    float s = 0.f;
-                    s = fmaf(w2q.x, fmaxf(0.f, ya[bt].x + r0.x), s);
-                    s = fmaf(w2q.y, fmaxf(0.f, ya[bt].y + r0.y), s);
-                    s = fmaf(w2q.z, fmaxf(0.f, ya[bt].z + r0.z), s);
-                    s = fmaf(w2q.w, fmaxf(0.f, ya[bt].w + r0.w), s);
-                    s = group_sum<16>(s);
-                    if (sub == 0 && valid) {
-                        s += y2b;
-                        yv[bt * DP + cls] = s;
-                        const int b = b0 + bt;
-                        if (b < B) W.y[((size_t)t * B + b) * D + cls] = s;
+                    const float4 z = lds4(zv + bt * M + p4 * (M / 4) + 4 * q);
+                    fma4(w0, z, g[bt][0]); fma4(w1, z, g[bt][1]); fma4(w2, z, g[bt][2]);
+                }
+            }
+#pragma unroll
+            for (int bt = 0; bt < BT; ++bt) {
+                const float gh_r = ghv[bt * 3 * HR + k4t], gh_u = ghv[bt * 3 * HR + HR + k4t], gh_n = ghv[bt * 3 * HR + 2 * HR + k4t];
+                const float hp = hv[bt * HR + k4t];
+                const float gi_r = group_sum<4>(hsum4(g[bt][0])) + bih_r;
+                const float gi_u = group_sum<4>(hsum4(g[bt][1])) + bih_u;
+                const float gi_n = group_sum<4>(hsum4(g[bt][2])) + bih_n;
+                const float r = fast_sigmoid(gi_r + gh_r);
+                const float u = fast_sigmoid(gi_u + gh_u);
+                const float nn = fast_tanh(gi_n + r * gh_n);
+                const float hn = nn + u * (hp - nn);
+                MMG_SYNCWARP();                      // every lane of the group has read hv[k] before it is overwritten
+                if (p4 == 0) {
+                    const int b = b0 + bt;
+                    hv[bt * HR + k4t] = hn;
+                    if (MMG_SAVE_OK(b)) {
+                        const size_t row = (size_t)t * B + b;
+                        float* gg = W.gates + row * 4 * HR;
+                        gg[k4t] = r; gg[HR + k4t] = u; gg[2 * HR + k4t] = nn; gg[3 * HR + k4t] = gh_n;
+                        W.h_z[((size_t)(t + 1) * B + b) * HR + k4t] = hn;
                     }
                 }
             }
         }
+        MMG_STAMP(3);
         MMG_SYNCTHREADS();
-        // ---- P6: q = softmax(y) (detached, model.py:441); h_w = tanh(w_h(h') + sum_d q_d wdd[d]) (442-452) ----------
-        // every warp evaluates the D exponentials once into its own strip of shared memory (no block barrier)
+        // ---- P4: rows [y1.weight[:, :64] ; w_h.weight] . h' (model.py:432,452): 2 threads per row --------------------
         {
-            const int k = tid >> 3, part = tid & 7;
+            float4 acc[BT];
+#pragma unroll
+            for (int bt = 0; bt < BT; ++bt) acc[bt] = zero4();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 w = rh[q];
+#pragma unroll
+                for (int bt = 0; bt < BT; ++bt) fma4(w, lds4(hv + bt * HR + hh * 32 + 4 * q), acc[bt]);
+            }
+#pragma unroll
+            for (int bt = 0; bt < BT; ++bt) {
+                const float v = group_sum<2>(hsum4(acc[bt])) + bhd_t;
+                if (hh == 0) {
+                    const int b = b0 + bt;
+                    if (oh < HR) {
+                        y1hv[bt * HR + oh] = v;
+                        if (MMG_SAVE_OK(b)) W.y1h[((size_t)t * B + b) * HR + oh] = v;
+                    } else {
+                        whv[bt * HR + oh - HR] = v;
+                    }
+                }
+            }
+        }
+        MMG_STAMP(4);
+        MMG_SYNCTHREADS();
+        // ---- P5: class scores y[d] = y2(relu(y1h + y1d[d])) (model.py:432-433), 8 lanes per class; the next step's
+        //      W_hh . h' rides along (independent chain) ---------------------------------------------------------------
+        {
+            float4 ya[BT], yb[BT];
+#pragma unroll
+            for (int bt = 0; bt < BT; ++bt) { ya[bt] = lds4(y1hv + bt * HR + 4 * sub); yb[bt] = lds4(y1hv + bt * HR + 32 + 4 * sub); }
+            float wm[BT];
+#pragma unroll
+            for (int bt = 0; bt < BT; ++bt) wm[bt] = -INFINITY;
+            for (int c0 = 0; c0 < D; c0 += 4 * NW) {
+                const int cls = c0 + warp * 4 + cw;
+                const bool valid = cls < D;
+                float4 r0 = zero4(), r1 = zero4();
+                if (valid) { r0 = y1d_t[cls * 16]; r1 = y1d_t[cls * 16 + 8]; }
+#pragma unroll
+                for (int bt = 0; bt < BT; ++bt) {
+                    float s0 = w2a.x * fmaxf(0.f, ya[bt].x + r0.x), s1 = w2a.y * fmaxf(0.f, ya[bt].y + r0.y);
+                    float s2 = w2a.z * fmaxf(0.f, ya[bt].z + r0.z), s3 = w2a.w * fmaxf(0.f, ya[bt].w + r0.w);
+                    s0 = fmaf(w2b.x, fmaxf(0.f, yb[bt].x + r1.x), s0); s1 = fmaf(w2b.y, fmaxf(0.f, yb[bt].y + r1.y), s1);
+                    s2 = fmaf(w2b.z, fmaxf(0.f, yb[bt].z + r1.z), s2); s3 = fmaf(w2b.w, fmaxf(0.f, yb[bt].w + r1.w), s3);
+                    const float s = group_sum<8>((s0 + s1) + (s2 + s3)) + y2b;
+                    if (valid) wm[bt] = fmaxf(wm[bt], s);
+                    if (sub == 0 && valid) {
+                        yv[bt * DP + cls] = s;
+                        const int b = b0 + bt;
+                        if (MMG_SAVE_OK(b)) W.y[((size_t)t * B + b) * D + cls] = s;
+                    }
+                }
+            }
+#pragma unroll
+            for (int bt = 0; bt < BT; ++bt) {    // maximum over this warp's classes (softmax shift for P6)
+                float m = wm[bt];
+                m = fmaxf(m, shfl_xor_f(m, 8));
+                m = fmaxf(m, shfl_xor_f(m, 16));
+                if (lane == 0) wmax[bt * 8 + warp] = m;
+            }
+            gh_phase();
+        }
+        MMG_STAMP(5);
+        MMG_SYNCTHREADS();
+        // ---- P6: q = softmax(y) (detached, model.py:441); h_w = tanh(w_h(h') + sum_d q_d wdd[d]) (442-452); the STOP
+        //      head (model.py:414-429, 852) rides along ------------------------------------------------------------------
+        {
 #pragma unroll
             for (int bt = 0; bt < BT; ++bt) {
                 const int b = b0 + bt;
-                float* e = ev + (bt * NW + warp) * DP;
-                float mx = -INFINITY;
-                for (int dd = lane; dd < D; dd += 32) mx = fmaxf(mx, yv[bt * DP + dd]);
-                mx = warp_max(mx);
-                float se = 0.f;
-                for (int dd = lane; dd < D; dd += 32) {
-                    const float x = expf(yv[bt * DP + dd] - mx);
-                    e[dd] = x;
-                    se += x;
+                const float4 m0 = lds4(wmax + bt * 8), m1 = lds4(wmax + bt * 8 + 4);
+                const float mx = fmaxf(fmaxf(fmaxf(m0.x, m0.y), fmaxf(m0.z, m0.w)), fmaxf(fmaxf(m1.x, m1.y), fmaxf(m1.z, m1.w)));
+                float acc0 = 0.f, acc1 = 0.f, se0 = 0.f, se1 = 0.f;
+                int dd = 0;
+                for (; dd + 8 <= DP; dd += 8) {      // this thread's classes: dd + p4 and dd + 4 + p4
+                    const float e0 = fast_exp(yv[bt * DP + dd + p4] - mx), e1 = fast_exp(yv[bt * DP + dd + 4 + p4] - mx);
+                    se0 += e0; se1 += e1;
+                    acc0 = fmaf(e0, wdd_t[(dd >> 2) * NT], acc0);
+                    acc1 = fmaf(e1, wdd_t[((dd >> 2) + 1) * NT], acc1);
                 }
-                se = warp_sum(se);
-                const float inv = 1.f / se;
-                MMG_SYNCWARP();
-                if (train && warp == 0 && b < B)
-                    for (int dd = lane; dd < D; dd += 32) W.q[((size_t)t * B + b) * D + dd] = e[dd] * inv;
-                float acc = 0.f;
-                for (int dd = part; dd < D; dd += 8) acc = fmaf(e[dd], wdd[((dd >> 3) * HR + k) * 8 + part], acc);
-                acc = group_sum<8>(acc);
-                if (part == 0) {
-                    const float hw = tanhf(whv[bt * HR + k] + acc * inv);
-                    hwv[bt * HR + k] = hw;
-                    if (b < B) W.h_w[((size_t)t * B + b) * HR + k] = hw;
+                if (dd < DP) {
+                    const float e0 = fast_exp(yv[bt * DP + dd + p4] - mx);
+                    se0 += e0;
+                    acc0 = fmaf(e0, wdd_t[(dd >> 2) * NT], acc0);
                 }
-                MMG_SYNCWARP();
+                // STOP head: every warp evaluates the 64-wide dot product (no divergent block), one lane commits
+                float sv = fmaf(ws_a, hv[bt * HR + lane], ws_b * hv[bt * HR + lane + 32]);
+                const float acc = group_sum<4>(acc0 + acc1);
+                const float se = group_sum<4>(se0 + se1);
+                sv = warp_sum(sv);
+                const float inv = fast_rcp(se);
+                if (train && MMG_SAVE_OK(b))
+                    for (int c = tid; c < D; c += NT) W.q[((size_t)t * B + b) * D + c] = fast_exp(yv[bt * DP + c] - mx) * inv;
+                if (p4 == 0) {
+                    const float hw = fast_tanh(whv[bt * HR + k4t] + acc * inv);
+                    hwv[bt * HR + k4t] = hw;
+                    if (MMG_SAVE_OK(b)) W.h_w[((size_t)t * B + b) * HR + k4t] = hw;
+                }
+                if (tid == NT - 1) {
+                    const size_t row = (size_t)t * B + b;
+                    const float sp = fast_sigmoid(sv + s_bias);
+                    float sbit;
+                    if (train) {
+                        if (b >= B) sbit = 0.f;
+                        else if (own_draws) sbit = (uni[(bt * T + t) * UST + 2 * M] < sp) ? 1.f : 0.f;
+                        else sbit = (in.u_stop[row] < (double)sp) ? 1.f : 0.f;
+                    } else {
+                        const float prod = (t == 0 || !d.s_prob_prod) ? sp : sprod[bt] * sp;
+                        sprod[bt] = prod;
+                        sbit = rintf(prod);
+                    }
+                    const float m = fminf(smask[bt], sbit);
+                    smask[bt] = m;
+                    if (MMG_SAVE_OK(b)) {
+                        W.stop_feat[row] = sbit;
+                        W.stop_prob[row] = sp;
+                        W.stop_mask[(size_t)(t + 1) * B + b] = (unsigned char)(m != 0.f);
+                    }
+                }
             }
         }
+        MMG_STAMP(6);
         MMG_SYNCTHREADS();
-        // ---- P8: receiver message w(h_w) (model.py:454-475): TPO threads per output ---------------------------------
+        // ---- P8: receiver message w(h_w) (model.py:454-475): LPO lanes per message bit -----------------------------
         {
-            const int j = tid / TPO, part = tid % TPO;
-            float acc[BT];
+            float4 acc[BT];
 #pragma unroll
-            for (int bt = 0; bt < BT; ++bt) acc[bt] = 0.f;
+            for (int bt = 0; bt < BT; ++bt) acc[bt] = zero4();
 #pragma unroll
             for (int q = 0; q < KPT / 4; ++q) {
-                const float4 w = Ww4[(q * M + j) * TPO + part];
+                const float4 w = rw[q];
 #pragma unroll
-                for (int bt = 0; bt < BT; ++bt)
-                    acc[bt] = dot4(w, *reinterpret_cast<const float4*>(hwv + bt * HR + part * KPT + 4 * q), acc[bt]);
+                for (int bt = 0; bt < BT; ++bt) fma4(w, lds4(hwv + bt * HR + po * KPT + 4 * q), acc[bt]);
             }
 #pragma unroll
             for (int bt = 0; bt < BT; ++bt) {
-                const float v = group_sum<TPO>(acc[bt]);
-                if (part == 0) {
-                    const int b = b0 + bt;
-                    const float logit = b_w[j] + v;
+                const float logit = b_w_t + group_sum<LPO>(hsum4(acc[bt]));
+                if (po == 0) {
+                    const int j = jo, b = b0 + bt;
                     const size_t row = (size_t)t * B + b;
                     float p = 0.f, wv;
                     if (binary) {
-                        p = sigmoidf_(logit);
+                        p = fast_sigmoid(logit);
                         if (train) {
                             if (b >= B) wv = 0.f;
                             else if (own_draws) wv = (uni[(bt * T + t) * UST + M + j] < p) ? 1.f : 0.f;
@@ -513,15 +580,19 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
                         wv = logit;
                     }
                     win[bt * M + j] = wv;
-                    if (b < B) {
+                    if (MMG_SAVE_OK(b)) {
                         W.rec_feats[((size_t)(t + 1) * B + b) * M + j] = wv;
                         if (binary) W.rec_probs[row * M + j] = p;
                     }
                 }
             }
         }
+        MMG_STAMP(7);
         MMG_SYNCTHREADS();
     }
+#if defined(MMG_PHASE_TIMING) && !defined(MMG_CPU_EMU)
+    if (blockIdx.x == 0) for (int i = tid; i < T * 64; i += NT) reinterpret_cast<unsigned*>(W.g_sen_probs)[i] = stamps[i];
+#endif
     pdl_launch_dependents();
 }
 
@@ -569,14 +640,11 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
         for (int t = 0; t < T; ++t) {
             const size_t i = ((size_t)t * B + b) * HI + n;
             const float a = as_s[t * HI + n];
-            float acc = 0.f;
+            float4 a4 = zero4();
 #pragma unroll
-            for (int j4 = 0; j4 < M4; ++j4) {
-                const float4 g = *reinterpret_cast<const float4*>(dlz + t * M + 4 * j4);
-                acc = fmaf(g.x, wb[4 * j4], acc); acc = fmaf(g.y, wb[4 * j4 + 1], acc);
-                acc = fmaf(g.z, wb[4 * j4 + 2], acc); acc = fmaf(g.w, wb[4 * j4 + 3], acc);
-            }
-            const float das = acc * (1.f - a * a);                    // through tanh (model.py:216)
+            for (int j4 = 0; j4 < M4; ++j4)
+                fma4(lds4(dlz + t * M + 4 * j4), make_float4(wb[4 * j4], wb[4 * j4 + 1], wb[4 * j4 + 2], wb[4 * j4 + 3]), a4);
+            const float das = hsum4(a4) * (1.f - a * a);              // through tanh (model.py:216)
             W.d_as[i] = das;
             if (t == 0) das0[n] = das;
             dhx += das;                                               // h_x is shared by all steps (model.py:195)
@@ -588,13 +656,13 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
         {
             const int j = tid % M, part = tid / M;                    // NT / M parts, each HI * M / NT rows
             constexpr int RPP = HI * M / NT;
-            float acc = 0.f;
-#pragma unroll 8
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
             for (int r = 0; r < RPP; ++r) {
                 const int nn = part * RPP + r;
-                acc = fmaf(das0[nn], ldg(code_w + (size_t)nn * M + j), acc);
+                acc[r & 3] = fmaf(das0[nn], ldg(code_w + (size_t)nn * M + j), acc[r & 3]);
             }
-            cred[part * M + j] = acc;
+            cred[part * M + j] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
         }
         MMG_SYNCTHREADS();
         if (tid < M) {
@@ -626,7 +694,6 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
     const float4* WwT4 = reinterpret_cast<const float4*>(sm + im.wwT);
     const float4* WhT4 = reinterpret_cast<const float4*>(sm + im.whT);
     const float4* W1hT4 = reinterpret_cast<const float4*>(sm + im.w1hT);
-    const float4* WhhT4 = reinterpret_cast<const float4*>(sm + im.whhT);
     const float* wsv = sm + im.ws;
     const float* w2 = sm + im.w2;
     const float* y1d = sm + im.y1d;
@@ -634,7 +701,14 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     MMG_SYNCTHREADS();
     pdl_wait();
-    if (tid == 0) tma_stage(sm, W.bwd_image, (uint32_t)im.total * 4u, bar);
+    // W_hh^T (48 KB) never touches shared memory: each thread keeps its 12 float4 of the BPTT mat-vec in registers
+    if (tid == 0) tma_stage2(sm, W.bwd_image, (uint32_t)im.whhT * 4u, sm + im.ws, W.bwd_image + im.ws, (uint32_t)(im.total - im.ws) * 4u, bar);
+    float4 rwhh[12];
+    {
+        const float4* src = reinterpret_cast<const float4*>(W.bwd_image + im.whhT) + (tid >> 2) * 4 + (tid & 3);
+#pragma unroll
+        for (int q = 0; q < 12; ++q) rwhh[q] = ldg4(src + q * HR * 4);
+    }
     // ---- A0: everything the chain needs, into shared memory -----------------------------------------------------
     for (int idx = tid; idx < T * M; idx += NT) {
         const int t = idx / M, j = idx % M;
@@ -674,9 +748,10 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
     const int k = tid >> 2, part = tid & 3;
     // ---- A1: d h_w for every step (t-parallel); class-score head at the prediction step ----------------------------
     for (int t = part; t < T; t += 4) {
-        float acc = 0.f;
+        float4 a4 = zero4();
 #pragma unroll
-        for (int j4 = 0; j4 < M4; ++j4) acc = dot4(WwT4[j4 * HR + k], *reinterpret_cast<const float4*>(dlw + t * M + 4 * j4), acc);
+        for (int j4 = 0; j4 < M4; ++j4) fma4(WwT4[j4 * HR + k], lds4(dlw + t * M + 4 * j4), a4);
+        const float acc = hsum4(a4);
         const size_t i = ((size_t)t * B + b) * HR + k;
         const float hw = hws[t * HR + k];
         const float v = acc * (1.f - hw * hw);                        // through tanh (model.py:452)
@@ -707,14 +782,14 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
     MMG_SYNCTHREADS();
     // ---- A2: per-step injection into d h': W_h^T d_hw + s.weight * d_ls (+ W_1h^T G at the prediction step) --------
     for (int t = part; t < T; t += 4) {
-        float acc = wsv[k] * dls[t];
+        float4 a4 = zero4();
 #pragma unroll
-        for (int k4 = 0; k4 < HR / 4; ++k4) acc = dot4(WhT4[k4 * HR + k], *reinterpret_cast<const float4*>(dhw + t * HR + 4 * k4), acc);
+        for (int k4 = 0; k4 < HR / 4; ++k4) fma4(WhT4[k4 * HR + k], lds4(dhw + t * HR + 4 * k4), a4);
         if (t == ys) {
 #pragma unroll
-            for (int k4 = 0; k4 < HR / 4; ++k4) acc = dot4(W1hT4[k4 * HR + k], *reinterpret_cast<const float4*>(gv + 4 * k4), acc);
+            for (int k4 = 0; k4 < HR / 4; ++k4) fma4(W1hT4[k4 * HR + k], lds4(gv + 4 * k4), a4);
         }
-        inj[t * HR + k] = acc;
+        inj[t * HR + k] = hsum4(a4) + wsv[k] * dls[t];
     }
     MMG_SYNCTHREADS();
     // ---- B: the BPTT chain (h_z is never detached between steps, model.py:340) --------------------------------------
@@ -745,10 +820,10 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
         MMG_SYNCTHREADS();
         {   // d h_prev += W_hh^T . d gh: 4 threads per output, 48 reduction elements each
             const float* dg = dghv + buf * 3 * HR;
-            float acc = 0.f;
+            float4 a4 = zero4();
 #pragma unroll
-            for (int q = 0; q < 12; ++q) acc = dot4(WhhT4[(q * HR + k) * 4 + part], *reinterpret_cast<const float4*>(dg + part * 48 + 4 * q), acc);
-            rec = group_sum<4>(acc);
+            for (int q = 0; q < 12; ++q) fma4(rwhh[q], lds4(dg + part * 48 + 4 * q), a4);
+            rec = group_sum<4>(hsum4(a4));
         }
         buf ^= 1;
     }

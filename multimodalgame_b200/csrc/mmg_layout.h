@@ -109,25 +109,25 @@ MMG_HOST_DEVICE BwdImage make_bwd_image(const Dims& d) {
 
 // ---- fast-path images (img_h_dim = 256, rec_hidden = 64, msg_dim in {32, 64}; mmg_fast.cuh) -------------------
 // Every matrix is stored in the order its consumer phase reads it: a warp's float4 loads are 512 contiguous bytes.
-enum { kFastThreads = 512, kFastBwdThreads = 256, kFastHi = 256, kFastHr = 64, kFastMaxT = 32 };
+enum { kFastThreads = 256, kFastBwdThreads = 256, kFastHi = 256, kFastHr = 64, kFastMaxT = 32 };
 struct FastFwdImage {
-    int wc;      // code_layer.weight    [q < M/8][n < 256][half < 2][4],  column = half*(M/2) + 4q + c
+    int wc;      // code_layer.weight    [k4 < M/4][n < 256][4]
     int wb;      // binary_layer.weight  row-major (M, 256): the state_dict layout
     int b_code, hw0, b_b;
     int sender_end;
-    int wih;     // rnn.weight_ih        [(g*(M/32) + q)][k < 64][part < 8][4],  column = part*(M/8) + 4q + c
-    int wfull;   // rows [y1.weight[:, :64] ; w_h.weight ; rnn.weight_hh[0:128]]  [q < 8][o < 256][half < 2][4], column = half*32 + 4q + c
-    int wghn;    // rnn.weight_hh[128:192]  [q < 2][k < 64][part < 8][4],  column = part*8 + 4q + c
-    int ww;      // w.weight             [q][j < M][part < TPO][4],  TPO = 512/M, column = part*(64/TPO) + 4q + c
+    int wih;     // rnn.weight_ih        [(g*(M/16) + q)][k < 64][part < 4][4],  column = part*(M/4) + 4q + c
+    int whead;   // rows [y1.weight[:, :64] ; w_h.weight]  [q < 8][o < 128][half < 2][4],  column = half*32 + 4q + c
+    int wgh;     // rnn.weight_hh        [(g*4 + q)][k < 64][part < 4][4],  column = part*16 + 4q + c
+    int ww;      // w.weight             [q][j < M][part < LPO][4],  LPO = 256/M, column = part*(64/LPO) + 4q + c
     int b_ih;    // [192]
-    int b_full;  // [256]: 0 (y1.bias lives in y1d), w_h.bias, rnn.bias_hh[0:128]
-    int b_ghn;   // [64] rnn.bias_hh[128:192]
+    int b_hh;    // [192]
+    int b_wh;    // [64] w_h.bias  (y1.bias lives in y1d)
     int ws;      // [64] s.weight
     int b_w;     // [M]
     int w2;      // [64] y2.weight
     int misc;    // [4]: y2.bias, s.bias
     int y1d;     // [D][64]   desc_d . y1.weight[:, 64:]^T + y1.bias
-    int wdd;     // [ceil(D/8)][64][8]   (desc_d . w_d.weight^T)[k] at ((d/8)*64 + k)*8 + d%8
+    int wdd;     // [ceil(D/4)][64][4]   (desc_d . w_d.weight^T)[k] at ((d/4)*64 + k)*4 + d%4
     int total;
 };
 MMG_HOST_DEVICE FastFwdImage make_fast_fwd_image(int M, int D) {
@@ -139,18 +139,18 @@ MMG_HOST_DEVICE FastFwdImage make_fast_fwd_image(int M, int D) {
     im.b_b = o; o += M;
     im.sender_end = o;
     im.wih = o; o += 3 * M * kFastHr;
-    im.wfull = o; o += 256 * kFastHr;
-    im.wghn = o; o += kFastHr * kFastHr;
+    im.whead = o; o += 2 * kFastHr * kFastHr;
+    im.wgh = o; o += 3 * kFastHr * kFastHr;
     im.ww = o; o += M * kFastHr;
     im.b_ih = o; o += 3 * kFastHr;
-    im.b_full = o; o += 256;
-    im.b_ghn = o; o += kFastHr;
+    im.b_hh = o; o += 3 * kFastHr;
+    im.b_wh = o; o += kFastHr;
     im.ws = o; o += kFastHr;
     im.b_w = o; o += M;
     im.w2 = o; o += kFastHr;
     im.misc = o; o += 4;
     im.y1d = o; o += D * kFastHr;
-    im.wdd = o; o += ((D + 7) / 8) * 8 * kFastHr;
+    im.wdd = o; o += ((D + 3) / 4) * 4 * kFastHr;
     im.total = o;
     return im;
 }
@@ -201,6 +201,7 @@ struct Ws {   // byte offsets into the workspace
     int64_t rowstat;   // (6,T,B)  logp_z, H_z, logp_w, H_w, logp_s, H_s
     int64_t h1s, h1r;  // (T,B,Hb) baseline hidden (post relu)
     int64_t bs_part, br_part;  // (T,B,NTb) partial dots with linear2.weight per 64-column tile
+    int64_t ubs;       // (B,Hb)  baseline_sen.linear1 applied to h_x only (+ bias): shared by all T steps of an example (fast path)
     // pre-pass
     int64_t hx_part;   // (S,B,Hi)
     int64_t fwd_image, bwd_image;

@@ -15,7 +15,7 @@
 namespace mmg {
 
 MMG_GLOBAL void __launch_bounds__(kGemmThreads)
-k_baseline_fwd(Dims d, ParamPtrs P, WsPtrs W, const float* desc, int n_bas_tiles) {
+k_baseline_fwd(Dims d, ParamPtrs P, WsPtrs W, const float* desc, int n_bas_tiles, int use_u) {
     MMG_SHARED __attribute__((aligned(16))) float gs[kGemmSmemFloats];
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
     const int ntm = cdiv(d.R, kTile), ntn = W.ntb;
@@ -47,7 +47,12 @@ k_baseline_fwd(Dims d, ParamPtrs P, WsPtrs W, const float* desc, int n_bas_tiles
     const float *b1, *w2;
     float *hid, *part;
     int K;
-    if (which == 0) {   // rows [h_x[b] ; z_r[t,b]]  (model.py:835-836), z_r[t] = rec_feats slot t
+    const float* u = nullptr;     // per-example partial pre-activation (already includes the bias)
+    if (which == 0 && use_u) {   // fast path: the h_x half of every row comes from U[b] (computed beside the exchange loop)
+        A = Operand{W.rec_feats, nullptr, nullptr, nullptr, d.M, 0, 0, 0, 0, OP_PLAIN};
+        Bo = Operand{P.p[MMG_P_BS_L1_W] + d.Hi, nullptr, nullptr, nullptr, d.Hi + d.M, 0, 0, 0, 0, OP_PLAIN};
+        b1 = P.p[MMG_P_BS_L1_B]; w2 = P.p[MMG_P_BS_L2_W]; hid = W.h1s; part = W.bs_part; K = d.M; u = W.ubs;
+    } else if (which == 0) {   // rows [h_x[b] ; z_r[t,b]]  (model.py:835-836), z_r[t] = rec_feats slot t
         A = Operand{W.h_x, W.rec_feats, nullptr, nullptr, d.Hi, d.M, 0, d.B, d.Hi, OP_PLAIN};
         Bo = Operand{P.p[MMG_P_BS_L1_W], nullptr, nullptr, nullptr, d.Hi + d.M, 0, 0, 0, 0, OP_PLAIN};
         b1 = P.p[MMG_P_BS_L1_B]; w2 = P.p[MMG_P_BS_L2_W]; hid = W.h1s; part = W.bs_part; K = d.Hi + d.M;
@@ -66,7 +71,7 @@ k_baseline_fwd(Dims d, ParamPtrs P, WsPtrs W, const float* desc, int n_bas_tiles
         for (int c = 0; c < 4; ++c) {
             const int n = nt * kTile + tx * 4 + c;
             if (r < d.R && n < d.Hb) {
-                const float v = fmaxf(0.f, acc[a][c] + ldg(b1 + n));
+                const float v = fmaxf(0.f, acc[a][c] + (u != nullptr ? u[(size_t)(r % d.B) * d.Hb + n] : ldg(b1 + n)));
                 hid[(size_t)r * d.Hb + n] = v;
                 dot = fmaf(v, ldg(w2 + n), dot);
             }

@@ -45,6 +45,12 @@ MMG_DEVICE float half_warp_sum(float v) {
 }
 
 MMG_DEVICE float shfl_xor_f(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+// Short-latency transcendentals for the recurrent fast path (MUFU.EX2 / MUFU.RCP; absolute error ~2e-7, far inside
+// the 1e-4 parity bar).  The generic kernels keep the libm-accurate versions.
+MMG_DEVICE float fast_exp(float x) { return __expf(x); }
+MMG_DEVICE float fast_rcp(float x) { return __fdividef(1.0f, x); }
+MMG_DEVICE float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+MMG_DEVICE float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 // sum over aligned groups of N lanes (N power of two <= 32); every lane of the group receives the sum
 template <int N>
 MMG_DEVICE float group_sum(float v) {
@@ -103,6 +109,16 @@ MMG_DEVICE void tma_stage(void* smem_dst, const void* gmem_src, uint32_t bytes, 
         uint32_t n = bytes - off < kPiece ? bytes - off : kPiece;
         tma_bulk_g2s((char*)smem_dst + off, (const char*)gmem_src + off, n, bar);
     }
+}
+// Two segments, one barrier phase (a second arrive.expect_tx would count as a second arrival).
+MMG_DEVICE void tma_stage2(void* dst1, const void* src1, uint32_t bytes1, void* dst2, const void* src2, uint32_t bytes2,
+                           uint64_t* bar) {
+    mbar_expect_tx(bar, bytes1 + bytes2);
+    const uint32_t kPiece = 32768;
+    for (uint32_t off = 0; off < bytes1; off += kPiece)
+        tma_bulk_g2s((char*)dst1 + off, (const char*)src1 + off, bytes1 - off < kPiece ? bytes1 - off : kPiece, bar);
+    for (uint32_t off = 0; off < bytes2; off += kPiece)
+        tma_bulk_g2s((char*)dst2 + off, (const char*)src2 + off, bytes2 - off < kPiece ? bytes2 - off : kPiece, bar);
 }
 // Programmatic dependent launch: wait for the producer grid's memory to be visible / let dependents start.
 MMG_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -194,6 +210,10 @@ MMG_DEVICE float half_warp_sum(float v) {
     return v;
 }
 MMG_DEVICE float shfl_xor_f(float v, int m) { return (float)emu::shfl_xor(v, m); }
+MMG_DEVICE float fast_exp(float x) { return expf(x); }
+MMG_DEVICE float fast_rcp(float x) { return 1.0f / x; }
+MMG_DEVICE float fast_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+MMG_DEVICE float fast_tanh(float x) { return 1.0f - 2.0f / (expf(2.0f * x) + 1.0f); }
 template <int N>
 MMG_DEVICE float group_sum(float v) {
     for (int o = N / 2; o > 0; o >>= 1) v += (float)emu::shfl_xor(v, o);
@@ -206,6 +226,11 @@ MMG_DEVICE void mbar_fence_init() {}
 MMG_DEVICE void mbar_wait(uint64_t*, uint32_t) {}
 MMG_DEVICE void tma_stage(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t*) {
     memcpy(smem_dst, gmem_src, bytes);
+}
+MMG_DEVICE void tma_stage2(void* dst1, const void* src1, uint32_t bytes1, void* dst2, const void* src2, uint32_t bytes2,
+                           uint64_t*) {
+    memcpy(dst1, src1, bytes1);
+    memcpy(dst2, src2, bytes2);
 }
 MMG_DEVICE void pdl_wait() {}
 MMG_DEVICE void pdl_launch_dependents() {}

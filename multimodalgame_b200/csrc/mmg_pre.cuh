@@ -139,7 +139,7 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
                 s = fmaf(ldg(in.desc + (size_t)dd * d.WV + v), ldg(P.p[MMG_P_REC_WD_W] + (size_t)k * d.WV + v), s);
             s = warp_sum(s);
             if (lane == 0) {
-                if (fast) W.fwd_image[ffi.wdd + ((dd >> 3) * d.Hr + k) * 8 + (dd & 7)] = s;
+                if (fast) W.fwd_image[ffi.wdd + ((dd >> 2) * d.Hr + k) * 4 + (dd & 3)] = s;
                 else      W.fwd_image[fim.wdd + oo] = s;
             }
         } else if (o < 2 * n_y1d + d.Hi) {     // hw0[n] = code_layer.bias[n] + sum_j sigmoid(code_bias[j]) * code_layer.weight[n][j]
@@ -157,11 +157,11 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
     }
     // pad tails of dot sections (keep the images fully defined for the bulk copies)
     if (fast) {
-        const int dpad8 = ((d.D + 7) / 8) * 8, dpad4 = ((d.D + 3) / 4) * 4;
-        for (int e = gtid; e < (dpad8 - d.D) * d.Hr; e += gthreads) {
+        const int dpad = ((d.D + 3) / 4) * 4;
+        for (int e = gtid; e < (dpad - d.D) * d.Hr; e += gthreads) {
             const int dd = d.D + e / d.Hr, k = e % d.Hr;
-            W.fwd_image[ffi.wdd + ((dd >> 3) * d.Hr + k) * 8 + (dd & 7)] = 0.f;
-            if (dd < dpad4) W.bwd_image[fbi.y1d + ((dd >> 2) * d.Hr + k) * 4 + (dd & 3)] = 0.f;
+            W.fwd_image[ffi.wdd + ((dd >> 2) * d.Hr + k) * 4 + (dd & 3)] = 0.f;
+            W.bwd_image[fbi.y1d + ((dd >> 2) * d.Hr + k) * 4 + (dd & 3)] = 0.f;
         }
         return;
     }

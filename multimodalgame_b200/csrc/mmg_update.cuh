@@ -13,7 +13,8 @@
 
 namespace mmg {
 
-enum { WG_GEMM = 0, WG_CODEBIAS = 2 };
+enum { WG_GEMM = 0, WG_ROWVEC = 1, WG_CODEBIAS = 2 };
+enum { kRowvecCols = 256 };
 enum { kMaxWgProblems = 20, kWgradKSlice = 128 };
 
 struct WgProblem {
@@ -67,6 +68,29 @@ k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, co
             }
         }
         if (want_bias && tid < kTile && mt * kTile + tid < pr.M) slab[pr.bias_off + mt * kTile + tid] = cs;
+    } else if (pr.kind == WG_ROWVEC) {
+        // single-row products C[0][j] = sum_k a[k] B[k][j] (STOP head, linear2 of both baselines): one column per thread
+        // instead of a 64x64 tile with 63 idle rows.  A: plain (K, 1) vector; B: plain k-major rows.
+        const int j = nt * kRowvecCols + tid;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f}, asum[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* a = pr.A.p;
+        const float* bp = pr.B.p + (j < pr.N ? j : 0);
+        int k = k0;
+        for (; k + 3 < k1; k += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float av = ldg(a + (size_t)(k + u) * pr.A.ld);
+                asum[u] += av;
+                acc[u] = fmaf(av, ldg(bp + (size_t)(k + u) * pr.B.ld), acc[u]);
+            }
+        }
+        for (; k < k1; ++k) {
+            const float av = ldg(a + (size_t)k * pr.A.ld);
+            asum[0] += av;
+            acc[0] = fmaf(av, ldg(bp + (size_t)k * pr.B.ld), acc[0]);
+        }
+        if (j < pr.N) slab[pr.c_off + j] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        if (pr.bias_off >= 0 && nt == 0 && tid == 0) slab[pr.bias_off] = (asum[0] + asum[1]) + (asum[2] + asum[3]);
     } else {
         // generic-path only (the fast backward kernel emits per-example partials instead):
         // d code_bias[j] = c0 (1 - c0) sum_n code_layer.weight[n][j] * (sum_b d_as[t=0][b][n])   (model.py:199-200)
