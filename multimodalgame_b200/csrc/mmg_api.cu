@@ -373,8 +373,10 @@ struct WgBuilder {
             p.ntm = cdiv(p.M, kTile);
             p.ntn = p.kind == WG_GEMM ? cdiv(p.N, kTile) : (p.kind == WG_ROWVEC ? cdiv(p.N, kRowvecCols) : 1);
             p.tile_begin = t->total_tiles;
+            t->tile_begin[i] = p.tile_begin;
             t->total_tiles += p.ntm * p.ntn * p.nsplit;
         }
+        t->tile_begin[t->count] = t->total_tiles;
     }
 };
 

@@ -18,8 +18,10 @@
 #if defined(MMG_PHASE_TIMING) && !defined(MMG_CPU_EMU)
 // debug build only (scripts/phase_timing.py): per-phase clock stamps of CTA 0 into the g_sen_probs scratch
 #define MMG_STAMP(p) do { if (lane == 0) stamps[(t * 8 + (p)) * 8 + warp] = (unsigned)clock64(); } while (0)
+#define MMG_BSTAMP(slot) do { if (threadIdx.x == 0 && (blockIdx.x == 0 || (int)blockIdx.x == n_rec_ctas)) reinterpret_cast<unsigned*>(W.g_bs)[((int)blockIdx.x == 0 ? 0 : 32) + (slot)] = (unsigned)clock64(); } while (0)
 #else
 #define MMG_STAMP(p) do { } while (0)
+#define MMG_BSTAMP(slot) do { } while (0)
 #endif
 
 namespace mmg {
@@ -126,7 +128,10 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
         pdl_wait();
         const int ntn = cdiv(d.Hb, kTile);
         const int tile = (int)blockIdx.x - n_conv_ctas, nt = tile % ntn, mt = tile / ntn;
-        Operand A = Operand{W.hx_part, nullptr, b_img, nullptr, HI, d.B, 0, W.hx_split, 0, OP_SUMSLABS};
+        // h_x rows are finalised by the conversation CTAs in their prologue (lower block indices, never blocked)
+        if (threadIdx.x == 0) flag_wait(W.tickets + 1, (unsigned)n_conv_ctas);
+        MMG_SYNCTHREADS();
+        Operand A = Operand{W.h_x, nullptr, nullptr, nullptr, HI, 0, 0, 0, 0, OP_PLAIN};
         Operand Bo = Operand{bs_w1, nullptr, nullptr, nullptr, HI + M, 0, 0, 0, 0, OP_PLAIN};
         float acc[4][4];
         gemm_tile(A, Bo, d.B, d.Hb, mt * kTile, nt * kTile, 0, HI, acc, nullptr, sm);
@@ -243,6 +248,10 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
         }
         if (n == 0) { sprod[bt] = 1.f; smask[bt] = 1.f; if (b < B) W.stop_mask[b] = 1; }
         for (int dd = D + n; dd < DP; dd += NT) yv[bt * DP + dd] = -INFINITY;   // padded classes never win the softmax
+    }
+    if (n_conv_ctas < (int)gridDim.x) {     // side-role CTAs wait for every h_x row
+        MMG_SYNCTHREADS();
+        if (tid == 0) flag_arrive(W.tickets + 1);
     }
     if (own_draws) {
         // every Bernoulli draw of this CTA's conversations up front (same Philox counters as the generic kernel:
@@ -600,7 +609,7 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
 // One example per CTA.  CTAs [0, n_rec): receiver (BPTT); the rest: sender (no recurrence, model.py:807-811).
 MMG_HOST_DEVICE int fast_bwd_rec_state_floats(int T, int M, int D) {
     // dlw (T,M) | dhw (T,64) | inj (T,64) | gat (T,5,64) | hws, y1hs (T,64 each) | dgh (2,192) | gv (64) | gout (DP) | dls (T) | barrier
-    return T * M + 2 * T * kFastHr + 5 * T * kFastHr + 2 * T * kFastHr + 2 * 3 * kFastHr + kFastHr + align4(D) + align4(T) + 8;
+    return T * (M + 4) + 2 * T * (kFastHr + 4) + 5 * T * kFastHr + 2 * T * kFastHr + 2 * 3 * kFastHr + kFastHr + align4(D) + align4(T) + 8;
 }
 MMG_HOST_DEVICE int fast_bwd_sen_state_floats(int T, int M) { return T * M + 2 * kFastHi + T * kFastHi + 8; }
 
@@ -619,12 +628,14 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
         const int b = (int)blockIdx.x - n_rec_ctas, n = tid;
         float* dlz = sm;                                              // (T, M)
         pdl_wait();
+        MMG_BSTAMP(0);
         float wb[M];                                                   // column n of binary_layer.weight
 #pragma unroll
         for (int j = 0; j < M; ++j) wb[j] = ldg(bin_w + (size_t)j * HI + n);
         float* das0 = sm + T * M;                                     // (256) d a at t = 0
         float* cred = das0 + HI;                                      // (256 / M, M) partial sums
         float* as_s = cred + HI;                                      // (T, 256) saved tanh outputs of this example
+#pragma unroll 4
         for (int t = 0; t < T; ++t) as_s[t * HI + n] = W.a_s[((size_t)t * B + b) * HI + n];
         for (int idx = tid; idx < T * M; idx += NT) {
             const int t = idx / M, j = idx % M;
@@ -635,6 +646,7 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
             dlz[idx] = dl;
         }
         MMG_SYNCTHREADS();
+        MMG_BSTAMP(1);
         float dhx = 0.f;
 #pragma unroll 2
         for (int t = 0; t < T; ++t) {
@@ -650,6 +662,7 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
             dhx += das;                                               // h_x is shared by all steps (model.py:195)
         }
         W.dhx[(size_t)b * HI + n] = dhx;
+        MMG_BSTAMP(2);
         // d code_layer-input at t = 0 (the code is sigmoid(code_bias) for every example, model.py:199-200):
         // dcode_part[b][j] = sum_n d_a[0][n] code_layer.weight[n][j]; K_wgrad sums over b and applies d sigmoid.
         MMG_SYNCTHREADS();
@@ -671,6 +684,7 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
             for (int p = 0; p < NT / M; ++p) v += cred[p * M + tid];
             W.dcode_part[(size_t)b * M + tid] = v;
         }
+        MMG_BSTAMP(3);
         return;
     }
 
@@ -679,9 +693,10 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
     const int b = blockIdx.x, lane = tid & 31;
     const int DP = align4(D);
     int o = im.total;
-    float* dlw = sm + o;  o += T * M;
-    float* dhw = sm + o;  o += T * HR;
-    float* inj = sm + o;  o += T * HR;
+    constexpr int LDM = M + 4, LDH = HR + 4;      // padded row strides: rows t, t+1, t+2, t+3 are read by one quarter-warp
+    float* dlw = sm + o;  o += T * LDM;
+    float* dhw = sm + o;  o += T * LDH;
+    float* inj = sm + o;  o += T * LDH;
     float* gat = sm + o;  o += 5 * T * HR;          // per step: r, u, n, gh_n, h_prev
     float* hws = sm + o;  o += T * HR;              // h_w of every step
     float* y1hs = sm + o; o += T * HR;              // y1h of every step (the prediction step is only known after the load)
@@ -701,6 +716,7 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     MMG_SYNCTHREADS();
     pdl_wait();
+    MMG_BSTAMP(0);
     // W_hh^T (48 KB) never touches shared memory: each thread keeps its 12 float4 of the BPTT mat-vec in registers
     if (tid == 0) tma_stage2(sm, W.bwd_image, (uint32_t)im.whhT * 4u, sm + im.ws, W.bwd_image + im.ws, (uint32_t)(im.total - im.ws) * 4u, bar);
     float4 rwhh[12];
@@ -719,12 +735,11 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
             dl = W.g_rec_probs[i] * p * (1.f - p);
         }
         W.d_lw[i] = dl;
-        dlw[idx] = dl;
+        dlw[t * LDM + j] = dl;
     }
-    for (int idx = tid; idx < T * 4 * HR; idx += NT) {
-        const int t = idx >> 8, c = idx & 255;
-        gat[t * 5 * HR + c] = W.gates[((size_t)t * B + b) * 4 * HR + c];
-    }
+#pragma unroll 4
+    for (int t = 0; t < T; ++t) gat[t * 5 * HR + tid] = W.gates[((size_t)t * B + b) * 4 * HR + tid];
+#pragma unroll 2
     for (int idx = tid; idx < T * HR; idx += NT) {
         const int t = idx >> 6, k = idx & 63;
         gat[t * 5 * HR + 4 * HR + k] = W.h_z[((size_t)t * B + b) * HR + k];   // slot t = state entering step t
@@ -740,23 +755,25 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
     }
     for (int dd = tid; dd < D; dd += NT) gout[dd] = W.g_outp[(size_t)b * D + dd];
     const int ys = W.ystep[b];
+    MMG_BSTAMP(1);
 #ifdef MMG_CPU_EMU
     MMG_SYNCTHREADS();
 #endif
     mbar_wait(bar, 0);
     MMG_SYNCTHREADS();
+    MMG_BSTAMP(2);
     const int k = tid >> 2, part = tid & 3;
     // ---- A1: d h_w for every step (t-parallel); class-score head at the prediction step ----------------------------
     for (int t = part; t < T; t += 4) {
         float4 a4 = zero4();
 #pragma unroll
-        for (int j4 = 0; j4 < M4; ++j4) fma4(WwT4[j4 * HR + k], lds4(dlw + t * M + 4 * j4), a4);
+        for (int j4 = 0; j4 < M4; ++j4) fma4(WwT4[j4 * HR + k], lds4(dlw + t * LDM + 4 * j4), a4);
         const float acc = hsum4(a4);
         const size_t i = ((size_t)t * B + b) * HR + k;
         const float hw = hws[t * HR + k];
         const float v = acc * (1.f - hw * hw);                        // through tanh (model.py:452)
         W.d_hw[i] = v;
-        dhw[t * HR + k] = v;
+        dhw[t * LDH + k] = v;
     }
     {
         // y[d] = y2.bias + sum_k w2[k] relu(y1h[k] + y1d[d][k])   (model.py:432-433)
@@ -780,25 +797,27 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
         }
     }
     MMG_SYNCTHREADS();
+    MMG_BSTAMP(3);
     // ---- A2: per-step injection into d h': W_h^T d_hw + s.weight * d_ls (+ W_1h^T G at the prediction step) --------
     for (int t = part; t < T; t += 4) {
         float4 a4 = zero4();
 #pragma unroll
-        for (int k4 = 0; k4 < HR / 4; ++k4) fma4(WhT4[k4 * HR + k], lds4(dhw + t * HR + 4 * k4), a4);
+        for (int k4 = 0; k4 < HR / 4; ++k4) fma4(WhT4[k4 * HR + k], lds4(dhw + t * LDH + 4 * k4), a4);
         if (t == ys) {
 #pragma unroll
             for (int k4 = 0; k4 < HR / 4; ++k4) fma4(W1hT4[k4 * HR + k], lds4(gv + 4 * k4), a4);
         }
-        inj[t * HR + k] = hsum4(a4) + wsv[k] * dls[t];
+        inj[t * LDH + k] = hsum4(a4) + wsv[k] * dls[t];
     }
     MMG_SYNCTHREADS();
+    MMG_BSTAMP(4);
     // ---- B: the BPTT chain (h_z is never detached between steps, model.py:340) --------------------------------------
     float direct = 0.f, rec = 0.f;
     int buf = 0;
     for (int t = T - 1; t >= 0; --t) {
         const float* g = gat + t * 5 * HR;
         const float r = g[k], u = g[HR + k], nn = g[2 * HR + k], ghn = g[3 * HR + k], hp = g[4 * HR + k];
-        const float dht = direct + rec + inj[t * HR + k];
+        const float dht = direct + rec + inj[t * LDH + k];
         // h' = n + u (h - n)
         const float du = dht * (hp - nn);
         const float dn = dht * (1.f - u);
@@ -827,6 +846,7 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
         }
         buf ^= 1;
     }
+    MMG_BSTAMP(5);
     (void)lane;
 }
 

@@ -12,7 +12,7 @@ namespace mmg {
 
 enum { kTile = 64, kChunk = 16, kLd = kTile + 4, kGemmThreads = 256 };
 enum { kGemmSmemFloats = 4 * kChunk * kLd };     // [buffer 0/1][A, B][kChunk][kLd]
-enum { OP_PLAIN = 0, OP_RELUGRAD = 1, OP_ONES = 2, OP_SUMSLABS = 3, OP_RELUGRAD_TSUM = 4 };
+enum { OP_PLAIN = 0, OP_RELUGRAD = 1, OP_ONES = 2, OP_RELUGRAD_TSUM = 4 };
 
 // Operand descriptor.  Element (k, i): k = reduction index, i = output index (row of C for A, column for B).
 struct Operand {
@@ -28,16 +28,10 @@ struct Operand {
                         //                         : (k >= split -> p2[i * ld2 + k - split]); 0 = none
     int kind;           // OP_PLAIN; OP_RELUGRAD: (p > 0) ? g[k] * w2[i] : 0; OP_ONES: 1 (column sums as a GEMM);
                         // OP_RELUGRAD_TSUM (k-major, k = example): w2[i] * sum_{t < mod} g[t * ld2 + k] * (p[(t * ld2 + k) * ld + i] > 0)
-                        // OP_SUMSLABS (k contiguous): g[k] + sum_{s < mod} p[(s * ld2 + i) * ld + k]  (split-K partials + bias)
 };
 
 MMG_DEVICE float operand_load(const Operand& op, int k, int i) {
     if (op.kind == OP_ONES) return 1.f;
-    if (op.kind == OP_SUMSLABS) {
-        float v = ldg(op.g + k);
-        for (int s = 0; s < op.mod; ++s) v += ldg(op.p + ((size_t)s * op.ld2 + i) * op.ld + k);
-        return v;
-    }
     if (op.kind == OP_RELUGRAD_TSUM) {
         float v = 0.f;
         for (int t = 0; t < op.mod; ++t)
@@ -73,7 +67,6 @@ MMG_DEVICE bool aligned16(const void* p) { return (((size_t)p) & 15) == 0; }
 //   mode 3 (float4 along k):       (kk, ii) = (4 (tid % 4) + c, tid/4)
 MMG_DEVICE int operand_mode(const Operand& op, int k0) {
     if (op.kind == OP_ONES) return 0;
-    if (op.kind == OP_SUMSLABS) return ((op.ld & 3) == 0 && aligned16(op.p) && aligned16(op.g) && (k0 & 3) == 0) ? 3 : 1;
     if (op.kind == OP_RELUGRAD_TSUM) return ((op.ld & 3) == 0 && aligned16(op.p) && aligned16(op.w2)) ? 2 : 0;
     const bool ok2 = op.p2 == nullptr || op.split == 0 || ((op.split & 3) == 0 && (op.ld2 & 3) == 0 && aligned16(op.p2));
     if ((op.ld & 3) != 0 || !aligned16(op.p) || !ok2) return op.kmajor ? 0 : 1;
@@ -122,15 +115,7 @@ MMG_DEVICE float4 chunk_fetch(const Operand& op, int mode, int kbase, int kend, 
     } else if (mode == 3) {
         const int k = kbase + 4 * (tid & 3), i = ibase + (tid >> 2);
         if (i < ilim) {
-            if (op.kind == OP_SUMSLABS && k + 3 < kend) {
-                float4 r = ldg4(reinterpret_cast<const float4*>(op.g + k));
-                for (int s = 0; s < op.mod; ++s) {
-                    const float4 a = ldg4(reinterpret_cast<const float4*>(op.p + ((size_t)s * op.ld2 + i) * op.ld + k));
-                    r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
-                }
-                return r;
-            }
-            if (op.kind != OP_SUMSLABS && k + 3 < kend && !(op.split > 0 && k + 3 >= op.split && k < op.split)) {
+            if (k + 3 < kend && !(op.split > 0 && k + 3 >= op.split && k < op.split)) {
                 if (op.split > 0 && k >= op.split)
                     return ldg4(reinterpret_cast<const float4*>(op.p2 + (size_t)i * op.ld2 + (k - op.split)));
                 const int row = op.mod > 0 ? i % op.mod : i;

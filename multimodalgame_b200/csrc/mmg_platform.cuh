@@ -64,6 +64,13 @@ MMG_DEVICE unsigned ticket_take(unsigned* counter) {
     return atomicAdd(counter, 1u);
 }
 MMG_DEVICE void fence_acquire() { __threadfence(); }
+// Producer side: publish this CTA's global writes, then count it.  Consumer side: spin until `target` CTAs have arrived.
+// Only legal when the producers cannot be starved by the spinning CTAs (producers have lower block indices and never wait).
+MMG_DEVICE void flag_arrive(unsigned* counter) { __threadfence(); atomicAdd(counter, 1u); }
+MMG_DEVICE void flag_wait(const unsigned* counter, unsigned target) {
+    while (*reinterpret_cast<const volatile unsigned*>(counter) < target) __nanosleep(64);
+    __threadfence();
+}
 
 // ---- mbarrier + TMA bulk copy (cp.async.bulk, SASS UBLKCP) ------------------------------------------
 MMG_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -221,6 +228,10 @@ MMG_DEVICE float group_sum(float v) {
 }
 MMG_DEVICE unsigned ticket_take(unsigned* counter) { return __atomic_fetch_add(counter, 1u, __ATOMIC_SEQ_CST); }
 MMG_DEVICE void fence_acquire() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+MMG_DEVICE void flag_arrive(unsigned* counter) { __atomic_fetch_add(counter, 1u, __ATOMIC_SEQ_CST); }
+MMG_DEVICE void flag_wait(const unsigned* counter, unsigned target) {   // blocks run in index order: already satisfied
+    while (__atomic_load_n(counter, __ATOMIC_SEQ_CST) < target) {}
+}
 MMG_DEVICE void mbar_init(uint64_t* bar, int) { *bar = 0; }
 MMG_DEVICE void mbar_fence_init() {}
 MMG_DEVICE void mbar_wait(uint64_t*, uint32_t) {}

@@ -65,6 +65,7 @@ MMG_GLOBAL void __launch_bounds__(kGemmThreads)
 k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_kslice, int fast) {
     MMG_SHARED __attribute__((aligned(16))) float gs[kGemmSmemFloats];
     const int tid = threadIdx.x;
+    if (blockIdx.x == 0 && tid == 0) W.tickets[1] = 0;      // "h_x rows ready" counter of the next forward kernel
     if ((int)blockIdx.x < n_hx_tiles) {
         // ---- role A: h_x split-K tile -------------------------------------------------------------------
         const int ntn = cdiv(d.Hi, kTile), ntm = cdiv(d.B, kTile);

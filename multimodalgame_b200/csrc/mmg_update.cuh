@@ -30,16 +30,17 @@ struct WgProblem {
 };
 struct WgTable {
     WgProblem p[kMaxWgProblems];
+    int tile_begin[kMaxWgProblems + 1];   // compact copy for the per-CTA problem lookup
     int count, total_tiles;
     long long slab_stride;   // floats between consecutive arena slabs (= flat layout total)
 };
 
-MMG_GLOBAL void __launch_bounds__(kGemmThreads)
+MMG_GLOBAL void __launch_bounds__(kGemmThreads, 4)
 k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, const float* code_bias, const float* d_as) {
     MMG_SHARED __attribute__((aligned(16))) float gs[kGemmSmemFloats];
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
     int tile = blockIdx.x, pi = 0;
-    while (pi + 1 < tab.count && tile >= tab.p[pi + 1].tile_begin) ++pi;
+    while (pi + 1 < tab.count && tile >= tab.tile_begin[pi + 1]) ++pi;
     const WgProblem& pr = tab.p[pi];
     tile -= pr.tile_begin;
     const int per_split = pr.ntm * pr.ntn;
@@ -55,15 +56,21 @@ k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, co
         float cs = 0.f;
         const bool want_bias = pr.bias_off >= 0 && nt == 0;
         gemm_tile(pr.A, pr.B, pr.M, pr.N, mt * kTile, nt * kTile, k0, k1, acc, want_bias ? &cs : nullptr, gs);
+        const int j0 = nt * kTile + tx * 4;
+        const bool vec = j0 + 3 < pr.N && (pr.ldc & 3) == 0 && (pr.c_off & 3) == 0 && pr.sig_rows == nullptr;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int i = mt * kTile + ty * 4 + a;
             if (i >= pr.M) continue;
+            if (vec) {
+                *reinterpret_cast<float4*>(slab + pr.c_off + (size_t)i * pr.ldc + j0) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+                continue;
+            }
             float rs = 1.f;
             if (pr.sig_rows != nullptr) { const float c0 = sigmoidf_(ldg(pr.sig_rows + i)); rs = c0 * (1.f - c0); }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const int j = nt * kTile + tx * 4 + c;
+                const int j = j0 + c;
                 if (j < pr.N) slab[pr.c_off + (size_t)i * pr.ldc + j] = acc[a][c] * rs;
             }
         }
