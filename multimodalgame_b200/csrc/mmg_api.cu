@@ -528,8 +528,8 @@ int mmg_workspace_init(const mmg_config* cfg, void* d_workspace, uint64_t seed, 
     return check_cuda("k_init_rng");
 }
 
-int mmg_exchange_forward(const mmg_config* cfg, const float* d_params, const mmg_inputs* in, void* d_workspace,
-                         void* stream) {
+static int exchange_forward_impl(const mmg_config* cfg, const float* d_params, const mmg_inputs* in, void* d_workspace,
+                                 void* stream, bool finish_baselines) {
     int rc = validate(cfg);
     if (rc) return rc;
     if (!d_params || !in || !d_workspace || !in->d_x || !in->d_desc) return fail(MMG_ERR_INVALID, "null pointer argument");
@@ -565,8 +565,17 @@ int mmg_exchange_forward(const mmg_config* cfg, const float* d_params, const mmg
         const int wd_tiles = pl.fast ? cdiv(d.R, kTile) * cdiv(d.WV, kTile) : 0;   // the generic kernel writes wd itself
         MMG_LAUNCH(k_baseline_fwd, tiles + wd_tiles, kGemmThreads, 0, st, d, P, W, ei.desc, tiles, pl.fast);
         if ((rc = check_cuda("k_baseline_fwd"))) return rc;
+        if (finish_baselines) {     // standalone forward: bs / br must be final on return (mmg_loss re-derives them anyway)
+            MMG_LAUNCH(k_baseline_finish, cdiv(d.R, 256), 256, 0, st, d, P, W);
+            if ((rc = check_cuda("k_baseline_finish"))) return rc;
+        }
     }
     return MMG_OK;
+}
+
+int mmg_exchange_forward(const mmg_config* cfg, const float* d_params, const mmg_inputs* in, void* d_workspace,
+                         void* stream) {
+    return exchange_forward_impl(cfg, d_params, in, d_workspace, stream, true);
 }
 
 int mmg_loss(const mmg_config* cfg, const float* d_params, const mmg_inputs* in, void* d_workspace, int phase,
@@ -679,7 +688,7 @@ int mmg_train_step(const mmg_config* cfg, float* d_params, float* d_grads, float
                    int64_t step, const mmg_inputs* in, void* d_workspace, void* stream) {
     int rc;
     if (!in || !in->train) return fail(MMG_ERR_INVALID, "mmg_train_step needs in->train = 1");
-    if ((rc = mmg_exchange_forward(cfg, d_params, in, d_workspace, stream))) return rc;
+    if ((rc = exchange_forward_impl(cfg, d_params, in, d_workspace, stream, false))) return rc;
     if ((rc = mmg_loss(cfg, d_params, in, d_workspace, -1, stream))) return rc;
     if ((rc = mmg_backward(cfg, d_params, in, d_workspace, d_grads, stream))) return rc;
     return mmg_clip_update(cfg, d_params, d_grads, d_state1, d_state2, step, 1.0f, d_workspace, stream);

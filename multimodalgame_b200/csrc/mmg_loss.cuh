@@ -81,6 +81,17 @@ k_baseline_fwd(Dims d, ParamPtrs P, WsPtrs W, const float* desc, int n_bas_tiles
     }
 }
 
+// Baseline scores = linear2 bias + the per-tile partial dot products of K_baseline_fwd (summed in tile order).
+MMG_GLOBAL void __launch_bounds__(256)
+k_baseline_finish(Dims d, ParamPtrs P, WsPtrs W) {
+    const float b2s = ldg(P.p[MMG_P_BS_L2_B]), b2r = ldg(P.p[MMG_P_BR_L2_B]);
+    for (int r = blockIdx.x * 256 + threadIdx.x; r < d.R; r += gridDim.x * 256) {
+        float s = b2s, q = b2r;
+        for (int j = 0; j < W.ntb; ++j) { s += W.bs_part[(size_t)r * W.ntb + j]; q += W.br_part[(size_t)r * W.ntb + j]; }
+        W.bs[r] = s; W.br[r] = q;
+    }
+}
+
 enum { kStatsThreads = 1024 };
 
 MMG_DEVICE unsigned char mask_at(const Dims& d, const WsPtrs& W, int slot, int b) {

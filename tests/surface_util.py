@@ -1,0 +1,198 @@
+"""Drives the reference-facing Python surface (multimodalgame_b200/model.py: Sender / Receiver / Baseline modules,
+exchange(), the loss functions, train_step()) exactly the way the reference's run() does (model.py:1240-1330) and
+compares with the CPU oracle.  Used by the CPU test (emulated kernels) and the GPU test (CUDA library)."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from multimodalgame_b200 import model as M
+from oracle import game_oracle as go
+from tests import golden_util as gu, parity_util as pu
+
+# state_dict keys of the reference's modules (verified against the reference classes)
+REF_KEYS = {
+    "sender": ["code_bias", "image_layer.weight", "image_layer.bias", "code_layer.weight", "code_layer.bias",
+               "binary_layer.weight", "binary_layer.bias"],
+    "receiver": ["rnn.weight_ih", "rnn.weight_hh", "rnn.bias_ih", "rnn.bias_hh", "w_h.weight", "w_h.bias", "w_d.weight",
+                 "w.weight", "w.bias", "y1.weight", "y1.bias", "y2.weight", "y2.bias", "s.weight", "s.bias"],
+    "baseline": ["linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias"],
+}
+
+_flags_defined = False
+
+
+def set_flags(cfg):
+    """Parse a reference-style command line (single-dash gflags syntax, model.py:1639-1741)."""
+    global _flags_defined
+    if not _flags_defined:
+        M.flags()
+        _flags_defined = True
+    argv = ["model.py", "-max_exchange", str(cfg.max_exchange), "-learning_rate", repr(cfg.learning_rate),
+            "-optim_type", cfg.optim_type, "-top_k_train", str(cfg.top_k_train), "-first_rec", repr(cfg.first_rec),
+            "-img_feat_dim", str(cfg.img_feat_dim), "-img_h_dim", str(cfg.img_h_dim), "-baseline_hid_dim",
+            str(cfg.baseline_hid_dim), "-sender_out_dim", str(cfg.sender_out_dim), "-rec_w_dim", str(cfg.rec_w_dim),
+            "-rec_hidden", str(cfg.rec_hidden), "-wv_dim", str(cfg.wv_dim), "-batch_size", str(cfg.batch_size)]
+    argv.append("-fixed_exchange" if cfg.fixed_exchange else "-nofixed_exchange")
+    argv.append("-use_binary" if cfg.use_binary else "-nouse_binary")
+    argv.append("-s_prob_prod" if cfg.s_prob_prod else "-nos_prob_prod")
+    for name in ("entropy_s", "entropy_sen", "entropy_rec"):
+        if getattr(cfg, name) is not None:
+            argv += ["-" + name, repr(getattr(cfg, name))]
+    M.FLAGS.unparse_flags()
+    for name in ("entropy_s", "entropy_sen", "entropy_rec"):
+        M.FLAGS[name].value = None
+    M.FLAGS(argv)
+    M.default_flags(argv)
+
+
+def build_modules(cfg, params, device):
+    """The four modules with the reference's constructor signatures (model.py:1014-1064)."""
+    sender = M.Sender("avgpool_512", cfg.img_feat_dim, cfg.img_h_dim, cfg.rec_w_dim, cfg.sender_out_dim, cfg.use_binary,
+                      False, 0, False, 0)
+    receiver = M.Receiver(cfg.sender_out_dim, cfg.wv_dim, cfg.rec_hidden, 1, cfg.rec_w_dim, 1, cfg.use_binary)
+    baseline_sen = M.Baseline(cfg.baseline_hid_dim, cfg.img_h_dim, cfg.rec_w_dim, 0)
+    baseline_rec = M.Baseline(cfg.baseline_hid_dim, 0, cfg.sender_out_dim, cfg.rec_hidden)
+    mods = dict(sender=sender, receiver=receiver, baseline_sen=baseline_sen, baseline_rec=baseline_rec)
+    assert list(sender.state_dict().keys()) == REF_KEYS["sender"]
+    assert list(receiver.state_dict().keys()) == REF_KEYS["receiver"]
+    assert list(baseline_sen.state_dict().keys()) == REF_KEYS["baseline"]
+    for a, m in mods.items():
+        if a in params:
+            m.load_state_dict(params[a])          # reference checkpoints load by key name
+        m.to(device)
+    return mods
+
+
+def reference_update_block(mods, cfg, x, desc, target, uniforms):
+    """model.py:1240-1330 written against the mirrored names; returns the loss dict (gradients land in .grad)."""
+    fl = M.FLAGS
+    exchange_args = dict(data=x, target=target, desc=desc, train=True, break_early=not fl.fixed_exchange,
+                         uniforms=uniforms)
+    s, sen_w, rec_w, y, bs, br = M.exchange(mods["sender"], mods["receiver"], mods["baseline_sen"], mods["baseline_rec"],
+                                            exchange_args)
+    s_masks, s_feats, s_probs = s
+    sen_feats, sen_probs = sen_w
+    rec_feats, rec_probs = rec_w
+    if fl.fixed_exchange:                                                     # model.py:1248-1262
+        binary_s_masks = binary_rec_masks = binary_sen_masks = bas_rec_masks = bas_sen_masks = y_masks = None
+    else:
+        binary_s_masks = s_masks[:-1]
+        binary_rec_masks = s_masks[1:-1]
+        binary_sen_masks = s_masks[:-1]
+        bas_rec_masks = s_masks[:-1]
+        bas_sen_masks = s_masks[:-1]
+        y_masks = [torch.min(1 - m2, m1) for m1, m2 in zip(s_masks[:-1], s_masks[1:])]
+    outp, _ = M.get_rec_outp(y, y_masks)                                      # model.py:1264
+    dist = F.log_softmax(outp, dim=1)
+    nll_loss = F.nll_loss(dist, target)
+    logs = M.loglikelihood(dist.detach(), target.view(-1, 1))
+    out = dict(nll_loss=nll_loss, steps=len(y), y=y, sen_feats=sen_feats, rec_feats=rec_feats, sen_probs=sen_probs,
+               s_masks=s_masks)
+    for m in mods.values():
+        m.zero_grad()
+    if cfg.use_binary:
+        loss_binary_s = None
+        if not fl.fixed_exchange:
+            loss_binary_s, _ = M.multistep_loss_binary(s_feats, s_probs, logs, br, binary_s_masks, fl.entropy_s)
+        if len(rec_feats[:-1]) > 0:                                            # model.py:1284-1289
+            loss_binary_rec, _ = M.multistep_loss_binary(rec_feats[:-1], rec_probs[:-1], logs, br[:-1], binary_rec_masks,
+                                                         fl.entropy_rec)
+        else:
+            loss_binary_rec = torch.zeros((), device=x.device)
+        loss_binary_sen, _ = M.multistep_loss_binary(sen_feats, sen_probs, logs, bs, binary_sen_masks, fl.entropy_sen)
+        loss_bas_rec = M.multistep_loss_bas(br, logs, bas_rec_masks)
+        loss_bas_sen = M.multistep_loss_bas(bs, logs, bas_sen_masks)
+        loss_rec = nll_loss + loss_binary_rec + (loss_binary_s if loss_binary_s is not None else 0)
+        loss_sen = loss_binary_sen
+        loss_rec.backward(retain_graph=True)                                   # the four graphs meet in one fused node
+        loss_sen.backward(retain_graph=True)
+        loss_bas_rec.backward(retain_graph=True)
+        loss_bas_sen.backward()
+        out.update(loss_rec=loss_rec, loss_sen=loss_sen, loss_bas_rec=loss_bas_rec, loss_bas_sen=loss_bas_sen)
+    else:
+        nll_loss.backward()
+        out.update(loss_rec=nll_loss)
+    return out
+
+
+def run_surface_case(case, device, iters=1):
+    z, cfg = gu.load(case)
+    set_flags(cfg)
+    params = gu.params_at(z, "P0")
+    full = go.init_params(cfg, seed=1)            # fixtures may store a subset of the agents
+    for a in full:
+        if a not in params:
+            params[a] = full[a]
+    oparams = go.clone_params(params)
+    mods = build_modules(cfg, params, device)
+    B = cfg.batch_size
+    x, desc, target = gu.batch_at(z, 0)
+    us = gu.uniforms_at(z, 0, cfg)
+    ex, res, grads = go.train_iteration(oparams, go.new_opt_state(oparams), x, target, desc, cfg, us, return_grads=True)
+    uni = tuple(u.to(device) for u in pu.stack_uniforms(us, cfg, B))
+    out = reference_update_block(mods, cfg, x.to(device), desc.to(device), target.to(device), uni)
+    Tp = len(ex["y"])
+    assert out["steps"] == Tp, (out["steps"], Tp)
+    st = lambda key: np.stack([t.detach().numpy() for t in ex[key]], 0)
+    got = lambda lst: np.stack([t.detach().cpu().numpy() for t in lst], 0)
+    pu.assert_close(case + "/y", got(out["y"]), st("y"))
+    if cfg.use_binary:
+        assert np.array_equal(got(out["sen_feats"]), st("sen_feats"))
+        assert np.array_equal(got(out["rec_feats"]), st("rec_feats"))
+        pu.assert_close(case + "/sen_probs", got(out["sen_probs"]), st("sen_probs"))
+    assert len(out["s_masks"]) == Tp + 1 and float(out["s_masks"][-1].sum()) == 0.0      # model.py:870
+    for name in ("nll_loss", "loss_rec", "loss_sen", "loss_bas_rec", "loss_bas_sen"):
+        if name in out and name in res:
+            pu.assert_close(case + "/" + name, float(out[name]), float(res[name]))
+    for a, mod in mods.items():
+        if a not in grads:
+            continue
+        gmax = max([float(g.abs().max()) for g in grads[a].values() if g is not None] + [1e-12])
+        for k, p in mod.named_parameters():
+            g = grads[a].get(k)
+            if g is None or (a, k) == ("receiver", "y2.bias"):
+                continue
+            assert p.grad is not None, (a, k)
+            pu.assert_close("%s/grad %s.%s" % (case, a, k), p.grad.detach().cpu().numpy(), g.numpy(), rtol=2e-3,
+                            atol=2e-5 * gmax + 1e-9)
+    return out
+
+
+def run_train_step_case(case, device):
+    """model.train_step(): the fused iteration behind the reference's module objects; module parameters (views of the
+    engine's flat buffer) must equal the oracle's post-step parameters, and .grad must hold the clipped gradients."""
+    z, cfg = gu.load(case)
+    set_flags(cfg)
+    params = gu.params_at(z, "P0")
+    full = go.init_params(cfg, seed=1)
+    for a in full:
+        if a not in params:
+            params[a] = full[a]
+    oparams = go.clone_params(params)
+    mods = build_modules(cfg, params, device)
+    x, desc, target = gu.batch_at(z, 0)
+    us = gu.uniforms_at(z, 0, cfg)
+    ex, res, grads = go.train_iteration(oparams, go.new_opt_state(oparams), x, target, desc, cfg, us, return_grads=True)
+    uni = tuple(u.to(device) for u in pu.stack_uniforms(us, cfg, cfg.batch_size))
+    eng = M.train_step(mods["sender"], mods["receiver"], mods["baseline_sen"], mods["baseline_rec"],
+                       dict(data=x.to(device), target=target.to(device), desc=desc.to(device), train=True, uniforms=uni))
+    L = eng.losses()
+    for name in ("nll_loss", "loss_rec", "loss_sen", "loss_bas_rec", "loss_bas_sen"):
+        if name in res:
+            pu.assert_close(case + "/" + name, L[name], float(res[name].detach()))
+    lr = cfg.learning_rate
+    for a, mod in mods.items():
+        if a not in oparams:
+            continue
+        for k, p in mod.named_parameters():
+            if (a, k) == ("receiver", "y2.bias"):
+                continue
+            g = grads.get(a, {}).get(k)
+            atol = 2e-2 * lr + 1e-7
+            if cfg.optim_type == "SGD":
+                atol = lr * 1e-3 + 1e-7
+            elif g is not None:
+                atol = np.where((g.abs() < 1e-6).numpy(), 12 * lr, atol)
+            pu.assert_close("%s/param %s.%s" % (case, a, k), p.detach().cpu().numpy(), oparams[a][k].numpy(), rtol=1e-5,
+                            atol=atol)
+    return eng
