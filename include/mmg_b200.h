@@ -244,6 +244,18 @@ int mmg_train_step_host(const mmg_config* cfg, float* d_params, float* d_grads, 
                         float* d_x_stage, int64_t* d_target_stage, float* d_desc_stage, const mmg_inputs* in,
                         void* d_workspace, float* h_losses, void* stream);
 
+/* Pipelined host-buffer variant: the H2D copy of batch i+1 runs on `copy_stream` while batch i trains on `stream`.
+ * mmg_host_prefetch: waits (on copy_stream) for `ev_free` (the staging slot's previous consumer), copies x (B,F) and
+ *   target (B) from pinned host memory into the slot and records `ev_ready`.
+ * mmg_train_step_staged: `stream` waits for `ev_ready`, runs mmg_train_step on the slot (in->d_x / in->d_target point
+ *   at it), records `ev_free` and copies the MMG_LOSS_COUNT loss floats to `h_losses` (pinned).  Streams and events are
+ *   caller-owned handles (cudaStream_t / cudaEvent_t passed as void*); nothing synchronises the host. */
+int mmg_host_prefetch(const mmg_config* cfg, const float* h_x, const int64_t* h_target, float* d_x_stage,
+                      int64_t* d_target_stage, void* copy_stream, void* ev_free, void* ev_ready);
+int mmg_train_step_staged(const mmg_config* cfg, float* d_params, float* d_grads, float* d_state1, float* d_state2,
+                          int64_t step, const mmg_inputs* in, void* d_workspace, float* h_losses, void* stream,
+                          void* ev_ready, void* ev_free);
+
 /* Number of kernels the last call of each entry point enqueued (for launch accounting). */
 int mmg_launch_count(void);
 void mmg_launch_count_reset(void);

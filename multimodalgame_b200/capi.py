@@ -75,7 +75,7 @@ class Library(object):
 
     SYMBOLS = ("mmg_abi_version", "mmg_last_error", "mmg_device_count", "mmg_param_layout_get",
                "mmg_workspace_layout_get", "mmg_workspace_init", "mmg_exchange_forward", "mmg_loss", "mmg_backward",
-               "mmg_grad_norm", "mmg_clip_update", "mmg_train_step", "mmg_train_step_host", "mmg_launch_count",
+               "mmg_grad_norm", "mmg_clip_update", "mmg_train_step", "mmg_train_step_host", "mmg_host_prefetch", "mmg_train_step_staged", "mmg_launch_count",
                "mmg_launch_count_reset")
 
     def __init__(self, path):
@@ -100,6 +100,8 @@ class Library(object):
         d.mmg_clip_update.argtypes = [cfgp, vp, vp, vp, vp, i64, f32, vp, vp]
         d.mmg_train_step.argtypes = [cfgp, vp, vp, vp, vp, i64, inp, vp, vp]
         d.mmg_train_step_host.argtypes = [cfgp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, inp, vp, vp, vp]
+        d.mmg_host_prefetch.argtypes = [cfgp, vp, vp, vp, vp, vp, vp, vp]
+        d.mmg_train_step_staged.argtypes = [cfgp, vp, vp, vp, vp, i64, inp, vp, vp, vp, vp, vp]
         for name in self.SYMBOLS:
             fn = getattr(d, name)
             if name not in ("mmg_last_error", "mmg_launch_count_reset"):

@@ -729,4 +729,47 @@ int mmg_train_step_host(const mmg_config* cfg, float* d_params, float* d_grads, 
 #endif
 }
 
+int mmg_host_prefetch(const mmg_config* cfg, const float* h_x, const int64_t* h_target, float* d_x_stage,
+                      int64_t* d_target_stage, void* copy_stream, void* ev_free, void* ev_ready) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!h_x || !h_target || !d_x_stage || !d_target_stage || !ev_ready) return fail(MMG_ERR_INVALID, "null pointer argument");
+#ifndef MMG_CPU_EMU
+    cudaStream_t cs = (cudaStream_t)copy_stream;
+    const Dims d = make_dims(*cfg);
+    if (ev_free != nullptr && cudaStreamWaitEvent(cs, (cudaEvent_t)ev_free, 0) != cudaSuccess) return check_cuda("wait ev_free");
+    if (cudaMemcpyAsync(d_x_stage, h_x, (size_t)d.B * d.F * sizeof(float), cudaMemcpyHostToDevice, cs) != cudaSuccess)
+        return check_cuda("H2D x");
+    if (cudaMemcpyAsync(d_target_stage, h_target, (size_t)d.B * sizeof(int64_t), cudaMemcpyHostToDevice, cs) != cudaSuccess)
+        return check_cuda("H2D target");
+    if (cudaEventRecord((cudaEvent_t)ev_ready, cs) != cudaSuccess) return check_cuda("record ev_ready");
+    return MMG_OK;
+#else
+    (void)copy_stream; (void)ev_free;
+    return fail(MMG_ERR_UNSUPPORTED, "host-buffer entry point is not part of the emulation build");
+#endif
+}
+
+int mmg_train_step_staged(const mmg_config* cfg, float* d_params, float* d_grads, float* d_state1, float* d_state2,
+                          int64_t step, const mmg_inputs* in, void* d_workspace, float* h_losses, void* stream,
+                          void* ev_ready, void* ev_free) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!in || !h_losses || !ev_ready || !ev_free) return fail(MMG_ERR_INVALID, "null pointer argument");
+#ifndef MMG_CPU_EMU
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaStreamWaitEvent(st, (cudaEvent_t)ev_ready, 0) != cudaSuccess) return check_cuda("wait ev_ready");
+    if ((rc = mmg_train_step(cfg, d_params, d_grads, d_state1, d_state2, step, in, d_workspace, stream))) return rc;
+    if (cudaEventRecord((cudaEvent_t)ev_free, st) != cudaSuccess) return check_cuda("record ev_free");
+    Ws w;
+    ws_layout(make_dims(*cfg), &w);
+    if (cudaMemcpyAsync(h_losses, (char*)d_workspace + w.pub.losses, MMG_LOSS_COUNT * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        return check_cuda("D2H losses");
+    return MMG_OK;
+#else
+    (void)d_params; (void)d_grads; (void)d_state1; (void)d_state2; (void)step; (void)d_workspace; (void)stream;
+    return fail(MMG_ERR_UNSUPPORTED, "host-buffer entry point is not part of the emulation build");
+#endif
+}
+
 }  // extern "C"

@@ -170,6 +170,45 @@ class GameEngine(object):
                       self.state1.data_ptr(), s2, C.c_int64(self.step), C.byref(self._inp), self.workspace.data_ptr(),
                       self._stream())
 
+    # ---- host-buffer pipeline (the end-to-end path: pinned host batches in, loss values out) -------------------------
+    def enable_host_pipeline(self, desc):
+        """Two device staging slots + a copy stream: the H2D copy of batch i+1 overlaps the training of batch i."""
+        d = self.dims
+        dev = self.device
+        self._hp = dict(
+            copy_stream=torch.cuda.Stream(device=dev),
+            x=[torch.empty(d["B"], d["F"], dtype=torch.float32, device=dev) for _ in range(2)],
+            t=[torch.empty(d["B"], dtype=torch.int64, device=dev) for _ in range(2)],
+            ready=[torch.cuda.Event() for _ in range(2)], free=[torch.cuda.Event() for _ in range(2)],
+            desc=torch.as_tensor(desc).to(device=dev, dtype=torch.float32).contiguous(), used=[False, False], n=0)
+        self._hp["inp"] = [self._inputs(self._hp["x"][i], self._hp["desc"], self._hp["t"][i], True, None, None, None, 6)
+                           for i in range(2)]
+        self._keep = None
+
+    def host_prefetch(self, h_x, h_target):
+        """Enqueue the H2D copy of the NEXT batch (pinned host tensors) into the free staging slot."""
+        hp = self._hp
+        slot = hp["n"] % 2
+        free = C.c_void_p(hp["free"][slot].cuda_event) if hp["used"][slot] else None
+        hp["ready"][slot].record(hp["copy_stream"])      # materialise the event handle before the C call re-records it
+        self.lib.call("mmg_host_prefetch", C.byref(self.cfg), h_x.data_ptr(), h_target.data_ptr(),
+                      hp["x"][slot].data_ptr(), hp["t"][slot].data_ptr(), C.c_void_p(hp["copy_stream"].cuda_stream), free,
+                      C.c_void_p(hp["ready"][slot].cuda_event))
+        hp["n"] += 1
+        hp["pending"] = slot
+
+    def train_step_staged(self, h_losses, slot):
+        """Train on staging slot `slot` (its prefetch was enqueued earlier); loss values land in pinned `h_losses`."""
+        hp = self._hp
+        self.step += 1
+        s2 = None if self.state2 is None else self.state2.data_ptr()
+        hp["free"][slot].record(torch.cuda.current_stream(self.device))
+        self.lib.call("mmg_train_step_staged", C.byref(self.cfg), self.params.data_ptr(), self.grads.data_ptr(),
+                      self.state1.data_ptr(), s2, C.c_int64(self.step), C.byref(hp["inp"][slot]), self.workspace.data_ptr(),
+                      h_losses.data_ptr(), self._stream(), C.c_void_p(hp["ready"][slot].cuda_event),
+                      C.c_void_p(hp["free"][slot].cuda_event))
+        hp["used"][slot] = True
+
     def train_step_dp(self, x, desc, target, group=None, uniforms=None, top_k=6):
         """Data-parallel iteration: this rank's batch shard; batch statistics and gradients are all-reduced
         (SURVEY.md §8e).  Two collectives per iteration: a few hundred doubles, then the flat gradient buffer."""
