@@ -278,6 +278,16 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     bytes_iter = algorithmic_bytes_per_iteration(cfgd, world)
+    # DRAM traffic per iteration from the committed ncu capture of this same command (profiles/, L2-flushed protocol)
+    traffic, traffic_src = None, None
+    if name == "C2" and world == 1 and flush is not None:
+        try:
+            import glob
+            f = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_dram_traffic.json")))[-1]
+            traffic = float(json.load(open(f))["per_iteration"]["total_bytes"])
+            traffic_src = os.path.relpath(f, ROOT)
+        except Exception:
+            pass
     ms_per_step = tot_ms / K
     achieved = bytes_iter / (ms_per_step * 1e-3) / 1e9
     value = world * steps_per_iter * K / (tot_ms * 1e-3)
@@ -294,8 +304,11 @@ def main():
         "gpu_launches": int(launches), "launches_per_step": launches / float(K),
         "wall_s_timed_region": t_wall, "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_iteration": bytes_iter,
-                     "kernel": "whole iteration (9 kernels); the path is latency/dependency-bound, see DESIGN.md"},
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "algorithmic_bytes_per_iteration": bytes_iter,
+                     "kernel": "whole iteration = one launch sequence of 9 kernels (k_pre, k_exchange_fwd, k_baseline_fwd, k_stats, "
+                               "k_lossgrad, k_exchange_bwd, k_wgrad, k_reduce_norm, k_update); achieved = algorithmic bytes per "
+                               "iteration / CUDA-event time per iteration; the path is latency/dependency-bound, see DESIGN.md"},
     }
     if e2e is not None:
         out["e2e"] = e2e
