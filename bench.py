@@ -150,6 +150,8 @@ def main():
     ap.add_argument("--config", default=None, choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--dp", default="peer", choices=["peer", "nccl"],
+                    help="N>1: in-kernel NVLink peer-memory reduction (default) or torch.distributed NCCL all-reduce")
     args = ap.parse_args()
     name = args.config or ("C2" if args.gpus == 1 else "C4")
     cfgd = dict(CONFIGS[name])
@@ -188,8 +190,24 @@ def main():
     ht = [b[2].pin_memory() for b in batches]
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    dp_mode = "none"
+    if world > 1:
+        dp_mode = "nccl"
+        if args.dp == "peer":
+            try:
+                e.enable_peer_dp()
+                dp_mode = "peer"
+            except Exception as ex:      # symmetric memory unavailable on this box: fall back to the NCCL path, and say so
+                sys.stderr.write("peer data-parallel path unavailable (%s); using NCCL all-reduce\n" % (ex,))
+        flag = torch.tensor([1 if dp_mode == "peer" else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag) == 0:
+            dp_mode = "nccl"
+
     def step(i):
-        if world > 1:
+        if dp_mode == "peer":
+            e.train_step_peer(xs[i % nb], desc, ts[i % nb])
+        elif dp_mode == "nccl":
             e.train_step_dp(xs[i % nb], desc, ts[i % nb])
         else:
             e.train_step(xs[i % nb], desc, ts[i % nb])
@@ -298,6 +316,9 @@ def main():
         "config": {"workload": WORKLOAD[name], "batch_per_gpu": B, "global_batch": B * world, "exchange_steps": steps_per_iter,
                    "sampling": "on-device Philox4x32-10 (parity tests inject the reference's float64 uniforms instead)",
                    "parallelism": "dp%d" % world,
+                   "dp_reduction": {"peer": "in-kernel sums over NVLink peer memory (statistics in k_lossgrad, gradient in "
+                                            "k_peer_allreduce_norm); no collective call", "nccl": "torch.distributed NCCL all-reduce "
+                                            "(statistics + flat gradient)", "none": "single GPU"}[dp_mode],
                    "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA events)" if flush is not None
                    else "not flushed (working set ~25 MB stays L2 resident)"},
         "value_l2_warm": world * steps_per_iter * K / (warm_ms * 1e-3), "ms_per_step_l2_warm": warm_ms / K,

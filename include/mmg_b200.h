@@ -256,6 +256,33 @@ int mmg_train_step_staged(const mmg_config* cfg, float* d_params, float* d_grads
                           int64_t step, const mmg_inputs* in, void* d_workspace, float* h_losses, void* stream,
                           void* ev_ready, void* ev_free);
 
+/* ---- data-parallel iteration over NVLink peer memory ----------------------------------------------------------------
+ * New capability (the reference is single-process).  Each rank owns one SYMMETRIC buffer (peer-mapped on every other
+ * rank, e.g. torch.distributed._symmetric_memory) holding, in this order:
+ *   send   : float[param_layout.total]      this rank's local gradient (split-K reduced), read by every peer
+ *   stats  : double[workspace.stats_count]  this rank's batch statistics, read by every peer
+ *   flags  : uint64[2][MMG_MAX_PEERS]       arrival counters written REMOTELY by the peers (row 0: statistics published,
+ *                                           row 1: gradient published); value = training step, monotonic
+ * No collective library call and no extra launch sits on the path: the producing kernels publish with a system-scope
+ * fence + remote flag store, the consuming kernels spin on their LOCAL flag row and then read the peers' buffers
+ * directly (rank order, so every rank computes bit-identical sums).  Waits are bounded; a timeout sets *d_error. */
+#define MMG_MAX_PEERS 8
+typedef struct mmg_peers {
+    int32_t world, rank;
+    float* d_send[MMG_MAX_PEERS];
+    double* d_stats[MMG_MAX_PEERS];
+    unsigned long long* d_flags[MMG_MAX_PEERS];
+    int32_t* d_error;      /* local device int, set non-zero when a peer wait timed out */
+} mmg_peers;
+/* Bytes of the symmetric buffer and the offsets of its three sections. */
+int mmg_peer_buffer_layout(const mmg_config* cfg, int64_t* total_bytes, int64_t* send_off, int64_t* stats_off,
+                           int64_t* flags_off);
+/* One training iteration on this rank's batch shard (cfg->batch rows of a global batch of cfg->batch_global rows):
+ * mmg_train_step with the statistics and the gradient summed across `peers` in-kernel.  `d_grads` (local, not
+ * symmetric) receives the global gradient; `step` must be identical on all ranks and increase by one per call. */
+int mmg_train_step_peer(const mmg_config* cfg, float* d_params, float* d_grads, float* d_state1, float* d_state2,
+                        int64_t step, const mmg_inputs* in, void* d_workspace, const mmg_peers* peers, void* stream);
+
 /* Number of kernels the last call of each entry point enqueued (for launch accounting). */
 int mmg_launch_count(void);
 void mmg_launch_count_reset(void);

@@ -66,6 +66,14 @@ class Inputs(C.Structure):
                 ("d_h0", C.c_void_p), ("top_k", C.c_int32), ("train", C.c_int32)]
 
 
+MMG_MAX_PEERS = 8
+
+
+class Peers(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("d_send", C.c_void_p * MMG_MAX_PEERS),
+                ("d_stats", C.c_void_p * MMG_MAX_PEERS), ("d_flags", C.c_void_p * MMG_MAX_PEERS), ("d_error", C.c_void_p)]
+
+
 class MmgError(RuntimeError):
     pass
 
@@ -75,7 +83,7 @@ class Library(object):
 
     SYMBOLS = ("mmg_abi_version", "mmg_last_error", "mmg_device_count", "mmg_param_layout_get",
                "mmg_workspace_layout_get", "mmg_workspace_init", "mmg_exchange_forward", "mmg_loss", "mmg_backward",
-               "mmg_grad_norm", "mmg_clip_update", "mmg_train_step", "mmg_train_step_host", "mmg_host_prefetch", "mmg_train_step_staged", "mmg_launch_count",
+               "mmg_grad_norm", "mmg_clip_update", "mmg_train_step", "mmg_train_step_host", "mmg_host_prefetch", "mmg_train_step_staged", "mmg_peer_buffer_layout", "mmg_train_step_peer", "mmg_launch_count",
                "mmg_launch_count_reset")
 
     def __init__(self, path):
@@ -102,6 +110,9 @@ class Library(object):
         d.mmg_train_step_host.argtypes = [cfgp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, inp, vp, vp, vp]
         d.mmg_host_prefetch.argtypes = [cfgp, vp, vp, vp, vp, vp, vp, vp]
         d.mmg_train_step_staged.argtypes = [cfgp, vp, vp, vp, vp, i64, inp, vp, vp, vp, vp, vp]
+        i64p = C.POINTER(C.c_int64)
+        d.mmg_peer_buffer_layout.argtypes = [cfgp, i64p, i64p, i64p, i64p]
+        d.mmg_train_step_peer.argtypes = [cfgp, vp, vp, vp, vp, i64, inp, vp, C.POINTER(Peers), vp]
         for name in self.SYMBOLS:
             fn = getattr(d, name)
             if name not in ("mmg_last_error", "mmg_launch_count_reset"):

@@ -443,6 +443,23 @@ static void build_wgrad_table(const Dims& d, const mmg_param_layout& L, const Pa
     b.finish();
 }
 
+static PeerView no_peers() {
+    PeerView pv;
+    memset(&pv, 0, sizeof(pv));
+    return pv;
+}
+static int resolve_peers(const mmg_peers* p, int64_t step, PeerView* pv) {
+    if (!p || p->world < 2 || p->world > MMG_MAX_PEERS || p->rank < 0 || p->rank >= p->world || !p->d_error)
+        return fail(MMG_ERR_INVALID, "bad mmg_peers");
+    memset(pv, 0, sizeof(*pv));
+    pv->world = p->world; pv->rank = p->rank; pv->error = p->d_error; pv->iter = (unsigned long long)step;
+    for (int r = 0; r < p->world; ++r) {
+        if (!p->d_send[r] || !p->d_stats[r] || !p->d_flags[r]) return fail(MMG_ERR_INVALID, "null peer pointer (rank %d)", r);
+        pv->send[r] = p->d_send[r]; pv->stats[r] = p->d_stats[r]; pv->flags[r] = p->d_flags[r];
+    }
+    return MMG_OK;
+}
+
 static int upd_ctas(int64_t total) {
     int64_t n = cdiv64(total / 4, kUpdThreads);
     if (n > kNormCtasMax) n = kNormCtasMax;
@@ -578,8 +595,8 @@ int mmg_exchange_forward(const mmg_config* cfg, const float* d_params, const mmg
     return exchange_forward_impl(cfg, d_params, in, d_workspace, stream, true);
 }
 
-int mmg_loss(const mmg_config* cfg, const float* d_params, const mmg_inputs* in, void* d_workspace, int phase,
-             void* stream) {
+static int loss_impl(const mmg_config* cfg, const float* d_params, const mmg_inputs* in, void* d_workspace, int phase,
+                     void* stream, const PeerView& pv) {
     int rc = validate(cfg);
     if (rc) return rc;
     if (!d_params || !in || !d_workspace || !in->d_target) return fail(MMG_ERR_INVALID, "null pointer argument");
@@ -593,21 +610,26 @@ int mmg_loss(const mmg_config* cfg, const float* d_params, const mmg_inputs* in,
     const ExchangeInputs ei = resolve_inputs(in);
     cudaStream_t st = (cudaStream_t)stream;
     if (phase <= 0) {
-        MMG_LAUNCH(k_stats, 1, kStatsThreads, 0, st, d, P, W, ei);
+        MMG_LAUNCH(k_stats, 1, kStatsThreads, 0, st, d, P, W, ei, pv);
         if ((rc = check_cuda("k_stats"))) return rc;
     }
     if (phase != 0) {
         int ctas = cdiv(d.R, kLossThreads / 32);
         if (ctas > 4 * 148) ctas = 4 * 148;
-        const int smem = 3 * d.T * (int)sizeof(LossCoef) + 16;
-        MMG_LAUNCH(k_lossgrad, ctas, kLossThreads, smem, st, d, *cfg, W);
+        const int smem = 3 * d.T * (int)sizeof(LossCoef) + 16 + (pv.world > 1 ? stats_count(d) * 8 + 16 : 0);
+        MMG_LAUNCH(k_lossgrad, ctas, kLossThreads, smem, st, d, *cfg, W, pv);
         if ((rc = check_cuda("k_lossgrad"))) return rc;
     }
     return MMG_OK;
 }
 
-int mmg_backward(const mmg_config* cfg, const float* d_params, const mmg_inputs* in, void* d_workspace, float* d_grads,
-                 void* stream) {
+int mmg_loss(const mmg_config* cfg, const float* d_params, const mmg_inputs* in, void* d_workspace, int phase,
+             void* stream) {
+    return loss_impl(cfg, d_params, in, d_workspace, phase, stream, no_peers());
+}
+
+static int backward_impl(const mmg_config* cfg, const float* d_params, const mmg_inputs* in, void* d_workspace,
+                         float* d_grads, void* stream, const PeerView& pv) {
     int rc = validate(cfg);
     if (rc) return rc;
     if (!d_params || !in || !d_workspace || !d_grads) return fail(MMG_ERR_INVALID, "null pointer argument");
@@ -639,8 +661,13 @@ int mmg_backward(const mmg_config* cfg, const float* d_params, const mmg_inputs*
     if ((rc = check_cuda("k_wgrad"))) return rc;
     const SegInfo seg = seg_info(L, d);
     MMG_LAUNCH(k_reduce_norm, upd_ctas(L.total), kUpdThreads, 0, st, seg, stab, W.slabs, (long long)L.total, d_grads, 1.0f,
-               1, W.norm_part);
+               1, W.norm_part, pv, W.tickets + 2);
     return check_cuda("k_reduce_norm");
+}
+
+int mmg_backward(const mmg_config* cfg, const float* d_params, const mmg_inputs* in, void* d_workspace, float* d_grads,
+                 void* stream) {
+    return backward_impl(cfg, d_params, in, d_workspace, d_grads, stream, no_peers());
 }
 
 int mmg_grad_norm(const mmg_config* cfg, float* d_grads, void* d_workspace, void* stream) {
@@ -657,7 +684,7 @@ int mmg_grad_norm(const mmg_config* cfg, float* d_grads, void* d_workspace, void
     SplitTable stab;
     memset(&stab, 0, sizeof(stab));
     MMG_LAUNCH(k_reduce_norm, upd_ctas(L.total), kUpdThreads, 0, (cudaStream_t)stream, seg, stab, W.slabs, (long long)L.total,
-               d_grads, 1.0f, 0, W.norm_part);
+               d_grads, 1.0f, 0, W.norm_part, no_peers(), W.tickets + 2);
     return check_cuda("k_reduce_norm");
 }
 
@@ -689,8 +716,8 @@ int mmg_train_step(const mmg_config* cfg, float* d_params, float* d_grads, float
     int rc;
     if (!in || !in->train) return fail(MMG_ERR_INVALID, "mmg_train_step needs in->train = 1");
     if ((rc = exchange_forward_impl(cfg, d_params, in, d_workspace, stream, false))) return rc;
-    if ((rc = mmg_loss(cfg, d_params, in, d_workspace, -1, stream))) return rc;
-    if ((rc = mmg_backward(cfg, d_params, in, d_workspace, d_grads, stream))) return rc;
+    if ((rc = loss_impl(cfg, d_params, in, d_workspace, -1, stream, no_peers()))) return rc;
+    if ((rc = backward_impl(cfg, d_params, in, d_workspace, d_grads, stream, no_peers()))) return rc;
     return mmg_clip_update(cfg, d_params, d_grads, d_state1, d_state2, step, 1.0f, d_workspace, stream);
 }
 
@@ -727,6 +754,47 @@ int mmg_train_step_host(const mmg_config* cfg, float* d_params, float* d_grads, 
     (void)d_params; (void)d_grads; (void)d_state1; (void)d_state2; (void)step; (void)h_desc; (void)d_desc_stage; (void)d_workspace; (void)stream;
     return fail(MMG_ERR_UNSUPPORTED, "host-buffer entry point is not part of the emulation build");
 #endif
+}
+
+static int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
+
+int mmg_peer_buffer_layout(const mmg_config* cfg, int64_t* total_bytes, int64_t* send_off, int64_t* stats_off,
+                           int64_t* flags_off) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!total_bytes || !send_off || !stats_off || !flags_off) return fail(MMG_ERR_INVALID, "null output");
+    const Dims d = make_dims(*cfg);
+    mmg_param_layout L;
+    param_layout(d, &L);
+    *send_off = 0;
+    *stats_off = align256(L.total * 4);
+    *flags_off = *stats_off + align256((int64_t)stats_count(d) * 8);
+    *total_bytes = *flags_off + align256(2 * MMG_MAX_PEERS * 8);
+    return MMG_OK;
+}
+
+int mmg_train_step_peer(const mmg_config* cfg, float* d_params, float* d_grads, float* d_state1, float* d_state2,
+                        int64_t step, const mmg_inputs* in, void* d_workspace, const mmg_peers* peers, void* stream) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!in || !in->train) return fail(MMG_ERR_INVALID, "mmg_train_step_peer needs in->train = 1");
+    if (step < 1) return fail(MMG_ERR_INVALID, "step must start at 1 and increase by one per call (it is the flag value)");
+    PeerView pv;
+    if ((rc = resolve_peers(peers, step, &pv))) return rc;
+    if ((rc = exchange_forward_impl(cfg, d_params, in, d_workspace, stream, false))) return rc;
+    if ((rc = loss_impl(cfg, d_params, in, d_workspace, -1, stream, pv))) return rc;
+    // local gradient -> this rank's symmetric send buffer, then the in-kernel sum over all peers -> d_grads
+    if ((rc = backward_impl(cfg, d_params, in, d_workspace, pv.send[pv.rank], stream, pv))) return rc;
+    const Dims d = make_dims(*cfg);
+    mmg_param_layout L;
+    param_layout(d, &L);
+    Ws w;
+    ws_layout(d, &w);
+    const WsPtrs W = resolve(w, d_workspace);
+    const SegInfo seg = seg_info(L, d);
+    MMG_LAUNCH(k_peer_allreduce_norm, upd_ctas(L.total), kUpdThreads, 0, (cudaStream_t)stream, seg, pv, d_grads, W.norm_part);
+    if ((rc = check_cuda("k_peer_allreduce_norm"))) return rc;
+    return mmg_clip_update(cfg, d_params, d_grads, d_state1, d_state2, step, 1.0f, d_workspace, stream);
 }
 
 int mmg_host_prefetch(const mmg_config* cfg, const float* h_x, const int64_t* h_target, float* d_x_stage,

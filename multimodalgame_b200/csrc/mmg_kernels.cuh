@@ -26,6 +26,15 @@ struct WsPtrs {               // resolved workspace arrays (device pointers)
     int hx_split, wgrad_split, ntb;
 };
 
+struct PeerView {             // mmg_peers resolved for the kernels; world <= 1: single-rank run, nothing is touched
+    int world, rank;
+    float* send[MMG_MAX_PEERS];
+    double* stats[MMG_MAX_PEERS];
+    unsigned long long* flags[MMG_MAX_PEERS];
+    int* error;
+    unsigned long long iter;
+};
+
 struct ExchangeInputs {       // device pointers of one exchange (mmg_inputs resolved)
     const float* x;
     const float* desc;

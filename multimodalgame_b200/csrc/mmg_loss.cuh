@@ -99,7 +99,7 @@ MMG_DEVICE unsigned char mask_at(const Dims& d, const WsPtrs& W, int slot, int b
 }
 
 MMG_GLOBAL void __launch_bounds__(kStatsThreads)
-k_stats(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in) {
+k_stats(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, PeerView pv) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kStatsThreads / 32;
     // ---- finalize baseline scores --------------------------------------------------------------------------
     const float b2s = ldg(P.p[MMG_P_BS_L2_B]), b2r = ldg(P.p[MMG_P_BR_L2_B]);
@@ -198,6 +198,14 @@ k_stats(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in) {
             }
         }
     }
+    if (pv.world > 1) {
+        // publish this rank's statistics: copy into the symmetric slot, then raise flag row 0 on every peer
+        MMG_SYNCTHREADS();
+        for (int i = tid; i < stats_count(d); i += kStatsThreads) pv.stats[pv.rank][i] = W.stats[i];
+        fence_system();
+        MMG_SYNCTHREADS();
+        if (tid < pv.world) peer_signal(pv.flags[tid] + pv.rank, pv.iter);
+    }
 }
 
 // Per (kind, t) coefficients derived from the (all-reduced) statistics.
@@ -243,12 +251,26 @@ MMG_DEVICE float binary_grad(float p, float f, float wcA, float cE) {
 }
 
 MMG_GLOBAL void __launch_bounds__(kLossThreads)
-k_lossgrad(Dims d, mmg_config cfg, WsPtrs W) {
+k_lossgrad(Dims d, mmg_config cfg, WsPtrs W, PeerView pv) {
     MMG_DYN_SMEM(smem_raw);
     LossCoef* coef = reinterpret_cast<LossCoef*>(smem_raw);          // [3][T]
     float* bas_scale = reinterpret_cast<float*>(coef + 3 * d.T);      // [2]: 1 / denominator of the baseline MSE
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double* st = W.stats;
+    if (pv.world > 1) {
+        // global batch statistics = sum over ranks, read straight from the peers' symmetric slots (rank order)
+        double* st_s = reinterpret_cast<double*>(bas_scale + 4);
+        if (tid < pv.world && !peer_wait(pv.flags[pv.rank] + tid, pv.iter)) *pv.error = 1;
+        MMG_SYNCTHREADS();
+        for (int i = tid; i < stats_count(d); i += kLossThreads) {
+            double v = 0.0;
+            for (int r = 0; r < pv.world; ++r) v += peer_load_d(pv.stats[r] + i);
+            st_s[i] = v;
+            if (blockIdx.x == 0) W.stats[i] = v;      // later kernels (K_update) read the global numbers from here
+        }
+        MMG_SYNCTHREADS();
+        st = st_s;
+    }
     for (int i = tid; i < 3 * d.T; i += kLossThreads) {
         double n;
         loss_coefs(d, cfg, st, i / d.T, i % d.T, coef[i], &n);

@@ -72,6 +72,22 @@ MMG_DEVICE void flag_wait(const unsigned* counter, unsigned target) {
     __threadfence();
 }
 
+// ---- cross-GPU flags over peer-mapped memory (NVLink) ----------------------------------------------------------------
+MMG_DEVICE void peer_signal(unsigned long long* remote_flag, unsigned long long value) {
+    __threadfence_system();                                   // this rank's prior writes are visible system-wide first
+    *reinterpret_cast<volatile unsigned long long*>(remote_flag) = value;
+}
+MMG_DEVICE bool peer_wait(const unsigned long long* local_flag, unsigned long long target) {
+    for (int spin = 0; spin < (1 << 23); ++spin) {            // bounded: a missing peer must not hang the GPU
+        if (*reinterpret_cast<const volatile unsigned long long*>(local_flag) >= target) { __threadfence_system(); return true; }
+        __nanosleep(200);
+    }
+    return false;
+}
+MMG_DEVICE void fence_system() { __threadfence_system(); }
+MMG_DEVICE float4 peer_load4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }   // L1 bypass
+MMG_DEVICE double peer_load_d(const double* p) { return __ldcg(p); }
+
 // ---- mbarrier + TMA bulk copy (cp.async.bulk, SASS UBLKCP) ------------------------------------------
 MMG_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -232,6 +248,11 @@ MMG_DEVICE void flag_arrive(unsigned* counter) { __atomic_fetch_add(counter, 1u,
 MMG_DEVICE void flag_wait(const unsigned* counter, unsigned target) {   // blocks run in index order: already satisfied
     while (__atomic_load_n(counter, __ATOMIC_SEQ_CST) < target) {}
 }
+MMG_DEVICE void peer_signal(unsigned long long* f, unsigned long long v) { __atomic_store_n(f, v, __ATOMIC_SEQ_CST); }
+MMG_DEVICE bool peer_wait(const unsigned long long* f, unsigned long long target) { return __atomic_load_n(f, __ATOMIC_SEQ_CST) >= target; }
+MMG_DEVICE void fence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+MMG_DEVICE float4 peer_load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+MMG_DEVICE double peer_load_d(const double* p) { return *p; }
 MMG_DEVICE void mbar_init(uint64_t* bar, int) { *bar = 0; }
 MMG_DEVICE void mbar_fence_init() {}
 MMG_DEVICE void mbar_wait(uint64_t*, uint32_t) {}

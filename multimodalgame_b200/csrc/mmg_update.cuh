@@ -156,7 +156,7 @@ MMG_DEVICE int tensor_of(const SplitTable& st, long long i) {
 // do_reduce = 0: gradients are final already (after the data-parallel all-reduce), only the norms are computed.
 MMG_GLOBAL void __launch_bounds__(kUpdThreads)
 k_reduce_norm(SegInfo seg, SplitTable st, const float* arena, long long slab_stride, float* grads, float scale,
-              int do_reduce, float* norm_part) {
+              int do_reduce, float* norm_part, PeerView pv, unsigned* ticket) {
     MMG_SHARED float red[4][kUpdThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long total = seg.begin[4];
@@ -179,6 +179,52 @@ k_reduce_norm(SegInfo seg, SplitTable st, const float* arena, long long slab_str
             g.x *= scale; g.y *= scale; g.z *= scale; g.w *= scale;
             *reinterpret_cast<float4*>(grads + i) = g;
         }
+        ss[sg] = fmaf(g.x, g.x, ss[sg]); ss[sg] = fmaf(g.y, g.y, ss[sg]);
+        ss[sg] = fmaf(g.z, g.z, ss[sg]); ss[sg] = fmaf(g.w, g.w, ss[sg]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float v = warp_sum(ss[k]);
+        if (lane == 0) red[k][warp] = v;
+    }
+    MMG_SYNCTHREADS();
+    if (tid < 4) {
+        float v = 0.f;
+        for (int w = 0; w < kUpdThreads / 32; ++w) v += red[tid][w];
+        norm_part[tid * gridDim.x + blockIdx.x] = v;
+    }
+    if (pv.world > 1) {
+        // `grads` is this rank's symmetric send buffer: once every CTA has written its part, raise flag row 1 on all peers
+        MMG_SHARED int s_last;
+        fence_system();
+        MMG_SYNCTHREADS();
+        if (tid == 0) s_last = (ticket_take(ticket) == gridDim.x - 1) ? 1 : 0;
+        MMG_SYNCTHREADS();
+        if (s_last) {
+            if (tid < pv.world) peer_signal(pv.flags[tid] + MMG_MAX_PEERS + pv.rank, pv.iter);
+            if (tid == 0) *ticket = 0;
+        }
+    }
+}
+
+// Data-parallel gradient sum over NVLink peer memory, fused with the per-module sum of squares: every rank reads all
+// send buffers (one-shot, rank order => bit-identical results everywhere) and writes the global gradient locally.
+MMG_GLOBAL void __launch_bounds__(kUpdThreads)
+k_peer_allreduce_norm(SegInfo seg, PeerView pv, float* grads_out, float* norm_part) {
+    MMG_SHARED float red[4][kUpdThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < pv.world && !peer_wait(pv.flags[pv.rank] + MMG_MAX_PEERS + tid, pv.iter)) *pv.error = 2;
+    MMG_SYNCTHREADS();
+    const long long total = seg.begin[4];
+    float ss[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long i = 4 * ((long long)blockIdx.x * kUpdThreads + tid); i < total; i += 4ll * gridDim.x * kUpdThreads) {
+        const int sg = seg_of(seg.begin, i);
+        float4 g = peer_load4(pv.send[0] + i);
+        for (int r = 1; r < pv.world; ++r) {
+            const float4 a = peer_load4(pv.send[r] + i);
+            g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
+        }
+        *reinterpret_cast<float4*>(grads_out + i) = g;
         ss[sg] = fmaf(g.x, g.x, ss[sg]); ss[sg] = fmaf(g.y, g.y, ss[sg]);
         ss[sg] = fmaf(g.z, g.z, ss[sg]); ss[sg] = fmaf(g.w, g.w, ss[sg]);
     }

@@ -209,6 +209,48 @@ class GameEngine(object):
                       C.c_void_p(hp["free"][slot].cuda_event))
         hp["used"][slot] = True
 
+    # ---- data parallel over NVLink peer memory (no collective call, no extra launch) ---------------------------------
+    def enable_peer_dp(self, group=None):
+        """Allocate this rank's symmetric exchange buffer (torch symmetric memory: peer-mapped on every rank of `group`)
+        and resolve the peers' pointers for `train_step_peer`.  Collective: every rank of the group must call it."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        tot, so, sto, fo = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        self.lib.call("mmg_peer_buffer_layout", C.byref(self.cfg), C.byref(tot), C.byref(so), C.byref(sto), C.byref(fo))
+        buf = symm_mem.empty(int(tot.value), dtype=torch.uint8, device=self.device)
+        buf.zero_()
+        hdl = symm_mem.rendezvous(buf, group)
+        world, rank = int(hdl.world_size), int(hdl.rank)
+        if world > capi.MMG_MAX_PEERS:
+            raise capi.MmgError("peer data parallelism supports up to %d ranks" % capi.MMG_MAX_PEERS)
+        p = capi.Peers()
+        p.world, p.rank = world, rank
+        for r in range(world):
+            base = int(hdl.buffer_ptrs[r])
+            p.d_send[r], p.d_stats[r], p.d_flags[r] = base + so.value, base + sto.value, base + fo.value
+        self._peer_err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        p.d_error = self._peer_err.data_ptr()
+        self._peers, self._peer_buf, self._peer_hdl = p, buf, hdl
+        torch.cuda.synchronize(self.device)
+        hdl.barrier()                      # every rank's buffer is zeroed before anyone's first flag lands
+        torch.cuda.synchronize(self.device)
+        return world, rank
+
+    def train_step_peer(self, x, desc, target, uniforms=None, top_k=6):
+        """Data-parallel iteration: this rank's batch shard; batch statistics and gradients are summed across the ranks
+        inside the kernels over NVLink peer memory (mmg_train_step_peer)."""
+        self._inp = self._inputs(x, desc, target, True, uniforms, None, None, top_k)
+        self.step += 1
+        s2 = None if self.state2 is None else self.state2.data_ptr()
+        self.lib.call("mmg_train_step_peer", C.byref(self.cfg), self.params.data_ptr(), self.grads.data_ptr(),
+                      self.state1.data_ptr(), s2, C.c_int64(self.step), C.byref(self._inp), self.workspace.data_ptr(),
+                      C.byref(self._peers), self._stream())
+
+    def peer_error(self):
+        """Non-zero when a peer wait timed out (synchronises)."""
+        return int(self._peer_err.item())
+
     def train_step_dp(self, x, desc, target, group=None, uniforms=None, top_k=6):
         """Data-parallel iteration: this rank's batch shard; batch statistics and gradients are all-reduced
         (SURVEY.md §8e).  Two collectives per iteration: a few hundred doubles, then the flat gradient buffer."""
