@@ -13,8 +13,8 @@ Everything the conversation computes runs in libmmg_b200.so (hand-written sm_100
 include/mmg_b200.h).  Two ways in:
 
   * `exchange()` — drop-in.  Returns the reference's tuple of lists; in train mode the probabilities / scores /
-    baseline values carry autograd history through ONE custom Function whose backward is the fused backward kernel
-    sequence, so `loss.backward()` + `torch.optim` work exactly as in the reference's loop.
+    baseline values carry autograd history through one custom Function node per module whose backward is the fused
+    backward kernel sequence, so `loss.backward()` + `torch.optim` work exactly as in the reference's loop.
   * `train_step()` — the whole iteration (conversation, the five losses, backward, 4x clip + optimizer step) fused on
     the device with no host round trip.  This is what `bench.py` measures.
 
@@ -342,34 +342,36 @@ def build_mask(region_str, size):
     return mask
 
 
-class _ExchangeFn(torch.autograd.Function):
-    """Autograd bridge: forward = fused conversation, backward = fused backward kernels for whatever upstream
-    gradients the caller's losses produce (the reference's four `.backward()` calls each trigger one pass)."""
+_AGENT_OUTPUTS = {"receiver": ("rec_probs", "stop_prob", "y"), "sender": ("sen_probs",), "baseline_rec": ("br",),
+                  "baseline_sen": ("bs",)}
+
+
+class _AgentFn(torch.autograd.Function):
+    """Autograd bridge, one node per module: the outputs of the (already executed) fused conversation that carry
+    gradient to THIS module's parameters.  The reference's four losses are disjoint graphs (every cross-agent tensor is
+    cut with `.data`, model.py:807-843), so each of its `loss.backward()` calls (model.py:1309,1316,1322,1328) reaches
+    exactly one of these nodes and runs the fused backward kernels for that module."""
 
     @staticmethod
-    def forward(ctx, binding, x, desc, target, uniforms, *params):
-        e = binding.engine
-        e.forward(x, desc, target, train=True, uniforms=uniforms)
-        o = e.outputs()
-        ctx.binding = binding
-        ctx.inp = e._inp
-        outs = (o["sen_probs"].clone(), o["rec_probs"].clone(), o["stop_prob"].clone(), o["y"].clone(), o["bs"].clone(),
-                o["br"].clone())
-        return outs
+    def forward(ctx, binding, agent, inp, *params):
+        o = binding.engine.outputs()
+        ctx.binding, ctx.agent, ctx.inp = binding, agent, inp
+        return tuple(o[name].clone() for name in _AGENT_OUTPUTS[agent])
 
     @staticmethod
-    def backward(ctx, g_sen, g_rec, g_stop, g_y, g_bs, g_br):
+    def backward(ctx, *gouts):
         b = ctx.binding
         e = b.engine
         d = e.dims
         T, B, M, D = d["T"], d["B"], d["M"], d["D"]
-        z = lambda g, shape: torch.zeros(shape, device=e.device) if g is None else g
-        e.ws("g_sen_probs", (T, B, M)).copy_(z(g_sen, (T, B, M)))
-        e.ws("g_rec_probs", (T, B, M)).copy_(z(g_rec, (T, B, M)))
-        e.ws("g_stop_prob", (T, B)).copy_(z(g_stop, (T, B, 1)).reshape(T, B))
-        e.ws("g_bs", (T, B)).copy_(z(g_bs, (T, B, 1)).reshape(T, B))
-        e.ws("g_br", (T, B)).copy_(z(g_br, (T, B, 1)).reshape(T, B))
-        gy = z(g_y, (T, B, D))
+        g = dict(zip(_AGENT_OUTPUTS[ctx.agent], gouts))
+        z = lambda name, shape: torch.zeros(shape, device=e.device) if g.get(name) is None else g[name]
+        e.ws("g_sen_probs", (T, B, M)).copy_(z("sen_probs", (T, B, M)))
+        e.ws("g_rec_probs", (T, B, M)).copy_(z("rec_probs", (T, B, M)))
+        e.ws("g_stop_prob", (T, B)).copy_(z("stop_prob", (T, B, 1)).reshape(T, B))
+        e.ws("g_bs", (T, B)).copy_(z("bs", (T, B, 1)).reshape(T, B))
+        e.ws("g_br", (T, B)).copy_(z("br", (T, B, 1)).reshape(T, B))
+        gy = z("y", (T, B, D))
         nz = (gy != 0).any(dim=2)                                  # (T, B): steps whose scores received gradient
         if bool((nz.sum(0) > 1).any()):
             _unsupported("gradients into the class scores of more than one step per example")
@@ -379,10 +381,8 @@ class _ExchangeFn(torch.autograd.Function):
         e._inp = ctx.inp
         e.backward()
         gv = b.gviews
-        grads = []
-        for agent, key in capi.PARAM_NAMES:
-            grads.append(gv[agent][key].clone())
-        return (None, None, None, None, None) + tuple(grads)
+        grads = [gv[ctx.agent][key].clone() for a, key in capi.PARAM_NAMES if a == ctx.agent]
+        return (None, None, None) + tuple(grads)
 
 
 def _device_of(module):
@@ -416,12 +416,16 @@ def exchange(sender, receiver, baseline_sen, baseline_rec, exchange_args):
     mask = build_mask(corrupt_region, sender.w_dim).to(dev) if corrupt else None
     binary = bool(sender.use_binary)
     if train:
-        params = []
-        for agent, key in capi.PARAM_NAMES:
-            mod = binding.mods[agent]
-            params.append(dict(mod.named_parameters())[key])
-        sen_p, rec_p, stop_p, y_all, bs_all, br_all = _ExchangeFn.apply(
-            binding, data.detach(), desc.detach(), target, exchange_args.get("uniforms"), *params)
+        with torch.no_grad():
+            e.forward(data.detach(), desc.detach(), target, train=True, uniforms=exchange_args.get("uniforms"))
+        outs = {}
+        for agent in capi.SEGMENTS:
+            named = dict(binding.mods[agent].named_parameters())
+            params = [named[key] for a, key in capi.PARAM_NAMES if a == agent]
+            res = _AgentFn.apply(binding, agent, e._inp, *params)
+            outs.update(zip(_AGENT_OUTPUTS[agent], res))
+        sen_p, rec_p, stop_p, y_all, bs_all, br_all = (outs["sen_probs"], outs["rec_probs"], outs["stop_prob"], outs["y"],
+                                                       outs["bs"], outs["br"])
         o = e.outputs()
     else:
         with torch.no_grad():

@@ -104,9 +104,9 @@ def reference_update_block(mods, cfg, x, desc, target, uniforms):
         loss_bas_sen = M.multistep_loss_bas(bs, logs, bas_sen_masks)
         loss_rec = nll_loss + loss_binary_rec + (loss_binary_s if loss_binary_s is not None else 0)
         loss_sen = loss_binary_sen
-        loss_rec.backward(retain_graph=True)                                   # the four graphs meet in one fused node
-        loss_sen.backward(retain_graph=True)
-        loss_bas_rec.backward(retain_graph=True)
+        loss_rec.backward()                                                    # model.py:1309, 1316, 1322, 1328
+        loss_sen.backward()
+        loss_bas_rec.backward()
         loss_bas_sen.backward()
         out.update(loss_rec=loss_rec, loss_sen=loss_sen, loss_bas_rec=loss_bas_rec, loss_bas_sen=loss_bas_sen)
     else:
