@@ -163,7 +163,7 @@ static void ws_layout(const Dims& d, Ws* w) {
     w->slabs = take(c, (int64_t)(kWgradSplitMax - 1) * L.total * f);
     w->norm_part = take(c, 4 * kNormCtasMax * f);
     w->loss_part = take(c, (int64_t)kLossCtasMax * 8 * 8);
-    w->tickets = take(c, 4 * 4);
+    w->tickets = take(c, 8 * 4);
     w->opt_counters = take(c, 4 * 8);
     p.total_bytes = c;
 }
@@ -306,16 +306,24 @@ static int launch_bwd(const Dims& d, const WsPtrs& W, const Plan& pl, cudaStream
 }
 
 struct FastFwdArgs { const float* b_img; const float* bs_w1; const float* bs_b1; };
-template <int BT, int M, bool SS>
-static int launch_fwd_fast_one(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const FastFwdArgs& fa, const Plan& pl,
-                               cudaStream_t st) {
-    auto kern = k_exchange_fwd_fast<BT, M, SS>;
+template <int BT, int M, bool SS, bool PERF>
+static int launch_fwd_fast_mode(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const FastFwdArgs& fa, const Plan& pl,
+                                cudaStream_t st) {
+    auto kern = k_exchange_fwd_fast<BT, M, SS, PERF>;
     int rc = set_smem(kern, pl.fwd_smem_bytes);
     if (rc) return rc;
     const int n_conv = cdiv(d.B, BT);
     const int n_side = in.train ? cdiv(d.B, kTile) * cdiv(d.Hb, kTile) : 0;     // baseline pre-activation tiles
     MMG_LAUNCH(kern, n_conv + n_side, kFastThreads, pl.fwd_smem_bytes, st, d, W, in, fa.b_img, 0, fa.bs_w1, fa.bs_b1, n_conv);
     return check_cuda("k_exchange_fwd_fast");
+}
+template <int BT, int M, bool SS>
+static int launch_fwd_fast_one(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const FastFwdArgs& fa, const Plan& pl,
+                               cudaStream_t st) {
+    const bool perf = in.train && d.use_binary && in.u_sen == nullptr && in.corrupt_mask == nullptr && !d.ignore_receiver &&
+                      d.B % BT == 0;
+    return perf ? launch_fwd_fast_mode<BT, M, SS, true>(d, W, in, fa, pl, st)
+                : launch_fwd_fast_mode<BT, M, SS, false>(d, W, in, fa, pl, st);
 }
 template <int M, bool SS>
 static int launch_fwd_fast_bt(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const FastFwdArgs& fa, const Plan& pl,
@@ -629,7 +637,7 @@ int mmg_loss(const mmg_config* cfg, const float* d_params, const mmg_inputs* in,
 }
 
 static int backward_impl(const mmg_config* cfg, const float* d_params, const mmg_inputs* in, void* d_workspace,
-                         float* d_grads, void* stream, const PeerView& pv) {
+                         float* d_grads, void* stream, const PeerView& pv, SplitTable* stab_out = nullptr) {
     int rc = validate(cfg);
     if (rc) return rc;
     if (!d_params || !in || !d_workspace || !d_grads) return fail(MMG_ERR_INVALID, "null pointer argument");
@@ -659,6 +667,7 @@ static int backward_impl(const mmg_config* cfg, const float* d_params, const mmg
     MMG_LAUNCH(k_wgrad, tab.total_tiles, kGemmThreads, 0, st, d, tab, d_grads, W.slabs, P.p[MMG_P_SEN_CODE_W],
                P.p[MMG_P_SEN_CODE_BIAS], W.d_as);
     if ((rc = check_cuda("k_wgrad"))) return rc;
+    if (stab_out != nullptr) { *stab_out = stab; return MMG_OK; }     // the caller fuses the slab reduction with the update
     const SegInfo seg = seg_info(L, d);
     MMG_LAUNCH(k_reduce_norm, upd_ctas(L.total), kUpdThreads, 0, st, seg, stab, W.slabs, (long long)L.total, d_grads, 1.0f,
                1, W.norm_part, pv, W.tickets + 2);
@@ -717,6 +726,46 @@ int mmg_train_step(const mmg_config* cfg, float* d_params, float* d_grads, float
     if (!in || !in->train) return fail(MMG_ERR_INVALID, "mmg_train_step needs in->train = 1");
     if ((rc = exchange_forward_impl(cfg, d_params, in, d_workspace, stream, false))) return rc;
     if ((rc = loss_impl(cfg, d_params, in, d_workspace, -1, stream, no_peers()))) return rc;
+#ifndef MMG_CPU_EMU
+    {
+        // slab reduction + gradient norms + clip + optimizer in ONE kernel (software grid barrier): the grid is capped at
+        // the number of co-resident CTAs, queried once
+        static int max_ctas = -1;
+        if (max_ctas < 0) {
+            int dev = 0, sms = 0, per_sm = 0;
+            if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_reduce_update, kUpdThreads, 0) != cudaSuccess)
+                max_ctas = 0;
+            else
+                max_ctas = sms * (per_sm > 4 ? 4 : per_sm);
+            // measured on B200: the fusion saves a launch but no time (the kernels, not their boundaries, are the cost),
+            // so the two-kernel sequence stays the default; MMG_FUSED_UPDATE=1 opts in
+            const char* e = getenv("MMG_FUSED_UPDATE");
+            if (!(e && e[0] == '1')) max_ctas = 0;
+        }
+        if (max_ctas > 0) {
+            if (!d_params || !d_grads) return fail(MMG_ERR_INVALID, "null pointer argument");
+            if (cfg->optim_type != MMG_OPT_SGD && !d_state1) return fail(MMG_ERR_INVALID, "optimizer state required");
+            if (cfg->optim_type == MMG_OPT_ADAM && !d_state2) return fail(MMG_ERR_INVALID, "Adam needs d_state2");
+            SplitTable stab;
+            if ((rc = backward_impl(cfg, d_params, in, d_workspace, d_grads, stream, no_peers(), &stab))) return rc;
+            const Dims d = make_dims(*cfg);
+            mmg_param_layout L;
+            param_layout(d, &L);
+            Ws w;
+            ws_layout(d, &w);
+            const WsPtrs W = resolve(w, d_workspace);
+            const SegInfo seg = seg_info(L, d);
+            OptHyper hp;
+            hp.optim = cfg->optim_type; hp.lr = cfg->learning_rate; hp.max_norm = cfg->max_norm; hp.step = step;
+            int nc = upd_ctas(L.total);
+            if (nc > max_ctas) nc = max_ctas;
+            MMG_LAUNCH(k_reduce_update, nc, kUpdThreads, 0, (cudaStream_t)stream, seg, stab, W.slabs, (long long)L.total, hp,
+                       d_params, d_grads, d_state1, d_state2, W.norm_part, W.grad_norms, W.stats, W.opt_counters, W.tickets + 4);
+            return check_cuda("k_reduce_update");
+        }
+    }
+#endif
     if ((rc = backward_impl(cfg, d_params, in, d_workspace, d_grads, stream, no_peers()))) return rc;
     return mmg_clip_update(cfg, d_params, d_grads, d_state1, d_state2, step, 1.0f, d_workspace, stream);
 }

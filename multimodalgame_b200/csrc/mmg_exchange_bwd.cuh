@@ -50,7 +50,7 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas) {
         uint64_t* bar = reinterpret_cast<uint64_t*>(sm + o);
         if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
         MMG_SYNCTHREADS();
-        pdl_wait();
+        pdl_wait(); pdl_launch_dependents();
         if (tid == 0) tma_stage(sm, W.bwd_image, (uint32_t)im.sender_end * 4u, bar);
         for (int idx = tid; idx < BT * MP; idx += kLoopThreads) dlz[idx] = 0.f;
         for (int idx = tid; idx < BT * HiP; idx += kLoopThreads) dhx[idx] = 0.f;
@@ -124,7 +124,7 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas) {
 
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     MMG_SYNCTHREADS();
-    pdl_wait();
+    pdl_wait(); pdl_launch_dependents();
     if (tid == 0) tma_stage(sm, W.bwd_image + img0, (uint32_t)(im.total - img0) * 4u, bar);
     for (int idx = tid; idx < BT * HrP; idx += kLoopThreads) dh[idx] = 0.f;
     for (int idx = tid; idx < BT * MP; idx += kLoopThreads) dlw[idx] = 0.f;

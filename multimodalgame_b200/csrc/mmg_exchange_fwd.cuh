@@ -146,7 +146,7 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
     // ---- prologue -------------------------------------------------------------------------------------------
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     MMG_SYNCTHREADS();
-    pdl_wait();
+    pdl_wait(); pdl_launch_dependents();
     if (tid == 0) tma_stage(sm, gimg + img0, (uint32_t)(im.total - img0) * 4u, bar);
     // h_x rows of this CTA: sum the split-K partials of K_pre in a fixed order, add the bias
     for (int idx = tid; idx < BT * d.Hi; idx += kLoopThreads) {
@@ -425,7 +425,6 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
             }
         }
     }
-    pdl_launch_dependents();
 }
 
 }  // namespace mmg

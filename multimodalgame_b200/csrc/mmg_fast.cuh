@@ -110,10 +110,12 @@ MMG_DEVICE float4 lds4(const float* p) { return *reinterpret_cast<const float4*>
 #ifdef MMG_NO_SAVE
 #define MMG_SAVE_OK(b) ((b) < 0)
 #else
-#define MMG_SAVE_OK(b) ((b) < B)
+#define MMG_SAVE_OK(b) (kPerf || (b) < B)
 #endif
 
-template <int BT, int M, bool kRegSend>
+// kPerf: the training configuration bench.py measures (binary messages, on-device draws, no corruption mask, batch a
+// multiple of BT) with every mode flag a compile-time constant: no mode branches and no row guards in the step loop.
+template <int BT, int M, bool kRegSend, bool kPerf>
 MMG_GLOBAL void __launch_bounds__(kFastThreads, 1)
 k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int row_offset, const float* bs_w1,
                     const float* bs_b1, int n_conv_ctas) {
@@ -125,7 +127,7 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
         // Side role on SMs the conversations leave idle: U[b] = baseline_sen.linear1[:, :Hi] . h_x[b] + bias
         // (model.py:835-836).  h_x is the same for all T steps of an example, so this 9/10 of the sender-side baseline
         // GEMM is done once per example, concurrently with the exchange loop.
-        pdl_wait();
+        pdl_wait(); pdl_launch_dependents();
         const int ntn = cdiv(d.Hb, kTile);
         const int tile = (int)blockIdx.x - n_conv_ctas, nt = tile % ntn, mt = tile / ntn;
         // h_x rows are finalised by the conversation CTAs in their prologue (lower block indices, never blocked)
@@ -178,9 +180,11 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
 
     const float* gimg = W.fwd_image;
     const float* simg = kRegSend ? gimg : simg_s;                 // sender section: read once from L2, or shared memory
-    const bool train = in.train != 0;
-    const bool binary = d.use_binary != 0;
-    const bool own_draws = train && in.u_sen == nullptr;   // on-device Philox stream (else: injected float64 uniforms)
+    const bool train = kPerf ? true : in.train != 0;
+    const bool binary = kPerf ? true : d.use_binary != 0;
+    const bool own_draws = kPerf ? true : (train && in.u_sen == nullptr);   // on-device Philox stream (else: injected float64 uniforms)
+    const float* corrupt_mask = kPerf ? nullptr : in.corrupt_mask;
+    const bool ignore_receiver = kPerf ? false : d.ignore_receiver != 0;
 
     // per-thread roles, fixed for the whole kernel (addresses hoisted out of the step loop)
     const int k4t = tid >> 2, p4 = tid & 3;                       // (hidden unit, K-quarter) pairs: GRU, W_hh, mix
@@ -199,7 +203,7 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
     // ---- prologue ----------------------------------------------------------------------------------------------
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     MMG_SYNCTHREADS();
-    pdl_wait();
+    pdl_wait(); pdl_launch_dependents();
     if (tid == 0) tma_stage2(sm, gimg, (uint32_t)snd * 4u, sm + snd, gimg + im.b_ih, (uint32_t)(im.total - im.b_ih) * 4u, bar);
     // this thread's slice of every loop matrix -> registers (coalesced 16-byte loads from the L2-resident image)
     float4 rc[kRegSend ? M4 : 1], rb[kRegSend ? KB / 4 : 1], ri[3 * MQ], rh[8], rg[12], rw[KPT / 4];
@@ -371,7 +375,7 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
                     if (binary) {
                         p = fast_sigmoid(logit);
                         if (train) {
-                            if (b >= B) zval = 0.f;
+                            if (!kPerf && b >= B) zval = 0.f;
                             else if (own_draws) zval = (uni[(bt * T + t) * UST + j] < p) ? 1.f : 0.f;
                             else zval = (in.u_sen[row * M + j] < (double)p) ? 1.f : 0.f;
                         } else {
@@ -380,7 +384,7 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
                     } else {
                         zval = logit;
                     }
-                    if (in.corrupt_mask != nullptr) zval = fabsf(zval - in.corrupt_mask[j]);
+                    if (corrupt_mask != nullptr) zval = fabsf(zval - corrupt_mask[j]);
                     zv[bt * M + j] = zval;
                     if (MMG_SAVE_OK(b)) {
                         W.sen_feats[row * M + j] = zval;
@@ -455,6 +459,7 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
                     }
                 }
             }
+            gh_phase();          // W_hh . h' for the NEXT step: independent of the head rows, interleaves with them
         }
         MMG_STAMP(4);
         MMG_SYNCTHREADS();
@@ -494,7 +499,6 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
                 m = fmaxf(m, shfl_xor_f(m, 16));
                 if (lane == 0) wmax[bt * 8 + warp] = m;
             }
-            gh_phase();
         }
         MMG_STAMP(5);
         MMG_SYNCTHREADS();
@@ -507,17 +511,22 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
                 const float4 m0 = lds4(wmax + bt * 8), m1 = lds4(wmax + bt * 8 + 4);
                 const float mx = fmaxf(fmaxf(fmaxf(m0.x, m0.y), fmaxf(m0.z, m0.w)), fmaxf(fmaxf(m1.x, m1.y), fmaxf(m1.z, m1.w)));
                 float acc0 = 0.f, acc1 = 0.f, se0 = 0.f, se1 = 0.f;
-                int dd = 0;
-                for (; dd + 8 <= DP; dd += 8) {      // this thread's classes: dd + p4 and dd + 4 + p4
-                    const float e0 = fast_exp(yv[bt * DP + dd + p4] - mx), e1 = fast_exp(yv[bt * DP + dd + 4 + p4] - mx);
-                    se0 += e0; se1 += e1;
-                    acc0 = fmaf(e0, wdd_t[(dd >> 2) * NT], acc0);
-                    acc1 = fmaf(e1, wdd_t[((dd >> 2) + 1) * NT], acc1);
-                }
-                if (dd < DP) {
-                    const float e0 = fast_exp(yv[bt * DP + dd + p4] - mx);
-                    se0 += e0;
-                    acc0 = fmaf(e0, wdd_t[(dd >> 2) * NT], acc0);
+                // this thread's classes: c = dd0 + 4 u + p4; 8 independent exponentials in flight per 32-class chunk
+                // (padded classes hold y = -inf and wdd = 0)
+                for (int dd0 = 0; dd0 < DP; dd0 += 32) {
+                    float e[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int c = dd0 + 4 * u + p4;
+                        e[u] = c < DP ? fast_exp(yv[bt * DP + c] - mx) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u += 2) {
+                        const int g0 = (dd0 >> 2) + u;
+                        se0 += e[u]; se1 += e[u + 1];
+                        if (dd0 + 4 * u < DP) acc0 = fmaf(e[u], wdd_t[g0 * NT], acc0);
+                        if (dd0 + 4 * u + 4 < DP) acc1 = fmaf(e[u + 1], wdd_t[(g0 + 1) * NT], acc1);
+                    }
                 }
                 // STOP head: every warp evaluates the 64-wide dot product (no divergent block), one lane commits
                 float sv = fmaf(ws_a, hv[bt * HR + lane], ws_b * hv[bt * HR + lane + 32]);
@@ -537,7 +546,7 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
                     const float sp = fast_sigmoid(sv + s_bias);
                     float sbit;
                     if (train) {
-                        if (b >= B) sbit = 0.f;
+                        if (!kPerf && b >= B) sbit = 0.f;
                         else if (own_draws) sbit = (uni[(bt * T + t) * UST + 2 * M] < sp) ? 1.f : 0.f;
                         else sbit = (in.u_stop[row] < (double)sp) ? 1.f : 0.f;
                     } else {
@@ -578,13 +587,13 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
                     if (binary) {
                         p = fast_sigmoid(logit);
                         if (train) {
-                            if (b >= B) wv = 0.f;
+                            if (!kPerf && b >= B) wv = 0.f;
                             else if (own_draws) wv = (uni[(bt * T + t) * UST + M + j] < p) ? 1.f : 0.f;
                             else wv = (in.u_rec[row * M + j] < (double)p) ? 1.f : 0.f;
                         } else {
                             wv = rintf(p);
                         }
-                        if (d.ignore_receiver) wv = 0.f;
+                        if (ignore_receiver) wv = 0.f;
                     } else {
                         wv = logit;
                     }
@@ -602,14 +611,13 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
 #if defined(MMG_PHASE_TIMING) && !defined(MMG_CPU_EMU)
     if (blockIdx.x == 0) for (int i = tid; i < T * 64; i += NT) reinterpret_cast<unsigned*>(W.g_sen_probs)[i] = stamps[i];
 #endif
-    pdl_launch_dependents();
 }
 
 // ---- backward ------------------------------------------------------------------------------------------------------
 // One example per CTA.  CTAs [0, n_rec): receiver (BPTT); the rest: sender (no recurrence, model.py:807-811).
 MMG_HOST_DEVICE int fast_bwd_rec_state_floats(int T, int M, int D) {
     // dlw (T,M) | dhw (T,64) | inj (T,64) | gat (T,5,64) | hws, y1hs (T,64 each) | dgh (2,192) | gv (64) | gout (DP) | dls (T) | barrier
-    return T * (M + 4) + 2 * T * (kFastHr + 4) + 5 * T * kFastHr + 2 * T * kFastHr + 2 * 3 * kFastHr + kFastHr + align4(D) + align4(T) + 8;
+    return T * (M + 4) + 2 * T * (kFastHr + 4) + 5 * T * kFastHr + 2 * T * kFastHr + 4 * T * kFastHr + 2 * 3 * kFastHr + kFastHr + align4(D) + align4(T) + 8;
 }
 MMG_HOST_DEVICE int fast_bwd_sen_state_floats(int T, int M) { return T * M + 2 * kFastHi + T * kFastHi + 8; }
 
@@ -627,7 +635,7 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
         // =================================== sender ==============================================================
         const int b = (int)blockIdx.x - n_rec_ctas, n = tid;
         float* dlz = sm;                                              // (T, M)
-        pdl_wait();
+        pdl_wait(); pdl_launch_dependents();
         MMG_BSTAMP(0);
         float wb[M];                                                   // column n of binary_layer.weight
 #pragma unroll
@@ -700,6 +708,7 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
     float* gat = sm + o;  o += 5 * T * HR;          // per step: r, u, n, gh_n, h_prev
     float* hws = sm + o;  o += T * HR;              // h_w of every step
     float* y1hs = sm + o; o += T * HR;              // y1h of every step (the prediction step is only known after the load)
+    float* dgs = sm + o;  o += 4 * T * HR;          // per step: d r_pre, d u_pre, d n_pre, d gh_n (stored to HBM after the chain)
     float* dghv = sm + o; o += 2 * 3 * HR;
     float* gv = sm + o;   o += HR;
     float* gout = sm + o; o += DP;
@@ -715,7 +724,7 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
 
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     MMG_SYNCTHREADS();
-    pdl_wait();
+    pdl_wait(); pdl_launch_dependents();
     MMG_BSTAMP(0);
     // W_hh^T (48 KB) never touches shared memory: each thread keeps its 12 float4 of the BPTT mat-vec in registers
     if (tid == 0) tma_stage2(sm, W.bwd_image, (uint32_t)im.whhT * 4u, sm + im.ws, W.bwd_image + im.ws, (uint32_t)(im.total - im.ws) * 4u, bar);
@@ -737,14 +746,17 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
         W.d_lw[i] = dl;
         dlw[t * LDM + j] = dl;
     }
-#pragma unroll 4
-    for (int t = 0; t < T; ++t) gat[t * 5 * HR + tid] = W.gates[((size_t)t * B + b) * 4 * HR + tid];
-#pragma unroll 2
-    for (int idx = tid; idx < T * HR; idx += NT) {
-        const int t = idx >> 6, k = idx & 63;
-        gat[t * 5 * HR + 4 * HR + k] = W.h_z[((size_t)t * B + b) * HR + k];   // slot t = state entering step t
-        hws[idx] = W.h_w[((size_t)t * B + b) * HR + k];
-        y1hs[idx] = W.y1h[((size_t)t * B + b) * HR + k];
+    // saved activations of this example: asynchronous 16-byte copies, all in flight together
+    for (int idx = tid; idx < T * HR; idx += NT) {             // gates: T rows of 256 floats = 64 chunks each
+        const int t = idx >> 6, c = idx & 63;
+        cp_async16(gat + t * 5 * HR + 4 * c, W.gates + ((size_t)t * B + b) * 4 * HR + 4 * c);
+    }
+    for (int idx = tid; idx < T * 16 * 3; idx += NT) {         // h_prev, h_w, y1h: T rows of 64 floats = 16 chunks each
+        const int which = idx / (T * 16), r = idx % (T * 16), t = r >> 4, c = r & 15;
+        const size_t row = ((size_t)t * B + b) * HR + 4 * c;
+        if (which == 0)      cp_async16(gat + t * 5 * HR + 4 * HR + 4 * c, W.h_z + row);     // slot t = state entering step t
+        else if (which == 1) cp_async16(hws + t * HR + 4 * c, W.h_w + row);
+        else                 cp_async16(y1hs + t * HR + 4 * c, W.y1h + row);
     }
     for (int t = tid; t < T; t += NT) {
         const size_t row = (size_t)t * B + b;
@@ -756,6 +768,7 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
     for (int dd = tid; dd < D; dd += NT) gout[dd] = W.g_outp[(size_t)b * D + dd];
     const int ys = W.ystep[b];
     MMG_BSTAMP(1);
+    cp_async_wait_all();
 #ifdef MMG_CPU_EMU
     MMG_SYNCTHREADS();
 #endif
@@ -827,11 +840,8 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
         const float dr_pre = dn_pre * ghn * r * (1.f - r);
         const float du_pre = du * u * (1.f - u);
         if (part == 0) {
-            const size_t row = (size_t)t * B + b;
-            float* gi = W.dgi + row * 3 * HR;
-            float* gh = W.dgh + row * 3 * HR;
-            gi[k] = dr_pre; gi[HR + k] = du_pre; gi[2 * HR + k] = dn_pre;
-            gh[k] = dr_pre; gh[HR + k] = du_pre; gh[2 * HR + k] = dghn;
+            float* ds = dgs + t * 4 * HR;
+            ds[k] = dr_pre; ds[HR + k] = du_pre; ds[2 * HR + k] = dn_pre; ds[3 * HR + k] = dghn;
             float* dg = dghv + buf * 3 * HR;
             dg[k] = dr_pre; dg[HR + k] = du_pre; dg[2 * HR + k] = dghn;
         }
@@ -845,6 +855,15 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
             rec = group_sum<4>(hsum4(a4));
         }
         buf ^= 1;
+    }
+    // gate deltas of all steps -> HBM in one coalesced sweep (d gi = [r, u, n], d gh = [r, u, gh_n])
+    MMG_SYNCTHREADS();
+    for (int idx = tid; idx < T * 3 * HR; idx += NT) {
+        const int t = idx / (3 * HR), c = idx % (3 * HR);
+        const size_t row = (size_t)t * B + b;
+        const float* ds = dgs + t * 4 * HR;
+        W.dgi[row * 3 * HR + c] = ds[c];
+        W.dgh[row * 3 * HR + c] = c < 2 * HR ? ds[c] : ds[c + HR];
     }
     MMG_BSTAMP(5);
     (void)lane;

@@ -49,10 +49,36 @@ struct ExchangeInputs {       // device pointers of one exchange (mmg_inputs res
 
 // ---- launch macro --------------------------------------------------------------------------------------
 #ifndef MMG_CPU_EMU
-#define MMG_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
-    do {                                                                    \
-        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);        \
-        mmg::host::count_launch();                                          \
+#include <utility>
+#include <stdlib.h>
+namespace mmg {
+namespace host {
+// Every launch carries the programmatic-stream-serialization attribute (PDL): the next kernel's CTAs are scheduled while
+// the previous grid drains and block in `griddepcontrol.wait` (first statement of every kernel) until it has completed
+// and flushed, which hides launch + CTA-scheduling latency at each of the 8 kernel boundaries of an iteration.
+// MMG_PDL=0 disables the attribute (plain stream order).
+inline int pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MMG_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
+template <typename... KArgs, typename... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+}  // namespace host
+}  // namespace mmg
+#define MMG_LAUNCH(kernel, grid, block, smem, stream, ...)                                          \
+    do {                                                                                             \
+        mmg::host::launch(kernel, dim3(grid), dim3(block), (size_t)(smem), (stream), __VA_ARGS__);  \
+        mmg::host::count_launch();                                                                   \
     } while (0)
 #else
 #define MMG_LAUNCH(kernel, grid, block, smem, stream, ...)                                   \

@@ -221,7 +221,7 @@ struct Ws {   // byte offsets into the workspace
     int64_t slabs;     // (kWgradSplitMax - 1, P) split-K partial gradients (split 0 lands in the gradient buffer itself)
     int64_t norm_part; // (4, kNormCtasMax) per-CTA partial sums of squares
     int64_t loss_part; // double (kLossCtasMax, 8) per-CTA loss partial sums, summed in CTA order by the last CTA
-    int64_t tickets;   // uint32[4] "last CTA done" counters (self-resetting)
+    int64_t tickets;   // uint32[8]: [0] loss reduction, [1] h_x rows ready, [2] send buffer complete, [4..5] grid barrier
     int64_t opt_counters; // int64[4]: [0] = number of updates that reached the receiver message head (Adam bias correction)
     int hx_split, wgrad_split, ntb;
 };

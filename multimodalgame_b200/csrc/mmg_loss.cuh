@@ -16,6 +16,8 @@ namespace mmg {
 
 MMG_GLOBAL void __launch_bounds__(kGemmThreads)
 k_baseline_fwd(Dims d, ParamPtrs P, WsPtrs W, const float* desc, int n_bas_tiles, int use_u) {
+    pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
+    pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
     MMG_SHARED __attribute__((aligned(16))) float gs[kGemmSmemFloats];
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
     const int ntm = cdiv(d.R, kTile), ntn = W.ntb;
@@ -84,6 +86,8 @@ k_baseline_fwd(Dims d, ParamPtrs P, WsPtrs W, const float* desc, int n_bas_tiles
 // Baseline scores = linear2 bias + the per-tile partial dot products of K_baseline_fwd (summed in tile order).
 MMG_GLOBAL void __launch_bounds__(256)
 k_baseline_finish(Dims d, ParamPtrs P, WsPtrs W) {
+    pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
+    pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
     const float b2s = ldg(P.p[MMG_P_BS_L2_B]), b2r = ldg(P.p[MMG_P_BR_L2_B]);
     for (int r = blockIdx.x * 256 + threadIdx.x; r < d.R; r += gridDim.x * 256) {
         float s = b2s, q = b2r;
@@ -100,6 +104,8 @@ MMG_DEVICE unsigned char mask_at(const Dims& d, const WsPtrs& W, int slot, int b
 
 MMG_GLOBAL void __launch_bounds__(kStatsThreads)
 k_stats(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, PeerView pv) {
+    pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
+    pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kStatsThreads / 32;
     // ---- finalize baseline scores --------------------------------------------------------------------------
     const float b2s = ldg(P.p[MMG_P_BS_L2_B]), b2r = ldg(P.p[MMG_P_BR_L2_B]);
@@ -252,6 +258,8 @@ MMG_DEVICE float binary_grad(float p, float f, float wcA, float cE) {
 
 MMG_GLOBAL void __launch_bounds__(kLossThreads)
 k_lossgrad(Dims d, mmg_config cfg, WsPtrs W, PeerView pv) {
+    pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
+    pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
     MMG_DYN_SMEM(smem_raw);
     LossCoef* coef = reinterpret_cast<LossCoef*>(smem_raw);          // [3][T]
     float* bas_scale = reinterpret_cast<float*>(coef + 3 * d.T);      // [2]: 1 / denominator of the baseline MSE

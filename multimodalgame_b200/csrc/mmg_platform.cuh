@@ -143,6 +143,11 @@ MMG_DEVICE void tma_stage2(void* dst1, const void* src1, uint32_t bytes1, void* 
     for (uint32_t off = 0; off < bytes2; off += kPiece)
         tma_bulk_g2s((char*)dst2 + off, (const char*)src2 + off, bytes2 - off < kPiece ? bytes2 - off : kPiece, bar);
 }
+// Ampere-style asynchronous 16-byte global -> shared copies (LDGSTS): fire-and-forget, one wait for all of them.
+MMG_DEVICE void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+MMG_DEVICE void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // Programmatic dependent launch: wait for the producer grid's memory to be visible / let dependents start.
 MMG_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 MMG_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -264,6 +269,8 @@ MMG_DEVICE void tma_stage2(void* dst1, const void* src1, uint32_t bytes1, void* 
     memcpy(dst1, src1, bytes1);
     memcpy(dst2, src2, bytes2);
 }
+MMG_DEVICE void cp_async16(void* smem_dst, const void* gmem_src) { memcpy(smem_dst, gmem_src, 16); }
+MMG_DEVICE void cp_async_wait_all() {}
 MMG_DEVICE void pdl_wait() {}
 MMG_DEVICE void pdl_launch_dependents() {}
 MMG_DEVICE float ldg(const float* p) { return *p; }

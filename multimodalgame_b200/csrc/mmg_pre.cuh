@@ -63,6 +63,8 @@ MMG_DEVICE float bwd_image_elem(const Dims& d, const BwdImage& im, const ParamPt
 
 MMG_GLOBAL void __launch_bounds__(kGemmThreads)
 k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_kslice, int fast) {
+    pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
+    pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
     MMG_SHARED __attribute__((aligned(16))) float gs[kGemmSmemFloats];
     const int tid = threadIdx.x;
     if (blockIdx.x == 0 && tid == 0) W.tickets[1] = 0;      // "h_x rows ready" counter of the next forward kernel

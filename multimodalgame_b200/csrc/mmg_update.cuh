@@ -37,6 +37,8 @@ struct WgTable {
 
 MMG_GLOBAL void __launch_bounds__(kGemmThreads, 4)
 k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, const float* code_bias, const float* d_as) {
+    pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
+    pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
     MMG_SHARED __attribute__((aligned(16))) float gs[kGemmSmemFloats];
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
     int tile = blockIdx.x, pi = 0;
@@ -154,9 +156,8 @@ MMG_DEVICE int tensor_of(const SplitTable& st, long long i) {
 
 // grads (+)= slabs, scaled; per-CTA partial sums of squares per module -> norm_part[module * gridDim.x + cta].
 // do_reduce = 0: gradients are final already (after the data-parallel all-reduce), only the norms are computed.
-MMG_GLOBAL void __launch_bounds__(kUpdThreads)
-k_reduce_norm(SegInfo seg, SplitTable st, const float* arena, long long slab_stride, float* grads, float scale,
-              int do_reduce, float* norm_part, PeerView pv, unsigned* ticket) {
+MMG_DEVICE void reduce_norm_body(const SegInfo& seg, const SplitTable& st, const float* arena, long long slab_stride,
+                                 float* grads, float scale, int do_reduce, float* norm_part) {
     MMG_SHARED float red[4][kUpdThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long total = seg.begin[4];
@@ -193,6 +194,15 @@ k_reduce_norm(SegInfo seg, SplitTable st, const float* arena, long long slab_str
         for (int w = 0; w < kUpdThreads / 32; ++w) v += red[tid][w];
         norm_part[tid * gridDim.x + blockIdx.x] = v;
     }
+}
+
+MMG_GLOBAL void __launch_bounds__(kUpdThreads)
+k_reduce_norm(SegInfo seg, SplitTable st, const float* arena, long long slab_stride, float* grads, float scale,
+              int do_reduce, float* norm_part, PeerView pv, unsigned* ticket) {
+    pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
+    pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
+    const int tid = threadIdx.x;
+    reduce_norm_body(seg, st, arena, slab_stride, grads, scale, do_reduce, norm_part);
     if (pv.world > 1) {
         // `grads` is this rank's symmetric send buffer: once every CTA has written its part, raise flag row 1 on all peers
         MMG_SHARED int s_last;
@@ -211,6 +221,8 @@ k_reduce_norm(SegInfo seg, SplitTable st, const float* arena, long long slab_str
 // send buffers (one-shot, rank order => bit-identical results everywhere) and writes the global gradient locally.
 MMG_GLOBAL void __launch_bounds__(kUpdThreads)
 k_peer_allreduce_norm(SegInfo seg, PeerView pv, float* grads_out, float* norm_part) {
+    pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
+    pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
     MMG_SHARED float red[4][kUpdThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < pv.world && !peer_wait(pv.flags[pv.rank] + MMG_MAX_PEERS + tid, pv.iter)) *pv.error = 2;
@@ -243,9 +255,9 @@ k_peer_allreduce_norm(SegInfo seg, PeerView pv, float* grads_out, float* norm_pa
 
 struct OptHyper { int optim; float lr, max_norm; long long step; };
 
-MMG_GLOBAL void __launch_bounds__(kUpdThreads)
-k_update(SegInfo seg, OptHyper hp, float* params, float* grads, float* state1, float* state2, const float* norm_part,
-         int n_norm_ctas, float* grad_norms, const double* stats, const long long* opt_counters) {
+MMG_DEVICE void update_body(const SegInfo& seg, const OptHyper& hp, float* params, float* grads, float* state1, float* state2,
+                            const float* norm_part, int n_norm_ctas, float* grad_norms, const double* stats,
+                            const long long* opt_counters) {
     MMG_SHARED float coef[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (warp < 4) {   // global L2 norm per module, partials summed in a fixed order
@@ -312,7 +324,43 @@ k_update(SegInfo seg, OptHyper hp, float* params, float* grads, float* state1, f
     }
 }
 
+MMG_GLOBAL void __launch_bounds__(kUpdThreads)
+k_update(SegInfo seg, OptHyper hp, float* params, float* grads, float* state1, float* state2, const float* norm_part,
+         int n_norm_ctas, float* grad_norms, const double* stats, const long long* opt_counters) {
+    pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
+    pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
+    update_body(seg, hp, params, grads, state1, state2, norm_part, n_norm_ctas, grad_norms, stats, opt_counters);
+}
+
+#ifndef MMG_CPU_EMU
+// Single-GPU fusion of K_reduce_norm and K_update: the global gradient norm is a grid-wide dependency, resolved by a
+// software grid barrier (arrival counter + spin).  Legal because the host launches at most as many CTAs as are
+// co-resident (occupancy x SM count), so every CTA is running when the first one starts to wait.
+MMG_DEVICE void grid_barrier(unsigned* ctr, unsigned n) {     // ctr[0] arrivals, ctr[1] departures; self-resetting
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        for (int spin = 0; spin < (1 << 26) && *reinterpret_cast<volatile unsigned*>(ctr) < n; ++spin) { }   // bounded
+        __threadfence();
+        if (atomicAdd(ctr + 1, 1u) == n - 1) { ctr[0] = 0; ctr[1] = 0; __threadfence(); }
+    }
+    __syncthreads();
+}
+MMG_GLOBAL void __launch_bounds__(kUpdThreads)
+k_reduce_update(SegInfo seg, SplitTable st, const float* arena, long long slab_stride, OptHyper hp, float* params,
+                float* grads, float* state1, float* state2, float* norm_part, float* grad_norms, const double* stats,
+                const long long* opt_counters, unsigned* barrier_ctr) {
+    pdl_wait();
+    pdl_launch_dependents();
+    reduce_norm_body(seg, st, arena, slab_stride, grads, 1.0f, 1, norm_part);
+    grid_barrier(barrier_ctr, gridDim.x);
+    update_body(seg, hp, params, grads, state1, state2, norm_part, (int)gridDim.x, grad_norms, stats, opt_counters);
+}
+#endif
+
 MMG_GLOBAL void k_init_rng(unsigned long long* st, unsigned long long seed) {
+    pdl_wait();
     if (threadIdx.x == 0 && blockIdx.x == 0) { st[0] = seed; st[1] = 0ull; }
 }
 

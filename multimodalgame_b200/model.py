@@ -5,6 +5,7 @@ reference's `run()` loop (model.py:1190-1339) can call into this module unchange
 
     Sender / Receiver / Baseline      model.py:49-238 / 241-477 / 480-516
     exchange(...)                     model.py:725-876
+    eval_dev(...)                     model.py:580-722 (batches as dicts; statistics accumulated on the device)
     get_rec_outp, calculate_loss_binary, multistep_loss_binary, calculate_loss_bas, multistep_loss_bas,
     build_inp, flipout, loglikelihood model.py:519-577, 879-988
     flags(), default_flags(), Fixed/Adaptive presets       model.py:1605-1810
@@ -455,6 +456,79 @@ def exchange(sender, receiver, baseline_sen, baseline_rec, exchange_args):
     receiver.h_z = o["h_z"][steps - 1]
     receiver.h_w = o["h_w"][steps - 1]
     return (stop_mask, stop_feat, stop_prob), (sen_feats, sen_probs), (rec_feats, rec_probs), y, bs, br
+
+
+def eval_dev(dev_file, batch_size, epoch, shuffle, cuda, top_k, sender, receiver, desc_dict, map_labels, file_name,
+             callback=None):
+    """Development accuracy and conversation statistics (model.py:580-722), same signature and return value
+    (accuracy, extra).  The conversations run in eval mode through the fused kernels; top-k membership, conversation
+    lengths, Hamming distances between consecutive messages and the confusion matrix are accumulated ON THE DEVICE and
+    read back once at the end (the reference copies every batch to the host and argsorts with NumPy).
+
+    `dev_file` is either an iterable of batch dicts in the layout `misc.load_hdf5` yields (keys "target" and
+    FLAGS.img_feat, model.py:614-615) or an HDF5 path (needs h5py, which this package does not depend on)."""
+    if isinstance(dev_file, str):
+        try:
+            import h5py  # noqa: F401
+        except ImportError:
+            raise ImportError("eval_dev(dev_file=<path>) needs h5py (misc.load_hdf5, misc.py:257-302); pass an iterable "
+                              "of batch dicts instead")
+        _unsupported("reading HDF5 feature files (data loading is outside the fused path; pass batch dicts)")
+    dev = _device_of(receiver)
+    desc = desc_dict["desc"].to(dev)
+    n_classes = desc.shape[0]
+    feat_key = _flag("img_feat", "avgpool_512")
+    fixed = bool(_flag("fixed_exchange", True))
+    total = 0.0
+    correct = torch.zeros((), dtype=torch.float64, device=dev)
+    conv_sum = torch.zeros((), dtype=torch.float64, device=dev)
+    conv_sq = torch.zeros((), dtype=torch.float64, device=dev)
+    conv_n = 0
+    ham_sen, ham_rec = [], []
+    conf = torch.zeros(n_classes, n_classes, dtype=torch.int64, device=dev)
+    for batch in dev_file:
+        target = batch["target"].to(dev)
+        data = batch[feat_key].to(dev)
+        bsz = target.size(0)
+        exchange_args = dict(data=data, target=target, desc=desc, desc_set=desc_dict.get("desc_set"),
+                             desc_set_lens=desc_dict.get("desc_set_lens"), train=False, break_early=not fixed,
+                             corrupt=bool(_flag("bit_flip", False)), corrupt_region=_flag("corrupt_region"))
+        s, sen_w, rec_w, y, bs, br = exchange(sender, receiver, None, None, exchange_args)
+        s_masks, s_feats, s_probs = s
+        sen_feats, sen_probs = sen_w
+        rec_feats, rec_probs = rec_w
+        y_masks = None if fixed else [torch.min(1 - m1, m2) for m1, m2 in zip(s_masks[1:], s_masks[:-1])]   # 648-652
+        outp, _ = get_rec_outp(y, y_masks)
+        dist = F.log_softmax(outp, dim=1)
+        k = min(int(top_k), n_classes)
+        top_k_ind = dist.topk(k, dim=1).indices                                   # model.py:658-660
+        correct += (top_k_ind == target.view(-1, 1)).sum()
+        total += float(batch_size)                                                # model.py:668 (nominal batch size)
+        argmax = dist.argmax(dim=1)
+        conf += torch.bincount(target * n_classes + argmax, minlength=n_classes * n_classes).view(n_classes, n_classes)
+        lengths = torch.cat(s_feats, 1).float().sum(1).double()                   # model.py:672-673
+        conv_sum += lengths.sum(); conv_sq += (lengths * lengths).sum(); conv_n += bsz
+        for feats, acc in ((sen_feats, ham_sen), (rec_feats, ham_rec)):            # model.py:676-690
+            msgs = torch.stack(feats, 0)
+            prev = torch.cat([torch.zeros_like(msgs[:1]), msgs[:-1]], 0)
+            acc.append((msgs - prev).abs().sum(2).mean(1).sum() / float(len(feats)))
+        if callback is not None:
+            callback(sender, receiver, batch, dict(s_masks=s_masks, s_feats=s_feats, s_probs=s_probs, sen_feats=sen_feats,
+                                                   sen_probs=sen_probs, rec_feats=rec_feats, rec_probs=rec_probs, y=y))
+    mean = float(conv_sum) / max(conv_n, 1)
+    extra = dict()
+    extra["conversation_lengths_mean"] = mean
+    extra["conversation_lengths_std"] = math.sqrt(max(float(conv_sq) / max(conv_n, 1) - mean * mean, 0.0))
+    extra["hamming_sen_mean"] = float(torch.stack(ham_sen).mean()) if ham_sen else float("nan")
+    extra["hamming_rec_mean"] = float(torch.stack(ham_rec).mean()) if ham_rec else float("nan")
+    extra["confusion_matrix"] = conf.cpu().numpy()
+    conf_path = _flag("conf_mat")
+    if conf_path:
+        try:
+            np.savetxt(conf_path, extra["confusion_matrix"], delimiter=",", fmt="%d")   # model.py:709-710
+        except (IOError, OSError):
+            pass
+    return float(correct) / max(total, 1.0), extra
 
 
 def train_step(sender, receiver, baseline_sen, baseline_rec, exchange_args, group=None):

@@ -196,3 +196,45 @@ def run_train_step_case(case, device):
             pu.assert_close("%s/param %s.%s" % (case, a, k), p.detach().cpu().numpy(), oparams[a][k].numpy(), rtol=1e-5,
                             atol=atol)
     return eng
+
+
+def run_eval_dev_case(case, device, top_k=2):
+    """model.eval_dev() on a reference-generated eval fixture (two identical batches) against the statistics recomputed in
+    NumPy from the fixture's arrays exactly as model.py:648-718 does."""
+    z, cfg = gu.load(case)
+    set_flags(cfg)
+    region = str(z["corrupt_region"])
+    M.FLAGS.bit_flip = bool(region)
+    M.FLAGS.corrupt_region = region or None
+    M.FLAGS.conf_mat = ""
+    params = gu.params_at(z, "P0")
+    full = go.init_params(cfg, seed=1)
+    for a in full:
+        if a not in params:
+            params[a] = full[a]
+    mods = build_modules(cfg, params, device)
+    x, desc, target = torch.from_numpy(z["x"]), torch.from_numpy(z["desc"]), torch.from_numpy(z["target"])
+    batches = [{"target": target, M.FLAGS.img_feat: x}, {"target": target, M.FLAGS.img_feat: x}]
+    acc, extra = M.eval_dev(batches, cfg.batch_size, 0, False, device != "cpu", top_k, mods["sender"], mods["receiver"],
+                            dict(desc=desc), None, None)
+    # expected, from the reference's own outputs
+    dist = torch.log_softmax(torch.from_numpy(z["outp"]), dim=1).numpy()
+    topk = np.argsort(dist, axis=1)[:, -top_k:]
+    tgt = z["target"].reshape(-1)
+    correct = float((topk == tgt[:, None]).sum())
+    pu.assert_close(case + "/accuracy", acc, correct / cfg.batch_size)
+    lengths = z["stop_feat"].reshape(z["stop_feat"].shape[0], -1).sum(0)
+    pu.assert_close(case + "/conv_mean", extra["conversation_lengths_mean"], lengths.mean())
+    pu.assert_close(case + "/conv_std", extra["conversation_lengths_std"], lengths.std())
+    for key, name in (("sen_feats", "hamming_sen_mean"), ("rec_feats", "hamming_rec_mean")):
+        msgs = z[key]
+        prev = np.concatenate([np.zeros_like(msgs[:1]), msgs[:-1]], 0)
+        pu.assert_close(case + "/" + name, extra[name], np.abs(msgs - prev).sum(2).mean(1).sum() / msgs.shape[0], rtol=1e-4,
+                        atol=1e-4)
+    pred = dist.argmax(1)
+    cm = np.zeros((cfg.n_classes, cfg.n_classes), dtype=np.int64)
+    for t, p in zip(tgt, pred):
+        cm[t, p] += 2
+    assert np.array_equal(extra["confusion_matrix"], cm)
+    M.FLAGS.bit_flip = False
+    M.FLAGS.corrupt_region = None

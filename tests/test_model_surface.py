@@ -26,6 +26,11 @@ def test_fused_train_step_behind_the_modules(case):
     su.run_train_step_case(case, "cpu")
 
 
+@pytest.mark.parametrize("case", ["eval_adaptive", "eval_fixed_corrupt"])
+def test_eval_dev_statistics(case):
+    su.run_eval_dev_case(case, "cpu")
+
+
 def test_unsupported_flags_raise():
     from tests import golden_util as gu
     z, cfg = gu.load("fixed_small")
