@@ -573,7 +573,8 @@ static int exchange_forward_impl(const mmg_config* cfg, const float* d_params, c
     const int n_hx = cdiv(d.B, kTile) * cdiv(d.Hi, kTile) * W.hx_split;
     const int hx_kslice = round_up(cdiv(d.F, W.hx_split), 4);
     const int n_pack = 64;
-    MMG_LAUNCH(k_pre, n_hx + n_pack, kGemmThreads, 0, st, d, P, W, ei, n_hx, hx_kslice, pl.fast);
+    const int n_cls = 2 * cdiv(d.D, kTile) * cdiv(d.Hr, kTile);
+    MMG_LAUNCH(k_pre, n_hx + n_cls + n_pack, kGemmThreads, 0, st, d, P, W, ei, n_hx, hx_kslice, pl.fast, n_cls);
     if ((rc = check_cuda("k_pre"))) return rc;
     // K_exchange_fwd
     const float* b_img = P.p[MMG_P_SEN_IMG_B];

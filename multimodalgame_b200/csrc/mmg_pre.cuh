@@ -62,7 +62,7 @@ MMG_DEVICE float bwd_image_elem(const Dims& d, const BwdImage& im, const ParamPt
 }
 
 MMG_GLOBAL void __launch_bounds__(kGemmThreads)
-k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_kslice, int fast) {
+k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_kslice, int fast, int n_cls_tiles) {
     pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
     pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
     MMG_SHARED __attribute__((aligned(16))) float gs[kGemmSmemFloats];
@@ -93,12 +93,52 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
         }
         return;
     }
-    // ---- role B: images + class halves ------------------------------------------------------------------
     const FwdImage fim = make_fwd_image(d);
     const BwdImage bim = make_bwd_image(d);
     const FastFwdImage ffi = make_fast_fwd_image(d.M, d.D);
     const FastBwdImage fbi = make_fast_bwd_image(d.M, d.D);
-    const int nblk = gridDim.x - n_hx_tiles, blk = blockIdx.x - n_hx_tiles;
+    if ((int)blockIdx.x < n_hx_tiles + n_cls_tiles) {
+        // ---- role C: loop-invariant class tables as two small GEMMs over the word-vector dimension -----------------
+        //   y1d[dd][k] = y1.bias[k] + sum_v desc[dd][v] * y1.weight[k][Hr + v]     wdd[dd][k] = sum_v desc[dd][v] * w_d.weight[k][v]
+        const int ntk = cdiv(d.Hr, kTile), ntd = cdiv(d.D, kTile);
+        int t = (int)blockIdx.x - n_hx_tiles;
+        const int which = t / (ntd * ntk);
+        t %= ntd * ntk;
+        const int nt = t % ntk, mt = t / ntk;
+        Operand A = {in.desc, nullptr, nullptr, nullptr, d.WV, 0, 0, 0, 0, OP_PLAIN};
+        Operand Bo = which == 0 ? Operand{P.p[MMG_P_REC_Y1_W] + d.Hr, nullptr, nullptr, nullptr, d.Hr + d.WV, 0, 0, 0, 0, OP_PLAIN}
+                                : Operand{P.p[MMG_P_REC_WD_W], nullptr, nullptr, nullptr, d.WV, 0, 0, 0, 0, OP_PLAIN};
+        float acc[4][4];
+        gemm_tile(A, Bo, d.D, d.Hr, mt * kTile, nt * kTile, 0, d.WV, acc, nullptr, gs);
+        const int tx = tid % 16, ty = tid / 16;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int dd = mt * kTile + ty * 4 + a;
+            if (dd >= d.D) continue;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int k = nt * kTile + tx * 4 + c;
+                if (k >= d.Hr) continue;
+                const int o = dd * d.Hr + k;
+                if (which == 0) {
+                    const float v = acc[a][c] + ldg(P.p[MMG_P_REC_Y1_B] + k);
+                    if (fast) {
+                        W.fwd_image[ffi.y1d + o] = v;
+                        W.bwd_image[fbi.y1d + ((dd >> 2) * d.Hr + k) * 4 + (dd & 3)] = v;
+                    } else {
+                        W.fwd_image[fim.y1d + o] = v;
+                        W.bwd_image[bim.y1d + o] = v;
+                    }
+                } else {
+                    if (fast) W.fwd_image[ffi.wdd + ((dd >> 2) * d.Hr + k) * 4 + (dd & 3)] = acc[a][c];
+                    else      W.fwd_image[fim.wdd + o] = acc[a][c];
+                }
+            }
+        }
+        return;
+    }
+    // ---- role B: images + the step-0 code term -------------------------------------------------------------
+    const int nblk = gridDim.x - n_hx_tiles - n_cls_tiles, blk = blockIdx.x - n_hx_tiles - n_cls_tiles;
     const int gthreads = nblk * kGemmThreads, gtid = blk * kGemmThreads + tid;
     if (fast) {
         for (int e = gtid; e < ffi.y1d; e += gthreads) {
@@ -117,35 +157,8 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
     const int lane = tid & 31, gwarp = gtid >> 5, nwarps = gthreads >> 5;
     const int n_y1d = d.D * d.Hr;
     const int n_out = 2 * n_y1d + d.Hi + d.M;
-    const float* y1w = P.p[MMG_P_REC_Y1_W];
-    for (int o = gwarp; o < n_out; o += nwarps) {
-        if (o < n_y1d) {                       // y1d[dd][k] = y1.bias[k] + sum_v desc[dd][v] * y1.weight[k][Hr + v]
-            const int dd = o / d.Hr, k = o % d.Hr;
-            float s = 0.f;
-            for (int v = lane; v < d.WV; v += 32)
-                s = fmaf(ldg(in.desc + (size_t)dd * d.WV + v), ldg(y1w + (size_t)k * (d.Hr + d.WV) + d.Hr + v), s);
-            s = warp_sum(s);
-            if (lane == 0) {
-                s += ldg(P.p[MMG_P_REC_Y1_B] + k);
-                if (fast) {
-                    W.fwd_image[ffi.y1d + o] = s;
-                    W.bwd_image[fbi.y1d + ((dd >> 2) * d.Hr + k) * 4 + (dd & 3)] = s;
-                } else {
-                    W.fwd_image[fim.y1d + o] = s;
-                    W.bwd_image[bim.y1d + o] = s;
-                }
-            }
-        } else if (o < 2 * n_y1d) {            // wdd[dd][k] = sum_v desc[dd][v] * w_d.weight[k][v]
-            const int oo = o - n_y1d, dd = oo / d.Hr, k = oo % d.Hr;
-            float s = 0.f;
-            for (int v = lane; v < d.WV; v += 32)
-                s = fmaf(ldg(in.desc + (size_t)dd * d.WV + v), ldg(P.p[MMG_P_REC_WD_W] + (size_t)k * d.WV + v), s);
-            s = warp_sum(s);
-            if (lane == 0) {
-                if (fast) W.fwd_image[ffi.wdd + ((dd >> 2) * d.Hr + k) * 4 + (dd & 3)] = s;
-                else      W.fwd_image[fim.wdd + oo] = s;
-            }
-        } else if (o < 2 * n_y1d + d.Hi) {     // hw0[n] = code_layer.bias[n] + sum_j sigmoid(code_bias[j]) * code_layer.weight[n][j]
+    for (int o = 2 * n_y1d + gwarp; o < n_out; o += nwarps) {
+        if (o < 2 * n_y1d + d.Hi) {     // hw0[n] = code_layer.bias[n] + sum_j sigmoid(code_bias[j]) * code_layer.weight[n][j]
             const int n = o - 2 * n_y1d;
             float s = 0.f;
             for (int j = lane; j < d.M; j += 32)
