@@ -133,7 +133,7 @@ static void ws_layout(const Dims& d, Ws* w) {
     w->bs_part = take(c, R * w->ntb * f);
     w->br_part = take(c, R * w->ntb * f);
     w->ubs = take(c, B * d.Hb * f);
-    int hs = d.F / 128;
+    int hs = d.F / 128;      // image-layer GEMM: K-slices of 128 features per CTA (8 chunks), partials summed by the consumer
     if (hs < 1) hs = 1;
     if (hs > kHxSplitMax) hs = kHxSplitMax;
     w->hx_split = hs;

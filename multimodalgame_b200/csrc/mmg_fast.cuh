@@ -227,14 +227,14 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
         const int b = b0 + bt, n = tid;
         float v = 0.f;
         if (b < B) {
-            float v0 = ldg(b_img + n), v1 = 0.f;
-            int s = 0;
-            for (; s + 1 < W.hx_split; s += 2) {
-                v0 += W.hx_part[((size_t)s * B + b) * HI + n];
-                v1 += W.hx_part[((size_t)(s + 1) * B + b) * HI + n];
+            v = ldg(b_img + n);
+            for (int s = 0; s < W.hx_split; s += 8) {      // 8 partial loads in flight, added in slab order
+                float pv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) pv[u] = s + u < W.hx_split ? W.hx_part[((size_t)(s + u) * B + b) * HI + n] : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v += pv[u];
             }
-            if (s < W.hx_split) v0 += W.hx_part[((size_t)s * B + b) * HI + n];
-            v = v0 + v1;
             W.h_x[(size_t)b * HI + n] = v;
         }
         hx[bt * HI + n] = v;

@@ -180,7 +180,7 @@ MMG_HOST_DEVICE bool fast_dims(const Dims& d) {
 }
 
 // ---- workspace ------------------------------------------------------------------------------------------
-enum { kHxSplitMax = 16, kWgradSplitMax = 16, kNormCtasMax = 592, kLossCtasMax = 592 };
+enum { kHxSplitMax = 32, kWgradSplitMax = 16, kNormCtasMax = 592, kLossCtasMax = 592 };
 enum { kStatKinds = 3 };  // 0: sender messages, 1: receiver messages, 2: stop bit
 // stats (double): per (kind, t): n, sum w, sum w^2 (w = logs - baseline); then per t: baseline_rec SSE,
 // baseline_sen SSE, n_mask; then scalars: nll_sum, topk_correct.

@@ -114,55 +114,65 @@ k_stats(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, PeerView pv) {
         for (int j = 0; j < W.ntb; ++j) { s += W.bs_part[(size_t)r * W.ntb + j]; q += W.br_part[(size_t)r * W.ntb + j]; }
         W.bs[r] = s; W.br[r] = q;
     }
-    // ---- per example (one warp each, lanes over classes): prediction step, log-softmax, log-likelihood, argmax,
-    //      top-k, dNLL/d outp ------------------------------------------------------------------------------------------
-    MMG_SHARED double s_red[2][kStatsThreads / 32];
+    // ---- per example (one HALF-warp each, lanes over classes; 64 examples per round): prediction step, log-softmax,
+    //      log-likelihood, argmax, top-k, dNLL/d outp -----------------------------------------------------------------
+    MMG_SHARED double s_red[2][kStatsThreads / 16];
     double nll_local = 0.0, correct_local = 0.0;
     const float invB = 1.0f / (float)d.Bg;
-    for (int b = warp; b < d.B; b += nwarps) {
+    const int hl = tid & 15, hwid = tid >> 4, nhw = kStatsThreads / 16;
+    for (int b0 = 0; b0 < d.B; b0 += nhw) {
+        const int b = b0 + hwid;
+        const bool ok = b < d.B;
+        const int bb = ok ? b : 0;
         int ts = d.T - 1;
         if (!d.fixed) {   // first step whose outgoing mask is 0 (model.py:893-896); the last mask is forced to 0 (870)
             float first = (float)(d.T - 1);
-            for (int t = lane; t < d.T; t += 32)
-                if (W.stop_mask[(size_t)(t + 1) * d.B + b] == 0) first = fminf(first, (float)t);
-            ts = (int)(-warp_max(-first));
+            for (int t = hl; t < d.T; t += 16)
+                if (W.stop_mask[(size_t)(t + 1) * d.B + bb] == 0) first = fminf(first, (float)t);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) first = fminf(first, shfl_xor_f(first, o));
+            ts = (int)first;
         }
-        const float* yy = W.y + ((size_t)ts * d.B + b) * d.D;
-        const int tg = (int)in.target[b];
+        const float* yy = W.y + ((size_t)ts * d.B + bb) * d.D;
+        const int tg = (int)in.target[bb];
         const float ytg = yy[tg];
         float mx = -INFINITY;
-        for (int dd = lane; dd < d.D; dd += 32) mx = fmaxf(mx, yy[dd]);
-        mx = warp_max(mx);
+        for (int dd = hl; dd < d.D; dd += 16) mx = fmaxf(mx, yy[dd]);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, shfl_xor_f(mx, o));
         float am = 3.0e9f, se = 0.f, rank = 0.f;
-        for (int dd = lane; dd < d.D; dd += 32) {
+        for (int dd = hl; dd < d.D; dd += 16) {
             const float v = yy[dd];
             if (v == mx) am = fminf(am, (float)dd);          // first index of the maximum, like a serial `>` scan
             se += expf(v - mx);
             if (v > ytg) rank += 1.f;
         }
-        am = -warp_max(-am);
-        se = warp_sum(se);
-        rank = warp_sum(rank);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) am = fminf(am, shfl_xor_f(am, o));
+        se = group_sum<16>(se);
+        rank = group_sum<16>(rank);
         const float lse = mx + logf(se);
         const float lt = ytg - lse;
-        for (int dd = lane; dd < d.D; dd += 32) {
-            const float v = yy[dd];
-            W.outp[(size_t)b * d.D + dd] = v;
-            W.g_outp[(size_t)b * d.D + dd] = (expf(v - lse) - (dd == tg ? 1.f : 0.f)) * invB;   // d nll / d outp
-        }
-        if (lane == 0) {
-            W.ystep[b] = ts;
-            W.logs[b] = lt;
-            W.argmax[b] = (int)am;
-            nll_local -= (double)lt;
-            if ((int)rank < in.top_k) correct_local += 1.0;
+        if (ok) {
+            for (int dd = hl; dd < d.D; dd += 16) {
+                const float v = yy[dd];
+                W.outp[(size_t)b * d.D + dd] = v;
+                W.g_outp[(size_t)b * d.D + dd] = (expf(v - lse) - (dd == tg ? 1.f : 0.f)) * invB;   // d nll / d outp
+            }
+            if (hl == 0) {
+                W.ystep[b] = ts;
+                W.logs[b] = lt;
+                W.argmax[b] = (int)am;
+                nll_local -= (double)lt;
+                if ((int)rank < in.top_k) correct_local += 1.0;
+            }
         }
     }
-    if (lane == 0) { s_red[0][warp] = nll_local; s_red[1][warp] = correct_local; }
+    if (hl == 0) { s_red[0][hwid] = nll_local; s_red[1][hwid] = correct_local; }
     MMG_SYNCTHREADS();
     if (tid == 0) {
         double a = 0, c = 0;
-        for (int w = 0; w < nwarps; ++w) { a += s_red[0][w]; c += s_red[1][w]; }
+        for (int w = 0; w < nhw; ++w) { a += s_red[0][w]; c += s_red[1][w]; }
         W.stats[stat_scalar(d, 0)] = a;
         W.stats[stat_scalar(d, 1)] = c;
         W.stats[stat_scalar(d, 2)] = 0.0;
@@ -175,7 +185,8 @@ k_stats(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, PeerView pv) {
     // kind 2: stop bit         (baseline br[t], mask s_masks[t])      model.py:1256,1279-1280
     for (int qn = warp; qn < 4 * d.T; qn += nwarps) {
         const int kind = qn / d.T, t = qn % d.T;
-        double n = 0, s1 = 0, s2 = 0, e1 = 0, e2 = 0;
+        double n = 0, s1 = 0, s2 = 0;      // kind < 3: count, sum w, sum w^2; kind 3: count, SSE baseline_rec, SSE baseline_sen
+#pragma unroll 2
         for (int b = lane; b < d.B; b += 32) {
             const float lg = W.logs[b];
             if (kind < 3) {
@@ -189,18 +200,18 @@ k_stats(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, PeerView pv) {
             } else {
                 if (mask_at(d, W, t, b)) {
                     const double er = (double)(W.br[(size_t)t * d.B + b] - lg), es = (double)(W.bs[(size_t)t * d.B + b] - lg);
-                    e1 += er * er; e2 += es * es;
+                    s1 += er * er; s2 += es * es;
                 }
                 if (mask_at(d, W, t + 1, b) && !d.fixed) n += 1.0;   // rows still active after step t
                 if (d.fixed) n += 1.0;
             }
         }
-        n = warp_sum_d(n); s1 = warp_sum_d(s1); s2 = warp_sum_d(s2); e1 = warp_sum_d(e1); e2 = warp_sum_d(e2);
+        n = warp_sum_d(n); s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
         if (lane == 0) {
             if (kind < 3) {
                 W.stats[stat_idx(d, kind, t, 0)] = n; W.stats[stat_idx(d, kind, t, 1)] = s1; W.stats[stat_idx(d, kind, t, 2)] = s2;
             } else {
-                W.stats[stat_bas(d, t, 0)] = e1; W.stats[stat_bas(d, t, 1)] = e2; W.stats[stat_bas(d, t, 2)] = n;
+                W.stats[stat_bas(d, t, 0)] = s1; W.stats[stat_bas(d, t, 1)] = s2; W.stats[stat_bas(d, t, 2)] = n;
             }
         }
     }
