@@ -123,7 +123,7 @@ def time_oracle(cfgd, iters, warmup, threads=None):
     return sum(times), steps, torch.get_num_threads()
 
 
-def run_reference(args, cfgd, name):
+def run_reference(args, cfgd, name, out_stream):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -138,10 +138,21 @@ def run_reference(args, cfgd, name):
                             "sample": "%d training iterations of the same workload on the host (oracle/game_oracle.py, "
                                       "torch CPU fp32, %d threads, os.cpu_count=%d)" % (iters, threads, os.cpu_count())},
            "e2e": {"value": val, "unit": "exchange-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    out_stream.write(json.dumps(out) + "\n")
+    out_stream.flush()
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner, for one), so
+    everything written to fd 1 during the run goes to stderr and the JSON line is written to the original stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
 
 
 def main():
+    out_stream = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -156,7 +167,7 @@ def main():
     name = args.config or ("C2" if args.gpus == 1 else "C4")
     cfgd = dict(CONFIGS[name])
     if args.impl == "reference":
-        run_reference(args, cfgd, name)
+        run_reference(args, cfgd, name, out_stream)
         return
 
     import __graft_entry__ as ge
@@ -338,7 +349,8 @@ def main():
         out["cpu_baseline"] = {"value": steps / total, "unit": "exchange-steps/s", "cores": threads, "kind": "port",
                                "sample": "30 training iterations of the same workload (oracle/game_oracle.py, torch CPU fp32, "
                                          "%d threads, os.cpu_count=%d), %.1f ms/iteration" % (threads, os.cpu_count(), 1e3 * total / 30)}
-    print(json.dumps(out))
+    out_stream.write(json.dumps(out) + "\n")
+    out_stream.flush()
     if dist is not None:
         dist.destroy_process_group()
 

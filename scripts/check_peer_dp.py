@@ -1,4 +1,6 @@
-"""2+ GPU check (torchrun): the NVLink peer-memory data-parallel iteration against (a) the NCCL all-reduce path on the
+"""2+ GPU check (torchrun).  With 2 ranks a + b is order-free, so the peer path must equal the NCCL path bit for bit; with more
+ranks the summation orders differ and RMSprop turns rounding-level gradient differences into up to ~10 x lr of parameter
+difference (same tolerance as the single-GPU parity tests).  2+ GPU check: the NVLink peer-memory data-parallel iteration against (a) the NCCL all-reduce path on the
 same shards and (b) the single-process global-batch CPU oracle.  Prints PASS/FAIL on rank 0."""
 import os, sys
 import numpy as np, torch, torch.distributed as dist
@@ -48,7 +50,7 @@ for name, kw in (("fixed", dict(fixed_exchange=True)), ("adaptive", dict(fixed_e
         # replicas must agree bit for bit across ranks
         ref = e_peer.params.clone(); dist.broadcast(ref, 0)
         rep = torch.equal(ref, e_peer.params)
-        good = err == 0 and rep and dmax <= 1e-7 and worst < 3e-3 * cfg.learning_rate * (it + 1) + 12 * cfg.learning_rate
+        good = err == 0 and rep and dmax <= (1e-7 if world <= 2 else 12 * cfg.learning_rate) and worst < 3e-3 * cfg.learning_rate * (it + 1) + 12 * cfg.learning_rate
         ok = ok and good
         if rank == 0:
             print("%s it%d: peer_error=%d replicas_identical=%s peer==nccl bitwise=%s (max diff %.2e) max|param - oracle|=%.3e -> %s" % (
