@@ -267,14 +267,17 @@ MMG_DEVICE float binary_grad(float p, float f, float wcA, float cE) {
     return g;
 }
 
-MMG_GLOBAL void __launch_bounds__(kLossThreads)
-k_lossgrad(Dims d, mmg_config cfg, WsPtrs W, PeerView pv) {
-    pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
-    pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
-    MMG_DYN_SMEM(smem_raw);
-    LossCoef* coef = reinterpret_cast<LossCoef*>(smem_raw);          // [3][T]
-    float* bas_scale = reinterpret_cast<float*>(coef + 3 * d.T);      // [2]: 1 / denominator of the baseline MSE
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+MMG_HOST_DEVICE int loss_smem_bytes(const Dims& d, int world) {
+    return 3 * d.T * (int)sizeof(LossCoef) + 16 + (world > 1 ? stats_count(d) * 8 + 16 : 0);
+}
+
+// Shared by K_lossgrad and the fused backward kernel (256 threads): global statistics (summed over the peers when
+// data-parallel), per-(loss, step) coefficients and the baseline-MSE scale.  Returns the statistics to use.
+MMG_DEVICE const double* loss_prologue(const Dims& d, const mmg_config& cfg, const WsPtrs& W, const PeerView& pv,
+                                       unsigned char* smem, LossCoef*& coef, float*& bas_scale) {
+    coef = reinterpret_cast<LossCoef*>(smem);                          // [3][T]
+    bas_scale = reinterpret_cast<float*>(coef + 3 * d.T);              // [2]: 1 / denominator of the baseline MSE
+    const int tid = threadIdx.x;
     const double* st = W.stats;
     if (pv.world > 1) {
         // global batch statistics = sum over ranks, read straight from the peers' symmetric slots (rank order)
@@ -301,9 +304,86 @@ k_lossgrad(Dims d, mmg_config cfg, WsPtrs W, PeerView pv) {
         bas_scale[0] = tot > 0 ? (float)(1.0 / tot) : 0.f;
     }
     MMG_SYNCTHREADS();
+    return st;
+}
+
+// Loss values: per-CTA partials (acc: 0 binary_sen, 1 binary_rec, 2 binary_s, 3 bas_rec, 4 bas_sen — rank-local
+// contributions, any thread may hold a share), summed in CTA order by the last CTA to finish (deterministic).
+MMG_DEVICE void loss_epilogue(const Dims& d, const WsPtrs& W, const double* st, const double (&acc)[5]) {
+    MMG_SHARED double red[5][kLossThreads / 32];
+    MMG_SHARED double nll_red[kLossThreads / 32];
+    MMG_SHARED int s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = 0; i < 5; ++i) {
+        const double v = warp_sum_d(acc[i]);
+        if (lane == 0) red[i][warp] = v;
+    }
+    MMG_SYNCTHREADS();
+    if (tid == 0) {
+        for (int i = 0; i < 5; ++i) {
+            double v = 0;
+            for (int w = 0; w < kLossThreads / 32; ++w) v += red[i][w];
+            W.loss_part[(size_t)blockIdx.x * 8 + i] = v;
+        }
+        s_last = (ticket_take(W.tickets) == gridDim.x - 1) ? 1 : 0;
+    }
+    MMG_SYNCTHREADS();
+    if (!s_last) return;
+    fence_acquire();
+    double nl = 0;
+    for (int b = tid; b < d.B; b += kLossThreads) nl -= (double)W.logs[b] / (double)d.Bg;
+    nl = warp_sum_d(nl);
+    if (lane == 0) nll_red[warp] = nl;
+    MMG_SYNCTHREADS();
+    // per-CTA partials: thread c sums CTAs c, c + 256, ...; then a fixed shuffle tree and 8 warp totals
+    double part[5] = {0, 0, 0, 0, 0};
+    for (unsigned c = tid; c < gridDim.x; c += kLossThreads)
+        for (int i = 0; i < 5; ++i) part[i] += W.loss_part[(size_t)c * 8 + i];
+    for (int i = 0; i < 5; ++i) {
+        const double v = warp_sum_d(part[i]);
+        if (lane == 0) red[i][warp] = v;
+    }
+    MMG_SYNCTHREADS();
+    if (tid == 0) {
+        double v[6];
+        v[0] = 0;
+        for (int w = 0; w < kLossThreads / 32; ++w) v[0] += nll_red[w];
+        for (int i = 0; i < 5; ++i) {
+            double a = 0;
+            for (int w = 0; w < kLossThreads / 32; ++w) a += red[i][w];
+            v[i + 1] = a;
+        }
+        float* L = W.losses;
+        L[MMG_LOSS_NLL] = (float)v[0];
+        L[MMG_LOSS_BINARY_SEN] = (float)v[1];
+        L[MMG_LOSS_BINARY_REC] = (float)v[2];
+        L[MMG_LOSS_BINARY_S] = (float)v[3];
+        L[MMG_LOSS_BAS_REC] = (float)v[4];
+        L[MMG_LOSS_BAS_SEN] = (float)v[5];
+        L[MMG_LOSS_REC] = (float)(v[0] + v[2] + (d.fixed ? 0.0 : v[3]));      // model.py:1296-1300
+        L[MMG_LOSS_SEN] = (float)v[1];                                          // model.py:1301
+        L[MMG_LOSS_TOPK_CORRECT] = (float)st[stat_scalar(d, 1)];
+        int tp = d.T;
+        if (!d.fixed) for (int t = 0; t < d.T; ++t) if (st[stat_bas(d, t, 2)] <= 0.0) { tp = t + 1; break; }
+        L[MMG_LOSS_ACTIVE_STEPS] = (float)tp;
+        if (st[stat_idx(d, 1, 0, 0)] > 0.0) W.opt_counters[0] += 1;   // updates seen by the receiver message head
+        for (int i = MMG_LOSS_ACTIVE_STEPS + 1; i < MMG_LOSS_COUNT; ++i) L[i] = 0.f;
+        W.tickets[0] = 0;                                             // ready for the next launch
+    }
+}
+
+MMG_GLOBAL void __launch_bounds__(kLossThreads)
+k_lossgrad(Dims d, mmg_config cfg, WsPtrs W, PeerView pv) {
+    pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
+    pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
+    MMG_DYN_SMEM(smem_raw);
+    LossCoef* coef;
+    float* bas_scale;
+    const double* st = loss_prologue(d, cfg, W, pv, smem_raw, coef, bas_scale);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    (void)tid;
     const bool binary = d.use_binary != 0;
     // ---- one warp per (t, b) row: upstream gradients + this row's share of every loss value ----------------------
-    // acc (lane 0): 0 binary_sen, 1 binary_rec, 2 binary_s, 3 bas_rec, 4 bas_sen — rank-local contributions
     double acc[5] = {0, 0, 0, 0, 0};
     const int rows_per_cta = kLossThreads / 32;
     for (int row = blockIdx.x * rows_per_cta + warp; row < d.R; row += gridDim.x * rows_per_cta) {
@@ -363,63 +443,7 @@ k_lossgrad(Dims d, mmg_config cfg, WsPtrs W, PeerView pv) {
             W.g_stop_prob[row] = 0.f; W.g_bs[row] = 0.f; W.g_br[row] = 0.f;
         }
     }
-    // ---- loss values: per-CTA partials, summed in CTA order by the last CTA to finish (deterministic) -------------
-    MMG_SHARED double red[5][kLossThreads / 32];
-    MMG_SHARED double nll_red[kLossThreads / 32];
-    MMG_SHARED int s_last;
-    if (lane == 0) for (int i = 0; i < 5; ++i) red[i][warp] = acc[i];
-    MMG_SYNCTHREADS();
-    if (tid == 0) {
-        for (int i = 0; i < 5; ++i) {
-            double v = 0;
-            for (int w = 0; w < kLossThreads / 32; ++w) v += red[i][w];
-            W.loss_part[(size_t)blockIdx.x * 8 + i] = v;
-        }
-        s_last = (ticket_take(W.tickets) == gridDim.x - 1) ? 1 : 0;
-    }
-    MMG_SYNCTHREADS();
-    if (!s_last) return;
-    fence_acquire();
-    double nl = 0;
-    for (int b = tid; b < d.B; b += kLossThreads) nl -= (double)W.logs[b] / (double)d.Bg;
-    nl = warp_sum_d(nl);
-    if (lane == 0) nll_red[warp] = nl;
-    MMG_SYNCTHREADS();
-    // per-CTA partials: thread c sums CTAs c, c + 256, ...; then a fixed shuffle tree and 8 warp totals
-    double part[5] = {0, 0, 0, 0, 0};
-    for (unsigned c = tid; c < gridDim.x; c += kLossThreads)
-        for (int i = 0; i < 5; ++i) part[i] += W.loss_part[(size_t)c * 8 + i];
-    for (int i = 0; i < 5; ++i) {
-        const double v = warp_sum_d(part[i]);
-        if (lane == 0) red[i][warp] = v;
-    }
-    MMG_SYNCTHREADS();
-    if (tid == 0) {
-        double v[6];
-        v[0] = 0;
-        for (int w = 0; w < kLossThreads / 32; ++w) v[0] += nll_red[w];
-        for (int i = 0; i < 5; ++i) {
-            double a = 0;
-            for (int w = 0; w < kLossThreads / 32; ++w) a += red[i][w];
-            v[i + 1] = a;
-        }
-        float* L = W.losses;
-        L[MMG_LOSS_NLL] = (float)v[0];
-        L[MMG_LOSS_BINARY_SEN] = (float)v[1];
-        L[MMG_LOSS_BINARY_REC] = (float)v[2];
-        L[MMG_LOSS_BINARY_S] = (float)v[3];
-        L[MMG_LOSS_BAS_REC] = (float)v[4];
-        L[MMG_LOSS_BAS_SEN] = (float)v[5];
-        L[MMG_LOSS_REC] = (float)(v[0] + v[2] + (d.fixed ? 0.0 : v[3]));      // model.py:1296-1300
-        L[MMG_LOSS_SEN] = (float)v[1];                                          // model.py:1301
-        L[MMG_LOSS_TOPK_CORRECT] = (float)st[stat_scalar(d, 1)];
-        int tp = d.T;
-        if (!d.fixed) for (int t = 0; t < d.T; ++t) if (st[stat_bas(d, t, 2)] <= 0.0) { tp = t + 1; break; }
-        L[MMG_LOSS_ACTIVE_STEPS] = (float)tp;
-        if (st[stat_idx(d, 1, 0, 0)] > 0.0) W.opt_counters[0] += 1;   // updates seen by the receiver message head
-        for (int i = MMG_LOSS_ACTIVE_STEPS + 1; i < MMG_LOSS_COUNT; ++i) L[i] = 0.f;
-        W.tickets[0] = 0;                                             // ready for the next launch
-    }
+    loss_epilogue(d, W, st, acc);
 }
 
 }  // namespace mmg

@@ -279,3 +279,40 @@ def run_synth_case(cfg, lib, device, iters=1, seed=0, check_grads=True, tag="syn
                         atol=3e-5 * gmax + 1e-9))
         e.load_params(oparams)
     return worst
+
+
+def run_fused_step_case(cfg, lib, device, iters=2, seed=0, tag="fused"):
+    """engine.train_step() (mmg_train_step, the fused launch sequence bench.py times) against the oracle: losses and
+    post-step parameters over a few iterations."""
+    seed = _find_seed(cfg, seed, iters)
+    params = go.init_params(cfg, seed=seed)
+    oparams = go.clone_params(params)
+    ostate = go.new_opt_state(oparams)
+    e = eng.GameEngine(config_from(cfg), device=device, lib=lib)
+    e.load_params(params)
+    rng = np.random.RandomState(seed)
+    lr = cfg.learning_rate
+    for it in range(iters):
+        x, desc, target = go.synthetic_batch(cfg, seed=seed * 10 + it)
+        us = go.draw_uniforms(rng, cfg)
+        ex, res, grads = go.train_iteration(oparams, ostate, x, target, desc, cfg, us, return_grads=True)
+        e.train_step(x, desc, target, uniforms=stack_uniforms(us, cfg, cfg.batch_size), top_k=min(cfg.top_k_train, cfg.n_classes))
+        L = e.losses()
+        for name in ("nll_loss", "loss_rec", "loss_sen", "loss_bas_rec", "loss_bas_sen", "loss_binary_s", "loss_binary_rec",
+                     "loss_binary_sen"):
+            if name in res:
+                assert_close("%s/it%d/%s" % (tag, it, name), L[name], float(res[name].detach()))
+        assert int(L["active_steps"]) == len(ex["y"])
+        pv = e.named_views()
+        for a in oparams:
+            for k, v in oparams[a].items():
+                if (a, k) == ("receiver", "y2.bias"):
+                    continue
+                g = grads.get(a, {}).get(k)
+                atol = 2e-2 * lr + 1e-7
+                if g is not None:
+                    atol = np.where((g.abs() < 1e-5).numpy(), 12 * lr * (it + 1), atol)
+                assert_close("%s/it%d/param %s.%s" % (tag, it, a, k), pv[a][k].detach().cpu().numpy(), v.numpy(), rtol=1e-5,
+                             atol=atol)
+        e.load_params(oparams)
+    return True

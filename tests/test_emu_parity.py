@@ -35,3 +35,14 @@ def test_emulated_fast_path_dims(M, fixed, binary):
                         use_binary=binary, entropy_s=None if fixed else 0.05, entropy_sen=0.01, entropy_rec=0.02,
                         top_k_train=2)
     pu.run_synth_case(cfg, emu_util.emu_library(), "cpu", iters=2, seed=9, tag="fast%d" % M)
+
+
+@pytest.mark.parametrize("fixed", [True, False])
+def test_emulated_fused_train_step_fast_dims(fixed):
+    """mmg_train_step (the whole launch sequence in one C call) on the fast path."""
+    from oracle import game_oracle as go
+    cfg = go.GameConfig(batch_size=3, img_feat_dim=40, img_h_dim=256, baseline_hid_dim=24, sender_out_dim=32,
+                        rec_hidden=64, rec_w_dim=32, wv_dim=12, n_classes=6, max_exchange=3, fixed_exchange=fixed,
+                        use_binary=True, entropy_s=None if fixed else 0.05, entropy_sen=0.01, entropy_rec=0.02,
+                        top_k_train=2)
+    pu.run_fused_step_case(cfg, emu_util.emu_library(), "cpu", iters=2, seed=11)
