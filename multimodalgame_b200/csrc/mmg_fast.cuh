@@ -99,9 +99,10 @@ MMG_HOST_DEVICE int fast_fwd_state_floats(int BT, int M, int D, int T) {
            align4(2 * BT) + 8;
 }
 
-MMG_DEVICE void fma4(const float4& w, const float4& x, float4& acc) {
-    acc.x = fmaf(w.x, x.x, acc.x); acc.y = fmaf(w.y, x.y, acc.y);
-    acc.z = fmaf(w.z, x.z, acc.z); acc.w = fmaf(w.w, x.w, acc.w);
+MMG_DEVICE void fma4(const float4& w, const float4& x, float4& acc) {      // two packed fp32x2 FMAs (FFMA2)
+    const float2 lo = ffma2(make_float2(w.x, w.y), make_float2(x.x, x.y), make_float2(acc.x, acc.y));
+    const float2 hi = ffma2(make_float2(w.z, w.w), make_float2(x.z, x.w), make_float2(acc.z, acc.w));
+    acc.x = lo.x; acc.y = lo.y; acc.z = hi.x; acc.w = hi.y;
 }
 MMG_DEVICE float hsum4(const float4& a) { return (a.x + a.y) + (a.z + a.w); }
 MMG_DEVICE float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }

@@ -45,6 +45,8 @@ MMG_DEVICE float half_warp_sum(float v) {
 }
 
 MMG_DEVICE float shfl_xor_f(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+// Blackwell packed fp32: one FFMA2 instruction = two IEEE-rn fused multiply-adds (bitwise equal to two fmaf)
+MMG_DEVICE float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 // Short-latency transcendentals for the recurrent fast path (MUFU.EX2 / MUFU.RCP; absolute error ~2e-7, far inside
 // the 1e-4 parity bar).  The generic kernels keep the libm-accurate versions.
 MMG_DEVICE float fast_exp(float x) { return __expf(x); }
@@ -175,6 +177,10 @@ MMG_DEVICE float4 ldg4(const float4* p) { return __ldg(p); }
 struct float4 {
     float x, y, z, w;
 };
+struct float2 {
+    float x, y;
+};
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 struct dim3 {
     unsigned x, y, z;
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
@@ -238,6 +244,7 @@ MMG_DEVICE float half_warp_sum(float v) {
     return v;
 }
 MMG_DEVICE float shfl_xor_f(float v, int m) { return (float)emu::shfl_xor(v, m); }
+MMG_DEVICE float2 ffma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
 MMG_DEVICE float fast_exp(float x) { return expf(x); }
 MMG_DEVICE float fast_rcp(float x) { return 1.0f / x; }
 MMG_DEVICE float fast_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
