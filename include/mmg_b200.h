@@ -153,6 +153,9 @@ typedef struct mmg_workspace_layout {
     int64_t g_bs;        /* (T,B)   */
     int64_t g_br;        /* (T,B)   */
     int64_t rng_state;   /* uint64[2]: {seed, iteration counter} of the on-device Philox sampler */
+    int64_t opt_counters; /* int64[4]: [0] = updates that reached the receiver message head (w_h, w_d, w): torch.optim keeps
+                             one step count per parameter and skips parameters without a gradient (one-step conversations),
+                             so Adam's bias correction for these tensors uses this count.  Part of a checkpoint. */
 } mmg_workspace_layout;
 
 enum {

@@ -53,7 +53,7 @@ class ParamLayout(C.Structure):
 _WS_FIELDS = ("total_bytes", "sen_feats", "sen_probs", "rec_feats", "rec_probs", "stop_feat", "stop_prob", "y",
               "stop_mask", "bs", "br", "h_x", "h_z", "h_w", "losses", "ystep", "outp", "logs", "argmax", "stats",
               "stats_count", "grad_norms", "g_sen_probs", "g_rec_probs", "g_stop_prob", "g_outp", "g_bs", "g_br",
-              "rng_state")
+              "rng_state", "opt_counters")
 
 
 class WorkspaceLayout(C.Structure):

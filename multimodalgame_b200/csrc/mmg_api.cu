@@ -165,6 +165,7 @@ static void ws_layout(const Dims& d, Ws* w) {
     w->loss_part = take(c, (int64_t)(2 * B > kLossCtasMax ? 2 * B : kLossCtasMax) * 8 * 8);   // K_lossgrad CTAs, or 2 CTAs per example (fused backward)
     w->tickets = take(c, 8 * 4);
     w->opt_counters = take(c, 4 * 8);
+    p.opt_counters = w->opt_counters;
     p.total_bytes = c;
 }
 

@@ -531,6 +531,105 @@ def eval_dev(dev_file, batch_size, epoch, shuffle, cuda, top_k, sender, receiver
     return float(correct) / max(total, 1.0), extra
 
 
+# ------------------------------------------------------------------------------------------------------------
+# checkpoints (misc.py:42-92): same dictionary layout {data, optimizers, models}, tensors always saved on the CPU
+# ------------------------------------------------------------------------------------------------------------
+def recursively_set_device(inp, gpu):
+    """misc.py:42-55."""
+    if hasattr(inp, "keys"):
+        for k in inp.keys():
+            inp[k] = recursively_set_device(inp[k], gpu)
+    elif isinstance(inp, list):
+        return [recursively_set_device(ii, gpu) for ii in inp]
+    elif isinstance(inp, tuple):
+        return tuple(recursively_set_device(ii, gpu) for ii in inp)
+    elif hasattr(inp, "cpu"):
+        inp = inp.cuda() if gpu >= 0 else inp.cpu()
+    return inp
+
+
+def torch_save(filename, data, models_dict, optimizers_dict, gpu):
+    """misc.py:58-75.  `optimizers_dict` values are torch.optim objects or `FusedOptimizer` views."""
+    models_to_save = {k: recursively_set_device({kk: vv.detach().clone() for kk, vv in v.state_dict().items()}, gpu=-1)
+                      for k, v in models_dict.items()}
+    optimizers_to_save = {k: recursively_set_device(v.state_dict(), gpu=-1) for k, v in optimizers_dict.items()}
+    torch.save({"data": data, "optimizers": optimizers_to_save, "models": models_to_save}, filename)
+
+
+def torch_load(filename, models_dict, optimizers_dict):
+    """misc.py:78-92.  Module parameters are views of the engine's flat buffer: loading copies INTO them."""
+    filename = os.path.expanduser(filename)
+    if not os.path.exists(filename):
+        raise Exception("File does not exist: " + filename)
+    checkpoint = torch.load(filename, weights_only=False)
+    for k, v in models_dict.items():
+        with torch.no_grad():
+            for key, p in v.named_parameters():
+                p.copy_(checkpoint["models"][k][key].to(p.device))
+    for k, v in optimizers_dict.items():
+        v.load_state_dict(checkpoint["optimizers"][k])
+    return checkpoint["data"]
+
+
+class FusedOptimizer(object):
+    """torch.optim-shaped view (state_dict / load_state_dict) of ONE module's slice of the fused optimizer state that
+    `train_step()` keeps in the engine, so the reference's checkpoint code (model.py:1139-1156,1569-1584) keeps working
+    with `optimizers_dict = dict(optimizer_rec=FusedOptimizer(engine, "receiver"), ...)`.  The layout follows
+    torch.optim.RMSprop / Adam: state[i] for the i-th parameter of the module in `parameters()` order."""
+
+    def __init__(self, engine, agent):
+        self.engine, self.agent = engine, agent
+        self.keys = [key for a, key in capi.PARAM_NAMES if a == agent]
+        # parameters() order = state_dict order (direct parameters first), which is how PARAM_NAMES is laid out
+        self.optim = {v: k for k, v in capi.OPTIM.items()}[int(engine.cfg.optim_type)]
+
+    def _views(self):
+        e = self.engine
+        s1 = e.named_views(e.state1)[self.agent]
+        s2 = e.named_views(e.state2)[self.agent] if e.state2 is not None else None
+        return s1, s2
+
+    def state_dict(self):
+        e = self.engine
+        s1, s2 = self._views()
+        state = {}
+        head_steps = float(e.ws("opt_counters", (4,), torch.int64)[0]) if self.agent == "receiver" else 0.0
+        for i, key in enumerate(self.keys):
+            in_head = self.agent == "receiver" and key.split(".")[0] in ("w_h", "w_d", "w")
+            st = {"step": torch.tensor(head_steps if in_head else float(e.step))}
+            if self.optim == "RMSprop":
+                st["square_avg"] = s1[key].detach().clone()
+            elif self.optim == "Adam":
+                st["exp_avg"] = s2[key].detach().clone()
+                st["exp_avg_sq"] = s1[key].detach().clone()
+            state[i] = st
+        group = dict(lr=float(e.cfg.learning_rate), params=list(range(len(self.keys))))
+        if self.optim == "RMSprop":
+            group.update(alpha=0.99, eps=1e-8, weight_decay=0, momentum=0, centered=False)
+        elif self.optim == "Adam":
+            group.update(betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False)
+        return {"state": state, "param_groups": [group], "fused": {"optim": self.optim, "agent": self.agent}}
+
+    def load_state_dict(self, sd):
+        e = self.engine
+        s1, s2 = self._views()
+        with torch.no_grad():
+            for i, key in enumerate(self.keys):
+                st = sd["state"].get(i, sd["state"].get(str(i)))
+                if st is None:
+                    continue
+                if self.optim == "RMSprop":
+                    s1[key].copy_(st["square_avg"].to(s1[key].device).reshape(s1[key].shape))
+                elif self.optim == "Adam":
+                    s2[key].copy_(st["exp_avg"].to(s2[key].device).reshape(s2[key].shape))
+                    s1[key].copy_(st["exp_avg_sq"].to(s1[key].device).reshape(s1[key].shape))
+                if "step" in st:
+                    if self.agent == "receiver" and key.split(".")[0] in ("w_h", "w_d", "w"):
+                        e.ws("opt_counters", (4,), torch.int64)[0] = int(float(st["step"]))
+                    else:
+                        e.step = int(float(st["step"]))
+
+
 def train_step(sender, receiver, baseline_sen, baseline_rec, exchange_args, group=None):
     """The whole iteration of run() (model.py:1240-1339) fused on the device: conversation, the five losses, backward,
     per-module clip_grad_norm(1.) and the optimizer step.  Returns the engine (losses()/outputs() read results).

@@ -238,3 +238,46 @@ def run_eval_dev_case(case, device, top_k=2):
     assert np.array_equal(extra["confusion_matrix"], cm)
     M.FLAGS.bit_flip = False
     M.FLAGS.corrupt_region = None
+
+
+def run_checkpoint_roundtrip(case, device, tmpdir):
+    """train 2 iterations -> torch_save (reference dictionary layout) -> fresh modules -> torch_load -> third iteration must
+    equal the uninterrupted run bit for bit (module parameters AND fused optimizer state travel through the file)."""
+    import os
+    z, cfg = gu.load(case)
+    set_flags(cfg)
+    params = gu.params_at(z, "P0")
+
+    def fresh():
+        M._BINDINGS.clear()
+        mods = build_modules(cfg, params, device)
+        return mods
+
+    def step(mods, it):
+        x, desc, target = gu.batch_at(z, it % int(z["iters"]))
+        us = gu.uniforms_at(z, it % int(z["iters"]), cfg)
+        uni = tuple(u.to(device) for u in pu.stack_uniforms(us, cfg, cfg.batch_size))
+        return M.train_step(mods["sender"], mods["receiver"], mods["baseline_sen"], mods["baseline_rec"],
+                            dict(data=x.to(device), target=target.to(device), desc=desc.to(device), train=True, uniforms=uni))
+
+    names = dict(receiver="optimizer_rec", sender="optimizer_sen", baseline_rec="optimizer_bas_rec", baseline_sen="optimizer_bas_sen")
+    a = fresh()
+    for it in range(3):
+        ea = step(a, it)
+    want = {k: {n: p.detach().cpu().clone() for n, p in m.named_parameters()} for k, m in a.items()}
+    b = fresh()
+    for it in range(2):
+        eb = step(b, it)
+    path = os.path.join(tmpdir, "ckpt.pt")
+    M.torch_save(path, dict(step=2, best_dev_acc=0.5), b, {names[k]: M.FusedOptimizer(eb, k) for k in names}, -1)
+    ck = torch.load(path, weights_only=False)
+    assert sorted(ck.keys()) == ["data", "models", "optimizers"]                        # misc.py:68-72
+    assert list(ck["models"]["receiver"].keys()) == REF_KEYS["receiver"]
+    c = fresh()
+    ec = step(c, 0)                    # binds modules to a new engine (state gets overwritten by the load)
+    data = M.torch_load(path, c, {names[k]: M.FusedOptimizer(ec, k) for k in names})
+    assert data["step"] == 2
+    ec = step(c, 2)
+    for k, m in c.items():
+        for n, p in m.named_parameters():
+            assert torch.equal(p.detach().cpu(), want[k][n]), (k, n)

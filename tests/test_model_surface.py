@@ -31,6 +31,11 @@ def test_eval_dev_statistics(case):
     su.run_eval_dev_case(case, "cpu")
 
 
+@pytest.mark.parametrize("case", ["fixed_small", "adaptive_b1_adam"])
+def test_checkpoint_roundtrip_reference_layout(case, tmp_path):
+    su.run_checkpoint_roundtrip(case, "cpu", str(tmp_path))
+
+
 def test_unsupported_flags_raise():
     from tests import golden_util as gu
     z, cfg = gu.load("fixed_small")
