@@ -64,7 +64,10 @@ typedef struct mmg_config {
     float learning_rate;    /* model.py:1728 */
     float max_norm;         /* clip_grad_norm(..., max_norm=1.) model.py:1310 */
     int32_t ignore_receiver; /* model.py:1703,470-472 */
-    int32_t reserved[7];
+    int32_t has_flipout_sen, has_flipout_rec; /* 0 when the flag is None (model.py:1710-1711) */
+    int32_t flipout_dev;     /* model.py:1712: flip in eval mode too */
+    float flipout_sen, flipout_rec;           /* bit-flip probabilities (model.py:233-234,467-468,554-568) */
+    int32_t reserved[2];
 } mmg_config;
 
 /* ---- parameter layout -------------------------------------------------------------------------------
@@ -186,6 +189,10 @@ typedef struct mmg_inputs {
     const float* d_h0;           /* (B,Hr) initial receiver state or NULL (zeros, model.py:336-337) */
     int32_t top_k;               /* FLAGS.top_k_train */
     int32_t train;               /* exchange_args["train"] model.py:767 */
+    /* optional float64 uniforms of the flipout draws, (T,B,M) each, consumed right after the message draw of the same
+     * agent (model.py:233-234 after 227; 467-468 after 460); NULL: on-device Philox stream */
+    const double* d_u_flip_sen;
+    const double* d_u_flip_rec;
 } mmg_inputs;
 
 int mmg_abi_version(void);

@@ -41,7 +41,8 @@ class Config(C.Structure):
         "baseline_hid", "max_exchange", "use_binary", "fixed_exchange", "s_prob_prod", "optim_type",
         "has_entropy_s", "has_entropy_sen", "has_entropy_rec")] + [
         (n, C.c_float) for n in ("entropy_s", "entropy_sen", "entropy_rec", "first_rec", "learning_rate", "max_norm")
-    ] + [("ignore_receiver", C.c_int32), ("reserved", C.c_int32 * 7)]
+    ] + [("ignore_receiver", C.c_int32), ("has_flipout_sen", C.c_int32), ("has_flipout_rec", C.c_int32),
+         ("flipout_dev", C.c_int32), ("flipout_sen", C.c_float), ("flipout_rec", C.c_float), ("reserved", C.c_int32 * 2)]
 
 
 class ParamLayout(C.Structure):
@@ -63,7 +64,8 @@ class WorkspaceLayout(C.Structure):
 class Inputs(C.Structure):
     _fields_ = [("d_x", C.c_void_p), ("d_desc", C.c_void_p), ("d_target", C.c_void_p), ("d_u_sen", C.c_void_p),
                 ("d_u_stop", C.c_void_p), ("d_u_rec", C.c_void_p), ("d_corrupt_mask", C.c_void_p),
-                ("d_h0", C.c_void_p), ("top_k", C.c_int32), ("train", C.c_int32)]
+                ("d_h0", C.c_void_p), ("top_k", C.c_int32), ("train", C.c_int32), ("d_u_flip_sen", C.c_void_p),
+                ("d_u_flip_rec", C.c_void_p)]
 
 
 MMG_MAX_PEERS = 8

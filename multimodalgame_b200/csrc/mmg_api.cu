@@ -205,6 +205,7 @@ static ExchangeInputs resolve_inputs(const mmg_inputs* in) {
     ExchangeInputs e;
     e.x = in->d_x; e.desc = in->d_desc; e.target = (const long long*)in->d_target;
     e.u_sen = in->d_u_sen; e.u_stop = in->d_u_stop; e.u_rec = in->d_u_rec;
+    e.u_flip_sen = in->d_u_flip_sen; e.u_flip_rec = in->d_u_flip_rec;
     e.corrupt_mask = in->d_corrupt_mask; e.h0 = in->d_h0; e.top_k = in->top_k; e.train = in->train;
     return e;
 }
@@ -322,7 +323,7 @@ template <int BT, int M, bool SS>
 static int launch_fwd_fast_one(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const FastFwdArgs& fa, const Plan& pl,
                                cudaStream_t st) {
     const bool perf = in.train && d.use_binary && in.u_sen == nullptr && in.corrupt_mask == nullptr && !d.ignore_receiver &&
-                      d.B % BT == 0;
+                      d.flip_sen < 0.f && d.flip_rec < 0.f && d.B % BT == 0;
     return perf ? launch_fwd_fast_mode<BT, M, SS, true>(d, W, in, fa, pl, st)
                 : launch_fwd_fast_mode<BT, M, SS, false>(d, W, in, fa, pl, st);
 }

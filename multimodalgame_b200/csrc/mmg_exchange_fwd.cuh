@@ -72,6 +72,20 @@ MMG_DEVICE float draw_bit(const double* u, size_t uidx, float p, unsigned long l
     return (r[col & 3] < p) ? 1.f : 0.f;
 }
 
+// flipout (model.py:554-568): |bit - 1[u < p_flip]| with a second uniform per bit, drawn right after the message draw.
+// `agent`: 0 sender, 1 receiver (separate halves of Philox stream 4 t + 3).
+MMG_DEVICE float flip_bit(float bit, float p_flip, const double* u, size_t uidx, unsigned long long seed,
+                          unsigned long long iter, int t, int agent, unsigned row, unsigned col) {
+    float m;
+    if (u != nullptr) m = (u[uidx] < (double)p_flip) ? 1.f : 0.f;
+    else {
+        float r[4];
+        philox_uniform4(seed, iter, t * 4 + 3, row * 65536u + (agent ? 32768u : 0u) + (col >> 2), r);
+        m = (r[col & 3] < p_flip) ? 1.f : 0.f;
+    }
+    return fabsf(bit - m);
+}
+
 MMG_HOST_DEVICE int fwd_state_floats(const Dims& d, int BT) {
     // hx, a, win, z, pz, h, head, yv, q, hwr, partA, partB, misc
     const int HiP = align4(d.Hi), MP = d.M4 * 4, HrP = d.Hr4 * 4;
@@ -184,7 +198,7 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
     MMG_SYNCTHREADS();
 
     unsigned long long seed = 0, iter = 0;
-    if (train && in.u_sen == nullptr) { seed = W.rng_state[0]; iter = W.rng_state[1]; }
+    if ((train && in.u_sen == nullptr) || d.flip_sen >= 0.f || d.flip_rec >= 0.f) { seed = W.rng_state[0]; iter = W.rng_state[1]; }
 
     for (int t = 0; t < d.T; ++t) {
         // ---- S1: sender code term W_code . w_prev (model.py:207); step 0 uses the constant hw0 (199-200) ----
@@ -243,6 +257,8 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
             } else {
                 zval = logit;
             }
+            if (binary && d.flip_sen >= 0.f && (train || d.flipout_dev) && b < d.B)
+                zval = flip_bit(zval, d.flip_sen, in.u_flip_sen, row * d.M + j, seed, iter, t, 0, b + row_offset, j);
             if (in.corrupt_mask != nullptr) zval = fabsf(zval - in.corrupt_mask[j]);
             zv[bt * MP + j] = zval;
             pv[bt * MP + j] = p;
@@ -394,6 +410,8 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
                 p = sigmoidf_(logit);
                 if (train) wv = (b < d.B) ? draw_bit(in.u_rec, row * d.M + j, p, seed, iter, t * 4 + 2, b + row_offset, j) : 0.f;
                 else       wv = rintf(p);
+                if (d.flip_rec >= 0.f && (train || d.flipout_dev) && b < d.B)
+                    wv = flip_bit(wv, d.flip_rec, in.u_flip_rec, row * d.M + j, seed, iter, t, 1, b + row_offset, j);
                 if (d.ignore_receiver) wv = 0.f;
             } else {
                 wv = logit;

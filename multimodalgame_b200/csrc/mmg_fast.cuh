@@ -186,6 +186,11 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
     const bool own_draws = kPerf ? true : (train && in.u_sen == nullptr);   // on-device Philox stream (else: injected float64 uniforms)
     const float* corrupt_mask = kPerf ? nullptr : in.corrupt_mask;
     const bool ignore_receiver = kPerf ? false : d.ignore_receiver != 0;
+    // flipout noise (model.py:233-234,467-468): never part of the kPerf instantiation
+    const bool flip_sen = !kPerf && binary && d.flip_sen >= 0.f && (train || d.flipout_dev);
+    const bool flip_rec = !kPerf && binary && d.flip_rec >= 0.f && (train || d.flipout_dev);
+    unsigned long long fseed = 0, fiter = 0;
+    if (flip_sen || flip_rec) { fseed = W.rng_state[0]; fiter = W.rng_state[1]; }
 
     // per-thread roles, fixed for the whole kernel (addresses hoisted out of the step loop)
     const int k4t = tid >> 2, p4 = tid & 3;                       // (hidden unit, K-quarter) pairs: GRU, W_hh, mix
@@ -385,6 +390,8 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
                     } else {
                         zval = logit;
                     }
+                    if (flip_sen && b < B)
+                        zval = flip_bit(zval, d.flip_sen, in.u_flip_sen, row * M + j, fseed, fiter, t, 0, b + row_offset, j);
                     if (corrupt_mask != nullptr) zval = fabsf(zval - corrupt_mask[j]);
                     zv[bt * M + j] = zval;
                     if (MMG_SAVE_OK(b)) {
@@ -594,6 +601,8 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
                         } else {
                             wv = rintf(p);
                         }
+                        if (flip_rec && b < B)
+                            wv = flip_bit(wv, d.flip_rec, in.u_flip_rec, row * M + j, fseed, fiter, t, 1, b + row_offset, j);
                         if (ignore_receiver) wv = 0.f;
                     } else {
                         wv = logit;

@@ -39,7 +39,7 @@ struct ExchangeInputs {       // device pointers of one exchange (mmg_inputs res
     const float* x;
     const float* desc;
     const long long* target;
-    const double *u_sen, *u_stop, *u_rec;
+    const double *u_sen, *u_stop, *u_rec, *u_flip_sen, *u_flip_rec;
     const float* corrupt_mask;
     const float* h0;
     int top_k, train;

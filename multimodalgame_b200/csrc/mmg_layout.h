@@ -14,6 +14,8 @@ struct Dims {
     int NH;       // stacked head rows: [y1.weight[:, :Hr] ; w_h.weight ; s.weight] = 2*Hr + 1
     int use_binary, fixed, s_prob_prod, ignore_receiver;
     float first_rec;
+    float flip_sen, flip_rec;   // flipout probabilities, < 0 = off (model.py:233-234,467-468)
+    int flipout_dev;
 };
 
 MMG_HOST_DEVICE Dims make_dims(const mmg_config& c) {
@@ -26,6 +28,9 @@ MMG_HOST_DEVICE Dims make_dims(const mmg_config& c) {
     d.use_binary = c.use_binary; d.fixed = c.fixed_exchange; d.s_prob_prod = c.s_prob_prod;
     d.ignore_receiver = c.ignore_receiver;
     d.first_rec = c.first_rec;
+    d.flip_sen = c.has_flipout_sen ? c.flipout_sen : -1.f;
+    d.flip_rec = c.has_flipout_rec ? c.flipout_rec : -1.f;
+    d.flipout_dev = c.flipout_dev;
     return d;
 }
 

@@ -18,7 +18,8 @@ from . import capi
 def make_config(batch, n_classes, img_feat_dim=4096, img_h_dim=100, baseline_hid_dim=500, sender_out_dim=50,
                 rec_hidden=128, rec_w_dim=50, wv_dim=100, max_exchange=3, fixed_exchange=True, use_binary=True,
                 entropy_s=None, entropy_sen=None, entropy_rec=None, first_rec=0.0, s_prob_prod=True,
-                learning_rate=1e-4, optim_type="RMSprop", ignore_receiver=False, batch_global=None, max_norm=1.0):
+                learning_rate=1e-4, optim_type="RMSprop", ignore_receiver=False, batch_global=None, max_norm=1.0,
+                flipout_sen=None, flipout_rec=None, flipout_dev=False):
     """Build the C config from reference flag names/defaults (model.py:1641-1741)."""
     assert sender_out_dim == rec_w_dim, \
         "Both sender and receiver should communicate with same dim vectors for now."   # model.py:1756
@@ -37,6 +38,9 @@ def make_config(batch, n_classes, img_feat_dim=4096, img_h_dim=100, baseline_hid
     c.has_entropy_rec, c.entropy_rec = int(entropy_rec is not None), float(entropy_rec or 0.0)
     c.first_rec, c.learning_rate, c.max_norm = float(first_rec), float(learning_rate), float(max_norm)
     c.ignore_receiver = int(bool(ignore_receiver))
+    c.has_flipout_sen, c.flipout_sen = int(flipout_sen is not None), float(flipout_sen or 0.0)     # model.py:1710-1712
+    c.has_flipout_rec, c.flipout_rec = int(flipout_rec is not None), float(flipout_rec or 0.0)
+    c.flipout_dev = int(bool(flipout_dev))
     return c
 
 
@@ -121,10 +125,10 @@ class GameEngine(object):
                 t = t.to(device=dev, dtype=dtype).contiguous()
             return t
         keep = [prep(x, torch.float32), prep(desc, torch.float32), prep(target, torch.int64)]
-        us = [None, None, None]
+        us = [None, None, None, None, None]       # sender, stop, receiver [, sender flipout, receiver flipout]
         if uniforms is not None:
-            us = [prep(u, torch.float64) for u in uniforms]
-        keep += us + [prep(corrupt_mask, torch.float32), prep(h0, torch.float32)]
+            us = [prep(u, torch.float64) for u in uniforms] + [None] * (5 - len(uniforms))
+        keep += us[:3] + [prep(corrupt_mask, torch.float32), prep(h0, torch.float32)] + us[3:]
         d = self.dims
         assert tuple(keep[0].shape) == (d["B"], d["F"]), (tuple(keep[0].shape), (d["B"], d["F"]))
         assert tuple(keep[1].shape) == (d["D"], d["WV"]), tuple(keep[1].shape)
@@ -133,6 +137,7 @@ class GameEngine(object):
         inp.d_x, inp.d_desc, inp.d_target = ptr(keep[0]), ptr(keep[1]), ptr(keep[2])
         inp.d_u_sen, inp.d_u_stop, inp.d_u_rec = ptr(keep[3]), ptr(keep[4]), ptr(keep[5])
         inp.d_corrupt_mask, inp.d_h0 = ptr(keep[6]), ptr(keep[7])
+        inp.d_u_flip_sen, inp.d_u_flip_rec = ptr(keep[8]), ptr(keep[9])
         inp.top_k, inp.train = int(top_k), int(bool(train))
         self._keep = keep      # keep the tensors alive until the next call
         return inp

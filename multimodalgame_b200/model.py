@@ -286,9 +286,8 @@ class _Binding(object):
             entropy_rec=_flag("entropy_rec"), first_rec=float(_flag("first_rec", 0) or 0),
             s_prob_prod=bool(_flag("s_prob_prod", True)), learning_rate=float(_flag("learning_rate", 1e-4)),
             optim_type=_flag("optim_type", "RMSprop"), ignore_receiver=bool(_flag("ignore_receiver", False)),
-            batch_global=batch_global)
-        if _flag("flipout_sen") is not None or _flag("flipout_rec") is not None:
-            _unsupported("-flipout_sen / -flipout_rec")
+            batch_global=batch_global, flipout_sen=_flag("flipout_sen"), flipout_rec=_flag("flipout_rec"),
+            flipout_dev=bool(_flag("flipout_dev", False)))
         self.engine = _engine.GameEngine(cfg, device=device, lib=_LIB_OVERRIDE)
         self.mods = mods
         self.key = None
@@ -322,7 +321,8 @@ _BINDINGS = {}
 def _binding_for(sender, receiver, baseline_sen, baseline_rec, B, D, device, batch_global=None):
     key = (id(sender), id(receiver), id(baseline_sen), id(baseline_rec), int(B), int(D), str(device),
            int(_flag("max_exchange", 3)), bool(_flag("fixed_exchange", True)), _flag("entropy_s"), _flag("entropy_sen"),
-           _flag("entropy_rec"), _flag("optim_type", "RMSprop"), float(_flag("learning_rate", 1e-4)), batch_global)
+           _flag("entropy_rec"), _flag("optim_type", "RMSprop"), float(_flag("learning_rate", 1e-4)), batch_global,
+           _flag("flipout_sen"), _flag("flipout_rec"), bool(_flag("flipout_dev", False)))
     b = _BINDINGS.get(key)
     if b is None:
         mods = dict(receiver=receiver, sender=sender, baseline_rec=baseline_rec, baseline_sen=baseline_sen)

@@ -37,7 +37,8 @@ class GameConfig(object):
                  sender_out_dim=50, rec_hidden=128, rec_w_dim=50, wv_dim=100, n_classes=30,
                  max_exchange=3, fixed_exchange=True, use_binary=True, entropy_s=None,
                  entropy_sen=None, entropy_rec=None, first_rec=0.0, s_prob_prod=True,
-                 learning_rate=1e-4, optim_type="RMSprop", top_k_train=6, ignore_receiver=False):
+                 learning_rate=1e-4, optim_type="RMSprop", top_k_train=6, ignore_receiver=False,
+                 flipout_sen=None, flipout_rec=None):
         assert sender_out_dim == rec_w_dim  # model.py:1756
         self.batch_size = batch_size
         self.img_feat_dim = img_feat_dim
@@ -60,6 +61,8 @@ class GameConfig(object):
         self.optim_type = optim_type
         self.top_k_train = top_k_train
         self.ignore_receiver = ignore_receiver
+        self.flipout_sen = flipout_sen      # model.py:1710-1711 (None = off)
+        self.flipout_rec = flipout_rec
 
     def as_dict(self):
         return dict(self.__dict__)
@@ -152,7 +155,13 @@ def _bernoulli(probs, u):
 # ------------------------------------------------------------------------------------------------
 # agents
 # ------------------------------------------------------------------------------------------------
-def sender_forward(P, x, w, t, cfg, train, u=None):
+def flipout(binary, p, u):
+    """model.py:554-568: |bit - 1[u < p]| with its own uniform draw."""
+    mask = torch.from_numpy((np.asarray(u, dtype=np.float64) < float(p)).astype("float32"))
+    return (binary - mask).abs()
+
+
+def sender_forward(P, x, w, t, cfg, train, u=None, u_flip=None):
     """Sender.forward default path (sender_mix='sum', no attention): model.py:195-238.
     Returns (message, probs_or_None, h_x)."""
     h_x = F.linear(x, P["image_layer.weight"], P["image_layer.bias"])          # :195
@@ -168,6 +177,8 @@ def sender_forward(P, x, w, t, cfg, train, u=None):
             msg = _bernoulli(probs, u)                                          # :225-227
         else:
             msg = torch.round(probs).detach()                                   # :229
+        if cfg.flipout_sen is not None and train:                               # :233-234 (flipout_dev not modelled)
+            msg = flipout(msg, cfg.flipout_sen, u_flip)
         return msg, probs, h_x
     return feats, None, h_x                                                     # :238
 
@@ -192,7 +203,7 @@ def gru_cell(P, z, h):
     return n + u * (h - n)
 
 
-def receiver_forward(P, z, desc, state, cfg, train, u_s=None, u_w=None):
+def receiver_forward(P, z, desc, state, cfg, train, u_s=None, u_w=None, u_flip=None):
     """Receiver.forward default path (no -desc_attn): model.py:333-342, 412-477.
     `state` = dict(h_z, s_prob_prod) mutated like the module attributes.
     Returns ((s_binary, s_prob), (w_feats, w_probs), y)."""
@@ -223,6 +234,8 @@ def receiver_forward(P, z, desc, state, cfg, train, u_s=None, u_w=None):
             w_feats = _bernoulli(w_probs, u_w)                                   # :458-460
         else:
             w_feats = torch.round(w_probs).detach()                              # :462
+        if cfg.flipout_rec is not None and train:                                # :467-468
+            w_feats = flipout(w_feats, cfg.flipout_rec, u_flip)
         if cfg.ignore_receiver:
             w_feats = torch.zeros_like(w_feats)                                  # :470-472
     else:
@@ -253,12 +266,13 @@ def exchange(params, x, desc, cfg, train, uniforms=None, break_early=False, corr
     state = dict(h_z=None, s_prob_prod=None)                                        # :798-799
     for t in range(cfg.max_exchange):                                               # :801
         z_r = w_binary
-        u = uniforms[t] if train else (None, None, None)
-        z_binary, z_probs, h_x = sender_forward(S, x, z_r.detach(), t, cfg, train, u[0])   # :807-811
+        u = tuple(uniforms[t]) if train else (None, None, None)
+        u = u + (None,) * (5 - len(u))          # (u_z, u_s, u_w [, u_flip_z, u_flip_w])
+        z_binary, z_probs, h_x = sender_forward(S, x, z_r.detach(), t, cfg, train, u[0], u[3])   # :807-811
         if corrupt_mask is not None:
             z_binary = (z_binary - corrupt_mask.view(1, -1)).abs()                  # :814-820
         (s_binary, s_prob), (w_binary, w_probs), outp = receiver_forward(
-            R, z_binary.detach(), desc.detach(), state, cfg, train, u[1], u[2])     # :826-829
+            R, z_binary.detach(), desc.detach(), state, cfg, train, u[1], u[2], u[4])     # :826-829
         if train:
             out["bs"].append(baseline_forward(params["baseline_sen"], h_x.detach(), z_r.detach(), None))   # :835-836
             out["br"].append(baseline_forward(params["baseline_rec"], None, z_binary.detach(),
@@ -481,7 +495,15 @@ def draw_uniforms(rng, cfg, B=None, steps=None):
     """Uniforms in the reference's consumption order from a numpy RandomState."""
     B = B or cfg.batch_size
     M = cfg.rec_w_dim
-    return [(rng.rand(B, M), rng.rand(B, 1), rng.rand(B, M)) for _ in range(steps or cfg.max_exchange)]
+    out = []
+    for _ in range(steps or cfg.max_exchange):      # reference draw order: z, [flip z], s, w, [flip w]
+        u_z = rng.rand(B, M)
+        u_fz = rng.rand(B, M) if cfg.flipout_sen is not None else None
+        u_s = rng.rand(B, 1)
+        u_w = rng.rand(B, M)
+        u_fw = rng.rand(B, M) if cfg.flipout_rec is not None else None
+        out.append((u_z, u_s, u_w, u_fz, u_fw) if (u_fz is not None or u_fw is not None) else (u_z, u_s, u_w))
+    return out
 
 
 def synthetic_batch(cfg, seed=0, B=None):

@@ -71,6 +71,12 @@ CASES = {
                                   entropy_rec=0.01, entropy_s=0.08, top_k_train=3, optim_type="SGD",
                                   learning_rate=1e-2),
                          iters=2, seed=18),
+    # flipout noise on both messages (model.py:233-234,467-468,554-568): two extra uniform draws per step
+    "flipout_small": dict(cfg=dict(batch_size=8, img_feat_dim=40, img_h_dim=24, baseline_hid_dim=20,
+                                   sender_out_dim=12, rec_hidden=16, rec_w_dim=12, wv_dim=20, n_classes=7,
+                                   max_exchange=4, fixed_exchange=False, use_binary=True, entropy_sen=0.01,
+                                   entropy_rec=0.02, entropy_s=0.05, top_k_train=2, flipout_sen=0.15, flipout_rec=0.1),
+                          iters=2, seed=19),
 }
 
 EVAL_CASES = {
@@ -100,8 +106,8 @@ def _ref_modules(model, cfg, params):
                  fixed_exchange=cfg.fixed_exchange, entropy_s=cfg.entropy_s, entropy_sen=cfg.entropy_sen,
                  entropy_rec=cfg.entropy_rec, batch_size=cfg.batch_size, top_k_train=cfg.top_k_train,
                  first_rec=cfg.first_rec, s_prob_prod=cfg.s_prob_prod, debug=False, sender_mix="sum",
-                 ignore_code=False, desc_attn=False, ignore_receiver=False, flipout_sen=None,
-                 flipout_rec=None, cuda=False, rec_w_dim=cfg.rec_w_dim, sender_out_dim=cfg.sender_out_dim)
+                 ignore_code=False, desc_attn=False, ignore_receiver=False, flipout_sen=cfg.flipout_sen,
+                 flipout_rec=cfg.flipout_rec, flipout_dev=False, cuda=False, rec_w_dim=cfg.rec_w_dim, sender_out_dim=cfg.sender_out_dim)
     sender = model.Sender("avgpool_512", cfg.img_feat_dim, cfg.img_h_dim, cfg.rec_w_dim, cfg.sender_out_dim,
                           cfg.use_binary, False, 0, False, 0)
     receiver = model.Receiver(cfg.sender_out_dim, cfg.wv_dim, cfg.rec_hidden, 1, cfg.rec_w_dim, 1, cfg.use_binary)
@@ -170,7 +176,15 @@ def make_train_case(model, name, spec):
                       optimizer_bas_sen=opts["baseline_sen"])
             exec(update_src, ns)
         steps = len(y)
-        if cfg.use_binary:
+        if cfg.use_binary and (cfg.flipout_sen is not None or cfg.flipout_rec is not None):
+            assert cfg.flipout_sen is not None and cfg.flipout_rec is not None
+            assert len(sink) == 5 * steps, (len(sink), steps)       # z, flip z, s, w, flip w
+            out[pre + "u_z"] = np.stack(sink[0::5], 0)
+            out[pre + "u_fz"] = np.stack(sink[1::5], 0)
+            out[pre + "u_s"] = np.stack(sink[2::5], 0)
+            out[pre + "u_w"] = np.stack(sink[3::5], 0)
+            out[pre + "u_fw"] = np.stack(sink[4::5], 0)
+        elif cfg.use_binary:
             assert len(sink) == 3 * steps, (len(sink), steps)
             out[pre + "u_z"] = np.stack(sink[0::3], 0)
             out[pre + "u_s"] = np.stack(sink[1::3], 0)
@@ -247,8 +261,13 @@ def make_eval_case(model, name, spec):
 def main():
     model = rs.load_reference()
     torch.set_num_threads(1)
+    only = sys.argv[1:]
     for name, spec in CASES.items():
+        if only and name not in only:
+            continue
         make_train_case(model, name, spec)
+    if only:
+        return
     for name, spec in EVAL_CASES.items():
         make_eval_case(model, name, spec)
 

@@ -12,7 +12,7 @@ from oracle import game_oracle as go
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 TRAIN_CASES = ["c1_continuous", "continuous_t3", "fixed_small", "fixed_t1_noent", "adaptive_small",
-               "adaptive_b1_adam", "headline_mid", "adaptive_sgd"]
+               "adaptive_b1_adam", "headline_mid", "adaptive_sgd", "flipout_small"]
 EVAL_CASES = ["eval_adaptive", "eval_adaptive_noprod", "eval_fixed_corrupt", "eval_continuous"]
 
 
@@ -37,6 +37,8 @@ def uniforms_at(z, it, cfg):
     pre = "it%d/" % it
     u_s = z[pre + "u_s"]
     steps = u_s.shape[0]
+    if cfg.use_binary and (pre + "u_fz") in z.files:
+        return [(z[pre + "u_z"][t], u_s[t], z[pre + "u_w"][t], z[pre + "u_fz"][t], z[pre + "u_fw"][t]) for t in range(steps)]
     if cfg.use_binary:
         return [(z[pre + "u_z"][t], u_s[t], z[pre + "u_w"][t]) for t in range(steps)]
     return [(None, u_s[t], None) for t in range(steps)]

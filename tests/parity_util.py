@@ -16,7 +16,8 @@ def config_from(cfg, B=None, batch_global=None):
         rec_w_dim=cfg.rec_w_dim, wv_dim=cfg.wv_dim, max_exchange=cfg.max_exchange, fixed_exchange=cfg.fixed_exchange,
         use_binary=cfg.use_binary, entropy_s=cfg.entropy_s, entropy_sen=cfg.entropy_sen, entropy_rec=cfg.entropy_rec,
         first_rec=cfg.first_rec, s_prob_prod=cfg.s_prob_prod, learning_rate=cfg.learning_rate,
-        optim_type=cfg.optim_type, ignore_receiver=cfg.ignore_receiver, batch_global=batch_global)
+        optim_type=cfg.optim_type, ignore_receiver=cfg.ignore_receiver, batch_global=batch_global,
+        flipout_sen=getattr(cfg, "flipout_sen", None), flipout_rec=getattr(cfg, "flipout_rec", None))
 
 
 def stack_uniforms(us, cfg, B):
@@ -24,13 +25,19 @@ def stack_uniforms(us, cfg, B):
     reference stops drawing after an early break; the kernel runs every step, masked)."""
     T, M = cfg.max_exchange, cfg.rec_w_dim
     rng = np.random.RandomState(4242)
-    uz, us_, uw = [], [], []
+    flips = getattr(cfg, "flipout_sen", None) is not None or getattr(cfg, "flipout_rec", None) is not None
+    uz, us_, uw, ufz, ufw = [], [], [], [], []
     for t in range(T):
-        a, b, c = us[t] if t < len(us) else (None, None, None)
-        uz.append(a if a is not None else rng.rand(B, M))
-        us_.append(b if b is not None else rng.rand(B, 1))
-        uw.append(c if c is not None else rng.rand(B, M))
+        u = tuple(us[t]) if t < len(us) else ()
+        u = u + (None,) * (5 - len(u))
+        uz.append(u[0] if u[0] is not None else rng.rand(B, M))
+        us_.append(u[1] if u[1] is not None else rng.rand(B, 1))
+        uw.append(u[2] if u[2] is not None else rng.rand(B, M))
+        ufz.append(u[3] if u[3] is not None else rng.rand(B, M))
+        ufw.append(u[4] if u[4] is not None else rng.rand(B, M))
     f = lambda l: torch.from_numpy(np.ascontiguousarray(np.stack(l, 0)))
+    if flips:       # five arrays: sender, stop, receiver, sender flipout, receiver flipout
+        return f(uz), f(us_).reshape(T, B), f(uw), f(ufz), f(ufw)
     return f(uz), f(us_).reshape(T, B), f(uw)
 
 
@@ -69,8 +76,9 @@ def run_train_case(case, lib, device, report=None, grad_rtol=2e-3):
         us = gu.uniforms_at(z, it, cfg)
         ex, res, grads = go.train_iteration(oparams, ostate, x, target, desc, cfg, us, return_grads=True)
         Tp = len(ex["y"])     # steps the reference executed (early break)
-        uz, us_, uw = stack_uniforms(us, cfg, B)
-        e.forward(x, desc, target, train=True, uniforms=(uz, us_, uw), top_k=min(cfg.top_k_train, cfg.n_classes))
+        stacked = stack_uniforms(us, cfg, B)
+        uz, us_, uw = stacked[:3]
+        e.forward(x, desc, target, train=True, uniforms=stacked, top_k=min(cfg.top_k_train, cfg.n_classes))
         e.loss()
         e.backward()
         out = {k: v.detach().cpu().numpy() for k, v in e.outputs().items()}
@@ -242,8 +250,9 @@ def run_synth_case(cfg, lib, device, iters=1, seed=0, check_grads=True, tag="syn
         us = go.draw_uniforms(rng, cfg)
         ex, res, grads = go.train_iteration(oparams, ostate, x, target, desc, cfg, us, return_grads=True)
         Tp = len(ex["y"])
-        uz, us_, uw = stack_uniforms(us, cfg, B)
-        e.train_step(x, desc, target, uniforms=(uz, us_, uw), top_k=min(cfg.top_k_train, cfg.n_classes))
+        stacked = stack_uniforms(us, cfg, B)
+        uz, us_, uw = stacked[:3]
+        e.train_step(x, desc, target, uniforms=stacked, top_k=min(cfg.top_k_train, cfg.n_classes))
         out = {k: v.detach().cpu().numpy() for k, v in e.outputs().items()}
         st = lambda key: np.stack([t.detach().numpy() for t in ex[key]], 0)
         t_ = "%s/it%d/" % (tag, it)

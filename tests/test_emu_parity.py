@@ -5,7 +5,8 @@ import pytest
 
 from tests import emu_util, parity_util as pu
 
-CASES = ["fixed_small", "fixed_t1_noent", "continuous_t3", "adaptive_small", "adaptive_b1_adam", "adaptive_sgd"]
+CASES = ["fixed_small", "fixed_t1_noent", "continuous_t3", "adaptive_small", "adaptive_b1_adam", "adaptive_sgd",
+         "flipout_small"]
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -46,3 +47,13 @@ def test_emulated_fused_train_step_fast_dims(fixed):
                         use_binary=True, entropy_s=None if fixed else 0.05, entropy_sen=0.01, entropy_rec=0.02,
                         top_k_train=2)
     pu.run_fused_step_case(cfg, emu_util.emu_library(), "cpu", iters=2, seed=11)
+
+
+def test_emulated_fast_path_flipout():
+    """flipout noise (model.py:233-234,467-468) through the specialised kernels, injected flip uniforms."""
+    from oracle import game_oracle as go
+    cfg = go.GameConfig(batch_size=3, img_feat_dim=40, img_h_dim=256, baseline_hid_dim=24, sender_out_dim=32,
+                        rec_hidden=64, rec_w_dim=32, wv_dim=12, n_classes=6, max_exchange=3, fixed_exchange=False,
+                        use_binary=True, entropy_s=0.05, entropy_sen=0.01, entropy_rec=0.02, top_k_train=2,
+                        flipout_sen=0.2, flipout_rec=0.1)
+    pu.run_synth_case(cfg, emu_util.emu_library(), "cpu", iters=2, seed=13, tag="fastflip")
