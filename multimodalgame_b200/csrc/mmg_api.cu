@@ -126,7 +126,6 @@ static void ws_layout(const Dims& d, Ws* w) {
     w->y1h = take(c, R * d.Hr * f);
     w->q = take(c, R * d.D * f);
     w->wd = take(c, R * d.WV * f);
-    w->rowstat = take(c, 6 * R * f);
     w->ntb = cdiv(d.Hb, kTile);
     w->h1s = take(c, R * d.Hb * f);
     w->h1r = take(c, R * d.Hb * f);
@@ -184,7 +183,7 @@ static WsPtrs resolve(const Ws& w, void* base) {
     r.stats = (double*)(b + p.stats);
     r.rng_state = (unsigned long long*)(b + p.rng_state);
 #define G_(name) r.name = (float*)(b + w.name)
-    G_(code_in); G_(a_s); G_(gates); G_(y1h); G_(q); G_(wd); G_(rowstat); G_(h1s); G_(h1r); G_(bs_part); G_(br_part); G_(ubs);
+    G_(code_in); G_(a_s); G_(gates); G_(y1h); G_(q); G_(wd); G_(h1s); G_(h1r); G_(bs_part); G_(br_part); G_(ubs);
     G_(hx_part); G_(fwd_image); G_(bwd_image); G_(d_lz); G_(d_as); G_(dhx); G_(dgi); G_(dgh); G_(d_lw); G_(d_hw);
     G_(d_ls); G_(g_h); G_(hsel); G_(dy1); G_(dw2p); G_(dcode_part); G_(slabs); G_(norm_part);
 #undef G_

@@ -104,7 +104,7 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas) {
     float* dlw = sm + o;   o += BT * MP;
     float* dvec = sm + o;  o += BT * H2P;      // [d_hw (Hr) ; G_h (Hr)]
     float* dghs = sm + o;  o += BT * G3P;
-    float* gy = sm + o;    o += BT * DP;
+    o += BT * DP;
     float* dls = sm + o;   o += BT;
     float* yflag = sm + o; o += BT;
     o = align4(o);

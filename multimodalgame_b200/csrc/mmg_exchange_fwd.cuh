@@ -205,24 +205,6 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
         if (t > 0) {
             if (sender_smem) split_matvec<BT, false>(Wc, d.Hi, d.M4, win, MP, partA, sp_code);
             else             split_matvec<BT, true>(Wc, d.Hi, d.M4, win, MP, partA, sp_code);
-            // log-likelihood / entropy sums of the previous receiver message (rows of calculate_loss_binary)
-            if (binary && warp == kLoopThreads / 32 - 1) {
-                for (int bt = 0; bt < BT; ++bt) {
-                    float lp = 0.f, hh = 0.f;
-                    for (int j = lane; j < d.M; j += 32) {
-                        const float p = pv[bt * MP + j], f = win[bt * MP + j];
-                        const float l1 = logf(p + 1e-8f), l0 = logf(1.f - p + 1e-8f);
-                        lp += f * l1 + (1.f - f) * l0;
-                        hh += p * l1 + (1.f - p) * l0;
-                    }
-                    lp = warp_sum(lp); hh = warp_sum(hh);
-                    const int b = b0 + bt;
-                    if (lane == 0 && b < d.B) {
-                        W.rowstat[(size_t)2 * d.R + (size_t)(t - 1) * d.B + b] = lp;
-                        W.rowstat[(size_t)3 * d.R + (size_t)(t - 1) * d.B + b] = hh;
-                    }
-                }
-            }
             MMG_SYNCTHREADS();
         }
         // ---- S2: a = tanh(h_x + h_w) (model.py:216) -------------------------------------------------------
@@ -271,23 +253,6 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
         // ---- S5: GRU mat-vecs (model.py:340) -------------------------------------------------------------------
         split_matvec<BT, false>(Wih, d.G3, d.M4, zv, MP, partA, sp_gi);
         split_matvec<BT, false>(Whh, d.G3, d.Hr4, hv, HrP, partB, sp_gh);
-        if (binary && warp == kLoopThreads / 32 - 1) {
-            for (int bt = 0; bt < BT; ++bt) {
-                float lp = 0.f, hh = 0.f;
-                for (int j = lane; j < d.M; j += 32) {
-                    const float p = pv[bt * MP + j], f = zv[bt * MP + j];
-                    const float l1 = logf(p + 1e-8f), l0 = logf(1.f - p + 1e-8f);
-                    lp += f * l1 + (1.f - f) * l0;
-                    hh += p * l1 + (1.f - p) * l0;
-                }
-                lp = warp_sum(lp); hh = warp_sum(hh);
-                const int b = b0 + bt;
-                if (lane == 0 && b < d.B) {
-                    W.rowstat[(size_t)0 * d.R + (size_t)t * d.B + b] = lp;
-                    W.rowstat[(size_t)1 * d.R + (size_t)t * d.B + b] = hh;
-                }
-            }
-        }
         MMG_SYNCTHREADS();
         // ---- S6: GRU gates, gate order r,z,n; h' = n + u (h - n) --------------------------------------------
         for (int idx = tid; idx < BT * d.Hr; idx += kLoopThreads) {
@@ -339,9 +304,6 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
                     W.stop_feat[row] = sbit;
                     W.stop_prob[row] = sp;
                     W.stop_mask[(size_t)(t + 1) * d.B + b] = (unsigned char)(m != 0.f);
-                    const float l1 = logf(sp + 1e-8f), l0 = logf(1.f - sp + 1e-8f);
-                    W.rowstat[(size_t)4 * d.R + row] = sbit * l1 + (1.f - sbit) * l0;
-                    W.rowstat[(size_t)5 * d.R + row] = sp * l1 + (1.f - sp) * l0;
                 }
             }
         }
@@ -424,24 +386,6 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
             }
         }
         MMG_SYNCTHREADS();
-    }
-    // log-likelihood / entropy sums of the last receiver message
-    if (binary && warp == kLoopThreads / 32 - 1) {
-        for (int bt = 0; bt < BT; ++bt) {
-            float lp = 0.f, hh = 0.f;
-            for (int j = lane; j < d.M; j += 32) {
-                const float p = pv[bt * MP + j], f = win[bt * MP + j];
-                const float l1 = logf(p + 1e-8f), l0 = logf(1.f - p + 1e-8f);
-                lp += f * l1 + (1.f - f) * l0;
-                hh += p * l1 + (1.f - p) * l0;
-            }
-            lp = warp_sum(lp); hh = warp_sum(hh);
-            const int b = b0 + bt;
-            if (lane == 0 && b < d.B) {
-                W.rowstat[(size_t)2 * d.R + (size_t)(d.T - 1) * d.B + b] = lp;
-                W.rowstat[(size_t)3 * d.R + (size_t)(d.T - 1) * d.B + b] = hh;
-            }
-        }
     }
 }
 

@@ -203,7 +203,6 @@ struct Ws {   // byte offsets into the workspace
     int64_t y1h;       // (T,B,Hr) y1.weight[:, :Hr] . h_z
     int64_t q;         // (T,B,D)  softmax(y)
     int64_t wd;        // (T,B,WV) q . desc
-    int64_t rowstat;   // (6,T,B)  logp_z, H_z, logp_w, H_w, logp_s, H_s
     int64_t h1s, h1r;  // (T,B,Hb) baseline hidden (post relu)
     int64_t bs_part, br_part;  // (T,B,NTb) partial dots with linear2.weight per 64-column tile
     int64_t ubs;       // (B,Hb)  baseline_sen.linear1 applied to h_x only (+ bias): shared by all T steps of an example (fast path)
