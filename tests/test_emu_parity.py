@@ -6,7 +6,7 @@ import pytest
 from tests import emu_util, parity_util as pu
 
 CASES = ["fixed_small", "fixed_t1_noent", "continuous_t3", "adaptive_small", "adaptive_b1_adam", "adaptive_sgd",
-         "flipout_small"]
+         "flipout_small", "ignore_rec_first1"]
 
 
 @pytest.mark.parametrize("case", CASES)
