@@ -41,6 +41,7 @@ typedef enum mmg_status {
 } mmg_status;
 
 enum { MMG_OPT_RMSPROP = 0, MMG_OPT_ADAM = 1, MMG_OPT_SGD = 2 }; /* model.py:1111-1137 */
+enum { MMG_MIX_SUM = 0, MMG_MIX_PROD = 1 };
 
 /* Flags that shape the path.  Field names follow the reference's gflags (model.py:1641-1741). */
 typedef struct mmg_config {
@@ -67,7 +68,8 @@ typedef struct mmg_config {
     int32_t has_flipout_sen, has_flipout_rec; /* 0 when the flag is None (model.py:1710-1711) */
     int32_t flipout_dev;     /* model.py:1712: flip in eval mode too */
     float flipout_sen, flipout_rec;           /* bit-flip probabilities (model.py:233-234,467-468,554-568) */
-    int32_t reserved[2];
+    int32_t sender_mix;      /* MMG_MIX_SUM: tanh(h_x + h_w); MMG_MIX_PROD: tanh(h_x * h_w)  (model.py:1692,208-221); "mou" unsupported */
+    int32_t ignore_code;     /* model.py:1704,208-213: the sender ignores the receiver's message, hidden = tanh(h_x) */
 } mmg_config;
 
 /* ---- parameter layout -------------------------------------------------------------------------------

@@ -33,6 +33,7 @@ SEGMENTS = ("receiver", "sender", "baseline_rec", "baseline_sen")
 LOSS_NAMES = ("nll_loss", "loss_rec", "loss_sen", "loss_bas_rec", "loss_bas_sen", "loss_binary_s", "loss_binary_rec",
               "loss_binary_sen", "topk_correct", "active_steps")
 OPTIM = {"RMSprop": 0, "Adam": 1, "SGD": 2}
+SENDER_MIX = {"sum": 0, "prod": 1}
 
 
 class Config(C.Structure):
@@ -42,7 +43,8 @@ class Config(C.Structure):
         "has_entropy_s", "has_entropy_sen", "has_entropy_rec")] + [
         (n, C.c_float) for n in ("entropy_s", "entropy_sen", "entropy_rec", "first_rec", "learning_rate", "max_norm")
     ] + [("ignore_receiver", C.c_int32), ("has_flipout_sen", C.c_int32), ("has_flipout_rec", C.c_int32),
-         ("flipout_dev", C.c_int32), ("flipout_sen", C.c_float), ("flipout_rec", C.c_float), ("reserved", C.c_int32 * 2)]
+         ("flipout_dev", C.c_int32), ("flipout_sen", C.c_float), ("flipout_rec", C.c_float), ("sender_mix", C.c_int32),
+         ("ignore_code", C.c_int32)]
 
 
 class ParamLayout(C.Structure):

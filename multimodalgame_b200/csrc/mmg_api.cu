@@ -48,6 +48,7 @@ static int validate(const mmg_config* c) {
     if (c->msg_dim > 256) return fail(MMG_ERR_UNSUPPORTED, "msg_dim=%d > 256 not supported by the fused path", c->msg_dim);
     if (c->img_h_dim > (int)kGemmSmemFloats * 64) return fail(MMG_ERR_UNSUPPORTED, "img_h_dim=%d too large", c->img_h_dim);
     if (c->optim_type < 0 || c->optim_type > 2) return fail(MMG_ERR_INVALID, "optim_type=%d", c->optim_type);
+    if (c->sender_mix != MMG_MIX_SUM && c->sender_mix != MMG_MIX_PROD) return fail(MMG_ERR_UNSUPPORTED, "sender_mix=%d (mou is not built)", c->sender_mix);
     if ((long long)c->max_exchange * c->batch > (1ll << 24)) return fail(MMG_ERR_UNSUPPORTED, "T*B too large");
     return MMG_OK;
 }
@@ -122,6 +123,7 @@ static void ws_layout(const Dims& d, Ws* w) {
     p.rng_state = take(c, 16);
     w->code_in = take(c, R * d.M * f);
     w->a_s = take(c, R * d.Hi * f);
+    w->hw_s = take(c, d.mix_prod ? R * d.Hi * f : 16);
     w->gates = take(c, R * 4 * d.Hr * f);
     w->y1h = take(c, R * d.Hr * f);
     w->q = take(c, R * d.D * f);
@@ -183,7 +185,7 @@ static WsPtrs resolve(const Ws& w, void* base) {
     r.stats = (double*)(b + p.stats);
     r.rng_state = (unsigned long long*)(b + p.rng_state);
 #define G_(name) r.name = (float*)(b + w.name)
-    G_(code_in); G_(a_s); G_(gates); G_(y1h); G_(q); G_(wd); G_(h1s); G_(h1r); G_(bs_part); G_(br_part); G_(ubs);
+    G_(code_in); G_(a_s); G_(hw_s); G_(gates); G_(y1h); G_(q); G_(wd); G_(h1s); G_(h1r); G_(bs_part); G_(br_part); G_(ubs);
     G_(hx_part); G_(fwd_image); G_(bwd_image); G_(d_lz); G_(d_as); G_(dhx); G_(dgi); G_(dgh); G_(d_lw); G_(d_hw);
     G_(d_ls); G_(g_h); G_(hsel); G_(dy1); G_(dw2p); G_(dcode_part); G_(slabs); G_(norm_part);
 #undef G_
@@ -322,7 +324,7 @@ template <int BT, int M, bool SS>
 static int launch_fwd_fast_one(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const FastFwdArgs& fa, const Plan& pl,
                                cudaStream_t st) {
     const bool perf = in.train && d.use_binary && in.u_sen == nullptr && in.corrupt_mask == nullptr && !d.ignore_receiver &&
-                      d.flip_sen < 0.f && d.flip_rec < 0.f && d.B % BT == 0;
+                      d.flip_sen < 0.f && d.flip_rec < 0.f && !d.mix_prod && !d.ignore_code && d.B % BT == 0;
     return perf ? launch_fwd_fast_mode<BT, M, SS, true>(d, W, in, fa, pl, st)
                 : launch_fwd_fast_mode<BT, M, SS, false>(d, W, in, fa, pl, st);
 }
@@ -393,7 +395,7 @@ static void build_wgrad_table(const Dims& d, const mmg_param_layout& L, const Pa
                               const ExchangeInputs& in, int fast, WgTable* t, SplitTable* st) {
     t->count = 0; t->total_tiles = 0; t->slab_stride = L.total;
     for (int i = 0; i < MMG_P_COUNT; ++i) {
-        st->begin[i] = L.offset[i]; st->numel[i] = L.rows[i] * L.cols[i]; st->nsplit[i] = 1;
+        st->begin[i] = L.offset[i]; st->numel[i] = L.rows[i] * L.cols[i]; st->nsplit[i] = 0;   // 0: no problem writes this tensor
     }
     st->begin[MMG_P_COUNT] = L.total;
     WgBuilder b{t, st, &L, {}, {}};
@@ -417,9 +419,11 @@ static void build_wgrad_table(const Dims& d, const mmg_param_layout& L, const Pa
     if (d.use_binary) {
         // sender
         b.add(km(W.d_lz, M), km(W.a_s, Hi), M, Hi, R, MMG_P_SEN_BIN_W, 0, MMG_P_SEN_BIN_B);
-        b.add(km(W.d_as, Hi), km(W.code_in, M), Hi, M, R, MMG_P_SEN_CODE_W, 0, MMG_P_SEN_CODE_B);
-        if (fast) b.add(km(W.dcode_part, M), ones(), M, 1, B, MMG_P_SEN_CODE_BIAS, 0, -1, WG_GEMM, P.p[MMG_P_SEN_CODE_BIAS]);
-        else      b.add(km(W.d_as, Hi), km(W.d_as, Hi), M, 1, 1, MMG_P_SEN_CODE_BIAS, 0, -1, WG_CODEBIAS);
+        if (!d.ignore_code) {      // -ignore_code: code_layer / code_bias receive no gradient (model.py:208-213); they stay zero
+            b.add(km(W.d_as, Hi), km(W.code_in, M), Hi, M, R, MMG_P_SEN_CODE_W, 0, MMG_P_SEN_CODE_B);
+            if (fast) b.add(km(W.dcode_part, M), ones(), M, 1, B, MMG_P_SEN_CODE_BIAS, 0, -1, WG_GEMM, P.p[MMG_P_SEN_CODE_BIAS]);
+            else      b.add(km(W.d_as, Hi), km(W.d_as, Hi), M, 1, 1, MMG_P_SEN_CODE_BIAS, 0, -1, WG_CODEBIAS);
+        }
         b.add(km(W.dhx, Hi), km(in.x, d.F), Hi, d.F, B, MMG_P_SEN_IMG_W, 0, MMG_P_SEN_IMG_B);
         // baseline_sen: d pre = g_bs * linear2.weight * (hidden > 0); rows [h_x[b] ; z_r[t,b]]
         {

@@ -81,9 +81,13 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas) {
                 if (b < d.B) {
                     const size_t i = ((size_t)t * d.B + b) * d.Hi + n;
                     const float a = W.a_s[i];
-                    const float das = gather_part<BT>(part, sp, bt, n) * (1.f - a * a);   // through tanh (model.py:216)
-                    W.d_as[i] = das;
-                    dhx[bt * HiP + n] += das;                               // h_x is shared by all steps (model.py:195)
+                    const float dpre = gather_part<BT>(part, sp, bt, n) * (1.f - a * a);  // through tanh (model.py:216)
+                    // d_as = gradient w.r.t. the code term h_w; sum: d pre, prod: d pre * h_x, ignore_code: none
+                    float dhw = dpre, dx = dpre;
+                    if (d.mix_prod && !d.ignore_code) { dhw = dpre * W.h_x[(size_t)b * d.Hi + n]; dx = dpre * W.hw_s[i]; }
+                    if (d.ignore_code) dhw = 0.f;
+                    W.d_as[i] = dhw;
+                    dhx[bt * HiP + n] += dx;                                // h_x is shared by all steps (model.py:195)
                 }
             }
             // next iteration's first stage only writes dlz (already consumed) -> the barrier after it orders `part`

@@ -211,9 +211,13 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
         for (int idx = tid; idx < BT * d.Hi; idx += kLoopThreads) {
             const int bt = idx / d.Hi, n = idx % d.Hi, b = b0 + bt;
             const float hw = (t == 0) ? hw0[n] : b_code[n] + gather_part<BT>(partA, sp_code, bt, n);
-            const float a = tanhf(hx[bt * HiP + n] + hw);
+            const float hxv = hx[bt * HiP + n];
+            const float a = tanhf(d.ignore_code ? hxv : (d.mix_prod ? hxv * hw : hxv + hw));     // model.py:208-221
             av[bt * HiP + n] = a;
-            if (b < d.B) W.a_s[((size_t)t * d.B + b) * d.Hi + n] = a;
+            if (b < d.B) {
+                W.a_s[((size_t)t * d.B + b) * d.Hi + n] = a;
+                if (d.mix_prod) W.hw_s[((size_t)t * d.B + b) * d.Hi + n] = hw;
+            }
         }
         if (t > 0) {
             for (int idx = tid; idx < BT * d.M; idx += kLoopThreads) {

@@ -349,10 +349,14 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
 #pragma unroll
             for (int bt = 0; bt < BT; ++bt) {
                 const int b = b0 + bt;
-                const float a = fast_tanh(hx[bt * HI + tid] + (base + hsum4(acc[bt])));
+                const float hwv = base + hsum4(acc[bt]), hxv = hx[bt * HI + tid];
+                float pre = hxv + hwv;                                        // model.py:208-221
+                if constexpr (!kPerf) { if (d.ignore_code) pre = hxv; else if (d.mix_prod) pre = hxv * hwv; }
+                const float a = fast_tanh(pre);
                 av[bt * HI + tid] = a;
                 if (MMG_SAVE_OK(b)) {
                     W.a_s[((size_t)t * B + b) * HI + tid] = a;
+                    if constexpr (!kPerf) { if (d.mix_prod) W.hw_s[((size_t)t * B + b) * HI + tid] = hwv; }
                     if (t > 0 && tid < M) W.code_in[((size_t)t * B + b) * M + tid] = win[bt * M + tid];
                 }
             }
@@ -674,10 +678,14 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
 #pragma unroll
             for (int j4 = 0; j4 < M4; ++j4)
                 fma4(lds4(dlz + t * M + 4 * j4), make_float4(wb[4 * j4], wb[4 * j4 + 1], wb[4 * j4 + 2], wb[4 * j4 + 3]), a4);
-            const float das = hsum4(a4) * (1.f - a * a);              // through tanh (model.py:216)
+            const float dpre = hsum4(a4) * (1.f - a * a);             // through tanh (model.py:216)
+            // d_as = gradient w.r.t. the code term h_w; sum: d pre, prod: d pre * h_x, ignore_code: none
+            float das = dpre, dx = dpre;
+            if (d.mix_prod && !d.ignore_code) { das = dpre * W.h_x[(size_t)b * HI + n]; dx = dpre * W.hw_s[i]; }
+            if (d.ignore_code) das = 0.f;
             W.d_as[i] = das;
             if (t == 0) das0[n] = das;
-            dhx += das;                                               // h_x is shared by all steps (model.py:195)
+            dhx += dx;                                                // h_x is shared by all steps (model.py:195)
         }
         W.dhx[(size_t)b * HI + n] = dhx;
         MMG_BSTAMP(2);

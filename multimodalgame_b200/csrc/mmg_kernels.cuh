@@ -17,7 +17,7 @@ struct WsPtrs {               // resolved workspace arrays (device pointers)
     double* stats;
     float *g_sen_probs, *g_rec_probs, *g_stop_prob, *g_outp, *g_bs, *g_br;
     unsigned long long* rng_state;
-    float *code_in, *a_s, *gates, *y1h, *q, *wd, *h1s, *h1r, *bs_part, *br_part, *ubs;
+    float *code_in, *a_s, *hw_s, *gates, *y1h, *q, *wd, *h1s, *h1r, *bs_part, *br_part, *ubs;
     float *hx_part, *fwd_image, *bwd_image;
     float *d_lz, *d_as, *dhx, *dgi, *dgh, *d_lw, *d_hw, *d_ls, *g_h, *hsel, *dy1, *dw2p, *dcode_part, *slabs, *norm_part;
     double* loss_part;

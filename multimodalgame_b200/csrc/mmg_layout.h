@@ -16,6 +16,7 @@ struct Dims {
     float first_rec;
     float flip_sen, flip_rec;   // flipout probabilities, < 0 = off (model.py:233-234,467-468)
     int flipout_dev;
+    int mix_prod, ignore_code;  // sender hidden: tanh(h_x * h_w) instead of the sum / tanh(h_x) alone (model.py:208-221)
 };
 
 MMG_HOST_DEVICE Dims make_dims(const mmg_config& c) {
@@ -31,6 +32,7 @@ MMG_HOST_DEVICE Dims make_dims(const mmg_config& c) {
     d.flip_sen = c.has_flipout_sen ? c.flipout_sen : -1.f;
     d.flip_rec = c.has_flipout_rec ? c.flipout_rec : -1.f;
     d.flipout_dev = c.flipout_dev;
+    d.mix_prod = c.sender_mix == MMG_MIX_PROD; d.ignore_code = c.ignore_code;
     return d;
 }
 
@@ -199,6 +201,7 @@ struct Ws {   // byte offsets into the workspace
     // saved activations
     int64_t code_in;   // (T,B,M)  sender code input: sigmoid(code_bias) at t=0, receiver message after
     int64_t a_s;       // (T,B,Hi) sender tanh hidden
+    int64_t hw_s;      // (T,B,Hi) sender code term h_w (kept only for sender_mix = prod: d h_x = d pre * h_w)
     int64_t gates;     // (T,B,4,Hr) r, u, n, (W_hn h + b_hn)
     int64_t y1h;       // (T,B,Hr) y1.weight[:, :Hr] . h_z
     int64_t q;         // (T,B,D)  softmax(y)

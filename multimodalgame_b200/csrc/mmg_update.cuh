@@ -168,7 +168,7 @@ MMG_DEVICE void reduce_norm_body(const SegInfo& seg, const SplitTable& st, const
         if (do_reduce) {
             const int tn = tensor_of(st, i);
             const long long valid = st.begin[tn] + st.numel[tn] - i;   // real floats in this group (>= 1)
-            if (!seg.trained[sg]) {
+            if (!seg.trained[sg] || st.nsplit[tn] == 0) {      // untrained module, or a tensor no gradient problem covers
                 g = make_float4(0.f, 0.f, 0.f, 0.f);
             } else {
                 for (int s = 1; s < st.nsplit[tn]; ++s) {

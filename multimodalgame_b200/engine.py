@@ -19,7 +19,7 @@ def make_config(batch, n_classes, img_feat_dim=4096, img_h_dim=100, baseline_hid
                 rec_hidden=128, rec_w_dim=50, wv_dim=100, max_exchange=3, fixed_exchange=True, use_binary=True,
                 entropy_s=None, entropy_sen=None, entropy_rec=None, first_rec=0.0, s_prob_prod=True,
                 learning_rate=1e-4, optim_type="RMSprop", ignore_receiver=False, batch_global=None, max_norm=1.0,
-                flipout_sen=None, flipout_rec=None, flipout_dev=False):
+                flipout_sen=None, flipout_rec=None, flipout_dev=False, sender_mix="sum", ignore_code=False):
     """Build the C config from reference flag names/defaults (model.py:1641-1741)."""
     assert sender_out_dim == rec_w_dim, \
         "Both sender and receiver should communicate with same dim vectors for now."   # model.py:1756
@@ -41,6 +41,9 @@ def make_config(batch, n_classes, img_feat_dim=4096, img_h_dim=100, baseline_hid
     c.has_flipout_sen, c.flipout_sen = int(flipout_sen is not None), float(flipout_sen or 0.0)     # model.py:1710-1712
     c.has_flipout_rec, c.flipout_rec = int(flipout_rec is not None), float(flipout_rec or 0.0)
     c.flipout_dev = int(bool(flipout_dev))
+    if sender_mix not in capi.SENDER_MIX:
+        raise NotImplementedError("sender_mix=%s is outside the fused B200 path" % sender_mix)        # 'mou', model.py:219-221
+    c.sender_mix, c.ignore_code = capi.SENDER_MIX[sender_mix], int(bool(ignore_code))
     return c
 
 

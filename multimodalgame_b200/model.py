@@ -182,8 +182,8 @@ class Sender(nn.Module):
         self.attn_dim, self.attn_extra_context, self.attn_context_dim = attn_dim, attn_extra_context, attn_context_dim
         if use_attn:
             _unsupported("-visual_attn (Sender visual attention, model.py:80-86,114-191)")
-        if _flag("sender_mix", "sum") != "sum" or _flag("ignore_code", False):
-            _unsupported("-sender_mix %s / -ignore_code" % _flag("sender_mix", "sum"))
+        if _flag("sender_mix", "sum") == "mou":
+            _unsupported("-sender_mix mou (4 x h_dim mixture, model.py:73-76,213-221)")
         self.image_layer = nn.Linear(self.feat_dim, self.h_dim)
         self.code_layer = nn.Linear(self.w_dim, self.h_dim)
         self.code_bias = Parameter(torch.Tensor(self.bin_dim_out))
@@ -287,7 +287,8 @@ class _Binding(object):
             s_prob_prod=bool(_flag("s_prob_prod", True)), learning_rate=float(_flag("learning_rate", 1e-4)),
             optim_type=_flag("optim_type", "RMSprop"), ignore_receiver=bool(_flag("ignore_receiver", False)),
             batch_global=batch_global, flipout_sen=_flag("flipout_sen"), flipout_rec=_flag("flipout_rec"),
-            flipout_dev=bool(_flag("flipout_dev", False)))
+            flipout_dev=bool(_flag("flipout_dev", False)), sender_mix=_flag("sender_mix", "sum"),
+            ignore_code=bool(_flag("ignore_code", False)))
         self.engine = _engine.GameEngine(cfg, device=device, lib=_LIB_OVERRIDE)
         self.mods = mods
         self.key = None
@@ -322,7 +323,8 @@ def _binding_for(sender, receiver, baseline_sen, baseline_rec, B, D, device, bat
     key = (id(sender), id(receiver), id(baseline_sen), id(baseline_rec), int(B), int(D), str(device),
            int(_flag("max_exchange", 3)), bool(_flag("fixed_exchange", True)), _flag("entropy_s"), _flag("entropy_sen"),
            _flag("entropy_rec"), _flag("optim_type", "RMSprop"), float(_flag("learning_rate", 1e-4)), batch_global,
-           _flag("flipout_sen"), _flag("flipout_rec"), bool(_flag("flipout_dev", False)))
+           _flag("flipout_sen"), _flag("flipout_rec"), bool(_flag("flipout_dev", False)), _flag("sender_mix", "sum"),
+           bool(_flag("ignore_code", False)))
     b = _BINDINGS.get(key)
     if b is None:
         mods = dict(receiver=receiver, sender=sender, baseline_rec=baseline_rec, baseline_sen=baseline_sen)

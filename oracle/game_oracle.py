@@ -38,7 +38,7 @@ class GameConfig(object):
                  max_exchange=3, fixed_exchange=True, use_binary=True, entropy_s=None,
                  entropy_sen=None, entropy_rec=None, first_rec=0.0, s_prob_prod=True,
                  learning_rate=1e-4, optim_type="RMSprop", top_k_train=6, ignore_receiver=False,
-                 flipout_sen=None, flipout_rec=None):
+                 flipout_sen=None, flipout_rec=None, sender_mix="sum", ignore_code=False):
         assert sender_out_dim == rec_w_dim  # model.py:1756
         self.batch_size = batch_size
         self.img_feat_dim = img_feat_dim
@@ -63,6 +63,8 @@ class GameConfig(object):
         self.ignore_receiver = ignore_receiver
         self.flipout_sen = flipout_sen      # model.py:1710-1711 (None = off)
         self.flipout_rec = flipout_rec
+        self.sender_mix = sender_mix        # 'sum' | 'prod' (model.py:1692); 'mou' is not restated
+        self.ignore_code = ignore_code      # model.py:1704
 
     def as_dict(self):
         return dict(self.__dict__)
@@ -170,7 +172,14 @@ def sender_forward(P, x, w, t, cfg, train, u=None, u_flip=None):
         h_w = F.linear(first_code, P["code_layer.weight"], P["code_layer.bias"]).expand(x.shape[0], -1)
     else:
         h_w = F.linear(w, P["code_layer.weight"], P["code_layer.bias"])        # :207
-    feats = F.linear(torch.tanh(h_x + h_w), P["binary_layer.weight"], P["binary_layer.bias"])  # :216
+    assert cfg.sender_mix in ("sum", "prod")
+    if cfg.ignore_code:
+        mixed = h_x                                                             # :208-210
+    elif cfg.sender_mix == "prod":
+        mixed = h_x * h_w                                                       # :217-218
+    else:
+        mixed = h_x + h_w                                                       # :215-216
+    feats = F.linear(torch.tanh(mixed), P["binary_layer.weight"], P["binary_layer.bias"])
     if cfg.use_binary:
         probs = torch.sigmoid(feats)                                            # :223
         if train:

@@ -77,6 +77,18 @@ CASES = {
                                        max_exchange=3, fixed_exchange=True, use_binary=True, entropy_sen=0.01,
                                        entropy_rec=0.02, top_k_train=2, ignore_receiver=True, first_rec=1.0),
                               iters=2, seed=20),
+    # -sender_mix prod: tanh(h_x * h_w) (model.py:217-218)
+    "mix_prod": dict(cfg=dict(batch_size=6, img_feat_dim=40, img_h_dim=24, baseline_hid_dim=20,
+                              sender_out_dim=12, rec_hidden=16, rec_w_dim=12, wv_dim=20, n_classes=7,
+                              max_exchange=4, fixed_exchange=False, use_binary=True, entropy_sen=0.01,
+                              entropy_rec=0.02, entropy_s=0.05, top_k_train=2, sender_mix="prod"),
+                     iters=2, seed=25),
+    # -ignore_code: the sender never sees the receiver's message (model.py:208-210); code_layer / code_bias get no gradient
+    "ignore_code": dict(cfg=dict(batch_size=6, img_feat_dim=40, img_h_dim=24, baseline_hid_dim=20,
+                                 sender_out_dim=12, rec_hidden=16, rec_w_dim=12, wv_dim=20, n_classes=7,
+                                 max_exchange=3, fixed_exchange=True, use_binary=True, entropy_sen=0.01,
+                                 entropy_rec=0.02, top_k_train=2, ignore_code=True),
+                        iters=2, seed=26),
     # flipout noise on both messages (model.py:233-234,467-468,554-568): two extra uniform draws per step
     "flipout_small": dict(cfg=dict(batch_size=8, img_feat_dim=40, img_h_dim=24, baseline_hid_dim=20,
                                    sender_out_dim=12, rec_hidden=16, rec_w_dim=12, wv_dim=20, n_classes=7,
@@ -111,8 +123,8 @@ def _ref_modules(model, cfg, params):
     rs.set_flags(model, max_exchange=cfg.max_exchange, use_binary=cfg.use_binary,
                  fixed_exchange=cfg.fixed_exchange, entropy_s=cfg.entropy_s, entropy_sen=cfg.entropy_sen,
                  entropy_rec=cfg.entropy_rec, batch_size=cfg.batch_size, top_k_train=cfg.top_k_train,
-                 first_rec=cfg.first_rec, s_prob_prod=cfg.s_prob_prod, debug=False, sender_mix="sum",
-                 ignore_code=False, desc_attn=False, ignore_receiver=cfg.ignore_receiver, flipout_sen=cfg.flipout_sen,
+                 first_rec=cfg.first_rec, s_prob_prod=cfg.s_prob_prod, debug=False, sender_mix=cfg.sender_mix,
+                 ignore_code=cfg.ignore_code, desc_attn=False, ignore_receiver=cfg.ignore_receiver, flipout_sen=cfg.flipout_sen,
                  flipout_rec=cfg.flipout_rec, flipout_dev=False, cuda=False, rec_w_dim=cfg.rec_w_dim, sender_out_dim=cfg.sender_out_dim)
     sender = model.Sender("avgpool_512", cfg.img_feat_dim, cfg.img_h_dim, cfg.rec_w_dim, cfg.sender_out_dim,
                           cfg.use_binary, False, 0, False, 0)

@@ -17,7 +17,8 @@ def config_from(cfg, B=None, batch_global=None):
         use_binary=cfg.use_binary, entropy_s=cfg.entropy_s, entropy_sen=cfg.entropy_sen, entropy_rec=cfg.entropy_rec,
         first_rec=cfg.first_rec, s_prob_prod=cfg.s_prob_prod, learning_rate=cfg.learning_rate,
         optim_type=cfg.optim_type, ignore_receiver=cfg.ignore_receiver, batch_global=batch_global,
-        flipout_sen=getattr(cfg, "flipout_sen", None), flipout_rec=getattr(cfg, "flipout_rec", None))
+        flipout_sen=getattr(cfg, "flipout_sen", None), flipout_rec=getattr(cfg, "flipout_rec", None),
+        sender_mix=getattr(cfg, "sender_mix", "sum"), ignore_code=getattr(cfg, "ignore_code", False))
 
 
 def stack_uniforms(us, cfg, B):

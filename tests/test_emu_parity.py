@@ -6,7 +6,7 @@ import pytest
 from tests import emu_util, parity_util as pu
 
 CASES = ["fixed_small", "fixed_t1_noent", "continuous_t3", "adaptive_small", "adaptive_b1_adam", "adaptive_sgd",
-         "flipout_small", "ignore_rec_first1"]
+         "flipout_small", "ignore_rec_first1", "mix_prod", "ignore_code"]
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -57,3 +57,14 @@ def test_emulated_fast_path_flipout():
                         use_binary=True, entropy_s=0.05, entropy_sen=0.01, entropy_rec=0.02, top_k_train=2,
                         flipout_sen=0.2, flipout_rec=0.1)
     pu.run_synth_case(cfg, emu_util.emu_library(), "cpu", iters=2, seed=13, tag="fastflip")
+
+
+@pytest.mark.parametrize("mix,ignore", [("prod", False), ("sum", True)])
+def test_emulated_fast_path_sender_variants(mix, ignore):
+    """-sender_mix prod / -ignore_code (model.py:208-221) through the specialised kernels."""
+    from oracle import game_oracle as go
+    cfg = go.GameConfig(batch_size=3, img_feat_dim=40, img_h_dim=256, baseline_hid_dim=24, sender_out_dim=32,
+                        rec_hidden=64, rec_w_dim=32, wv_dim=12, n_classes=6, max_exchange=3, fixed_exchange=True,
+                        use_binary=True, entropy_sen=0.01, entropy_rec=0.02, top_k_train=2, sender_mix=mix,
+                        ignore_code=ignore)
+    pu.run_synth_case(cfg, emu_util.emu_library(), "cpu", iters=2, seed=15, tag="fast-" + mix)
