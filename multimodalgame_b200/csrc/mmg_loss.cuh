@@ -91,7 +91,16 @@ k_baseline_finish(Dims d, ParamPtrs P, WsPtrs W) {
     const float b2s = ldg(P.p[MMG_P_BS_L2_B]), b2r = ldg(P.p[MMG_P_BR_L2_B]);
     for (int r = blockIdx.x * 256 + threadIdx.x; r < d.R; r += gridDim.x * 256) {
         float s = b2s, q = b2r;
-        for (int j = 0; j < W.ntb; ++j) { s += W.bs_part[(size_t)r * W.ntb + j]; q += W.br_part[(size_t)r * W.ntb + j]; }
+        for (int j0 = 0; j0 < W.ntb; j0 += 8) {          // 16 partial loads in flight, added in tile order
+            float ps[8], pq[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                ps[u] = j0 + u < W.ntb ? W.bs_part[(size_t)r * W.ntb + j0 + u] : 0.f;
+                pq[u] = j0 + u < W.ntb ? W.br_part[(size_t)r * W.ntb + j0 + u] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { s += ps[u]; q += pq[u]; }
+        }
         W.bs[r] = s; W.br[r] = q;
     }
 }
@@ -111,7 +120,16 @@ k_stats(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, PeerView pv) {
     const float b2s = ldg(P.p[MMG_P_BS_L2_B]), b2r = ldg(P.p[MMG_P_BR_L2_B]);
     for (int r = tid; r < d.R; r += kStatsThreads) {
         float s = b2s, q = b2r;
-        for (int j = 0; j < W.ntb; ++j) { s += W.bs_part[(size_t)r * W.ntb + j]; q += W.br_part[(size_t)r * W.ntb + j]; }
+        for (int j0 = 0; j0 < W.ntb; j0 += 8) {          // 16 partial loads in flight, added in tile order
+            float ps[8], pq[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                ps[u] = j0 + u < W.ntb ? W.bs_part[(size_t)r * W.ntb + j0 + u] : 0.f;
+                pq[u] = j0 + u < W.ntb ? W.br_part[(size_t)r * W.ntb + j0 + u] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { s += ps[u]; q += pq[u]; }
+        }
         W.bs[r] = s; W.br[r] = q;
     }
     // ---- per example (one HALF-warp each, lanes over classes; 64 examples per round): prediction step, log-softmax,
@@ -228,20 +246,13 @@ k_stats(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, PeerView pv) {
 // Per (kind, t) coefficients derived from the (all-reduced) statistics.
 struct LossCoef { float cA, cE; };   // REINFORCE scale (step weight / n / max(1, std)), entropy scale (lambda * step weight / n)
 
-MMG_DEVICE void loss_coefs(const Dims& d, const mmg_config& cfg, const double* st, int kind, int t, LossCoef& out,
-                           double* n_out) {
+MMG_DEVICE void loss_coefs(const Dims& d, const mmg_config& cfg, const double* st, int kind, int t, double tot_kind,
+                           LossCoef& out) {
     const double n = st[stat_idx(d, kind, t, 0)];
-    *n_out = n;
     out.cA = 0.f; out.cE = 0.f;
     if (n <= 0.0) return;
     const int steps = (kind == 1) ? d.T - 1 : d.T;                 // list lengths, model.py:967
-    double sw;
-    if (d.fixed) sw = 1.0 / (double)steps;
-    else {
-        double tot = 0;
-        for (int tt = 0; tt < steps; ++tt) tot += st[stat_idx(d, kind, tt, 0)];
-        sw = n / tot;                                              // model.py:960-961
-    }
+    const double sw = d.fixed ? 1.0 / (double)steps : n / tot_kind;   // model.py:960-961, tot_kind = sum_t n_t of this loss
     double inv = 1.0;
     if (n > 1.0) {                                                 // model.py:914-915, unbiased std
         const double s1 = st[stat_idx(d, kind, t, 1)], s2 = st[stat_idx(d, kind, t, 2)];
@@ -293,14 +304,23 @@ MMG_DEVICE const double* loss_prologue(const Dims& d, const mmg_config& cfg, con
         MMG_SYNCTHREADS();
         st = st_s;
     }
-    for (int i = tid; i < 3 * d.T; i += kLossThreads) {
-        double n;
-        loss_coefs(d, cfg, st, i / d.T, i % d.T, coef[i], &n);
+    // active-row totals per loss kind: one warp each, lanes over steps (a serial accumulate would pay one memory round
+    // trip per step); only needed for adaptive-length conversations
+    MMG_SHARED double tot_s[3];
+    if (!d.fixed && tid < 96) {
+        const int kind = tid >> 5, lane = tid & 31;
+        const int steps = (kind == 1) ? d.T - 1 : d.T;
+        double v = 0.0;
+        for (int t = lane; t < steps; t += 32) v += st[stat_idx(d, kind, t, 0)];
+        v = warp_sum_d(v);
+        if (lane == 0) tot_s[kind] = v;
     }
+    MMG_SYNCTHREADS();
+    for (int i = tid; i < 3 * d.T; i += kLossThreads)
+        loss_coefs(d, cfg, st, i / d.T, i % d.T, d.fixed ? 0.0 : tot_s[i / d.T], coef[i]);
     if (tid == 0) {
-        double tot = 0;   // sum_t n_t over s_masks[:-1] (model.py:983); fixed: B_global * T (mean over steps of batch means)
-        for (int t = 0; t < d.T; ++t) tot += st[stat_idx(d, 0, t, 0)];
-        if (d.fixed) tot = (double)d.Bg * d.T;
+        // sum_t n_t over s_masks[:-1] (model.py:983); fixed: B_global * T (mean over steps of batch means)
+        const double tot = d.fixed ? (double)d.Bg * d.T : tot_s[0];
         bas_scale[0] = tot > 0 ? (float)(1.0 / tot) : 0.f;
     }
     MMG_SYNCTHREADS();

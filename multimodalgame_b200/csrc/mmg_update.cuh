@@ -261,8 +261,19 @@ MMG_DEVICE void update_body(const SegInfo& seg, const OptHyper& hp, float* param
     MMG_SHARED float coef[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (warp < 4) {   // global L2 norm per module, partials summed in a fixed order
+        // per-CTA partials of this module: all loads in flight together (a plain accumulate loop would pay one L2 round
+        // trip per element), added in a fixed order
         double v = 0.0;
-        for (int c = lane; c < n_norm_ctas; c += 32) v += (double)norm_part[warp * n_norm_ctas + c];
+        for (int c0 = 0; c0 < n_norm_ctas; c0 += 32 * 8) {
+            float pv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = c0 + u * 32 + lane;
+                pv[u] = c < n_norm_ctas ? norm_part[warp * n_norm_ctas + c] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v += (double)pv[u];
+        }
         v = warp_sum_d(v);
         if (lane == 0) {
             const float total = (float)sqrt(v);
