@@ -38,7 +38,8 @@ class GameConfig(object):
                  max_exchange=3, fixed_exchange=True, use_binary=True, entropy_s=None,
                  entropy_sen=None, entropy_rec=None, first_rec=0.0, s_prob_prod=True,
                  learning_rate=1e-4, optim_type="RMSprop", top_k_train=6, ignore_receiver=False,
-                 flipout_sen=None, flipout_rec=None, sender_mix="sum", ignore_code=False):
+                 flipout_sen=None, flipout_rec=None, sender_mix="sum", ignore_code=False, desc_attn=False,
+                 desc_attn_dim=64):
         assert sender_out_dim == rec_w_dim  # model.py:1756
         self.batch_size = batch_size
         self.img_feat_dim = img_feat_dim
@@ -65,6 +66,8 @@ class GameConfig(object):
         self.flipout_rec = flipout_rec
         self.sender_mix = sender_mix        # 'sum' | 'prod' (model.py:1692); 'mou' is not restated
         self.ignore_code = ignore_code      # model.py:1704
+        self.desc_attn = desc_attn          # model.py:1719-1720: the receiver attends over the words of every class description
+        self.desc_attn_dim = desc_attn_dim
 
     def as_dict(self):
         return dict(self.__dict__)
@@ -121,6 +124,14 @@ def init_params(cfg, seed=0):
     rec["y2.bias"] = z(1)
     rec["s.weight"] = _xavier_normal_(z(1, Hr), g)
     rec["s.bias"] = z(1)
+    if cfg.desc_attn:                                                             # model.py:267-271
+        A = cfg.desc_attn_dim
+        rec["d_d.weight"] = _xavier_normal_(z(A, WV), g)
+        rec["d_d.bias"] = z(A)
+        rec["d_h.weight"] = _xavier_normal_(z(A, Hr), g)
+        rec["d_h.bias"] = z(A)
+        rec["d_attn.weight"] = _xavier_normal_(z(1, A), g)
+        rec["d_attn.bias"] = z(1)
     bsen = OrderedDict()
     bsen["linear1.weight"], bsen["linear1.bias"] = z(Hb, Hi + M), z(Hb)
     _torch_default_linear_(bsen["linear1.weight"], bsen["linear1.bias"], g)
@@ -212,15 +223,37 @@ def gru_cell(P, z, h):
     return n + u * (h - n)
 
 
-def receiver_forward(P, z, desc, state, cfg, train, u_s=None, u_w=None, u_flip=None):
-    """Receiver.forward default path (no -desc_attn): model.py:333-342, 412-477.
+def attend_descriptions(P, h_z, desc_set, desc_set_lens):
+    """-desc_attn (model.py:344-410): additive attention of the hidden state over the NW description words,
+    softmax within each class's word segment, per-(example, class) weighted bag of words.
+    Returns (B, D, WV)."""
+    dd = F.linear(desc_set, P["d_d.weight"], P["d_d.bias"])                       # :352  NW x A
+    dh = F.linear(h_z, P["d_h.weight"], P["d_h.bias"])                            # :359  B x A
+    e = F.linear(torch.tanh(dd.unsqueeze(0) + dh.unsqueeze(1)), P["d_attn.weight"], P["d_attn.bias"]).squeeze(2)  # :366
+    out, start = [], 0
+    for n in desc_set_lens:                                                       # :372-397
+        a = torch.softmax(e[:, start:start + n], 1)                               # B x NW_i
+        out.append((a.unsqueeze(2) * desc_set[start:start + n].unsqueeze(0)).sum(1, keepdim=True))
+        start += n
+    return torch.cat(out, 1)
+
+
+def receiver_forward(P, z, desc, state, cfg, train, u_s=None, u_w=None, u_flip=None, desc_set=None,
+                     desc_set_lens=None):
+    """Receiver.forward: model.py:333-342, 412-477; -desc_attn branch 344-410.
     `state` = dict(h_z, s_prob_prod) mutated like the module attributes.
     Returns ((s_binary, s_prob), (w_feats, w_probs), y)."""
     B = z.shape[0]
     if state.get("h_z") is None:
         state["h_z"] = torch.zeros(B, cfg.rec_hidden)                            # :336-337
     h_z = state["h_z"] = gru_cell(P, z, state["h_z"])                            # :340
-    inp = build_inp(h_z, desc)                                                   # :412
+    if cfg.desc_attn:
+        weighted_desc = attend_descriptions(P, h_z, desc_set, desc_set_lens)     # B x D x WV
+        D = weighted_desc.shape[1]
+        inp = torch.cat([weighted_desc.reshape(B * D, -1),
+                         h_z.unsqueeze(1).expand(B, D, h_z.shape[1]).reshape(B * D, -1)], 1)   # :408-410 [desc ; h_z]
+    else:
+        inp = build_inp(h_z, desc)                                               # :412
     s_prob = torch.sigmoid(F.linear(h_z, P["s.weight"], P["s.bias"]))            # :414-415
     if train:
         s_binary = _bernoulli(s_prob, u_s)                                       # :418-420
@@ -233,7 +266,8 @@ def receiver_forward(P, z, desc, state, cfg, train, u_s=None, u_w=None, u_flip=N
     y = F.linear(inp, P["y1.weight"], P["y1.bias"]).clamp(min=0)                 # :432
     y = F.linear(y, P["y2.weight"], P["y2.bias"]).view(B, -1)                    # :433
     y_scores = torch.softmax(y, 1).detach()                                      # :441
-    wd_inp = (y_scores.unsqueeze(2) * desc.unsqueeze(0)).sum(1)                  # :442-449
+    wd_src = weighted_desc if cfg.desc_attn else desc.unsqueeze(0)               # :444-448 (not detached)
+    wd_inp = (y_scores.unsqueeze(2) * wd_src).sum(1)                             # :442-449
     h_w = torch.tanh(F.linear(h_z, P["w_h.weight"], P["w_h.bias"]) + F.linear(wd_inp, P["w_d.weight"]))  # :452
     state["h_w"] = h_w
     w_scores = F.linear(h_w, P["w.weight"], P["w.bias"])                         # :454
@@ -262,7 +296,8 @@ def baseline_forward(P, x, binary, inp):
 # ------------------------------------------------------------------------------------------------
 # exchange (model.py:725-876)
 # ------------------------------------------------------------------------------------------------
-def exchange(params, x, desc, cfg, train, uniforms=None, break_early=False, corrupt_mask=None):
+def exchange(params, x, desc, cfg, train, uniforms=None, break_early=False, corrupt_mask=None, desc_set=None,
+             desc_set_lens=None):
     """`uniforms`: per step a triple (u_z (B,M), u_s (B,1), u_w (B,M)) of float64 arrays (train only).
     `corrupt_mask`: optional (M,) 0/1 tensor XOR-ed onto the sender message (model.py:814-820).
     Returns a dict with the reference's lists: stop_mask[T'+1] (uint8), stop_feat, stop_prob, sen_feats,
@@ -281,7 +316,7 @@ def exchange(params, x, desc, cfg, train, uniforms=None, break_early=False, corr
         if corrupt_mask is not None:
             z_binary = (z_binary - corrupt_mask.view(1, -1)).abs()                  # :814-820
         (s_binary, s_prob), (w_binary, w_probs), outp = receiver_forward(
-            R, z_binary.detach(), desc.detach(), state, cfg, train, u[1], u[2], u[4])     # :826-829
+            R, z_binary.detach(), desc.detach(), state, cfg, train, u[1], u[2], u[4], desc_set, desc_set_lens)  # :826-829
         if train:
             out["bs"].append(baseline_forward(params["baseline_sen"], h_x.detach(), z_r.detach(), None))   # :835-836
             out["br"].append(baseline_forward(params["baseline_rec"], None, z_binary.detach(),
@@ -466,14 +501,16 @@ def optimizer_step(p, g, st, cfg):
         raise NotImplementedError(cfg.optim_type)
 
 
-def train_iteration(params, opt_state, x, target, desc, cfg, uniforms, return_grads=False):
+def train_iteration(params, opt_state, x, target, desc, cfg, uniforms, return_grads=False, desc_set=None,
+                    desc_set_lens=None):
     """One iteration of run()'s loop body: model.py:1229-1339.  `params` (leaf tensors) are updated in
     place.  Returns (exchange dict, losses dict[, grads])."""
     for a in params:
         for v in params[a].values():
             v.requires_grad_(True)
             v.grad = None
-    ex = exchange(params, x, desc, cfg, True, uniforms, break_early=not cfg.fixed_exchange)
+    ex = exchange(params, x, desc, cfg, True, uniforms, break_early=not cfg.fixed_exchange, desc_set=desc_set,
+                  desc_set_lens=desc_set_lens)
     res = compute_losses(ex, target, cfg)
     plan = [("receiver", "loss_rec")]
     if cfg.use_binary:
@@ -513,6 +550,14 @@ def draw_uniforms(rng, cfg, B=None, steps=None):
         u_fw = rng.rand(B, M) if cfg.flipout_rec is not None else None
         out.append((u_z, u_s, u_w, u_fz, u_fw) if (u_fz is not None or u_fw is not None) else (u_z, u_s, u_w))
     return out
+
+
+def synthetic_desc_set(cfg, seed=0, min_words=1, max_words=12):
+    """Ragged word-level descriptions for -desc_attn: (desc_set (NW, WV), desc_set_lens [D]); the real data has
+    3..20 words per class (NW = 259 for the 30-class set)."""
+    g = torch.Generator().manual_seed(2000 + seed)
+    lens = [int(v) for v in torch.randint(min_words, max_words + 1, (cfg.n_classes,), generator=g)]
+    return torch.randn(sum(lens), cfg.wv_dim, generator=g), lens
 
 
 def synthetic_batch(cfg, seed=0, B=None):

@@ -95,6 +95,18 @@ CASES = {
                                    max_exchange=4, fixed_exchange=False, use_binary=True, entropy_sen=0.01,
                                    entropy_rec=0.02, entropy_s=0.05, top_k_train=2, flipout_sen=0.15, flipout_rec=0.1),
                           iters=2, seed=19),
+    # -desc_attn (model.py:344-410): ragged word-level attention, adaptive length so that prediction steps differ
+    "desc_attn_small": dict(cfg=dict(batch_size=7, img_feat_dim=40, img_h_dim=24, baseline_hid_dim=20,
+                                     sender_out_dim=12, rec_hidden=16, rec_w_dim=12, wv_dim=20, n_classes=6,
+                                     max_exchange=4, fixed_exchange=False, use_binary=True, entropy_sen=0.01,
+                                     entropy_rec=0.02, entropy_s=0.05, top_k_train=2, desc_attn=True, desc_attn_dim=10),
+                            iters=3, seed=27),
+    # -desc_attn at the headline agent shapes (fast-path dimensions), fixed length, 30 classes x 3..14 words
+    "desc_attn_mid": dict(cfg=dict(batch_size=16, img_feat_dim=64, img_h_dim=256, baseline_hid_dim=32,
+                                   sender_out_dim=32, rec_hidden=64, rec_w_dim=32, wv_dim=100, n_classes=30,
+                                   max_exchange=5, fixed_exchange=True, use_binary=True, entropy_sen=0.01,
+                                   entropy_rec=0.01, top_k_train=6, desc_attn=True, desc_attn_dim=64),
+                          iters=1, seed=28, words=(3, 14)),
 }
 
 EVAL_CASES = {
@@ -115,6 +127,11 @@ EVAL_CASES = {
                                      sender_out_dim=12, rec_hidden=16, rec_w_dim=12, wv_dim=20, n_classes=7,
                                      max_exchange=3, fixed_exchange=True, use_binary=False),
                             seed=24, corrupt_region=None, s_bias=0.0),
+    "eval_desc_attn": dict(cfg=dict(batch_size=9, img_feat_dim=40, img_h_dim=24, baseline_hid_dim=20,
+                                    sender_out_dim=12, rec_hidden=16, rec_w_dim=12, wv_dim=20, n_classes=6,
+                                    max_exchange=5, fixed_exchange=False, use_binary=True, desc_attn=True,
+                                    desc_attn_dim=10),
+                           seed=29, corrupt_region=None, s_bias=0.3),
 }
 
 
@@ -124,7 +141,7 @@ def _ref_modules(model, cfg, params):
                  fixed_exchange=cfg.fixed_exchange, entropy_s=cfg.entropy_s, entropy_sen=cfg.entropy_sen,
                  entropy_rec=cfg.entropy_rec, batch_size=cfg.batch_size, top_k_train=cfg.top_k_train,
                  first_rec=cfg.first_rec, s_prob_prod=cfg.s_prob_prod, debug=False, sender_mix=cfg.sender_mix,
-                 ignore_code=cfg.ignore_code, desc_attn=False, ignore_receiver=cfg.ignore_receiver, flipout_sen=cfg.flipout_sen,
+                 ignore_code=cfg.ignore_code, desc_attn=cfg.desc_attn, desc_attn_dim=cfg.desc_attn_dim, ignore_receiver=cfg.ignore_receiver, flipout_sen=cfg.flipout_sen,
                  flipout_rec=cfg.flipout_rec, flipout_dev=False, cuda=False, rec_w_dim=cfg.rec_w_dim, sender_out_dim=cfg.sender_out_dim)
     sender = model.Sender("avgpool_512", cfg.img_feat_dim, cfg.img_h_dim, cfg.rec_w_dim, cfg.sender_out_dim,
                           cfg.use_binary, False, 0, False, 0)
@@ -181,11 +198,17 @@ def make_train_case(model, name, spec):
         x, desc, target = go.synthetic_batch(cfg, seed=spec["seed"] * 10 + it)
         pre = "it%d/" % it
         out[pre + "x"], out[pre + "desc"], out[pre + "target"] = x.numpy(), desc.numpy(), target.numpy()
+        extra = {}
+        if cfg.desc_attn:
+            lo, hi = spec.get("words", (1, 9))
+            desc_set, lens = go.synthetic_desc_set(cfg, seed=spec["seed"] * 10 + it, min_words=lo, max_words=hi)
+            out[pre + "desc_set"], out[pre + "desc_set_lens"] = desc_set.numpy(), np.array(lens, np.int32)
+            extra = dict(desc_set=desc_set, desc_set_lens=lens)
         sink = []
         with rs.legacy_semantics(), rs.record_uniforms(spec["seed"] * 100 + it, sink):
             s, sen_w, rec_w, y, bs, br = model.exchange(
                 mods["sender"], mods["receiver"], mods["baseline_sen"], mods["baseline_rec"],
-                dict(data=x, target=target, desc=desc, train=True, break_early=not cfg.fixed_exchange))
+                dict(data=x, target=target, desc=desc, train=True, break_early=not cfg.fixed_exchange, **extra))
             ns = dict(model.__dict__)
             ns.update(s=s, sen_w=sen_w, rec_w=rec_w, y=y, bs=bs, br=br, target=target,
                       sender=mods["sender"], receiver=mods["receiver"], baseline_sen=mods["baseline_sen"],
@@ -260,11 +283,16 @@ def make_eval_case(model, name, spec):
             out["P0/%s/%s" % (a, k)] = v.numpy().copy()
     x, desc, target = go.synthetic_batch(cfg, seed=spec["seed"])
     out["x"], out["desc"], out["target"] = x.numpy(), desc.numpy(), target.numpy()
+    extra = {}
+    if cfg.desc_attn:
+        desc_set, lens = go.synthetic_desc_set(cfg, seed=spec["seed"], min_words=1, max_words=9)
+        out["desc_set"], out["desc_set_lens"] = desc_set.numpy(), np.array(lens, np.int32)
+        extra = dict(desc_set=desc_set, desc_set_lens=lens)
     with rs.legacy_semantics(), torch.no_grad():
         s, sen_w, rec_w, y, bs, br = model.exchange(
             mods["sender"], mods["receiver"], None, None,
             dict(data=x, target=target, desc=desc, train=False, break_early=not cfg.fixed_exchange,
-                 corrupt=spec["corrupt_region"] is not None, corrupt_region=spec["corrupt_region"]))
+                 corrupt=spec["corrupt_region"] is not None, corrupt_region=spec["corrupt_region"], **extra))
         if cfg.fixed_exchange:
             y_masks = None
         else:
@@ -284,9 +312,9 @@ def main():
         if only and name not in only:
             continue
         make_train_case(model, name, spec)
-    if only:
-        return
     for name, spec in EVAL_CASES.items():
+        if only and name not in only:
+            continue
         make_eval_case(model, name, spec)
 
 

@@ -13,6 +13,8 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 TRAIN_CASES = ["c1_continuous", "continuous_t3", "fixed_small", "fixed_t1_noent", "adaptive_small",
                "adaptive_b1_adam", "headline_mid", "adaptive_sgd", "flipout_small", "ignore_rec_first1", "mix_prod", "ignore_code"]
+ATTN_TRAIN_CASES = ["desc_attn_small", "desc_attn_mid"]      # -desc_attn (model.py:344-410)
+ATTN_EVAL_CASES = ["eval_desc_attn"]
 EVAL_CASES = ["eval_adaptive", "eval_adaptive_noprod", "eval_fixed_corrupt", "eval_continuous"]
 
 
@@ -52,6 +54,15 @@ def pad_uniforms(us, cfg, B, seed=99):
     while len(us) < cfg.max_exchange:
         us.append((rng.rand(B, cfg.rec_w_dim), rng.rand(B, 1), rng.rand(B, cfg.rec_w_dim)))
     return us
+
+
+def desc_set_at(z, it=None):
+    """-desc_attn fixtures: dict(desc_set=(NW, WV) tensor, desc_set_lens=[D]) or {}."""
+    pre = "" if it is None else "it%d/" % it
+    if pre + "desc_set" not in z.files:
+        return {}
+    return dict(desc_set=torch.from_numpy(z[pre + "desc_set"].copy()),
+                desc_set_lens=[int(v) for v in z[pre + "desc_set_lens"]])
 
 
 def batch_at(z, it):
