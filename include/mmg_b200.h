@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MMG_ABI_VERSION 1
+#define MMG_ABI_VERSION 2
 
 typedef enum mmg_status {
     MMG_OK = 0,
@@ -70,6 +70,9 @@ typedef struct mmg_config {
     float flipout_sen, flipout_rec;           /* bit-flip probabilities (model.py:233-234,467-468,554-568) */
     int32_t sender_mix;      /* MMG_MIX_SUM: tanh(h_x + h_w); MMG_MIX_PROD: tanh(h_x * h_w)  (model.py:1692,208-221); "mou" unsupported */
     int32_t ignore_code;     /* model.py:1704,208-213: the sender ignores the receiver's message, hidden = tanh(h_x) */
+    int32_t desc_attn;       /* model.py:1719,344-410: the receiver attends over the words of each class description */
+    int32_t desc_attn_dim;   /* A   model.py:1720 */
+    int32_t n_words;         /* NW  rows of `desc_set` (sum of desc_set_lens); only read when desc_attn != 0 */
 } mmg_config;
 
 /* ---- parameter layout -------------------------------------------------------------------------------
@@ -87,12 +90,20 @@ enum {
     MMG_P_REC_WD_W,         /* receiver.w_d.weight      (Hr, WV)   model.py:259 (no bias) */
     MMG_P_REC_W_W,          /* receiver.w.weight        (M, Hr)    model.py:260 */
     MMG_P_REC_W_B,          /* receiver.w.bias          (M)       */
-    MMG_P_REC_Y1_W,         /* receiver.y1.weight       (Hr, Hr+WV) columns [h_z ; desc]  model.py:262,548 */
+    MMG_P_REC_Y1_W,         /* receiver.y1.weight       (Hr, Hr+WV) columns [h_z ; desc]  model.py:262,548;
+                               with desc_attn the columns are [desc ; h_z]  model.py:408-410 */
     MMG_P_REC_Y1_B,         /* receiver.y1.bias         (Hr)      */
     MMG_P_REC_Y2_W,         /* receiver.y2.weight       (1, Hr)    model.py:263 */
     MMG_P_REC_Y2_B,         /* receiver.y2.bias         (1)       */
     MMG_P_REC_S_W,          /* receiver.s.weight        (1, Hr)    model.py:265 */
     MMG_P_REC_S_B,          /* receiver.s.bias          (1)       */
+    /* desc_attn only (zero-sized otherwise), model.py:267-271 */
+    MMG_P_REC_DD_W,         /* receiver.d_d.weight      (A, WV)   */
+    MMG_P_REC_DD_B,         /* receiver.d_d.bias        (A)       */
+    MMG_P_REC_DH_W,         /* receiver.d_h.weight      (A, Hr)   */
+    MMG_P_REC_DH_B,         /* receiver.d_h.bias        (A)       */
+    MMG_P_REC_DA_W,         /* receiver.d_attn.weight   (1, A)    */
+    MMG_P_REC_DA_B,         /* receiver.d_attn.bias     (1)       */
     MMG_P_SEN_CODE_BIAS,    /* sender.code_bias         (M)        model.py:69 */
     MMG_P_SEN_IMG_W,        /* sender.image_layer.weight (Hi, F)   model.py:67 */
     MMG_P_SEN_IMG_B,        /* sender.image_layer.bias  (Hi)      */
@@ -195,6 +206,10 @@ typedef struct mmg_inputs {
      * agent (model.py:233-234 after 227; 467-468 after 460); NULL: on-device Philox stream */
     const double* d_u_flip_sen;
     const double* d_u_flip_rec;
+    /* desc_attn only (model.py:765-766): the words of all class descriptions, class after class, and the number of
+     * words of each class; every class has at least one word */
+    const float* d_desc_set;        /* (NW,WV) exchange_args["desc_set"] */
+    const int32_t* d_desc_set_lens; /* (D)     exchange_args["desc_set_lens"] */
 } mmg_inputs;
 
 int mmg_abi_version(void);

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libmmg_b200.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 
-MMG_P_COUNT = 30
+MMG_P_COUNT = 36
 MMG_SEG_COUNT = 4
 MMG_LOSS_COUNT = 16
 
@@ -21,6 +21,8 @@ PARAM_NAMES = [
     ("receiver", "rnn.bias_hh"), ("receiver", "w_h.weight"), ("receiver", "w_h.bias"), ("receiver", "w_d.weight"),
     ("receiver", "w.weight"), ("receiver", "w.bias"), ("receiver", "y1.weight"), ("receiver", "y1.bias"),
     ("receiver", "y2.weight"), ("receiver", "y2.bias"), ("receiver", "s.weight"), ("receiver", "s.bias"),
+    ("receiver", "d_d.weight"), ("receiver", "d_d.bias"), ("receiver", "d_h.weight"), ("receiver", "d_h.bias"),
+    ("receiver", "d_attn.weight"), ("receiver", "d_attn.bias"),      # -desc_attn only, zero-sized otherwise
     ("sender", "code_bias"), ("sender", "image_layer.weight"), ("sender", "image_layer.bias"),
     ("sender", "code_layer.weight"), ("sender", "code_layer.bias"), ("sender", "binary_layer.weight"),
     ("sender", "binary_layer.bias"),
@@ -44,7 +46,7 @@ class Config(C.Structure):
         (n, C.c_float) for n in ("entropy_s", "entropy_sen", "entropy_rec", "first_rec", "learning_rate", "max_norm")
     ] + [("ignore_receiver", C.c_int32), ("has_flipout_sen", C.c_int32), ("has_flipout_rec", C.c_int32),
          ("flipout_dev", C.c_int32), ("flipout_sen", C.c_float), ("flipout_rec", C.c_float), ("sender_mix", C.c_int32),
-         ("ignore_code", C.c_int32)]
+         ("ignore_code", C.c_int32), ("desc_attn", C.c_int32), ("desc_attn_dim", C.c_int32), ("n_words", C.c_int32)]
 
 
 class ParamLayout(C.Structure):
@@ -67,7 +69,7 @@ class Inputs(C.Structure):
     _fields_ = [("d_x", C.c_void_p), ("d_desc", C.c_void_p), ("d_target", C.c_void_p), ("d_u_sen", C.c_void_p),
                 ("d_u_stop", C.c_void_p), ("d_u_rec", C.c_void_p), ("d_corrupt_mask", C.c_void_p),
                 ("d_h0", C.c_void_p), ("top_k", C.c_int32), ("train", C.c_int32), ("d_u_flip_sen", C.c_void_p),
-                ("d_u_flip_rec", C.c_void_p)]
+                ("d_u_flip_rec", C.c_void_p), ("d_desc_set", C.c_void_p), ("d_desc_set_lens", C.c_void_p)]
 
 
 MMG_MAX_PEERS = 8

@@ -50,11 +50,16 @@ static int validate(const mmg_config* c) {
     if (c->optim_type < 0 || c->optim_type > 2) return fail(MMG_ERR_INVALID, "optim_type=%d", c->optim_type);
     if (c->sender_mix != MMG_MIX_SUM && c->sender_mix != MMG_MIX_PROD) return fail(MMG_ERR_UNSUPPORTED, "sender_mix=%d (mou is not built)", c->sender_mix);
     if ((long long)c->max_exchange * c->batch > (1ll << 24)) return fail(MMG_ERR_UNSUPPORTED, "T*B too large");
+    if (c->desc_attn) {
+        if (c->desc_attn_dim < 1 || c->desc_attn_dim > 256) return fail(MMG_ERR_INVALID, "desc_attn_dim=%d", c->desc_attn_dim);
+        if (c->n_words < c->n_classes) return fail(MMG_ERR_INVALID, "n_words=%d < n_classes=%d (every class needs a word)", c->n_words, c->n_classes);
+        if (c->n_words > 4096) return fail(MMG_ERR_UNSUPPORTED, "n_words=%d > 4096", c->n_words);
+    }
     return MMG_OK;
 }
 
 static void param_layout(const Dims& d, mmg_param_layout* L) {
-    const int Hr = d.Hr, M = d.M, WV = d.WV, Hi = d.Hi, F = d.F, Hb = d.Hb;
+    const int Hr = d.Hr, M = d.M, WV = d.WV, Hi = d.Hi, F = d.F, Hb = d.Hb, A = d.A, on = d.A ? 1 : 0;
     struct E { int id, rows, cols, seg; };
     const E tab[MMG_P_COUNT] = {
         {MMG_P_REC_RNN_WIH, 3 * Hr, M, 0}, {MMG_P_REC_RNN_WHH, 3 * Hr, Hr, 0}, {MMG_P_REC_RNN_BIH, 3 * Hr, 1, 0},
@@ -62,6 +67,8 @@ static void param_layout(const Dims& d, mmg_param_layout* L) {
         {MMG_P_REC_WD_W, Hr, WV, 0}, {MMG_P_REC_W_W, M, Hr, 0}, {MMG_P_REC_W_B, M, 1, 0},
         {MMG_P_REC_Y1_W, Hr, Hr + WV, 0}, {MMG_P_REC_Y1_B, Hr, 1, 0}, {MMG_P_REC_Y2_W, 1, Hr, 0},
         {MMG_P_REC_Y2_B, 1, 1, 0}, {MMG_P_REC_S_W, 1, Hr, 0}, {MMG_P_REC_S_B, 1, 1, 0},
+        {MMG_P_REC_DD_W, A, on * WV, 0}, {MMG_P_REC_DD_B, A, on, 0}, {MMG_P_REC_DH_W, A, on * Hr, 0}, {MMG_P_REC_DH_B, A, on, 0},
+        {MMG_P_REC_DA_W, on, A, 0}, {MMG_P_REC_DA_B, on, on, 0},
         {MMG_P_SEN_CODE_BIAS, M, 1, 1}, {MMG_P_SEN_IMG_W, Hi, F, 1}, {MMG_P_SEN_IMG_B, Hi, 1, 1},
         {MMG_P_SEN_CODE_W, Hi, M, 1}, {MMG_P_SEN_CODE_B, Hi, 1, 1}, {MMG_P_SEN_BIN_W, M, Hi, 1},
         {MMG_P_SEN_BIN_B, M, 1, 1},
@@ -167,6 +174,21 @@ static void ws_layout(const Dims& d, Ws* w) {
     w->tickets = take(c, 8 * 4);
     w->opt_counters = take(c, 4 * 8);
     p.opt_counters = w->opt_counters;
+    if (d.A) {
+        const int64_t NW = d.NW, A = d.A;
+        w->wtab_dd = take(c, NW * A * f);
+        w->wtab_y1 = take(c, NW * d.Hr * f);
+        w->wtab_wd = take(c, NW * d.Hr * f);
+        w->seg = take(c, (d.D + 1) * 4);
+        w->wcls = take(c, NW * 4);
+        w->attn = take(c, R * NW * f);
+        w->dh_s = take(c, R * A * f);
+        w->ddh = take(c, R * A * f);
+        w->dva = take(c, R * A * f);
+        w->dba = take(c, R * f);
+        w->ddd_part = take(c, B * NW * A * f);      // at most one receiver CTA per example
+        w->wdsel = take(c, B * d.D * d.WV * f);
+    }
     p.total_bytes = c;
 }
 
@@ -192,6 +214,10 @@ static WsPtrs resolve(const Ws& w, void* base) {
     r.loss_part = (double*)(b + w.loss_part);
     r.tickets = (unsigned*)(b + w.tickets);
     r.opt_counters = (long long*)(b + w.opt_counters);
+#define G_(name) r.name = (float*)(b + w.name)
+    G_(wtab_dd); G_(wtab_y1); G_(wtab_wd); G_(attn); G_(dh_s); G_(ddh); G_(dva); G_(dba); G_(ddd_part); G_(wdsel);
+#undef G_
+    r.seg = (int*)(b + w.seg); r.wcls = (int*)(b + w.wcls);
     r.hx_split = w.hx_split; r.wgrad_split = w.wgrad_split; r.ntb = w.ntb;
     return r;
 }
@@ -208,10 +234,21 @@ static ExchangeInputs resolve_inputs(const mmg_inputs* in) {
     e.u_sen = in->d_u_sen; e.u_stop = in->d_u_stop; e.u_rec = in->d_u_rec;
     e.u_flip_sen = in->d_u_flip_sen; e.u_flip_rec = in->d_u_flip_rec;
     e.corrupt_mask = in->d_corrupt_mask; e.h0 = in->d_h0; e.top_k = in->top_k; e.train = in->train;
+    e.desc_set = in->d_desc_set; e.desc_set_lens = in->d_desc_set_lens;
     return e;
 }
 
 struct Plan { int BT; int sender_smem; int fwd_smem_bytes; int bwd_smem_bytes; int fast; };
+
+static AttnArgs attn_args(const Dims& d, const ParamPtrs& P, const ExchangeInputs& in) {
+    AttnArgs a;
+    memset(&a, 0, sizeof(a));
+    if (d.A) {
+        a.dh_w = P.p[MMG_P_REC_DH_W]; a.dh_b = P.p[MMG_P_REC_DH_B]; a.va = P.p[MMG_P_REC_DA_W]; a.ba = P.p[MMG_P_REC_DA_B];
+        a.b1 = P.p[MMG_P_REC_Y1_B]; a.desc_set = in.desc_set;
+    }
+    return a;
+}
 
 static int choose_bt(int B) {
     if (B <= 148) return 1;
@@ -293,18 +330,18 @@ static int set_smem(K, int) { return MMG_OK; }
 
 template <int BT>
 static int launch_fwd(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const float* b_img, const Plan& pl,
-                      cudaStream_t st) {
+                      cudaStream_t st, const AttnArgs& aa) {
     int rc = set_smem(k_exchange_fwd<BT>, pl.fwd_smem_bytes);
     if (rc) return rc;
-    MMG_LAUNCH(k_exchange_fwd<BT>, cdiv(d.B, BT), kLoopThreads, pl.fwd_smem_bytes, st, d, W, in, b_img, pl.sender_smem, 0);
+    MMG_LAUNCH(k_exchange_fwd<BT>, cdiv(d.B, BT), kLoopThreads, pl.fwd_smem_bytes, st, d, W, in, b_img, pl.sender_smem, 0, aa);
     return check_cuda("k_exchange_fwd");
 }
 template <int BT>
-static int launch_bwd(const Dims& d, const WsPtrs& W, const Plan& pl, cudaStream_t st) {
+static int launch_bwd(const Dims& d, const WsPtrs& W, const Plan& pl, cudaStream_t st, const AttnArgs& aa) {
     int rc = set_smem(k_exchange_bwd<BT>, pl.bwd_smem_bytes);
     if (rc) return rc;
     const int n_rec = cdiv(d.B, BT), n_sen = d.use_binary ? cdiv(d.B, BT) : 0;
-    MMG_LAUNCH(k_exchange_bwd<BT>, n_rec + n_sen, kLoopThreads, pl.bwd_smem_bytes, st, d, W, n_rec);
+    MMG_LAUNCH(k_exchange_bwd<BT>, n_rec + n_sen, kLoopThreads, pl.bwd_smem_bytes, st, d, W, n_rec, aa);
     return check_cuda("k_exchange_bwd");
 }
 
@@ -392,7 +429,7 @@ struct WgBuilder {
 };
 
 static void build_wgrad_table(const Dims& d, const mmg_param_layout& L, const ParamPtrs& P, const WsPtrs& W,
-                              const ExchangeInputs& in, int fast, WgTable* t, SplitTable* st) {
+                              const ExchangeInputs& in, int fast, int n_rec_ctas, WgTable* t, SplitTable* st) {
     t->count = 0; t->total_tiles = 0; t->slab_stride = L.total;
     for (int i = 0; i < MMG_P_COUNT; ++i) {
         st->begin[i] = L.offset[i]; st->numel[i] = L.rows[i] * L.cols[i]; st->nsplit[i] = 0;   // 0: no problem writes this tensor
@@ -408,11 +445,20 @@ static void build_wgrad_table(const Dims& d, const mmg_param_layout& L, const Pa
     b.add(km(W.d_hw, Hr), km(h_after, Hr), Hr, Hr, R, MMG_P_REC_WH_W, 0, MMG_P_REC_WH_B);
     b.add(km(W.d_hw, Hr), km(W.wd, d.WV), Hr, d.WV, R, MMG_P_REC_WD_W, 0, -1);
     b.add(km(W.d_ls, 1), km(h_after, Hr), 1, Hr, R, MMG_P_REC_S_W, 0, MMG_P_REC_S_B, WG_ROWVEC);
-    b.add(km(W.g_h, Hr), km(W.hsel, Hr), Hr, Hr, B, MMG_P_REC_Y1_W, 0, -1);
-    {
+    b.add(km(W.g_h, Hr), km(W.hsel, Hr), Hr, Hr, B, MMG_P_REC_Y1_W, d.y1_hcol, -1);
+    if (d.A) {
+        // -desc_attn: the description rows of y1's input are the attended bags of words of the prediction step
+        b.add(km(W.dy1, Hr), km(W.wdsel, d.WV), Hr, d.WV, B * d.D, MMG_P_REC_Y1_W, d.y1_dcol, MMG_P_REC_Y1_B);
+        b.add(km(W.ddh, d.A), km(h_after, Hr), d.A, Hr, R, MMG_P_REC_DH_W, 0, MMG_P_REC_DH_B);
+        b.add(km(W.dva, d.A), ones(), d.A, 1, R, MMG_P_REC_DA_W, 0, -1);                 // d_attn.weight (1, A)
+        b.add(km(W.dba, 1), ones(), 1, 1, R, MMG_P_REC_DA_B, 0, -1);
+        Operand bw = km(in.desc_set, d.WV);
+        bw.mod = d.NW;                                       // row (cta, n) -> desc_set[n]
+        b.add(km(W.ddd_part, d.A), bw, d.A, d.WV, n_rec_ctas * d.NW, MMG_P_REC_DD_W, 0, MMG_P_REC_DD_B);
+    } else {
         Operand bd = km(in.desc, d.WV);
         bd.mod = d.D;                                        // row (b, d) -> desc[d]
-        b.add(km(W.dy1, Hr), bd, Hr, d.WV, B * d.D, MMG_P_REC_Y1_W, Hr, MMG_P_REC_Y1_B);
+        b.add(km(W.dy1, Hr), bd, Hr, d.WV, B * d.D, MMG_P_REC_Y1_W, d.y1_dcol, MMG_P_REC_Y1_B);
     }
     b.add(km(W.dw2p, Hr), ones(), Hr, 1, B, MMG_P_REC_Y2_W, 0, -1);          // y2.weight (1, Hr): sum over examples
     b.add(km(W.g_outp, 1), ones(), 1, 1, B * d.D, MMG_P_REC_Y2_B, 0, -1);
@@ -578,17 +624,20 @@ static int exchange_forward_impl(const mmg_config* cfg, const float* d_params, c
     const int n_hx = cdiv(d.B, kTile) * cdiv(d.Hi, kTile) * W.hx_split;
     const int hx_kslice = round_up(cdiv(d.F, W.hx_split), 4);
     const int n_pack = 64;
-    const int n_cls = 2 * cdiv(d.D, kTile) * cdiv(d.Hr, kTile);
+    if (d.A && (!in->d_desc_set || !in->d_desc_set_lens)) return fail(MMG_ERR_INVALID, "desc_attn needs d_desc_set and d_desc_set_lens");
+    const int n_cls = d.A ? cdiv(d.NW, kTile) * (2 * cdiv(d.Hr, kTile) + cdiv(d.A, kTile))      // word tables
+                          : 2 * cdiv(d.D, kTile) * cdiv(d.Hr, kTile);                            // class tables
     MMG_LAUNCH(k_pre, n_hx + n_cls + n_pack, kGemmThreads, 0, st, d, P, W, ei, n_hx, hx_kslice, pl.fast, n_cls);
     if ((rc = check_cuda("k_pre"))) return rc;
     // K_exchange_fwd
+    const AttnArgs aa = attn_args(d, P, ei);
     const float* b_img = P.p[MMG_P_SEN_IMG_B];
     if (pl.fast) rc = launch_fwd_fast(d, W, ei, FastFwdArgs{b_img, P.p[MMG_P_BS_L1_W], P.p[MMG_P_BS_L1_B]}, pl, st);
     else switch (pl.BT) {
-        case 1: rc = launch_fwd<1>(d, W, ei, b_img, pl, st); break;
-        case 2: rc = launch_fwd<2>(d, W, ei, b_img, pl, st); break;
-        case 4: rc = launch_fwd<4>(d, W, ei, b_img, pl, st); break;
-        default: rc = launch_fwd<8>(d, W, ei, b_img, pl, st); break;
+        case 1: rc = launch_fwd<1>(d, W, ei, b_img, pl, st, aa); break;
+        case 2: rc = launch_fwd<2>(d, W, ei, b_img, pl, st, aa); break;
+        case 4: rc = launch_fwd<4>(d, W, ei, b_img, pl, st, aa); break;
+        default: rc = launch_fwd<8>(d, W, ei, b_img, pl, st, aa); break;
     }
     if (rc) return rc;
     if (in->train) {
@@ -658,18 +707,20 @@ static int backward_impl(const mmg_config* cfg, const float* d_params, const mmg
     const ParamPtrs P = param_ptrs(L, d_params);
     const ExchangeInputs ei = resolve_inputs(in);
     cudaStream_t st = (cudaStream_t)stream;
+    if (d.A && (!in->d_desc_set || !in->d_desc_set_lens)) return fail(MMG_ERR_INVALID, "desc_attn needs d_desc_set and d_desc_set_lens");
+    const AttnArgs aa = attn_args(d, P, ei);
     if (pl.fast) rc = d.M == 32 ? launch_bwd_fast_m<32>(d, W, P.p[MMG_P_SEN_BIN_W], P.p[MMG_P_SEN_CODE_W], pl, st)
                                 : launch_bwd_fast_m<64>(d, W, P.p[MMG_P_SEN_BIN_W], P.p[MMG_P_SEN_CODE_W], pl, st);
     else switch (pl.BT) {
-        case 1: rc = launch_bwd<1>(d, W, pl, st); break;
-        case 2: rc = launch_bwd<2>(d, W, pl, st); break;
-        case 4: rc = launch_bwd<4>(d, W, pl, st); break;
-        default: rc = launch_bwd<8>(d, W, pl, st); break;
+        case 1: rc = launch_bwd<1>(d, W, pl, st, aa); break;
+        case 2: rc = launch_bwd<2>(d, W, pl, st, aa); break;
+        case 4: rc = launch_bwd<4>(d, W, pl, st, aa); break;
+        default: rc = launch_bwd<8>(d, W, pl, st, aa); break;
     }
     if (rc) return rc;
     WgTable tab;
     SplitTable stab;
-    build_wgrad_table(d, L, P, W, ei, pl.fast, &tab, &stab);
+    build_wgrad_table(d, L, P, W, ei, pl.fast, cdiv(d.B, pl.BT), &tab, &stab);
     MMG_LAUNCH(k_wgrad, tab.total_tiles, kGemmThreads, 0, st, d, tab, d_grads, W.slabs, P.p[MMG_P_SEN_CODE_W],
                P.p[MMG_P_SEN_CODE_BIAS], W.d_as);
     if ((rc = check_cuda("k_wgrad"))) return rc;

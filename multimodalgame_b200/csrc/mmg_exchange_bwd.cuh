@@ -14,9 +14,10 @@
 namespace mmg {
 
 MMG_HOST_DEVICE int bwd_rec_state_floats(const Dims& d, int BT) {
-    const int MP = d.M4 * 4, HrP = d.Hr4 * 4, G3P = align4(d.G3), H2P = align4(2 * d.Hr), DP = align4(d.D);
+    const int MP = d.M4 * 4, HrP = d.Hr4 * 4, G3P = align4(d.G3), H2P = align4(2 * d.Hr + d.A), DP = align4(d.D);
     int n = BT * (HrP + MP + H2P + G3P + DP) + 4 * BT;
     n += 2 * BT * kLoopThreads + 8;
+    if (d.A) n += BT * (align4(d.D * d.Hr) + align4(d.NW) + 2 * (kLoopThreads / 32) * align4(d.A));
     (void)HrP;
     return n;
 }
@@ -29,12 +30,12 @@ MMG_HOST_DEVICE int bwd_sen_state_floats(const Dims& d, int BT) {
 
 template <int BT>
 MMG_GLOBAL void __launch_bounds__(kLoopThreads, 1)
-k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas) {
+k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
     MMG_DYN_SMEM(smem_raw);
     float* sm = reinterpret_cast<float*>(smem_raw);
     const BwdImage im = make_bwd_image(d);
     const int tid = threadIdx.x;
-    const int MP = d.M4 * 4, HrP = d.Hr4 * 4, HiP = align4(d.Hi), G3P = align4(d.G3), H2P = align4(2 * d.Hr), DP = align4(d.D);
+    const int MP = d.M4 * 4, HrP = d.Hr4 * 4, HiP = align4(d.Hi), G3P = align4(d.G3), H2P = align4(2 * d.Hr + d.A), DP = align4(d.D);
     const bool binary = d.use_binary != 0;
 
     if ((int)blockIdx.x >= n_rec_ctas) {
@@ -114,6 +115,11 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas) {
     o = align4(o);
     float* partA = sm + o; o += BT * kLoopThreads;
     float* partB = sm + o; o += BT * kLoopThreads;
+    const int NWP = align4(d.NW), AP = align4(d.A), DH = align4(d.D * d.Hr), lane = tid & 31, warp = tid >> 5;
+    float* y1e = sm + o;   o += d.A ? BT * DH : 0;                          // attended description half of y1 (prediction step)
+    float* dav = sm + o;   o += d.A ? BT * NWP : 0;                         // d attention weights, then d scores
+    float* pddh = sm + o;  o += d.A ? BT * (kLoopThreads / 32) * AP : 0;    // per-warp partials of d (d_h(h))
+    float* pdva = sm + o;  o += d.A ? BT * (kLoopThreads / 32) * AP : 0;    // per-warp partials of d d_attn.weight
     o += (o & 1);
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + o);
 
@@ -123,7 +129,7 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas) {
     const float* ws = img + im.ws;
     const float* w2 = img + im.w2;
     const float* y1d = img + im.y1d;
-    const SplitPlan sp_w = make_split(d.Hr, d.M4), sp_head = make_split(d.Hr, cdiv(2 * d.Hr, 4)),
+    const SplitPlan sp_w = make_split(d.Hr, d.M4), sp_head = make_split(d.Hr, cdiv(2 * d.Hr + d.A, 4)),
                     sp_hh = make_split(d.Hr, cdiv(d.G3, 4));
 
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
@@ -170,6 +176,29 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas) {
             dls[tid] = v; yflag[tid] = fl;
         }
         MMG_SYNCTHREADS();
+        if (d.A) {
+            // ---- -desc_attn, prediction step only: rebuild the attended y1 half from the saved attention weights, and the
+            //      attended description itself (the `weighted_desc` rows that multiply d y1, model.py:383-410)
+            for (int idx = tid; idx < BT * d.D * d.Hr; idx += kLoopThreads) {
+                const int bt = idx / (d.D * d.Hr), r = idx % (d.D * d.Hr), dd = r / d.Hr, k = r % d.Hr, b = b0 + bt;
+                if (yflag[bt] == 0.f) continue;
+                const float* arow = W.attn + ((size_t)t * d.B + b) * d.NW;
+                float s = ldg(aa.b1 + k);
+                const int s1 = W.seg[dd + 1];
+                for (int n = W.seg[dd]; n < s1; ++n) s = fmaf(arow[n], ldg(W.wtab_y1 + (size_t)n * d.Hr + k), s);
+                y1e[bt * DH + r] = s;
+            }
+            for (int idx = tid; idx < BT * d.D * d.WV; idx += kLoopThreads) {
+                const int bt = idx / (d.D * d.WV), r = idx % (d.D * d.WV), dd = r / d.WV, v = r % d.WV, b = b0 + bt;
+                if (yflag[bt] == 0.f) continue;
+                const float* arow = W.attn + ((size_t)t * d.B + b) * d.NW;
+                float s = 0.f;
+                const int s1 = W.seg[dd + 1];
+                for (int n = W.seg[dd]; n < s1; ++n) s = fmaf(arow[n], ldg(aa.desc_set + (size_t)n * d.WV + v), s);
+                W.wdsel[(size_t)b * d.D * d.WV + r] = s;
+            }
+            MMG_SYNCTHREADS();
+        }
         // ---- R2: d h_w = W_w^T . d logits_w ;  class-score head at the prediction step ---------------------------
         split_matvec<BT, false>(WwT, d.Hr, d.M4, dlw, MP, partA, sp_w);
         for (int idx = tid; idx < BT * d.Hr; idx += kLoopThreads) {
@@ -182,7 +211,7 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas) {
                 float dw2 = 0.f;
                 for (int dd = 0; dd < d.D; ++dd) {
                     const float g = W.g_outp[(size_t)b * d.D + dd];
-                    const float pre = yh + y1d[dd * d.Hr + k];
+                    const float pre = yh + (d.A ? y1e[bt * DH + dd * d.Hr + k] : y1d[dd * d.Hr + k]);
                     const float v = pre > 0.f ? g * wk : 0.f;
                     W.dy1[((size_t)b * d.D + dd) * d.Hr + k] = v;
                     G += v;
@@ -208,8 +237,89 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas) {
             dvec[bt * H2P + k] = v;
         }
         MMG_SYNCTHREADS();
-        // ---- R4: d h' += W_h^T . d_hw + W_1h^T . G_h ------------------------------------------------------------
-        split_matvec<BT, false>(HeadT, d.Hr, cdiv(2 * d.Hr, 4), dvec, H2P, partA, sp_head);
+        if (d.A) {
+            // ---- -desc_attn backward.  a_n enters (1) the message hidden through q_class(n) a_n (desc_set . w_d^T)[n]
+            //      at every step (weighted_desc is NOT detached, model.py:444-449) and (2) the class scores through
+            //      a_n (desc_set . y1^T)[n] at the prediction step.
+            for (int o2 = warp; o2 < BT * d.NW; o2 += kLoopThreads / 32) {
+                const int bt = o2 / d.NW, n = o2 % d.NW, b = b0 + bt;
+                float s = 0.f;
+                if (b < d.B) {
+                    const int cls = W.wcls[n];
+                    const float qd = W.q[((size_t)t * d.B + b) * d.D + cls];
+                    const float* dyr = W.dy1 + ((size_t)b * d.D + cls) * d.Hr;
+                    const bool yf = yflag[bt] != 0.f;
+                    for (int k = lane; k < d.Hr; k += 32) {
+                        s = fmaf(qd * dvec[bt * H2P + k], ldg(W.wtab_wd + (size_t)n * d.Hr + k), s);
+                        if (yf) s = fmaf(dyr[k], ldg(W.wtab_y1 + (size_t)n * d.Hr + k), s);
+                    }
+                }
+                s = warp_sum(s);
+                if (lane == 0) dav[bt * NWP + n] = s;
+            }
+            MMG_SYNCTHREADS();
+            for (int o2 = warp; o2 < BT * d.D; o2 += kLoopThreads / 32) {          // through the segment softmax (model.py:378)
+                const int bt = o2 / d.D, dd = o2 % d.D, b = b0 + bt;
+                if (b >= d.B) continue;
+                const float* arow = W.attn + ((size_t)t * d.B + b) * d.NW;
+                const int s0 = W.seg[dd], s1 = W.seg[dd + 1];
+                float s = 0.f;
+                for (int n = s0 + lane; n < s1; n += 32) s = fmaf(arow[n], dav[bt * NWP + n], s);
+                s = warp_sum(s);
+                for (int n = s0 + lane; n < s1; n += 32) dav[bt * NWP + n] = arow[n] * (dav[bt * NWP + n] - s);
+            }
+            MMG_SYNCTHREADS();
+            // through score = d_attn(tanh(d_d(word) + d_h(h))) (model.py:366): each thread owns fixed (word, unit) pairs for the
+            // whole kernel, so its running sum of d (d_d(word)) needs no atomics
+            float* dslab = W.ddd_part + (size_t)blockIdx.x * d.NW * d.A;
+            for (int a = lane; a < d.A; a += 32) {
+                const float va = ldg(aa.va + a);
+                for (int bt = 0; bt < BT; ++bt) {
+                    const int b = b0 + bt;
+                    float accd = 0.f, accv = 0.f;
+                    if (b < d.B) {
+                        const float dha = W.dh_s[((size_t)t * d.B + b) * d.A + a];
+                        for (int n = warp; n < d.NW; n += kLoopThreads / 32) {
+                            const float th = tanhf(ldg(W.wtab_dd + (size_t)n * d.A + a) + dha);
+                            const float de = dav[bt * NWP + n];
+                            const float du = de * va * (1.f - th * th);
+                            accd += du;
+                            accv = fmaf(de, th, accv);
+                            float* slot = dslab + (size_t)n * d.A + a;
+                            *slot = (first && bt == 0) ? du : *slot + du;
+                        }
+                    } else if (first && bt == 0) {
+                        for (int n = warp; n < d.NW; n += kLoopThreads / 32) dslab[(size_t)n * d.A + a] = 0.f;
+                    }
+                    pddh[(bt * (kLoopThreads / 32) + warp) * AP + a] = accd;
+                    pdva[(bt * (kLoopThreads / 32) + warp) * AP + a] = accv;
+                }
+            }
+            MMG_SYNCTHREADS();
+            for (int idx = tid; idx < BT * d.A; idx += kLoopThreads) {
+                const int bt = idx / d.A, a = idx % d.A, b = b0 + bt;
+                float sd = 0.f, sv = 0.f;
+                for (int w = 0; w < kLoopThreads / 32; ++w) {
+                    sd += pddh[(bt * (kLoopThreads / 32) + w) * AP + a];
+                    sv += pdva[(bt * (kLoopThreads / 32) + w) * AP + a];
+                }
+                dvec[bt * H2P + 2 * d.Hr + a] = sd;
+                if (b < d.B) {
+                    W.ddh[((size_t)t * d.B + b) * d.A + a] = sd;
+                    W.dva[((size_t)t * d.B + b) * d.A + a] = sv;
+                }
+            }
+            for (int bt = warp; bt < BT; bt += kLoopThreads / 32) {               // d d_attn.bias (zero up to rounding)
+                const int b = b0 + bt;
+                float s = 0.f;
+                if (b < d.B) for (int n = lane; n < d.NW; n += 32) s += dav[bt * NWP + n];
+                s = warp_sum(s);
+                if (lane == 0 && b < d.B) W.dba[(size_t)t * d.B + b] = s;
+            }
+            MMG_SYNCTHREADS();
+        }
+        // ---- R4: d h' += W_h^T . d_hw + W_1h^T . G_h (+ d_h^T . d (d_h(h))) ---------------------------------------
+        split_matvec<BT, false>(HeadT, d.Hr, cdiv(2 * d.Hr + d.A, 4), dvec, H2P, partA, sp_head);
         MMG_SYNCTHREADS();
         // ---- R5: total d h', GRU gate gradients -----------------------------------------------------------------
         for (int idx = tid; idx < BT * d.Hr; idx += kLoopThreads) {

@@ -96,12 +96,13 @@ MMG_HOST_DEVICE int fwd_state_floats(const Dims& d, int BT) {
     if (pmax < kLoopThreads) pmax = kLoopThreads;
     n += 2 * BT * pmax;
     n += 4 * BT + 8;   // sprod, active, barrier
+    if (d.A) n += BT * (2 * align4(d.NW) + align4(d.A) + align4(d.D * d.Hr));   // scores, attention, d_h(h), attended y1 half
     return n;
 }
 
 template <int BT>
 MMG_GLOBAL void __launch_bounds__(kLoopThreads, 1)
-k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int sender_smem, int row_offset) {
+k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int sender_smem, int row_offset, AttnArgs aa) {
     MMG_DYN_SMEM(smem_raw);
     float* sm = reinterpret_cast<float*>(smem_raw);
     const FwdImage im = make_fwd_image(d);
@@ -131,6 +132,11 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
     float* sprod = sm + o; o += BT;
     float* smask = sm + o; o += BT;
     o = align4(o);
+    const int NWP = align4(d.NW), AP = align4(d.A);
+    float* ev = sm + o;   o += d.A ? BT * NWP : 0;                    // attention scores, later q_d(n) * a_n
+    float* att = sm + o;  o += d.A ? BT * NWP : 0;                    // attention weights
+    float* dhv = sm + o;  o += d.A ? BT * AP : 0;                     // d_h(h')
+    float* y1e = sm + o;  o += d.A ? BT * align4(d.D * d.Hr) : 0;     // attended description half of y1
     o += (o & 1);
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + o);
 
@@ -312,12 +318,65 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
             }
         }
         MMG_SYNCTHREADS();
+        if (d.A) {
+            // ---- -desc_attn (model.py:344-410): additive attention of h' over the words, softmax inside each class's
+            //      segment.  The per-word halves (d_d(desc_set), desc_set . y1^T, desc_set . w_d^T) are loop invariant
+            //      tables written by K_pre, so the (B, NW, WV) broadcasts of the reference never exist.
+            const int DH = align4(d.D * d.Hr);
+            for (int o2 = warp; o2 < BT * d.A; o2 += kLoopThreads / 32) {                    // d_h(h')  model.py:359
+                const int bt = o2 / d.A, a = o2 % d.A, b = b0 + bt;
+                float s = 0.f;
+                for (int k = lane; k < d.Hr; k += 32) s = fmaf(ldg(aa.dh_w + (size_t)a * d.Hr + k), hv[bt * HrP + k], s);
+                s = warp_sum(s);
+                if (lane == 0) {
+                    s += ldg(aa.dh_b + a);
+                    dhv[bt * AP + a] = s;
+                    if (train && b < d.B) W.dh_s[((size_t)t * d.B + b) * d.A + a] = s;
+                }
+            }
+            MMG_SYNCTHREADS();
+            for (int o2 = warp; o2 < BT * d.NW; o2 += kLoopThreads / 32) {                   // scores  model.py:366
+                const int bt = o2 / d.NW, n = o2 % d.NW;
+                float s = 0.f;
+                for (int a = lane; a < d.A; a += 32)
+                    s = fmaf(ldg(aa.va + a), tanhf(ldg(W.wtab_dd + (size_t)n * d.A + a) + dhv[bt * AP + a]), s);
+                s = warp_sum(s);
+                if (lane == 0) ev[bt * NWP + n] = s + ldg(aa.ba);
+            }
+            MMG_SYNCTHREADS();
+            for (int o2 = warp; o2 < BT * d.D; o2 += kLoopThreads / 32) {                    // segment softmax  model.py:372-381
+                const int bt = o2 / d.D, dd = o2 % d.D, b = b0 + bt;
+                const int s0 = W.seg[dd], s1 = W.seg[dd + 1];
+                float mx = -INFINITY;
+                for (int n = s0 + lane; n < s1; n += 32) mx = fmaxf(mx, ev[bt * NWP + n]);
+                mx = warp_max(mx);
+                float se = 0.f;
+                for (int n = s0 + lane; n < s1; n += 32) se += expf(ev[bt * NWP + n] - mx);
+                se = warp_sum(se);
+                const float inv = 1.f / se;
+                for (int n = s0 + lane; n < s1; n += 32) {
+                    const float a = expf(ev[bt * NWP + n] - mx) * inv;
+                    att[bt * NWP + n] = a;
+                    if (train && b < d.B) W.attn[((size_t)t * d.B + b) * d.NW + n] = a;
+                }
+            }
+            MMG_SYNCTHREADS();
+            for (int idx = tid; idx < BT * d.D * d.Hr; idx += kLoopThreads) {                // y1 . [attended desc ; .]  model.py:383-410,432
+                const int bt = idx / (d.D * d.Hr), r = idx % (d.D * d.Hr), dd = r / d.Hr, k = r % d.Hr;
+                float s = ldg(aa.b1 + k);
+                const int s1 = W.seg[dd + 1];
+                for (int n = W.seg[dd]; n < s1; ++n) s = fmaf(att[bt * NWP + n], ldg(W.wtab_y1 + (size_t)n * d.Hr + k), s);
+                y1e[bt * DH + r] = s;
+            }
+            MMG_SYNCTHREADS();
+        }
         // ---- S8b: class scores y[d] = y2(relu(y1h + y1d[d])) (model.py:432-433) — one warp per (example, class)
         for (int pair = warp; pair < BT * d.D; pair += kLoopThreads / 32) {
             const int bt = pair / d.D, dd = pair % d.D, b = b0 + bt;
+            const float* yd = d.A ? y1e + bt * align4(d.D * d.Hr) + dd * d.Hr : y1d + dd * d.Hr;
             float s = 0.f;
             for (int k = lane; k < d.Hr; k += 32)
-                s = fmaf(w2[k], fmaxf(0.f, head[bt * NHP + k] + y1d[dd * d.Hr + k]), s);
+                s = fmaf(w2[k], fmaxf(0.f, head[bt * NHP + k] + yd[k]), s);
             s = warp_sum(s);
             if (lane == 0) {
                 s += img[im.misc];
@@ -343,12 +402,20 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
             }
         }
         MMG_SYNCTHREADS();
+        if (d.A) {                      // word weights of the confidence-weighted description: q_class(n) * a_n (model.py:441-449)
+            for (int idx = tid; idx < BT * d.NW; idx += kLoopThreads) {
+                const int bt = idx / d.NW, n = idx % d.NW;
+                ev[bt * NWP + n] = qv[bt * DP + W.wcls[n]] * att[bt * NWP + n];
+            }
+            MMG_SYNCTHREADS();
+        }
         // ---- S10: h_w = tanh(w_h(h') + w_d(q . desc)) (model.py:442-452); wd = q . desc saved for the backward --
         for (int idx = tid; idx < BT * (d.Hr + d.WV); idx += kLoopThreads) {
             if (idx < BT * d.Hr) {
                 const int bt = idx / d.Hr, k = idx % d.Hr, b = b0 + bt;
                 float s = 0.f;
-                for (int dd = 0; dd < d.D; ++dd) s = fmaf(qv[bt * DP + dd], wdd[dd * d.Hr + k], s);
+                if (d.A) for (int n = 0; n < d.NW; ++n) s = fmaf(ev[bt * NWP + n], ldg(W.wtab_wd + (size_t)n * d.Hr + k), s);
+                else for (int dd = 0; dd < d.D; ++dd) s = fmaf(qv[bt * DP + dd], wdd[dd * d.Hr + k], s);
                 const float hw = tanhf(head[bt * NHP + d.Hr + k] + s);
                 hwr[bt * HrP + k] = hw;
                 if (b < d.B) W.h_w[((size_t)t * d.B + b) * d.Hr + k] = hw;
@@ -357,7 +424,8 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
                 const int bt = i2 / d.WV, v = i2 % d.WV, b = b0 + bt;
                 if (b < d.B) {
                     float s = 0.f;
-                    for (int dd = 0; dd < d.D; ++dd) s = fmaf(qv[bt * DP + dd], ldg(in.desc + (size_t)dd * d.WV + v), s);
+                    if (d.A) for (int n = 0; n < d.NW; ++n) s = fmaf(ev[bt * NWP + n], ldg(aa.desc_set + (size_t)n * d.WV + v), s);
+                    else for (int dd = 0; dd < d.D; ++dd) s = fmaf(qv[bt * DP + dd], ldg(in.desc + (size_t)dd * d.WV + v), s);
                     W.wd[((size_t)t * d.B + b) * d.WV + v] = s;
                 }
             }

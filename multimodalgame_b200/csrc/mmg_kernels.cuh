@@ -23,6 +23,9 @@ struct WsPtrs {               // resolved workspace arrays (device pointers)
     double* loss_part;
     unsigned* tickets;
     long long* opt_counters;
+    // -desc_attn
+    float *wtab_dd, *wtab_y1, *wtab_wd, *attn, *dh_s, *ddh, *dva, *dba, *ddd_part, *wdsel;
+    int *seg, *wcls;
     int hx_split, wgrad_split, ntb;
 };
 
@@ -43,6 +46,17 @@ struct ExchangeInputs {       // device pointers of one exchange (mmg_inputs res
     const float* corrupt_mask;
     const float* h0;
     int top_k, train;
+    const float* desc_set;     // (NW,WV) -desc_attn
+    const int* desc_set_lens;  // (D)
+};
+
+struct AttnArgs {             // -desc_attn parameters read straight from the flat parameter buffer (all L2 resident)
+    const float* dh_w;         // d_h.weight (A,Hr)
+    const float* dh_b;         // d_h.bias (A)
+    const float* va;           // d_attn.weight (A)
+    const float* ba;           // d_attn.bias (1)
+    const float* b1;           // y1.bias (Hr)
+    const float* desc_set;     // (NW,WV)
 };
 
 }  // namespace mmg

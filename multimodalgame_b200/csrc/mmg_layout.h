@@ -17,6 +17,9 @@ struct Dims {
     float flip_sen, flip_rec;   // flipout probabilities, < 0 = off (model.py:233-234,467-468)
     int flipout_dev;
     int mix_prod, ignore_code;  // sender hidden: tanh(h_x * h_w) instead of the sum / tanh(h_x) alone (model.py:208-221)
+    // -desc_attn (model.py:344-410): A = attention width (0 = off), NW = words of all class descriptions.
+    // y1.weight columns are [h_z ; desc] without and [desc ; h_z] with attention (model.py:408-410 vs 548).
+    int A, NW, y1_hcol, y1_dcol;
 };
 
 MMG_HOST_DEVICE Dims make_dims(const mmg_config& c) {
@@ -33,6 +36,8 @@ MMG_HOST_DEVICE Dims make_dims(const mmg_config& c) {
     d.flip_rec = c.has_flipout_rec ? c.flipout_rec : -1.f;
     d.flipout_dev = c.flipout_dev;
     d.mix_prod = c.sender_mix == MMG_MIX_PROD; d.ignore_code = c.ignore_code;
+    d.A = c.desc_attn ? c.desc_attn_dim : 0; d.NW = c.desc_attn ? c.n_words : 0;
+    d.y1_hcol = d.A ? d.WV : 0; d.y1_dcol = d.A ? 0 : d.Hr;
     return d;
 }
 
@@ -67,7 +72,7 @@ struct BwdImage {
     int wbT;     // binary_layer.weight^T  out=Hi red=M      (sender rows)
     int sender_end;
     int wwT;     // w.weight^T             out=Hr red=M
-    int headT;   // [w_h.weight ; y1.weight[:, :Hr]]^T  out=Hr red=2Hr
+    int headT;   // [w_h.weight ; y1.weight[:, h cols] ; d_h.weight (desc_attn)]^T  out=Hr red=2Hr+A
     int whhT;    // rnn.weight_hh^T        out=Hr red=3Hr
     int ws;      // [Hr] s.weight
     int w2;      // [Hr] y2.weight
@@ -105,7 +110,7 @@ MMG_HOST_DEVICE BwdImage make_bwd_image(const Dims& d) {
     im.wbT = o; o += d.M4 * d.Hi * 4;
     im.sender_end = o;
     im.wwT = o; o += d.M4 * d.Hr * 4;
-    im.headT = o; o += cdiv(2 * d.Hr, 4) * d.Hr * 4;
+    im.headT = o; o += cdiv(2 * d.Hr + d.A, 4) * d.Hr * 4;
     im.whhT = o; o += cdiv(d.G3, 4) * d.Hr * 4;
     im.ws = o; o += align4(d.Hr);
     im.w2 = o; o += align4(d.Hr);
@@ -183,7 +188,7 @@ MMG_HOST_DEVICE FastBwdImage make_fast_bwd_image(int M, int D) {
     return im;
 }
 MMG_HOST_DEVICE bool fast_dims(const Dims& d) {
-    return d.Hi == kFastHi && d.Hr == kFastHr && (d.M == 32 || d.M == 64) && d.T <= kFastMaxT;
+    return d.Hi == kFastHi && d.Hr == kFastHr && (d.M == 32 || d.M == 64) && d.T <= kFastMaxT && d.A == 0;
 }
 
 // ---- workspace ------------------------------------------------------------------------------------------
@@ -230,6 +235,19 @@ struct Ws {   // byte offsets into the workspace
     int64_t loss_part; // double (kLossCtasMax, 8) per-CTA loss partial sums, summed in CTA order by the last CTA
     int64_t tickets;   // uint32[8]: [0] loss reduction, [1] h_x rows ready, [2] send buffer complete, [4..5] grid barrier
     int64_t opt_counters; // int64[4]: [0] = number of updates that reached the receiver message head (Adam bias correction)
+    // -desc_attn (all zero-sized otherwise)
+    int64_t wtab_dd;   // (NW,A)   d_d(desc_set): word half of the attention pre-activation, loop invariant
+    int64_t wtab_y1;   // (NW,Hr)  desc_set . y1.weight[:, :WV]^T
+    int64_t wtab_wd;   // (NW,Hr)  desc_set . w_d.weight^T
+    int64_t seg;       // int32 (D+1) first word of each class;  wcls: int32 (NW) class of each word
+    int64_t wcls;
+    int64_t attn;      // (T,B,NW) attention weights (softmax within each class's words)
+    int64_t dh_s;      // (T,B,A)  d_h(h_z): hidden half of the attention pre-activation
+    int64_t ddh;       // (T,B,A)  dL/d dh_s
+    int64_t dva;       // (T,B,A)  per-row partial of dL/d d_attn.weight;  dba (T,B): of d_attn.bias
+    int64_t dba;
+    int64_t ddd_part;  // (n_rec_ctas, NW, A) per-CTA partial of dL/d wtab_dd, accumulated over the CTA's steps/examples
+    int64_t wdsel;     // (B,D,WV) attended description of every class at the prediction step
     int hx_split, wgrad_split, ntb;
 };
 

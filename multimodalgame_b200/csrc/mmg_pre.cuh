@@ -27,7 +27,7 @@ MMG_DEVICE float fwd_image_elem(const Dims& d, const FwdImage& im, const ParamPt
     if (e < im.whead) { int q = e - im.whh; int r = (q / (d.G3 * 4)) * 4 + (q & 3), o = (q >> 2) % d.G3;
         return packed_src(P.p[MMG_P_REC_RNN_WHH], d.Hr, o, r, d.Hr); }
     if (e < im.ww) { int q = e - im.whead; int r = (q / (d.NH * 4)) * 4 + (q & 3), o = (q >> 2) % d.NH;
-        if (o < d.Hr) return packed_src(P.p[MMG_P_REC_Y1_W], d.Hr + d.WV, o, r, d.Hr);
+        if (o < d.Hr) return packed_src(P.p[MMG_P_REC_Y1_W] + d.y1_hcol, d.Hr + d.WV, o, r, d.Hr);
         if (o < 2 * d.Hr) return packed_src(P.p[MMG_P_REC_WH_W], d.Hr, o - d.Hr, r, d.Hr);
         return packed_src(P.p[MMG_P_REC_S_W], d.Hr, 0, r, d.Hr); }
     if (e < im.b_ih) { int q = e - im.ww; int r = (q / (d.M * 4)) * 4 + (q & 3), o = (q >> 2) % d.M;
@@ -52,7 +52,8 @@ MMG_DEVICE float bwd_image_elem(const Dims& d, const BwdImage& im, const ParamPt
         return r < d.M ? ldg(P.p[MMG_P_REC_W_W] + (size_t)r * d.Hr + o) : 0.f; }
     if (e < im.whhT) { int q = e - im.headT; int r = (q / (d.Hr * 4)) * 4 + (q & 3), o = (q >> 2) % d.Hr;
         if (r < d.Hr) return ldg(P.p[MMG_P_REC_WH_W] + (size_t)r * d.Hr + o);
-        if (r < 2 * d.Hr) return ldg(P.p[MMG_P_REC_Y1_W] + (size_t)(r - d.Hr) * (d.Hr + d.WV) + o);
+        if (r < 2 * d.Hr) return ldg(P.p[MMG_P_REC_Y1_W] + (size_t)(r - d.Hr) * (d.Hr + d.WV) + d.y1_hcol + o);
+        if (r < 2 * d.Hr + d.A) return ldg(P.p[MMG_P_REC_DH_W] + (size_t)(r - 2 * d.Hr) * d.Hr + o);   // d_h.weight^T (desc_attn)
         return 0.f; }
     if (e < im.ws) { int q = e - im.whhT; int r = (q / (d.Hr * 4)) * 4 + (q & 3), o = (q >> 2) % d.Hr;
         return r < d.G3 ? ldg(P.p[MMG_P_REC_RNN_WHH] + (size_t)r * d.Hr + o) : 0.f; }
@@ -97,6 +98,38 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
     const BwdImage bim = make_bwd_image(d);
     const FastFwdImage ffi = make_fast_fwd_image(d.M, d.D);
     const FastBwdImage fbi = make_fast_bwd_image(d.M, d.D);
+    if ((int)blockIdx.x < n_hx_tiles + n_cls_tiles && d.A) {
+        // ---- role C, -desc_attn: loop-invariant WORD tables (model.py:352 and the word halves of y1 / w_d) ------------
+        //   wtab_y1[n][k] = desc_set[n] . y1.weight[k][:WV]   wtab_wd[n][k] = desc_set[n] . w_d.weight[k]
+        //   wtab_dd[n][a] = d_d.bias[a] + desc_set[n] . d_d.weight[a]
+        const int ntk = cdiv(d.Hr, kTile), nta = cdiv(d.A, kTile), per_m = 2 * ntk + nta;
+        int t = (int)blockIdx.x - n_hx_tiles;
+        const int mt = t / per_m;
+        t %= per_m;
+        const int which = t < ntk ? 0 : (t < 2 * ntk ? 1 : 2);
+        const int nt = which == 0 ? t : (which == 1 ? t - ntk : t - 2 * ntk);
+        const int N = which == 2 ? d.A : d.Hr;
+        Operand A = {in.desc_set, nullptr, nullptr, nullptr, d.WV, 0, 0, 0, 0, OP_PLAIN};
+        Operand Bo = which == 0 ? Operand{P.p[MMG_P_REC_Y1_W] + d.y1_dcol, nullptr, nullptr, nullptr, d.Hr + d.WV, 0, 0, 0, 0, OP_PLAIN}
+                   : which == 1 ? Operand{P.p[MMG_P_REC_WD_W], nullptr, nullptr, nullptr, d.WV, 0, 0, 0, 0, OP_PLAIN}
+                                : Operand{P.p[MMG_P_REC_DD_W], nullptr, nullptr, nullptr, d.WV, 0, 0, 0, 0, OP_PLAIN};
+        float acc[4][4];
+        gemm_tile(A, Bo, d.NW, N, mt * kTile, nt * kTile, 0, d.WV, acc, nullptr, gs);
+        const int tx = tid % 16, ty = tid / 16;
+        float* out = which == 0 ? W.wtab_y1 : (which == 1 ? W.wtab_wd : W.wtab_dd);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int n = mt * kTile + ty * 4 + a;
+            if (n >= d.NW) continue;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int k = nt * kTile + tx * 4 + c;
+                if (k >= N) continue;
+                out[(size_t)n * N + k] = acc[a][c] + (which == 2 ? ldg(P.p[MMG_P_REC_DD_B] + k) : 0.f);
+            }
+        }
+        return;
+    }
     if ((int)blockIdx.x < n_hx_tiles + n_cls_tiles) {
         // ---- role C: loop-invariant class tables as two small GEMMs over the word-vector dimension -----------------
         //   y1d[dd][k] = y1.bias[k] + sum_v desc[dd][v] * y1.weight[k][Hr + v]     wdd[dd][k] = sum_v desc[dd][v] * w_d.weight[k][v]
@@ -140,6 +173,17 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
     // ---- role B: images + the step-0 code term -------------------------------------------------------------
     const int nblk = gridDim.x - n_hx_tiles - n_cls_tiles, blk = blockIdx.x - n_hx_tiles - n_cls_tiles;
     const int gthreads = nblk * kGemmThreads, gtid = blk * kGemmThreads + tid;
+    if (d.A && blk == 0 && tid == 0) {          // word segments of the classes (model.py:372-376)
+        int start = 0;
+        for (int dd = 0; dd < d.D; ++dd) {
+            W.seg[dd] = start;
+            const int n = in.desc_set_lens[dd];
+            for (int i = 0; i < n && start + i < d.NW; ++i) W.wcls[start + i] = dd;
+            start += n;
+            if (start > d.NW) start = d.NW;
+        }
+        W.seg[d.D] = start;
+    }
     if (fast) {
         for (int e = gtid; e < ffi.y1d; e += gthreads) {
             if (e >= ffi.hw0 && e < ffi.b_b) continue;
@@ -156,6 +200,7 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
     // dot role: one warp per output, lanes along the reduction
     const int lane = tid & 31, gwarp = gtid >> 5, nwarps = gthreads >> 5;
     const int n_y1d = d.D * d.Hr;
+    const int n_y1d_w = d.A ? 0 : n_y1d;      // -desc_attn: the class tables are replaced by word tables, the sections stay zero
     const int n_out = 2 * n_y1d + d.Hi + d.M;
     for (int o = 2 * n_y1d + gwarp; o < n_out; o += nwarps) {
         if (o < 2 * n_y1d + d.Hi) {     // hw0[n] = code_layer.bias[n] + sum_j sigmoid(code_bias[j]) * code_layer.weight[n][j]
@@ -182,10 +227,10 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
         return;
     }
     for (int e = gtid; e < fim.total; e += gthreads) {
-        if ((e >= fim.hw0 + d.Hi && e < fim.b_b) || (e >= fim.y1d + n_y1d && e < fim.wdd) || (e >= fim.wdd + n_y1d))
+        if ((e >= fim.hw0 + d.Hi && e < fim.b_b) || (e >= fim.y1d + n_y1d_w && e < fim.wdd) || (e >= fim.wdd + n_y1d_w))
             W.fwd_image[e] = 0.f;
     }
-    for (int e = gtid + bim.y1d + n_y1d; e < bim.total; e += gthreads) W.bwd_image[e] = 0.f;
+    for (int e = gtid + bim.y1d + n_y1d_w; e < bim.total; e += gthreads) W.bwd_image[e] = 0.f;
 }
 
 }  // namespace mmg

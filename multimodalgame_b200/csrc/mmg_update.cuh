@@ -15,7 +15,7 @@ namespace mmg {
 
 enum { WG_GEMM = 0, WG_ROWVEC = 1, WG_CODEBIAS = 2 };
 enum { kRowvecCols = 256 };
-enum { kMaxWgProblems = 20, kWgradKSlice = 128 };
+enum { kMaxWgProblems = 26, kWgradKSlice = 128 };
 
 struct WgProblem {
     Operand A, B;

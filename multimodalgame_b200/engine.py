@@ -19,7 +19,8 @@ def make_config(batch, n_classes, img_feat_dim=4096, img_h_dim=100, baseline_hid
                 rec_hidden=128, rec_w_dim=50, wv_dim=100, max_exchange=3, fixed_exchange=True, use_binary=True,
                 entropy_s=None, entropy_sen=None, entropy_rec=None, first_rec=0.0, s_prob_prod=True,
                 learning_rate=1e-4, optim_type="RMSprop", ignore_receiver=False, batch_global=None, max_norm=1.0,
-                flipout_sen=None, flipout_rec=None, flipout_dev=False, sender_mix="sum", ignore_code=False):
+                flipout_sen=None, flipout_rec=None, flipout_dev=False, sender_mix="sum", ignore_code=False,
+                desc_attn=False, desc_attn_dim=64, n_words=0):
     """Build the C config from reference flag names/defaults (model.py:1641-1741)."""
     assert sender_out_dim == rec_w_dim, \
         "Both sender and receiver should communicate with same dim vectors for now."   # model.py:1756
@@ -44,6 +45,8 @@ def make_config(batch, n_classes, img_feat_dim=4096, img_h_dim=100, baseline_hid
     if sender_mix not in capi.SENDER_MIX:
         raise NotImplementedError("sender_mix=%s is outside the fused B200 path" % sender_mix)        # 'mou', model.py:219-221
     c.sender_mix, c.ignore_code = capi.SENDER_MIX[sender_mix], int(bool(ignore_code))
+    c.desc_attn = int(bool(desc_attn))                                                               # model.py:1719-1720
+    c.desc_attn_dim, c.n_words = (int(desc_attn_dim), int(n_words)) if desc_attn else (0, 0)
     return c
 
 
@@ -96,8 +99,24 @@ class GameEngine(object):
         flat = self.params if flat is None else flat
         out = OrderedDict((a, OrderedDict()) for a in capi.SEGMENTS)
         for idx, (agent, key) in enumerate(capi.PARAM_NAMES):
+            if int(self.layout.rows[idx]) * int(self.layout.cols[idx]) == 0:
+                continue                                   # tensors of a branch that is switched off (-desc_attn)
             out[agent][key] = self._flat_view(flat, idx)
         return out
+
+    def param_keys(self, agent):
+        """state_dict keys of one module, in the flat buffer's (= the reference's registration) order."""
+        return list(self.named_views()[agent].keys())
+
+    def set_desc_set(self, desc_set, desc_set_lens):
+        """-desc_attn: the words of all class descriptions (NW, WV) and the word count of each class (model.py:765-766)."""
+        dev = self.device
+        lens = torch.as_tensor([int(v) for v in desc_set_lens], dtype=torch.int32)
+        assert lens.numel() == self.cfg.n_classes and int(lens.min()) >= 1, "one non-empty word segment per class"
+        assert int(lens.sum()) == self.cfg.n_words, (int(lens.sum()), self.cfg.n_words)
+        ds = torch.as_tensor(desc_set).to(device=dev, dtype=torch.float32).contiguous()
+        assert tuple(ds.shape) == (self.cfg.n_words, self.cfg.wv_dim), tuple(ds.shape)
+        self._desc_words = (ds, lens.to(dev))
 
     def load_params(self, params):
         """params: {agent: {key: tensor}} (e.g. four state_dicts)."""
@@ -142,6 +161,12 @@ class GameEngine(object):
         inp.d_corrupt_mask, inp.d_h0 = ptr(keep[6]), ptr(keep[7])
         inp.d_u_flip_sen, inp.d_u_flip_rec = ptr(keep[8]), ptr(keep[9])
         inp.top_k, inp.train = int(top_k), int(bool(train))
+        if self.cfg.desc_attn:
+            words = getattr(self, "_desc_words", None)
+            if words is None:
+                raise ValueError("-desc_attn: call set_desc_set(desc_set, desc_set_lens) first")
+            inp.d_desc_set, inp.d_desc_set_lens = ptr(words[0]), ptr(words[1])
+            keep = keep + list(words)
         self._keep = keep      # keep the tensors alive until the next call
         return inp
 

@@ -9,7 +9,7 @@ from oracle import game_oracle as go
 from tests import golden_util as gu
 
 
-def config_from(cfg, B=None, batch_global=None):
+def config_from(cfg, B=None, batch_global=None, n_words=0):
     return eng.make_config(
         batch=B or cfg.batch_size, n_classes=cfg.n_classes, img_feat_dim=cfg.img_feat_dim, img_h_dim=cfg.img_h_dim,
         baseline_hid_dim=cfg.baseline_hid_dim, sender_out_dim=cfg.sender_out_dim, rec_hidden=cfg.rec_hidden,
@@ -18,7 +18,8 @@ def config_from(cfg, B=None, batch_global=None):
         first_rec=cfg.first_rec, s_prob_prod=cfg.s_prob_prod, learning_rate=cfg.learning_rate,
         optim_type=cfg.optim_type, ignore_receiver=cfg.ignore_receiver, batch_global=batch_global,
         flipout_sen=getattr(cfg, "flipout_sen", None), flipout_rec=getattr(cfg, "flipout_rec", None),
-        sender_mix=getattr(cfg, "sender_mix", "sum"), ignore_code=getattr(cfg, "ignore_code", False))
+        sender_mix=getattr(cfg, "sender_mix", "sum"), ignore_code=getattr(cfg, "ignore_code", False),
+        desc_attn=getattr(cfg, "desc_attn", False), desc_attn_dim=getattr(cfg, "desc_attn_dim", 64), n_words=n_words)
 
 
 def stack_uniforms(us, cfg, B):
@@ -69,13 +70,27 @@ def run_train_case(case, lib, device, report=None, grad_rtol=2e-3):
     params = gu.params_at(z, "P0")
     oparams = go.clone_params(params)
     ostate = go.new_opt_state(oparams)
-    e = eng.GameEngine(config_from(cfg), device=device, lib=lib)
-    e.load_params(params)
+    e = None
     errs = {}
     for it in range(int(z["iters"])):
         x, desc, target = gu.batch_at(z, it)
         us = gu.uniforms_at(z, it, cfg)
-        ex, res, grads = go.train_iteration(oparams, ostate, x, target, desc, cfg, us, return_grads=True)
+        words = gu.desc_set_at(z, it)
+        nw = int(words["desc_set"].shape[0]) if words else 0
+        if e is None or (words and e.cfg.n_words != nw):       # the number of description words is part of the config
+            state = None if e is None else (e.state1.clone(), None if e.state2 is None else e.state2.clone(), e.step,
+                                            e.ws("opt_counters", (4,), torch.int64).clone())
+            e = eng.GameEngine(config_from(cfg, n_words=nw), device=device, lib=lib)
+            e.load_params(oparams)
+            if state is not None:
+                e.state1.copy_(state[0])
+                if state[1] is not None:
+                    e.state2.copy_(state[1])
+                e.step = state[2]
+                e.ws("opt_counters", (4,), torch.int64).copy_(state[3])
+        if words:
+            e.set_desc_set(**words)
+        ex, res, grads = go.train_iteration(oparams, ostate, x, target, desc, cfg, us, return_grads=True, **words)
         Tp = len(ex["y"])     # steps the reference executed (early break)
         stacked = stack_uniforms(us, cfg, B)
         uz, us_, uw = stacked[:3]
@@ -130,7 +145,7 @@ def run_train_case(case, lib, device, report=None, grad_rtol=2e-3):
                 if g is None:
                     assert np.all(got == 0), tag + "grad %s.%s should be exactly zero" % (a, k)
                     continue
-                if (a, k) == ("receiver", "y2.bias"):
+                if (a, k) in (("receiver", "y2.bias"), ("receiver", "d_attn.bias")):     # mathematically zero (shift invariance)
                     assert abs(float(got.reshape(-1)[0])) < 1e-5
                     continue
                 errs["grad_" + a] = max(errs.get("grad_" + a, 0.0), assert_close(
@@ -148,7 +163,7 @@ def run_train_case(case, lib, device, report=None, grad_rtol=2e-3):
                 got = pv[a][k].detach().cpu().numpy()
                 # RMSprop/Adam turn a tiny gradient difference into at most ~10*lr of parameter difference
                 # (see tests/test_oracle_golden.py on y2.bias); SGD is linear.
-                atol = 12 * lr * (it + 1) if (a, k) == ("receiver", "y2.bias") else 2e-2 * lr + 1e-7
+                atol = 12 * lr * (it + 1) if (a, k) in (("receiver", "y2.bias"), ("receiver", "d_attn.bias")) else 2e-2 * lr + 1e-7
                 if cfg.optim_type == "SGD":
                     atol = lr * 1e-3 + 1e-7
                 elif a in grads and grads[a].get(k) is not None:
@@ -170,8 +185,11 @@ def run_eval_case(case, lib, device):
     z, cfg = gu.load(case)
     B = cfg.batch_size
     params = gu.params_at(z, "P0")
-    e = eng.GameEngine(config_from(cfg), device=device, lib=lib)
+    words = gu.desc_set_at(z)
+    e = eng.GameEngine(config_from(cfg, n_words=int(words["desc_set"].shape[0]) if words else 0), device=device, lib=lib)
     e.load_params(params)
+    if words:
+        e.set_desc_set(**words)
     x, desc, target = torch.from_numpy(z["x"]), torch.from_numpy(z["desc"]), torch.from_numpy(z["target"])
     region = str(z["corrupt_region"])
     mask = None

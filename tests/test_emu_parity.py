@@ -6,7 +6,7 @@ import pytest
 from tests import emu_util, parity_util as pu
 
 CASES = ["fixed_small", "fixed_t1_noent", "continuous_t3", "adaptive_small", "adaptive_b1_adam", "adaptive_sgd",
-         "flipout_small", "ignore_rec_first1", "mix_prod", "ignore_code"]
+         "flipout_small", "ignore_rec_first1", "mix_prod", "ignore_code", "desc_attn_small"]
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -14,7 +14,8 @@ def test_emulated_kernels_match_oracle(case):
     pu.run_train_case(case, emu_util.emu_library(), "cpu")
 
 
-@pytest.mark.parametrize("case", ["eval_adaptive", "eval_adaptive_noprod", "eval_fixed_corrupt", "eval_continuous"])
+@pytest.mark.parametrize("case", ["eval_adaptive", "eval_adaptive_noprod", "eval_fixed_corrupt", "eval_continuous",
+                                  "eval_desc_attn"])
 def test_emulated_eval_matches_reference_golden(case):
     pu.run_eval_case(case, emu_util.emu_library(), "cpu")
 
