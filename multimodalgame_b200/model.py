@@ -218,8 +218,6 @@ class Receiver(nn.Module):
         self.w_dim, self.s_dim, self.use_binary = w_dim, s_dim, use_binary
         if out_dim != 1 or s_dim != 1:
             _unsupported("rec_out_dim/rec_s_dim != 1")
-        if _flag("desc_attn", False):
-            _unsupported("-desc_attn (word-level description attention, model.py:344-410)")
         self.rnn = nn.GRUCell(self.z_dim, self.hid_dim)
         self.w_h = nn.Linear(self.hid_dim, self.hid_dim, bias=True)
         self.w_d = nn.Linear(self.desc_dim, self.hid_dim, bias=False)
@@ -227,6 +225,12 @@ class Receiver(nn.Module):
         self.y1 = nn.Linear(self.hid_dim + self.desc_dim, self.hid_dim)
         self.y2 = nn.Linear(self.hid_dim, self.out_dim)
         self.s = nn.Linear(self.hid_dim, self.s_dim)
+        self.desc_attn = bool(_flag("desc_attn", False))
+        if self.desc_attn:                                          # model.py:267-271
+            self.attn_dim = int(_flag("desc_attn_dim", 64))
+            self.d_d = nn.Linear(self.desc_dim, self.attn_dim)
+            self.d_h = nn.Linear(self.hid_dim, self.attn_dim)
+            self.d_attn = nn.Linear(self.attn_dim, 1)
         self.reset_parameters()
         self.reset_state()
 
@@ -275,7 +279,7 @@ class Baseline(nn.Module):
 class _Binding(object):
     """One engine per (modules, batch, classes, flags); module parameters become views of the flat buffer."""
 
-    def __init__(self, mods, B, D, device, batch_global=None):
+    def __init__(self, mods, B, D, device, batch_global=None, n_words=0):
         s, r = mods["sender"], mods["receiver"]
         cfg = _engine.make_config(
             batch=B, n_classes=D, img_feat_dim=s.feat_dim, img_h_dim=s.h_dim, baseline_hid_dim=mods["baseline_sen"].hid_dim
@@ -288,8 +292,10 @@ class _Binding(object):
             optim_type=_flag("optim_type", "RMSprop"), ignore_receiver=bool(_flag("ignore_receiver", False)),
             batch_global=batch_global, flipout_sen=_flag("flipout_sen"), flipout_rec=_flag("flipout_rec"),
             flipout_dev=bool(_flag("flipout_dev", False)), sender_mix=_flag("sender_mix", "sum"),
-            ignore_code=bool(_flag("ignore_code", False)))
+            ignore_code=bool(_flag("ignore_code", False)), desc_attn=getattr(r, "desc_attn", False),
+            desc_attn_dim=getattr(r, "attn_dim", 0), n_words=n_words)
         self.engine = _engine.GameEngine(cfg, device=device, lib=_LIB_OVERRIDE)
+        self.words_key = None
         self.mods = mods
         self.key = None
         self.rebind()
@@ -319,16 +325,36 @@ class _Binding(object):
 _BINDINGS = {}
 
 
-def _binding_for(sender, receiver, baseline_sen, baseline_rec, B, D, device, batch_global=None):
+def _binding_for(sender, receiver, baseline_sen, baseline_rec, B, D, device, batch_global=None, exchange_args=None):
+    """One engine per shape/flag combination.  With -desc_attn the word set of the class descriptions
+    (exchange_args["desc_set"], ["desc_set_lens"], model.py:765-766) belongs to the binding: its size is part of the
+    configuration and the words are uploaded once per distinct set (train / dev sets differ)."""
+    n_words = 0
+    if getattr(receiver, "desc_attn", False):
+        desc_set = (exchange_args or {}).get("desc_set")
+        lens = (exchange_args or {}).get("desc_set_lens")
+        if desc_set is None or lens is None:
+            raise ValueError("-desc_attn needs exchange_args['desc_set'] and ['desc_set_lens']")
+        n_words = int(desc_set.shape[0])
+    b = _binding_lookup(sender, receiver, baseline_sen, baseline_rec, B, D, device, batch_global, n_words)
+    if n_words:
+        wk = (id(desc_set), int(desc_set.data_ptr()) if torch.is_tensor(desc_set) else 0, tuple(int(v) for v in lens))
+        if b.words_key != wk:
+            b.engine.set_desc_set(desc_set, lens)
+            b.words_key = wk
+    return b
+
+
+def _binding_lookup(sender, receiver, baseline_sen, baseline_rec, B, D, device, batch_global, n_words):
     key = (id(sender), id(receiver), id(baseline_sen), id(baseline_rec), int(B), int(D), str(device),
            int(_flag("max_exchange", 3)), bool(_flag("fixed_exchange", True)), _flag("entropy_s"), _flag("entropy_sen"),
            _flag("entropy_rec"), _flag("optim_type", "RMSprop"), float(_flag("learning_rate", 1e-4)), batch_global,
            _flag("flipout_sen"), _flag("flipout_rec"), bool(_flag("flipout_dev", False)), _flag("sender_mix", "sum"),
-           bool(_flag("ignore_code", False)))
+           bool(_flag("ignore_code", False)), n_words)
     b = _BINDINGS.get(key)
     if b is None:
         mods = dict(receiver=receiver, sender=sender, baseline_rec=baseline_rec, baseline_sen=baseline_sen)
-        b = _Binding(mods, B, D, device, batch_global)
+        b = _Binding(mods, B, D, device, batch_global, n_words)
         _BINDINGS[key] = b
     else:
         b.rebind()
@@ -384,7 +410,7 @@ class _AgentFn(torch.autograd.Function):
         e._inp = ctx.inp
         e.backward()
         gv = b.gviews
-        grads = [gv[ctx.agent][key].clone() for a, key in capi.PARAM_NAMES if a == ctx.agent]
+        grads = [gv[ctx.agent][key].clone() for key in e.param_keys(ctx.agent)]
         return (None, None, None) + tuple(grads)
 
 
@@ -408,7 +434,7 @@ def exchange(sender, receiver, baseline_sen, baseline_rec, exchange_args):
         _unsupported("data_context (visual attention)")
     dev = _device_of(receiver)
     B, D = data.shape[0], desc.shape[0]
-    binding = _binding_for(sender, receiver, baseline_sen, baseline_rec, B, D, dev)
+    binding = _binding_for(sender, receiver, baseline_sen, baseline_rec, B, D, dev, exchange_args=exchange_args)
     e = binding.engine
     T = e.dims["T"]
     if train:
@@ -424,7 +450,7 @@ def exchange(sender, receiver, baseline_sen, baseline_rec, exchange_args):
         outs = {}
         for agent in capi.SEGMENTS:
             named = dict(binding.mods[agent].named_parameters())
-            params = [named[key] for a, key in capi.PARAM_NAMES if a == agent]
+            params = [named[key] for key in e.param_keys(agent)]
             res = _AgentFn.apply(binding, agent, e._inp, *params)
             outs.update(zip(_AGENT_OUTPUTS[agent], res))
         sen_p, rec_p, stop_p, y_all, bs_all, br_all = (outs["sen_probs"], outs["rec_probs"], outs["stop_prob"], outs["y"],
@@ -581,7 +607,7 @@ class FusedOptimizer(object):
 
     def __init__(self, engine, agent):
         self.engine, self.agent = engine, agent
-        self.keys = [key for a, key in capi.PARAM_NAMES if a == agent]
+        self.keys = engine.param_keys(agent)
         # parameters() order = state_dict order (direct parameters first), which is how PARAM_NAMES is laid out
         self.optim = {v: k for k, v in capi.OPTIM.items()}[int(engine.cfg.optim_type)]
 
@@ -644,7 +670,7 @@ def train_step(sender, receiver, baseline_sen, baseline_rec, exchange_args, grou
         import torch.distributed as dist
         world = dist.get_world_size(group)
     binding = _binding_for(sender, receiver, baseline_sen, baseline_rec, data.shape[0], desc.shape[0], dev,
-                           batch_global=data.shape[0] * world if world > 1 else None)
+                           batch_global=data.shape[0] * world if world > 1 else None, exchange_args=exchange_args)
     e = binding.engine
     top_k = min(int(_flag("top_k_train", 6)), desc.shape[0])
     if world > 1:

@@ -17,6 +17,8 @@ REF_KEYS = {
                  "w.weight", "w.bias", "y1.weight", "y1.bias", "y2.weight", "y2.bias", "s.weight", "s.bias"],
     "baseline": ["linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias"],
 }
+ATTN_KEYS = ["d_d.weight", "d_d.bias", "d_h.weight", "d_h.bias", "d_attn.weight", "d_attn.bias"]   # -desc_attn, model.py:267-271
+ZERO_GRAD = (("receiver", "y2.bias"), ("receiver", "d_attn.bias"))    # softmax shift invariance: rounding noise only
 
 _flags_defined = False
 
@@ -35,6 +37,10 @@ def set_flags(cfg):
     argv.append("-fixed_exchange" if cfg.fixed_exchange else "-nofixed_exchange")
     argv.append("-use_binary" if cfg.use_binary else "-nouse_binary")
     argv.append("-s_prob_prod" if cfg.s_prob_prod else "-nos_prob_prod")
+    if getattr(cfg, "desc_attn", False):
+        argv += ["-desc_attn", "-desc_attn_dim", str(cfg.desc_attn_dim)]
+    else:
+        argv.append("-nodesc_attn")
     for name in ("entropy_s", "entropy_sen", "entropy_rec"):
         if getattr(cfg, name) is not None:
             argv += ["-" + name, repr(getattr(cfg, name))]
@@ -54,7 +60,7 @@ def build_modules(cfg, params, device):
     baseline_rec = M.Baseline(cfg.baseline_hid_dim, 0, cfg.sender_out_dim, cfg.rec_hidden)
     mods = dict(sender=sender, receiver=receiver, baseline_sen=baseline_sen, baseline_rec=baseline_rec)
     assert list(sender.state_dict().keys()) == REF_KEYS["sender"]
-    assert list(receiver.state_dict().keys()) == REF_KEYS["receiver"]
+    assert list(receiver.state_dict().keys()) == REF_KEYS["receiver"] + (ATTN_KEYS if getattr(cfg, "desc_attn", False) else [])
     assert list(baseline_sen.state_dict().keys()) == REF_KEYS["baseline"]
     for a, m in mods.items():
         if a in params:
@@ -63,11 +69,11 @@ def build_modules(cfg, params, device):
     return mods
 
 
-def reference_update_block(mods, cfg, x, desc, target, uniforms):
+def reference_update_block(mods, cfg, x, desc, target, uniforms, words=None):
     """model.py:1240-1330 written against the mirrored names; returns the loss dict (gradients land in .grad)."""
     fl = M.FLAGS
     exchange_args = dict(data=x, target=target, desc=desc, train=True, break_early=not fl.fixed_exchange,
-                         uniforms=uniforms)
+                         uniforms=uniforms, **(words or {}))
     s, sen_w, rec_w, y, bs, br = M.exchange(mods["sender"], mods["receiver"], mods["baseline_sen"], mods["baseline_rec"],
                                             exchange_args)
     s_masks, s_feats, s_probs = s
@@ -128,9 +134,11 @@ def run_surface_case(case, device, iters=1):
     B = cfg.batch_size
     x, desc, target = gu.batch_at(z, 0)
     us = gu.uniforms_at(z, 0, cfg)
-    ex, res, grads = go.train_iteration(oparams, go.new_opt_state(oparams), x, target, desc, cfg, us, return_grads=True)
+    words = gu.desc_set_at(z, 0)
+    ex, res, grads = go.train_iteration(oparams, go.new_opt_state(oparams), x, target, desc, cfg, us, return_grads=True,
+                                        **words)
     uni = tuple(u.to(device) for u in pu.stack_uniforms(us, cfg, B))
-    out = reference_update_block(mods, cfg, x.to(device), desc.to(device), target.to(device), uni)
+    out = reference_update_block(mods, cfg, x.to(device), desc.to(device), target.to(device), uni, words)
     Tp = len(ex["y"])
     assert out["steps"] == Tp, (out["steps"], Tp)
     st = lambda key: np.stack([t.detach().numpy() for t in ex[key]], 0)
@@ -150,7 +158,7 @@ def run_surface_case(case, device, iters=1):
         gmax = max([float(g.abs().max()) for g in grads[a].values() if g is not None] + [1e-12])
         for k, p in mod.named_parameters():
             g = grads[a].get(k)
-            if g is None or (a, k) == ("receiver", "y2.bias"):
+            if g is None or (a, k) in ZERO_GRAD:
                 continue
             assert p.grad is not None, (a, k)
             pu.assert_close("%s/grad %s.%s" % (case, a, k), p.grad.detach().cpu().numpy(), g.numpy(), rtol=2e-3,
@@ -172,10 +180,13 @@ def run_train_step_case(case, device):
     mods = build_modules(cfg, params, device)
     x, desc, target = gu.batch_at(z, 0)
     us = gu.uniforms_at(z, 0, cfg)
-    ex, res, grads = go.train_iteration(oparams, go.new_opt_state(oparams), x, target, desc, cfg, us, return_grads=True)
+    words = gu.desc_set_at(z, 0)
+    ex, res, grads = go.train_iteration(oparams, go.new_opt_state(oparams), x, target, desc, cfg, us, return_grads=True,
+                                        **words)
     uni = tuple(u.to(device) for u in pu.stack_uniforms(us, cfg, cfg.batch_size))
     eng = M.train_step(mods["sender"], mods["receiver"], mods["baseline_sen"], mods["baseline_rec"],
-                       dict(data=x.to(device), target=target.to(device), desc=desc.to(device), train=True, uniforms=uni))
+                       dict(data=x.to(device), target=target.to(device), desc=desc.to(device), train=True, uniforms=uni,
+                            **words))
     L = eng.losses()
     for name in ("nll_loss", "loss_rec", "loss_sen", "loss_bas_rec", "loss_bas_sen"):
         if name in res:
@@ -185,7 +196,7 @@ def run_train_step_case(case, device):
         if a not in oparams:
             continue
         for k, p in mod.named_parameters():
-            if (a, k) == ("receiver", "y2.bias"):
+            if (a, k) in ZERO_GRAD:
                 continue
             g = grads.get(a, {}).get(k)
             atol = 2e-2 * lr + 1e-7

@@ -16,12 +16,12 @@ def emulated_library():
     M._BINDINGS.clear()
 
 
-@pytest.mark.parametrize("case", ["fixed_small", "adaptive_small", "continuous_t3", "fixed_t1_noent"])
+@pytest.mark.parametrize("case", ["fixed_small", "adaptive_small", "continuous_t3", "fixed_t1_noent", "desc_attn_small"])
 def test_reference_update_block_on_mirrored_surface(case):
     su.run_surface_case(case, "cpu")
 
 
-@pytest.mark.parametrize("case", ["fixed_small", "adaptive_sgd"])
+@pytest.mark.parametrize("case", ["fixed_small", "adaptive_sgd", "desc_attn_small"])
 def test_fused_train_step_behind_the_modules(case):
     su.run_train_step_case(case, "cpu")
 
@@ -40,9 +40,5 @@ def test_unsupported_flags_raise():
     from tests import golden_util as gu
     z, cfg = gu.load("fixed_small")
     su.set_flags(cfg)
-    M.FLAGS.desc_attn = True
-    with pytest.raises(NotImplementedError):
-        M.Receiver(cfg.sender_out_dim, cfg.wv_dim, cfg.rec_hidden, 1, cfg.rec_w_dim, 1, True)
-    M.FLAGS.desc_attn = False
     with pytest.raises(NotImplementedError):
         M.Sender("layer4_2", 512, 16, 8, 8, True, True, 256, True, 1000)      # visual attention
