@@ -36,12 +36,16 @@ CONFIGS = {
     "C4": dict(batch_size=64, img_feat_dim=2048, n_classes=30, max_exchange=10, fixed_exchange=True, use_binary=True, **HEAD),
     "C5": dict(batch_size=128, img_feat_dim=2048, n_classes=100, max_exchange=20, fixed_exchange=False, use_binary=True,
                entropy_s=0.08, **dict(HEAD, sender_out_dim=64, rec_w_dim=64)),
+    # C2 with the receiver's word-level description attention (-desc_attn, model.py:344-410): 30 classes x 3..14 words
+    "C2A": dict(batch_size=64, img_feat_dim=2048, n_classes=30, max_exchange=10, fixed_exchange=True, use_binary=True,
+                desc_attn=True, desc_attn_dim=64, **HEAD),
 }
 WORKLOAD = {
     "C2": "BASELINE.json configs[1]: fixed 10-step exchange, batch=64, 30 classes, 2048-d feats, -use_binary",
     "C3": "BASELINE.json configs[2]: adaptive max_exchange=10, batch=256, 30 classes, entropy_s=0.08",
     "C4": "BASELINE.json configs[3]: fixed 10-step, 64 rows per GPU, 30 classes, -use_binary, data-parallel",
     "C5": "BASELINE.json configs[4]: adaptive max_exchange=20, 128 rows per GPU, 100 classes, rec_w_dim=64",
+    "C2A": "configs[1] with -desc_attn -desc_attn_dim 64: fixed 10-step, batch=64, 30 classes x 3..14 description words",
 }
 
 
@@ -50,6 +54,9 @@ def param_counts(c):
     sender = Hi * F + Hi + Hi * M + Hi + M + M * Hi + M
     receiver = 3 * Hr * M + 3 * Hr * Hr + 6 * Hr + Hr * Hr + Hr + Hr * WV + M * Hr + M + Hr * (Hr + WV) + Hr + Hr + 1 + Hr + 1
     bas = Hb * (Hi + M) + Hb + Hb + 1 + Hb * (M + Hr) + Hb + Hb + 1
+    if c.get("desc_attn"):
+        A = c["desc_attn_dim"]
+        receiver += A * WV + A + A * Hr + A + A + 1
     return sender + receiver + bas
 
 
@@ -110,12 +117,14 @@ def time_oracle(cfgd, iters, warmup, threads=None):
     params = go.init_params(cfg, seed=0)
     state = go.new_opt_state(params)
     x, desc, target = go.synthetic_batch(cfg, seed=0)
+    from tests import parity_util as pu
+    words = pu._synth_words(cfg, 0)
     rng = np.random.RandomState(0)
     times, steps = [], 0
     for i in range(warmup + iters):
         us = go.draw_uniforms(rng, cfg)
         t0 = time.perf_counter()
-        ex, _ = go.train_iteration(params, state, x, target, desc, cfg, us)
+        ex, _ = go.train_iteration(params, state, x, target, desc, cfg, us, **words)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
@@ -189,8 +198,12 @@ def main():
     lib = capi.load()
     cfg = go.GameConfig(**cfgd)
     B, T = cfg.batch_size, cfg.max_exchange
-    e = eng.GameEngine(pu.config_from(cfg, batch_global=B * world), device=dev, lib=lib, seed=1 + rank * 0)
+    words = pu._synth_words(cfg, 0)
+    e = eng.GameEngine(pu.config_from(cfg, batch_global=B * world, n_words=int(words["desc_set"].shape[0]) if words else 0),
+                       device=dev, lib=lib, seed=1 + rank * 0)
     e.load_params(go.init_params(cfg, seed=0))
+    if words:
+        e.set_desc_set(**words)
     # synthetic inputs: a ring of distinct batches, resident in HBM for `value`, in pinned host memory for `e2e`
     nb = 8
     batches = [go.synthetic_batch(cfg, seed=100 * rank + i) for i in range(nb)]

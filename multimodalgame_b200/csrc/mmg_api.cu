@@ -176,9 +176,11 @@ static void ws_layout(const Dims& d, Ws* w) {
     p.opt_counters = w->opt_counters;
     if (d.A) {
         const int64_t NW = d.NW, A = d.A;
-        w->wtab_dd = take(c, NW * A * f);
-        w->wtab_y1 = take(c, NW * d.Hr * f);
-        w->wtab_wd = take(c, NW * d.Hr * f);
+        const int64_t AP = align4(d.A), HrP = align4(d.Hr);     // table rows padded to whole float4 groups
+        w->wtab_dd = take(c, NW * AP * f);
+        w->wtab_y1 = take(c, NW * HrP * f);
+        w->wtab_wd = take(c, NW * HrP * f);
+        w->qa = take(c, R * NW * f);
         w->seg = take(c, (d.D + 1) * 4);
         w->wcls = take(c, NW * 4);
         w->attn = take(c, R * NW * f);
@@ -186,7 +188,7 @@ static void ws_layout(const Dims& d, Ws* w) {
         w->ddh = take(c, R * A * f);
         w->dva = take(c, R * A * f);
         w->dba = take(c, R * f);
-        w->ddd_part = take(c, B * NW * A * f);      // at most one receiver CTA per example
+        w->ddd_part = take(c, B * NW * AP * f);     // at most one receiver CTA per example
         w->wdsel = take(c, B * d.D * d.WV * f);
     }
     p.total_bytes = c;
@@ -215,7 +217,7 @@ static WsPtrs resolve(const Ws& w, void* base) {
     r.tickets = (unsigned*)(b + w.tickets);
     r.opt_counters = (long long*)(b + w.opt_counters);
 #define G_(name) r.name = (float*)(b + w.name)
-    G_(wtab_dd); G_(wtab_y1); G_(wtab_wd); G_(attn); G_(dh_s); G_(ddh); G_(dva); G_(dba); G_(ddd_part); G_(wdsel);
+    G_(wtab_dd); G_(wtab_y1); G_(wtab_wd); G_(qa); G_(attn); G_(dh_s); G_(ddh); G_(dva); G_(dba); G_(ddd_part); G_(wdsel);
 #undef G_
     r.seg = (int*)(b + w.seg); r.wcls = (int*)(b + w.wcls);
     r.hx_split = w.hx_split; r.wgrad_split = w.wgrad_split; r.ntb = w.ntb;
@@ -454,7 +456,7 @@ static void build_wgrad_table(const Dims& d, const mmg_param_layout& L, const Pa
         b.add(km(W.dba, 1), ones(), 1, 1, R, MMG_P_REC_DA_B, 0, -1);
         Operand bw = km(in.desc_set, d.WV);
         bw.mod = d.NW;                                       // row (cta, n) -> desc_set[n]
-        b.add(km(W.ddd_part, d.A), bw, d.A, d.WV, n_rec_ctas * d.NW, MMG_P_REC_DD_W, 0, MMG_P_REC_DD_B);
+        b.add(km(W.ddd_part, align4(d.A)), bw, d.A, d.WV, n_rec_ctas * d.NW, MMG_P_REC_DD_W, 0, MMG_P_REC_DD_B);
     } else {
         Operand bd = km(in.desc, d.WV);
         bd.mod = d.D;                                        // row (b, d) -> desc[d]
@@ -642,8 +644,9 @@ static int exchange_forward_impl(const mmg_config* cfg, const float* d_params, c
     if (rc) return rc;
     if (in->train) {
         const int tiles = 2 * cdiv(d.R, kTile) * W.ntb;
-        const int wd_tiles = pl.fast ? cdiv(d.R, kTile) * cdiv(d.WV, kTile) : 0;   // the generic kernel writes wd itself
-        MMG_LAUNCH(k_baseline_fwd, tiles + wd_tiles, kGemmThreads, 0, st, d, P, W, ei.desc, tiles, pl.fast);
+        // wd rows as GEMM tiles (fast path and -desc_attn); otherwise the generic kernel writes wd itself
+        const int wd_tiles = (pl.fast || d.A) ? cdiv(d.R, kTile) * cdiv(d.WV, kTile) : 0;
+        MMG_LAUNCH(k_baseline_fwd, tiles + wd_tiles, kGemmThreads, 0, st, d, P, W, d.A ? ei.desc_set : ei.desc, tiles, pl.fast);
         if ((rc = check_cuda("k_baseline_fwd"))) return rc;
         if (finish_baselines) {     // standalone forward: bs / br must be final on return (mmg_loss re-derives them anyway)
             MMG_LAUNCH(k_baseline_finish, cdiv(d.R, 256), 256, 0, st, d, P, W);

@@ -17,7 +17,7 @@ MMG_HOST_DEVICE int bwd_rec_state_floats(const Dims& d, int BT) {
     const int MP = d.M4 * 4, HrP = d.Hr4 * 4, G3P = align4(d.G3), H2P = align4(2 * d.Hr + d.A), DP = align4(d.D);
     int n = BT * (HrP + MP + H2P + G3P + DP) + 4 * BT;
     n += 2 * BT * kLoopThreads + 8;
-    if (d.A) n += BT * (align4(d.D * d.Hr) + align4(d.NW) + 2 * (kLoopThreads / 32) * align4(d.A));
+    if (d.A) n += BT * (d.D * HrP + 2 * align4(d.NW) + align4(d.A) + 2 * (kLoopThreads / 32) * align4(d.A)) + align4(d.A) + HrP;
     (void)HrP;
     return n;
 }
@@ -109,15 +109,19 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
     float* dlw = sm + o;   o += BT * MP;
     float* dvec = sm + o;  o += BT * H2P;      // [d_hw (Hr) ; G_h (Hr)]
     float* dghs = sm + o;  o += BT * G3P;
-    o += BT * DP;
+    float* qs = sm + o;    o += BT * DP;       // softmax(y) of this step (desc_attn)
     float* dls = sm + o;   o += BT;
     float* yflag = sm + o; o += BT;
     o = align4(o);
     float* partA = sm + o; o += BT * kLoopThreads;
     float* partB = sm + o; o += BT * kLoopThreads;
-    const int NWP = align4(d.NW), AP = align4(d.A), DH = align4(d.D * d.Hr), lane = tid & 31, warp = tid >> 5;
-    float* y1e = sm + o;   o += d.A ? BT * DH : 0;                          // attended description half of y1 (prediction step)
+    const int NWP = align4(d.NW), AP = align4(d.A), DH = d.D * HrP, lane = tid & 31, warp = tid >> 5;
+    float* y1e = sm + o;   o += d.A ? BT * DH : 0;                          // attended description half of y1, then d y1 (prediction step)
     float* dav = sm + o;   o += d.A ? BT * NWP : 0;                         // d attention weights, then d scores
+    float* att = sm + o;   o += d.A ? BT * NWP : 0;                         // attention weights of this step
+    float* dhs = sm + o;   o += d.A ? BT * AP : 0;                          // d_h(h) of this step
+    float* vas = sm + o;   o += d.A ? AP : 0;                               // d_attn.weight, zero padded
+    float* b1s = sm + o;   o += d.A ? HrP : 0;                              // y1.bias
     float* pddh = sm + o;  o += d.A ? BT * (kLoopThreads / 32) * AP : 0;    // per-warp partials of d (d_h(h))
     float* pdva = sm + o;  o += d.A ? BT * (kLoopThreads / 32) * AP : 0;    // per-warp partials of d d_attn.weight
     o += (o & 1);
@@ -141,6 +145,12 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
     for (int idx = tid; idx < BT * H2P; idx += kLoopThreads) dvec[idx] = 0.f;
     for (int idx = tid; idx < BT * G3P; idx += kLoopThreads) dghs[idx] = 0.f;
     for (int idx = tid; idx < BT * kLoopThreads; idx += kLoopThreads) { partA[idx] = 0.f; partB[idx] = 0.f; }
+    if (d.A) {
+        for (int idx = tid; idx < AP; idx += kLoopThreads) vas[idx] = idx < d.A ? ldg(aa.va + idx) : 0.f;
+        for (int idx = tid; idx < HrP; idx += kLoopThreads) b1s[idx] = idx < d.Hr ? ldg(aa.b1 + idx) : 0.f;
+        for (int idx = tid; idx < BT * AP; idx += kLoopThreads) dhs[idx] = 0.f;
+        for (int idx = tid; idx < BT * DH; idx += kLoopThreads) y1e[idx] = 0.f;
+    }
 #ifdef MMG_CPU_EMU
     MMG_SYNCTHREADS();
 #endif
@@ -175,26 +185,46 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
             }
             dls[tid] = v; yflag[tid] = fl;
         }
+        if (d.A) {      // this step's attention weights, d_h(h) and softmax(y) rows -> shared memory
+            for (int idx = tid; idx < BT * d.NW; idx += kLoopThreads) {
+                const int bt = idx / d.NW, n = idx % d.NW, b = b0 + bt;
+                att[bt * NWP + n] = b < d.B ? W.attn[((size_t)t * d.B + b) * d.NW + n] : 0.f;
+            }
+            for (int idx = tid; idx < BT * d.A; idx += kLoopThreads) {
+                const int bt = idx / d.A, a = idx % d.A, b = b0 + bt;
+                dhs[bt * AP + a] = b < d.B ? W.dh_s[((size_t)t * d.B + b) * d.A + a] : 0.f;
+            }
+            for (int idx = tid; idx < BT * d.D; idx += kLoopThreads) {
+                const int bt = idx / d.D, dd = idx % d.D, b = b0 + bt;
+                qs[bt * DP + dd] = b < d.B ? W.q[((size_t)t * d.B + b) * d.D + dd] : 0.f;
+            }
+        }
         MMG_SYNCTHREADS();
         if (d.A) {
             // ---- -desc_attn, prediction step only: rebuild the attended y1 half from the saved attention weights, and the
             //      attended description itself (the `weighted_desc` rows that multiply d y1, model.py:383-410)
-            for (int idx = tid; idx < BT * d.D * d.Hr; idx += kLoopThreads) {
-                const int bt = idx / (d.D * d.Hr), r = idx % (d.D * d.Hr), dd = r / d.Hr, k = r % d.Hr, b = b0 + bt;
+            const int K4 = HrP >> 2;
+            for (int idx = tid; idx < BT * d.D * K4; idx += kLoopThreads) {
+                const int bt = idx / (d.D * K4), r = idx % (d.D * K4), dd = r / K4, k4 = r % K4;
                 if (yflag[bt] == 0.f) continue;
-                const float* arow = W.attn + ((size_t)t * d.B + b) * d.NW;
-                float s = ldg(aa.b1 + k);
+                float4 s4 = *reinterpret_cast<const float4*>(b1s + 4 * k4);
                 const int s1 = W.seg[dd + 1];
-                for (int n = W.seg[dd]; n < s1; ++n) s = fmaf(arow[n], ldg(W.wtab_y1 + (size_t)n * d.Hr + k), s);
-                y1e[bt * DH + r] = s;
+                const float4* tab = reinterpret_cast<const float4*>(W.wtab_y1) + k4;
+#pragma unroll 8
+                for (int n = W.seg[dd]; n < s1; ++n) {
+                    const float4 w = ldg4(tab + (size_t)n * K4);
+                    const float a = att[bt * NWP + n];
+                    s4.x = fmaf(a, w.x, s4.x); s4.y = fmaf(a, w.y, s4.y); s4.z = fmaf(a, w.z, s4.z); s4.w = fmaf(a, w.w, s4.w);
+                }
+                *reinterpret_cast<float4*>(y1e + bt * DH + dd * HrP + 4 * k4) = s4;
             }
             for (int idx = tid; idx < BT * d.D * d.WV; idx += kLoopThreads) {
                 const int bt = idx / (d.D * d.WV), r = idx % (d.D * d.WV), dd = r / d.WV, v = r % d.WV, b = b0 + bt;
                 if (yflag[bt] == 0.f) continue;
-                const float* arow = W.attn + ((size_t)t * d.B + b) * d.NW;
                 float s = 0.f;
                 const int s1 = W.seg[dd + 1];
-                for (int n = W.seg[dd]; n < s1; ++n) s = fmaf(arow[n], ldg(aa.desc_set + (size_t)n * d.WV + v), s);
+#pragma unroll 8
+                for (int n = W.seg[dd]; n < s1; ++n) s = fmaf(att[bt * NWP + n], ldg(aa.desc_set + (size_t)n * d.WV + v), s);
                 W.wdsel[(size_t)b * d.D * d.WV + r] = s;
             }
             MMG_SYNCTHREADS();
@@ -211,9 +241,10 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
                 float dw2 = 0.f;
                 for (int dd = 0; dd < d.D; ++dd) {
                     const float g = W.g_outp[(size_t)b * d.D + dd];
-                    const float pre = yh + (d.A ? y1e[bt * DH + dd * d.Hr + k] : y1d[dd * d.Hr + k]);
+                    const float pre = yh + (d.A ? y1e[bt * DH + dd * HrP + k] : y1d[dd * d.Hr + k]);
                     const float v = pre > 0.f ? g * wk : 0.f;
                     W.dy1[((size_t)b * d.D + dd) * d.Hr + k] = v;
+                    if (d.A) y1e[bt * DH + dd * HrP + k] = v;       // the attention backward reads d y1 from shared memory
                     G += v;
                     dw2 = fmaf(g, fmaxf(pre, 0.f), dw2);
                 }
@@ -241,58 +272,88 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
             // ---- -desc_attn backward.  a_n enters (1) the message hidden through q_class(n) a_n (desc_set . w_d^T)[n]
             //      at every step (weighted_desc is NOT detached, model.py:444-449) and (2) the class scores through
             //      a_n (desc_set . y1^T)[n] at the prediction step.
-            for (int o2 = warp; o2 < BT * d.NW; o2 += kLoopThreads / 32) {
-                const int bt = o2 / d.NW, n = o2 % d.NW, b = b0 + bt;
+            const int q4 = tid & 3, g4 = tid >> 2, K4 = HrP >> 2, A4 = AP >> 2;
+            for (int base = 0; base < BT * d.NW; base += kLoopThreads / 4) {
+                const int o2 = base + g4;
+                const bool ok = o2 < BT * d.NW;
+                const int bt = ok ? o2 / d.NW : 0, n = ok ? o2 % d.NW : 0, b = b0 + bt;
                 float s = 0.f;
-                if (b < d.B) {
+                if (ok && b < d.B) {
                     const int cls = W.wcls[n];
-                    const float qd = W.q[((size_t)t * d.B + b) * d.D + cls];
-                    const float* dyr = W.dy1 + ((size_t)b * d.D + cls) * d.Hr;
+                    const float qd = qs[bt * DP + cls];
                     const bool yf = yflag[bt] != 0.f;
-                    for (int k = lane; k < d.Hr; k += 32) {
-                        s = fmaf(qd * dvec[bt * H2P + k], ldg(W.wtab_wd + (size_t)n * d.Hr + k), s);
-                        if (yf) s = fmaf(dyr[k], ldg(W.wtab_y1 + (size_t)n * d.Hr + k), s);
+                    const float4* twd = reinterpret_cast<const float4*>(W.wtab_wd + (size_t)n * HrP);
+                    const float4* ty1 = reinterpret_cast<const float4*>(W.wtab_y1 + (size_t)n * HrP);
+                    const float4* dhw = reinterpret_cast<const float4*>(dvec + bt * H2P);
+                    const float4* dyr = reinterpret_cast<const float4*>(y1e + bt * DH + cls * HrP);
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+                    for (int i = q4; i < K4; i += 4) {
+                        const float4 w = ldg4(twd + i), g = dhw[i];
+                        s1 = fmaf(g.x, w.x, s1); s1 = fmaf(g.y, w.y, s1); s1 = fmaf(g.z, w.z, s1); s1 = fmaf(g.w, w.w, s1);
+                        if (yf) {
+                            const float4 u = ldg4(ty1 + i), e = dyr[i];
+                            s2 = fmaf(e.x, u.x, s2); s2 = fmaf(e.y, u.y, s2); s2 = fmaf(e.z, u.z, s2); s2 = fmaf(e.w, u.w, s2);
+                        }
                     }
+                    s = fmaf(qd, s1, s2);
                 }
-                s = warp_sum(s);
-                if (lane == 0) dav[bt * NWP + n] = s;
+                s = group_sum<4>(s);
+                if (ok && q4 == 0) dav[bt * NWP + n] = s;
             }
             MMG_SYNCTHREADS();
-            for (int o2 = warp; o2 < BT * d.D; o2 += kLoopThreads / 32) {          // through the segment softmax (model.py:378)
-                const int bt = o2 / d.D, dd = o2 % d.D, b = b0 + bt;
-                if (b >= d.B) continue;
-                const float* arow = W.attn + ((size_t)t * d.B + b) * d.NW;
-                const int s0 = W.seg[dd], s1 = W.seg[dd + 1];
+            for (int base = 0; base < BT * d.D; base += kLoopThreads / 8) {        // through the segment softmax (model.py:378)
+                const int o2 = base + (tid >> 3), l8 = tid & 7;
+                const bool ok = o2 < BT * d.D;
+                const int bt = ok ? o2 / d.D : 0, dd = ok ? o2 % d.D : 0;
+                const int s0 = ok ? W.seg[dd] : 0, s1 = ok ? W.seg[dd + 1] : 0;
                 float s = 0.f;
-                for (int n = s0 + lane; n < s1; n += 32) s = fmaf(arow[n], dav[bt * NWP + n], s);
-                s = warp_sum(s);
-                for (int n = s0 + lane; n < s1; n += 32) dav[bt * NWP + n] = arow[n] * (dav[bt * NWP + n] - s);
+                for (int n = s0 + l8; n < s1; n += 8) s = fmaf(att[bt * NWP + n], dav[bt * NWP + n], s);
+                s = group_sum<8>(s);
+                for (int n = s0 + l8; n < s1; n += 8) dav[bt * NWP + n] = att[bt * NWP + n] * (dav[bt * NWP + n] - s);
             }
             MMG_SYNCTHREADS();
-            // through score = d_attn(tanh(d_d(word) + d_h(h))) (model.py:366): each thread owns fixed (word, unit) pairs for the
-            // whole kernel, so its running sum of d (d_d(word)) needs no atomics
-            float* dslab = W.ddd_part + (size_t)blockIdx.x * d.NW * d.A;
-            for (int a = lane; a < d.A; a += 32) {
-                const float va = ldg(aa.va + a);
+            // through score = d_attn(tanh(d_d(word) + d_h(h))) (model.py:366): thread = (word group, float4 unit group); every
+            // thread owns fixed (word, unit) elements for the whole kernel, so its running sum of d (d_d(word)) needs no atomics
+            float* dslab = W.ddd_part + (size_t)blockIdx.x * d.NW * AP;
+            for (int ib = 0; ib < A4; ib += 4) {        // uniform trip count: the partial sums meet through warp shuffles
+                const int i4 = ib + q4 < A4 ? ib + q4 : A4 - 1;
+                const bool act = ib + q4 < A4;
+                const float4 va = *reinterpret_cast<const float4*>(vas + 4 * i4);
                 for (int bt = 0; bt < BT; ++bt) {
                     const int b = b0 + bt;
-                    float accd = 0.f, accv = 0.f;
-                    if (b < d.B) {
-                        const float dha = W.dh_s[((size_t)t * d.B + b) * d.A + a];
-                        for (int n = warp; n < d.NW; n += kLoopThreads / 32) {
-                            const float th = tanhf(ldg(W.wtab_dd + (size_t)n * d.A + a) + dha);
+                    float4 accd = make_float4(0.f, 0.f, 0.f, 0.f), accv = accd;
+                    if (b < d.B && act) {
+                        const float4 dha = *reinterpret_cast<const float4*>(dhs + bt * AP + 4 * i4);
+                        const bool init = first && bt == 0;
+#pragma unroll 4
+                        for (int n = g4; n < d.NW; n += kLoopThreads / 4) {
+                            const float4 w = ldg4(reinterpret_cast<const float4*>(W.wtab_dd + (size_t)n * AP) + i4);
+                            float4* slot = reinterpret_cast<float4*>(dslab + (size_t)n * AP) + i4;
+                            float4 acc = init ? make_float4(0.f, 0.f, 0.f, 0.f) : *slot;
                             const float de = dav[bt * NWP + n];
-                            const float du = de * va * (1.f - th * th);
-                            accd += du;
-                            accv = fmaf(de, th, accv);
-                            float* slot = dslab + (size_t)n * d.A + a;
-                            *slot = (first && bt == 0) ? du : *slot + du;
+                            const float tx = tanhf(w.x + dha.x), ty = tanhf(w.y + dha.y), tz = tanhf(w.z + dha.z), tw = tanhf(w.w + dha.w);
+                            const float ux = de * va.x * (1.f - tx * tx), uy = de * va.y * (1.f - ty * ty),
+                                        uz = de * va.z * (1.f - tz * tz), uw = de * va.w * (1.f - tw * tw);
+                            accd.x += ux; accd.y += uy; accd.z += uz; accd.w += uw;
+                            accv.x = fmaf(de, tx, accv.x); accv.y = fmaf(de, ty, accv.y); accv.z = fmaf(de, tz, accv.z); accv.w = fmaf(de, tw, accv.w);
+                            acc.x += ux; acc.y += uy; acc.z += uz; acc.w += uw;
+                            *slot = acc;
                         }
-                    } else if (first && bt == 0) {
-                        for (int n = warp; n < d.NW; n += kLoopThreads / 32) dslab[(size_t)n * d.A + a] = 0.f;
+                    } else if (first && bt == 0 && act) {
+                        for (int n = g4; n < d.NW; n += kLoopThreads / 4)
+                            *(reinterpret_cast<float4*>(dslab + (size_t)n * AP) + i4) = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    pddh[(bt * (kLoopThreads / 32) + warp) * AP + a] = accd;
-                    pdva[(bt * (kLoopThreads / 32) + warp) * AP + a] = accv;
+                    // sum over the 8 word groups of this warp (lanes with equal q4), then one partial per warp
+#pragma unroll
+                    for (int m = 4; m < 32; m <<= 1) {
+                        accd.x += shfl_xor_f(accd.x, m); accd.y += shfl_xor_f(accd.y, m); accd.z += shfl_xor_f(accd.z, m); accd.w += shfl_xor_f(accd.w, m);
+                        accv.x += shfl_xor_f(accv.x, m); accv.y += shfl_xor_f(accv.y, m); accv.z += shfl_xor_f(accv.z, m); accv.w += shfl_xor_f(accv.w, m);
+                    }
+                    if (lane < 4 && act) {
+                        *reinterpret_cast<float4*>(pddh + (bt * (kLoopThreads / 32) + warp) * AP + 4 * i4) = accd;
+                        *reinterpret_cast<float4*>(pdva + (bt * (kLoopThreads / 32) + warp) * AP + 4 * i4) = accv;
+                    }
                 }
             }
             MMG_SYNCTHREADS();

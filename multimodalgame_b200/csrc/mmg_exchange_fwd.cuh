@@ -96,7 +96,7 @@ MMG_HOST_DEVICE int fwd_state_floats(const Dims& d, int BT) {
     if (pmax < kLoopThreads) pmax = kLoopThreads;
     n += 2 * BT * pmax;
     n += 4 * BT + 8;   // sprod, active, barrier
-    if (d.A) n += BT * (2 * align4(d.NW) + align4(d.A) + align4(d.D * d.Hr));   // scores, attention, d_h(h), attended y1 half
+    if (d.A) n += BT * (2 * align4(d.NW) + align4(d.A) + d.D * HrP + (kLoopThreads / d.Hr4) * HrP) + align4(d.A) + HrP;
     return n;
 }
 
@@ -136,7 +136,11 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
     float* ev = sm + o;   o += d.A ? BT * NWP : 0;                    // attention scores, later q_d(n) * a_n
     float* att = sm + o;  o += d.A ? BT * NWP : 0;                    // attention weights
     float* dhv = sm + o;  o += d.A ? BT * AP : 0;                     // d_h(h')
-    float* y1e = sm + o;  o += d.A ? BT * align4(d.D * d.Hr) : 0;     // attended description half of y1
+    const int DH = d.D * HrP;
+    float* y1e = sm + o;  o += d.A ? BT * DH : 0;                     // attended description half of y1, rows padded to float4
+    float* vas = sm + o;  o += d.A ? AP : 0;                          // d_attn.weight, zero padded
+    float* b1s = sm + o;  o += d.A ? HrP : 0;                         // y1.bias
+    float* wpart = sm + o; o += d.A ? BT * (kLoopThreads / (HrP >> 2)) * HrP : 0;   // word-slice partials of the w_d mix
     o += (o & 1);
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + o);
 
@@ -197,6 +201,11 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
     }
     if (tid < BT) { sprod[tid] = 1.f; smask[tid] = 1.f; if (b0 + tid < d.B) W.stop_mask[b0 + tid] = 1; }
     for (int idx = tid; idx < BT * HiP; idx += kLoopThreads) av[idx] = 0.f;
+    if (d.A) {
+        for (int idx = tid; idx < AP; idx += kLoopThreads) vas[idx] = idx < d.A ? ldg(aa.va + idx) : 0.f;
+        for (int idx = tid; idx < HrP; idx += kLoopThreads) b1s[idx] = idx < d.Hr ? ldg(aa.b1 + idx) : 0.f;
+        for (int idx = tid; idx < BT * AP; idx += kLoopThreads) dhv[idx] = 0.f;
+    }
 #ifdef MMG_CPU_EMU
     MMG_SYNCTHREADS();
 #endif
@@ -321,59 +330,87 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
         if (d.A) {
             // ---- -desc_attn (model.py:344-410): additive attention of h' over the words, softmax inside each class's
             //      segment.  The per-word halves (d_d(desc_set), desc_set . y1^T, desc_set . w_d^T) are loop invariant
-            //      tables written by K_pre, so the (B, NW, WV) broadcasts of the reference never exist.
-            const int DH = align4(d.D * d.Hr);
-            for (int o2 = warp; o2 < BT * d.A; o2 += kLoopThreads / 32) {                    // d_h(h')  model.py:359
-                const int bt = o2 / d.A, a = o2 % d.A, b = b0 + bt;
+            //      tables written by K_pre (rows padded to float4), so the (B, NW, WV) broadcasts of the reference never
+            //      exist.  The tables live in L2; every loop below keeps several independent 16-byte loads in flight per
+            //      thread and reduces inside 4- or 8-lane groups.
+            const int q4 = tid & 3, g4 = tid >> 2, A4 = AP >> 2;
+            for (int base = 0; base < BT * d.A; base += kLoopThreads / 4) {                    // d_h(h')  model.py:359
+                const int o2 = base + g4;
+                const bool ok = o2 < BT * d.A;
+                const int bt = ok ? o2 / d.A : 0, a = ok ? o2 % d.A : 0;
                 float s = 0.f;
-                for (int k = lane; k < d.Hr; k += 32) s = fmaf(ldg(aa.dh_w + (size_t)a * d.Hr + k), hv[bt * HrP + k], s);
-                s = warp_sum(s);
-                if (lane == 0) {
+                if (ok) {
+                    const float* wr = aa.dh_w + (size_t)a * d.Hr;
+#pragma unroll 4
+                    for (int k = q4; k < d.Hr; k += 4) s = fmaf(ldg(wr + k), hv[bt * HrP + k], s);
+                }
+                s = group_sum<4>(s);
+                if (ok && q4 == 0) {
                     s += ldg(aa.dh_b + a);
                     dhv[bt * AP + a] = s;
-                    if (train && b < d.B) W.dh_s[((size_t)t * d.B + b) * d.A + a] = s;
+                    if (train && b0 + bt < d.B) W.dh_s[((size_t)t * d.B + b0 + bt) * d.A + a] = s;
                 }
             }
             MMG_SYNCTHREADS();
-            for (int o2 = warp; o2 < BT * d.NW; o2 += kLoopThreads / 32) {                   // scores  model.py:366
-                const int bt = o2 / d.NW, n = o2 % d.NW;
+            for (int base = 0; base < BT * d.NW; base += kLoopThreads / 4) {                   // scores  model.py:366
+                const int o2 = base + g4;
+                const bool ok = o2 < BT * d.NW;
+                const int bt = ok ? o2 / d.NW : 0, n = ok ? o2 % d.NW : 0;
                 float s = 0.f;
-                for (int a = lane; a < d.A; a += 32)
-                    s = fmaf(ldg(aa.va + a), tanhf(ldg(W.wtab_dd + (size_t)n * d.A + a) + dhv[bt * AP + a]), s);
-                s = warp_sum(s);
-                if (lane == 0) ev[bt * NWP + n] = s + ldg(aa.ba);
+                if (ok) {
+                    const float4* row = reinterpret_cast<const float4*>(W.wtab_dd + (size_t)n * AP);
+                    const float4* dh4 = reinterpret_cast<const float4*>(dhv + bt * AP);
+                    const float4* va4 = reinterpret_cast<const float4*>(vas);
+#pragma unroll 4
+                    for (int i = q4; i < A4; i += 4) {
+                        const float4 w = ldg4(row + i), h = dh4[i], v = va4[i];
+                        s = fmaf(v.x, tanhf(w.x + h.x), s); s = fmaf(v.y, tanhf(w.y + h.y), s);
+                        s = fmaf(v.z, tanhf(w.z + h.z), s); s = fmaf(v.w, tanhf(w.w + h.w), s);
+                    }
+                }
+                s = group_sum<4>(s);
+                if (ok && q4 == 0) ev[bt * NWP + n] = s + ldg(aa.ba);
             }
             MMG_SYNCTHREADS();
-            for (int o2 = warp; o2 < BT * d.D; o2 += kLoopThreads / 32) {                    // segment softmax  model.py:372-381
-                const int bt = o2 / d.D, dd = o2 % d.D, b = b0 + bt;
-                const int s0 = W.seg[dd], s1 = W.seg[dd + 1];
+            for (int base = 0; base < BT * d.D; base += kLoopThreads / 8) {                    // segment softmax  model.py:372-381
+                const int o2 = base + (tid >> 3), l8 = tid & 7;
+                const bool ok = o2 < BT * d.D;
+                const int bt = ok ? o2 / d.D : 0, dd = ok ? o2 % d.D : 0, b = b0 + bt;
+                const int s0 = ok ? W.seg[dd] : 0, s1 = ok ? W.seg[dd + 1] : 0;
                 float mx = -INFINITY;
-                for (int n = s0 + lane; n < s1; n += 32) mx = fmaxf(mx, ev[bt * NWP + n]);
-                mx = warp_max(mx);
+                for (int n = s0 + l8; n < s1; n += 8) mx = fmaxf(mx, ev[bt * NWP + n]);
+                mx = group_max<8>(mx);
                 float se = 0.f;
-                for (int n = s0 + lane; n < s1; n += 32) se += expf(ev[bt * NWP + n] - mx);
-                se = warp_sum(se);
+                for (int n = s0 + l8; n < s1; n += 8) se += expf(ev[bt * NWP + n] - mx);
+                se = group_sum<8>(se);
                 const float inv = 1.f / se;
-                for (int n = s0 + lane; n < s1; n += 32) {
+                for (int n = s0 + l8; n < s1; n += 8) {
                     const float a = expf(ev[bt * NWP + n] - mx) * inv;
                     att[bt * NWP + n] = a;
                     if (train && b < d.B) W.attn[((size_t)t * d.B + b) * d.NW + n] = a;
                 }
             }
             MMG_SYNCTHREADS();
-            for (int idx = tid; idx < BT * d.D * d.Hr; idx += kLoopThreads) {                // y1 . [attended desc ; .]  model.py:383-410,432
-                const int bt = idx / (d.D * d.Hr), r = idx % (d.D * d.Hr), dd = r / d.Hr, k = r % d.Hr;
-                float s = ldg(aa.b1 + k);
+            const int K4 = HrP >> 2;
+            for (int idx = tid; idx < BT * d.D * K4; idx += kLoopThreads) {                    // y1 . [attended desc ; .]  model.py:383-410,432
+                const int bt = idx / (d.D * K4), r = idx % (d.D * K4), dd = r / K4, k4 = r % K4;
+                float4 s = *reinterpret_cast<const float4*>(b1s + 4 * k4);
                 const int s1 = W.seg[dd + 1];
-                for (int n = W.seg[dd]; n < s1; ++n) s = fmaf(att[bt * NWP + n], ldg(W.wtab_y1 + (size_t)n * d.Hr + k), s);
-                y1e[bt * DH + r] = s;
+                const float4* tab = reinterpret_cast<const float4*>(W.wtab_y1) + k4;
+#pragma unroll 8
+                for (int n = W.seg[dd]; n < s1; ++n) {
+                    const float4 w = ldg4(tab + (size_t)n * K4);
+                    const float a = att[bt * NWP + n];
+                    s.x = fmaf(a, w.x, s.x); s.y = fmaf(a, w.y, s.y); s.z = fmaf(a, w.z, s.z); s.w = fmaf(a, w.w, s.w);
+                }
+                *reinterpret_cast<float4*>(y1e + bt * DH + dd * HrP + 4 * k4) = s;
             }
             MMG_SYNCTHREADS();
         }
         // ---- S8b: class scores y[d] = y2(relu(y1h + y1d[d])) (model.py:432-433) — one warp per (example, class)
         for (int pair = warp; pair < BT * d.D; pair += kLoopThreads / 32) {
             const int bt = pair / d.D, dd = pair % d.D, b = b0 + bt;
-            const float* yd = d.A ? y1e + bt * align4(d.D * d.Hr) + dd * d.Hr : y1d + dd * d.Hr;
+            const float* yd = d.A ? y1e + bt * DH + dd * HrP : y1d + dd * d.Hr;
             float s = 0.f;
             for (int k = lane; k < d.Hr; k += 32)
                 s = fmaf(w2[k], fmaxf(0.f, head[bt * NHP + k] + yd[k]), s);
@@ -402,10 +439,31 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
             }
         }
         MMG_SYNCTHREADS();
-        if (d.A) {                      // word weights of the confidence-weighted description: q_class(n) * a_n (model.py:441-449)
+        if (d.A) {
+            // word weights of the confidence-weighted description: q_class(n) * a_n (model.py:441-449); the rows are also the
+            // A operand of the wd = (q a) . desc_set GEMM tiles that run beside the baselines (w_d gradient)
             for (int idx = tid; idx < BT * d.NW; idx += kLoopThreads) {
-                const int bt = idx / d.NW, n = idx % d.NW;
-                ev[bt * NWP + n] = qv[bt * DP + W.wcls[n]] * att[bt * NWP + n];
+                const int bt = idx / d.NW, n = idx % d.NW, b = b0 + bt;
+                const float v = qv[bt * DP + W.wcls[n]] * att[bt * NWP + n];
+                ev[bt * NWP + n] = v;
+                if (train && b < d.B) W.qa[((size_t)t * d.B + b) * d.NW + n] = v;
+            }
+            MMG_SYNCTHREADS();
+            // partial sums of (q a) . (desc_set . w_d^T): thread = (word slice, float4 column group)
+            const int K4 = HrP >> 2, NS = kLoopThreads / K4;
+            const int k4 = tid % K4, sl = tid / K4;
+            if (sl < NS) {
+                const float4* tab = reinterpret_cast<const float4*>(W.wtab_wd) + k4;
+                for (int bt = 0; bt < BT; ++bt) {
+                    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+                    for (int n = sl; n < d.NW; n += NS) {
+                        const float4 w = ldg4(tab + (size_t)n * K4);
+                        const float a = ev[bt * NWP + n];
+                        s.x = fmaf(a, w.x, s.x); s.y = fmaf(a, w.y, s.y); s.z = fmaf(a, w.z, s.z); s.w = fmaf(a, w.w, s.w);
+                    }
+                    *reinterpret_cast<float4*>(wpart + (bt * NS + sl) * HrP + 4 * k4) = s;
+                }
             }
             MMG_SYNCTHREADS();
         }
@@ -414,18 +472,17 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
             if (idx < BT * d.Hr) {
                 const int bt = idx / d.Hr, k = idx % d.Hr, b = b0 + bt;
                 float s = 0.f;
-                if (d.A) for (int n = 0; n < d.NW; ++n) s = fmaf(ev[bt * NWP + n], ldg(W.wtab_wd + (size_t)n * d.Hr + k), s);
+                if (d.A) { const int NS = kLoopThreads / (HrP >> 2); for (int sl = 0; sl < NS; ++sl) s += wpart[(bt * NS + sl) * HrP + k]; }
                 else for (int dd = 0; dd < d.D; ++dd) s = fmaf(qv[bt * DP + dd], wdd[dd * d.Hr + k], s);
                 const float hw = tanhf(head[bt * NHP + d.Hr + k] + s);
                 hwr[bt * HrP + k] = hw;
                 if (b < d.B) W.h_w[((size_t)t * d.B + b) * d.Hr + k] = hw;
-            } else if (train) {
+            } else if (train && !d.A) {        // -desc_attn: wd comes from GEMM tiles beside the baselines
                 const int i2 = idx - BT * d.Hr;
                 const int bt = i2 / d.WV, v = i2 % d.WV, b = b0 + bt;
                 if (b < d.B) {
                     float s = 0.f;
-                    if (d.A) for (int n = 0; n < d.NW; ++n) s = fmaf(ev[bt * NWP + n], ldg(aa.desc_set + (size_t)n * d.WV + v), s);
-                    else for (int dd = 0; dd < d.D; ++dd) s = fmaf(qv[bt * DP + dd], ldg(in.desc + (size_t)dd * d.WV + v), s);
+                    for (int dd = 0; dd < d.D; ++dd) s = fmaf(qv[bt * DP + dd], ldg(in.desc + (size_t)dd * d.WV + v), s);
                     W.wd[((size_t)t * d.B + b) * d.WV + v] = s;
                 }
             }

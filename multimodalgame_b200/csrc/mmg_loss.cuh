@@ -27,10 +27,12 @@ k_baseline_fwd(Dims d, ParamPtrs P, WsPtrs W, const float* desc, int n_bas_tiles
         t -= n_bas_tiles;
         const int nwv = cdiv(d.WV, kTile);
         const int nt = t % nwv, mt = t / nwv;
-        const Operand A = Operand{W.q, nullptr, nullptr, nullptr, d.D, 0, 0, 0, 0, OP_PLAIN};
+        // -desc_attn: rows (q_class(n) a_n) over the NW words and desc = desc_set (model.py:444-449)
+        const int Kw = d.A ? d.NW : d.D;
+        const Operand A = Operand{d.A ? W.qa : W.q, nullptr, nullptr, nullptr, Kw, 0, 0, 0, 0, OP_PLAIN};
         const Operand Bo = Operand{desc, nullptr, nullptr, nullptr, d.WV, 0, 1, 0, 0, OP_PLAIN};
         float acc[4][4];
-        gemm_tile(A, Bo, d.R, d.WV, mt * kTile, nt * kTile, 0, d.D, acc, nullptr, gs);
+        gemm_tile(A, Bo, d.R, d.WV, mt * kTile, nt * kTile, 0, Kw, acc, nullptr, gs);
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int r = mt * kTile + ty * 4 + a;

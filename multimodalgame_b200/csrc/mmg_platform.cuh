@@ -60,6 +60,12 @@ MMG_DEVICE float group_sum(float v) {
     for (int o = N / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+template <int N>
+MMG_DEVICE float group_max(float v) {
+#pragma unroll
+    for (int o = N / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
 // "last CTA done" ticket: returns the number of CTAs that arrived before this one (release/acquire around it)
 MMG_DEVICE unsigned ticket_take(unsigned* counter) {
     __threadfence();
@@ -252,6 +258,11 @@ MMG_DEVICE float fast_tanh(float x) { return 1.0f - 2.0f / (expf(2.0f * x) + 1.0
 template <int N>
 MMG_DEVICE float group_sum(float v) {
     for (int o = N / 2; o > 0; o >>= 1) v += (float)emu::shfl_xor(v, o);
+    return v;
+}
+template <int N>
+MMG_DEVICE float group_max(float v) {
+    for (int o = N / 2; o > 0; o >>= 1) v = fmaxf(v, (float)emu::shfl_xor(v, o));
     return v;
 }
 MMG_DEVICE unsigned ticket_take(unsigned* counter) { return __atomic_fetch_add(counter, 1u, __ATOMIC_SEQ_CST); }

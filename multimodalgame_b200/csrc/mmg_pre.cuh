@@ -117,6 +117,7 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
         gemm_tile(A, Bo, d.NW, N, mt * kTile, nt * kTile, 0, d.WV, acc, nullptr, gs);
         const int tx = tid % 16, ty = tid / 16;
         float* out = which == 0 ? W.wtab_y1 : (which == 1 ? W.wtab_wd : W.wtab_dd);
+        const int NP = align4(N);                   // rows padded to whole float4 groups, padding zero
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int n = mt * kTile + ty * 4 + a;
@@ -124,8 +125,8 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int k = nt * kTile + tx * 4 + c;
-                if (k >= N) continue;
-                out[(size_t)n * N + k] = acc[a][c] + (which == 2 ? ldg(P.p[MMG_P_REC_DD_B] + k) : 0.f);
+                if (k >= NP) continue;
+                out[(size_t)n * NP + k] = k < N ? acc[a][c] + (which == 2 ? ldg(P.p[MMG_P_REC_DD_B] + k) : 0.f) : 0.f;
             }
         }
         return;
