@@ -240,12 +240,13 @@ static ExchangeInputs resolve_inputs(const mmg_inputs* in) {
     return e;
 }
 
-struct Plan { int BT; int sender_smem; int fwd_smem_bytes; int bwd_smem_bytes; int fast; };
+struct Plan { int BT; int sender_smem; int fwd_smem_bytes; int bwd_smem_bytes; int fast; int attn_acc; };
 
-static AttnArgs attn_args(const Dims& d, const ParamPtrs& P, const ExchangeInputs& in) {
+static AttnArgs attn_args(const Dims& d, const ParamPtrs& P, const ExchangeInputs& in, const Plan& pl) {
     AttnArgs a;
     memset(&a, 0, sizeof(a));
     if (d.A) {
+        a.acc_smem = pl.attn_acc;
         a.dh_w = P.p[MMG_P_REC_DH_W]; a.dh_b = P.p[MMG_P_REC_DH_B]; a.va = P.p[MMG_P_REC_DA_W]; a.ba = P.p[MMG_P_REC_DA_B];
         a.b1 = P.p[MMG_P_REC_Y1_B]; a.desc_set = in.desc_set;
     }
@@ -295,7 +296,7 @@ static bool make_fast_plan(const Dims& d, Plan* pl) {
 }
 
 static int make_plan(const Dims& d, Plan* pl) {
-    pl->fast = 0;
+    pl->fast = 0; pl->attn_acc = 0;
     if (make_fast_plan(d, pl)) return MMG_OK;
     const FwdImage fi = make_fwd_image(d);
     const BwdImage bi = make_bwd_image(d);
@@ -305,8 +306,14 @@ static int make_plan(const Dims& d, Plan* pl) {
         const int full = (fi.total + st) * 4, recv_only = (fi.total - fi.sender_end + st) * 4;
         int bw_rec = (bi.total - bi.sender_end + bwd_rec_state_floats(d, pl->BT)) * 4;
         int bw_sen = (bi.sender_end + bwd_sen_state_floats(d, pl->BT)) * 4;
-        const int bw = bw_rec > bw_sen ? bw_rec : bw_sen;
+        int bw = bw_rec > bw_sen ? bw_rec : bw_sen;
         if (recv_only <= kMaxSmem && bw <= kMaxSmem) {
+            const int acc_bytes = d.A ? d.NW * align4(d.A) * 4 : 0;      // -desc_attn: d (d_d(word)) sums beside the weights when they fit
+            const char* env = getenv("MMG_ATTN_ACC_SMEM");        // =0 forces the global-memory accumulators (tests)
+            if (d.A && bw_rec + acc_bytes <= kMaxSmem && !(env && env[0] == '0')) {
+                pl->attn_acc = 1;
+                if (bw_rec + acc_bytes > bw) bw = bw_rec + acc_bytes;
+            }
             pl->sender_smem = full <= kMaxSmem ? 1 : 0;
             pl->fwd_smem_bytes = pl->sender_smem ? full : recv_only;
             pl->bwd_smem_bytes = bw;
@@ -456,7 +463,7 @@ static void build_wgrad_table(const Dims& d, const mmg_param_layout& L, const Pa
         b.add(km(W.dba, 1), ones(), 1, 1, R, MMG_P_REC_DA_B, 0, -1);
         Operand bw = km(in.desc_set, d.WV);
         bw.mod = d.NW;                                       // row (cta, n) -> desc_set[n]
-        b.add(km(W.ddd_part, align4(d.A)), bw, d.A, d.WV, n_rec_ctas * d.NW, MMG_P_REC_DD_W, 0, MMG_P_REC_DD_B);
+        b.add(km(W.ddd_part, align4(d.A)), bw, d.A, d.WV, d.NW, MMG_P_REC_DD_W, 0, MMG_P_REC_DD_B);   // slab 0 = sum over CTAs (K_attn_reduce)
     } else {
         Operand bd = km(in.desc, d.WV);
         bd.mod = d.D;                                        // row (b, d) -> desc[d]
@@ -632,7 +639,7 @@ static int exchange_forward_impl(const mmg_config* cfg, const float* d_params, c
     MMG_LAUNCH(k_pre, n_hx + n_cls + n_pack, kGemmThreads, 0, st, d, P, W, ei, n_hx, hx_kslice, pl.fast, n_cls);
     if ((rc = check_cuda("k_pre"))) return rc;
     // K_exchange_fwd
-    const AttnArgs aa = attn_args(d, P, ei);
+    const AttnArgs aa = attn_args(d, P, ei, pl);
     const float* b_img = P.p[MMG_P_SEN_IMG_B];
     if (pl.fast) rc = launch_fwd_fast(d, W, ei, FastFwdArgs{b_img, P.p[MMG_P_BS_L1_W], P.p[MMG_P_BS_L1_B]}, pl, st);
     else switch (pl.BT) {
@@ -711,7 +718,7 @@ static int backward_impl(const mmg_config* cfg, const float* d_params, const mmg
     const ExchangeInputs ei = resolve_inputs(in);
     cudaStream_t st = (cudaStream_t)stream;
     if (d.A && (!in->d_desc_set || !in->d_desc_set_lens)) return fail(MMG_ERR_INVALID, "desc_attn needs d_desc_set and d_desc_set_lens");
-    const AttnArgs aa = attn_args(d, P, ei);
+    const AttnArgs aa = attn_args(d, P, ei, pl);
     if (pl.fast) rc = d.M == 32 ? launch_bwd_fast_m<32>(d, W, P.p[MMG_P_SEN_BIN_W], P.p[MMG_P_SEN_CODE_W], pl, st)
                                 : launch_bwd_fast_m<64>(d, W, P.p[MMG_P_SEN_BIN_W], P.p[MMG_P_SEN_CODE_W], pl, st);
     else switch (pl.BT) {
@@ -721,6 +728,13 @@ static int backward_impl(const mmg_config* cfg, const float* d_params, const mmg
         default: rc = launch_bwd<8>(d, W, pl, st, aa); break;
     }
     if (rc) return rc;
+    if (d.A) {
+        const int slab_f4 = d.NW * align4(d.A) / 4;
+        int ctas = cdiv(slab_f4, 256);
+        if (ctas > 592) ctas = 592;
+        MMG_LAUNCH(k_attn_reduce, ctas, 256, 0, st, W.ddd_part, cdiv(d.B, pl.BT), slab_f4);
+        if ((rc = check_cuda("k_attn_reduce"))) return rc;
+    }
     WgTable tab;
     SplitTable stab;
     build_wgrad_table(d, L, P, W, ei, pl.fast, cdiv(d.B, pl.BT), &tab, &stab);

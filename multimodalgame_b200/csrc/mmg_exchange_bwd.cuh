@@ -122,6 +122,7 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
     float* dhs = sm + o;   o += d.A ? BT * AP : 0;                          // d_h(h) of this step
     float* vas = sm + o;   o += d.A ? AP : 0;                               // d_attn.weight, zero padded
     float* b1s = sm + o;   o += d.A ? HrP : 0;                              // y1.bias
+    float* ddacc = sm + o; o += (d.A && aa.acc_smem) ? d.NW * AP : 0;       // running d (d_d(word)) sums of this CTA
     float* pddh = sm + o;  o += d.A ? BT * (kLoopThreads / 32) * AP : 0;    // per-warp partials of d (d_h(h))
     float* pdva = sm + o;  o += d.A ? BT * (kLoopThreads / 32) * AP : 0;    // per-warp partials of d d_attn.weight
     o += (o & 1);
@@ -150,6 +151,7 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
         for (int idx = tid; idx < HrP; idx += kLoopThreads) b1s[idx] = idx < d.Hr ? ldg(aa.b1 + idx) : 0.f;
         for (int idx = tid; idx < BT * AP; idx += kLoopThreads) dhs[idx] = 0.f;
         for (int idx = tid; idx < BT * DH; idx += kLoopThreads) y1e[idx] = 0.f;
+        if (aa.acc_smem) for (int idx = tid; idx < d.NW * AP; idx += kLoopThreads) ddacc[idx] = 0.f;
     }
 #ifdef MMG_CPU_EMU
     MMG_SYNCTHREADS();
@@ -315,7 +317,7 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
             MMG_SYNCTHREADS();
             // through score = d_attn(tanh(d_d(word) + d_h(h))) (model.py:366): thread = (word group, float4 unit group); every
             // thread owns fixed (word, unit) elements for the whole kernel, so its running sum of d (d_d(word)) needs no atomics
-            float* dslab = W.ddd_part + (size_t)blockIdx.x * d.NW * AP;
+            float* dslab = aa.acc_smem ? ddacc : W.ddd_part + (size_t)blockIdx.x * d.NW * AP;
             for (int ib = 0; ib < A4; ib += 4) {        // uniform trip count: the partial sums meet through warp shuffles
                 const int i4 = ib + q4 < A4 ? ib + q4 : A4 - 1;
                 const bool act = ib + q4 < A4;
@@ -325,14 +327,14 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
                     float4 accd = make_float4(0.f, 0.f, 0.f, 0.f), accv = accd;
                     if (b < d.B && act) {
                         const float4 dha = *reinterpret_cast<const float4*>(dhs + bt * AP + 4 * i4);
-                        const bool init = first && bt == 0;
+                        const bool init = first && bt == 0 && !aa.acc_smem;
 #pragma unroll 4
                         for (int n = g4; n < d.NW; n += kLoopThreads / 4) {
                             const float4 w = ldg4(reinterpret_cast<const float4*>(W.wtab_dd + (size_t)n * AP) + i4);
                             float4* slot = reinterpret_cast<float4*>(dslab + (size_t)n * AP) + i4;
                             float4 acc = init ? make_float4(0.f, 0.f, 0.f, 0.f) : *slot;
                             const float de = dav[bt * NWP + n];
-                            const float tx = tanhf(w.x + dha.x), ty = tanhf(w.y + dha.y), tz = tanhf(w.z + dha.z), tw = tanhf(w.w + dha.w);
+                            const float tx = fast_tanh(w.x + dha.x), ty = fast_tanh(w.y + dha.y), tz = fast_tanh(w.z + dha.z), tw = fast_tanh(w.w + dha.w);
                             const float ux = de * va.x * (1.f - tx * tx), uy = de * va.y * (1.f - ty * ty),
                                         uz = de * va.z * (1.f - tz * tz), uw = de * va.w * (1.f - tw * tw);
                             accd.x += ux; accd.y += uy; accd.z += uz; accd.w += uw;
@@ -340,7 +342,7 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
                             acc.x += ux; acc.y += uy; acc.z += uz; acc.w += uw;
                             *slot = acc;
                         }
-                    } else if (first && bt == 0 && act) {
+                    } else if (first && bt == 0 && act && !aa.acc_smem) {
                         for (int n = g4; n < d.NW; n += kLoopThreads / 4)
                             *(reinterpret_cast<float4*>(dslab + (size_t)n * AP) + i4) = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
@@ -414,6 +416,28 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
         split_matvec<BT, false>(WhhT, d.Hr, cdiv(d.G3, 4), dghs, G3P, partB, sp_hh);
         first = false;
         // no barrier needed here: R1 of the next step touches dlw/dls/yflag only, and the barrier after it orders partB
+    }
+    if (d.A && aa.acc_smem) {       // publish this CTA's d (d_d(word)) sums (summed over CTAs by K_attn_reduce)
+        MMG_SYNCTHREADS();
+        float4* out = reinterpret_cast<float4*>(W.ddd_part + (size_t)blockIdx.x * d.NW * AP);
+        for (int idx = tid; idx < d.NW * (AP >> 2); idx += kLoopThreads) out[idx] = reinterpret_cast<const float4*>(ddacc)[idx];
+    }
+}
+
+// Sum of the per-CTA d (d_d(word)) slabs into slab 0, slab order (deterministic): K = NW rows for the d_d.weight GEMM
+// instead of n_ctas * NW.
+MMG_GLOBAL void __launch_bounds__(256)
+k_attn_reduce(float* slabs, int n_slabs, int slab_f4) {
+    pdl_wait(); pdl_launch_dependents();
+    float4* s4 = reinterpret_cast<float4*>(slabs);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < slab_f4; i += gridDim.x * 256) {
+        float4 acc = s4[i];
+#pragma unroll 8
+        for (int c = 1; c < n_slabs; ++c) {
+            const float4 v = s4[(size_t)c * slab_f4 + i];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        s4[i] = acc;
     }
 }
 

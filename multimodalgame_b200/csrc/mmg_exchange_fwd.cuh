@@ -364,8 +364,8 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
 #pragma unroll 4
                     for (int i = q4; i < A4; i += 4) {
                         const float4 w = ldg4(row + i), h = dh4[i], v = va4[i];
-                        s = fmaf(v.x, tanhf(w.x + h.x), s); s = fmaf(v.y, tanhf(w.y + h.y), s);
-                        s = fmaf(v.z, tanhf(w.z + h.z), s); s = fmaf(v.w, tanhf(w.w + h.w), s);
+                        s = fmaf(v.x, fast_tanh(w.x + h.x), s); s = fmaf(v.y, fast_tanh(w.y + h.y), s);
+                        s = fmaf(v.z, fast_tanh(w.z + h.z), s); s = fmaf(v.w, fast_tanh(w.w + h.w), s);
                     }
                 }
                 s = group_sum<4>(s);

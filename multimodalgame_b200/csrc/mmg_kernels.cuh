@@ -57,6 +57,7 @@ struct AttnArgs {             // -desc_attn parameters read straight from the fl
     const float* ba;           // d_attn.bias (1)
     const float* b1;           // y1.bias (Hr)
     const float* desc_set;     // (NW,WV)
+    int acc_smem;              // backward: the running d (d_d(word)) sums live in shared memory (they fit beside the weights)
 };
 
 }  // namespace mmg

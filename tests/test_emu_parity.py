@@ -20,6 +20,12 @@ def test_emulated_eval_matches_reference_golden(case):
     pu.run_eval_case(case, emu_util.emu_library(), "cpu")
 
 
+def test_emulated_desc_attn_global_accumulators(monkeypatch):
+    """-desc_attn backward with the d (d_d(word)) sums in global memory (word sets too large for shared memory)."""
+    monkeypatch.setenv("MMG_ATTN_ACC_SMEM", "0")
+    pu.run_train_case("desc_attn_small", emu_util.emu_library(), "cpu")
+
+
 def test_emulated_synthetic_odd_dims():
     from oracle import game_oracle as go
     cfg = go.GameConfig(batch_size=7, img_feat_dim=131, img_h_dim=45, baseline_hid_dim=71, sender_out_dim=13,
