@@ -188,8 +188,7 @@ static void ws_layout(const Dims& d, Ws* w) {
         w->ddh = take(c, R * A * f);
         w->dva = take(c, R * A * f);
         w->dba = take(c, R * f);
-        w->ddd_part = take(c, B * NW * AP * f);     // at most one receiver CTA per example
-        w->wdsel = take(c, B * d.D * d.WV * f);
+        w->ddd_part = take(c, B * NW * (AP + HrP) * f);     // per receiver CTA (at most one per example): [NW][AP] ; [NW][HrP]
     }
     p.total_bytes = c;
 }
@@ -217,7 +216,7 @@ static WsPtrs resolve(const Ws& w, void* base) {
     r.tickets = (unsigned*)(b + w.tickets);
     r.opt_counters = (long long*)(b + w.opt_counters);
 #define G_(name) r.name = (float*)(b + w.name)
-    G_(wtab_dd); G_(wtab_y1); G_(wtab_wd); G_(qa); G_(attn); G_(dh_s); G_(ddh); G_(dva); G_(dba); G_(ddd_part); G_(wdsel);
+    G_(wtab_dd); G_(wtab_y1); G_(wtab_wd); G_(qa); G_(attn); G_(dh_s); G_(ddh); G_(dva); G_(dba); G_(ddd_part);
 #undef G_
     r.seg = (int*)(b + w.seg); r.wcls = (int*)(b + w.wcls);
     r.hx_split = w.hx_split; r.wgrad_split = w.wgrad_split; r.ntb = w.ntb;
@@ -457,7 +456,9 @@ static void build_wgrad_table(const Dims& d, const mmg_param_layout& L, const Pa
     b.add(km(W.g_h, Hr), km(W.hsel, Hr), Hr, Hr, B, MMG_P_REC_Y1_W, d.y1_hcol, -1);
     if (d.A) {
         // -desc_attn: the description rows of y1's input are the attended bags of words of the prediction step
-        b.add(km(W.dy1, Hr), km(W.wdsel, d.WV), Hr, d.WV, B * d.D, MMG_P_REC_Y1_W, d.y1_dcol, MMG_P_REC_Y1_B);
+        Operand bz = km(in.desc_set, d.WV);
+        b.add(km(W.ddd_part + (size_t)d.NW * align4(d.A), align4(Hr)), bz, Hr, d.WV, d.NW, MMG_P_REC_Y1_W, d.y1_dcol, -1);   // Z^T . desc_set
+        b.add(km(W.dy1, Hr), ones(), Hr, 1, B * d.D, MMG_P_REC_Y1_B, 0, -1);
         b.add(km(W.ddh, d.A), km(h_after, Hr), d.A, Hr, R, MMG_P_REC_DH_W, 0, MMG_P_REC_DH_B);
         b.add(km(W.dva, d.A), ones(), d.A, 1, R, MMG_P_REC_DA_W, 0, -1);                 // d_attn.weight (1, A)
         b.add(km(W.dba, 1), ones(), 1, 1, R, MMG_P_REC_DA_B, 0, -1);
@@ -729,8 +730,8 @@ static int backward_impl(const mmg_config* cfg, const float* d_params, const mmg
     }
     if (rc) return rc;
     if (d.A) {
-        const int slab_f4 = d.NW * align4(d.A) / 4;
-        int ctas = cdiv(slab_f4, 256);
+        const int slab_f4 = d.NW * (align4(d.A) + align4(d.Hr)) / 4;
+        int ctas = cdiv(slab_f4, 32);
         if (ctas > 592) ctas = 592;
         MMG_LAUNCH(k_attn_reduce, ctas, 256, 0, st, W.ddd_part, cdiv(d.B, pl.BT), slab_f4);
         if ((rc = check_cuda("k_attn_reduce"))) return rc;

@@ -123,6 +123,7 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
     float* vas = sm + o;   o += d.A ? AP : 0;                               // d_attn.weight, zero padded
     float* b1s = sm + o;   o += d.A ? HrP : 0;                              // y1.bias
     float* ddacc = sm + o; o += (d.A && aa.acc_smem) ? d.NW * AP : 0;       // running d (d_d(word)) sums of this CTA
+    const size_t slab_floats = (size_t)d.NW * (AP + HrP);                   // per-CTA slab: [NW][AP] d (d_d(word)) ; [NW][HrP] Z
     float* pddh = sm + o;  o += d.A ? BT * (kLoopThreads / 32) * AP : 0;    // per-warp partials of d (d_h(h))
     float* pdva = sm + o;  o += d.A ? BT * (kLoopThreads / 32) * AP : 0;    // per-warp partials of d d_attn.weight
     o += (o & 1);
@@ -152,6 +153,8 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
         for (int idx = tid; idx < BT * AP; idx += kLoopThreads) dhs[idx] = 0.f;
         for (int idx = tid; idx < BT * DH; idx += kLoopThreads) y1e[idx] = 0.f;
         if (aa.acc_smem) for (int idx = tid; idx < d.NW * AP; idx += kLoopThreads) ddacc[idx] = 0.f;
+        float4* zs = reinterpret_cast<float4*>(W.ddd_part + (size_t)blockIdx.x * slab_floats + (size_t)d.NW * AP);
+        for (int idx = tid; idx < d.NW * (HrP >> 2); idx += kLoopThreads) zs[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #ifdef MMG_CPU_EMU
     MMG_SYNCTHREADS();
@@ -204,7 +207,7 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
         MMG_SYNCTHREADS();
         if (d.A) {
             // ---- -desc_attn, prediction step only: rebuild the attended y1 half from the saved attention weights, and the
-            //      attended description itself (the `weighted_desc` rows that multiply d y1, model.py:383-410)
+            //      (the weight gradient of y1's description columns is formed per WORD below, after R2)
             const int K4 = HrP >> 2;
             for (int idx = tid; idx < BT * d.D * K4; idx += kLoopThreads) {
                 const int bt = idx / (d.D * K4), r = idx % (d.D * K4), dd = r / K4, k4 = r % K4;
@@ -219,15 +222,6 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
                     s4.x = fmaf(a, w.x, s4.x); s4.y = fmaf(a, w.y, s4.y); s4.z = fmaf(a, w.z, s4.z); s4.w = fmaf(a, w.w, s4.w);
                 }
                 *reinterpret_cast<float4*>(y1e + bt * DH + dd * HrP + 4 * k4) = s4;
-            }
-            for (int idx = tid; idx < BT * d.D * d.WV; idx += kLoopThreads) {
-                const int bt = idx / (d.D * d.WV), r = idx % (d.D * d.WV), dd = r / d.WV, v = r % d.WV, b = b0 + bt;
-                if (yflag[bt] == 0.f) continue;
-                float s = 0.f;
-                const int s1 = W.seg[dd + 1];
-#pragma unroll 8
-                for (int n = W.seg[dd]; n < s1; ++n) s = fmaf(att[bt * NWP + n], ldg(aa.desc_set + (size_t)n * d.WV + v), s);
-                W.wdsel[(size_t)b * d.D * d.WV + r] = s;
             }
             MMG_SYNCTHREADS();
         }
@@ -257,6 +251,25 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
             dvec[bt * H2P + d.Hr + k] = G;
         }
         MMG_SYNCTHREADS();
+        if (d.A) {
+            // d y1.weight[:, desc columns] = sum_{b,class} d y1[b,class]^T (x) weighted_desc[b,class]  (model.py:383-410)
+            //                              = sum_words ( sum_b a[b,n] d y1[b,class(n)] )^T (x) desc_set[n]:
+            // accumulate the per-word factor Z[n] in this CTA's slab (fixed element -> thread mapping, no atomics);
+            // K_attn_reduce sums the slabs and K_wgrad multiplies by desc_set (K = NW instead of B*D attended rows)
+            const int K4 = HrP >> 2;
+            float4* zs = reinterpret_cast<float4*>(W.ddd_part + (size_t)blockIdx.x * slab_floats + (size_t)d.NW * AP);
+            for (int bt = 0; bt < BT; ++bt) {
+                if (yflag[bt] == 0.f) continue;
+                for (int idx = tid; idx < d.NW * K4; idx += kLoopThreads) {
+                    const int n = idx / K4, k4 = idx % K4;
+                    const float a = att[bt * NWP + n];
+                    const float4 g = *reinterpret_cast<const float4*>(y1e + bt * DH + W.wcls[n] * HrP + 4 * k4);
+                    float4 z = zs[idx];
+                    z.x = fmaf(a, g.x, z.x); z.y = fmaf(a, g.y, z.y); z.z = fmaf(a, g.z, z.z); z.w = fmaf(a, g.w, z.w);
+                    zs[idx] = z;
+                }
+            }
+        }
         // ---- R3: through tanh of the message hidden (model.py:452) ---------------------------------------------
         for (int idx = tid; idx < BT * d.Hr; idx += kLoopThreads) {
             const int bt = idx / d.Hr, k = idx % d.Hr, b = b0 + bt;
@@ -317,7 +330,7 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
             MMG_SYNCTHREADS();
             // through score = d_attn(tanh(d_d(word) + d_h(h))) (model.py:366): thread = (word group, float4 unit group); every
             // thread owns fixed (word, unit) elements for the whole kernel, so its running sum of d (d_d(word)) needs no atomics
-            float* dslab = aa.acc_smem ? ddacc : W.ddd_part + (size_t)blockIdx.x * d.NW * AP;
+            float* dslab = aa.acc_smem ? ddacc : W.ddd_part + (size_t)blockIdx.x * slab_floats;
             for (int ib = 0; ib < A4; ib += 4) {        // uniform trip count: the partial sums meet through warp shuffles
                 const int i4 = ib + q4 < A4 ? ib + q4 : A4 - 1;
                 const bool act = ib + q4 < A4;
@@ -419,7 +432,7 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
     }
     if (d.A && aa.acc_smem) {       // publish this CTA's d (d_d(word)) sums (summed over CTAs by K_attn_reduce)
         MMG_SYNCTHREADS();
-        float4* out = reinterpret_cast<float4*>(W.ddd_part + (size_t)blockIdx.x * d.NW * AP);
+        float4* out = reinterpret_cast<float4*>(W.ddd_part + (size_t)blockIdx.x * slab_floats);
         for (int idx = tid; idx < d.NW * (AP >> 2); idx += kLoopThreads) out[idx] = reinterpret_cast<const float4*>(ddacc)[idx];
     }
 }
@@ -428,16 +441,28 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
 // instead of n_ctas * NW.
 MMG_GLOBAL void __launch_bounds__(256)
 k_attn_reduce(float* slabs, int n_slabs, int slab_f4) {
+    // CTA = 32 float4 columns x 8 slab groups; the groups meet in shared memory in a fixed order
+    MMG_SHARED float4 part[8][32];
     pdl_wait(); pdl_launch_dependents();
     float4* s4 = reinterpret_cast<float4*>(slabs);
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < slab_f4; i += gridDim.x * 256) {
-        float4 acc = s4[i];
+    const int col = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    for (int base = blockIdx.x * 32; base < slab_f4; base += gridDim.x * 32) {
+        const int i = base + col;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < slab_f4) {
 #pragma unroll 8
-        for (int c = 1; c < n_slabs; ++c) {
-            const float4 v = s4[(size_t)c * slab_f4 + i];
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            for (int c = grp; c < n_slabs; c += 8) {
+                const float4 v = s4[(size_t)c * slab_f4 + i];
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
         }
-        s4[i] = acc;
+        part[grp][col] = acc;
+        MMG_SYNCTHREADS();
+        if (grp == 0 && i < slab_f4) {
+            for (int g = 1; g < 8; ++g) { const float4 v = part[g][col]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+            s4[i] = acc;
+        }
+        MMG_SYNCTHREADS();
     }
 }
 

@@ -24,7 +24,7 @@ struct WsPtrs {               // resolved workspace arrays (device pointers)
     unsigned* tickets;
     long long* opt_counters;
     // -desc_attn
-    float *wtab_dd, *wtab_y1, *wtab_wd, *qa, *attn, *dh_s, *ddh, *dva, *dba, *ddd_part, *wdsel;
+    float *wtab_dd, *wtab_y1, *wtab_wd, *qa, *attn, *dh_s, *ddh, *dva, *dba, *ddd_part;
     int *seg, *wcls;
     int hx_split, wgrad_split, ntb;
 };

@@ -247,8 +247,8 @@ struct Ws {   // byte offsets into the workspace
     int64_t ddh;       // (T,B,A)  dL/d dh_s
     int64_t dva;       // (T,B,A)  per-row partial of dL/d d_attn.weight;  dba (T,B): of d_attn.bias
     int64_t dba;
-    int64_t ddd_part;  // (n_rec_ctas, NW, A) per-CTA partial of dL/d wtab_dd, accumulated over the CTA's steps/examples
-    int64_t wdsel;     // (B,D,WV) attended description of every class at the prediction step
+    int64_t ddd_part;  // (n_rec_ctas, [NW][A4] ; [NW][Hr4]) per-CTA partials: dL/d wtab_dd summed over the CTA's steps/examples,
+                       // and Z[n] = sum_b a[b,n] d y1[b,class(n)] (word factor of the y1 description-column gradient)
     int hx_split, wgrad_split, ntb;
 };
 
