@@ -307,6 +307,10 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
             const size_t row = (size_t)t * d.B + b;
             if (oo < d.Hr) {
                 if (b < d.B) W.y1h[row * d.Hr + oo] = v;
+            } else if (oo > 2 * d.Hr) {        // d_h(h') of the description attention (model.py:359), rides in the stacked heads
+                const int a = oo - 2 * d.Hr - 1;
+                dhv[bt * AP + a] = v;
+                if (train && b < d.B) W.dh_s[row * d.A + a] = v;
             } else if (oo == 2 * d.Hr) {
                 const float sp = sigmoidf_(v);
                 float sbit;
@@ -334,42 +338,32 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
             //      exist.  The tables live in L2; every loop below keeps several independent 16-byte loads in flight per
             //      thread and reduces inside 4- or 8-lane groups.
             const int q4 = tid & 3, g4 = tid >> 2, A4 = AP >> 2;
-            for (int base = 0; base < BT * d.A; base += kLoopThreads / 4) {                    // d_h(h')  model.py:359
-                const int o2 = base + g4;
-                const bool ok = o2 < BT * d.A;
-                const int bt = ok ? o2 / d.A : 0, a = ok ? o2 % d.A : 0;
-                float s = 0.f;
-                if (ok) {
-                    const float* wr = aa.dh_w + (size_t)a * d.Hr;
+            // scores (model.py:366): 4 lanes per word, two words per lane group in flight
+            for (int base = 0; base < BT * d.NW; base += kLoopThreads / 2) {
+                const int oa = base + g4, ob = oa + kLoopThreads / 4;
+                const bool oka = oa < BT * d.NW, okb = ob < BT * d.NW;
+                const int bta = oka ? oa / d.NW : 0, na = oka ? oa % d.NW : 0;
+                const int btb = okb ? ob / d.NW : 0, nb = okb ? ob % d.NW : 0;
+                const float4* rowa = reinterpret_cast<const float4*>(W.wtab_dd + (size_t)na * AP);
+                const float4* rowb = reinterpret_cast<const float4*>(W.wtab_dd + (size_t)nb * AP);
+                const float4* dha = reinterpret_cast<const float4*>(dhv + bta * AP);
+                const float4* dhb = reinterpret_cast<const float4*>(dhv + btb * AP);
+                const float4* va4 = reinterpret_cast<const float4*>(vas);
+                float sa = 0.f, sb = 0.f;
 #pragma unroll 4
-                    for (int k = q4; k < d.Hr; k += 4) s = fmaf(ldg(wr + k), hv[bt * HrP + k], s);
+                for (int i = q4; i < A4; i += 4) {
+                    const float4 wa = ldg4(rowa + i), wb = ldg4(rowb + i), ha = dha[i], hb = dhb[i], v = va4[i];
+                    sa = fmaf(v.x, fast_tanh(wa.x + ha.x), sa); sa = fmaf(v.y, fast_tanh(wa.y + ha.y), sa);
+                    sa = fmaf(v.z, fast_tanh(wa.z + ha.z), sa); sa = fmaf(v.w, fast_tanh(wa.w + ha.w), sa);
+                    sb = fmaf(v.x, fast_tanh(wb.x + hb.x), sb); sb = fmaf(v.y, fast_tanh(wb.y + hb.y), sb);
+                    sb = fmaf(v.z, fast_tanh(wb.z + hb.z), sb); sb = fmaf(v.w, fast_tanh(wb.w + hb.w), sb);
                 }
-                s = group_sum<4>(s);
-                if (ok && q4 == 0) {
-                    s += ldg(aa.dh_b + a);
-                    dhv[bt * AP + a] = s;
-                    if (train && b0 + bt < d.B) W.dh_s[((size_t)t * d.B + b0 + bt) * d.A + a] = s;
+                sa = group_sum<4>(sa); sb = group_sum<4>(sb);
+                if (q4 == 0) {
+                    const float ba = ldg(aa.ba);
+                    if (oka) ev[bta * NWP + na] = sa + ba;
+                    if (okb) ev[btb * NWP + nb] = sb + ba;
                 }
-            }
-            MMG_SYNCTHREADS();
-            for (int base = 0; base < BT * d.NW; base += kLoopThreads / 4) {                   // scores  model.py:366
-                const int o2 = base + g4;
-                const bool ok = o2 < BT * d.NW;
-                const int bt = ok ? o2 / d.NW : 0, n = ok ? o2 % d.NW : 0;
-                float s = 0.f;
-                if (ok) {
-                    const float4* row = reinterpret_cast<const float4*>(W.wtab_dd + (size_t)n * AP);
-                    const float4* dh4 = reinterpret_cast<const float4*>(dhv + bt * AP);
-                    const float4* va4 = reinterpret_cast<const float4*>(vas);
-#pragma unroll 4
-                    for (int i = q4; i < A4; i += 4) {
-                        const float4 w = ldg4(row + i), h = dh4[i], v = va4[i];
-                        s = fmaf(v.x, fast_tanh(w.x + h.x), s); s = fmaf(v.y, fast_tanh(w.y + h.y), s);
-                        s = fmaf(v.z, fast_tanh(w.z + h.z), s); s = fmaf(v.w, fast_tanh(w.w + h.w), s);
-                    }
-                }
-                s = group_sum<4>(s);
-                if (ok && q4 == 0) ev[bt * NWP + n] = s + ldg(aa.ba);
             }
             MMG_SYNCTHREADS();
             for (int base = 0; base < BT * d.D; base += kLoopThreads / 8) {                    // segment softmax  model.py:372-381
@@ -392,18 +386,28 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
             }
             MMG_SYNCTHREADS();
             const int K4 = HrP >> 2;
-            for (int idx = tid; idx < BT * d.D * K4; idx += kLoopThreads) {                    // y1 . [attended desc ; .]  model.py:383-410,432
-                const int bt = idx / (d.D * K4), r = idx % (d.D * K4), dd = r / K4, k4 = r % K4;
-                float4 s = *reinterpret_cast<const float4*>(b1s + 4 * k4);
-                const int s1 = W.seg[dd + 1];
-                const float4* tab = reinterpret_cast<const float4*>(W.wtab_y1) + k4;
-#pragma unroll 8
-                for (int n = W.seg[dd]; n < s1; ++n) {
-                    const float4 w = ldg4(tab + (size_t)n * K4);
-                    const float a = att[bt * NWP + n];
-                    s.x = fmaf(a, w.x, s.x); s.y = fmaf(a, w.y, s.y); s.z = fmaf(a, w.z, s.z); s.w = fmaf(a, w.w, s.w);
+            // y1 . [attended desc ; .] (model.py:383-410,432): thread = (class, float4 column group), two items in flight
+            for (int base = 0; base < BT * d.D * K4; base += 2 * kLoopThreads) {
+                const int ia = base + tid, ib = ia + kLoopThreads, tot = BT * d.D * K4;
+                const bool oka = ia < tot, okb = ib < tot;
+                const int ra = oka ? ia : 0, rb = okb ? ib : 0;
+                const int bta = ra / (d.D * K4), da = (ra % (d.D * K4)) / K4, ka = ra % K4;
+                const int btb = rb / (d.D * K4), db = (rb % (d.D * K4)) / K4, kb = rb % K4;
+                const int a0 = W.seg[da], a1 = W.seg[da + 1], c0 = W.seg[db], c1 = W.seg[db + 1];
+                const int len = max(a1 - a0, c1 - c0);
+                float4 sa = *reinterpret_cast<const float4*>(b1s + 4 * ka), sb = *reinterpret_cast<const float4*>(b1s + 4 * kb);
+                const float4* taba = reinterpret_cast<const float4*>(W.wtab_y1) + ka;
+                const float4* tabb = reinterpret_cast<const float4*>(W.wtab_y1) + kb;
+#pragma unroll 4
+                for (int i = 0; i < len; ++i) {
+                    const int na = min(a0 + i, a1 - 1), nb = min(c0 + i, c1 - 1);      // clamped: the load is always legal
+                    const float4 wa = ldg4(taba + (size_t)na * K4), wb = ldg4(tabb + (size_t)nb * K4);
+                    const float fa = a0 + i < a1 ? att[bta * NWP + na] : 0.f, fb = c0 + i < c1 ? att[btb * NWP + nb] : 0.f;
+                    sa.x = fmaf(fa, wa.x, sa.x); sa.y = fmaf(fa, wa.y, sa.y); sa.z = fmaf(fa, wa.z, sa.z); sa.w = fmaf(fa, wa.w, sa.w);
+                    sb.x = fmaf(fb, wb.x, sb.x); sb.y = fmaf(fb, wb.y, sb.y); sb.z = fmaf(fb, wb.z, sb.z); sb.w = fmaf(fb, wb.w, sb.w);
                 }
-                *reinterpret_cast<float4*>(y1e + bt * DH + dd * HrP + 4 * k4) = s;
+                if (oka) *reinterpret_cast<float4*>(y1e + bta * DH + da * HrP + 4 * ka) = sa;
+                if (okb) *reinterpret_cast<float4*>(y1e + btb * DH + db * HrP + 4 * kb) = sb;
             }
             MMG_SYNCTHREADS();
         }

@@ -11,7 +11,7 @@ struct Dims {
     int R;        // T * B rows, step-major
     int G3;       // 3 * Hr
     int M4, Hr4, Hi4;   // ceil(x / 4): float4 groups along a reduction dimension
-    int NH;       // stacked head rows: [y1.weight[:, :Hr] ; w_h.weight ; s.weight] = 2*Hr + 1
+    int NH;       // stacked head rows: [y1.weight[:, h cols] ; w_h.weight ; s.weight ; d_h.weight (desc_attn)] = 2*Hr + 1 + A
     int use_binary, fixed, s_prob_prod, ignore_receiver;
     float first_rec;
     float flip_sen, flip_rec;   // flipout probabilities, < 0 = off (model.py:233-234,467-468)
@@ -28,7 +28,6 @@ MMG_HOST_DEVICE Dims make_dims(const mmg_config& c) {
     d.Hr = c.rec_hidden; d.D = c.n_classes; d.WV = c.wv_dim; d.Hb = c.baseline_hid; d.T = c.max_exchange;
     d.R = d.T * d.B; d.G3 = 3 * d.Hr;
     d.M4 = cdiv(d.M, 4); d.Hr4 = cdiv(d.Hr, 4); d.Hi4 = cdiv(d.Hi, 4);
-    d.NH = 2 * d.Hr + 1;
     d.use_binary = c.use_binary; d.fixed = c.fixed_exchange; d.s_prob_prod = c.s_prob_prod;
     d.ignore_receiver = c.ignore_receiver;
     d.first_rec = c.first_rec;
@@ -38,6 +37,7 @@ MMG_HOST_DEVICE Dims make_dims(const mmg_config& c) {
     d.mix_prod = c.sender_mix == MMG_MIX_PROD; d.ignore_code = c.ignore_code;
     d.A = c.desc_attn ? c.desc_attn_dim : 0; d.NW = c.desc_attn ? c.n_words : 0;
     d.y1_hcol = d.A ? d.WV : 0; d.y1_dcol = d.A ? 0 : d.Hr;
+    d.NH = 2 * d.Hr + 1 + d.A;
     return d;
 }
 
@@ -57,7 +57,7 @@ struct FwdImage {
     // receiver part
     int wih;     // rnn.weight_ih  out=3Hr red=M
     int whh;     // rnn.weight_hh  out=3Hr red=Hr
-    int whead;   // [y1.weight[:, :Hr] ; w_h.weight ; s.weight]  out=NH red=Hr
+    int whead;   // [y1.weight[:, h cols] ; w_h.weight ; s.weight ; d_h.weight]  out=NH red=Hr
     int ww;      // w.weight       out=M   red=Hr
     int b_ih, b_hh;   // [3Hr] each
     int b_head;  // [NH]  (0 for the y1 rows: y1.bias is folded into y1d; w_h.bias; s.bias)
@@ -100,8 +100,8 @@ MMG_HOST_DEVICE FwdImage make_fwd_image(const Dims& d) {
     im.w2 = o; o += align4(d.Hr);
     im.b_w = o; o += align4(d.M);
     im.misc = o; o += 4;
-    im.y1d = o; o += align4(d.D * d.Hr);
-    im.wdd = o; o += align4(d.D * d.Hr);
+    im.y1d = o; o += d.A ? 0 : align4(d.D * d.Hr);      // -desc_attn: word tables in global memory replace the class tables
+    im.wdd = o; o += d.A ? 0 : align4(d.D * d.Hr);
     im.total = o;
     return im;
 }

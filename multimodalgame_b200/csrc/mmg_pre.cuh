@@ -29,7 +29,8 @@ MMG_DEVICE float fwd_image_elem(const Dims& d, const FwdImage& im, const ParamPt
     if (e < im.ww) { int q = e - im.whead; int r = (q / (d.NH * 4)) * 4 + (q & 3), o = (q >> 2) % d.NH;
         if (o < d.Hr) return packed_src(P.p[MMG_P_REC_Y1_W] + d.y1_hcol, d.Hr + d.WV, o, r, d.Hr);
         if (o < 2 * d.Hr) return packed_src(P.p[MMG_P_REC_WH_W], d.Hr, o - d.Hr, r, d.Hr);
-        return packed_src(P.p[MMG_P_REC_S_W], d.Hr, 0, r, d.Hr); }
+        if (o == 2 * d.Hr) return packed_src(P.p[MMG_P_REC_S_W], d.Hr, 0, r, d.Hr);
+        return packed_src(P.p[MMG_P_REC_DH_W], d.Hr, o - 2 * d.Hr - 1, r, d.Hr); }      // d_h.weight (desc_attn)
     if (e < im.b_ih) { int q = e - im.ww; int r = (q / (d.M * 4)) * 4 + (q & 3), o = (q >> 2) % d.M;
         return packed_src(P.p[MMG_P_REC_W_W], d.Hr, o, r, d.Hr); }
     if (e < im.b_hh) { int i = e - im.b_ih; return i < d.G3 ? ldg(P.p[MMG_P_REC_RNN_BIH] + i) : 0.f; }
@@ -38,6 +39,7 @@ MMG_DEVICE float fwd_image_elem(const Dims& d, const FwdImage& im, const ParamPt
         if (i < d.Hr) return 0.f;
         if (i < 2 * d.Hr) return ldg(P.p[MMG_P_REC_WH_B] + (i - d.Hr));
         if (i == 2 * d.Hr) return ldg(P.p[MMG_P_REC_S_B]);
+        if (i < d.NH) return ldg(P.p[MMG_P_REC_DH_B] + (i - 2 * d.Hr - 1));
         return 0.f; }
     if (e < im.b_w) { int i = e - im.w2; return i < d.Hr ? ldg(P.p[MMG_P_REC_Y2_W] + i) : 0.f; }
     if (e < im.misc) { int i = e - im.b_w; return i < d.M ? ldg(P.p[MMG_P_REC_W_B] + i) : 0.f; }
