@@ -147,7 +147,7 @@ static void ws_layout(const Dims& d, Ws* w) {
     w->hx_split = hs;
     w->hx_part = take(c, (int64_t)hs * B * d.Hi * f);
     int64_t fi = make_fwd_image(d).total, bi = make_bwd_image(d).total;
-    if (fast_dims(d)) {   // the fast-path images share the buffers
+    if (fast_dims(d) || fast_fwd_attn_dims(d)) {   // the fast-path images share the buffers
         const int64_t ffi = make_fast_fwd_image(d.M, d.D).total, fbi = make_fast_bwd_image(d.M, d.D).total;
         if (ffi > fi) fi = ffi;
         if (fbi > bi) bi = fbi;
@@ -239,7 +239,9 @@ static ExchangeInputs resolve_inputs(const mmg_inputs* in) {
     return e;
 }
 
-struct Plan { int BT; int sender_smem; int fwd_smem_bytes; int bwd_smem_bytes; int fast; int attn_acc; };
+struct Plan { int BT; int sender_smem; int fwd_smem_bytes; int bwd_smem_bytes; int fast; int attn_acc;
+              int fast_fwd; int fast_fwd_smem_bytes; };   // fast_fwd: the register-resident forward kernel (always with `fast`;
+                                                          // alone for -desc_attn, whose backward runs on the generic kernel)
 
 static AttnArgs attn_args(const Dims& d, const ParamPtrs& P, const ExchangeInputs& in, const Plan& pl) {
     AttnArgs a;
@@ -295,8 +297,15 @@ static bool make_fast_plan(const Dims& d, Plan* pl) {
 }
 
 static int make_plan(const Dims& d, Plan* pl) {
-    pl->fast = 0; pl->attn_acc = 0;
-    if (make_fast_plan(d, pl)) return MMG_OK;
+    pl->fast = 0; pl->attn_acc = 0; pl->fast_fwd = 0; pl->fast_fwd_smem_bytes = 0;
+    if (make_fast_plan(d, pl)) { pl->fast_fwd = 1; pl->fast_fwd_smem_bytes = pl->fwd_smem_bytes; return MMG_OK; }
+    if (!g_force_generic && fast_fwd_attn_dims(d)) {
+        // -desc_attn at the fast shapes: forward on the register-resident kernel with the word tables in shared memory
+        const FastFwdImage fi = make_fast_fwd_image(d.M, d.D);
+        const int need = (fi.total - fi.b_ih + fast_fwd_state_floats(1, d.M, d.D, d.T) + fast_fwd_attn_floats(d.D, d.NW)) * 4;
+        const char* env = getenv("MMG_FAST_ATTN");            // =0: generic forward (tests)
+        if (need <= kMaxSmem && !(env && env[0] == '0')) { pl->fast_fwd = 1; pl->fast_fwd_smem_bytes = need; }
+    }
     const FwdImage fi = make_fwd_image(d);
     const BwdImage bi = make_bwd_image(d);
     pl->BT = choose_bt(d.B);
@@ -362,7 +371,9 @@ static int launch_fwd_fast_mode(const Dims& d, const WsPtrs& W, const ExchangeIn
     if (rc) return rc;
     const int n_conv = cdiv(d.B, BT);
     const int n_side = in.train ? cdiv(d.B, kTile) * cdiv(d.Hb, kTile) : 0;     // baseline pre-activation tiles
-    MMG_LAUNCH(kern, n_conv + n_side, kFastThreads, pl.fwd_smem_bytes, st, d, W, in, fa.b_img, 0, fa.bs_w1, fa.bs_b1, n_conv);
+    AttnArgs none;
+    memset(&none, 0, sizeof(none));
+    MMG_LAUNCH(kern, n_conv + n_side, kFastThreads, pl.fwd_smem_bytes, st, d, W, in, fa.b_img, 0, fa.bs_w1, fa.bs_b1, n_conv, none);
     return check_cuda("k_exchange_fwd_fast");
 }
 template <int BT, int M, bool SS>
@@ -381,6 +392,14 @@ static int launch_fwd_fast_bt(const Dims& d, const WsPtrs& W, const ExchangeInpu
         case 2: return launch_fwd_fast_one<2, M, SS>(d, W, in, fa, pl, st);
         default: return launch_fwd_fast_one<4, M, SS>(d, W, in, fa, pl, st);
     }
+}
+static int launch_fwd_fast_attn(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const FastFwdArgs& fa, const Plan& pl,
+                                cudaStream_t st, const AttnArgs& aa) {
+    auto kern = k_exchange_fwd_fast<1, 32, true, false, true>;
+    int rc = set_smem(kern, pl.fast_fwd_smem_bytes);
+    if (rc) return rc;
+    MMG_LAUNCH(kern, d.B, kFastThreads, pl.fast_fwd_smem_bytes, st, d, W, in, fa.b_img, 0, fa.bs_w1, fa.bs_b1, d.B, aa);
+    return check_cuda("k_exchange_fwd_fast<attn>");
 }
 static int launch_fwd_fast(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const FastFwdArgs& fa, const Plan& pl,
                            cudaStream_t st) {
@@ -637,12 +656,14 @@ static int exchange_forward_impl(const mmg_config* cfg, const float* d_params, c
     if (d.A && (!in->d_desc_set || !in->d_desc_set_lens)) return fail(MMG_ERR_INVALID, "desc_attn needs d_desc_set and d_desc_set_lens");
     const int n_cls = d.A ? cdiv(d.NW, kTile) * (2 * cdiv(d.Hr, kTile) + cdiv(d.A, kTile))      // word tables
                           : 2 * cdiv(d.D, kTile) * cdiv(d.Hr, kTile);                            // class tables
-    MMG_LAUNCH(k_pre, n_hx + n_cls + n_pack, kGemmThreads, 0, st, d, P, W, ei, n_hx, hx_kslice, pl.fast, n_cls);
+    // image formats: bit 0 = fast forward image, bit 1 = fast backward image
+    MMG_LAUNCH(k_pre, n_hx + n_cls + n_pack, kGemmThreads, 0, st, d, P, W, ei, n_hx, hx_kslice, pl.fast_fwd | (pl.fast << 1), n_cls);
     if ((rc = check_cuda("k_pre"))) return rc;
     // K_exchange_fwd
     const AttnArgs aa = attn_args(d, P, ei, pl);
     const float* b_img = P.p[MMG_P_SEN_IMG_B];
     if (pl.fast) rc = launch_fwd_fast(d, W, ei, FastFwdArgs{b_img, P.p[MMG_P_BS_L1_W], P.p[MMG_P_BS_L1_B]}, pl, st);
+    else if (pl.fast_fwd) rc = launch_fwd_fast_attn(d, W, ei, FastFwdArgs{b_img, P.p[MMG_P_BS_L1_W], P.p[MMG_P_BS_L1_B]}, pl, st, aa);
     else switch (pl.BT) {
         case 1: rc = launch_fwd<1>(d, W, ei, b_img, pl, st, aa); break;
         case 2: rc = launch_fwd<2>(d, W, ei, b_img, pl, st, aa); break;

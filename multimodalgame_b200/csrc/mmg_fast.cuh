@@ -48,7 +48,7 @@ MMG_DEVICE float fast_fwd_image_elem(const Dims& d, const FastFwdImage& im, cons
         return ldg(P.p[MMG_P_REC_RNN_WIH] + (size_t)(g * 64 + k) * M + part * (M / 4) + 4 * qq + c); }
     if (e < im.wgh) { const int q = e - im.whead; const int c = q & 3, f4 = q >> 2, half = f4 & 1, o = (f4 >> 1) & 127, qq = f4 >> 8;
         const int col = half * 32 + 4 * qq + c;
-        if (o < 64) return ldg(P.p[MMG_P_REC_Y1_W] + (size_t)o * (64 + d.WV) + col);
+        if (o < 64) return ldg(P.p[MMG_P_REC_Y1_W] + (size_t)o * (64 + d.WV) + d.y1_hcol + col);
         return ldg(P.p[MMG_P_REC_WH_W] + (size_t)(o - 64) * 64 + col); }
     if (e < im.ww) { const int q = e - im.wgh; const int c = q & 3, f4 = q >> 2, part = f4 & 3, k = (f4 >> 2) & 63, gq = f4 >> 8;
         const int g = gq >> 2, qq = gq & 3;
@@ -99,6 +99,18 @@ MMG_HOST_DEVICE int fast_fwd_state_floats(int BT, int M, int D, int T) {
            align4(2 * BT) + 8;
 }
 
+// -desc_attn on the fast forward kernel (one example per CTA, msg_dim 32, attention width 64): the two word tables read
+// every step by all threads (d_d(desc_set) and desc_set . w_d^T) live in shared memory with rows padded to 72 floats;
+// desc_set . y1^T is read from L2 once per step by the (class, column group) threads.
+enum { kFastAttnLd = 72, kFastAttnA = 64 };   // row stride 72: the per-unit reads of 4 consecutive words hit 32 distinct banks
+MMG_HOST_DEVICE int fast_fwd_attn_floats(int D, int NW) {
+    // tdd, twd (NW x 72) | ev, att (NWP) | dhv, vas, b1s (64) | y1e (D x 64) | seg (D+1), wcls (NW) as ints
+    return 2 * NW * kFastAttnLd + 2 * align4(NW) + 3 * 64 + D * 64 + align4(D + 1) + align4(NW);
+}
+MMG_HOST_DEVICE bool fast_fwd_attn_dims(const Dims& d) {
+    return d.Hi == kFastHi && d.Hr == kFastHr && d.M == 32 && d.T <= kFastMaxT && d.A == kFastAttnA && d.B <= 148;
+}
+
 MMG_DEVICE void fma4(const float4& w, const float4& x, float4& acc) {      // two packed fp32x2 FMAs (FFMA2)
     const float2 lo = ffma2(make_float2(w.x, w.y), make_float2(x.x, x.y), make_float2(acc.x, acc.y));
     const float2 hi = ffma2(make_float2(w.z, w.w), make_float2(x.z, x.w), make_float2(acc.z, acc.w));
@@ -116,10 +128,11 @@ MMG_DEVICE float4 lds4(const float* p) { return *reinterpret_cast<const float4*>
 
 // kPerf: the training configuration bench.py measures (binary messages, on-device draws, no corruption mask, batch a
 // multiple of BT) with every mode flag a compile-time constant: no mode branches and no row guards in the step loop.
-template <int BT, int M, bool kRegSend, bool kPerf>
+template <int BT, int M, bool kRegSend, bool kPerf, bool kAttn = false>
 MMG_GLOBAL void __launch_bounds__(kFastThreads, 1)
 k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int row_offset, const float* bs_w1,
-                    const float* bs_b1, int n_conv_ctas) {
+                    const float* bs_b1, int n_conv_ctas, AttnArgs aa) {
+    static_assert(!kAttn || (BT == 1 && M == 32 && kRegSend && !kPerf), "attention: one example per CTA, msg_dim 32");
     constexpr int HI = kFastHi, HR = kFastHr, NT = kFastThreads, NW = NT / 32;
     constexpr int M4 = M / 4, MQ = M / 16, LPO = NT / M, KPT = HR / LPO, KB = HI / LPO, UST = 2 * M + 4;
     MMG_DYN_SMEM(smem_raw);
@@ -174,6 +187,20 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
     float* sprod = sm + o; o += BT;
     float* smask = sm + o; o += BT;
     o = align4(o);
+    // -desc_attn state (kAttn)
+    constexpr int LDT = kFastAttnLd;
+    const int NWD = kAttn ? d.NW : 0, NWP = align4(NWD);
+    float* tdd = sm + o;   o += NWD * LDT;          // d_d(desc_set), rows padded
+    float* twd = sm + o;   o += NWD * LDT;          // desc_set . w_d^T
+    float* ev = sm + o;    o += NWP;                // scores
+    float* att = sm + o;   o += NWP;                // attention weights
+    float* dhv = sm + o;   o += kAttn ? 64 : 0;     // d_h(h')
+    float* vas = sm + o;   o += kAttn ? 64 : 0;     // d_attn.weight
+    float* b1s = sm + o;   o += kAttn ? 64 : 0;     // y1.bias
+    float* y1e = sm + o;   o += kAttn ? D * 64 : 0; // attended description half of y1, [class][64] like the y1d table
+    int* segs = reinterpret_cast<int*>(sm + o); o += kAttn ? align4(D + 1) : 0;
+    int* wcl = reinterpret_cast<int*>(sm + o);  o += NWP;
+    o = align4(o);
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm + o);
 #if defined(MMG_PHASE_TIMING) && !defined(MMG_CPU_EMU)
     unsigned* stamps = reinterpret_cast<unsigned*>(sm + o + 4);     // (T, 8 phases, 8 warps), debug build only
@@ -203,7 +230,7 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
     const float4* whd_t = reinterpret_cast<const float4*>(gimg + im.whead) + oh * 2 + hh;     // + q * 256
     const float4* wgh_t = reinterpret_cast<const float4*>(gimg + im.wgh) + k4t * 4 + p4;      // + (g*4+q) * 256
     const float4* ww_t = reinterpret_cast<const float4*>(gimg + im.ww) + jo * LPO + po;       // + q * M * LPO
-    const float4* y1d_t = reinterpret_cast<const float4*>(img + im.y1d) + sub;                // + cls*16 (+8)
+    const float4* y1d_t = reinterpret_cast<const float4*>(kAttn ? y1e : img + im.y1d) + sub;  // + cls*16 (+8)
     const float* wdd_t = img + im.wdd + k4t * 4 + p4;                                          // + (d/4) * 256
 
     // ---- prologue ----------------------------------------------------------------------------------------------
@@ -227,6 +254,23 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
     for (int i = 0; i < 12; ++i) rg[i] = ldg4(wgh_t + i * NT);
 #pragma unroll
     for (int q = 0; q < KPT / 4; ++q) rw[q] = ldg4(ww_t + q * M * LPO);
+    float4 rdh[kAttn ? 8 : 1];                    // d_h.weight (64, 64): threads < 128 = (row, K-half)
+    float bdh_t = 0.f;
+    if constexpr (kAttn) {
+        if (tid < 128) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) rdh[q] = ldg4(reinterpret_cast<const float4*>(aa.dh_w + (size_t)oh * 64 + hh * 32) + q);
+            bdh_t = ldg(aa.dh_b + oh);
+        }
+        for (int idx = tid; idx < NWD * 16; idx += NT) {
+            const int n = idx >> 4, c = idx & 15;
+            *reinterpret_cast<float4*>(tdd + n * LDT + 4 * c) = ldg4(reinterpret_cast<const float4*>(W.wtab_dd + (size_t)n * 64) + c);
+            *reinterpret_cast<float4*>(twd + n * LDT + 4 * c) = ldg4(reinterpret_cast<const float4*>(W.wtab_wd + (size_t)n * 64) + c);
+        }
+        if (tid < 64) { vas[tid] = ldg(aa.va + tid); b1s[tid] = ldg(aa.b1 + tid); }
+        for (int idx = tid; idx <= D; idx += NT) segs[idx] = W.seg[idx];
+        for (int idx = tid; idx < NWD; idx += NT) wcl[idx] = W.wcls[idx];
+    }
     // h_x rows of this CTA: split-K partials of K_pre summed in a fixed order + bias (model.py:195)
 #pragma unroll
     for (int bt = 0; bt < BT; ++bt) {
@@ -471,10 +515,86 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
                     }
                 }
             }
+            if constexpr (kAttn) {       // d_h(h') (model.py:359): 64 more rows, threads < 128 (whole warps)
+                if (tid < 128) {
+                    float4 a4 = zero4();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) fma4(rdh[q], lds4(hv + hh * 32 + 4 * q), a4);
+                    const float v = group_sum<2>(hsum4(a4)) + bdh_t;
+                    if (hh == 0) {
+                        dhv[oh] = v;
+                        if (train && MMG_SAVE_OK(b0)) W.dh_s[((size_t)t * B + b0) * 64 + oh] = v;
+                    }
+                }
+            }
             gh_phase();          // W_hh . h' for the NEXT step: independent of the head rows, interleaves with them
         }
         MMG_STAMP(4);
         MMG_SYNCTHREADS();
+        if constexpr (kAttn) {
+            // ---- PA: description attention (model.py:344-410) from the shared-memory word tables ------------------------
+            {   // scores: 4 lanes per word (16 units each), 64 words per pass
+                const float4 va0 = lds4(vas + 4 * p4), va1 = lds4(vas + 16 + 4 * p4), va2 = lds4(vas + 32 + 4 * p4), va3 = lds4(vas + 48 + 4 * p4);
+                const float4 h0 = lds4(dhv + 4 * p4), h1 = lds4(dhv + 16 + 4 * p4), h2 = lds4(dhv + 32 + 4 * p4), h3 = lds4(dhv + 48 + 4 * p4);
+                const float ba = ldg(aa.ba);
+                for (int base = 0; base < NWD; base += NT / 4) {
+                    const int n = base + k4t;
+                    const bool ok = n < NWD;
+                    const float* row = tdd + (ok ? n : 0) * LDT + 4 * p4;
+                    const float4 w0 = lds4(row), w1 = lds4(row + 16), w2 = lds4(row + 32), w3 = lds4(row + 48);
+                    float s0 = va0.x * fast_tanh(w0.x + h0.x), s1 = va0.y * fast_tanh(w0.y + h0.y), s2 = va0.z * fast_tanh(w0.z + h0.z), s3 = va0.w * fast_tanh(w0.w + h0.w);
+                    s0 = fmaf(va1.x, fast_tanh(w1.x + h1.x), s0); s1 = fmaf(va1.y, fast_tanh(w1.y + h1.y), s1); s2 = fmaf(va1.z, fast_tanh(w1.z + h1.z), s2); s3 = fmaf(va1.w, fast_tanh(w1.w + h1.w), s3);
+                    s0 = fmaf(va2.x, fast_tanh(w2.x + h2.x), s0); s1 = fmaf(va2.y, fast_tanh(w2.y + h2.y), s1); s2 = fmaf(va2.z, fast_tanh(w2.z + h2.z), s2); s3 = fmaf(va2.w, fast_tanh(w2.w + h2.w), s3);
+                    s0 = fmaf(va3.x, fast_tanh(w3.x + h3.x), s0); s1 = fmaf(va3.y, fast_tanh(w3.y + h3.y), s1); s2 = fmaf(va3.z, fast_tanh(w3.z + h3.z), s2); s3 = fmaf(va3.w, fast_tanh(w3.w + h3.w), s3);
+                    const float sc = group_sum<4>((s0 + s1) + (s2 + s3)) + ba;
+                    if (ok && p4 == 0) ev[n] = sc;
+                }
+            }
+            MMG_SYNCTHREADS();
+            {   // softmax inside each class's word segment: 8 lanes per class
+                const int l8 = tid & 7;
+                for (int base = 0; base < D; base += NT / 8) {
+                    const int dd = base + (tid >> 3);
+                    const bool ok = dd < D;
+                    const int s0 = ok ? segs[dd] : 0, s1 = ok ? segs[dd + 1] : 0;
+                    float mx = -INFINITY;
+                    for (int n = s0 + l8; n < s1; n += 8) mx = fmaxf(mx, ev[n]);
+                    mx = group_max<8>(mx);
+                    float se = 0.f;
+                    for (int n = s0 + l8; n < s1; n += 8) se += fast_exp(ev[n] - mx);
+                    se = group_sum<8>(se);
+                    const float inv = fast_rcp(se);
+                    for (int n = s0 + l8; n < s1; n += 8) {
+                        const float a = fast_exp(ev[n] - mx) * inv;
+                        att[n] = a;
+                        if (train && MMG_SAVE_OK(b0)) W.attn[((size_t)t * B + b0) * NWD + n] = a;
+                    }
+                }
+            }
+            MMG_SYNCTHREADS();
+            {   // attended description half of y1: thread = (class, float4 column group), two items in flight, table in L2
+                const float4* tab = reinterpret_cast<const float4*>(W.wtab_y1);
+                for (int base = 0; base < D * 16; base += 2 * NT) {
+                    const int ia = base + tid, ib = ia + NT;
+                    const bool oka = ia < D * 16, okb = ib < D * 16;
+                    const int da = oka ? ia >> 4 : 0, ka = ia & 15, db = okb ? ib >> 4 : 0, kb = ib & 15;
+                    const int a0 = segs[da], a1 = segs[da + 1], c0 = segs[db], c1 = segs[db + 1];
+                    const int len = max(a1 - a0, c1 - c0);
+                    float4 sa = lds4(b1s + 4 * ka), sb = lds4(b1s + 4 * kb);
+#pragma unroll 4
+                    for (int i = 0; i < len; ++i) {
+                        const int na = min(a0 + i, a1 - 1), nb = min(c0 + i, c1 - 1);
+                        const float4 wa = ldg4(tab + (size_t)na * 16 + ka), wb = ldg4(tab + (size_t)nb * 16 + kb);
+                        const float fa = a0 + i < a1 ? att[na] : 0.f, fb = c0 + i < c1 ? att[nb] : 0.f;
+                        sa.x = fmaf(fa, wa.x, sa.x); sa.y = fmaf(fa, wa.y, sa.y); sa.z = fmaf(fa, wa.z, sa.z); sa.w = fmaf(fa, wa.w, sa.w);
+                        sb.x = fmaf(fb, wb.x, sb.x); sb.y = fmaf(fb, wb.y, sb.y); sb.z = fmaf(fb, wb.z, sb.z); sb.w = fmaf(fb, wb.w, sb.w);
+                    }
+                    if (oka) *reinterpret_cast<float4*>(y1e + da * 64 + 4 * ka) = sa;
+                    if (okb) *reinterpret_cast<float4*>(y1e + db * 64 + 4 * kb) = sb;
+                }
+            }
+            MMG_SYNCTHREADS();
+        }
         // ---- P5: class scores y[d] = y2(relu(y1h + y1d[d])) (model.py:432-433), 8 lanes per class; the next step's
         //      W_hh . h' rides along (independent chain) ---------------------------------------------------------------
         {
@@ -542,8 +662,31 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
                 }
                 // STOP head: every warp evaluates the 64-wide dot product (no divergent block), one lane commits
                 float sv = fmaf(ws_a, hv[bt * HR + lane], ws_b * hv[bt * HR + lane + 32]);
-                const float acc = group_sum<4>(acc0 + acc1);
                 const float se = group_sum<4>(se0 + se1);
+                if constexpr (kAttn) {
+                    // confidence-weighted ATTENDED description through w_d (model.py:441-452): sum over words of
+                    // q_class(n) a_n (desc_set . w_d^T)[n].  The word weights are formed once per word (into the score
+                    // buffer, no longer needed), then thread (unit k4t, quarter p4) takes words p4, p4 + 4, ...
+                    const float inv_se = fast_rcp(se);
+                    for (int n = tid; n < NWD; n += NT) {
+                        const float qa = fast_exp(yv[bt * DP + wcl[n]] - mx) * att[n];
+                        ev[n] = qa;
+                        if (train && MMG_SAVE_OK(b)) W.qa[((size_t)t * B + b) * NWD + n] = qa * inv_se;
+                    }
+                    MMG_SYNCTHREADS();
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                    const float* tw = twd + k4t;
+                    int n = p4;
+                    for (; n + 12 < NWD; n += 16) {
+                        a0 = fmaf(ev[n], tw[n * LDT], a0);
+                        a1 = fmaf(ev[n + 4], tw[(n + 4) * LDT], a1);
+                        a2 = fmaf(ev[n + 8], tw[(n + 8) * LDT], a2);
+                        a3 = fmaf(ev[n + 12], tw[(n + 12) * LDT], a3);
+                    }
+                    for (; n < NWD; n += 4) a0 = fmaf(ev[n], tw[n * LDT], a0);
+                    acc0 = (a0 + a1) + (a2 + a3); acc1 = 0.f;
+                }
+                const float acc = group_sum<4>(acc0 + acc1);
                 sv = warp_sum(sv);
                 const float inv = fast_rcp(se);
                 if (train && MMG_SAVE_OK(b))

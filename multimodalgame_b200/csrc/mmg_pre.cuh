@@ -187,19 +187,20 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
         }
         W.seg[d.D] = start;
     }
-    if (fast) {
+    const bool ff = (fast & 1) != 0, fb = (fast & 2) != 0;      // forward / backward image in the fast-path format
+    if (ff) {
         for (int e = gtid; e < ffi.y1d; e += gthreads) {
             if (e >= ffi.hw0 && e < ffi.b_b) continue;
             W.fwd_image[e] = fast_fwd_image_elem(d, ffi, P, e);
         }
-        for (int e = gtid; e < fbi.y1d; e += gthreads) W.bwd_image[e] = fast_bwd_image_elem(d, fbi, P, e);
     } else {
         for (int e = gtid; e < fim.y1d; e += gthreads) {
             if (e >= fim.hw0 && e < fim.b_b) continue;
             W.fwd_image[e] = fwd_image_elem(d, fim, P, e);
         }
-        for (int e = gtid; e < bim.y1d; e += gthreads) W.bwd_image[e] = bwd_image_elem(d, bim, P, e);
     }
+    if (fb) for (int e = gtid; e < fbi.y1d; e += gthreads) W.bwd_image[e] = fast_bwd_image_elem(d, fbi, P, e);
+    else    for (int e = gtid; e < bim.y1d; e += gthreads) W.bwd_image[e] = bwd_image_elem(d, bim, P, e);
     // dot role: one warp per output, lanes along the reduction
     const int lane = tid & 31, gwarp = gtid >> 5, nwarps = gthreads >> 5;
     const int n_y1d = d.D * d.Hr;
@@ -212,7 +213,7 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
             for (int j = lane; j < d.M; j += 32)
                 s = fmaf(sigmoidf_(ldg(P.p[MMG_P_SEN_CODE_BIAS] + j)), ldg(P.p[MMG_P_SEN_CODE_W] + (size_t)n * d.M + j), s);
             s = warp_sum(s);
-            if (lane == 0) W.fwd_image[(fast ? ffi.hw0 : fim.hw0) + n] = s + ldg(P.p[MMG_P_SEN_CODE_B] + n);
+            if (lane == 0) W.fwd_image[(ff ? ffi.hw0 : fim.hw0) + n] = s + ldg(P.p[MMG_P_SEN_CODE_B] + n);
         } else {                               // code_in[0][b][j] = sigmoid(code_bias[j]) for every row b
             const int j = o - 2 * n_y1d - d.Hi;
             const float c0 = sigmoidf_(ldg(P.p[MMG_P_SEN_CODE_BIAS] + j));
@@ -220,20 +221,21 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
         }
     }
     // pad tails of dot sections (keep the images fully defined for the bulk copies)
-    if (fast) {
-        const int dpad = ((d.D + 3) / 4) * 4;
+    const int dpad = ((d.D + 3) / 4) * 4;
+    if (ff || fb) {
         for (int e = gtid; e < (dpad - d.D) * d.Hr; e += gthreads) {
             const int dd = d.D + e / d.Hr, k = e % d.Hr;
-            W.fwd_image[ffi.wdd + ((dd >> 2) * d.Hr + k) * 4 + (dd & 3)] = 0.f;
-            W.bwd_image[fbi.y1d + ((dd >> 2) * d.Hr + k) * 4 + (dd & 3)] = 0.f;
+            if (ff) W.fwd_image[ffi.wdd + ((dd >> 2) * d.Hr + k) * 4 + (dd & 3)] = 0.f;
+            if (fb) W.bwd_image[fbi.y1d + ((dd >> 2) * d.Hr + k) * 4 + (dd & 3)] = 0.f;
         }
-        return;
     }
-    for (int e = gtid; e < fim.total; e += gthreads) {
-        if ((e >= fim.hw0 + d.Hi && e < fim.b_b) || (e >= fim.y1d + n_y1d_w && e < fim.wdd) || (e >= fim.wdd + n_y1d_w))
-            W.fwd_image[e] = 0.f;
+    if (!ff) {
+        for (int e = gtid; e < fim.total; e += gthreads) {
+            if ((e >= fim.hw0 + d.Hi && e < fim.b_b) || (e >= fim.y1d + n_y1d_w && e < fim.wdd) || (e >= fim.wdd + n_y1d_w))
+                W.fwd_image[e] = 0.f;
+        }
     }
-    for (int e = gtid + bim.y1d + n_y1d_w; e < bim.total; e += gthreads) W.bwd_image[e] = 0.f;
+    if (!fb) for (int e = gtid + bim.y1d + n_y1d_w; e < bim.total; e += gthreads) W.bwd_image[e] = 0.f;
 }
 
 }  // namespace mmg
