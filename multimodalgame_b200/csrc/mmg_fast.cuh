@@ -105,7 +105,7 @@ MMG_HOST_DEVICE int fast_fwd_state_floats(int BT, int M, int D, int T) {
 enum { kFastAttnLd = 72, kFastAttnA = 64 };   // row stride 72: the per-unit reads of 4 consecutive words hit 32 distinct banks
 MMG_HOST_DEVICE int fast_fwd_attn_floats(int D, int NW) {
     // tdd, twd (NW x 72) | ev, att (NWP) | dhv, vas, b1s (64) | y1e (D x 64) | seg (D+1), wcls (NW) as ints
-    return 2 * NW * kFastAttnLd + 2 * align4(NW) + 3 * 64 + D * 64 + align4(D + 1) + align4(NW);
+    return 2 * NW * kFastAttnLd + 2 * align4(NW) + 3 * 64 + D * 64 + 64 * 64 + align4(D + 1) + align4(NW);
 }
 MMG_HOST_DEVICE bool fast_fwd_attn_dims(const Dims& d) {
     return d.Hi == kFastHi && d.Hr == kFastHr && d.M == 32 && d.T <= kFastMaxT && d.A == kFastAttnA && d.B <= 148;
@@ -198,6 +198,7 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
     float* vas = sm + o;   o += kAttn ? 64 : 0;     // d_attn.weight
     float* b1s = sm + o;   o += kAttn ? 64 : 0;     // y1.bias
     float* y1e = sm + o;   o += kAttn ? D * 64 : 0; // attended description half of y1, [class][64] like the y1d table
+    float* wdh = sm + o;   o += kAttn ? 64 * 64 : 0; // d_h.weight
     int* segs = reinterpret_cast<int*>(sm + o); o += kAttn ? align4(D + 1) : 0;
     int* wcl = reinterpret_cast<int*>(sm + o);  o += NWP;
     o = align4(o);
@@ -254,13 +255,14 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
     for (int i = 0; i < 12; ++i) rg[i] = ldg4(wgh_t + i * NT);
 #pragma unroll
     for (int q = 0; q < KPT / 4; ++q) rw[q] = ldg4(ww_t + q * M * LPO);
-    float4 rdh[kAttn ? 8 : 1];                    // d_h.weight (64, 64): threads < 128 = (row, K-half)
     float bdh_t = 0.f;
     if constexpr (kAttn) {
-        if (tid < 128) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) rdh[q] = ldg4(reinterpret_cast<const float4*>(aa.dh_w + (size_t)oh * 64 + hh * 32) + q);
-            bdh_t = ldg(aa.dh_b + oh);
+        // d_h.weight (64, 64) in shared memory, stored [q][row][half][4] so that thread (row, K-half) of P4 reads float4 q at
+        // a unit-stride address (the register file is full: GRU, heads and sender already live there)
+        if (tid < 128) bdh_t = ldg(aa.dh_b + oh);
+        for (int idx = tid; idx < 64 * 16; idx += NT) {
+            const int row = idx >> 4, c4 = idx & 15, half = c4 >> 3, q = c4 & 7;
+            *reinterpret_cast<float4*>(wdh + ((q * 64 + row) * 2 + half) * 4) = ldg4(reinterpret_cast<const float4*>(aa.dh_w + (size_t)row * 64) + c4);
         }
         for (int idx = tid; idx < NWD * 16; idx += NT) {
             const int n = idx >> 4, c = idx & 15;
@@ -519,7 +521,7 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
                 if (tid < 128) {
                     float4 a4 = zero4();
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) fma4(rdh[q], lds4(hv + hh * 32 + 4 * q), a4);
+                    for (int q = 0; q < 8; ++q) fma4(lds4(wdh + (q * 128 + tid) * 4), lds4(hv + hh * 32 + 4 * q), a4);
                     const float v = group_sum<2>(hsum4(a4)) + bdh_t;
                     if (hh == 0) {
                         dhv[oh] = v;
@@ -581,7 +583,7 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
                     const int a0 = segs[da], a1 = segs[da + 1], c0 = segs[db], c1 = segs[db + 1];
                     const int len = max(a1 - a0, c1 - c0);
                     float4 sa = lds4(b1s + 4 * ka), sb = lds4(b1s + 4 * kb);
-#pragma unroll 4
+#pragma unroll 8
                     for (int i = 0; i < len; ++i) {
                         const int na = min(a0 + i, a1 - 1), nb = min(c0 + i, c1 - 1);
                         const float4 wa = ldg4(tab + (size_t)na * 16 + ka), wb = ldg4(tab + (size_t)nb * 16 + kb);
