@@ -395,10 +395,19 @@ static int launch_fwd_fast_bt(const Dims& d, const WsPtrs& W, const ExchangeInpu
 }
 static int launch_fwd_fast_attn(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const FastFwdArgs& fa, const Plan& pl,
                                 cudaStream_t st, const AttnArgs& aa) {
-    auto kern = k_exchange_fwd_fast<1, 32, true, false, true>;
-    int rc = set_smem(kern, pl.fast_fwd_smem_bytes);
-    if (rc) return rc;
-    MMG_LAUNCH(kern, d.B, kFastThreads, pl.fast_fwd_smem_bytes, st, d, W, in, fa.b_img, 0, fa.bs_w1, fa.bs_b1, d.B, aa);
+    // kPerf: the training configuration bench.py measures, every mode flag a compile-time constant
+    const bool perf = in.train && d.use_binary && in.u_sen == nullptr && in.corrupt_mask == nullptr && !d.ignore_receiver &&
+                      d.flip_sen < 0.f && d.flip_rec < 0.f && !d.mix_prod && !d.ignore_code;
+    int rc;
+    if (perf) {
+        auto kern = k_exchange_fwd_fast<1, 32, true, true, true>;
+        if ((rc = set_smem(kern, pl.fast_fwd_smem_bytes))) return rc;
+        MMG_LAUNCH(kern, d.B, kFastThreads, pl.fast_fwd_smem_bytes, st, d, W, in, fa.b_img, 0, fa.bs_w1, fa.bs_b1, d.B, aa);
+    } else {
+        auto kern = k_exchange_fwd_fast<1, 32, true, false, true>;
+        if ((rc = set_smem(kern, pl.fast_fwd_smem_bytes))) return rc;
+        MMG_LAUNCH(kern, d.B, kFastThreads, pl.fast_fwd_smem_bytes, st, d, W, in, fa.b_img, 0, fa.bs_w1, fa.bs_b1, d.B, aa);
+    }
     return check_cuda("k_exchange_fwd_fast<attn>");
 }
 static int launch_fwd_fast(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const FastFwdArgs& fa, const Plan& pl,

@@ -132,7 +132,7 @@ template <int BT, int M, bool kRegSend, bool kPerf, bool kAttn = false>
 MMG_GLOBAL void __launch_bounds__(kFastThreads, 1)
 k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int row_offset, const float* bs_w1,
                     const float* bs_b1, int n_conv_ctas, AttnArgs aa) {
-    static_assert(!kAttn || (BT == 1 && M == 32 && kRegSend && !kPerf), "attention: one example per CTA, msg_dim 32");
+    static_assert(!kAttn || (BT == 1 && M == 32 && kRegSend), "attention: one example per CTA, msg_dim 32");
     constexpr int HI = kFastHi, HR = kFastHr, NT = kFastThreads, NW = NT / 32;
     constexpr int M4 = M / 4, MQ = M / 16, LPO = NT / M, KPT = HR / LPO, KB = HI / LPO, UST = 2 * M + 4;
     MMG_DYN_SMEM(smem_raw);
@@ -266,7 +266,11 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
         }
         for (int idx = tid; idx < NWD * 16; idx += NT) {
             const int n = idx >> 4, c = idx & 15;
-            *reinterpret_cast<float4*>(tdd + n * LDT + 4 * c) = ldg4(reinterpret_cast<const float4*>(W.wtab_dd + (size_t)n * 64) + c);
+            // tanh(w + h) = 1 - 2 / (e^{2w} e^{2h} + 1): the word factor e^{2w} is loop invariant, so the table holds it and a
+            // score element costs one MUFU (the reciprocal) instead of two (overflow saturates to tanh = 1, as it should)
+            float4 wv = ldg4(reinterpret_cast<const float4*>(W.wtab_dd + (size_t)n * 64) + c);
+            wv.x = fast_exp(2.f * wv.x); wv.y = fast_exp(2.f * wv.y); wv.z = fast_exp(2.f * wv.z); wv.w = fast_exp(2.f * wv.w);
+            *reinterpret_cast<float4*>(tdd + n * LDT + 4 * c) = wv;
             *reinterpret_cast<float4*>(twd + n * LDT + 4 * c) = ldg4(reinterpret_cast<const float4*>(W.wtab_wd + (size_t)n * 64) + c);
         }
         if (tid < 64) { vas[tid] = ldg(aa.va + tid); b1s[tid] = ldg(aa.b1 + tid); }
@@ -537,17 +541,20 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
             // ---- PA: description attention (model.py:344-410) from the shared-memory word tables ------------------------
             {   // scores: 4 lanes per word (16 units each), 64 words per pass
                 const float4 va0 = lds4(vas + 4 * p4), va1 = lds4(vas + 16 + 4 * p4), va2 = lds4(vas + 32 + 4 * p4), va3 = lds4(vas + 48 + 4 * p4);
-                const float4 h0 = lds4(dhv + 4 * p4), h1 = lds4(dhv + 16 + 4 * p4), h2 = lds4(dhv + 32 + 4 * p4), h3 = lds4(dhv + 48 + 4 * p4);
+                float4 h0 = lds4(dhv + 4 * p4), h1 = lds4(dhv + 16 + 4 * p4), h2 = lds4(dhv + 32 + 4 * p4), h3 = lds4(dhv + 48 + 4 * p4);
+                auto e2 = [](float4& v) { v.x = fast_exp(2.f * v.x); v.y = fast_exp(2.f * v.y); v.z = fast_exp(2.f * v.z); v.w = fast_exp(2.f * v.w); };
+                e2(h0); e2(h1); e2(h2); e2(h3);                     // e^{2 d_h(h')}: 16 exponentials per thread and step
+                auto th = [](float ew, float eh) { return 1.0f - fast_rcp(fmaf(ew, eh, 1.0f)) * 2.0f; };
                 const float ba = ldg(aa.ba);
                 for (int base = 0; base < NWD; base += NT / 4) {
                     const int n = base + k4t;
                     const bool ok = n < NWD;
                     const float* row = tdd + (ok ? n : 0) * LDT + 4 * p4;
                     const float4 w0 = lds4(row), w1 = lds4(row + 16), w2 = lds4(row + 32), w3 = lds4(row + 48);
-                    float s0 = va0.x * fast_tanh(w0.x + h0.x), s1 = va0.y * fast_tanh(w0.y + h0.y), s2 = va0.z * fast_tanh(w0.z + h0.z), s3 = va0.w * fast_tanh(w0.w + h0.w);
-                    s0 = fmaf(va1.x, fast_tanh(w1.x + h1.x), s0); s1 = fmaf(va1.y, fast_tanh(w1.y + h1.y), s1); s2 = fmaf(va1.z, fast_tanh(w1.z + h1.z), s2); s3 = fmaf(va1.w, fast_tanh(w1.w + h1.w), s3);
-                    s0 = fmaf(va2.x, fast_tanh(w2.x + h2.x), s0); s1 = fmaf(va2.y, fast_tanh(w2.y + h2.y), s1); s2 = fmaf(va2.z, fast_tanh(w2.z + h2.z), s2); s3 = fmaf(va2.w, fast_tanh(w2.w + h2.w), s3);
-                    s0 = fmaf(va3.x, fast_tanh(w3.x + h3.x), s0); s1 = fmaf(va3.y, fast_tanh(w3.y + h3.y), s1); s2 = fmaf(va3.z, fast_tanh(w3.z + h3.z), s2); s3 = fmaf(va3.w, fast_tanh(w3.w + h3.w), s3);
+                    float s0 = va0.x * th(w0.x, h0.x), s1 = va0.y * th(w0.y, h0.y), s2 = va0.z * th(w0.z, h0.z), s3 = va0.w * th(w0.w, h0.w);
+                    s0 = fmaf(va1.x, th(w1.x, h1.x), s0); s1 = fmaf(va1.y, th(w1.y, h1.y), s1); s2 = fmaf(va1.z, th(w1.z, h1.z), s2); s3 = fmaf(va1.w, th(w1.w, h1.w), s3);
+                    s0 = fmaf(va2.x, th(w2.x, h2.x), s0); s1 = fmaf(va2.y, th(w2.y, h2.y), s1); s2 = fmaf(va2.z, th(w2.z, h2.z), s2); s3 = fmaf(va2.w, th(w2.w, h2.w), s3);
+                    s0 = fmaf(va3.x, th(w3.x, h3.x), s0); s1 = fmaf(va3.y, th(w3.y, h3.y), s1); s2 = fmaf(va3.z, th(w3.z, h3.z), s2); s3 = fmaf(va3.w, th(w3.w, h3.w), s3);
                     const float sc = group_sum<4>((s0 + s1) + (s2 + s3)) + ba;
                     if (ok && p4 == 0) ev[n] = sc;
                 }
