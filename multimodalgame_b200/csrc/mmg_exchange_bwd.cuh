@@ -347,7 +347,7 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
                             float4* slot = reinterpret_cast<float4*>(dslab + (size_t)n * AP) + i4;
                             float4 acc = init ? make_float4(0.f, 0.f, 0.f, 0.f) : *slot;
                             const float de = dav[bt * NWP + n];
-                            const float tx = fast_tanh(w.x + dha.x), ty = fast_tanh(w.y + dha.y), tz = fast_tanh(w.z + dha.z), tw = fast_tanh(w.w + dha.w);
+                            const float tx = attn_tanh(w.x, dha.x), ty = attn_tanh(w.y, dha.y), tz = attn_tanh(w.z, dha.z), tw = attn_tanh(w.w, dha.w);
                             const float ux = de * va.x * (1.f - tx * tx), uy = de * va.y * (1.f - ty * ty),
                                         uz = de * va.z * (1.f - tz * tz), uw = de * va.w * (1.f - tw * tw);
                             accd.x += ux; accd.y += uy; accd.z += uz; accd.w += uw;

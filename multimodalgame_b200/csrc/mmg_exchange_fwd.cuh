@@ -309,8 +309,9 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
                 if (b < d.B) W.y1h[row * d.Hr + oo] = v;
             } else if (oo > 2 * d.Hr) {        // d_h(h') of the description attention (model.py:359), rides in the stacked heads
                 const int a = oo - 2 * d.Hr - 1;
-                dhv[bt * AP + a] = v;
-                if (train && b < d.B) W.dh_s[row * d.A + a] = v;
+                const float eh = attn_e2(v);            // kept as e^{2 d_h(h')}, see attn_tanh
+                dhv[bt * AP + a] = eh;
+                if (train && b < d.B) W.dh_s[row * d.A + a] = eh;
             } else if (oo == 2 * d.Hr) {
                 const float sp = sigmoidf_(v);
                 float sbit;
@@ -353,10 +354,10 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
 #pragma unroll 4
                 for (int i = q4; i < A4; i += 4) {
                     const float4 wa = ldg4(rowa + i), wb = ldg4(rowb + i), ha = dha[i], hb = dhb[i], v = va4[i];
-                    sa = fmaf(v.x, fast_tanh(wa.x + ha.x), sa); sa = fmaf(v.y, fast_tanh(wa.y + ha.y), sa);
-                    sa = fmaf(v.z, fast_tanh(wa.z + ha.z), sa); sa = fmaf(v.w, fast_tanh(wa.w + ha.w), sa);
-                    sb = fmaf(v.x, fast_tanh(wb.x + hb.x), sb); sb = fmaf(v.y, fast_tanh(wb.y + hb.y), sb);
-                    sb = fmaf(v.z, fast_tanh(wb.z + hb.z), sb); sb = fmaf(v.w, fast_tanh(wb.w + hb.w), sb);
+                    sa = fmaf(v.x, attn_tanh(wa.x, ha.x), sa); sa = fmaf(v.y, attn_tanh(wa.y, ha.y), sa);
+                    sa = fmaf(v.z, attn_tanh(wa.z, ha.z), sa); sa = fmaf(v.w, attn_tanh(wa.w, ha.w), sa);
+                    sb = fmaf(v.x, attn_tanh(wb.x, hb.x), sb); sb = fmaf(v.y, attn_tanh(wb.y, hb.y), sb);
+                    sb = fmaf(v.z, attn_tanh(wb.z, hb.z), sb); sb = fmaf(v.w, attn_tanh(wb.w, hb.w), sb);
                 }
                 sa = group_sum<4>(sa); sb = group_sum<4>(sb);
                 if (q4 == 0) {

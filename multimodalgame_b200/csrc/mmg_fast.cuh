@@ -266,11 +266,8 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
         }
         for (int idx = tid; idx < NWD * 16; idx += NT) {
             const int n = idx >> 4, c = idx & 15;
-            // tanh(w + h) = 1 - 2 / (e^{2w} e^{2h} + 1): the word factor e^{2w} is loop invariant, so the table holds it and a
-            // score element costs one MUFU (the reciprocal) instead of two (overflow saturates to tanh = 1, as it should)
-            float4 wv = ldg4(reinterpret_cast<const float4*>(W.wtab_dd + (size_t)n * 64) + c);
-            wv.x = fast_exp(2.f * wv.x); wv.y = fast_exp(2.f * wv.y); wv.z = fast_exp(2.f * wv.z); wv.w = fast_exp(2.f * wv.w);
-            *reinterpret_cast<float4*>(tdd + n * LDT + 4 * c) = wv;
+            // the table holds the word factor e^{2 d_d(word)} of tanh(w + h) = 1 - 2 / (e^{2w} e^{2h} + 1) (K_pre, attn_tanh)
+            *reinterpret_cast<float4*>(tdd + n * LDT + 4 * c) = ldg4(reinterpret_cast<const float4*>(W.wtab_dd + (size_t)n * 64) + c);
             *reinterpret_cast<float4*>(twd + n * LDT + 4 * c) = ldg4(reinterpret_cast<const float4*>(W.wtab_wd + (size_t)n * 64) + c);
         }
         if (tid < 64) { vas[tid] = ldg(aa.va + tid); b1s[tid] = ldg(aa.b1 + tid); }
@@ -528,8 +525,9 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
                     for (int q = 0; q < 8; ++q) fma4(lds4(wdh + (q * 128 + tid) * 4), lds4(hv + hh * 32 + 4 * q), a4);
                     const float v = group_sum<2>(hsum4(a4)) + bdh_t;
                     if (hh == 0) {
-                        dhv[oh] = v;
-                        if (train && MMG_SAVE_OK(b0)) W.dh_s[((size_t)t * B + b0) * 64 + oh] = v;
+                        const float eh = attn_e2(v);        // kept as e^{2 d_h(h')}, see attn_tanh
+                        dhv[oh] = eh;
+                        if (train && MMG_SAVE_OK(b0)) W.dh_s[((size_t)t * B + b0) * 64 + oh] = eh;
                     }
                 }
             }
@@ -541,10 +539,8 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
             // ---- PA: description attention (model.py:344-410) from the shared-memory word tables ------------------------
             {   // scores: 4 lanes per word (16 units each), 64 words per pass
                 const float4 va0 = lds4(vas + 4 * p4), va1 = lds4(vas + 16 + 4 * p4), va2 = lds4(vas + 32 + 4 * p4), va3 = lds4(vas + 48 + 4 * p4);
-                float4 h0 = lds4(dhv + 4 * p4), h1 = lds4(dhv + 16 + 4 * p4), h2 = lds4(dhv + 32 + 4 * p4), h3 = lds4(dhv + 48 + 4 * p4);
-                auto e2 = [](float4& v) { v.x = fast_exp(2.f * v.x); v.y = fast_exp(2.f * v.y); v.z = fast_exp(2.f * v.z); v.w = fast_exp(2.f * v.w); };
-                e2(h0); e2(h1); e2(h2); e2(h3);                     // e^{2 d_h(h')}: 16 exponentials per thread and step
-                auto th = [](float ew, float eh) { return 1.0f - fast_rcp(fmaf(ew, eh, 1.0f)) * 2.0f; };
+                const float4 h0 = lds4(dhv + 4 * p4), h1 = lds4(dhv + 16 + 4 * p4), h2 = lds4(dhv + 32 + 4 * p4), h3 = lds4(dhv + 48 + 4 * p4);
+                auto th = [](float ew, float eh) { return attn_tanh(ew, eh); };
                 const float ba = ldg(aa.ba);
                 for (int base = 0; base < NWD; base += NT / 4) {
                     const int n = base + k4t;

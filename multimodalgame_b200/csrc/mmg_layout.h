@@ -236,14 +236,14 @@ struct Ws {   // byte offsets into the workspace
     int64_t tickets;   // uint32[8]: [0] loss reduction, [1] h_x rows ready, [2] send buffer complete, [4..5] grid barrier
     int64_t opt_counters; // int64[4]: [0] = number of updates that reached the receiver message head (Adam bias correction)
     // -desc_attn (all zero-sized otherwise)
-    int64_t wtab_dd;   // (NW,A4)  d_d(desc_set): word half of the attention pre-activation, loop invariant
+    int64_t wtab_dd;   // (NW,A4)  e^{2 d_d(desc_set)}: word factor of the attention tanh (attn_tanh), loop invariant
     int64_t wtab_y1;   // (NW,Hr)  desc_set . y1.weight[:, :WV]^T
     int64_t wtab_wd;   // (NW,Hr)  desc_set . w_d.weight^T
     int64_t seg;       // int32 (D+1) first word of each class;  wcls: int32 (NW) class of each word
     int64_t wcls;
     int64_t qa;        // (T,B,NW) softmax(y)[class of word] * attention weight: rows of the wd = (q a) . desc_set GEMM
     int64_t attn;      // (T,B,NW) attention weights (softmax within each class's words)
-    int64_t dh_s;      // (T,B,A)  d_h(h_z): hidden half of the attention pre-activation
+    int64_t dh_s;      // (T,B,A)  e^{2 d_h(h_z)}: hidden factor of the attention tanh
     int64_t ddh;       // (T,B,A)  dL/d dh_s
     int64_t dva;       // (T,B,A)  per-row partial of dL/d d_attn.weight;  dba (T,B): of d_attn.bias
     int64_t dba;

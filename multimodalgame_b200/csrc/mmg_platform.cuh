@@ -53,6 +53,10 @@ MMG_DEVICE float fast_exp(float x) { return __expf(x); }
 MMG_DEVICE float fast_rcp(float x) { return __fdividef(1.0f, x); }
 MMG_DEVICE float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 MMG_DEVICE float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+// Additive attention scores tanh(w + h) with the two halves kept as e2(w) = e^{2w}, e2(h) = e^{2h} (arguments clamped so
+// that neither factor is 0 or inf): tanh(w + h) = 1 - 2 / (e^{2w} e^{2h} + 1), one reciprocal per element.
+MMG_DEVICE float attn_e2(float x) { return __expf(2.0f * fminf(fmaxf(x, -40.0f), 40.0f)); }
+MMG_DEVICE float attn_tanh(float ew, float eh) { return 1.0f - 2.0f * __fdividef(1.0f, fmaf(ew, eh, 1.0f)); }
 // sum over aligned groups of N lanes (N power of two <= 32); every lane of the group receives the sum
 template <int N>
 MMG_DEVICE float group_sum(float v) {
@@ -255,6 +259,8 @@ MMG_DEVICE float fast_exp(float x) { return expf(x); }
 MMG_DEVICE float fast_rcp(float x) { return 1.0f / x; }
 MMG_DEVICE float fast_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 MMG_DEVICE float fast_tanh(float x) { return 1.0f - 2.0f / (expf(2.0f * x) + 1.0f); }
+MMG_DEVICE float attn_e2(float x) { return expf(2.0f * fminf(fmaxf(x, -40.0f), 40.0f)); }
+MMG_DEVICE float attn_tanh(float ew, float eh) { return 1.0f - 2.0f / (fmaf(ew, eh, 1.0f)); }
 template <int N>
 MMG_DEVICE float group_sum(float v) {
     for (int o = N / 2; o > 0; o >>= 1) v += (float)emu::shfl_xor(v, o);

@@ -103,7 +103,7 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
     if ((int)blockIdx.x < n_hx_tiles + n_cls_tiles && d.A) {
         // ---- role C, -desc_attn: loop-invariant WORD tables (model.py:352 and the word halves of y1 / w_d) ------------
         //   wtab_y1[n][k] = desc_set[n] . y1.weight[k][:WV]   wtab_wd[n][k] = desc_set[n] . w_d.weight[k]
-        //   wtab_dd[n][a] = d_d.bias[a] + desc_set[n] . d_d.weight[a]
+        //   wtab_dd[n][a] = e^{2 (d_d.bias[a] + desc_set[n] . d_d.weight[a])}: the word factor of tanh(d_d(word) + d_h(h)), see attn_tanh
         const int ntk = cdiv(d.Hr, kTile), nta = cdiv(d.A, kTile), per_m = 2 * ntk + nta;
         int t = (int)blockIdx.x - n_hx_tiles;
         const int mt = t / per_m;
@@ -128,7 +128,7 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
             for (int c = 0; c < 4; ++c) {
                 const int k = nt * kTile + tx * 4 + c;
                 if (k >= NP) continue;
-                out[(size_t)n * NP + k] = k < N ? acc[a][c] + (which == 2 ? ldg(P.p[MMG_P_REC_DD_B] + k) : 0.f) : 0.f;
+                out[(size_t)n * NP + k] = k < N ? (which == 2 ? attn_e2(acc[a][c] + ldg(P.p[MMG_P_REC_DD_B] + k)) : acc[a][c]) : 0.f;
             }
         }
         return;

@@ -355,3 +355,47 @@ def run_fused_step_case(cfg, lib, device, iters=2, seed=0, tag="fused"):
                              atol=atol)
         e.load_params(oparams)
     return True
+
+
+def run_replay_case(cfg, lib, device, seed=3, tag="replay"):
+    """The training configuration bench.py times (on-device Philox draws, compile-time mode flags) against the oracle:
+    the bits the device sampled are replayed through the oracle with uniforms u = 1 - bit (u < p reproduces the bit for
+    any p in (0, 1)), then probabilities, scores, losses and post-step parameters must agree."""
+    B, T = cfg.batch_size, cfg.max_exchange
+    params = go.init_params(cfg, seed=seed)
+    oparams = go.clone_params(params)
+    ostate = go.new_opt_state(oparams)
+    words = _synth_words(cfg, seed)
+    e = eng.GameEngine(config_from(cfg, n_words=int(words["desc_set"].shape[0]) if words else 0), device=device, lib=lib,
+                       seed=99)
+    e.load_params(params)
+    if words:
+        e.set_desc_set(**words)
+    x, desc, target = go.synthetic_batch(cfg, seed=seed)
+    e.train_step(x, desc, target, top_k=min(cfg.top_k_train, cfg.n_classes))          # no injected uniforms
+    out = {k: v.detach().cpu().numpy() for k, v in e.outputs().items()}
+    us = [(1.0 - out["sen_feats"][t].astype(np.float64), 1.0 - out["stop_feat"][t].astype(np.float64).reshape(B, 1),
+           1.0 - out["rec_feats"][t].astype(np.float64)) for t in range(T)]
+    ex, res, grads = go.train_iteration(oparams, ostate, x, target, desc, cfg, us, return_grads=True, **words)
+    Tp = len(ex["y"])
+    st = lambda key: np.stack([t.detach().numpy() for t in ex[key]], 0)
+    assert np.array_equal(out["sen_feats"][:Tp], st("sen_feats")) and np.array_equal(out["rec_feats"][:Tp], st("rec_feats"))
+    worst = dict(sen_probs=assert_close(tag + "/sen_probs", out["sen_probs"][:Tp], st("sen_probs")),
+                 rec_probs=assert_close(tag + "/rec_probs", out["rec_probs"][:Tp], st("rec_probs")),
+                 y=assert_close(tag + "/y", out["y"][:Tp], st("y")))
+    assert np.array_equal(out["argmax"], res["argmax"].numpy()), tag + " argmax differs"
+    L = e.losses()
+    for name in ("nll_loss", "loss_rec", "loss_sen", "loss_bas_rec", "loss_bas_sen"):
+        worst[name] = assert_close(tag + "/" + name, L[name], float(res[name].detach()), rtol=1e-4, atol=1e-4)
+    pv = e.named_views()
+    lr = cfg.learning_rate
+    for a in oparams:
+        for k, v in oparams[a].items():
+            if (a, k) in (("receiver", "y2.bias"), ("receiver", "d_attn.bias")):
+                continue
+            g = grads.get(a, {}).get(k)
+            atol = 2e-2 * lr + 1e-7
+            if g is not None:
+                atol = np.where((g.abs() < 1e-5).numpy(), 12 * lr, atol)
+            assert_close("%s/param %s.%s" % (tag, a, k), pv[a][k].detach().cpu().numpy(), v.numpy(), rtol=1e-5, atol=atol)
+    return worst
