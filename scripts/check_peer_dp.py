@@ -17,15 +17,20 @@ lib = capi.load()
 HEAD = dict(img_h_dim=256, baseline_hid_dim=500, sender_out_dim=32, rec_hidden=64, rec_w_dim=32, wv_dim=100,
             entropy_sen=0.01, entropy_rec=0.01, top_k_train=6)
 ok = True
-for name, kw in (("fixed", dict(fixed_exchange=True)), ("adaptive", dict(fixed_exchange=False, entropy_s=0.08))):
+for name, kw in (("fixed", dict(fixed_exchange=True)), ("adaptive", dict(fixed_exchange=False, entropy_s=0.08)),
+                 ("desc_attn", dict(fixed_exchange=True, desc_attn=True, desc_attn_dim=64))):
     Bl = 16
     B = Bl * world
     cfg = go.GameConfig(batch_size=B, img_feat_dim=512, n_classes=30, max_exchange=6, use_binary=True, **kw, **HEAD)
     params = go.init_params(cfg, seed=5)
     oparams = go.clone_params(params); ostate = go.new_opt_state(oparams)
-    e_peer = eng.GameEngine(pu.config_from(cfg, B=Bl, batch_global=B), device=dev, lib=lib)
-    e_nccl = eng.GameEngine(pu.config_from(cfg, B=Bl, batch_global=B), device=dev, lib=lib)
+    words = pu._synth_words(cfg, 5)
+    nw = int(words["desc_set"].shape[0]) if words else 0
+    e_peer = eng.GameEngine(pu.config_from(cfg, B=Bl, batch_global=B, n_words=nw), device=dev, lib=lib)
+    e_nccl = eng.GameEngine(pu.config_from(cfg, B=Bl, batch_global=B, n_words=nw), device=dev, lib=lib)
     e_peer.load_params(params); e_nccl.load_params(params)
+    if words:
+        e_peer.set_desc_set(**words); e_nccl.set_desc_set(**words)
     e_peer.enable_peer_dp()
     lo, hi = rank * Bl, (rank + 1) * Bl
     for it in range(3):
@@ -36,7 +41,7 @@ for name, kw in (("fixed", dict(fixed_exchange=True)), ("adaptive", dict(fixed_e
         e_peer.train_step_peer(x[lo:hi], desc, target[lo:hi], uniforms=(sh(uz), sh(us_), sh(uw)))
         e_nccl.train_step_dp(x[lo:hi], desc, target[lo:hi], uniforms=(sh(uz), sh(us_), sh(uw)))
         torch.cuda.synchronize()
-        go.train_iteration(oparams, ostate, x, target, desc, cfg, us)
+        go.train_iteration(oparams, ostate, x, target, desc, cfg, us, **words)
         err = e_peer.peer_error()
         same = torch.equal(e_peer.params, e_nccl.params)
         dmax = float((e_peer.params - e_nccl.params).abs().max())
@@ -44,7 +49,7 @@ for name, kw in (("fixed", dict(fixed_exchange=True)), ("adaptive", dict(fixed_e
         worst = 0.0
         for a in oparams:
             for k, v in oparams[a].items():
-                if (a, k) == ("receiver", "y2.bias"):
+                if (a, k) in (("receiver", "y2.bias"), ("receiver", "d_attn.bias")):
                     continue
                 worst = max(worst, float((pv[a][k].detach().cpu() - v).abs().max()))
         # replicas must agree bit for bit across ranks
