@@ -399,14 +399,15 @@ static int launch_fwd_fast_attn(const Dims& d, const WsPtrs& W, const ExchangeIn
     const bool perf = in.train && d.use_binary && in.u_sen == nullptr && in.corrupt_mask == nullptr && !d.ignore_receiver &&
                       d.flip_sen < 0.f && d.flip_rec < 0.f && !d.mix_prod && !d.ignore_code;
     int rc;
+    const int n_side = in.train ? cdiv(d.B, kTile) * cdiv(d.Hb, kTile) : 0;     // baseline pre-activation tiles (U[b])
     if (perf) {
         auto kern = k_exchange_fwd_fast<1, 32, true, true, true>;
         if ((rc = set_smem(kern, pl.fast_fwd_smem_bytes))) return rc;
-        MMG_LAUNCH(kern, d.B, kFastThreads, pl.fast_fwd_smem_bytes, st, d, W, in, fa.b_img, 0, fa.bs_w1, fa.bs_b1, d.B, aa);
+        MMG_LAUNCH(kern, d.B + n_side, kFastThreads, pl.fast_fwd_smem_bytes, st, d, W, in, fa.b_img, 0, fa.bs_w1, fa.bs_b1, d.B, aa);
     } else {
         auto kern = k_exchange_fwd_fast<1, 32, true, false, true>;
         if ((rc = set_smem(kern, pl.fast_fwd_smem_bytes))) return rc;
-        MMG_LAUNCH(kern, d.B, kFastThreads, pl.fast_fwd_smem_bytes, st, d, W, in, fa.b_img, 0, fa.bs_w1, fa.bs_b1, d.B, aa);
+        MMG_LAUNCH(kern, d.B + n_side, kFastThreads, pl.fast_fwd_smem_bytes, st, d, W, in, fa.b_img, 0, fa.bs_w1, fa.bs_b1, d.B, aa);
     }
     return check_cuda("k_exchange_fwd_fast<attn>");
 }
@@ -465,7 +466,7 @@ struct WgBuilder {
 };
 
 static void build_wgrad_table(const Dims& d, const mmg_param_layout& L, const ParamPtrs& P, const WsPtrs& W,
-                              const ExchangeInputs& in, int fast, int n_rec_ctas, WgTable* t, SplitTable* st) {
+                              const ExchangeInputs& in, int fast, int fast_bs, int n_rec_ctas, WgTable* t, SplitTable* st) {
     t->count = 0; t->total_tiles = 0; t->slab_stride = L.total;
     for (int i = 0; i < MMG_P_COUNT; ++i) {
         st->begin[i] = L.offset[i]; st->numel[i] = L.rows[i] * L.cols[i]; st->nsplit[i] = 0;   // 0: no problem writes this tensor
@@ -513,7 +514,7 @@ static void build_wgrad_table(const Dims& d, const mmg_param_layout& L, const Pa
         {
             Operand a = km(W.h1s, d.Hb);
             a.kind = OP_RELUGRAD; a.g = W.g_bs; a.w2 = P.p[MMG_P_BS_L2_W];
-            if (fast) {
+            if (fast_bs) {
                 // h_x is shared by the T rows of an example: sum the relu-gradient over t first (K = B instead of T*B),
                 // the z_r columns keep the full row range
                 Operand at = a;
@@ -684,7 +685,7 @@ static int exchange_forward_impl(const mmg_config* cfg, const float* d_params, c
         const int tiles = 2 * cdiv(d.R, kTile) * W.ntb;
         // wd rows as GEMM tiles (fast path and -desc_attn); otherwise the generic kernel writes wd itself
         const int wd_tiles = (pl.fast || d.A) ? cdiv(d.R, kTile) * cdiv(d.WV, kTile) : 0;
-        MMG_LAUNCH(k_baseline_fwd, tiles + wd_tiles, kGemmThreads, 0, st, d, P, W, d.A ? ei.desc_set : ei.desc, tiles, pl.fast);
+        MMG_LAUNCH(k_baseline_fwd, tiles + wd_tiles, kGemmThreads, 0, st, d, P, W, d.A ? ei.desc_set : ei.desc, tiles, pl.fast_fwd);
         if ((rc = check_cuda("k_baseline_fwd"))) return rc;
         if (finish_baselines) {     // standalone forward: bs / br must be final on return (mmg_loss re-derives them anyway)
             MMG_LAUNCH(k_baseline_finish, cdiv(d.R, 256), 256, 0, st, d, P, W);
@@ -768,7 +769,7 @@ static int backward_impl(const mmg_config* cfg, const float* d_params, const mmg
     }
     WgTable tab;
     SplitTable stab;
-    build_wgrad_table(d, L, P, W, ei, pl.fast, cdiv(d.B, pl.BT), &tab, &stab);
+    build_wgrad_table(d, L, P, W, ei, pl.fast, pl.fast_fwd, cdiv(d.B, pl.BT), &tab, &stab);
     MMG_LAUNCH(k_wgrad, tab.total_tiles, kGemmThreads, 0, st, d, tab, d_grads, W.slabs, P.p[MMG_P_SEN_CODE_W],
                P.p[MMG_P_SEN_CODE_BIAS], W.d_as);
     if ((rc = check_cuda("k_wgrad"))) return rc;
