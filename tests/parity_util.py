@@ -399,3 +399,32 @@ def run_replay_case(cfg, lib, device, seed=3, tag="replay"):
                 atol = np.where((g.abs() < 1e-5).numpy(), 12 * lr, atol)
             assert_close("%s/param %s.%s" % (tag, a, k), pv[a][k].detach().cpu().numpy(), v.numpy(), rtol=1e-5, atol=atol)
     return worst
+
+
+def run_attn_eval_fast_vs_generic(lib, device, monkeypatch):
+    """Eval-mode conversation with -desc_attn at the fast shapes: the fast forward kernel against the generic one
+    (itself pinned to the reference by the eval_desc_attn golden) and against the oracle."""
+    cfg = go.GameConfig(batch_size=5, img_feat_dim=32, n_classes=7, max_exchange=4, fixed_exchange=False, use_binary=True,
+                        img_h_dim=256, baseline_hid_dim=16, sender_out_dim=32, rec_hidden=64, rec_w_dim=32, wv_dim=20,
+                        desc_attn=True, desc_attn_dim=64)
+    params = go.init_params(cfg, seed=4)
+    params["receiver"]["s.weight"].mul_(3.0)
+    words = _synth_words(cfg, 4)
+    x, desc, target = go.synthetic_batch(cfg, seed=4)
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("MMG_FAST_ATTN", flag)
+        e = eng.GameEngine(config_from(cfg, n_words=int(words["desc_set"].shape[0])), device=device, lib=lib)
+        e.load_params(params)
+        e.set_desc_set(**words)
+        e.forward(x, desc, target, train=False)
+        outs.append({k: v.detach().cpu().numpy().copy() for k, v in e.outputs().items()})
+    a, b = outs
+    for k in ("sen_feats", "rec_feats", "stop_feat", "stop_mask"):
+        assert np.array_equal(a[k], b[k]), k
+    for k in ("sen_probs", "rec_probs", "stop_prob", "y"):
+        assert_close("fast vs generic " + k, a[k], b[k])
+    with torch.no_grad():
+        ex = go.exchange(params, x, desc, cfg, False, None, break_early=False, **words)
+    assert_close("fast vs oracle y", a["y"], np.stack([t.numpy() for t in ex["y"]], 0))
+    assert np.array_equal(a["sen_feats"], np.stack([t.numpy() for t in ex["sen_feats"]], 0))
