@@ -99,7 +99,7 @@ MMG_HOST_DEVICE int fast_fwd_state_floats(int BT, int M, int D, int T) {
            align4(2 * BT) + 8;
 }
 
-// -desc_attn on the fast forward kernel (one example per CTA, msg_dim 32, attention width 64): the two word tables read
+// -desc_attn on the fast forward kernel (one example per CTA, any batch, msg_dim 32, attention width 64): the two word tables read
 // every step by all threads (d_d(desc_set) and desc_set . w_d^T) live in shared memory with rows padded to 72 floats;
 // desc_set . y1^T is read from L2 once per step by the (class, column group) threads.
 enum { kFastAttnLd = 72, kFastAttnA = 64 };   // row stride 72: the per-unit reads of 4 consecutive words hit 32 distinct banks
@@ -108,7 +108,8 @@ MMG_HOST_DEVICE int fast_fwd_attn_floats(int D, int NW) {
     return 2 * NW * kFastAttnLd + 2 * align4(NW) + 3 * 64 + D * 64 + 64 * 64 + align4(D + 1) + align4(NW);
 }
 MMG_HOST_DEVICE bool fast_fwd_attn_dims(const Dims& d) {
-    return d.Hi == kFastHi && d.Hr == kFastHr && d.M == 32 && d.T <= kFastMaxT && d.A == kFastAttnA && d.B <= 148;
+    // any batch: one example per CTA, in waves when B exceeds the SM count (conversation CTAs never wait on anything)
+    return d.Hi == kFastHi && d.Hr == kFastHr && d.M == 32 && d.T <= kFastMaxT && d.A == kFastAttnA;
 }
 
 MMG_DEVICE void fma4(const float4& w, const float4& x, float4& acc) {      // two packed fp32x2 FMAs (FFMA2)
