@@ -322,10 +322,11 @@ def main():
     bytes_iter = algorithmic_bytes_per_iteration(cfgd, world)
     # DRAM traffic per iteration from the committed ncu capture of this same command (profiles/, L2-flushed protocol)
     traffic, traffic_src = None, None
-    if name == "C2" and world == 1 and flush is not None:
+    if name in ("C2", "C2A") and world == 1 and flush is not None:
         try:
             import glob
-            f = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_dram_traffic.json")))[-1]
+            pat = "*_dram_traffic.json" if name == "C2" else "*_c2a_desc_attn_dram.json"
+            f = sorted(glob.glob(os.path.join(ROOT, "profiles", pat)))[-1]
             traffic = float(json.load(open(f))["per_iteration"]["total_bytes"])
             traffic_src = os.path.relpath(f, ROOT)
         except Exception:
