@@ -352,8 +352,9 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_iteration": bytes_iter,
-                     "kernel": "whole iteration = one launch sequence of 9 kernels (k_pre, k_exchange_fwd, k_baseline_fwd, k_stats, "
-                               "k_lossgrad, k_exchange_bwd, k_wgrad, k_reduce_norm, k_update); achieved = algorithmic bytes per "
+                     "kernel": "whole iteration = one launch sequence of %d kernels (k_pre, k_exchange_fwd, k_baseline_fwd, k_stats, "
+                               "k_lossgrad, k_exchange_bwd, %sk_wgrad, k_reduce_norm, k_update); achieved = algorithmic bytes per "
+                               % ((10, "k_attn_reduce, ") if cfgd.get("desc_attn") else (9, "")) +
                                "iteration / CUDA-event time per iteration; the path is latency/dependency-bound, see DESIGN.md"},
     }
     if e2e is not None:
