@@ -6,6 +6,8 @@
 //       (model.py:441) so non-prediction steps contribute nothing to y1/y2.
 //   sender CTAs: the Sender has no recurrence (every inter-agent tensor is cut with .data, model.py:807-811), so its
 //       per-step MLP backward runs concurrently on other SMs and only accumulates d h_x over steps.
+// With -desc_attn the receiver CTAs also run the attention backward of every step (scores, segment softmax, the two
+// places the attention weights enter) and keep per-CTA sums of the per-word gradients, see the blocks marked desc_attn.
 // The kernels emit the pre-activation gradients ("deltas"); all weight gradients are then batched GEMMs over the
 // T*B rows (K_wgrad).  Transposed, packed weight copies come from the backward image (TMA bulk copy into smem).
 #pragma once

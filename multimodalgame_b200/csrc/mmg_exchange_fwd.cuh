@@ -11,6 +11,8 @@
 //                     q = softmax(y);  h_w = tanh(w_h(h') + sum_d q_d wdd[d]);  p_w = sigmoid(w(h_w));  w ~ Bernoulli
 // Mat-vecs read "packed" weights (see mmg_layout.h) as float4, split along the reduction dimension across warps when
 // the output is narrower than the CTA, and meet in shared memory.
+// -desc_attn (model.py:344-410): between the heads and the class scores the receiver attends over the words of every
+// class description; the per-word linear halves are loop-invariant tables written by K_pre, see the block in the loop.
 #pragma once
 #include "mmg_kernels.cuh"
 
