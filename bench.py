@@ -1,19 +1,22 @@
 #!/usr/bin/env python
 """bench.py — exchange-steps/sec of the referential-game training iteration (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2|C3|C4|C5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2|C3|C4|C5|C2A]
 
 One "step" = one full training iteration (model.py:1240-1339: T-step conversation, losses, backward, 4x clip +
 RMSprop) over one synthetic batch; the metric is exchange steps per second = T' x iterations / second, whole job.
 N=1 runs configs[1] of BASELINE.json (the configuration the metric is quoted on): fixed 10-step exchange, batch 64,
 30 classes, 2048-d features, -use_binary.  N>1 (torchrun, one rank per GPU) keeps 64 rows per GPU (weak scaling,
-configs[3] at N=8) and all-reduces the batch statistics and the flat gradient buffer over NCCL.
+configs[3] at N=8); the batch statistics and the flat gradient are summed across the ranks inside the kernels over NVLink
+peer memory (or by NCCL with --dp nccl).
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port of the reference path on the host cores
-(the reference itself is Python 2 / torch 0.1.12 code that only runs under the build container's compat shim).
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU port of the reference path (oracle/game_oracle.py) on
+the host cores, on the SAME global batch, honouring --steps / --warmup (the reference itself is Python 2 / torch 0.1.12
+code that only runs under the build container's compat shim).
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -49,6 +52,14 @@ WORKLOAD = {
 }
 
 
+def bench_config(name, cfgd, world):
+    """The `config` object of the JSON line: identical for both arms (`--impl ours` and `--impl reference`)."""
+    return {"workload": WORKLOAD[name], "name": name, "batch_per_gpu": cfgd["batch_size"],
+            "global_batch": cfgd["batch_size"] * world, "max_exchange": cfgd["max_exchange"],
+            "fixed_exchange": bool(cfgd["fixed_exchange"]), "n_classes": cfgd["n_classes"], "img_feat_dim": cfgd["img_feat_dim"],
+            "msg_dim": cfgd["rec_w_dim"], "parallelism": "dp%d" % world}
+
+
 def param_counts(c):
     F, Hi, M, Hr, WV, Hb = c["img_feat_dim"], c["img_h_dim"], c["rec_w_dim"], c["rec_hidden"], c["wv_dim"], c["baseline_hid_dim"]
     sender = Hi * F + Hi + Hi * M + Hi + M + M * Hi + M
@@ -72,30 +83,40 @@ def algorithmic_bytes_per_iteration(c, n_gpus):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the run (B200_PROFILING.md recipe); every sample carries its
+    arrival time so that only samples taken under load (between `mark_begin` and `mark_end`) are reported."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.proc = index, [], None
+        self.t0, self.t1 = None, None
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, universal_newlines=True)
             for line in self.proc.stdout:
-                self.rows.append([f.strip() for f in line.split(",")])
+                self.rows.append((time.time(), [f.strip() for f in line.split(",")]))
         except Exception:
             pass
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
         self.join(timeout=2)
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for ts, r in self.rows:
+            if self.t0 is not None and not (self.t0 <= ts <= (self.t1 or ts)):
+                continue
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
@@ -105,47 +126,93 @@ class ClockSampler(threading.Thread):
                 continue
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "window": "untimed pre-conditioning burst of the same step (>= 0.6 s) + warm-up + timed region"}
 
 
-def time_oracle(cfgd, iters, warmup, threads=None):
-    """The reference path's CPU port (oracle/game_oracle.py): full training iterations incl. host-side sampling."""
-    from oracle import game_oracle as go
-    if threads:
-        torch.set_num_threads(threads)
-    cfg = go.GameConfig(**cfgd)
-    params = go.init_params(cfg, seed=0)
-    state = go.new_opt_state(params)
-    x, desc, target = go.synthetic_batch(cfg, seed=0)
-    from tests import parity_util as pu
-    words = pu._synth_words(cfg, 0)
-    rng = np.random.RandomState(0)
-    times, steps = [], 0
-    for i in range(warmup + iters):
-        us = go.draw_uniforms(rng, cfg)
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference path's port (oracle/game_oracle.py), full training iterations incl. host-side sampling
+# ---------------------------------------------------------------------------------------------------------------------
+class CpuArm(object):
+    def __init__(self, cfgd, world):
+        from oracle import game_oracle as go
+        from multimodalgame_b200 import synthetic as syn
+        self.go = go
+        gd = dict(cfgd, batch_size=cfgd["batch_size"] * world)          # the SAME workload: the global batch
+        self.cfg = go.GameConfig(**gd)
+        fl = syn.GameFlags(**gd)
+        self.params = go.clone_params(syn.init_params(fl, seed=0))
+        self.state = go.new_opt_state(self.params)
+        self.x, self.desc, self.target = syn.batch(fl, seed=0)
+        self.words = syn.desc_set(fl, seed=0)
+        self.rng = np.random.RandomState(0)
+
+    def iteration(self):
+        us = self.go.draw_uniforms(self.rng, self.cfg)
         t0 = time.perf_counter()
-        ex, _ = go.train_iteration(params, state, x, target, desc, cfg, us, **words)
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-            steps += len(ex["y"])
-    return sum(times), steps, torch.get_num_threads()
+        ex, _ = self.go.train_iteration(self.params, self.state, self.x, self.target, self.desc, self.cfg, us, **self.words)
+        return time.perf_counter() - t0, len(ex["y"])
+
+    def run(self, iters, warmup, threads):
+        torch.set_num_threads(threads)
+        for _ in range(warmup):
+            self.iteration()
+        total, steps = 0.0, 0
+        for _ in range(iters):
+            dt, n = self.iteration()
+            total += dt; steps += n
+        return total, steps
+
+
+def cpu_baseline_sample(cfgd, world, budget_s=12.0, max_iters=30):
+    """Bounded sample (about 10-30 s of CPU work) of the same workload with all host threads AND one thread; best reported."""
+    arm = CpuArm(cfgd, world)
+    ncpu = os.cpu_count() or 1
+    best = None
+    for threads in sorted({ncpu, 1}, reverse=True):
+        torch.set_num_threads(threads)
+        dt, _ = arm.iteration()                                         # warm-up + cost estimate
+        iters = int(max(2, min(max_iters, budget_s / max(dt, 1e-4))))
+        total, steps = arm.run(iters, 1, threads)
+        r = dict(value=world * steps / total, threads=threads, iters=iters, ms=1e3 * total / iters)
+        if best is None or r["value"] > best["value"]:
+            best = r
+    return best, ncpu
 
 
 def run_reference(args, cfgd, name, out_stream):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    iters = max(1, min(args.steps, 40))
-    total, steps, threads = time_oracle(cfgd, iters, min(args.warmup, 3))
-    val = steps / total
+    world = args.gpus
+    ncpu = os.cpu_count() or 1
+    arm = CpuArm(cfgd, world)
+    K, Wm = max(1, args.steps if args.steps else 20), max(0, args.warmup)
+    torch.set_num_threads(ncpu)            # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every host core it can
+    t_probe, _ = arm.iteration()
+    threads = ncpu
+    if ncpu > 1:                           # the tiny per-op GEMMs of this path do not always scale with threads: probe one thread
+        torch.set_num_threads(1)
+        arm.iteration()
+        t1, _ = arm.iteration()
+        torch.set_num_threads(ncpu)
+        tn, _ = arm.iteration()
+        if t1 < tn:
+            threads, t_probe = 1, t1
+        else:
+            t_probe = tn
+    n_timed = K if K * t_probe < 150.0 else max(1, int(150.0 / t_probe))       # bounded: the whole run ends within minutes
+    total, steps = arm.run(n_timed, Wm, threads)
+    val = world * steps / total            # same unit as the GPU arm: one exchange step over one batch shard (N shards per global step)
+    sample = ("%d training iterations of the same workload (global batch %d = %d shard(s) of %d rows, each exchange step counted "
+              "once per shard like the GPU arm) on the host: oracle/game_oracle.py, torch CPU fp32, %d threads (os.cpu_count=%d; "
+              "all-threads vs 1-thread probed, faster one used), %.1f ms/iteration"
+              % (n_timed, arm.cfg.batch_size, world, cfgd["batch_size"], threads, ncpu, 1e3 * total / n_timed))
     out = {"impl": "reference", "metric": "exchange-steps/sec", "value": val, "unit": "exchange-steps/s", "n_gpus": args.gpus,
-           "steps": iters, "warmup": min(args.warmup, 3), "ms_per_step": 1e3 * total / iters, "higher_is_better": True,
+           "steps": n_timed, "warmup": Wm, "ms_per_step": 1e3 * total / n_timed, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": WORKLOAD[name], "batch": cfgd["batch_size"], "parallelism": "cpu"},
-           "cpu_baseline": {"value": val, "unit": "exchange-steps/s", "cores": threads, "kind": "port",
-                            "sample": "%d training iterations of the same workload on the host (oracle/game_oracle.py, "
-                                      "torch CPU fp32, %d threads, os.cpu_count=%d)" % (iters, threads, os.cpu_count())},
+           "config": bench_config(name, cfgd, world),
+           "cpu_baseline": {"value": val, "unit": "exchange-steps/s", "cores": threads, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": "exchange-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     out_stream.write(json.dumps(out) + "\n")
     out_stream.flush()
@@ -160,16 +227,93 @@ def _claim_stdout():
     return os.fdopen(saved, "w")
 
 
+def dp_oracle_check(e, fl, cfgd, world, rank, dev, dist, step_fn):
+    """One data-parallel iteration with injected uniforms against the CPU oracle on the GLOBAL batch (rank 0 computes the
+    oracle; every rank compares its own shard).  Returns a summary dict; raises on a parity violation."""
+    from oracle import game_oracle as go
+    from multimodalgame_b200 import synthetic as syn
+    B, T, M = fl.batch_size, fl.max_exchange, fl.rec_w_dim
+
+    def close(what, got, want, tol=1e-4):
+        got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+        err = float(np.max(np.abs(got - want) - tol * np.abs(want))) if got.size else 0.0
+        assert err <= tol, "data-parallel check: %s off by %.3g (> %.0e)" % (what, err + tol, tol)
+        return float(np.max(np.abs(got - want))) if got.size else 0.0
+    gcfg = go.GameConfig(**dict(cfgd, batch_size=B * world))
+    gfl = syn.GameFlags(**dict(cfgd, batch_size=B * world))
+    params0 = {a: {k: v.detach().cpu().clone() for k, v in d_.items()} for a, d_ in e.named_views().items()}
+    words = syn.desc_set(fl, seed=0)
+    seed = 7
+    for attempt in range(6):
+        x, desc, target = syn.batch(gfl, seed=500 + seed)
+        us = go.draw_uniforms(np.random.RandomState(seed), gcfg)
+        verdict = torch.zeros(1, dtype=torch.int32, device=dev)
+        ex = res = oparams = None
+        if rank == 0:
+            oparams = go.clone_params(params0)
+            ex, res = go.train_iteration(oparams, go.new_opt_state(oparams), x, target, desc, gcfg, us, **words)
+            gap = 1.0
+            for t in range(len(ex["y"])):
+                gap = min(gap, float(np.abs(us[t][0] - ex["sen_probs"][t].detach().numpy()).min()),
+                          float(np.abs(us[t][2] - ex["rec_probs"][t].detach().numpy()).min()),
+                          float(np.abs(us[t][1] - ex["stop_prob"][t].detach().numpy()).min()))
+            verdict[0] = 1 if gap > 1e-6 else 0          # a uniform within rounding distance of a probability: next seed
+        dist.broadcast(verdict, 0)
+        if int(verdict[0]) == 1:
+            break
+        seed += 1
+    else:
+        raise AssertionError("no seed with a sampling margin found for the data-parallel oracle check")
+    sl = slice(rank * B, (rank + 1) * B)
+    stacked = (torch.from_numpy(np.ascontiguousarray(np.stack([u[0][sl] for u in us], 0))),
+               torch.from_numpy(np.ascontiguousarray(np.stack([u[1][sl] for u in us], 0).reshape(T, B))),
+               torch.from_numpy(np.ascontiguousarray(np.stack([u[2][sl] for u in us], 0))))
+    step_fn(x[sl].to(dev), desc.to(dev), target[sl].to(dev), stacked)
+    torch.cuda.synchronize(dev)
+    out = {k: v.detach().cpu() for k, v in e.outputs().items()}
+    L = e.losses()
+    # every rank ships its shard's bits / scores to rank 0
+    sf, yy = out["sen_feats"].to(dev).contiguous(), out["y"].to(dev).contiguous()
+    gf = [torch.zeros_like(sf) for _ in range(world)]
+    gy = [torch.zeros_like(yy) for _ in range(world)]
+    dist.all_gather(gf, sf)
+    dist.all_gather(gy, yy)
+    summary = {}
+    if rank == 0:
+        Tp = len(ex["y"])
+        st = lambda key: np.stack([t.detach().numpy() for t in ex[key]], 0)
+        got_f = torch.cat([g.cpu() for g in gf], 1).numpy()[:Tp]
+        got_y = torch.cat([g.cpu() for g in gy], 1).numpy()[:Tp]
+        assert np.array_equal(got_f, st("sen_feats")), "data-parallel check: sender bits differ from the global-batch oracle"
+        summary["y_max_err"] = close("y", got_y, st("y"))
+        for nm in ("nll_loss", "loss_rec", "loss_sen", "loss_bas_rec", "loss_bas_sen"):
+            summary[nm + "_err"] = close(nm, L[nm], float(res[nm].detach()))
+        pv = e.named_views()
+        lr = fl.learning_rate
+        worst = 0.0
+        for a in oparams:
+            for k, v in oparams[a].items():
+                if (a, k) in (("receiver", "y2.bias"), ("receiver", "d_attn.bias")):
+                    continue
+                worst = max(worst, float((pv[a][k].detach().cpu() - v).abs().max()))
+        assert worst <= 12 * lr, "data-parallel check: post-step parameters off by %.3g (> 12 lr)" % worst
+        summary["param_max_err_over_lr"] = worst / lr
+        summary["seed"] = seed
+        summary["global_batch"] = B * world
+    return summary
+
+
 def main():
     out_stream = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=None, help="timed iterations (default: as many as fill ~0.6 s)")
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=None, choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--no-dp-check", action="store_true", help="N>1: skip the global-batch oracle check before timing")
     ap.add_argument("--dp", default="peer", choices=["peer", "nccl"],
                     help="N>1: in-kernel NVLink peer-memory reduction (default) or torch.distributed NCCL all-reduce")
     args = ap.parse_args()
@@ -179,16 +323,17 @@ def main():
         run_reference(args, cfgd, name, out_stream)
         return
 
-    import __graft_entry__ as ge
-    ge.build()
-    from multimodalgame_b200 import capi, engine as eng
-    from oracle import game_oracle as go     # cpu_baseline leg + synthetic inputs only
-    from tests import parity_util as pu
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
+    sampler = ClockSampler(local)
+    sampler.start()                       # nvidia-smi takes a few hundred ms to produce its first line: start it first
+
+    import __graft_entry__ as ge
+    ge.build()
+    from multimodalgame_b200 import capi, engine as eng, synthetic as syn
+
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
@@ -196,18 +341,19 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     lib = capi.load()
-    cfg = go.GameConfig(**cfgd)
-    B, T = cfg.batch_size, cfg.max_exchange
-    words = pu._synth_words(cfg, 0)
-    e = eng.GameEngine(pu.config_from(cfg, batch_global=B * world, n_words=int(words["desc_set"].shape[0]) if words else 0),
-                       device=dev, lib=lib, seed=1 + rank * 0)
-    e.load_params(go.init_params(cfg, seed=0))
+    fl = syn.GameFlags(**cfgd)
+    B, T = fl.batch_size, fl.max_exchange
+    words = syn.desc_set(fl, seed=0)
+    # every rank uses the SAME sampler seed: the Philox counters are keyed by the global row (batch_offset)
+    e = eng.GameEngine(syn.config_from_flags(fl, batch_global=B * world, n_words=int(words["desc_set"].shape[0]) if words else 0,
+                                             batch_offset=rank * B), device=dev, lib=lib, seed=1)
+    e.load_params(syn.init_params(fl, seed=0))
     if words:
         e.set_desc_set(**words)
     # synthetic inputs: a ring of distinct batches, resident in HBM for `value`, in pinned host memory for `e2e`
     nb = 8
-    batches = [go.synthetic_batch(cfg, seed=100 * rank + i) for i in range(nb)]
-    desc = batches[0][1].to(dev)
+    batches = [syn.batch(fl, seed=100 * rank + i) for i in range(nb)]
+    desc = syn.batch(fl, seed=0)[1].to(dev)             # class descriptions are shared by all ranks
     xs = [b[0].to(dev) for b in batches]
     ts = [b[2].to(dev) for b in batches]
     hx = [b[0].pin_memory() for b in batches]
@@ -228,13 +374,16 @@ def main():
         if int(flag) == 0:
             dp_mode = "nccl"
 
-    def step(i):
+    def step_on(x, d, t, uniforms=None):
         if dp_mode == "peer":
-            e.train_step_peer(xs[i % nb], desc, ts[i % nb])
+            e.train_step_peer(x, d, t, uniforms=uniforms)
         elif dp_mode == "nccl":
-            e.train_step_dp(xs[i % nb], desc, ts[i % nb])
+            e.train_step_dp(x, d, t, uniforms=uniforms)
         else:
-            e.train_step(xs[i % nb], desc, ts[i % nb])
+            e.train_step(x, d, t, uniforms=uniforms)
+
+    def step(i):
+        step_on(xs[i % nb], desc, ts[i % nb])
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -242,13 +391,39 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    for i in range(max(3, args.warmup)):
+    # ---- N>1: parity of the data-parallel iteration with the global-batch oracle, before anything is timed ------------
+    dp_check = None
+    if world > 1 and not args.no_dp_check:
+        dp_check = dp_oracle_check(e, fl, cfgd, world, rank, dev, dist, step_on)
+        sync_all()
+
+    # ---- untimed pre-conditioning burst (clocks ramp up, sampler collects under-load samples), then W warm-up steps -----
+    sampler.mark_begin()
+    t_burst = time.perf_counter()
+    n_burst = 0
+    while True:
+        for i in range(50):
+            step(n_burst + i)
+        n_burst += 50
+        torch.cuda.synchronize(dev)
+        go_on = torch.tensor([1 if time.perf_counter() - t_burst < 0.6 else 0], device=dev)
+        if dist is not None:
+            dist.all_reduce(go_on, op=dist.ReduceOp.MAX)       # every rank runs the same number of iterations
+        if int(go_on) == 0:
+            break
+    burst_ms_per_iter = 1e3 * (time.perf_counter() - t_burst) / n_burst
+    W = max(3, args.warmup)
+    for i in range(W):
         step(i)
     sync_all()
-    sampler = ClockSampler(local)
-    sampler.start()
+    if args.steps:
+        K = args.steps
+    else:                                  # default: a timed region of >= 0.6 s (a handful of nvidia-smi samples fit inside)
+        kk = torch.tensor([int(min(20000, max(200, math.ceil(600.0 / max(burst_ms_per_iter, 1e-3)))))], device=dev)
+        if dist is not None:
+            dist.all_reduce(kk, op=dist.ReduceOp.MAX)
+        K = int(kk)
     lib.dll.mmg_launch_count_reset()
-    K = args.steps
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     sync_all()
     t_wall = time.perf_counter()
@@ -273,45 +448,61 @@ def main():
     a1.record()
     sync_all()
     warm_ms = a0.elapsed_time(a1)
+    sampler.mark_end()
     clocks = sampler.stop()
-    t = torch.tensor([tot_ms, warm_ms], dtype=torch.float64, device=dev)
+    steps_per_iter = T if fl.fixed_exchange else float(active)
+
+    # ---- e2e: host buffers through the public API: every step copies its batch from pinned host memory (H2D, on a copy
+    #      stream, double-buffered: overlaps the previous step) and its loss values back (D2H).  Timed on the device with
+    #      one pair of events around the K steps (plus the host wall clock), max over ranks.
+    hl = torch.zeros(K, capi.MMG_LOSS_COUNT, dtype=torch.float32).pin_memory()
+    e.enable_host_pipeline(desc)
+
+    def run_host(n):
+        e.host_prefetch(hx[0], ht[0])
+        for i in range(n):
+            slot = i % 2
+            if i + 1 < n:
+                e.host_prefetch(hx[(i + 1) % nb], ht[(i + 1) % nb])
+            e.train_step_staged(hl[i % K], slot, dp_group=dist.group.WORLD if dp_mode == "nccl" else None)
+    run_host(6)
+    sync_all()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    h0.record()
+    run_host(K)
+    h1.record()
+    torch.cuda.synchronize(dev)
+    e2e_wall_ms = 1e3 * (time.perf_counter() - t0)
+    e2e_ms = max(h0.elapsed_time(h1), 0.0)
+    assert float(hl[K - 1][0]) != 0.0          # the loss values really arrived on the host
+
+    # ---- N>1: the replicas must still be bit-identical and no peer wait may have timed out ----------------------------------
+    replicas = None
+    t = torch.tensor([tot_ms, warm_ms, e2e_ms, e2e_wall_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    tot_ms, warm_ms = float(t[0]), float(t[1])
-    steps_per_iter = T if cfg.fixed_exchange else float(active)
-
-    # ---- e2e: host buffers through the C-ABI (mmg_host_prefetch + mmg_train_step_staged): every step copies its batch
-    #      from pinned host memory (H2D, on a copy stream, overlapping the previous step) and its loss values back (D2H)
-    e2e = None
-    if world == 1:
-        hl = torch.zeros(K, capi.MMG_LOSS_COUNT, dtype=torch.float32).pin_memory()
-        e.enable_host_pipeline(desc)
-
-        def run_host(n):
-            e.host_prefetch(hx[0], ht[0])
-            for i in range(n):
-                slot = i % 2
-                if i + 1 < n:
-                    e.host_prefetch(hx[(i + 1) % nb], ht[(i + 1) % nb])
-                e.train_step_staged(hl[i % K], slot)
-        run_host(6)
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        run_host(K)
-        torch.cuda.synchronize(dev)
-        e2e_wall = time.perf_counter() - t0
-        e2e_ms = 1e3 * e2e_wall
-        assert float(hl[K - 1][0]) != 0.0      # the loss values really arrived on the host
-        e2e = {"value": steps_per_iter * K / (e2e_ms * 1e-3), "unit": "exchange-steps/s",
-               "h2d_bytes_per_step": int(B * cfg.img_feat_dim * 4 + B * 8), "d2h_bytes_per_step": capi.MMG_LOSS_COUNT * 4,
-               "ms_per_step": e2e_ms / K, "note": "mmg_host_prefetch + mmg_train_step_staged: pinned host x/target -> device on a "
-               "copy stream (double-buffered, overlaps the previous step), losses -> pinned host every step; timed host-side "
-               "from the first enqueue to the final synchronize"}
+        if dp_mode == "peer":
+            assert e.peer_error() == 0, "a peer wait timed out on rank %d (error %d): the numbers are void" % (rank, e.peer_error())
+        digest = torch.stack([e.params.view(torch.int32).to(torch.int64).sum(), (e.params.double() ** 2).sum().view(torch.int64)])
+        alld = [torch.zeros_like(digest) for _ in range(world)]
+        dist.all_gather(alld, digest)
+        same = all(bool(torch.equal(alld[0], d_)) for d_ in alld)
+        assert same, "parameter replicas diverged across ranks: %s" % [d_.tolist() for d_ in alld]
+        replicas = "bit-identical on %d ranks (int32 checksum + sum of squares of the flat parameter buffer)" % world
+    tot_ms, warm_ms, e2e_ms, e2e_wall_ms = [float(v) for v in t]
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
+    e2e = {"value": world * steps_per_iter * K / (e2e_ms * 1e-3), "unit": "exchange-steps/s",
+           "h2d_bytes_per_step": int(world * (B * fl.img_feat_dim * 4 + B * 8)),
+           "d2h_bytes_per_step": int(world * capi.MMG_LOSS_COUNT * 4), "ms_per_step": e2e_ms / K,
+           "ms_per_step_host_wall": e2e_wall_ms / K,
+           "note": "mmg_host_prefetch + mmg_train_step_staged (N>1: the same staging slots feeding mmg_train_step_peer): pinned "
+                   "host x/target -> device on a copy stream (double-buffered, overlaps the previous step), losses -> pinned "
+                   "host every step; bytes are the whole job's (all ranks); device-timed, max over ranks"}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -320,54 +511,57 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     bytes_iter = algorithmic_bytes_per_iteration(cfgd, world)
-    # DRAM traffic per iteration from the committed ncu capture of this same command (profiles/, L2-flushed protocol)
-    traffic, traffic_src = None, None
+    # DRAM traffic per iteration from the committed ncu capture of this same command (profiles/)
+    traffic, traffic_src, traffic_protocol = None, None, None
     if name in ("C2", "C2A") and world == 1 and flush is not None:
         try:
             import glob
             pat = "*_dram_traffic.json" if name == "C2" else "*_c2a_desc_attn_dram.json"
             f = sorted(glob.glob(os.path.join(ROOT, "profiles", pat)))[-1]
-            traffic = float(json.load(open(f))["per_iteration"]["total_bytes"])
+            tj = json.load(open(f))
+            traffic = float(tj["per_iteration"]["total_bytes"])
             traffic_src = os.path.relpath(f, ROOT)
+            traffic_protocol = tj.get("protocol", "ncu default cache control: L2 flushed before EVERY kernel (per-kernel cold-cache "
+                                                  "upper bound of the in-iteration traffic)")
         except Exception:
             pass
     ms_per_step = tot_ms / K
     achieved = bytes_iter / (ms_per_step * 1e-3) / 1e9
     value = world * steps_per_iter * K / (tot_ms * 1e-3)
+    cfg_out = bench_config(name, cfgd, world)
     out = {
         "metric": "exchange-steps/sec", "value": value, "unit": "exchange-steps/s", "n_gpus": world, "steps": K,
-        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD[name], "batch_per_gpu": B, "global_batch": B * world, "exchange_steps": steps_per_iter,
-                   "sampling": "on-device Philox4x32-10 (parity tests inject the reference's float64 uniforms instead)",
-                   "parallelism": "dp%d" % world,
-                   "dp_reduction": {"peer": "in-kernel sums over NVLink peer memory (statistics in k_lossgrad, gradient in "
-                                            "k_peer_allreduce_norm); no collective call", "nccl": "torch.distributed NCCL all-reduce "
-                                            "(statistics + flat gradient)", "none": "single GPU"}[dp_mode],
-                   "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA events)" if flush is not None
-                   else "not flushed (working set ~25 MB stays L2 resident)"},
+        "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_out,
+        "run": {"exchange_steps": steps_per_iter,
+                "sampling": "on-device Philox4x32-10 keyed by the global batch row (parity tests inject the reference's float64 "
+                            "uniforms instead)",
+                "dp_reduction": {"peer": "in-kernel sums over NVLink peer memory (statistics + gradient); no collective call",
+                                 "nccl": "torch.distributed NCCL all-reduce (statistics + flat gradient)",
+                                 "none": "single GPU"}[dp_mode],
+                "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA events)" if flush is not None
+                else "not flushed (working set ~25 MB stays L2 resident)",
+                "preconditioning_iterations": n_burst, "dp_oracle_check": dp_check, "replicas": replicas},
         "value_l2_warm": world * steps_per_iter * K / (warm_ms * 1e-3), "ms_per_step_l2_warm": warm_ms / K,
         "gpu_launches": int(launches), "launches_per_step": launches / float(K),
         "wall_s_timed_region": t_wall, "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                     "algorithmic_bytes_per_iteration": bytes_iter,
-                     "kernel": "whole iteration = one launch sequence of %d kernels (k_pre, k_exchange_fwd, k_baseline_fwd, k_stats, "
-                               "k_lossgrad, k_exchange_bwd, %sk_wgrad, k_reduce_norm, k_update); achieved = algorithmic bytes per "
-                               % ((10, "k_attn_reduce, ") if cfgd.get("desc_attn") else (9, "")) +
-                               "iteration / CUDA-event time per iteration; the path is latency/dependency-bound, see DESIGN.md"},
+                     "traffic": traffic, "traffic_source": traffic_src, "traffic_protocol": traffic_protocol,
+                     "peak_source": peak_src, "algorithmic_bytes_per_iteration": bytes_iter,
+                     "kernel": "whole iteration = one launch sequence of %.0f kernels; achieved = algorithmic bytes per iteration / "
+                               "CUDA-event time per iteration; the path is latency/dependency-bound, see DESIGN.md" % (launches / float(K))},
+        "e2e": e2e,
     }
-    if e2e is not None:
-        out["e2e"] = e2e
-    if not args.no_cpu_baseline and world == 1:
-        total, steps, threads = time_oracle(cfgd, 30, 3)
-        out["cpu_baseline"] = {"value": steps / total, "unit": "exchange-steps/s", "cores": threads, "kind": "port",
-                               "sample": "30 training iterations of the same workload (oracle/game_oracle.py, torch CPU fp32, "
-                                         "%d threads, os.cpu_count=%d), %.1f ms/iteration" % (threads, os.cpu_count(), 1e3 * total / 30)}
-    out_stream.write(json.dumps(out) + "\n")
-    out_stream.flush()
     if dist is not None:
         dist.destroy_process_group()
+    if not args.no_cpu_baseline:
+        best, ncpu = cpu_baseline_sample(cfgd, world)
+        out["cpu_baseline"] = {"value": best["value"], "unit": "exchange-steps/s", "cores": best["threads"], "kind": "port",
+                               "sample": "%d training iterations of the same workload (global batch %d; oracle/game_oracle.py, torch CPU "
+                                         "fp32), %.1f ms/iteration with %d threads; all-threads (%d) and 1-thread both timed, best "
+                                         "reported" % (best["iters"], B * world, best["ms"], best["threads"], ncpu)}
+    out_stream.write(json.dumps(out) + "\n")
+    out_stream.flush()
 
 
 if __name__ == "__main__":

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MMG_ABI_VERSION 2
+#define MMG_ABI_VERSION 3
 
 typedef enum mmg_status {
     MMG_OK = 0,
@@ -73,6 +73,9 @@ typedef struct mmg_config {
     int32_t desc_attn;       /* model.py:1719,344-410: the receiver attends over the words of each class description */
     int32_t desc_attn_dim;   /* A   model.py:1720 */
     int32_t n_words;         /* NW  rows of `desc_set` (sum of desc_set_lens); only read when desc_attn != 0 */
+    int32_t batch_offset;    /* index of this rank's first row inside the global batch (rank * batch in a data-parallel run, else 0):
+                                the on-device sampler keys its Philox counters by the GLOBAL row, so the shards of one global batch
+                                draw independent noise and a G-way run consumes the same stream as a single-GPU run of the global batch */
 } mmg_config;
 
 /* ---- parameter layout -------------------------------------------------------------------------------
@@ -309,6 +312,34 @@ int mmg_peer_buffer_layout(const mmg_config* cfg, int64_t* total_bytes, int64_t*
  * symmetric) receives the global gradient; `step` must be identical on all ranks and increase by one per call. */
 int mmg_train_step_peer(const mmg_config* cfg, float* d_params, float* d_grads, float* d_state1, float* d_state2,
                         int64_t step, const mmg_inputs* in, void* d_workspace, const mmg_peers* peers, void* stream);
+
+/* ---- module-level single-turn forwards ---------------------------------------------------------------------------------
+ * The reference's nn.Module.forward entry points, for callers that drive the agents turn by turn instead of through
+ * exchange().  `rows` examples (independent of cfg->batch); parameters are read from the same flat buffer / layout as
+ * everywhere else; no activations are saved (no backward).  Training draws use the injected float64 uniforms when given,
+ * else the Philox stream (seed, counter) — the caller advances `counter` per call.
+ *
+ * mmg_sender_forward: Sender.forward(x, w, g, t) default path, model.py:144-238 (sender_mix sum/prod, ignore_code,
+ *   flipout_sen).  d_w (rows,M) may be NULL when t == 0 (the code is sigmoid(code_bias), model.py:199-200).
+ *   Outputs: d_msg (rows,M) message {0,1} or raw scores (continuous), d_probs (rows,M) (untouched when !use_binary),
+ *   d_h_x (rows,Hi) = sender.h_x (model.py:195). */
+int mmg_sender_forward(const mmg_config* cfg, const float* d_params, int32_t rows, const float* d_x, const float* d_w,
+                       int32_t t, int32_t train, const double* d_u, const double* d_u_flip, uint64_t seed, uint64_t counter,
+                       float* d_msg, float* d_probs, float* d_h_x, void* stream);
+/* mmg_receiver_forward: Receiver.forward(z, desc, desc_set, desc_set_lens), model.py:303-477 incl. the -desc_attn branch
+ *   (344-410).  State: d_h_z (rows,Hr) in/out (`first` != 0: the state was reset, h_z starts at zero, model.py:336-337);
+ *   d_s_prob_prod (rows) in/out, eval only (model.py:423-427).  Outputs: d_s, d_s_prob (rows), d_w, d_w_probs (rows,M),
+ *   d_y (rows,D), d_h_w (rows,Hr). */
+int mmg_receiver_forward(const mmg_config* cfg, const float* d_params, int32_t rows, const float* d_z, const float* d_desc,
+                         const float* d_desc_set, const int32_t* d_desc_set_lens, float* d_h_z, float* d_s_prob_prod,
+                         int32_t first, int32_t train, const double* d_u_stop, const double* d_u_rec, const double* d_u_flip,
+                         uint64_t seed, uint64_t counter, float* d_s, float* d_s_prob, float* d_w, float* d_w_probs,
+                         float* d_y, float* d_h_w, void* stream);
+/* mmg_baseline_forward: Baseline.forward(x, binary, inp), model.py:496-516.  `which`: MMG_SEG_BASELINE_SEN or
+ *   MMG_SEG_BASELINE_REC; absent pieces are NULL with width 0; widths must add up to linear1's input width.  d_out (rows). */
+int mmg_baseline_forward(const mmg_config* cfg, const float* d_params, int32_t which, int32_t rows, const float* d_x,
+                         int32_t x_dim, const float* d_binary, int32_t binary_dim, const float* d_inp, int32_t inp_dim,
+                         float* d_out, void* stream);
 
 /* Number of kernels the last call of each entry point enqueued (for launch accounting). */
 int mmg_launch_count(void);

@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libmmg_b200.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 
+MMG_ABI_VERSION = 3          # include/mmg_b200.h; a library built from other headers is refused at load time
 MMG_P_COUNT = 36
 MMG_SEG_COUNT = 4
 MMG_LOSS_COUNT = 16
@@ -46,7 +47,8 @@ class Config(C.Structure):
         (n, C.c_float) for n in ("entropy_s", "entropy_sen", "entropy_rec", "first_rec", "learning_rate", "max_norm")
     ] + [("ignore_receiver", C.c_int32), ("has_flipout_sen", C.c_int32), ("has_flipout_rec", C.c_int32),
          ("flipout_dev", C.c_int32), ("flipout_sen", C.c_float), ("flipout_rec", C.c_float), ("sender_mix", C.c_int32),
-         ("ignore_code", C.c_int32), ("desc_attn", C.c_int32), ("desc_attn_dim", C.c_int32), ("n_words", C.c_int32)]
+         ("ignore_code", C.c_int32), ("desc_attn", C.c_int32), ("desc_attn_dim", C.c_int32), ("n_words", C.c_int32),
+         ("batch_offset", C.c_int32)]
 
 
 class ParamLayout(C.Structure):
@@ -90,7 +92,7 @@ class Library(object):
     SYMBOLS = ("mmg_abi_version", "mmg_last_error", "mmg_device_count", "mmg_param_layout_get",
                "mmg_workspace_layout_get", "mmg_workspace_init", "mmg_exchange_forward", "mmg_loss", "mmg_backward",
                "mmg_grad_norm", "mmg_clip_update", "mmg_train_step", "mmg_train_step_host", "mmg_host_prefetch", "mmg_train_step_staged", "mmg_peer_buffer_layout", "mmg_train_step_peer", "mmg_launch_count",
-               "mmg_launch_count_reset")
+               "mmg_launch_count_reset", "mmg_sender_forward", "mmg_receiver_forward", "mmg_baseline_forward")
 
     def __init__(self, path):
         self.path = path
@@ -119,10 +121,19 @@ class Library(object):
         i64p = C.POINTER(C.c_int64)
         d.mmg_peer_buffer_layout.argtypes = [cfgp, i64p, i64p, i64p, i64p]
         d.mmg_train_step_peer.argtypes = [cfgp, vp, vp, vp, vp, i64, inp, vp, C.POINTER(Peers), vp]
+        i32, u64 = C.c_int32, C.c_uint64
+        d.mmg_sender_forward.argtypes = [cfgp, vp, i32, vp, vp, i32, i32, vp, vp, u64, u64, vp, vp, vp, vp]
+        d.mmg_receiver_forward.argtypes = [cfgp, vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, u64, u64,
+                                           vp, vp, vp, vp, vp, vp, vp]
+        d.mmg_baseline_forward.argtypes = [cfgp, vp, i32, i32, vp, i32, vp, i32, vp, i32, vp, vp]
         for name in self.SYMBOLS:
             fn = getattr(d, name)
             if name not in ("mmg_last_error", "mmg_launch_count_reset"):
                 fn.restype = C.c_int
+        got = int(d.mmg_abi_version())
+        if got != MMG_ABI_VERSION:
+            raise MmgError("%s implements ABI version %d, this binding expects %d (mmg_config / entry points differ): "
+                           "rebuild it with __graft_entry__.build(force=True)" % (path, got, MMG_ABI_VERSION))
 
     def check(self, rc, what):
         if rc < 0:

@@ -6,6 +6,7 @@
 #include "mmg_fast.cuh"
 #include "mmg_loss.cuh"
 #include "mmg_update.cuh"
+#include "mmg_single.cuh"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -41,6 +42,8 @@ static const int kMaxSmem = 227 * 1024;
 static int validate(const mmg_config* c) {
     if (c == nullptr) return fail(MMG_ERR_INVALID, "null config");
     if (c->batch < 1 || c->batch_global < c->batch) return fail(MMG_ERR_INVALID, "batch=%d batch_global=%d", c->batch, c->batch_global);
+    if (c->batch_offset < 0 || c->batch_offset + c->batch > c->batch_global)
+        return fail(MMG_ERR_INVALID, "batch_offset=%d outside the global batch (batch=%d batch_global=%d)", c->batch_offset, c->batch, c->batch_global);
     if (c->img_feat_dim < 1 || c->img_h_dim < 1 || c->msg_dim < 1 || c->rec_hidden < 1 || c->n_classes < 1 ||
         c->wv_dim < 1 || c->baseline_hid < 1 || c->max_exchange < 1)
         return fail(MMG_ERR_INVALID, "all dimensions must be >= 1");
@@ -350,7 +353,7 @@ static int launch_fwd(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, 
                       cudaStream_t st, const AttnArgs& aa) {
     int rc = set_smem(k_exchange_fwd<BT>, pl.fwd_smem_bytes);
     if (rc) return rc;
-    MMG_LAUNCH(k_exchange_fwd<BT>, cdiv(d.B, BT), kLoopThreads, pl.fwd_smem_bytes, st, d, W, in, b_img, pl.sender_smem, 0, aa);
+    MMG_LAUNCH(k_exchange_fwd<BT>, cdiv(d.B, BT), kLoopThreads, pl.fwd_smem_bytes, st, d, W, in, b_img, pl.sender_smem, d.row0, aa);
     return check_cuda("k_exchange_fwd");
 }
 template <int BT>
@@ -373,7 +376,7 @@ static int launch_fwd_fast_mode(const Dims& d, const WsPtrs& W, const ExchangeIn
     const int n_side = in.train ? cdiv(d.B, kTile) * cdiv(d.Hb, kTile) : 0;     // baseline pre-activation tiles
     AttnArgs none;
     memset(&none, 0, sizeof(none));
-    MMG_LAUNCH(kern, n_conv + n_side, kFastThreads, pl.fwd_smem_bytes, st, d, W, in, fa.b_img, 0, fa.bs_w1, fa.bs_b1, n_conv, none);
+    MMG_LAUNCH(kern, n_conv + n_side, kFastThreads, pl.fwd_smem_bytes, st, d, W, in, fa.b_img, d.row0, fa.bs_w1, fa.bs_b1, n_conv, none);
     return check_cuda("k_exchange_fwd_fast");
 }
 template <int BT, int M, bool SS>
@@ -403,11 +406,11 @@ static int launch_fwd_fast_attn(const Dims& d, const WsPtrs& W, const ExchangeIn
     if (perf) {
         auto kern = k_exchange_fwd_fast<1, 32, true, true, true>;
         if ((rc = set_smem(kern, pl.fast_fwd_smem_bytes))) return rc;
-        MMG_LAUNCH(kern, d.B + n_side, kFastThreads, pl.fast_fwd_smem_bytes, st, d, W, in, fa.b_img, 0, fa.bs_w1, fa.bs_b1, d.B, aa);
+        MMG_LAUNCH(kern, d.B + n_side, kFastThreads, pl.fast_fwd_smem_bytes, st, d, W, in, fa.b_img, d.row0, fa.bs_w1, fa.bs_b1, d.B, aa);
     } else {
         auto kern = k_exchange_fwd_fast<1, 32, true, false, true>;
         if ((rc = set_smem(kern, pl.fast_fwd_smem_bytes))) return rc;
-        MMG_LAUNCH(kern, d.B + n_side, kFastThreads, pl.fast_fwd_smem_bytes, st, d, W, in, fa.b_img, 0, fa.bs_w1, fa.bs_b1, d.B, aa);
+        MMG_LAUNCH(kern, d.B + n_side, kFastThreads, pl.fast_fwd_smem_bytes, st, d, W, in, fa.b_img, d.row0, fa.bs_w1, fa.bs_b1, d.B, aa);
     }
     return check_cuda("k_exchange_fwd_fast<attn>");
 }
@@ -995,6 +998,76 @@ int mmg_train_step_staged(const mmg_config* cfg, float* d_params, float* d_grads
     (void)d_params; (void)d_grads; (void)d_state1; (void)d_state2; (void)step; (void)d_workspace; (void)stream;
     return fail(MMG_ERR_UNSUPPORTED, "host-buffer entry point is not part of the emulation build");
 #endif
+}
+
+int mmg_sender_forward(const mmg_config* cfg, const float* d_params, int32_t rows, const float* d_x, const float* d_w,
+                       int32_t t, int32_t train, const double* d_u, const double* d_u_flip, uint64_t seed, uint64_t counter,
+                       float* d_msg, float* d_probs, float* d_h_x, void* stream) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!d_params || !d_x || !d_msg || !d_h_x || rows < 1) return fail(MMG_ERR_INVALID, "null pointer argument");
+    if (t != 0 && !d_w) return fail(MMG_ERR_INVALID, "Sender.forward at t > 0 needs the receiver's message w");
+    if (cfg->use_binary && !d_probs) return fail(MMG_ERR_INVALID, "d_probs required with use_binary");
+    const Dims d = make_dims(*cfg);
+    mmg_param_layout L;
+    param_layout(d, &L);
+    const ParamPtrs P = param_ptrs(L, d_params);
+    const int smem = sender_step_smem_floats(d) * 4;
+    if (smem > kMaxSmem) return fail(MMG_ERR_UNSUPPORTED, "img_feat_dim=%d too large for the single-turn sender kernel", d.F);
+    if ((rc = set_smem(k_sender_step, smem))) return rc;
+    MMG_LAUNCH(k_sender_step, rows, kSingleThreads, smem, (cudaStream_t)stream, d, P, d_x, d_w, (int)t, (int)train, d_u, d_u_flip,
+               (unsigned long long)seed, (unsigned long long)counter, d_msg, d_probs, d_h_x);
+    return check_cuda("k_sender_step");
+}
+
+int mmg_receiver_forward(const mmg_config* cfg, const float* d_params, int32_t rows, const float* d_z, const float* d_desc,
+                         const float* d_desc_set, const int32_t* d_desc_set_lens, float* d_h_z, float* d_s_prob_prod,
+                         int32_t first, int32_t train, const double* d_u_stop, const double* d_u_rec, const double* d_u_flip,
+                         uint64_t seed, uint64_t counter, float* d_s, float* d_s_prob, float* d_w, float* d_w_probs,
+                         float* d_y, float* d_h_w, void* stream) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!d_params || !d_z || !d_desc || !d_h_z || !d_s || !d_s_prob || !d_w || !d_y || !d_h_w || rows < 1)
+        return fail(MMG_ERR_INVALID, "null pointer argument");
+    if (!train && !d_s_prob_prod) return fail(MMG_ERR_INVALID, "eval mode needs d_s_prob_prod (model.py:423-427)");
+    if (cfg->use_binary && !d_w_probs) return fail(MMG_ERR_INVALID, "d_w_probs required with use_binary");
+    if (cfg->desc_attn && (!d_desc_set || !d_desc_set_lens)) return fail(MMG_ERR_INVALID, "desc_attn needs d_desc_set and d_desc_set_lens");
+    const Dims d = make_dims(*cfg);
+    mmg_param_layout L;
+    param_layout(d, &L);
+    const ParamPtrs P = param_ptrs(L, d_params);
+    ReceiverStepIO io;
+    io.z = d_z; io.desc = d_desc; io.desc_set = d_desc_set; io.desc_set_lens = d_desc_set_lens; io.h_z = d_h_z;
+    io.s_prob_prod = d_s_prob_prod; io.u_stop = d_u_stop; io.u_rec = d_u_rec; io.u_flip = d_u_flip;
+    io.s = d_s; io.s_prob = d_s_prob; io.w = d_w; io.w_probs = d_w_probs; io.y = d_y; io.h_w = d_h_w;
+    io.first = first; io.train = train; io.seed = seed; io.counter = counter;
+    const int smem = receiver_step_smem_floats(d) * 4;
+    if (smem > kMaxSmem) return fail(MMG_ERR_UNSUPPORTED, "single-turn receiver kernel: %d bytes of shared memory", smem);
+    if ((rc = set_smem(k_receiver_step, smem))) return rc;
+    MMG_LAUNCH(k_receiver_step, rows, kSingleThreads, smem, (cudaStream_t)stream, d, P, io);
+    return check_cuda("k_receiver_step");
+}
+
+int mmg_baseline_forward(const mmg_config* cfg, const float* d_params, int32_t which, int32_t rows, const float* d_x,
+                         int32_t x_dim, const float* d_binary, int32_t binary_dim, const float* d_inp, int32_t inp_dim,
+                         float* d_out, void* stream) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!d_params || !d_out || rows < 1) return fail(MMG_ERR_INVALID, "null pointer argument");
+    if (which != MMG_SEG_BASELINE_SEN && which != MMG_SEG_BASELINE_REC) return fail(MMG_ERR_INVALID, "which=%d", which);
+    if ((x_dim > 0 && !d_x) || (binary_dim > 0 && !d_binary) || (inp_dim > 0 && !d_inp) || x_dim < 0 || binary_dim < 0 || inp_dim < 0)
+        return fail(MMG_ERR_INVALID, "piece pointer / width mismatch");
+    const Dims d = make_dims(*cfg);
+    mmg_param_layout L;
+    param_layout(d, &L);
+    const ParamPtrs P = param_ptrs(L, d_params);
+    const int w1 = which == MMG_SEG_BASELINE_SEN ? MMG_P_BS_L1_W : MMG_P_BR_L1_W;
+    if (x_dim + binary_dim + inp_dim != L.cols[w1])
+        return fail(MMG_ERR_INVALID, "input width %d != linear1 width %d", x_dim + binary_dim + inp_dim, L.cols[w1]);
+    const int smem = align4(L.cols[w1]) * 4;
+    MMG_LAUNCH(k_baseline_step, rows, kSingleThreads, smem, (cudaStream_t)stream, P.p[w1], P.p[w1 + 1], P.p[w1 + 2], P.p[w1 + 3], d.Hb,
+               d_x, (int)x_dim, d_binary, (int)binary_dim, d_inp, (int)inp_dim, d_out);
+    return check_cuda("k_baseline_step");
 }
 
 }  // extern "C"

@@ -20,6 +20,7 @@ struct Dims {
     // -desc_attn (model.py:344-410): A = attention width (0 = off), NW = words of all class descriptions.
     // y1.weight columns are [h_z ; desc] without and [desc ; h_z] with attention (model.py:408-410 vs 548).
     int A, NW, y1_hcol, y1_dcol;
+    int row0;     // global index of this rank's first batch row (Philox counters are keyed by the global row)
 };
 
 MMG_HOST_DEVICE Dims make_dims(const mmg_config& c) {
@@ -38,6 +39,7 @@ MMG_HOST_DEVICE Dims make_dims(const mmg_config& c) {
     d.A = c.desc_attn ? c.desc_attn_dim : 0; d.NW = c.desc_attn ? c.n_words : 0;
     d.y1_hcol = d.A ? d.WV : 0; d.y1_dcol = d.A ? 0 : d.Hr;
     d.NH = 2 * d.Hr + 1 + d.A;
+    d.row0 = c.batch_offset;
     return d;
 }
 

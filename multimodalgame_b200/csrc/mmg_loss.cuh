@@ -197,7 +197,6 @@ k_stats(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, PeerView pv) {
         W.stats[stat_scalar(d, 1)] = c;
         W.stats[stat_scalar(d, 2)] = 0.0;
         W.stats[stat_scalar(d, 3)] = 0.0;
-        if (in.train && in.u_sen == nullptr) W.rng_state[1] += 1ull;   // next iteration draws a fresh Philox stream
     }
     // ---- batch statistics per (loss kind, step): one warp per quantity ------------------------------------------
     // kind 0: sender messages  (baseline bs[t], mask s_masks[t])      model.py:1258,1291

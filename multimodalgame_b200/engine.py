@@ -20,7 +20,7 @@ def make_config(batch, n_classes, img_feat_dim=4096, img_h_dim=100, baseline_hid
                 entropy_s=None, entropy_sen=None, entropy_rec=None, first_rec=0.0, s_prob_prod=True,
                 learning_rate=1e-4, optim_type="RMSprop", ignore_receiver=False, batch_global=None, max_norm=1.0,
                 flipout_sen=None, flipout_rec=None, flipout_dev=False, sender_mix="sum", ignore_code=False,
-                desc_attn=False, desc_attn_dim=64, n_words=0):
+                desc_attn=False, desc_attn_dim=64, n_words=0, batch_offset=0):
     """Build the C config from reference flag names/defaults (model.py:1641-1741)."""
     assert sender_out_dim == rec_w_dim, \
         "Both sender and receiver should communicate with same dim vectors for now."   # model.py:1756
@@ -47,6 +47,7 @@ def make_config(batch, n_classes, img_feat_dim=4096, img_h_dim=100, baseline_hid
     c.sender_mix, c.ignore_code = capi.SENDER_MIX[sender_mix], int(bool(ignore_code))
     c.desc_attn = int(bool(desc_attn))                                                               # model.py:1719-1720
     c.desc_attn_dim, c.n_words = (int(desc_attn_dim), int(n_words)) if desc_attn else (0, 0)
+    c.batch_offset = int(batch_offset)      # rank * batch in a data-parallel run: the sampler is keyed by the global row
     return c
 
 
@@ -230,9 +231,22 @@ class GameEngine(object):
         hp["n"] += 1
         hp["pending"] = slot
 
-    def train_step_staged(self, h_losses, slot):
-        """Train on staging slot `slot` (its prefetch was enqueued earlier); loss values land in pinned `h_losses`."""
+    def train_step_staged(self, h_losses, slot, dp_group=None):
+        """Train on staging slot `slot` (its prefetch was enqueued earlier); loss values land in pinned `h_losses`.
+        Data-parallel engines (enable_peer_dp, or `dp_group` for the NCCL variant) run their own iteration on the slot."""
         hp = self._hp
+        if getattr(self, "_peers", None) is not None or dp_group is not None:
+            st = torch.cuda.current_stream(self.device)
+            st.wait_event(hp["ready"][slot])
+            if dp_group is not None:
+                self._inp = hp["inp"][slot]
+                self._dp_iteration(dp_group)
+            else:
+                self._peer_iteration(hp["inp"][slot])
+            hp["free"][slot].record(st)
+            hp["used"][slot] = True
+            h_losses.copy_(self.ws("losses", (capi.MMG_LOSS_COUNT,)), non_blocking=True)
+            return
         self.step += 1
         s2 = None if self.state2 is None else self.state2.data_ptr()
         hp["free"][slot].record(torch.cuda.current_stream(self.device))
@@ -274,10 +288,13 @@ class GameEngine(object):
         """Data-parallel iteration: this rank's batch shard; batch statistics and gradients are summed across the ranks
         inside the kernels over NVLink peer memory (mmg_train_step_peer)."""
         self._inp = self._inputs(x, desc, target, True, uniforms, None, None, top_k)
+        self._peer_iteration(self._inp)
+
+    def _peer_iteration(self, inp):
         self.step += 1
         s2 = None if self.state2 is None else self.state2.data_ptr()
         self.lib.call("mmg_train_step_peer", C.byref(self.cfg), self.params.data_ptr(), self.grads.data_ptr(),
-                      self.state1.data_ptr(), s2, C.c_int64(self.step), C.byref(self._inp), self.workspace.data_ptr(),
+                      self.state1.data_ptr(), s2, C.c_int64(self.step), C.byref(inp), self.workspace.data_ptr(),
                       C.byref(self._peers), self._stream())
 
     def peer_error(self):
@@ -287,8 +304,13 @@ class GameEngine(object):
     def train_step_dp(self, x, desc, target, group=None, uniforms=None, top_k=6):
         """Data-parallel iteration: this rank's batch shard; batch statistics and gradients are all-reduced
         (SURVEY.md §8e).  Two collectives per iteration: a few hundred doubles, then the flat gradient buffer."""
+        self._inp = self._inputs(x, desc, target, True, uniforms, None, None, top_k)
+        self._dp_iteration(group)
+
+    def _dp_iteration(self, group):
         import torch.distributed as dist
-        self.forward(x, desc, target, True, uniforms, None, None, top_k)
+        self.lib.call("mmg_exchange_forward", C.byref(self.cfg), self.params.data_ptr(), C.byref(self._inp),
+                      self.workspace.data_ptr(), self._stream())
         self.loss(0)
         dist.all_reduce(self.stats(), group=group)
         self.loss(1)

@@ -25,6 +25,7 @@ import ctypes as C
 import math
 import os
 import sys
+import weakref
 
 import numpy as np
 import torch
@@ -43,6 +44,13 @@ except ImportError:  # pragma: no cover
 FLAGS = gflags.FLAGS
 
 _LIB_OVERRIDE = None   # tests hand the emulated build in here; the product never sets it
+_SAMPLER_SEED = [0]    # key of the on-device Philox sampler (the reference seeds nothing: np.random global state)
+
+
+def set_sampler_seed(seed):
+    """Seed of the on-device Bernoulli / flipout sampler used by every engine created afterwards (and by the single-turn
+    module forwards).  Data-parallel ranks use the SAME seed: their draws differ through the global row index."""
+    _SAMPLER_SEED[0] = int(seed) & 0xFFFFFFFFFFFFFFFF
 
 
 def _flag(name, default=None):
@@ -203,10 +211,12 @@ class Sender(nn.Module):
         self.h_x = None
         self.attn_scores = []
 
-    def forward(self, x, w, g, t):
-        """One sender turn (model.py:144-238): (message, probs-or-None).  Runs the fused kernels for a single step;
-        no autograd history (training goes through `exchange()` / `train_step()`)."""
-        return _single_sender_step(self, x, w, t)
+    def forward(self, x, w, g, t, uniforms=None):
+        """One sender turn (model.py:144-238): (message, probs-or-None); sets `self.h_x` (model.py:195).  Runs the
+        stand-alone single-turn kernel (`mmg_sender_forward`); the result carries no autograd history (training goes
+        through `exchange()` / `train_step()`).  `g` (visual-attention context) must be None on this path.
+        `uniforms` (optional, (B,M) float64 [, flipout (B,M)]) replaces the on-device sampler by injected draws."""
+        return _single_sender_step(self, x, w, g, t, uniforms)
 
 
 class Receiver(nn.Module):
@@ -255,9 +265,11 @@ class Receiver(nn.Module):
     def initial_state(self, batch_size):
         return torch.zeros(batch_size, self.hid_dim, device=self.rnn.weight_ih.device)
 
-    def forward(self, z, desc, desc_set=None, desc_set_lens=None):
-        """One receiver turn (model.py:303-477): ((s, s_prob), (w, w_probs), y); updates `h_z`."""
-        return _single_receiver_step(self, z, desc)
+    def forward(self, z, desc, desc_set=None, desc_set_lens=None, uniforms=None):
+        """One receiver turn (model.py:303-477): ((s, s_prob), (w, w_probs), y); updates `h_z`, `h_w` and (eval mode)
+        `s_prob_prod` like the reference module.  Stand-alone single-turn kernel (`mmg_receiver_forward`), no autograd
+        history.  `uniforms` (optional): (u_stop (B,1), u_rec (B,M) [, flipout (B,M)]) float64 injected draws."""
+        return _single_receiver_step(self, z, desc, desc_set, desc_set_lens, uniforms)
 
 
 class Baseline(nn.Module):
@@ -270,7 +282,9 @@ class Baseline(nn.Module):
         self.linear2 = nn.Linear(self.hid_dim, 1)
 
     def forward(self, x, binary, inp):
-        _unsupported("calling a Baseline outside exchange() (its forward is fused into the exchange kernels)")
+        """model.py:496-516: linear2(relu(linear1(cat(x, binary, inp)))) for whichever pieces are not None.  Stand-alone
+        kernel (`mmg_baseline_forward`), no autograd history (inside `exchange()` the baselines are fused GEMM tiles)."""
+        return _single_baseline_step(self, x, binary, inp)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -279,9 +293,9 @@ class Baseline(nn.Module):
 class _Binding(object):
     """One engine per (modules, batch, classes, flags); module parameters become views of the flat buffer."""
 
-    def __init__(self, mods, B, D, device, batch_global=None, n_words=0):
+    def __init__(self, mods, B, D, device, batch_global=None, n_words=0, batch_offset=0):
         s, r = mods["sender"], mods["receiver"]
-        cfg = _engine.make_config(
+        cfg = _engine.make_config(batch_offset=batch_offset, 
             batch=B, n_classes=D, img_feat_dim=s.feat_dim, img_h_dim=s.h_dim, baseline_hid_dim=mods["baseline_sen"].hid_dim
             if mods.get("baseline_sen") is not None else int(_flag("baseline_hid_dim", 500)),
             sender_out_dim=s.bin_dim_out, rec_hidden=r.hid_dim, rec_w_dim=r.w_dim, wv_dim=r.desc_dim,
@@ -294,11 +308,15 @@ class _Binding(object):
             flipout_dev=bool(_flag("flipout_dev", False)), sender_mix=_flag("sender_mix", "sum"),
             ignore_code=bool(_flag("ignore_code", False)), desc_attn=getattr(r, "desc_attn", False),
             desc_attn_dim=getattr(r, "attn_dim", 0), n_words=n_words)
-        self.engine = _engine.GameEngine(cfg, device=device, lib=_LIB_OVERRIDE)
+        self.engine = _engine.GameEngine(cfg, device=device, lib=_LIB_OVERRIDE, seed=_SAMPLER_SEED[0])
         self.words_key = None
-        self.mods = mods
+        self._mods = {a: (None if m is None else weakref.ref(m)) for a, m in mods.items()}   # engines must not keep modules alive
         self.key = None
         self.rebind()
+
+    @property
+    def mods(self):
+        return {a: (None if r is None else r()) for a, r in self._mods.items()}
 
     def rebind(self):
         views = self.engine.named_views()
@@ -323,9 +341,36 @@ class _Binding(object):
 
 
 _BINDINGS = {}
+_LAST_BINDING = {}     # module set -> the binding that trained last: owner of the freshest optimizer state
 
 
-def _binding_for(sender, receiver, baseline_sen, baseline_rec, B, D, device, batch_global=None, exchange_args=None):
+def _mods_key(sender, receiver, baseline_sen, baseline_rec):
+    return (id(sender), id(receiver), id(baseline_sen), id(baseline_rec))
+
+
+def _drop_bindings(mkey):
+    for k in [k for k in _BINDINGS if k[:4] == mkey]:
+        del _BINDINGS[k]
+    _LAST_BINDING.pop(mkey, None)
+
+
+def _adopt_state(dst, src):
+    """The fused optimizer state (RMSprop / Adam moments, step counts) does not depend on the batch size: an engine created
+    for another batch size or flag value of the SAME modules continues from the state of the engine that trained last
+    instead of starting from zero."""
+    a, b = dst.engine, src.engine
+    if a is b or int(a.layout.total) != int(b.layout.total) or int(a.cfg.optim_type) != int(b.cfg.optim_type):
+        return
+    with torch.no_grad():
+        a.state1.copy_(b.state1)
+        if a.state2 is not None and b.state2 is not None:
+            a.state2.copy_(b.state2)
+        a.ws("opt_counters", (4,), torch.int64).copy_(b.ws("opt_counters", (4,), torch.int64))
+    a.step = b.step
+
+
+def _binding_for(sender, receiver, baseline_sen, baseline_rec, B, D, device, batch_global=None, exchange_args=None,
+                 batch_offset=0):
     """One engine per shape/flag combination.  With -desc_attn the word set of the class descriptions
     (exchange_args["desc_set"], ["desc_set_lens"], model.py:765-766) belongs to the binding: its size is part of the
     configuration and the words are uploaded once per distinct set (train / dev sets differ)."""
@@ -336,7 +381,7 @@ def _binding_for(sender, receiver, baseline_sen, baseline_rec, B, D, device, bat
         if desc_set is None or lens is None:
             raise ValueError("-desc_attn needs exchange_args['desc_set'] and ['desc_set_lens']")
         n_words = int(desc_set.shape[0])
-    b = _binding_lookup(sender, receiver, baseline_sen, baseline_rec, B, D, device, batch_global, n_words)
+    b = _binding_lookup(sender, receiver, baseline_sen, baseline_rec, B, D, device, batch_global, n_words, batch_offset)
     if n_words:
         wk = (id(desc_set), int(desc_set.data_ptr()) if torch.is_tensor(desc_set) else 0, tuple(int(v) for v in lens))
         if b.words_key != wk:
@@ -345,19 +390,28 @@ def _binding_for(sender, receiver, baseline_sen, baseline_rec, B, D, device, bat
     return b
 
 
-def _binding_lookup(sender, receiver, baseline_sen, baseline_rec, B, D, device, batch_global, n_words):
-    key = (id(sender), id(receiver), id(baseline_sen), id(baseline_rec), int(B), int(D), str(device),
+def _binding_lookup(sender, receiver, baseline_sen, baseline_rec, B, D, device, batch_global, n_words, batch_offset=0):
+    mkey = _mods_key(sender, receiver, baseline_sen, baseline_rec)
+    # every flag that reaches mmg_config is part of the key: a changed flag never reuses a stale configuration
+    key = mkey + (int(B), int(D), str(device),
            int(_flag("max_exchange", 3)), bool(_flag("fixed_exchange", True)), _flag("entropy_s"), _flag("entropy_sen"),
            _flag("entropy_rec"), _flag("optim_type", "RMSprop"), float(_flag("learning_rate", 1e-4)), batch_global,
            _flag("flipout_sen"), _flag("flipout_rec"), bool(_flag("flipout_dev", False)), _flag("sender_mix", "sum"),
-           bool(_flag("ignore_code", False)), n_words)
+           bool(_flag("ignore_code", False)), n_words, float(_flag("first_rec", 0) or 0), bool(_flag("ignore_receiver", False)),
+           bool(_flag("s_prob_prod", True)), int(_flag("baseline_hid_dim", 500)), bool(sender.use_binary), int(batch_offset),
+           _SAMPLER_SEED[0])
     b = _BINDINGS.get(key)
     if b is None:
         mods = dict(receiver=receiver, sender=sender, baseline_rec=baseline_rec, baseline_sen=baseline_sen)
-        b = _Binding(mods, B, D, device, batch_global, n_words)
+        b = _Binding(mods, B, D, device, batch_global, n_words, batch_offset)
+        if not any(k[:4] == mkey for k in _BINDINGS):
+            weakref.finalize(sender, _drop_bindings, mkey)      # engines die with their modules
         _BINDINGS[key] = b
     else:
         b.rebind()
+    last = _LAST_BINDING.get(mkey)
+    if last is not None and last is not b:
+        _adopt_state(b, last)
     return b
 
 
@@ -669,8 +723,11 @@ def train_step(sender, receiver, baseline_sen, baseline_rec, exchange_args, grou
     if group is not None:
         import torch.distributed as dist
         world = dist.get_world_size(group)
+    rank = dist.get_rank(group) if world > 1 else 0
     binding = _binding_for(sender, receiver, baseline_sen, baseline_rec, data.shape[0], desc.shape[0], dev,
-                           batch_global=data.shape[0] * world if world > 1 else None, exchange_args=exchange_args)
+                           batch_global=data.shape[0] * world if world > 1 else None, exchange_args=exchange_args,
+                           batch_offset=rank * data.shape[0])
+    _LAST_BINDING[_mods_key(sender, receiver, baseline_sen, baseline_rec)] = binding
     e = binding.engine
     top_k = min(int(_flag("top_k_train", 6)), desc.shape[0])
     if world > 1:
@@ -684,14 +741,143 @@ def train_step(sender, receiver, baseline_sen, baseline_rec, exchange_args, grou
 # ------------------------------------------------------------------------------------------------------------
 # single-turn module forwards (no autograd): one-step conversations through the same kernels
 # ------------------------------------------------------------------------------------------------------------
-def _single_sender_step(sender, x, w, t):
-    _unsupported("Sender.forward outside exchange() (use exchange() / train_step(); single-turn entry points are "
-                 "SURVEY.md §8f work)")
+class _ModuleFlat(object):
+    """Flat parameter buffer (the C-ABI's layout) of ONE stand-alone module: the single-turn entry points read the
+    module's tensors from it; the other modules' slots stay zero and are never read."""
+
+    def __init__(self, module, agent, dims):
+        self.lib = _LIB_OVERRIDE if _LIB_OVERRIDE is not None else capi.load()
+        self.agent = agent
+        self.cfg = _engine.make_config(batch=1, **dims)
+        self.layout = capi.ParamLayout()
+        self.lib.call("mmg_param_layout_get", C.byref(self.cfg), C.byref(self.layout))
+        self.device = _device_of(module)
+        self.flat = torch.zeros(int(self.layout.total), dtype=torch.float32, device=self.device)
+        self.slots = {}
+        for idx, (a, key) in enumerate(capi.PARAM_NAMES):
+            n = int(self.layout.rows[idx]) * int(self.layout.cols[idx])
+            if a == agent and n:
+                off = int(self.layout.offset[idx])
+                self.slots[key] = self.flat[off:off + n]
+        self.counter = 0
+
+    def refresh(self, module):
+        with torch.no_grad():
+            for key, p in module.named_parameters():
+                self.slots[key].copy_(p.detach().reshape(-1))
+
+    def stream(self):
+        if self.device.type == "cuda":
+            return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return C.c_void_p(0)
 
 
-def _single_receiver_step(receiver, z, desc):
-    _unsupported("Receiver.forward outside exchange() (use exchange() / train_step(); single-turn entry points are "
-                 "SURVEY.md §8f work)")
+def _flat_for(module, agent, dims):
+    key = tuple(sorted(dims.items()))
+    mf = module.__dict__.get("_mmg_flat")
+    if mf is None or mf[0] != key or mf[1].device != _device_of(module):
+        mf = (key, _ModuleFlat(module, agent, dims))
+        module.__dict__["_mmg_flat"] = mf
+    mf[1].refresh(module)
+    return mf[1]
+
+
+def _f32(t, dev):
+    return None if t is None else torch.as_tensor(t).detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+def _f64(t, dev):
+    return None if t is None else torch.as_tensor(t).detach().to(device=dev, dtype=torch.float64).contiguous()
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _flip_flags():
+    return dict(flipout_sen=_flag("flipout_sen"), flipout_rec=_flag("flipout_rec"), flipout_dev=bool(_flag("flipout_dev", False)))
+
+
+def _single_sender_step(sender, x, w, g, t, uniforms=None):
+    if g is not None:
+        _unsupported("data_context (visual attention)")
+    mf = _flat_for(sender, "sender", dict(
+        n_classes=1, img_feat_dim=sender.feat_dim, img_h_dim=sender.h_dim, sender_out_dim=sender.bin_dim_out,
+        rec_w_dim=sender.bin_dim_out, rec_hidden=1, wv_dim=1, baseline_hid_dim=1, use_binary=bool(sender.use_binary),
+        sender_mix=_flag("sender_mix", "sum"), ignore_code=bool(_flag("ignore_code", False)), **_flip_flags()))
+    dev = mf.device
+    xx = _f32(x, dev)
+    B, M = xx.shape[0], sender.bin_dim_out
+    ww = _f32(w, dev) if t != 0 else None
+    us = [_f64(u, dev) for u in (uniforms or ())] + [None, None]
+    msg = torch.empty(B, M, device=dev)
+    probs = torch.empty(B, M, device=dev) if sender.use_binary else None
+    h_x = torch.empty(B, sender.h_dim, device=dev)
+    mf.counter += 1
+    mf.lib.call("mmg_sender_forward", C.byref(mf.cfg), mf.flat.data_ptr(), B, _ptr(xx), _ptr(ww), int(t), int(sender.training),
+                _ptr(us[0]), _ptr(us[1]), C.c_uint64(_SAMPLER_SEED[0]), C.c_uint64(2 * mf.counter),
+                _ptr(msg), _ptr(probs), _ptr(h_x), mf.stream())
+    sender.h_x = h_x
+    return msg, probs
+
+
+def _single_receiver_step(receiver, z, desc, desc_set=None, desc_set_lens=None, uniforms=None):
+    attn = bool(getattr(receiver, "desc_attn", False))
+    n_words = int(desc_set.shape[0]) if attn else 0
+    if attn and (desc_set is None or desc_set_lens is None):
+        raise ValueError("-desc_attn needs desc_set and desc_set_lens")
+    mf = _flat_for(receiver, "receiver", dict(
+        n_classes=int(desc.shape[0]), img_feat_dim=1, img_h_dim=1, sender_out_dim=receiver.w_dim, rec_w_dim=receiver.w_dim,
+        rec_hidden=receiver.hid_dim, wv_dim=receiver.desc_dim, baseline_hid_dim=1, use_binary=bool(receiver.use_binary),
+        s_prob_prod=bool(_flag("s_prob_prod", True)), ignore_receiver=bool(_flag("ignore_receiver", False)),
+        desc_attn=attn, desc_attn_dim=getattr(receiver, "attn_dim", 0), n_words=n_words, **_flip_flags()))
+    dev = mf.device
+    zz, dd = _f32(z, dev), _f32(desc, dev)
+    B, M, Hr, D = zz.shape[0], receiver.w_dim, receiver.hid_dim, dd.shape[0]
+    first = receiver.h_z is None                                   # model.py:336-337
+    h_z = torch.zeros(B, Hr, device=dev) if first else _f32(receiver.h_z, dev).clone()
+    train = bool(receiver.training)
+    sprod, first_prod = None, True
+    if not train:
+        first_prod = receiver.s_prob_prod is None                   # model.py:423
+        sprod = torch.zeros(B, device=dev) if first_prod else _f32(receiver.s_prob_prod, dev).reshape(B).clone()
+    ds = _f32(desc_set, dev) if attn else None
+    dl = torch.as_tensor([int(v) for v in desc_set_lens], dtype=torch.int32, device=dev) if attn else None
+    us = [_f64(u, dev) for u in (uniforms or ())] + [None, None, None]
+    s, s_prob = torch.empty(B, 1, device=dev), torch.empty(B, 1, device=dev)
+    wv = torch.empty(B, M, device=dev)
+    w_probs = torch.empty(B, M, device=dev) if receiver.use_binary else None
+    y, h_w = torch.empty(B, D, device=dev), torch.empty(B, Hr, device=dev)
+    mf.counter += 1
+    # `first` also resets the running STOP product: both states are cleared together by reset_state() (model.py:290-298)
+    mf.lib.call("mmg_receiver_forward", C.byref(mf.cfg), mf.flat.data_ptr(), B, _ptr(zz), _ptr(dd), _ptr(ds), _ptr(dl),
+                _ptr(h_z), _ptr(sprod), int(first and first_prod), int(train), _ptr(us[0]), _ptr(us[1]), _ptr(us[2]),
+                C.c_uint64(_SAMPLER_SEED[0]), C.c_uint64(2 * mf.counter + 1), _ptr(s), _ptr(s_prob), _ptr(wv),
+                _ptr(w_probs), _ptr(y), _ptr(h_w), mf.stream())
+    receiver.h_z, receiver.h_w = h_z, h_w
+    if not train:
+        receiver.s_prob_prod = sprod.view(B, 1)
+    return (s, s_prob), (wv, w_probs), y
+
+
+def _single_baseline_step(baseline, x, binary, inp):
+    which = 3 if baseline.x_dim > 0 else 2            # MMG_SEG_BASELINE_SEN: [h_x ; z_r]; MMG_SEG_BASELINE_REC: [z ; h_z]
+    if which == 3:
+        dims = dict(img_h_dim=baseline.x_dim, sender_out_dim=baseline.binary_dim, rec_w_dim=baseline.binary_dim, rec_hidden=1)
+        if baseline.inp_dim:
+            _unsupported("Baseline with all three inputs (the game only builds (x, binary) and (binary, inp) baselines)")
+    else:
+        dims = dict(img_h_dim=1, sender_out_dim=baseline.binary_dim, rec_w_dim=baseline.binary_dim, rec_hidden=baseline.inp_dim)
+    mf = _flat_for(baseline, "baseline_sen" if which == 3 else "baseline_rec",
+                   dict(n_classes=1, img_feat_dim=1, wv_dim=1, baseline_hid_dim=baseline.hid_dim, **dims))
+    dev = mf.device
+    xx, bb, ii = _f32(x, dev), _f32(binary, dev), _f32(inp, dev)
+    rows = next(t for t in (xx, bb, ii) if t is not None).shape[0]
+    out = torch.empty(rows, 1, device=dev)
+    width = lambda t: 0 if t is None else int(t.shape[1])
+    mf.lib.call("mmg_baseline_forward", C.byref(mf.cfg), mf.flat.data_ptr(), which, rows, _ptr(xx), width(xx), _ptr(bb), width(bb),
+                _ptr(ii), width(ii), _ptr(out), mf.stream())
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------

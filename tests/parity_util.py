@@ -4,22 +4,13 @@ loss, gradient and post-step parameter with the CPU oracle (oracle/game_oracle.p
 import numpy as np
 import torch
 
-from multimodalgame_b200 import capi, engine as eng
+from multimodalgame_b200 import capi, engine as eng, synthetic as syn
 from oracle import game_oracle as go
 from tests import golden_util as gu
 
 
-def config_from(cfg, B=None, batch_global=None, n_words=0):
-    return eng.make_config(
-        batch=B or cfg.batch_size, n_classes=cfg.n_classes, img_feat_dim=cfg.img_feat_dim, img_h_dim=cfg.img_h_dim,
-        baseline_hid_dim=cfg.baseline_hid_dim, sender_out_dim=cfg.sender_out_dim, rec_hidden=cfg.rec_hidden,
-        rec_w_dim=cfg.rec_w_dim, wv_dim=cfg.wv_dim, max_exchange=cfg.max_exchange, fixed_exchange=cfg.fixed_exchange,
-        use_binary=cfg.use_binary, entropy_s=cfg.entropy_s, entropy_sen=cfg.entropy_sen, entropy_rec=cfg.entropy_rec,
-        first_rec=cfg.first_rec, s_prob_prod=cfg.s_prob_prod, learning_rate=cfg.learning_rate,
-        optim_type=cfg.optim_type, ignore_receiver=cfg.ignore_receiver, batch_global=batch_global,
-        flipout_sen=getattr(cfg, "flipout_sen", None), flipout_rec=getattr(cfg, "flipout_rec", None),
-        sender_mix=getattr(cfg, "sender_mix", "sum"), ignore_code=getattr(cfg, "ignore_code", False),
-        desc_attn=getattr(cfg, "desc_attn", False), desc_attn_dim=getattr(cfg, "desc_attn_dim", 64), n_words=n_words)
+def config_from(cfg, B=None, batch_global=None, n_words=0, batch_offset=0):
+    return syn.config_from_flags(cfg, batch=B, batch_global=batch_global, n_words=n_words, batch_offset=batch_offset)
 
 
 def stack_uniforms(us, cfg, B):

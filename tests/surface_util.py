@@ -41,11 +41,14 @@ def set_flags(cfg):
         argv += ["-desc_attn", "-desc_attn_dim", str(cfg.desc_attn_dim)]
     else:
         argv.append("-nodesc_attn")
-    for name in ("entropy_s", "entropy_sen", "entropy_rec"):
-        if getattr(cfg, name) is not None:
+    for name in ("entropy_s", "entropy_sen", "entropy_rec", "flipout_sen", "flipout_rec"):
+        if getattr(cfg, name, None) is not None:
             argv += ["-" + name, repr(getattr(cfg, name))]
+    argv += ["-sender_mix", getattr(cfg, "sender_mix", "sum")]
+    argv.append("-ignore_code" if getattr(cfg, "ignore_code", False) else "-noignore_code")
+    argv.append("-ignore_receiver" if getattr(cfg, "ignore_receiver", False) else "-noignore_receiver")
     M.FLAGS.unparse_flags()
-    for name in ("entropy_s", "entropy_sen", "entropy_rec"):
+    for name in ("entropy_s", "entropy_sen", "entropy_rec", "flipout_sen", "flipout_rec"):
         M.FLAGS[name].value = None
     M.FLAGS(argv)
     M.default_flags(argv)
@@ -260,7 +263,7 @@ def run_checkpoint_roundtrip(case, device, tmpdir):
     params = gu.params_at(z, "P0")
 
     def fresh():
-        M._BINDINGS.clear()
+        M._BINDINGS.clear(); M._LAST_BINDING.clear()
         mods = build_modules(cfg, params, device)
         return mods
 
@@ -292,3 +295,65 @@ def run_checkpoint_roundtrip(case, device, tmpdir):
     for k, m in c.items():
         for n, p in m.named_parameters():
             assert torch.equal(p.detach().cpu(), want[k][n]), (k, n)
+
+
+def run_single_turn_case(case, device, train=True):
+    """Sender.forward / Receiver.forward / Baseline.forward driven turn by turn exactly as the reference's exchange() loop
+    does (model.py:801-867), against the oracle's conversation on the same inputs and injected uniforms."""
+    z, cfg = gu.load(case)
+    set_flags(cfg)
+    params = gu.params_at(z, "P0")
+    full = go.init_params(cfg, seed=1)
+    for a in full:
+        if a not in params:
+            params[a] = full[a]
+    mods = build_modules(cfg, params, device)
+    sender, receiver = mods["sender"], mods["receiver"]
+    if "iters" in z.files:
+        x, desc, target = gu.batch_at(z, 0)
+        us = gu.uniforms_at(z, 0, cfg) if train else None
+        words = gu.desc_set_at(z, 0)
+    else:                                     # eval fixtures store one batch
+        x, desc, target = torch.from_numpy(z["x"]), torch.from_numpy(z["desc"]), torch.from_numpy(z["target"])
+        us, words = None, {}
+        if "desc_set" in z.files:
+            words = dict(desc_set=torch.from_numpy(z["desc_set"]), desc_set_lens=[int(v) for v in z["desc_set_lens"]])
+    if train and us is None:
+        us = go.draw_uniforms(np.random.RandomState(5), cfg)
+    ex = go.exchange(go.clone_params(params), x, desc, cfg, train, uniforms=us, break_early=not cfg.fixed_exchange, **words)
+    for m in mods.values():
+        m.train() if train else m.eval()
+    sender.reset_state(); receiver.reset_state()
+    B = x.shape[0]
+    xd, dd = x.to(device), desc.to(device)
+    w = torch.full((B, cfg.rec_w_dim), float(cfg.first_rec), device=device)            # model.py:786
+    wkw = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in words.items()}
+    for t in range(len(ex["y"])):
+        u = [None if a is None else torch.from_numpy(np.asarray(a, dtype=np.float64)) for a in us[t]] if train else [None] * 5
+        u = u + [None] * (5 - len(u))
+        z_r = w
+        zb, zp = sender.forward(xd, z_r, None, t, uniforms=(u[0], u[3]) if train else None)
+        (s, sp), (w, wp), y = receiver.forward(zb, dd, uniforms=(u[1], u[2], u[4]) if train else None, **wkw)
+        tag = "%s/t%d/" % (case, t)
+        npy = lambda v: v.detach().cpu().numpy()
+        pu.assert_close(tag + "y", npy(y), ex["y"][t].detach().numpy())
+        pu.assert_close(tag + "s_prob", npy(sp), ex["stop_prob"][t].detach().numpy())
+        pu.assert_close(tag + "h_x", npy(sender.h_x), ex["h_x"].detach().numpy())
+        pu.assert_close(tag + "h_z", npy(receiver.h_z), ex["h_z"][t].detach().numpy())
+        pu.assert_close(tag + "h_w", npy(receiver.h_w), ex["h_w"][t].detach().numpy())
+        if cfg.use_binary:
+            pu.assert_close(tag + "sen_probs", npy(zp), ex["sen_probs"][t].detach().numpy())
+            pu.assert_close(tag + "rec_probs", npy(wp), ex["rec_probs"][t].detach().numpy())
+            assert np.array_equal(npy(zb), ex["sen_feats"][t].numpy()), tag + "sender bits"
+            assert np.array_equal(npy(w), ex["rec_feats"][t].numpy()), tag + "receiver bits"
+            assert np.array_equal(npy(s), ex["stop_feat"][t].numpy()), tag + "stop bits"
+        else:
+            assert zp is None and wp is None
+            pu.assert_close(tag + "sen_feats", npy(zb), ex["sen_feats"][t].detach().numpy())
+            pu.assert_close(tag + "rec_feats", npy(w), ex["rec_feats"][t].detach().numpy())
+        if train:
+            bs = mods["baseline_sen"].forward(sender.h_x, z_r, None)                    # model.py:835-836
+            br = mods["baseline_rec"].forward(None, zb, receiver.h_z)                   # model.py:842-843
+            pu.assert_close(tag + "bs", npy(bs), ex["bs"][t].detach().numpy())
+            pu.assert_close(tag + "br", npy(br), ex["br"][t].detach().numpy())
+    return len(ex["y"])
