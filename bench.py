@@ -227,65 +227,52 @@ def _claim_stdout():
     return os.fdopen(saved, "w")
 
 
-def dp_oracle_check(e, fl, cfgd, world, rank, dev, dist, step_fn):
-    """One data-parallel iteration with injected uniforms against the CPU oracle on the GLOBAL batch (rank 0 computes the
-    oracle; every rank compares its own shard).  Returns a summary dict; raises on a parity violation."""
+def dp_oracle_check(e, fl, cfgd, world, rank, dev, dist, step_on):
+    """One data-parallel iteration of the timed configuration (on-device sampler) against the CPU oracle on the GLOBAL batch:
+    the bits every rank drew are gathered and replayed through the oracle (u = 1 - bit reproduces the bit for any
+    probability); class scores, losses and post-step parameters must agree.  Rank 0 computes the oracle and raises on a
+    parity violation; returns a summary dict."""
     from oracle import game_oracle as go
     from multimodalgame_b200 import synthetic as syn
-    B, T, M = fl.batch_size, fl.max_exchange, fl.rec_w_dim
+    B, T = fl.batch_size, fl.max_exchange
 
     def close(what, got, want, tol=1e-4):
         got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
         err = float(np.max(np.abs(got - want) - tol * np.abs(want))) if got.size else 0.0
         assert err <= tol, "data-parallel check: %s off by %.3g (> %.0e)" % (what, err + tol, tol)
         return float(np.max(np.abs(got - want))) if got.size else 0.0
+
     gcfg = go.GameConfig(**dict(cfgd, batch_size=B * world))
     gfl = syn.GameFlags(**dict(cfgd, batch_size=B * world))
     params0 = {a: {k: v.detach().cpu().clone() for k, v in d_.items()} for a, d_ in e.named_views().items()}
     words = syn.desc_set(fl, seed=0)
-    seed = 7
-    for attempt in range(6):
-        x, desc, target = syn.batch(gfl, seed=500 + seed)
-        us = go.draw_uniforms(np.random.RandomState(seed), gcfg)
-        verdict = torch.zeros(1, dtype=torch.int32, device=dev)
-        ex = res = oparams = None
-        if rank == 0:
-            oparams = go.clone_params(params0)
-            ex, res = go.train_iteration(oparams, go.new_opt_state(oparams), x, target, desc, gcfg, us, **words)
-            gap = 1.0
-            for t in range(len(ex["y"])):
-                gap = min(gap, float(np.abs(us[t][0] - ex["sen_probs"][t].detach().numpy()).min()),
-                          float(np.abs(us[t][2] - ex["rec_probs"][t].detach().numpy()).min()),
-                          float(np.abs(us[t][1] - ex["stop_prob"][t].detach().numpy()).min()))
-            verdict[0] = 1 if gap > 1e-6 else 0          # a uniform within rounding distance of a probability: next seed
-        dist.broadcast(verdict, 0)
-        if int(verdict[0]) == 1:
-            break
-        seed += 1
-    else:
-        raise AssertionError("no seed with a sampling margin found for the data-parallel oracle check")
+    x, desc, target = syn.batch(gfl, seed=507)
     sl = slice(rank * B, (rank + 1) * B)
-    stacked = (torch.from_numpy(np.ascontiguousarray(np.stack([u[0][sl] for u in us], 0))),
-               torch.from_numpy(np.ascontiguousarray(np.stack([u[1][sl] for u in us], 0).reshape(T, B))),
-               torch.from_numpy(np.ascontiguousarray(np.stack([u[2][sl] for u in us], 0))))
-    step_fn(x[sl].to(dev), desc.to(dev), target[sl].to(dev), stacked)
+    step_on(x[sl].to(dev), desc.to(dev), target[sl].to(dev))
     torch.cuda.synchronize(dev)
-    out = {k: v.detach().cpu() for k, v in e.outputs().items()}
-    L = e.losses()
-    # every rank ships its shard's bits / scores to rank 0
-    sf, yy = out["sen_feats"].to(dev).contiguous(), out["y"].to(dev).contiguous()
-    gf = [torch.zeros_like(sf) for _ in range(world)]
-    gy = [torch.zeros_like(yy) for _ in range(world)]
-    dist.all_gather(gf, sf)
-    dist.all_gather(gy, yy)
+    o = e.outputs()
+    from multimodalgame_b200 import capi
+    lv = e.ws("losses", (capi.MMG_LOSS_COUNT,)).double().clone()
+    dist.all_reduce(lv)                        # every rank reports its contribution to the global means
+    L = dict(zip(capi.LOSS_NAMES, lv.cpu().tolist()))
+    gathered = {}
+    for key in ("sen_feats", "rec_feats", "stop_feat", "y"):
+        t = o[key].contiguous()
+        parts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        gathered[key] = torch.cat([p_.cpu() for p_ in parts], 1).numpy()
     summary = {}
     if rank == 0:
+        G = B * world
+        us = [(1.0 - gathered["sen_feats"][t].astype(np.float64), 1.0 - gathered["stop_feat"][t].astype(np.float64).reshape(G, 1),
+               1.0 - gathered["rec_feats"][t].astype(np.float64)) for t in range(T)]
+        oparams = go.clone_params(params0)
+        ex, res = go.train_iteration(oparams, go.new_opt_state(oparams), x, target, desc, gcfg, us, **words)
         Tp = len(ex["y"])
-        st = lambda key: np.stack([t.detach().numpy() for t in ex[key]], 0)
-        got_f = torch.cat([g.cpu() for g in gf], 1).numpy()[:Tp]
-        got_y = torch.cat([g.cpu() for g in gy], 1).numpy()[:Tp]
-        assert np.array_equal(got_f, st("sen_feats")), "data-parallel check: sender bits differ from the global-batch oracle"
-        summary["y_max_err"] = close("y", got_y, st("y"))
+        st = lambda key: np.stack([t_.detach().numpy() for t_ in ex[key]], 0)
+        assert np.array_equal(gathered["sen_feats"][:Tp], st("sen_feats")), "data-parallel check: replayed sender bits differ"
+        assert not np.array_equal(gathered["sen_feats"][:, :B], gathered["sen_feats"][:, B:2 * B]), "ranks drew identical noise"
+        summary["y_max_err"] = close("y", gathered["y"][:Tp], st("y"))
         for nm in ("nll_loss", "loss_rec", "loss_sen", "loss_bas_rec", "loss_bas_sen"):
             summary[nm + "_err"] = close(nm, L[nm], float(res[nm].detach()))
         pv = e.named_views()
@@ -298,8 +285,8 @@ def dp_oracle_check(e, fl, cfgd, world, rank, dev, dist, step_fn):
                 worst = max(worst, float((pv[a][k].detach().cpu() - v).abs().max()))
         assert worst <= 12 * lr, "data-parallel check: post-step parameters off by %.3g (> 12 lr)" % worst
         summary["param_max_err_over_lr"] = worst / lr
-        summary["seed"] = seed
-        summary["global_batch"] = B * world
+        summary["global_batch"] = G
+        summary["what"] = "1 iteration, on-device sampler, bits replayed through oracle/game_oracle.py on the global batch"
     return summary
 
 

@@ -289,27 +289,35 @@ int mmg_train_step_staged(const mmg_config* cfg, float* d_params, float* d_grads
 /* ---- data-parallel iteration over NVLink peer memory ----------------------------------------------------------------
  * New capability (the reference is single-process).  Each rank owns one SYMMETRIC buffer (peer-mapped on every other
  * rank, e.g. torch.distributed._symmetric_memory) holding, in this order:
- *   send   : float[param_layout.total]      this rank's local gradient (split-K reduced), read by every peer
+ *   send   : float[param_layout.total]      this rank's local gradient, read by every peer
+ *   recv   : float[param_layout.total]      the GLOBAL gradient: slice r is written here by rank r (two-shot reduction)
  *   stats  : double[workspace.stats_count]  this rank's batch statistics, read by every peer
- *   flags  : uint64[2][MMG_MAX_PEERS]       arrival counters written REMOTELY by the peers (row 0: statistics published,
- *                                           row 1: gradient published); value = training step, monotonic
- * No collective library call and no extra launch sits on the path: the producing kernels publish with a system-scope
- * fence + remote flag store, the consuming kernels spin on their LOCAL flag row and then read the peers' buffers
- * directly (rank order, so every rank computes bit-identical sums).  Waits are bounded; a timeout sets *d_error. */
+ *   norms  : double[MMG_MAX_PEERS][4]       per-module sums of squares of slice r of the global gradient, written by rank r
+ *   flags  : uint64[3][MMG_MAX_PEERS]       arrival counters written REMOTELY by the peers (row 0: statistics published,
+ *                                           row 1: send buffer published, row 2: reduced slice stored); value = training
+ *                                           step, monotonic
+ * No collective library call sits on the path: the producing kernels publish with a system-scope fence + remote flag store,
+ * the consuming kernels spin on their LOCAL flag row and then read the peers' buffers directly (rank order, so every rank
+ * computes bit-identical sums).  Gradient: rank r sums ITS 1/G slice over all send buffers and stores the result into every
+ * rank's recv buffer — (G-1)/G of a gradient in and out per rank over NVLink.  Waits are bounded (~15 s: ranks must run in
+ * lockstep within that window); a timeout sets *d_error, which is STICKY: later waits give up at once and the update kernel
+ * leaves parameters and optimizer state untouched, so the caller must poll it (GameEngine.peer_error()) and abort. */
 #define MMG_MAX_PEERS 8
 typedef struct mmg_peers {
     int32_t world, rank;
     float* d_send[MMG_MAX_PEERS];
+    float* d_recv[MMG_MAX_PEERS];
     double* d_stats[MMG_MAX_PEERS];
+    double* d_norms[MMG_MAX_PEERS];
     unsigned long long* d_flags[MMG_MAX_PEERS];
     int32_t* d_error;      /* local device int, set non-zero when a peer wait timed out */
 } mmg_peers;
-/* Bytes of the symmetric buffer and the offsets of its three sections. */
-int mmg_peer_buffer_layout(const mmg_config* cfg, int64_t* total_bytes, int64_t* send_off, int64_t* stats_off,
-                           int64_t* flags_off);
+/* Bytes of the symmetric buffer and the offsets of its five sections. */
+int mmg_peer_buffer_layout(const mmg_config* cfg, int64_t* total_bytes, int64_t* send_off, int64_t* recv_off, int64_t* stats_off,
+                           int64_t* norms_off, int64_t* flags_off);
 /* One training iteration on this rank's batch shard (cfg->batch rows of a global batch of cfg->batch_global rows):
  * mmg_train_step with the statistics and the gradient summed across `peers` in-kernel.  `d_grads` (local, not
- * symmetric) receives the global gradient; `step` must be identical on all ranks and increase by one per call. */
+ * symmetric) receives the clipped global gradient; `step` must be identical on all ranks and increase by one per call. */
 int mmg_train_step_peer(const mmg_config* cfg, float* d_params, float* d_grads, float* d_state1, float* d_state2,
                         int64_t step, const mmg_inputs* in, void* d_workspace, const mmg_peers* peers, void* stream);
 

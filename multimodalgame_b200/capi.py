@@ -79,7 +79,8 @@ MMG_MAX_PEERS = 8
 
 class Peers(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("d_send", C.c_void_p * MMG_MAX_PEERS),
-                ("d_stats", C.c_void_p * MMG_MAX_PEERS), ("d_flags", C.c_void_p * MMG_MAX_PEERS), ("d_error", C.c_void_p)]
+                ("d_recv", C.c_void_p * MMG_MAX_PEERS), ("d_stats", C.c_void_p * MMG_MAX_PEERS),
+                ("d_norms", C.c_void_p * MMG_MAX_PEERS), ("d_flags", C.c_void_p * MMG_MAX_PEERS), ("d_error", C.c_void_p)]
 
 
 class MmgError(RuntimeError):
@@ -119,7 +120,7 @@ class Library(object):
         d.mmg_host_prefetch.argtypes = [cfgp, vp, vp, vp, vp, vp, vp, vp]
         d.mmg_train_step_staged.argtypes = [cfgp, vp, vp, vp, vp, i64, inp, vp, vp, vp, vp, vp]
         i64p = C.POINTER(C.c_int64)
-        d.mmg_peer_buffer_layout.argtypes = [cfgp, i64p, i64p, i64p, i64p]
+        d.mmg_peer_buffer_layout.argtypes = [cfgp, i64p, i64p, i64p, i64p, i64p, i64p]
         d.mmg_train_step_peer.argtypes = [cfgp, vp, vp, vp, vp, i64, inp, vp, C.POINTER(Peers), vp]
         i32, u64 = C.c_int32, C.c_uint64
         d.mmg_sender_forward.argtypes = [cfgp, vp, i32, vp, vp, i32, i32, vp, vp, u64, u64, vp, vp, vp, vp]

@@ -173,8 +173,13 @@ static void ws_layout(const Dims& d, Ws* w) {
     w->wgrad_split = kWgradSplitMax;
     w->slabs = take(c, (int64_t)(kWgradSplitMax - 1) * L.total * f);
     w->norm_part = take(c, 4 * kNormCtasMax * f);
+    w->tile_norm = take(c, kMaxOutTiles * f);
+    w->tile_tickets = take(c, kMaxOutTiles * 4);
+    w->norm_final = take(c, 4 * 8);
+    w->hit = take(c, B * f);
+    w->coefs = take(c, (6 * d.T + 4) * f);
     w->loss_part = take(c, (int64_t)(2 * B > kLossCtasMax ? 2 * B : kLossCtasMax) * 8 * 8);   // K_lossgrad CTAs, or 2 CTAs per example (fused backward)
-    w->tickets = take(c, 8 * 4);
+    w->tickets = take(c, 16 * 4);
     w->opt_counters = take(c, 4 * 8);
     p.opt_counters = w->opt_counters;
     if (d.A) {
@@ -217,6 +222,11 @@ static WsPtrs resolve(const Ws& w, void* base) {
 #undef G_
     r.loss_part = (double*)(b + w.loss_part);
     r.tickets = (unsigned*)(b + w.tickets);
+    r.tile_norm = (float*)(b + w.tile_norm);
+    r.tile_tickets = (unsigned*)(b + w.tile_tickets);
+    r.norm_final = (double*)(b + w.norm_final);
+    r.hit = (float*)(b + w.hit);
+    r.coefs = (float*)(b + w.coefs);
     r.opt_counters = (long long*)(b + w.opt_counters);
 #define G_(name) r.name = (float*)(b + w.name)
     G_(wtab_dd); G_(wtab_y1); G_(wtab_wd); G_(qa); G_(attn); G_(dh_s); G_(ddh); G_(dva); G_(dba); G_(ddd_part);
@@ -365,7 +375,7 @@ static int launch_bwd(const Dims& d, const WsPtrs& W, const Plan& pl, cudaStream
     return check_cuda("k_exchange_bwd");
 }
 
-struct FastFwdArgs { const float* b_img; const float* bs_w1; const float* bs_b1; };
+struct FastFwdArgs { const float* b_img; const float* bs_w1; const float* bs_b1; int epilogue; };
 template <int BT, int M, bool SS, bool PERF>
 static int launch_fwd_fast_mode(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const FastFwdArgs& fa, const Plan& pl,
                                 cudaStream_t st) {
@@ -376,7 +386,7 @@ static int launch_fwd_fast_mode(const Dims& d, const WsPtrs& W, const ExchangeIn
     const int n_side = in.train ? cdiv(d.B, kTile) * cdiv(d.Hb, kTile) : 0;     // baseline pre-activation tiles
     AttnArgs none;
     memset(&none, 0, sizeof(none));
-    MMG_LAUNCH(kern, n_conv + n_side, kFastThreads, pl.fwd_smem_bytes, st, d, W, in, fa.b_img, d.row0, fa.bs_w1, fa.bs_b1, n_conv, none);
+    MMG_LAUNCH(kern, n_conv + n_side, kFastThreads, pl.fwd_smem_bytes, st, d, W, in, fa.b_img, d.row0, fa.bs_w1, fa.bs_b1, n_conv, none, fa.epilogue);
     return check_cuda("k_exchange_fwd_fast");
 }
 template <int BT, int M, bool SS>
@@ -406,11 +416,11 @@ static int launch_fwd_fast_attn(const Dims& d, const WsPtrs& W, const ExchangeIn
     if (perf) {
         auto kern = k_exchange_fwd_fast<1, 32, true, true, true>;
         if ((rc = set_smem(kern, pl.fast_fwd_smem_bytes))) return rc;
-        MMG_LAUNCH(kern, d.B + n_side, kFastThreads, pl.fast_fwd_smem_bytes, st, d, W, in, fa.b_img, d.row0, fa.bs_w1, fa.bs_b1, d.B, aa);
+        MMG_LAUNCH(kern, d.B + n_side, kFastThreads, pl.fast_fwd_smem_bytes, st, d, W, in, fa.b_img, d.row0, fa.bs_w1, fa.bs_b1, d.B, aa, fa.epilogue);
     } else {
         auto kern = k_exchange_fwd_fast<1, 32, true, false, true>;
         if ((rc = set_smem(kern, pl.fast_fwd_smem_bytes))) return rc;
-        MMG_LAUNCH(kern, d.B + n_side, kFastThreads, pl.fast_fwd_smem_bytes, st, d, W, in, fa.b_img, d.row0, fa.bs_w1, fa.bs_b1, d.B, aa);
+        MMG_LAUNCH(kern, d.B + n_side, kFastThreads, pl.fast_fwd_smem_bytes, st, d, W, in, fa.b_img, d.row0, fa.bs_w1, fa.bs_b1, d.B, aa, fa.epilogue);
     }
     return check_cuda("k_exchange_fwd_fast<attn>");
 }
@@ -419,13 +429,17 @@ static int launch_fwd_fast(const Dims& d, const WsPtrs& W, const ExchangeInputs&
     if (d.M == 32) return launch_fwd_fast_bt<32, true>(d, W, in, fa, pl, st);
     return launch_fwd_fast_bt<64, false>(d, W, in, fa, pl, st);
 }
-template <int M>
+template <int M, bool FUSE>
 static int launch_bwd_fast_m(const Dims& d, const WsPtrs& W, const float* bin_w, const float* code_w, const Plan& pl,
-                             cudaStream_t st) {
-    int rc = set_smem(k_exchange_bwd_fast<M>, pl.bwd_smem_bytes);
+                             cudaStream_t st, const mmg_config& cfg, const PeerView& pv) {
+    const int loss_off = (pl.bwd_smem_bytes + 15) / 16 * 4;          // floats; the coefficient scratch follows the state
+    const int smem = FUSE ? loss_off * 4 + loss_smem_bytes(d, pv.world) : pl.bwd_smem_bytes;
+    if (smem > kMaxSmem) return fail(MMG_ERR_UNSUPPORTED, "fused backward: %d bytes of shared memory", smem);
+    auto kern = k_exchange_bwd_fast<M, FUSE>;
+    int rc = set_smem(kern, smem);
     if (rc) return rc;
     const int n_rec = d.B, n_sen = d.use_binary ? d.B : 0;
-    MMG_LAUNCH(k_exchange_bwd_fast<M>, n_rec + n_sen, kFastBwdThreads, pl.bwd_smem_bytes, st, d, W, bin_w, code_w, n_rec);
+    MMG_LAUNCH(kern, n_rec + n_sen, kFastBwdThreads, smem, st, d, W, bin_w, code_w, n_rec, cfg, pv, loss_off);
     return check_cuda("k_exchange_bwd_fast");
 }
 
@@ -434,48 +448,63 @@ static Operand ones() { return Operand{nullptr, nullptr, nullptr, nullptr, 0, 0,
 
 struct WgBuilder {
     WgTable* t;
-    SplitTable* st;
     const mmg_param_layout* L;
-    int w_id[kMaxWgProblems], b_id[kMaxWgProblems];
-    // C (M x N) = A^T B goes to tensor `w_id` at column offset `col`; colsum(A) (optional) to tensor `b_id`
+    bool covered[MMG_P_COUNT];
+    // C (M x N) = A^T B goes to tensor `wid` at column offset `col`; colsum(A) (optional) to tensor `bid`
     void add(const Operand& A, const Operand& B, int M, int N, int K, int wid, int col, int bid, int kind = WG_GEMM,
              const float* sig_rows = nullptr) {
         WgProblem& p = t->p[t->count];
-        w_id[t->count] = wid; b_id[t->count] = bid;
         ++t->count;
+        covered[wid] = true;
+        if (bid >= 0) covered[bid] = true;
         p.A = A; p.B = B; p.M = M; p.N = N; p.K = K;
         p.c_off = L->offset[wid] + col; p.ldc = N == 1 ? 1 : L->cols[wid];   // N == 1: column sums land contiguously
         p.bias_off = bid >= 0 ? L->offset[bid] : -1;
         p.sig_rows = sig_rows; p.kind = kind;
-        int ns = kind != WG_CODEBIAS ? cdiv(K, kWgradKSlice) : 1;
+        p.seg = L->segment[wid];
+        int ns = kind != WG_CODEBIAS ? cdiv(K, kWgradKSlice) : 1;     // every problem picks its own split factor
         if (ns < 1) ns = 1;
         if (ns > kWgradSplitMax) ns = kWgradSplitMax;
-        if (ns > st->nsplit[wid]) st->nsplit[wid] = ns;
+        p.nsplit = ns;
     }
-    void finish() {
-        t->total_tiles = 0;
+    void add_zero(int tensor) {
+        WgProblem& p = t->p[t->count];
+        ++t->count;
+        memset(&p, 0, sizeof(p));
+        p.kind = WG_ZERO; p.nsplit = 1; p.N = 1; p.K = 1;
+        p.M = (int)round_up64((int64_t)L->rows[tensor] * L->cols[tensor], 4);     // floats to clear (the whole 4-float slot)
+        p.c_off = L->offset[tensor]; p.bias_off = -1; p.seg = L->segment[tensor];
+    }
+    int finish() {
+        for (int i = 0; i < MMG_P_COUNT; ++i) {     // tensors nobody writes this iteration: cleared (the buffer is fully defined)
+            if (covered[i] || (int64_t)L->rows[i] * L->cols[i] == 0) continue;
+            if (t->count >= kMaxWgProblems) return -1;
+            add_zero(i);
+        }
+        t->total_tiles = 0; t->total_out = 0;
         for (int i = 0; i < t->count; ++i) {
             WgProblem& p = t->p[i];
-            p.nsplit = st->nsplit[w_id[i]];                  // problems sharing a tensor share its split factor
-            if (b_id[i] >= 0) st->nsplit[b_id[i]] = p.nsplit;
-            p.ntm = cdiv(p.M, kTile);
-            p.ntn = p.kind == WG_GEMM ? cdiv(p.N, kTile) : (p.kind == WG_ROWVEC ? cdiv(p.N, kRowvecCols) : 1);
+            if (p.kind == WG_ZERO) { p.ntm = cdiv(p.M, kZeroChunk); p.ntn = 1; }
+            else {
+                p.ntm = cdiv(p.M, kTile);
+                p.ntn = p.kind == WG_GEMM ? cdiv(p.N, kTile) : (p.kind == WG_ROWVEC ? cdiv(p.N, kRowvecCols) : 1);
+            }
             p.tile_begin = t->total_tiles;
+            p.out_begin = t->total_out;
             t->tile_begin[i] = p.tile_begin;
             t->total_tiles += p.ntm * p.ntn * p.nsplit;
+            t->total_out += p.ntm * p.ntn;
         }
         t->tile_begin[t->count] = t->total_tiles;
+        return t->total_out <= kMaxOutTiles ? 0 : -3;
     }
 };
 
-static void build_wgrad_table(const Dims& d, const mmg_param_layout& L, const ParamPtrs& P, const WsPtrs& W,
-                              const ExchangeInputs& in, int fast, int fast_bs, int n_rec_ctas, WgTable* t, SplitTable* st) {
+static int build_wgrad_table(const Dims& d, const mmg_param_layout& L, const ParamPtrs& P, const WsPtrs& W,
+                             const ExchangeInputs& in, int fast, int fast_bs, int n_rec_ctas, WgTable* t) {
     t->count = 0; t->total_tiles = 0; t->slab_stride = L.total;
-    for (int i = 0; i < MMG_P_COUNT; ++i) {
-        st->begin[i] = L.offset[i]; st->numel[i] = L.rows[i] * L.cols[i]; st->nsplit[i] = 0;   // 0: no problem writes this tensor
-    }
-    st->begin[MMG_P_COUNT] = L.total;
-    WgBuilder b{t, st, &L, {}, {}};
+    WgBuilder b{t, &L, {}};
+    for (int i = 0; i < MMG_P_COUNT; ++i) b.covered[i] = false;
     const int R = d.R, B = d.B, Hr = d.Hr, M = d.M, Hi = d.Hi;
     const float* h_after = W.h_z + (size_t)B * Hr;       // h_z after step t, row-aligned with (t, b)
     // receiver
@@ -541,7 +570,15 @@ static void build_wgrad_table(const Dims& d, const mmg_param_layout& L, const Pa
             b.add(km(W.g_br, 1), km(W.h1r, d.Hb), 1, d.Hb, R, MMG_P_BR_L2_W, 0, MMG_P_BR_L2_B, WG_ROWVEC);
         }
     }
-    b.finish();
+    return b.finish();
+}
+
+// The loss gradients can be evaluated inside the fast backward kernel when both of its roles run (binary messages) and no
+// -desc_attn backward (generic kernel) is involved.
+static bool fuse_loss_ok(const mmg_config* c) {
+    static int off = -1;
+    if (off < 0) { const char* e = getenv("MMG_FUSE_LOSS"); off = (e && e[0] == '0') ? 1 : 0; }   // =0: separate K_lossgrad (tests)
+    return !off && c->use_binary && !c->desc_attn;
 }
 
 static PeerView no_peers() {
@@ -555,8 +592,10 @@ static int resolve_peers(const mmg_peers* p, int64_t step, PeerView* pv) {
     memset(pv, 0, sizeof(*pv));
     pv->world = p->world; pv->rank = p->rank; pv->error = p->d_error; pv->iter = (unsigned long long)step;
     for (int r = 0; r < p->world; ++r) {
-        if (!p->d_send[r] || !p->d_stats[r] || !p->d_flags[r]) return fail(MMG_ERR_INVALID, "null peer pointer (rank %d)", r);
-        pv->send[r] = p->d_send[r]; pv->stats[r] = p->d_stats[r]; pv->flags[r] = p->d_flags[r];
+        if (!p->d_send[r] || !p->d_recv[r] || !p->d_stats[r] || !p->d_norms[r] || !p->d_flags[r])
+            return fail(MMG_ERR_INVALID, "null peer pointer (rank %d)", r);
+        pv->send[r] = p->d_send[r]; pv->recv[r] = p->d_recv[r]; pv->stats[r] = p->d_stats[r]; pv->norms[r] = p->d_norms[r];
+        pv->flags[r] = p->d_flags[r];
     }
     return MMG_OK;
 }
@@ -646,8 +685,11 @@ int mmg_workspace_init(const mmg_config* cfg, void* d_workspace, uint64_t seed, 
     return check_cuda("k_init_rng");
 }
 
+// `fuse`: non-null inside the fused training iteration: the per-example loss inputs are produced by the conversation kernel's
+// epilogue and the batch statistics by the last CTA of K_baseline_fwd (with `*fuse` as the peers to publish them to); on
+// return `*fused` tells whether that happened (fast kernels only) or K_stats still has to run.
 static int exchange_forward_impl(const mmg_config* cfg, const float* d_params, const mmg_inputs* in, void* d_workspace,
-                                 void* stream, bool finish_baselines) {
+                                 void* stream, bool finish_baselines, const PeerView* fuse = nullptr, bool* fused = nullptr) {
     int rc = validate(cfg);
     if (rc) return rc;
     if (!d_params || !in || !d_workspace || !in->d_x || !in->d_desc) return fail(MMG_ERR_INVALID, "null pointer argument");
@@ -669,14 +711,33 @@ static int exchange_forward_impl(const mmg_config* cfg, const float* d_params, c
     if (d.A && (!in->d_desc_set || !in->d_desc_set_lens)) return fail(MMG_ERR_INVALID, "desc_attn needs d_desc_set and d_desc_set_lens");
     const int n_cls = d.A ? cdiv(d.NW, kTile) * (2 * cdiv(d.Hr, kTile) + cdiv(d.A, kTile))      // word tables
                           : 2 * cdiv(d.D, kTile) * cdiv(d.Hr, kTile);                            // class tables
+    // image-layer GEMM on the tensor cores (tcgen05, 3xTF32) when the shapes allow: 128-row tiles of hidden units, K-slices of
+    // whole 32-float swizzle atoms, 16-byte aligned rows (MMG_UMMA=0 keeps the FFMA tiles)
+    int use_umma = 0, pre_smem = 0, n_hx_l = n_hx;
+#ifndef MMG_CPU_EMU
+    {
+        static int umma_off = -1;
+        if (umma_off < 0) { const char* e = getenv("MMG_UMMA"); umma_off = (e && e[0] == '0') ? 1 : 0; }
+        if (!umma_off && d.Hi % umma::kM == 0 && d.F % 32 == 0 && hx_kslice % 32 == 0 && hx_kslice <= umma::kMaxSliceK &&
+            (((size_t)in->d_x | (size_t)P.p[MMG_P_SEN_IMG_W]) & 15) == 0) {
+            use_umma = 1;
+            pre_smem = umma::tile_smem_bytes(hx_kslice);
+            n_hx_l = (d.Hi / umma::kM) * cdiv(d.B, umma::kN) * W.hx_split;
+            if ((rc = set_smem(k_pre, pre_smem))) return rc;
+        }
+    }
+#endif
     // image formats: bit 0 = fast forward image, bit 1 = fast backward image
-    MMG_LAUNCH(k_pre, n_hx + n_cls + n_pack, kGemmThreads, 0, st, d, P, W, ei, n_hx, hx_kslice, pl.fast_fwd | (pl.fast << 1), n_cls);
+    MMG_LAUNCH(k_pre, n_hx_l + n_cls + n_pack, kGemmThreads, pre_smem, st, d, P, W, ei, n_hx_l, hx_kslice, pl.fast_fwd | (pl.fast << 1), n_cls,
+               use_umma);
     if ((rc = check_cuda("k_pre"))) return rc;
     // K_exchange_fwd
     const AttnArgs aa = attn_args(d, P, ei, pl);
     const float* b_img = P.p[MMG_P_SEN_IMG_B];
-    if (pl.fast) rc = launch_fwd_fast(d, W, ei, FastFwdArgs{b_img, P.p[MMG_P_BS_L1_W], P.p[MMG_P_BS_L1_B]}, pl, st);
-    else if (pl.fast_fwd) rc = launch_fwd_fast_attn(d, W, ei, FastFwdArgs{b_img, P.p[MMG_P_BS_L1_W], P.p[MMG_P_BS_L1_B]}, pl, st, aa);
+    const int epi = (fuse != nullptr && pl.fast_fwd && in->train && in->d_target != nullptr) ? 1 : 0;
+    if (fused != nullptr) *fused = epi != 0;
+    if (pl.fast) rc = launch_fwd_fast(d, W, ei, FastFwdArgs{b_img, P.p[MMG_P_BS_L1_W], P.p[MMG_P_BS_L1_B], epi}, pl, st);
+    else if (pl.fast_fwd) rc = launch_fwd_fast_attn(d, W, ei, FastFwdArgs{b_img, P.p[MMG_P_BS_L1_W], P.p[MMG_P_BS_L1_B], epi}, pl, st, aa);
     else switch (pl.BT) {
         case 1: rc = launch_fwd<1>(d, W, ei, b_img, pl, st, aa); break;
         case 2: rc = launch_fwd<2>(d, W, ei, b_img, pl, st, aa); break;
@@ -688,7 +749,8 @@ static int exchange_forward_impl(const mmg_config* cfg, const float* d_params, c
         const int tiles = 2 * cdiv(d.R, kTile) * W.ntb;
         // wd rows as GEMM tiles (fast path and -desc_attn); otherwise the generic kernel writes wd itself
         const int wd_tiles = (pl.fast || d.A) ? cdiv(d.R, kTile) * cdiv(d.WV, kTile) : 0;
-        MMG_LAUNCH(k_baseline_fwd, tiles + wd_tiles, kGemmThreads, 0, st, d, P, W, d.A ? ei.desc_set : ei.desc, tiles, pl.fast_fwd);
+        MMG_LAUNCH(k_baseline_fwd, tiles + wd_tiles, kGemmThreads, 0, st, d, P, W, d.A ? ei.desc_set : ei.desc, tiles, pl.fast_fwd, epi, ei,
+                   epi ? *fuse : no_peers(), *cfg);
         if ((rc = check_cuda("k_baseline_fwd"))) return rc;
         if (finish_baselines) {     // standalone forward: bs / br must be final on return (mmg_loss re-derives them anyway)
             MMG_LAUNCH(k_baseline_finish, cdiv(d.R, 256), 256, 0, st, d, P, W);
@@ -704,7 +766,7 @@ int mmg_exchange_forward(const mmg_config* cfg, const float* d_params, const mmg
 }
 
 static int loss_impl(const mmg_config* cfg, const float* d_params, const mmg_inputs* in, void* d_workspace, int phase,
-                     void* stream, const PeerView& pv) {
+                     void* stream, const PeerView& pv, bool stats_done = false) {
     int rc = validate(cfg);
     if (rc) return rc;
     if (!d_params || !in || !d_workspace || !in->d_target) return fail(MMG_ERR_INVALID, "null pointer argument");
@@ -717,8 +779,8 @@ static int loss_impl(const mmg_config* cfg, const float* d_params, const mmg_inp
     const ParamPtrs P = param_ptrs(L, d_params);
     const ExchangeInputs ei = resolve_inputs(in);
     cudaStream_t st = (cudaStream_t)stream;
-    if (phase <= 0) {
-        MMG_LAUNCH(k_stats, 1, kStatsThreads, 0, st, d, P, W, ei, pv);
+    if (phase <= 0 && !stats_done) {
+        MMG_LAUNCH(k_stats, 1, kStatsThreadsMax, 0, st, d, P, W, ei, pv);
         if ((rc = check_cuda("k_stats"))) return rc;
     }
     if (phase != 0) {
@@ -736,8 +798,10 @@ int mmg_loss(const mmg_config* cfg, const float* d_params, const mmg_inputs* in,
     return loss_impl(cfg, d_params, in, d_workspace, phase, stream, no_peers());
 }
 
+// `fuse_loss`: the loss gradients (K_lossgrad) are evaluated inside the fast backward kernel; needs the batch statistics in
+// the workspace (fused forward sequence) and use_binary (both backward roles run).
 static int backward_impl(const mmg_config* cfg, const float* d_params, const mmg_inputs* in, void* d_workspace,
-                         float* d_grads, void* stream, const PeerView& pv, SplitTable* stab_out = nullptr) {
+                         float* d_grads, void* stream, const PeerView& pv, bool fuse_loss = false) {
     int rc = validate(cfg);
     if (rc) return rc;
     if (!d_params || !in || !d_workspace || !d_grads) return fail(MMG_ERR_INVALID, "null pointer argument");
@@ -754,8 +818,11 @@ static int backward_impl(const mmg_config* cfg, const float* d_params, const mmg
     cudaStream_t st = (cudaStream_t)stream;
     if (d.A && (!in->d_desc_set || !in->d_desc_set_lens)) return fail(MMG_ERR_INVALID, "desc_attn needs d_desc_set and d_desc_set_lens");
     const AttnArgs aa = attn_args(d, P, ei, pl);
-    if (pl.fast) rc = d.M == 32 ? launch_bwd_fast_m<32>(d, W, P.p[MMG_P_SEN_BIN_W], P.p[MMG_P_SEN_CODE_W], pl, st)
-                                : launch_bwd_fast_m<64>(d, W, P.p[MMG_P_SEN_BIN_W], P.p[MMG_P_SEN_CODE_W], pl, st);
+    if (pl.fast) {
+        const float *bw = P.p[MMG_P_SEN_BIN_W], *cw = P.p[MMG_P_SEN_CODE_W];
+        if (fuse_loss) rc = d.M == 32 ? launch_bwd_fast_m<32, true>(d, W, bw, cw, pl, st, *cfg, pv) : launch_bwd_fast_m<64, true>(d, W, bw, cw, pl, st, *cfg, pv);
+        else           rc = d.M == 32 ? launch_bwd_fast_m<32, false>(d, W, bw, cw, pl, st, *cfg, pv) : launch_bwd_fast_m<64, false>(d, W, bw, cw, pl, st, *cfg, pv);
+    }
     else switch (pl.BT) {
         case 1: rc = launch_bwd<1>(d, W, pl, st, aa); break;
         case 2: rc = launch_bwd<2>(d, W, pl, st, aa); break;
@@ -771,16 +838,14 @@ static int backward_impl(const mmg_config* cfg, const float* d_params, const mmg
         if ((rc = check_cuda("k_attn_reduce"))) return rc;
     }
     WgTable tab;
-    SplitTable stab;
-    build_wgrad_table(d, L, P, W, ei, pl.fast, pl.fast_fwd, cdiv(d.B, pl.BT), &tab, &stab);
-    MMG_LAUNCH(k_wgrad, tab.total_tiles, kGemmThreads, 0, st, d, tab, d_grads, W.slabs, P.p[MMG_P_SEN_CODE_W],
-               P.p[MMG_P_SEN_CODE_BIAS], W.d_as);
-    if ((rc = check_cuda("k_wgrad"))) return rc;
-    if (stab_out != nullptr) { *stab_out = stab; return MMG_OK; }     // the caller fuses the slab reduction with the update
-    const SegInfo seg = seg_info(L, d);
-    MMG_LAUNCH(k_reduce_norm, upd_ctas(L.total), kUpdThreads, 0, st, seg, stab, W.slabs, (long long)L.total, d_grads, 1.0f,
-               1, W.norm_part, pv, W.tickets + 2);
-    return check_cuda("k_reduce_norm");
+    const int trc = build_wgrad_table(d, L, P, W, ei, pl.fast, pl.fast_fwd, cdiv(d.B, pl.BT), &tab);
+    if (trc) return fail(MMG_ERR_UNSUPPORTED, "weight-gradient problem table (%d): too many problems / tiles for these dimensions", trc);
+    // tensors of untrained modules keep a zero gradient: their problems are not in the table, so they are cleared there
+    const WgSync sy{W.tile_tickets, W.tile_norm, W.tickets + 3, W.norm_final};
+    if ((rc = set_smem(k_wgrad, wgrad_smem_bytes()))) return rc;
+    MMG_LAUNCH(k_wgrad, tab.total_tiles, kGemmThreads, wgrad_smem_bytes(), st, d, tab, d_grads, W.slabs, P.p[MMG_P_SEN_CODE_W],
+               P.p[MMG_P_SEN_CODE_BIAS], W.d_as, sy, pv, W, (fuse_loss && pl.fast) ? (d.use_binary ? 2 * d.B : d.B) : 0);
+    return check_cuda("k_wgrad");
 }
 
 int mmg_backward(const mmg_config* cfg, const float* d_params, const mmg_inputs* in, void* d_workspace, float* d_grads,
@@ -799,11 +864,9 @@ int mmg_grad_norm(const mmg_config* cfg, float* d_grads, void* d_workspace, void
     ws_layout(d, &w);
     const WsPtrs W = resolve(w, d_workspace);
     const SegInfo seg = seg_info(L, d);
-    SplitTable stab;
-    memset(&stab, 0, sizeof(stab));
-    MMG_LAUNCH(k_reduce_norm, upd_ctas(L.total), kUpdThreads, 0, (cudaStream_t)stream, seg, stab, W.slabs, (long long)L.total,
-               d_grads, 1.0f, 0, W.norm_part, no_peers(), W.tickets + 2);
-    return check_cuda("k_reduce_norm");
+    MMG_LAUNCH(k_grad_norm, upd_ctas(L.total), kUpdThreads, 0, (cudaStream_t)stream, seg, (const float*)d_grads, W.norm_part,
+               W.tickets + 6, W.norm_final);
+    return check_cuda("k_grad_norm");
 }
 
 int mmg_clip_update(const mmg_config* cfg, float* d_params, float* d_grads, float* d_state1, float* d_state2,
@@ -823,9 +886,9 @@ int mmg_clip_update(const mmg_config* cfg, float* d_params, float* d_grads, floa
     const SegInfo seg = seg_info(L, d);
     OptHyper hp;
     hp.optim = cfg->optim_type; hp.lr = cfg->learning_rate; hp.max_norm = cfg->max_norm; hp.step = step;
-    const int nc = upd_ctas(L.total);
-    MMG_LAUNCH(k_update, nc, kUpdThreads, 0, (cudaStream_t)stream, seg, hp, d_params, d_grads, d_state1, d_state2,
-               W.norm_part, nc, W.grad_norms, W.stats, W.opt_counters);
+    MMG_LAUNCH(k_update, upd_ctas(L.total), kUpdThreads, 0, (cudaStream_t)stream, seg, hp, d_params, (const float*)d_grads, d_grads,
+               d_state1, d_state2, (const double*)W.norm_final, W.grad_norms, (const double*)W.stats,
+               (const long long*)W.opt_counters, no_peers());
     return check_cuda("k_update");
 }
 
@@ -833,51 +896,12 @@ int mmg_train_step(const mmg_config* cfg, float* d_params, float* d_grads, float
                    int64_t step, const mmg_inputs* in, void* d_workspace, void* stream) {
     int rc;
     if (!in || !in->train) return fail(MMG_ERR_INVALID, "mmg_train_step needs in->train = 1");
-    if ((rc = exchange_forward_impl(cfg, d_params, in, d_workspace, stream, false))) return rc;
-    // (measured: evaluating the loss gradients inside the backward kernel moves K_lossgrad's latency chain instead of
-    //  removing it — 30 us fused vs 15 + 11 us — so the two kernels stay separate)
-    if ((rc = loss_impl(cfg, d_params, in, d_workspace, -1, stream, no_peers()))) return rc;
-#ifndef MMG_CPU_EMU
-    {
-        // slab reduction + gradient norms + clip + optimizer in ONE kernel (software grid barrier): the grid is capped at
-        // the number of co-resident CTAs, queried once
-        static int max_ctas = -1;
-        if (max_ctas < 0) {
-            int dev = 0, sms = 0, per_sm = 0;
-            if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_reduce_update, kUpdThreads, 0) != cudaSuccess)
-                max_ctas = 0;
-            else
-                max_ctas = sms * (per_sm > 4 ? 4 : per_sm);
-            // measured on B200: the fusion saves a launch but no time (the kernels, not their boundaries, are the cost),
-            // so the two-kernel sequence stays the default; MMG_FUSED_UPDATE=1 opts in
-            const char* e = getenv("MMG_FUSED_UPDATE");
-            if (!(e && e[0] == '1')) max_ctas = 0;
-        }
-        if (max_ctas > 0) {
-            if (!d_params || !d_grads) return fail(MMG_ERR_INVALID, "null pointer argument");
-            if (cfg->optim_type != MMG_OPT_SGD && !d_state1) return fail(MMG_ERR_INVALID, "optimizer state required");
-            if (cfg->optim_type == MMG_OPT_ADAM && !d_state2) return fail(MMG_ERR_INVALID, "Adam needs d_state2");
-            SplitTable stab;
-            if ((rc = backward_impl(cfg, d_params, in, d_workspace, d_grads, stream, no_peers(), &stab))) return rc;
-            const Dims d = make_dims(*cfg);
-            mmg_param_layout L;
-            param_layout(d, &L);
-            Ws w;
-            ws_layout(d, &w);
-            const WsPtrs W = resolve(w, d_workspace);
-            const SegInfo seg = seg_info(L, d);
-            OptHyper hp;
-            hp.optim = cfg->optim_type; hp.lr = cfg->learning_rate; hp.max_norm = cfg->max_norm; hp.step = step;
-            int nc = upd_ctas(L.total);
-            if (nc > max_ctas) nc = max_ctas;
-            MMG_LAUNCH(k_reduce_update, nc, kUpdThreads, 0, (cudaStream_t)stream, seg, stab, W.slabs, (long long)L.total, hp,
-                       d_params, d_grads, d_state1, d_state2, W.norm_part, W.grad_norms, W.stats, W.opt_counters, W.tickets + 4);
-            return check_cuda("k_reduce_update");
-        }
-    }
-#endif
-    if ((rc = backward_impl(cfg, d_params, in, d_workspace, d_grads, stream, no_peers()))) return rc;
+    const PeerView none = no_peers();
+    bool fused = false;
+    if ((rc = exchange_forward_impl(cfg, d_params, in, d_workspace, stream, false, &none, &fused))) return rc;
+    const bool fuse_loss = fused && fuse_loss_ok(cfg);
+    if (!fuse_loss && (rc = loss_impl(cfg, d_params, in, d_workspace, -1, stream, none, fused))) return rc;
+    if ((rc = backward_impl(cfg, d_params, in, d_workspace, d_grads, stream, none, fuse_loss))) return rc;
     return mmg_clip_update(cfg, d_params, d_grads, d_state1, d_state2, step, 1.0f, d_workspace, stream);
 }
 
@@ -918,18 +942,20 @@ int mmg_train_step_host(const mmg_config* cfg, float* d_params, float* d_grads, 
 
 static int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
-int mmg_peer_buffer_layout(const mmg_config* cfg, int64_t* total_bytes, int64_t* send_off, int64_t* stats_off,
-                           int64_t* flags_off) {
+int mmg_peer_buffer_layout(const mmg_config* cfg, int64_t* total_bytes, int64_t* send_off, int64_t* recv_off, int64_t* stats_off,
+                           int64_t* norms_off, int64_t* flags_off) {
     int rc = validate(cfg);
     if (rc) return rc;
-    if (!total_bytes || !send_off || !stats_off || !flags_off) return fail(MMG_ERR_INVALID, "null output");
+    if (!total_bytes || !send_off || !recv_off || !stats_off || !norms_off || !flags_off) return fail(MMG_ERR_INVALID, "null output");
     const Dims d = make_dims(*cfg);
     mmg_param_layout L;
     param_layout(d, &L);
     *send_off = 0;
-    *stats_off = align256(L.total * 4);
-    *flags_off = *stats_off + align256((int64_t)stats_count(d) * 8);
-    *total_bytes = *flags_off + align256(2 * MMG_MAX_PEERS * 8);
+    *recv_off = align256(L.total * 4);
+    *stats_off = *recv_off + align256(L.total * 4);
+    *norms_off = *stats_off + align256((int64_t)stats_count(d) * 8);
+    *flags_off = *norms_off + align256(4 * MMG_MAX_PEERS * 8);
+    *total_bytes = *flags_off + align256(3 * MMG_MAX_PEERS * 8);
     return MMG_OK;
 }
 
@@ -939,12 +965,17 @@ int mmg_train_step_peer(const mmg_config* cfg, float* d_params, float* d_grads, 
     if (rc) return rc;
     if (!in || !in->train) return fail(MMG_ERR_INVALID, "mmg_train_step_peer needs in->train = 1");
     if (step < 1) return fail(MMG_ERR_INVALID, "step must start at 1 and increase by one per call (it is the flag value)");
+    if (!d_params || !d_grads) return fail(MMG_ERR_INVALID, "null pointer argument");
+    if (cfg->optim_type != MMG_OPT_SGD && !d_state1) return fail(MMG_ERR_INVALID, "optimizer state required");
+    if (cfg->optim_type == MMG_OPT_ADAM && !d_state2) return fail(MMG_ERR_INVALID, "Adam needs d_state2");
     PeerView pv;
     if ((rc = resolve_peers(peers, step, &pv))) return rc;
-    if ((rc = exchange_forward_impl(cfg, d_params, in, d_workspace, stream, false))) return rc;
-    if ((rc = loss_impl(cfg, d_params, in, d_workspace, -1, stream, pv))) return rc;
-    // local gradient -> this rank's symmetric send buffer, then the in-kernel sum over all peers -> d_grads
-    if ((rc = backward_impl(cfg, d_params, in, d_workspace, pv.send[pv.rank], stream, pv))) return rc;
+    bool fused = false;
+    if ((rc = exchange_forward_impl(cfg, d_params, in, d_workspace, stream, false, &pv, &fused))) return rc;
+    const bool fuse_loss = fused && fuse_loss_ok(cfg);
+    if (!fuse_loss && (rc = loss_impl(cfg, d_params, in, d_workspace, -1, stream, pv, fused))) return rc;
+    // local gradient -> this rank's symmetric send buffer (K_wgrad raises flag row 1 when it is complete)
+    if ((rc = backward_impl(cfg, d_params, in, d_workspace, pv.send[pv.rank], stream, pv, fuse_loss))) return rc;
     const Dims d = make_dims(*cfg);
     mmg_param_layout L;
     param_layout(d, &L);
@@ -952,9 +983,17 @@ int mmg_train_step_peer(const mmg_config* cfg, float* d_params, float* d_grads, 
     ws_layout(d, &w);
     const WsPtrs W = resolve(w, d_workspace);
     const SegInfo seg = seg_info(L, d);
-    MMG_LAUNCH(k_peer_allreduce_norm, upd_ctas(L.total), kUpdThreads, 0, (cudaStream_t)stream, seg, pv, d_grads, W.norm_part);
-    if ((rc = check_cuda("k_peer_allreduce_norm"))) return rc;
-    return mmg_clip_update(cfg, d_params, d_grads, d_state1, d_state2, step, 1.0f, d_workspace, stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    // two-shot sum: this rank reduces its 1/G slice of all send buffers into every rank's receive buffer ...
+    MMG_LAUNCH(k_peer_reduce_scatter, upd_ctas(cdiv64(L.total, pv.world)), kUpdThreads, 0, st, seg, pv, W.norm_part, W.tickets + 6,
+               W.norm_final);
+    if ((rc = check_cuda("k_peer_reduce_scatter"))) return rc;
+    // ... and the update waits for all slices (flag row 2), then clips and steps from the local receive buffer
+    OptHyper hp;
+    hp.optim = cfg->optim_type; hp.lr = cfg->learning_rate; hp.max_norm = cfg->max_norm; hp.step = step;
+    MMG_LAUNCH(k_update, upd_ctas(L.total), kUpdThreads, 0, st, seg, hp, d_params, (const float*)pv.recv[pv.rank], d_grads, d_state1,
+               d_state2, (const double*)W.norm_final, W.grad_norms, (const double*)W.stats, (const long long*)W.opt_counters, pv);
+    return check_cuda("k_update");
 }
 
 int mmg_host_prefetch(const mmg_config* cfg, const float* h_x, const int64_t* h_target, float* d_x_stage,

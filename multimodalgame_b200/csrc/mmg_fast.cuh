@@ -14,6 +14,7 @@
 //     and the true BPTT chain, which is reduced to gate algebra + one 192x64 mat-vec per step on shared memory.
 #pragma once
 #include "mmg_exchange_fwd.cuh"
+#include "mmg_loss.cuh"
 
 #if defined(MMG_PHASE_TIMING) && !defined(MMG_CPU_EMU)
 // debug build only (scripts/phase_timing.py): per-phase clock stamps of CTA 0 into the g_sen_probs scratch
@@ -95,7 +96,8 @@ MMG_HOST_DEVICE int fast_uni_stride(int M) { return 2 * M + 4; }       // per (e
 MMG_HOST_DEVICE int fast_fwd_state_floats(int BT, int M, int D, int T) {
     // hx, av (256 each) | win, zv (M each) | hv, y1hv, whv, hwv (64 each) | ghv (192) | yv (DP) | wmax (8)
     // | uniforms (T x stride) | sprod, smask | barrier
-    return BT * (2 * kFastHi + 2 * M + 4 * kFastHr + 3 * kFastHr + align4(D) + 8 + T * fast_uni_stride(M)) +
+    // | ysel (DP): class scores of the prediction step (kept for the per-example epilogue)
+    return BT * (2 * kFastHi + 2 * M + 4 * kFastHr + 3 * kFastHr + 2 * align4(D) + 8 + T * fast_uni_stride(M)) +
            align4(2 * BT) + 8;
 }
 
@@ -132,7 +134,7 @@ MMG_DEVICE float4 lds4(const float* p) { return *reinterpret_cast<const float4*>
 template <int BT, int M, bool kRegSend, bool kPerf, bool kAttn = false>
 MMG_GLOBAL void __launch_bounds__(kFastThreads, 1)
 k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int row_offset, const float* bs_w1,
-                    const float* bs_b1, int n_conv_ctas, AttnArgs aa) {
+                    const float* bs_b1, int n_conv_ctas, AttnArgs aa, int epilogue) {
     static_assert(!kAttn || (BT == 1 && M == 32 && kRegSend), "attention: one example per CTA, msg_dim 32");
     constexpr int HI = kFastHi, HR = kFastHr, NT = kFastThreads, NW = NT / 32;
     constexpr int M4 = M / 4, MQ = M / 16, LPO = NT / M, KPT = HR / LPO, KB = HI / LPO, UST = 2 * M + 4;
@@ -183,6 +185,7 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
     float* hwv = sm + o;   o += BT * HR;
     float* ghv = sm + o;   o += BT * 3 * HR;
     float* yv = sm + o;    o += BT * DP;
+    float* ysel = sm + o;  o += BT * DP;
     float* wmax = sm + o;  o += BT * 8;
     float* uni = sm + o;   o += BT * T * UST;
     float* sprod = sm + o; o += BT;
@@ -376,6 +379,14 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
 
     gh_phase();                                   // gates' recurrent half for step 0 from the initial state
     MMG_SYNCTHREADS();
+    // prediction step of every example (model.py:893-896): the first step whose outgoing stop mask is 0, else the last one.
+    // Every thread tracks it in registers (smask only changes between barriers), so the scores can be kept when they appear.
+    int ystep_r[BT];
+#pragma unroll
+    for (int bt = 0; bt < BT; ++bt) ystep_r[bt] = -1;
+    // the label of the example this warp finishes in the epilogue, fetched now (first touch of `target`: a DRAM round trip)
+    long long tg_pref = 0;
+    if (epilogue && warp < BT && b0 + warp < B) tg_pref = in.target[b0 + warp];
 
     for (int t = 0; t < T; ++t) {
         // ---- P1: sender hidden a = tanh(h_x + code_layer(w_prev)) (model.py:199-216): one thread per unit -----------
@@ -728,6 +739,15 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
         MMG_STAMP(6);
         MMG_SYNCTHREADS();
         // ---- P8: receiver message w(h_w) (model.py:454-475): LPO lanes per message bit -----------------------------
+        if (epilogue) {
+#pragma unroll
+            for (int bt = 0; bt < BT; ++bt) {
+                if (ystep_r[bt] < 0 && (t == T - 1 || (!d.fixed && smask[bt] == 0.f))) {
+                    ystep_r[bt] = t;
+                    for (int c = tid; c < DP; c += NT) ysel[bt * DP + c] = yv[bt * DP + c];
+                }
+            }
+        }
         {
             float4 acc[BT];
 #pragma unroll
@@ -771,6 +791,45 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
         MMG_STAMP(7);
         MMG_SYNCTHREADS();
     }
+    if (epilogue) {
+        // ---- per-example results (get_rec_outp, model.py:879-904; log_softmax / NLL / loglikelihood / argmax, 1264-1275;
+        //      top-k, 1333-1338; d nll / d outp): one warp per example, lanes over the classes.  This is the per-example half
+        //      of K_stats; the batch statistics follow in the last CTA of K_baseline_fwd (they need the baselines).
+        const float invB = 1.0f / (float)d.Bg;
+        for (int bt = warp; bt < BT; bt += NW) {
+            const int b = b0 + bt;
+            if (b >= B) continue;
+            const float* yy = ysel + bt * DP;
+            const int tg = (int)tg_pref;               // bt == warp: BT <= 4 < 8 warps
+            const float ytg = yy[tg];
+            float mx = -INFINITY;
+            for (int dd = lane; dd < D; dd += 32) mx = fmaxf(mx, yy[dd]);
+            mx = warp_max(mx);
+            float am = 3.0e9f, se = 0.f, rank = 0.f;
+            for (int dd = lane; dd < D; dd += 32) {
+                const float v = yy[dd];
+                if (v == mx) am = fminf(am, (float)dd);          // first index of the maximum, like a serial `>` scan
+                se += expf(v - mx);
+                if (v > ytg) rank += 1.f;
+            }
+            am = -warp_max(-am);
+            se = warp_sum(se);
+            rank = warp_sum(rank);
+            const float lse = mx + logf(se);
+            const float lt = ytg - lse;
+            for (int dd = lane; dd < D; dd += 32) {
+                const float v = yy[dd];
+                W.outp[(size_t)b * D + dd] = v;
+                W.g_outp[(size_t)b * D + dd] = (expf(v - lse) - (dd == tg ? 1.f : 0.f)) * invB;   // d nll / d outp
+            }
+            if (lane == 0) {
+                W.ystep[b] = ystep_r[bt];
+                W.logs[b] = lt;
+                W.argmax[b] = (int)am;
+                W.hit[b] = ((int)rank < in.top_k) ? 1.f : 0.f;
+            }
+        }
+    }
 #if defined(MMG_PHASE_TIMING) && !defined(MMG_CPU_EMU)
     if (blockIdx.x == 0) for (int i = tid; i < T * 64; i += NT) reinterpret_cast<unsigned*>(W.g_sen_probs)[i] = stamps[i];
 #endif
@@ -784,21 +843,42 @@ MMG_HOST_DEVICE int fast_bwd_rec_state_floats(int T, int M, int D) {
 }
 MMG_HOST_DEVICE int fast_bwd_sen_state_floats(int T, int M) { return T * M + 2 * kFastHi + T * kFastHi + 8; }
 
-template <int M>
+// Loss coefficients for the fused backward: single rank -> the table K_baseline_fwd's last CTA derived (one load per thread);
+// with peers -> the full prologue (wait for the peers' statistics, sum them in rank order, derive the coefficients).
+MMG_DEVICE void fused_loss_coefs(const Dims& d, const mmg_config& cfg, const WsPtrs& W, const PeerView& pv, unsigned char* smem,
+                                 LossCoef*& coef, float*& bas_scale) {
+    if (pv.world > 1) { loss_prologue(d, cfg, W, pv, smem, coef, bas_scale); return; }
+    coef = reinterpret_cast<LossCoef*>(smem);
+    bas_scale = reinterpret_cast<float*>(coef + 3 * d.T);
+    float* dst = reinterpret_cast<float*>(smem);
+    for (int i = threadIdx.x; i < 6 * d.T + 1; i += kFastBwdThreads) dst[i] = W.coefs[i];
+    MMG_SYNCTHREADS();
+}
+
+// kFuse: the closed-form loss gradients of K_lossgrad (calculate_loss_binary / calculate_loss_bas, model.py:907-988, with the
+// mask wiring of 1248-1262) are evaluated HERE, where the backward pass consumes them, from the batch statistics the forward
+// sequence left in the workspace; the loss values come out of the same pass (per-CTA partials, summed in CTA order by the
+// last CTA).  `loss_off`: float offset of the coefficient scratch inside the dynamic shared memory.
+template <int M, bool kFuse>
 MMG_GLOBAL void __launch_bounds__(kFastBwdThreads, 1)
-k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, int n_rec_ctas) {
+k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, int n_rec_ctas, mmg_config cfg, PeerView pv,
+                    int loss_off) {
     constexpr int HI = kFastHi, HR = kFastHr, NT = kFastBwdThreads, M4 = M / 4;
     MMG_DYN_SMEM(smem_raw);
     float* sm = reinterpret_cast<float*>(smem_raw);
     const int tid = threadIdx.x;
     const int T = d.T, B = d.B, D = d.D;
     const bool binary = d.use_binary != 0;
+    LossCoef* coef = nullptr;
+    float* bas_scale = nullptr;
+    double lacc[5] = {0, 0, 0, 0, 0};      // this thread's share of: binary_sen, binary_rec, binary_s, bas_rec, bas_sen
 
     if ((int)blockIdx.x >= n_rec_ctas) {
         // =================================== sender ==============================================================
         const int b = (int)blockIdx.x - n_rec_ctas, n = tid;
         float* dlz = sm;                                              // (T, M)
         pdl_wait(); pdl_launch_dependents();
+        if constexpr (kFuse) fused_loss_coefs(d, cfg, W, pv, smem_raw + (size_t)loss_off * 4, coef, bas_scale);
         MMG_BSTAMP(0);
         float wb[M];                                                   // column n of binary_layer.weight
 #pragma unroll
@@ -812,7 +892,26 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
             const int t = idx / M, j = idx % M;
             const size_t i = ((size_t)t * B + b) * M + j;
             const float p = W.sen_probs[i];
-            const float dl = W.g_sen_probs[i] * p * (1.f - p);        // through the sigmoid (model.py:223)
+            float g;
+            if constexpr (kFuse) {
+                // sender REINFORCE + entropy term of step t (kind 0: baseline bs[t], mask s_masks[t], model.py:1258,1291)
+                g = 0.f;
+                const size_t row = (size_t)t * B + b;
+                const bool m_in = binary && mask_at(d, W, t, b) != 0;
+                const float lg = W.logs[b], bsv = W.bs[row];
+                if (m_in) {
+                    const LossCoef c0 = coef[t];
+                    const float f = W.sen_feats[i];
+                    const float l1 = logf(p + 1e-8f), l0 = logf(1.f - p + 1e-8f);
+                    lacc[0] += (double)(-(lg - bsv) * c0.cA) * (double)(f * l1 + (1.f - f) * l0) + (double)c0.cE * (double)(p * l1 + (1.f - p) * l0);
+                    g = binary_grad(p, f, (lg - bsv) * c0.cA, c0.cE);
+                    if (j == 0) lacc[4] += (double)(bsv - lg) * (double)(bsv - lg) * bas_scale[0];
+                }
+                if (j == 0) W.g_bs[row] = m_in ? 2.f * (bsv - lg) * bas_scale[0] : 0.f;     // model.py:971-988
+            } else {
+                g = W.g_sen_probs[i];
+            }
+            const float dl = g * p * (1.f - p);                       // through the sigmoid (model.py:223)
             W.d_lz[i] = dl;
             dlz[idx] = dl;
         }
@@ -859,6 +958,7 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
             for (int p = 0; p < NT / M; ++p) v += cred[p * M + tid];
             W.dcode_part[(size_t)b * M + tid] = v;
         }
+        if constexpr (kFuse) loss_partials(W, lacc);     // this CTA's share of the loss values (summed by K_wgrad's last CTA)
         MMG_BSTAMP(3);
         return;
     }
@@ -895,6 +995,7 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
     MMG_BSTAMP(0);
     // W_hh^T (48 KB) never touches shared memory: each thread keeps its 12 float4 of the BPTT mat-vec in registers
     if (tid == 0) tma_stage2(sm, W.bwd_image, (uint32_t)im.whhT * 4u, sm + im.ws, W.bwd_image + im.ws, (uint32_t)(im.total - im.ws) * 4u, bar);
+    if constexpr (kFuse) fused_loss_coefs(d, cfg, W, pv, smem_raw + (size_t)loss_off * 4, coef, bas_scale);
     float4 rwhh[12];
     {
         const float4* src = reinterpret_cast<const float4*>(W.bwd_image + im.whhT) + (tid >> 2) * 4 + (tid & 3);
@@ -908,7 +1009,23 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
         float dl = 0.f;
         if (binary) {
             const float p = W.rec_probs[i];
-            dl = W.g_rec_probs[i] * p * (1.f - p);
+            float g;
+            if constexpr (kFuse) {
+                // receiver-message term of step t (kind 1: baseline br[t], mask s_masks[t+1], none at the last step;
+                // model.py:1257,1284-1286)
+                g = 0.f;
+                if (t < T - 1 && mask_at(d, W, t + 1, b) != 0) {
+                    const LossCoef c1 = coef[T + t];
+                    const float lg = W.logs[b], brv = W.br[(size_t)t * B + b];
+                    const float f = W.rec_feats[i + (size_t)B * M];
+                    const float l1 = logf(p + 1e-8f), l0 = logf(1.f - p + 1e-8f);
+                    lacc[1] += (double)(-(lg - brv) * c1.cA) * (double)(f * l1 + (1.f - f) * l0) + (double)c1.cE * (double)(p * l1 + (1.f - p) * l0);
+                    g = binary_grad(p, f, (lg - brv) * c1.cA, c1.cE);
+                }
+            } else {
+                g = W.g_rec_probs[i];
+            }
+            dl = g * p * (1.f - p);
         }
         W.d_lw[i] = dl;
         dlw[t * LDM + j] = dl;
@@ -928,7 +1045,28 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
     for (int t = tid; t < T; t += NT) {
         const size_t row = (size_t)t * B + b;
         const float sp = W.stop_prob[row];
-        const float v = W.g_stop_prob[row] * sp * (1.f - sp);
+        float g;
+        if constexpr (kFuse) {
+            // STOP bit (kind 2: baseline br[t], mask s_masks[t], adaptive length only; model.py:1256,1279-1280) and the
+            // receiver-side baseline's MSE (model.py:971-988)
+            g = 0.f;
+            const bool m_in = binary && mask_at(d, W, t, b) != 0;
+            const float lg = W.logs[b], brv = W.br[row];
+            if (m_in) {
+                if (!d.fixed) {
+                    const LossCoef c2 = coef[2 * T + t];
+                    const float sf = W.stop_feat[row];
+                    const float l1 = logf(sp + 1e-8f), l0 = logf(1.f - sp + 1e-8f);
+                    lacc[2] += (double)(-(lg - brv) * c2.cA) * (double)(sf * l1 + (1.f - sf) * l0) + (double)c2.cE * (double)(sp * l1 + (1.f - sp) * l0);
+                    g = binary_grad(sp, sf, (lg - brv) * c2.cA, c2.cE);
+                }
+                lacc[3] += (double)(brv - lg) * (double)(brv - lg) * bas_scale[0];
+            }
+            W.g_br[row] = m_in ? 2.f * (brv - lg) * bas_scale[0] : 0.f;
+        } else {
+            g = W.g_stop_prob[row];
+        }
+        const float v = g * sp * (1.f - sp);
         W.d_ls[row] = v;
         dls[t] = v;
     }
@@ -1032,6 +1170,7 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
         W.dgi[row * 3 * HR + c] = ds[c];
         W.dgh[row * 3 * HR + c] = c < 2 * HR ? ds[c] : ds[c + HR];
     }
+    if constexpr (kFuse) loss_partials(W, lacc);         // off the BPTT critical path
     MMG_BSTAMP(5);
     (void)lane;
 }

@@ -217,4 +217,56 @@ MMG_DEVICE void gemm_tile(const Operand& A, const Operand& Bm, int Mdim, int Ndi
     if (colsum != nullptr && tid < kTile) *colsum = cs;
 }
 
+// Same tile for SHORT reductions (k1 - k0 <= kDeep * kChunk): every chunk of both operands is fetched into registers up front
+// (all global loads of the CTA in flight at once: one memory latency instead of one per chunk), then stored / multiplied chunk
+// by chunk through the double-buffered shared memory.  Longer reductions fall back to gemm_tile.
+enum { kDeep = 8 };
+MMG_DEVICE void gemm_tile_deep(const Operand& A, const Operand& Bm, int Mdim, int Ndim, int m0, int n0, int k0, int k1,
+                               float (&acc)[4][4], float* smem) {
+    if (k1 - k0 > kDeep * kChunk) { gemm_tile(A, Bm, Mdim, Ndim, m0, n0, k0, k1, acc, nullptr, smem); return; }
+    const int tid = threadIdx.x;
+    const int tx = tid % 16, ty = tid / 16;
+    float2 acc2[4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { acc2[a][0] = make_float2(0.f, 0.f); acc2[a][1] = make_float2(0.f, 0.f); }
+    const int modeA = operand_mode(A, k0), modeB = operand_mode(Bm, k0);
+    float4 ra[kDeep], rb[kDeep];
+#pragma unroll
+    for (int c = 0; c < kDeep; ++c) {
+        const int kb = k0 + c * kChunk;
+        if (kb < k1) {
+            ra[c] = chunk_fetch(A, modeA, kb, k1, m0, Mdim, tid);
+            rb[c] = chunk_fetch(Bm, modeB, kb, k1, n0, Ndim, tid);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < kDeep; ++c) {
+        const int kb = k0 + c * kChunk;
+        if (kb >= k1) break;
+        float* As = smem + (c & 1) * 2 * kChunk * kLd;
+        float* Bs = As + kChunk * kLd;
+        chunk_store(As, modeA, ra[c], tid);
+        chunk_store(Bs, modeB, rb[c], tid);
+        MMG_SYNCTHREADS();          // one barrier per chunk: buffer (c & 1) is only rewritten two chunks later, after the next barrier
+#pragma unroll
+        for (int kk = 0; kk < kChunk; ++kk) {
+            const float4 a4 = *reinterpret_cast<const float4*>(As + kk * kLd + ty * 4);
+            const float4 b4 = *reinterpret_cast<const float4*>(Bs + kk * kLd + tx * 4);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float2 b01 = make_float2(b4.x, b4.y), b23 = make_float2(b4.z, b4.w);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const float2 aa = make_float2(av[a], av[a]);
+                acc2[a][0] = ffma2(aa, b01, acc2[a][0]);
+                acc2[a][1] = ffma2(aa, b23, acc2[a][1]);
+            }
+        }
+    }
+    MMG_SYNCTHREADS();              // the caller may reuse `smem`
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        acc[a][0] = acc2[a][0].x; acc[a][1] = acc2[a][0].y; acc[a][2] = acc2[a][1].x; acc[a][3] = acc2[a][1].y;
+    }
+}
+
 }  // namespace mmg

@@ -19,7 +19,9 @@ struct WsPtrs {               // resolved workspace arrays (device pointers)
     unsigned long long* rng_state;
     float *code_in, *a_s, *hw_s, *gates, *y1h, *q, *wd, *h1s, *h1r, *bs_part, *br_part, *ubs;
     float *hx_part, *fwd_image, *bwd_image;
-    float *d_lz, *d_as, *dhx, *dgi, *dgh, *d_lw, *d_hw, *d_ls, *g_h, *hsel, *dy1, *dw2p, *dcode_part, *slabs, *norm_part;
+    float *d_lz, *d_as, *dhx, *dgi, *dgh, *d_lw, *d_hw, *d_ls, *g_h, *hsel, *dy1, *dw2p, *dcode_part, *slabs, *norm_part, *tile_norm, *hit, *coefs;
+    unsigned* tile_tickets;
+    double* norm_final;
     double* loss_part;
     unsigned* tickets;
     long long* opt_counters;
@@ -31,9 +33,11 @@ struct WsPtrs {               // resolved workspace arrays (device pointers)
 
 struct PeerView {             // mmg_peers resolved for the kernels; world <= 1: single-rank run, nothing is touched
     int world, rank;
-    float* send[MMG_MAX_PEERS];
+    float* send[MMG_MAX_PEERS];     // local gradients (read by the peers)
+    float* recv[MMG_MAX_PEERS];     // global gradient, written slice by slice by the rank that owns the slice
     double* stats[MMG_MAX_PEERS];
-    unsigned long long* flags[MMG_MAX_PEERS];
+    double* norms[MMG_MAX_PEERS];   // [world][4] per-slice sums of squares of the global gradient
+    unsigned long long* flags[MMG_MAX_PEERS];   // [3][MMG_MAX_PEERS]: statistics / send buffer / slice published
     int* error;
     unsigned long long iter;
 };

@@ -233,10 +233,16 @@ struct Ws {   // byte offsets into the workspace
     int64_t dw2p;      // (B,Hr)
     int64_t dcode_part; // (B,M)   per-example d code_layer-input at t = 0 (fast path), summed into d code_bias
     int64_t slabs;     // (kWgradSplitMax - 1, P) split-K partial gradients (split 0 lands in the gradient buffer itself)
-    int64_t norm_part; // (4, kNormCtasMax) per-CTA partial sums of squares
+    int64_t norm_part; // (4, kNormCtasMax) per-CTA partial sums of squares (K_grad_norm, K_peer_reduce_scatter)
+    int64_t tile_norm; // float (kMaxOutTiles) sum of squares of each finished gradient tile (K_wgrad)
+    int64_t tile_tickets; // uint32 (kMaxOutTiles) split-K arrival counters per output tile, zero between launches
+    int64_t norm_final; // double[4] per-module sum of squares of the gradient (pre-clip), consumed by K_update
     int64_t loss_part; // double (kLossCtasMax, 8) per-CTA loss partial sums, summed in CTA order by the last CTA
-    int64_t tickets;   // uint32[8]: [0] loss reduction, [1] h_x rows ready, [2] send buffer complete, [4..5] grid barrier
+    int64_t tickets;   // uint32[16]: [0] loss reduction, [1] h_x rows ready, [3] finished gradient tiles, [6] norm partials,
+                       //             [7] baseline tiles
     int64_t opt_counters; // int64[4]: [0] = number of updates that reached the receiver message head (Adam bias correction)
+    int64_t coefs;     // float (6 T + 4) loss coefficients derived once from the batch statistics (single-rank fused iteration)
+    int64_t hit;       // (B) 1 when the target is among the top-k classes of the prediction (fused iteration)
     // -desc_attn (all zero-sized otherwise)
     int64_t wtab_dd;   // (NW,A4)  e^{2 d_d(desc_set)}: word factor of the attention tanh (attn_tanh), loop invariant
     int64_t wtab_y1;   // (NW,Hr)  desc_set . y1.weight[:, :WV]^T

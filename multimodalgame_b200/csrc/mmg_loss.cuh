@@ -14,10 +14,7 @@
 
 namespace mmg {
 
-MMG_GLOBAL void __launch_bounds__(kGemmThreads)
-k_baseline_fwd(Dims d, ParamPtrs P, WsPtrs W, const float* desc, int n_bas_tiles, int use_u) {
-    pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
-    pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
+MMG_DEVICE void baseline_fwd_tile(const Dims& d, const ParamPtrs& P, const WsPtrs& W, const float* desc, int n_bas_tiles, int use_u) {
     MMG_SHARED __attribute__((aligned(16))) float gs[kGemmSmemFloats];
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
     const int ntm = cdiv(d.R, kTile), ntn = W.ntb;
@@ -32,7 +29,7 @@ k_baseline_fwd(Dims d, ParamPtrs P, WsPtrs W, const float* desc, int n_bas_tiles
         const Operand A = Operand{d.A ? W.qa : W.q, nullptr, nullptr, nullptr, Kw, 0, 0, 0, 0, OP_PLAIN};
         const Operand Bo = Operand{desc, nullptr, nullptr, nullptr, d.WV, 0, 1, 0, 0, OP_PLAIN};
         float acc[4][4];
-        gemm_tile(A, Bo, d.R, d.WV, mt * kTile, nt * kTile, 0, Kw, acc, nullptr, gs);
+        gemm_tile_deep(A, Bo, d.R, d.WV, mt * kTile, nt * kTile, 0, Kw, acc, gs);
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int r = mt * kTile + ty * 4 + a;
@@ -66,7 +63,7 @@ k_baseline_fwd(Dims d, ParamPtrs P, WsPtrs W, const float* desc, int n_bas_tiles
         b1 = P.p[MMG_P_BR_L1_B]; w2 = P.p[MMG_P_BR_L2_W]; hid = W.h1r; part = W.br_part; K = d.M + d.Hr;
     }
     float acc[4][4];
-    gemm_tile(A, Bo, d.R, d.Hb, mt * kTile, nt * kTile, 0, K, acc, nullptr, gs);
+    gemm_tile_deep(A, Bo, d.R, d.Hb, mt * kTile, nt * kTile, 0, K, acc, gs);
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const int r = mt * kTile + ty * 4 + a;
@@ -107,39 +104,54 @@ k_baseline_finish(Dims d, ParamPtrs P, WsPtrs W) {
     }
 }
 
-enum { kStatsThreads = 1024 };
+enum { kStatsThreadsMax = 1024 };
 
 MMG_DEVICE unsigned char mask_at(const Dims& d, const WsPtrs& W, int slot, int b) {
     return d.fixed ? (unsigned char)1 : W.stop_mask[(size_t)slot * d.B + b];
 }
 
-MMG_GLOBAL void __launch_bounds__(kStatsThreads)
-k_stats(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, PeerView pv) {
-    pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
-    pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
+// Body of K_stats for a CTA of NT threads.  `per_example_done`: the conversation kernel's epilogue has already produced the
+// per-example results (ystep, outp, g_outp, logs, argmax, hit); only the batch sums remain.
+template <int NT>
+MMG_DEVICE void stats_body(const Dims& d, const ParamPtrs& P, const WsPtrs& W, const ExchangeInputs& in, const PeerView& pv,
+                           bool per_example_done) {
+    constexpr int kStatsThreads = NT;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kStatsThreads / 32;
-    // ---- finalize baseline scores --------------------------------------------------------------------------
+    // ---- finalize baseline scores: per-tile partial dots added in tile order; two rows per pass, all loads in flight --------
     const float b2s = ldg(P.p[MMG_P_BS_L2_B]), b2r = ldg(P.p[MMG_P_BR_L2_B]);
-    for (int r = tid; r < d.R; r += kStatsThreads) {
-        float s = b2s, q = b2r;
-        for (int j0 = 0; j0 < W.ntb; j0 += 8) {          // 16 partial loads in flight, added in tile order
-            float ps[8], pq[8];
+    for (int r0 = tid; r0 < d.R; r0 += 2 * kStatsThreads) {
+        const int r1 = r0 + kStatsThreads;
+        const bool two = r1 < d.R;
+        float s0 = b2s, q0 = b2r, s1 = b2s, q1 = b2r;
+        for (int j0 = 0; j0 < W.ntb; j0 += 8) {
+            float ps[2][8], pq[2][8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                ps[u] = j0 + u < W.ntb ? W.bs_part[(size_t)r * W.ntb + j0 + u] : 0.f;
-                pq[u] = j0 + u < W.ntb ? W.br_part[(size_t)r * W.ntb + j0 + u] : 0.f;
+                const bool ok = j0 + u < W.ntb;
+                ps[0][u] = ok ? W.bs_part[(size_t)r0 * W.ntb + j0 + u] : 0.f;
+                pq[0][u] = ok ? W.br_part[(size_t)r0 * W.ntb + j0 + u] : 0.f;
+                ps[1][u] = ok && two ? W.bs_part[(size_t)r1 * W.ntb + j0 + u] : 0.f;
+                pq[1][u] = ok && two ? W.br_part[(size_t)r1 * W.ntb + j0 + u] : 0.f;
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { s += ps[u]; q += pq[u]; }
+            for (int u = 0; u < 8; ++u) { s0 += ps[0][u]; q0 += pq[0][u]; s1 += ps[1][u]; q1 += pq[1][u]; }
         }
-        W.bs[r] = s; W.br[r] = q;
+        W.bs[r0] = s0; W.br[r0] = q0;
+        if (two) { W.bs[r1] = s1; W.br[r1] = q1; }
     }
     // ---- per example (one HALF-warp each, lanes over classes; 64 examples per round): prediction step, log-softmax,
     //      log-likelihood, argmax, top-k, dNLL/d outp -----------------------------------------------------------------
-    MMG_SHARED double s_red[2][kStatsThreads / 16];
+    MMG_SHARED double s_red[2][kStatsThreadsMax / 16];
     double nll_local = 0.0, correct_local = 0.0;
     const float invB = 1.0f / (float)d.Bg;
     const int hl = tid & 15, hwid = tid >> 4, nhw = kStatsThreads / 16;
+    if (per_example_done) {     // the conversation kernel left logs[] / hit[]: every thread adds its rows, tree below
+        for (int b = tid; b < d.B; b += kStatsThreads) { nll_local -= (double)W.logs[b]; correct_local += (double)W.hit[b]; }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {      // half-warp tree so that the hl == 0 lanes hold the partials the code below expects
+            nll_local += shfl_xor_d(nll_local, o); correct_local += shfl_xor_d(correct_local, o);
+        }
+    } else
     for (int b0 = 0; b0 < d.B; b0 += nhw) {
         const int b = b0 + hwid;
         const bool ok = b < d.B;
@@ -198,40 +210,36 @@ k_stats(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, PeerView pv) {
         W.stats[stat_scalar(d, 2)] = 0.0;
         W.stats[stat_scalar(d, 3)] = 0.0;
     }
-    // ---- batch statistics per (loss kind, step): one warp per quantity ------------------------------------------
+    // ---- batch statistics per (loss kind, step): one warp per STEP, all kinds in one pass over the rows (shared loads) ------
     // kind 0: sender messages  (baseline bs[t], mask s_masks[t])      model.py:1258,1291
     // kind 1: receiver message (baseline br[t], mask s_masks[t+1], t <= T-2)   model.py:1257,1285-1286
     // kind 2: stop bit         (baseline br[t], mask s_masks[t])      model.py:1256,1279-1280
-    for (int qn = warp; qn < 4 * d.T; qn += nwarps) {
-        const int kind = qn / d.T, t = qn % d.T;
-        double n = 0, s1 = 0, s2 = 0;      // kind < 3: count, sum w, sum w^2; kind 3: count, SSE baseline_rec, SSE baseline_sen
+    // baselines: SSE of both over s_masks[t]; n_mask = rows still active after step t
+    for (int t = warp; t < d.T; t += nwarps) {
+        double n0 = 0, a0 = 0, c0 = 0, n1 = 0, a1 = 0, c1 = 0, n2 = 0, a2 = 0, c2 = 0, er2 = 0, es2 = 0, nm = 0;
 #pragma unroll 2
         for (int b = lane; b < d.B; b += 32) {
             const float lg = W.logs[b];
-            if (kind < 3) {
-                const int slot = (kind == 1) ? t + 1 : t;
-                const bool valid = !(kind == 1 && t == d.T - 1) && !(kind == 2 && d.fixed);
-                if (valid && mask_at(d, W, slot, b)) {
-                    const float base = (kind == 0) ? W.bs[(size_t)t * d.B + b] : W.br[(size_t)t * d.B + b];
-                    const double w = (double)(lg - base);
-                    n += 1.0; s1 += w; s2 += w * w;
-                }
-            } else {
-                if (mask_at(d, W, t, b)) {
-                    const double er = (double)(W.br[(size_t)t * d.B + b] - lg), es = (double)(W.bs[(size_t)t * d.B + b] - lg);
-                    s1 += er * er; s2 += es * es;
-                }
-                if (mask_at(d, W, t + 1, b) && !d.fixed) n += 1.0;   // rows still active after step t
-                if (d.fixed) n += 1.0;
+            const float bsv = W.bs[(size_t)t * d.B + b], brv = W.br[(size_t)t * d.B + b];
+            const bool m_in = mask_at(d, W, t, b) != 0, m_out = mask_at(d, W, t + 1, b) != 0;
+            const double ws = (double)(lg - bsv), wr = (double)(lg - brv);
+            if (m_in) {
+                n0 += 1.0; a0 += ws; c0 += ws * ws;
+                if (!d.fixed) { n2 += 1.0; a2 += wr; c2 += wr * wr; }
+                er2 += wr * wr; es2 += ws * ws;
             }
+            if (m_out && t < d.T - 1) { n1 += 1.0; a1 += wr; c1 += wr * wr; }
+            if (d.fixed || m_out) nm += 1.0;
         }
-        n = warp_sum_d(n); s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
+        n0 = warp_sum_d(n0); a0 = warp_sum_d(a0); c0 = warp_sum_d(c0);
+        n1 = warp_sum_d(n1); a1 = warp_sum_d(a1); c1 = warp_sum_d(c1);
+        n2 = warp_sum_d(n2); a2 = warp_sum_d(a2); c2 = warp_sum_d(c2);
+        er2 = warp_sum_d(er2); es2 = warp_sum_d(es2); nm = warp_sum_d(nm);
         if (lane == 0) {
-            if (kind < 3) {
-                W.stats[stat_idx(d, kind, t, 0)] = n; W.stats[stat_idx(d, kind, t, 1)] = s1; W.stats[stat_idx(d, kind, t, 2)] = s2;
-            } else {
-                W.stats[stat_bas(d, t, 0)] = s1; W.stats[stat_bas(d, t, 1)] = s2; W.stats[stat_bas(d, t, 2)] = n;
-            }
+            W.stats[stat_idx(d, 0, t, 0)] = n0; W.stats[stat_idx(d, 0, t, 1)] = a0; W.stats[stat_idx(d, 0, t, 2)] = c0;
+            W.stats[stat_idx(d, 1, t, 0)] = n1; W.stats[stat_idx(d, 1, t, 1)] = a1; W.stats[stat_idx(d, 1, t, 2)] = c1;
+            W.stats[stat_idx(d, 2, t, 0)] = n2; W.stats[stat_idx(d, 2, t, 1)] = a2; W.stats[stat_idx(d, 2, t, 2)] = c2;
+            W.stats[stat_bas(d, t, 0)] = er2; W.stats[stat_bas(d, t, 1)] = es2; W.stats[stat_bas(d, t, 2)] = nm;
         }
     }
     if (pv.world > 1) {
@@ -279,6 +287,58 @@ MMG_DEVICE float binary_grad(float p, float f, float wcA, float cE) {
     return g;
 }
 
+// Single-rank runs: the statistics are final as soon as they are computed, so the CTA that computes them also derives the
+// loss coefficients once (W.coefs: [3][T] LossCoef, then 1 / denominator of the baseline MSE) instead of every consumer CTA.
+MMG_DEVICE void loss_coefs_store(const Dims& d, const mmg_config& cfg, const WsPtrs& W, int nthreads) {
+    MMG_SHARED double tot_c[3];
+    const int tid = threadIdx.x;
+    const double* st = W.stats;
+    if (tid < 3) {
+        const int steps = (tid == 1) ? d.T - 1 : d.T;
+        double v = 0.0;
+        for (int t = 0; t < steps; ++t) v += st[stat_idx(d, tid, t, 0)];
+        tot_c[tid] = v;
+    }
+    MMG_SYNCTHREADS();
+    LossCoef* out = reinterpret_cast<LossCoef*>(W.coefs);
+    for (int i = tid; i < 3 * d.T; i += nthreads) loss_coefs(d, cfg, st, i / d.T, i % d.T, d.fixed ? 0.0 : tot_c[i / d.T], out[i]);
+    if (tid == 0) {
+        const double tot = d.fixed ? (double)d.Bg * d.T : tot_c[0];
+        W.coefs[6 * d.T] = tot > 0 ? (float)(1.0 / tot) : 0.f;
+    }
+}
+
+// `fuse_stats`: the last CTA to finish its tile (ticket) also runs the batch statistics, so K_stats is not launched: the
+// per-example half was done by the conversation kernel's epilogue.
+MMG_GLOBAL void __launch_bounds__(kGemmThreads)
+k_baseline_fwd(Dims d, ParamPtrs P, WsPtrs W, const float* desc, int n_bas_tiles, int use_u, int fuse_stats, ExchangeInputs in,
+               PeerView pv, mmg_config cfg) {
+    pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
+    pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
+    baseline_fwd_tile(d, P, W, desc, n_bas_tiles, use_u);
+    if (!fuse_stats) return;
+    MMG_SHARED int s_last;
+    fence_acquire();            // every thread: its tile results are visible device-wide before the CTA is counted
+    MMG_SYNCTHREADS();
+    if (threadIdx.x == 0) s_last = (ticket_take(W.tickets + 7) == gridDim.x - 1) ? 1 : 0;
+    MMG_SYNCTHREADS();
+    if (!s_last) return;
+    fence_acquire();
+    if (threadIdx.x == 0) W.tickets[7] = 0;
+    stats_body<kGemmThreads>(d, P, W, in, pv, true);
+    if (pv.world <= 1) {
+        MMG_SYNCTHREADS();
+        loss_coefs_store(d, cfg, W, kGemmThreads);
+    }
+}
+
+MMG_GLOBAL void __launch_bounds__(kStatsThreadsMax)
+k_stats(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, PeerView pv) {
+    pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
+    pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
+    stats_body<kStatsThreadsMax>(d, P, W, in, pv, false);
+}
+
 MMG_HOST_DEVICE int loss_smem_bytes(const Dims& d, int world) {
     return 3 * d.T * (int)sizeof(LossCoef) + 16 + (world > 1 ? stats_count(d) * 8 + 16 : 0);
 }
@@ -294,7 +354,7 @@ MMG_DEVICE const double* loss_prologue(const Dims& d, const mmg_config& cfg, con
     if (pv.world > 1) {
         // global batch statistics = sum over ranks, read straight from the peers' symmetric slots (rank order)
         double* st_s = reinterpret_cast<double*>(bas_scale + 4);
-        if (tid < pv.world && !peer_wait(pv.flags[pv.rank] + tid, pv.iter)) *pv.error = 1;
+        if (tid < pv.world && !peer_wait(pv.flags[pv.rank] + tid, pv.iter, pv.error)) *pv.error = 1;
         MMG_SYNCTHREADS();
         for (int i = tid; i < stats_count(d); i += kLossThreads) {
             double v = 0.0;
@@ -330,35 +390,36 @@ MMG_DEVICE const double* loss_prologue(const Dims& d, const mmg_config& cfg, con
 
 // Loss values: per-CTA partials (acc: 0 binary_sen, 1 binary_rec, 2 binary_s, 3 bas_rec, 4 bas_sen — rank-local
 // contributions, any thread may hold a share), summed in CTA order by the last CTA to finish (deterministic).
-MMG_DEVICE void loss_epilogue(const Dims& d, const WsPtrs& W, const double* st, const double (&acc)[5]) {
+// Per-CTA partial of the five loss sums -> loss_part[cta][0..4] (256 threads).
+MMG_DEVICE void loss_partials(const WsPtrs& W, const double (&acc)[5]) {
     MMG_SHARED double red[5][kLossThreads / 32];
-    MMG_SHARED double nll_red[kLossThreads / 32];
-    MMG_SHARED int s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = 0; i < 5; ++i) {
         const double v = warp_sum_d(acc[i]);
         if (lane == 0) red[i][warp] = v;
     }
     MMG_SYNCTHREADS();
-    if (tid == 0) {
-        for (int i = 0; i < 5; ++i) {
-            double v = 0;
-            for (int w = 0; w < kLossThreads / 32; ++w) v += red[i][w];
-            W.loss_part[(size_t)blockIdx.x * 8 + i] = v;
-        }
-        s_last = (ticket_take(W.tickets) == gridDim.x - 1) ? 1 : 0;
+    if (tid < 5) {
+        double v = 0;
+        for (int w = 0; w < kLossThreads / 32; ++w) v += red[tid][w];
+        W.loss_part[(size_t)blockIdx.x * 8 + tid] = v;
     }
-    MMG_SYNCTHREADS();
-    if (!s_last) return;
-    fence_acquire();
+}
+
+// The loss values from `nparts` per-CTA partials (added in CTA order: deterministic) and the global statistics in W.stats;
+// one CTA of 256 threads, after every partial is visible.
+MMG_DEVICE void loss_finalize(const Dims& d, const WsPtrs& W, int nparts) {
+    MMG_SHARED double red[5][kLossThreads / 32];
+    MMG_SHARED double nll_red[kLossThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* st = W.stats;
     double nl = 0;
     for (int b = tid; b < d.B; b += kLossThreads) nl -= (double)W.logs[b] / (double)d.Bg;
     nl = warp_sum_d(nl);
     if (lane == 0) nll_red[warp] = nl;
-    MMG_SYNCTHREADS();
     // per-CTA partials: thread c sums CTAs c, c + 256, ...; then a fixed shuffle tree and 8 warp totals
     double part[5] = {0, 0, 0, 0, 0};
-    for (unsigned c = tid; c < gridDim.x; c += kLossThreads)
+    for (int c = tid; c < nparts; c += kLossThreads)
         for (int i = 0; i < 5; ++i) part[i] += W.loss_part[(size_t)c * 8 + i];
     for (int i = 0; i < 5; ++i) {
         const double v = warp_sum_d(part[i]);
@@ -389,8 +450,22 @@ MMG_DEVICE void loss_epilogue(const Dims& d, const WsPtrs& W, const double* st, 
         L[MMG_LOSS_ACTIVE_STEPS] = (float)tp;
         if (st[stat_idx(d, 1, 0, 0)] > 0.0) W.opt_counters[0] += 1;   // updates seen by the receiver message head
         for (int i = MMG_LOSS_ACTIVE_STEPS + 1; i < MMG_LOSS_COUNT; ++i) L[i] = 0.f;
-        W.tickets[0] = 0;                                             // ready for the next launch
     }
+}
+
+// Loss values: per-CTA partials (acc: 0 binary_sen, 1 binary_rec, 2 binary_s, 3 bas_rec, 4 bas_sen — rank-local
+// contributions, any thread may hold a share), summed in CTA order by the last CTA to finish (deterministic).
+MMG_DEVICE void loss_epilogue(const Dims& d, const WsPtrs& W, const double (&acc)[5]) {
+    MMG_SHARED int s_last;
+    loss_partials(W, acc);
+    fence_acquire();
+    MMG_SYNCTHREADS();
+    if (threadIdx.x == 0) s_last = (ticket_take(W.tickets) == gridDim.x - 1) ? 1 : 0;
+    MMG_SYNCTHREADS();
+    if (!s_last) return;
+    fence_acquire();
+    loss_finalize(d, W, (int)gridDim.x);
+    if (threadIdx.x == 0) W.tickets[0] = 0;                              // ready for the next launch
 }
 
 MMG_GLOBAL void __launch_bounds__(kLossThreads)
@@ -464,7 +539,8 @@ k_lossgrad(Dims d, mmg_config cfg, WsPtrs W, PeerView pv) {
             W.g_stop_prob[row] = 0.f; W.g_bs[row] = 0.f; W.g_br[row] = 0.f;
         }
     }
-    loss_epilogue(d, W, st, acc);
+    (void)st;
+    loss_epilogue(d, W, acc);
 }
 
 }  // namespace mmg

@@ -45,6 +45,7 @@ MMG_DEVICE float half_warp_sum(float v) {
 }
 
 MMG_DEVICE float shfl_xor_f(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+MMG_DEVICE double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 // Blackwell packed fp32: one FFMA2 instruction = two IEEE-rn fused multiply-adds (bitwise equal to two fmaf)
 MMG_DEVICE float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 // Short-latency transcendentals for the recurrent fast path (MUFU.EX2 / MUFU.RCP; absolute error ~2e-7, far inside
@@ -89,16 +90,24 @@ MMG_DEVICE void peer_signal(unsigned long long* remote_flag, unsigned long long 
     __threadfence_system();                                   // this rank's prior writes are visible system-wide first
     *reinterpret_cast<volatile unsigned long long*>(remote_flag) = value;
 }
-MMG_DEVICE bool peer_wait(const unsigned long long* local_flag, unsigned long long target) {
-    for (int spin = 0; spin < (1 << 23); ++spin) {            // bounded: a missing peer must not hang the GPU
+// Bounded wait (~15 s: ranks must run in lockstep within that window; a dead peer must not hang the GPU for good).  `err`
+// is the rank's sticky error word: once a wait has timed out every later wait gives up at once, the update kernels skip
+// their work and the host raises (GameEngine.peer_error()).
+MMG_DEVICE bool peer_wait(const unsigned long long* local_flag, unsigned long long target, const int* err) {
+    if (*reinterpret_cast<const volatile unsigned long long*>(local_flag) >= target) { __threadfence_system(); return true; }
+    if (*reinterpret_cast<const volatile int*>(err) != 0) return false;
+    for (int spin = 0; spin < (1 << 26); ++spin) {
         if (*reinterpret_cast<const volatile unsigned long long*>(local_flag) >= target) { __threadfence_system(); return true; }
-        __nanosleep(200);
+        __nanosleep(spin < 4096 ? 32 : 256);
     }
     return false;
 }
 MMG_DEVICE void fence_system() { __threadfence_system(); }
 MMG_DEVICE float4 peer_load4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }   // L1 bypass
 MMG_DEVICE double peer_load_d(const double* p) { return __ldcg(p); }
+// L1-bypassing loads for data another CTA of the SAME grid has just written (split-K partial tiles)
+MMG_DEVICE float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+MMG_DEVICE float ld_cg(const float* p) { return __ldcg(p); }
 
 // ---- mbarrier + TMA bulk copy (cp.async.bulk, SASS UBLKCP) ------------------------------------------
 MMG_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -254,6 +263,7 @@ MMG_DEVICE float half_warp_sum(float v) {
     return v;
 }
 MMG_DEVICE float shfl_xor_f(float v, int m) { return (float)emu::shfl_xor(v, m); }
+MMG_DEVICE double shfl_xor_d(double v, int m) { return emu::shfl_xor(v, m); }
 MMG_DEVICE float2 ffma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
 MMG_DEVICE float fast_exp(float x) { return expf(x); }
 MMG_DEVICE float fast_rcp(float x) { return 1.0f / x; }
@@ -278,10 +288,12 @@ MMG_DEVICE void flag_wait(const unsigned* counter, unsigned target) {   // block
     while (__atomic_load_n(counter, __ATOMIC_SEQ_CST) < target) {}
 }
 MMG_DEVICE void peer_signal(unsigned long long* f, unsigned long long v) { __atomic_store_n(f, v, __ATOMIC_SEQ_CST); }
-MMG_DEVICE bool peer_wait(const unsigned long long* f, unsigned long long target) { return __atomic_load_n(f, __ATOMIC_SEQ_CST) >= target; }
+MMG_DEVICE bool peer_wait(const unsigned long long* f, unsigned long long target, const int*) { return __atomic_load_n(f, __ATOMIC_SEQ_CST) >= target; }
 MMG_DEVICE void fence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 MMG_DEVICE float4 peer_load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 MMG_DEVICE double peer_load_d(const double* p) { return *p; }
+MMG_DEVICE float4 ld_cg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+MMG_DEVICE float ld_cg(const float* p) { return *p; }
 MMG_DEVICE void mbar_init(uint64_t* bar, int) { *bar = 0; }
 MMG_DEVICE void mbar_fence_init() {}
 MMG_DEVICE void mbar_wait(uint64_t*, uint32_t) {}

@@ -8,6 +8,7 @@
 //          term hw0 = code_layer(sigmoid(code_bias)) (model.py:199-200) and code_in[0] = sigmoid(code_bias).
 #pragma once
 #include "mmg_fast.cuh"
+#include "mmg_umma.cuh"
 
 namespace mmg {
 
@@ -65,11 +66,26 @@ MMG_DEVICE float bwd_image_elem(const Dims& d, const BwdImage& im, const ParamPt
 }
 
 MMG_GLOBAL void __launch_bounds__(kGemmThreads)
-k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_kslice, int fast, int n_cls_tiles) {
+k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_kslice, int fast, int n_cls_tiles, int use_umma) {
     pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
     pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
     MMG_SHARED __attribute__((aligned(16))) float gs[kGemmSmemFloats];
     const int tid = threadIdx.x;
+#ifndef MMG_CPU_EMU
+    if (use_umma && (int)blockIdx.x < n_hx_tiles) {
+        // ---- role A on the tensor cores (tcgen05, 3xTF32): 128 hidden units x 64 batch rows x one K-slice per CTA --------------
+        MMG_DYN_SMEM(umma_smem);
+        const int nbt = cdiv(d.B, umma::kN), nmt = d.Hi / umma::kM;
+        int t = blockIdx.x;
+        const int bt = t % nbt; t /= nbt;
+        const int mt = t % nmt; t /= nmt;
+        const int s = t;
+        const int k0 = s * hx_kslice, nk = min(hx_kslice, d.F - k0);
+        umma::image_layer_tile(P.p[MMG_P_SEN_IMG_W], in.x, d.F, d.Hi, d.B, mt * umma::kM, bt * umma::kN, k0, nk,
+                               W.hx_part + (size_t)s * d.B * d.Hi, umma_smem);
+        return;
+    }
+#endif
     if (blockIdx.x == 0 && tid == 0) {
         W.tickets[1] = 0;      // "h_x rows ready" counter of the next forward kernel
         // Every exchange that consumes on-device draws (Bernoulli samples without injected uniforms, flipout noise) gets a
@@ -125,7 +141,7 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
                    : which == 1 ? Operand{P.p[MMG_P_REC_WD_W], nullptr, nullptr, nullptr, d.WV, 0, 0, 0, 0, OP_PLAIN}
                                 : Operand{P.p[MMG_P_REC_DD_W], nullptr, nullptr, nullptr, d.WV, 0, 0, 0, 0, OP_PLAIN};
         float acc[4][4];
-        gemm_tile(A, Bo, d.NW, N, mt * kTile, nt * kTile, 0, d.WV, acc, nullptr, gs);
+        gemm_tile_deep(A, Bo, d.NW, N, mt * kTile, nt * kTile, 0, d.WV, acc, gs);
         const int tx = tid % 16, ty = tid / 16;
         float* out = which == 0 ? W.wtab_y1 : (which == 1 ? W.wtab_wd : W.wtab_dd);
         const int NP = align4(N);                   // rows padded to whole float4 groups, padding zero
@@ -154,7 +170,7 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
         Operand Bo = which == 0 ? Operand{P.p[MMG_P_REC_Y1_W] + d.Hr, nullptr, nullptr, nullptr, d.Hr + d.WV, 0, 0, 0, 0, OP_PLAIN}
                                 : Operand{P.p[MMG_P_REC_WD_W], nullptr, nullptr, nullptr, d.WV, 0, 0, 0, 0, OP_PLAIN};
         float acc[4][4];
-        gemm_tile(A, Bo, d.D, d.Hr, mt * kTile, nt * kTile, 0, d.WV, acc, nullptr, gs);
+        gemm_tile_deep(A, Bo, d.D, d.Hr, mt * kTile, nt * kTile, 0, d.WV, acc, gs);
         const int tx = tid % 16, ty = tid / 16;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {

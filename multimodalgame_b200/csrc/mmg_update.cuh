@@ -1,21 +1,29 @@
-// K_wgrad, K_reduce_norm, K_update.
+// K_wgrad, K_grad_norm, K_peer_reduce_scatter, K_update.
 //
-// K_wgrad: every weight / bias gradient of the four modules as ONE grouped launch of 64x64 fp32 tiles
-//   C = A^T . B reduced over the T*B (or B, or B*D) rows.  Each tensor picks its own split-K factor so that every CTA
-//   multiplies a K-slice of ~128 rows (balanced single wave); split 0 writes straight into the flat gradient buffer,
-//   splits 1.. into arena slabs that K_reduce_norm adds in a fixed order, so gradients are bit-reproducible run to run
-//   (no float atomics).  Column sums (bias-like gradients) run through the same tiles with a constant-one operand.
-// K_reduce_norm: gradient += slabs, plus per-CTA partial sums of squares per module (float4 streams).
+// K_wgrad: every weight / bias gradient of the four modules as ONE grouped launch of 64x64 fp32 tiles C = A^T . B reduced
+//   over the T*B (or B, or B*D) rows.  Each CTA stages its WHOLE K-slice (<= 128 rows of both operands, 70 KB) in shared
+//   memory with asynchronous 16-byte copies — every load of the CTA is in flight at once, one barrier — then multiplies.
+//   Each problem picks its own split-K factor; a split CTA writes its partial tile (split 0 into the gradient buffer,
+//   the others into arena slabs) and takes a ticket on the OUTPUT tile: the last CTA to arrive re-reads all partials in
+//   split order (bit-reproducible whatever the arrival order, no float atomics), writes the final tile and its sum of
+//   squares.  The CTA that finishes the last output tile adds the per-tile sums in tile order into the four per-module
+//   squared gradient norms, so clip + optimizer can follow directly: no separate reduction pass over the gradient.
+//   Column sums (bias-like gradients) run through the same tiles with a constant-one operand.
+// K_grad_norm: per-module sums of squares of a finished gradient buffer (after an NCCL all-reduce).
+// K_peer_reduce_scatter: data-parallel gradient sum over NVLink peer memory, two-shot: every rank sums ITS 1/G slice of
+//   all ranks' send buffers and stores the result (+ the slice's sums of squares) into every rank's receive buffer.
 // K_update: torch.nn.utils.clip_grad_norm(params, 1.) per module (model.py:1310,1317,1323,1329) fused with the
 //   optimizer step (RMSprop default, model.py:1725; Adam / SGD, 1111-1137).
 #pragma once
 #include "mmg_kernels.cuh"
+#include "mmg_loss.cuh"
 
 namespace mmg {
 
-enum { WG_GEMM = 0, WG_ROWVEC = 1, WG_CODEBIAS = 2 };
-enum { kRowvecCols = 256 };
-enum { kMaxWgProblems = 26, kWgradKSlice = 128 };
+enum { WG_GEMM = 0, WG_ROWVEC = 1, WG_CODEBIAS = 2, WG_ZERO = 3 };
+enum { kRowvecCols = 256, kZeroChunk = 4096 };
+enum { kMaxWgProblems = 48, kWgradKSlice = 128, kWgLd = kTile + 4, kMaxOutTiles = 8192 };
+MMG_HOST_DEVICE int wgrad_smem_bytes() { return (2 * kWgradKSlice * kWgLd + kWgradKSlice) * 4; }
 
 struct WgProblem {
     Operand A, B;
@@ -27,19 +35,105 @@ struct WgProblem {
     int kind;
     int nsplit;
     int tile_begin, ntm, ntn;
+    int out_begin;        // index of this problem's first OUTPUT tile (tickets, per-tile sums of squares)
+    int seg;              // module (MMG_SEG_*) the output belongs to
 };
 struct WgTable {
     WgProblem p[kMaxWgProblems];
     int tile_begin[kMaxWgProblems + 1];   // compact copy for the per-CTA problem lookup
-    int count, total_tiles;
+    int count, total_tiles, total_out;
     long long slab_stride;   // floats between consecutive arena slabs (= flat layout total)
 };
+struct WgSync {               // workspace pieces of the split-K / norm protocol
+    unsigned* tile_tickets;   // [kMaxOutTiles], zero between launches
+    float* tile_norm;         // [kMaxOutTiles] sum of squares of each finished output tile
+    unsigned* done;           // finished output tiles of this launch
+    double* norm_final;       // [4] per-module sum of squares of the gradient
+};
 
-MMG_GLOBAL void __launch_bounds__(kGemmThreads, 4)
-k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, const float* code_bias, const float* d_as) {
+// Stages rows [k0, k1) x columns [i0, i0 + 64) of a k-major operand into S[kk][kWgLd]; rows up to `rows_pad` are zeroed.
+// PLAIN / RELUGRAD rows travel as asynchronous 16-byte copies (RELUGRAD: the raw hidden values, transformed in place later).
+MMG_DEVICE void wg_stage(const Operand& op, int k0, int k1, int i0, int ilim, float* S, int rows_pad, int tid) {
+    const bool vec = op.kind != OP_ONES && (op.ld & 3) == 0 && aligned16(op.p) &&
+                     (op.kind == OP_RELUGRAD_TSUM ? aligned16(op.w2)
+                                                  : (op.p2 == nullptr || op.split == 0 ||
+                                                     ((op.split & 3) == 0 && (op.ld2 & 3) == 0 && aligned16(op.p2))));
+    for (int idx = tid; idx < rows_pad * (kTile / 4); idx += kGemmThreads) {
+        const int kk = idx >> 4, g = idx & 15;
+        const int k = k0 + kk, i = i0 + 4 * g;
+        float* dst = S + kk * kWgLd + 4 * g;
+        if (k >= k1 || i >= ilim) { *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+        if (vec && i + 3 < ilim) {
+            if (op.kind == OP_RELUGRAD_TSUM) {
+                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int t = 0; t < op.mod; ++t) {
+                    const float4 h = ldg4(reinterpret_cast<const float4*>(op.p + ((size_t)t * op.ld2 + k) * op.ld + i));
+                    const float gg = ldg(op.g + (size_t)t * op.ld2 + k);
+                    r.x += h.x > 0.f ? gg : 0.f; r.y += h.y > 0.f ? gg : 0.f; r.z += h.z > 0.f ? gg : 0.f; r.w += h.w > 0.f ? gg : 0.f;
+                }
+                const float4 w = ldg4(reinterpret_cast<const float4*>(op.w2 + i));
+                *reinterpret_cast<float4*>(dst) = make_float4(r.x * w.x, r.y * w.y, r.z * w.z, r.w * w.w);
+            } else if (op.split > 0 && i >= op.split) {
+                cp_async16(dst, op.p2 + (size_t)k * op.ld2 + (i - op.split));
+            } else {
+                const int row = op.mod > 0 ? k % op.mod : k;
+                cp_async16(dst, op.p + (size_t)row * op.ld + i);
+            }
+            continue;
+        }
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (i + c >= ilim) continue;
+            if (op.kind == OP_RELUGRAD) v[c] = ldg(op.p + (size_t)k * op.ld + i + c);      // raw, see wg_relu_pass
+            else v[c] = operand_load(op, k, i + c);
+        }
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+// RELUGRAD operand in place: hidden value h -> (h > 0) ? g[k] : 0; the per-column factor w2[i] is applied to the rows of C.
+MMG_DEVICE void wg_relu_pass(const Operand& op, int k0, int k1, float* S, float* gk, int tid) {
+    const int nk = k1 - k0;
+    for (int kk = tid; kk < nk; kk += kGemmThreads) gk[kk] = ldg(op.g + k0 + kk);
+    MMG_SYNCTHREADS();
+    for (int idx = tid; idx < nk * (kTile / 4); idx += kGemmThreads) {
+        const int kk = idx >> 4, g = idx & 15;
+        float4* q = reinterpret_cast<float4*>(S + kk * kWgLd + 4 * g);
+        float4 h = *q;
+        const float gg = gk[kk];
+        h.x = h.x > 0.f ? gg : 0.f; h.y = h.y > 0.f ? gg : 0.f; h.z = h.z > 0.f ? gg : 0.f; h.w = h.w > 0.f ? gg : 0.f;
+        *q = h;
+    }
+}
+
+MMG_DEVICE int wg_seg_of_out(const WgTable& tab, int o) {
+    int pi = 0;
+    while (pi + 1 < tab.count && o >= tab.p[pi + 1].out_begin) ++pi;
+    return tab.p[pi].seg;
+}
+
+// Block-wide sum of one float per thread (256 threads), result valid in thread 0.
+MMG_DEVICE float block_sum_256(float v, float* red) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    v = warp_sum(v);
+    if (lane == 0) red[warp] = v;
+    MMG_SYNCTHREADS();
+    float s = 0.f;
+    if (tid == 0) for (int w = 0; w < kGemmThreads / 32; ++w) s += red[w];
+    return s;
+}
+
+MMG_GLOBAL void __launch_bounds__(kGemmThreads, 3)
+k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, const float* code_bias, const float* d_as,
+        WgSync sy, PeerView pv, WsPtrs W, int n_loss_parts) {
     pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
     pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
-    MMG_SHARED __attribute__((aligned(16))) float gs[kGemmSmemFloats];
+    MMG_DYN_SMEM(smem_raw);
+    float* As = reinterpret_cast<float*>(smem_raw);
+    float* Bs = As + kWgradKSlice * kWgLd;
+    float* gk = Bs + kWgradKSlice * kWgLd;
+    MMG_SHARED float red[kGemmThreads / 32];
+    MMG_SHARED int s_flag;
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
     int tile = blockIdx.x, pi = 0;
     while (pi + 1 < tab.count && tile >= tab.tile_begin[pi + 1]) ++pi;
@@ -48,67 +142,249 @@ k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, co
     const int per_split = pr.ntm * pr.ntn;
     const int s = tile / per_split;
     tile %= per_split;
+    const int out_tile = pr.out_begin + tile;
     const int nt = tile % pr.ntn, mt = tile / pr.ntn;
     float* slab = s == 0 ? grads : arena + (size_t)(s - 1) * tab.slab_stride;
     const int ks = round_up(cdiv(pr.K, pr.nsplit), 4);
     const int k0 = s * ks, k1 = min(pr.K, k0 + ks);
+    float ss = 0.f;             // this thread's share of the finished tile's sum of squares
+    bool fin = pr.nsplit == 1;  // this CTA holds the final values of its output tile
 
     if (pr.kind == WG_GEMM) {
-        float acc[4][4];
-        float cs = 0.f;
+        const int m0 = mt * kTile, n0 = nt * kTile;
+        float2 acc2[4][2];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { acc2[a][0] = make_float2(0.f, 0.f); acc2[a][1] = make_float2(0.f, 0.f); }
         const bool want_bias = pr.bias_off >= 0 && nt == 0;
-        gemm_tile(pr.A, pr.B, pr.M, pr.N, mt * kTile, nt * kTile, k0, k1, acc, want_bias ? &cs : nullptr, gs);
-        const int j0 = nt * kTile + tx * 4;
-        const bool vec = j0 + 3 < pr.N && (pr.ldc & 3) == 0 && (pr.c_off & 3) == 0 && pr.sig_rows == nullptr;
+        float csa[4] = {0.f, 0.f, 0.f, 0.f};       // column sums of A (bias gradients) of rows ty*4.., held by the tx == 0 threads
+        MMG_SHARED float csum_sm[kTile];
+        if (want_bias && tid < kTile) csum_sm[tid] = 0.f;
+        // the K-slice in passes of at most kWgradKSlice rows (one pass at the BASELINE.json shapes)
+        for (int kb = k0; kb < k1; kb += kWgradKSlice) {
+        const int ke = min(k1, kb + kWgradKSlice);
+        const int rows_pad = round_up(ke - kb, 8);
+        if (kb > k0) MMG_SYNCTHREADS();            // the previous pass has been consumed
+        wg_stage(pr.A, kb, ke, m0, pr.M, As, rows_pad, tid);
+        wg_stage(pr.B, kb, ke, n0, pr.N, Bs, rows_pad, tid);
+        cp_async_wait_all();
+        MMG_SYNCTHREADS();
+        if (pr.A.kind == OP_RELUGRAD) { wg_relu_pass(pr.A, kb, ke, As, gk, tid); MMG_SYNCTHREADS(); }
+#pragma unroll 8
+        for (int kk = 0; kk < rows_pad; ++kk) {
+            const float4 a4 = *reinterpret_cast<const float4*>(As + kk * kWgLd + ty * 4);
+            const float4 b4 = *reinterpret_cast<const float4*>(Bs + kk * kWgLd + tx * 4);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float2 b01 = make_float2(b4.x, b4.y), b23 = make_float2(b4.z, b4.w);
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int i = mt * kTile + ty * 4 + a;
-            if (i >= pr.M) continue;
-            if (vec) {
-                *reinterpret_cast<float4*>(slab + pr.c_off + (size_t)i * pr.ldc + j0) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
-                continue;
-            }
-            float rs = 1.f;
-            if (pr.sig_rows != nullptr) { const float c0 = sigmoidf_(ldg(pr.sig_rows + i)); rs = c0 * (1.f - c0); }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int j = j0 + c;
-                if (j < pr.N) slab[pr.c_off + (size_t)i * pr.ldc + j] = acc[a][c] * rs;
+            for (int a = 0; a < 4; ++a) {      // packed fp32x2 FMA (FFMA2): 8 instructions for the 4x4 update
+                const float2 aa = make_float2(av[a], av[a]);
+                acc2[a][0] = ffma2(aa, b01, acc2[a][0]);
+                acc2[a][1] = ffma2(aa, b23, acc2[a][1]);
             }
         }
-        if (want_bias && tid < kTile && mt * kTile + tid < pr.M) slab[pr.bias_off + mt * kTile + tid] = cs;
+        if (want_bias) {
+            // column sums of A (bias gradients): thread (column c, quarter q) adds rows q, q + 4, ...; the quarters meet in the
+            // idle tail of gk (128 floats: 64 columns x ... two halves at a time)
+            const int c = tid & 63, q = tid >> 6;
+            float s0 = 0.f, s1 = 0.f;
+            for (int kk = q; kk < rows_pad; kk += 8) { s0 += As[kk * kWgLd + c]; s1 += As[(kk + 4) * kWgLd + c]; }
+            MMG_SYNCTHREADS();                      // gk (relu pass) is no longer read
+            if (q >= 2) gk[(q - 2) * 64 + c] = s0 + s1;
+            MMG_SYNCTHREADS();
+            float part = s0 + s1;
+            if (q < 2) part += gk[q * 64 + c];
+            MMG_SYNCTHREADS();
+            if (q == 1) gk[c] = part;
+            MMG_SYNCTHREADS();
+            if (q == 0) csum_sm[c] += part + gk[c];
+        }
+        }
+        // row factors: w2[i] of a relu-gradient operand, d sigmoid(code_bias)
+        auto row_scale = [&](int i) {
+            float r = 1.f;
+            if (pr.A.kind == OP_RELUGRAD) r = ldg(pr.A.w2 + i);
+            if (pr.sig_rows != nullptr) { const float c0 = sigmoidf_(ldg(pr.sig_rows + i)); r *= c0 * (1.f - c0); }
+            return r;
+        };
+        const bool scaled = pr.A.kind == OP_RELUGRAD || pr.sig_rows != nullptr;
+        const int j0 = n0 + tx * 4;
+        const bool vec = j0 + 3 < pr.N && (pr.ldc & 3) == 0 && (pr.c_off & 3) == 0;
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int i = m0 + ty * 4 + a;
+            const float rs = (scaled && i < pr.M) ? row_scale(i) : 1.f;
+            acc[a][0] = acc2[a][0].x * rs; acc[a][1] = acc2[a][0].y * rs; acc[a][2] = acc2[a][1].x * rs; acc[a][3] = acc2[a][1].y * rs;
+        }
+        const bool bias_thread = want_bias && tx == 0;
+        if (want_bias) {
+            MMG_SYNCTHREADS();
+            if (tx == 0) { csa[0] = csum_sm[ty * 4]; csa[1] = csum_sm[ty * 4 + 1]; csa[2] = csum_sm[ty * 4 + 2]; csa[3] = csum_sm[ty * 4 + 3]; }
+        }
+        if (bias_thread && scaled) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) if (m0 + ty * 4 + a < pr.M) csa[a] *= row_scale(m0 + ty * 4 + a);
+        }
+        // this CTA's (partial or final) tile
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int i = m0 + ty * 4 + a;
+            if (i >= pr.M) continue;
+            float* row = slab + pr.c_off + (size_t)i * pr.ldc;
+            if (vec) *reinterpret_cast<float4*>(row + j0) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+            else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) if (j0 + c < pr.N) row[j0 + c] = acc[a][c];
+            }
+        }
+        if (bias_thread) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) if (m0 + ty * 4 + a < pr.M) slab[pr.bias_off + m0 + ty * 4 + a] = csa[a];
+        }
+        if (pr.nsplit > 1) {
+            fence_acquire();             // every thread: its partial is visible device-wide before the ticket is taken
+            MMG_SYNCTHREADS();
+            if (tid == 0) s_flag = (ticket_take(sy.tile_tickets + out_tile) == (unsigned)pr.nsplit - 1) ? 1 : 0;
+            MMG_SYNCTHREADS();
+            fin = s_flag != 0;
+            if (fin) {
+                fence_acquire();
+                // last split to arrive: sum all partials in split order and write the final tile
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int i = m0 + ty * 4 + a;
+                    if (i >= pr.M) continue;
+                    const size_t off = (size_t)pr.c_off + (size_t)i * pr.ldc + j0;
+                    if (vec) {
+                        float4 v = ld_cg4(grads + off);
+                        for (int q = 1; q < pr.nsplit; ++q) {
+                            const float4 t4 = ld_cg4(arena + (size_t)(q - 1) * tab.slab_stride + off);
+                            v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w;
+                        }
+                        *reinterpret_cast<float4*>(grads + off) = v;
+                        acc[a][0] = v.x; acc[a][1] = v.y; acc[a][2] = v.z; acc[a][3] = v.w;
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            if (j0 + c >= pr.N) continue;
+                            float v = ld_cg(grads + off + c);
+                            for (int q = 1; q < pr.nsplit; ++q) v += ld_cg(arena + (size_t)(q - 1) * tab.slab_stride + off + c);
+                            grads[off + c] = v;
+                            acc[a][c] = v;
+                        }
+                    }
+                }
+                if (bias_thread) {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        if (m0 + ty * 4 + a >= pr.M) continue;
+                        const size_t off = (size_t)pr.bias_off + m0 + ty * 4 + a;
+                        float v = ld_cg(grads + off);
+                        for (int q = 1; q < pr.nsplit; ++q) v += ld_cg(arena + (size_t)(q - 1) * tab.slab_stride + off);
+                        grads[off] = v;
+                        csa[a] = v;
+                    }
+                }
+            }
+        }
+        if (fin) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                if (m0 + ty * 4 + a >= pr.M) continue;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) if (j0 + c < pr.N) ss = fmaf(acc[a][c], acc[a][c], ss);
+            }
+            if (bias_thread) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a) if (m0 + ty * 4 + a < pr.M) ss = fmaf(csa[a], csa[a], ss);
+            }
+        }
     } else if (pr.kind == WG_ROWVEC) {
         // single-row products C[0][j] = sum_k a[k] B[k][j] (STOP head, linear2 of both baselines): one column per thread
         // instead of a 64x64 tile with 63 idle rows.  A: plain (K, 1) vector; B: plain k-major rows.
+        // thread (column quad cq, row group kg): rows k0 + kg, + 4, ... of 4 adjacent columns, 8 independent loads in flight;
+        // the 4 row groups meet in shared memory, thread tid then owns column nt * 256 + tid
         const int j = nt * kRowvecCols + tid;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f}, asum[4] = {0.f, 0.f, 0.f, 0.f};
+        const int cq = tid & 63, kg = tid >> 6, jq = nt * kRowvecCols + 4 * cq;
         const float* a = pr.A.p;
-        const float* bp = pr.B.p + (j < pr.N ? j : 0);
-        int k = k0;
-        for (; k + 3 < k1; k += 4) {
+        const bool vecb = (pr.B.ld & 3) == 0 && aligned16(pr.B.p) && jq + 3 < pr.N;
+        float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float asum_t = 0.f;
+        for (int kb = k0 + kg; kb < k1; kb += 32) {
+            float av[8];
+            float4 bv4[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float av = ldg(a + (size_t)(k + u) * pr.A.ld);
-                asum[u] += av;
-                acc[u] = fmaf(av, ldg(bp + (size_t)(k + u) * pr.B.ld), acc[u]);
+            for (int u = 0; u < 8; ++u) {
+                const int k = kb + 4 * u;
+                av[u] = k < k1 ? ldg(a + (size_t)k * pr.A.ld) : 0.f;
+                bv4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < k1) {
+                    const float* bp = pr.B.p + (size_t)k * pr.B.ld + jq;
+                    if (vecb) bv4[u] = ldg4(reinterpret_cast<const float4*>(bp));
+                    else {
+                        if (jq < pr.N) bv4[u].x = ldg(bp);
+                        if (jq + 1 < pr.N) bv4[u].y = ldg(bp + 1);
+                        if (jq + 2 < pr.N) bv4[u].z = ldg(bp + 2);
+                        if (jq + 3 < pr.N) bv4[u].w = ldg(bp + 3);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                asum_t += av[u];
+                acc4.x = fmaf(av[u], bv4[u].x, acc4.x); acc4.y = fmaf(av[u], bv4[u].y, acc4.y);
+                acc4.z = fmaf(av[u], bv4[u].z, acc4.z); acc4.w = fmaf(av[u], bv4[u].w, acc4.w);
             }
         }
-        for (; k < k1; ++k) {
-            const float av = ldg(a + (size_t)k * pr.A.ld);
-            asum[0] += av;
-            acc[0] = fmaf(av, ldg(bp + (size_t)k * pr.B.ld), acc[0]);
+        float* rv = As;                                   // [4 row groups][256 columns] + [4] sums of a
+        *reinterpret_cast<float4*>(rv + kg * kRowvecCols + 4 * cq) = acc4;
+        if (cq == 0) rv[4 * kRowvecCols + kg] = asum_t;
+        MMG_SYNCTHREADS();
+        float v = (rv[tid] + rv[kRowvecCols + tid]) + (rv[2 * kRowvecCols + tid] + rv[3 * kRowvecCols + tid]);
+        float bv = (rv[4 * kRowvecCols] + rv[4 * kRowvecCols + 1]) + (rv[4 * kRowvecCols + 2] + rv[4 * kRowvecCols + 3]);
+        const bool want_bias = pr.bias_off >= 0 && nt == 0 && tid == 0;
+        if (j < pr.N) slab[pr.c_off + j] = v;
+        if (want_bias) slab[pr.bias_off] = bv;
+        if (pr.nsplit > 1) {
+            fence_acquire();
+            MMG_SYNCTHREADS();
+            if (tid == 0) s_flag = (ticket_take(sy.tile_tickets + out_tile) == (unsigned)pr.nsplit - 1) ? 1 : 0;
+            MMG_SYNCTHREADS();
+            fin = s_flag != 0;
+            if (fin) {
+                fence_acquire();
+                if (j < pr.N) {
+                    v = ld_cg(grads + pr.c_off + j);
+                    for (int q = 1; q < pr.nsplit; ++q) v += ld_cg(arena + (size_t)(q - 1) * tab.slab_stride + pr.c_off + j);
+                    grads[pr.c_off + j] = v;
+                }
+                if (want_bias) {
+                    bv = ld_cg(grads + pr.bias_off);
+                    for (int q = 1; q < pr.nsplit; ++q) bv += ld_cg(arena + (size_t)(q - 1) * tab.slab_stride + pr.bias_off);
+                    grads[pr.bias_off] = bv;
+                }
+            }
         }
-        if (j < pr.N) slab[pr.c_off + j] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-        if (pr.bias_off >= 0 && nt == 0 && tid == 0) slab[pr.bias_off] = (asum[0] + asum[1]) + (asum[2] + asum[3]);
+        if (fin) {
+            if (j < pr.N) ss = v * v;
+            if (want_bias) ss = fmaf(bv, bv, ss);
+        }
+    } else if (pr.kind == WG_ZERO) {
+        // tensors no gradient problem covers this iteration (untrained modules, the code path under -ignore_code ...):
+        // the gradient buffer is fully defined after every backward pass
+        const long long lo = (long long)tile * kZeroChunk, hi = min((long long)pr.M, lo + kZeroChunk);
+        for (long long i = lo + 4 * tid; i < hi; i += 4 * kGemmThreads)
+            *reinterpret_cast<float4*>(grads + pr.c_off + i) = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
         // generic-path only (the fast backward kernel emits per-example partials instead):
         // d code_bias[j] = c0 (1 - c0) sum_n code_layer.weight[n][j] * (sum_b d_as[t=0][b][n])   (model.py:199-200)
-        float* v = gs;
+        float* v = As;
+        const int vcap = 2 * kWgradKSlice * kWgLd;
         for (int j0 = 0; j0 < d.M; j0 += kGemmThreads) {
             const int j = j0 + tid;
             float accj = 0.f;
-            for (int nb = 0; nb < d.Hi; nb += kGemmSmemFloats) {
-                const int nlim = min(d.Hi - nb, (int)kGemmSmemFloats);
+            for (int nb = 0; nb < d.Hi; nb += vcap) {
+                const int nlim = min(d.Hi - nb, vcap);
                 MMG_SYNCTHREADS();
                 for (int n = tid; n < nlim; n += kGemmThreads) {
                     float sv = 0.f;
@@ -120,8 +396,49 @@ k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, co
             }
             if (j < d.M) {
                 const float c0 = sigmoidf_(ldg(code_bias + j));
-                slab[pr.c_off + j] = accj * c0 * (1.f - c0);
+                const float r = accj * c0 * (1.f - c0);
+                grads[pr.c_off + j] = r;
+                ss = fmaf(r, r, ss);
             }
+        }
+    }
+    if (!fin) return;
+    if (pv.world > 1) fence_system();     // the tile lives in the symmetric send buffer: visible to the peers before it is counted
+    // ---- finished output tile: its sum of squares; the CTA that finishes the LAST tile adds them up per module --------------
+    const float tile_ss = block_sum_256(ss, red);
+    if (tid == 0) {
+        sy.tile_norm[out_tile] = tile_ss;
+        if (pr.nsplit > 1) sy.tile_tickets[out_tile] = 0;                // ready for the next launch
+        s_flag = (ticket_take(sy.done) == (unsigned)tab.total_out - 1) ? 1 : 0;
+    }
+    MMG_SYNCTHREADS();
+    if (!s_flag) return;
+    fence_acquire();
+    {
+        MMG_SHARED double dred[4][kGemmThreads / 32];
+        double s4[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int o = tid; o < tab.total_out; o += kGemmThreads) s4[wg_seg_of_out(tab, o)] += (double)sy.tile_norm[o];
+        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double v = warp_sum_d(s4[k]);
+            if (lane == 0) dred[k][warp] = v;
+        }
+        MMG_SYNCTHREADS();
+        if (tid < 4) {
+            double v = 0.0;
+            for (int w = 0; w < kGemmThreads / 32; ++w) v += dred[tid][w];
+            sy.norm_final[tid] = v;
+        }
+        if (tid == 0) *sy.done = 0;
+        // fused iteration: the backward kernel left per-CTA partials of the five loss values; they are added up here, off
+        // every critical path (the values are only reported)
+        if (n_loss_parts > 0) { MMG_SYNCTHREADS(); loss_finalize(d, W, n_loss_parts); }
+        if (pv.world > 1) {
+            // `grads` is this rank's symmetric send buffer and it is complete: raise flag row 1 on every peer
+            fence_system();
+            MMG_SYNCTHREADS();
+            if (tid < pv.world) peer_signal(pv.flags[tid] + MMG_MAX_PEERS + pv.rank, pv.iter);
         }
     }
 }
@@ -134,55 +451,17 @@ struct SegInfo {
     long long whead_begin, whead_end, shead_begin, shead_end;
     int shead_active, whead_stat;
 };
-// Per state_dict tensor: where it lives, how many floats are real (the rest of its 4-float slot is padding) and how
-// many split-K partials K_wgrad produced for it.
-struct SplitTable {
-    long long begin[MMG_P_COUNT + 1];
-    int numel[MMG_P_COUNT];
-    int nsplit[MMG_P_COUNT];
-};
 
 MMG_DEVICE int seg_of(const long long* seg_begin, long long i) {
     return i < seg_begin[1] ? 0 : (i < seg_begin[2] ? 1 : (i < seg_begin[3] ? 2 : 3));
 }
-MMG_DEVICE int tensor_of(const SplitTable& st, long long i) {
-    int lo = 0, hi = MMG_P_COUNT - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (st.begin[mid] <= i) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
 
-// grads (+)= slabs, scaled; per-CTA partial sums of squares per module -> norm_part[module * gridDim.x + cta].
-// do_reduce = 0: gradients are final already (after the data-parallel all-reduce), only the norms are computed.
-MMG_DEVICE void reduce_norm_body(const SegInfo& seg, const SplitTable& st, const float* arena, long long slab_stride,
-                                 float* grads, float scale, int do_reduce, float* norm_part) {
+// Per-CTA partial sums of squares per module -> norm_part[module * gridDim.x + cta]; the last CTA to finish adds the
+// partials in CTA order into norm_final[4] (deterministic).  Returns true in the finishing CTA (all its threads).
+MMG_DEVICE bool finish_norms(const float (&ss)[4], float* norm_part, unsigned* ticket, double* norm_final) {
     MMG_SHARED float red[4][kUpdThreads / 32];
+    MMG_SHARED int s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long total = seg.begin[4];
-    float ss[4] = {0.f, 0.f, 0.f, 0.f};
-    for (long long i = 4 * ((long long)blockIdx.x * kUpdThreads + tid); i < total; i += 4ll * gridDim.x * kUpdThreads) {
-        const int sg = seg_of(seg.begin, i);
-        float4 g = *reinterpret_cast<const float4*>(grads + i);
-        if (do_reduce) {
-            const int tn = tensor_of(st, i);
-            const long long valid = st.begin[tn] + st.numel[tn] - i;   // real floats in this group (>= 1)
-            if (!seg.trained[sg] || st.nsplit[tn] == 0) {      // untrained module, or a tensor no gradient problem covers
-                g = make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-                for (int s = 1; s < st.nsplit[tn]; ++s) {
-                    const float4 a = *reinterpret_cast<const float4*>(arena + (size_t)(s - 1) * slab_stride + i);
-                    g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
-                }
-                if (valid < 4) { if (valid < 2) g.y = 0.f; if (valid < 3) g.z = 0.f; g.w = 0.f; }
-            }
-            g.x *= scale; g.y *= scale; g.z *= scale; g.w *= scale;
-            *reinterpret_cast<float4*>(grads + i) = g;
-        }
-        ss[sg] = fmaf(g.x, g.x, ss[sg]); ss[sg] = fmaf(g.y, g.y, ss[sg]);
-        ss[sg] = fmaf(g.z, g.z, ss[sg]); ss[sg] = fmaf(g.w, g.w, ss[sg]);
-    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const float v = warp_sum(ss[k]);
@@ -194,95 +473,114 @@ MMG_DEVICE void reduce_norm_body(const SegInfo& seg, const SplitTable& st, const
         for (int w = 0; w < kUpdThreads / 32; ++w) v += red[tid][w];
         norm_part[tid * gridDim.x + blockIdx.x] = v;
     }
+    fence_acquire();
+    MMG_SYNCTHREADS();
+    if (tid == 0) s_last = (ticket_take(ticket) == gridDim.x - 1) ? 1 : 0;
+    MMG_SYNCTHREADS();
+    if (!s_last) return false;
+    fence_acquire();
+    if (warp < 4) {
+        double v = 0.0;
+        for (int c0 = 0; c0 < (int)gridDim.x; c0 += 32 * 8) {       // 8 loads in flight per lane, added in a fixed order
+            float pv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = c0 + u * 32 + lane;
+                pv[u] = c < (int)gridDim.x ? norm_part[warp * gridDim.x + c] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v += (double)pv[u];
+        }
+        v = warp_sum_d(v);
+        if (lane == 0) norm_final[warp] = v;
+    }
+    if (tid == 0) *ticket = 0;
+    MMG_SYNCTHREADS();
+    return true;
 }
 
+// Per-module sums of squares of a finished gradient buffer (data-parallel NCCL variant: after the all-reduce).
 MMG_GLOBAL void __launch_bounds__(kUpdThreads)
-k_reduce_norm(SegInfo seg, SplitTable st, const float* arena, long long slab_stride, float* grads, float scale,
-              int do_reduce, float* norm_part, PeerView pv, unsigned* ticket) {
+k_grad_norm(SegInfo seg, const float* grads, float* norm_part, unsigned* ticket, double* norm_final) {
     pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
     pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
     const int tid = threadIdx.x;
-    reduce_norm_body(seg, st, arena, slab_stride, grads, scale, do_reduce, norm_part);
-    if (pv.world > 1) {
-        // `grads` is this rank's symmetric send buffer: once every CTA has written its part, raise flag row 1 on all peers
-        MMG_SHARED int s_last;
-        fence_system();
-        MMG_SYNCTHREADS();
-        if (tid == 0) s_last = (ticket_take(ticket) == gridDim.x - 1) ? 1 : 0;
-        MMG_SYNCTHREADS();
-        if (s_last) {
-            if (tid < pv.world) peer_signal(pv.flags[tid] + MMG_MAX_PEERS + pv.rank, pv.iter);
-            if (tid == 0) *ticket = 0;
-        }
-    }
-}
-
-// Data-parallel gradient sum over NVLink peer memory, fused with the per-module sum of squares: every rank reads all
-// send buffers (one-shot, rank order => bit-identical results everywhere) and writes the global gradient locally.
-MMG_GLOBAL void __launch_bounds__(kUpdThreads)
-k_peer_allreduce_norm(SegInfo seg, PeerView pv, float* grads_out, float* norm_part) {
-    pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
-    pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
-    MMG_SHARED float red[4][kUpdThreads / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < pv.world && !peer_wait(pv.flags[pv.rank] + MMG_MAX_PEERS + tid, pv.iter)) *pv.error = 2;
-    MMG_SYNCTHREADS();
     const long long total = seg.begin[4];
     float ss[4] = {0.f, 0.f, 0.f, 0.f};
     for (long long i = 4 * ((long long)blockIdx.x * kUpdThreads + tid); i < total; i += 4ll * gridDim.x * kUpdThreads) {
+        const int sg = seg_of(seg.begin, i);
+        const float4 g = *reinterpret_cast<const float4*>(grads + i);
+        ss[sg] = fmaf(g.x, g.x, ss[sg]); ss[sg] = fmaf(g.y, g.y, ss[sg]);
+        ss[sg] = fmaf(g.z, g.z, ss[sg]); ss[sg] = fmaf(g.w, g.w, ss[sg]);
+    }
+    finish_norms(ss, norm_part, ticket, norm_final);
+}
+
+// Data-parallel gradient sum over NVLink peer memory, two-shot.  Rank r owns the r-th 1/G slice of the flat gradient:
+// it waits until every rank has published its send buffer, sums the slice over all send buffers (rank order => the result
+// is the same number whoever computes it), stores it into EVERY rank's receive buffer together with the slice's per-module
+// sums of squares, and raises flag row 2 on every rank.  Per rank and iteration: (G-1)/G of the gradient in over NVLink and
+// the same amount out, instead of (G-1) whole gradients in with a one-shot read.
+MMG_GLOBAL void __launch_bounds__(kUpdThreads)
+k_peer_reduce_scatter(SegInfo seg, PeerView pv, float* norm_part, unsigned* ticket, double* norm_scratch) {
+    pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
+    pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
+    const int tid = threadIdx.x;
+    if (tid < pv.world && !peer_wait(pv.flags[pv.rank] + MMG_MAX_PEERS + tid, pv.iter, pv.error)) *pv.error = 2;
+    MMG_SYNCTHREADS();
+    const long long n4 = seg.begin[4] / 4;
+    const long long per = cdiv64(n4, pv.world);
+    const long long lo = per * pv.rank, hi = min(n4, lo + per);
+    float ss[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long q = lo + (long long)blockIdx.x * kUpdThreads + tid; q < hi; q += (long long)gridDim.x * kUpdThreads) {
+        const long long i = 4 * q;
         const int sg = seg_of(seg.begin, i);
         float4 g = peer_load4(pv.send[0] + i);
         for (int r = 1; r < pv.world; ++r) {
             const float4 a = peer_load4(pv.send[r] + i);
             g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
         }
-        *reinterpret_cast<float4*>(grads_out + i) = g;
+        for (int r = 0; r < pv.world; ++r) *reinterpret_cast<float4*>(pv.recv[r] + i) = g;
         ss[sg] = fmaf(g.x, g.x, ss[sg]); ss[sg] = fmaf(g.y, g.y, ss[sg]);
         ss[sg] = fmaf(g.z, g.z, ss[sg]); ss[sg] = fmaf(g.w, g.w, ss[sg]);
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float v = warp_sum(ss[k]);
-        if (lane == 0) red[k][warp] = v;
-    }
-    MMG_SYNCTHREADS();
-    if (tid < 4) {
-        float v = 0.f;
-        for (int w = 0; w < kUpdThreads / 32; ++w) v += red[tid][w];
-        norm_part[tid * gridDim.x + blockIdx.x] = v;
+    fence_system();             // this CTA's remote stores are visible system-wide before it is counted as finished
+    if (finish_norms(ss, norm_part, ticket, norm_scratch)) {
+        // the whole slice is reduced and stored: publish its sums of squares and raise flag row 2 everywhere
+        if (tid < 4 * pv.world) pv.norms[tid >> 2][4 * pv.rank + (tid & 3)] = norm_scratch[tid & 3];
+        fence_system();
+        MMG_SYNCTHREADS();
+        if (tid < pv.world) peer_signal(pv.flags[tid] + 2 * MMG_MAX_PEERS + pv.rank, pv.iter);
     }
 }
 
 struct OptHyper { int optim; float lr, max_norm; long long step; };
 
-MMG_DEVICE void update_body(const SegInfo& seg, const OptHyper& hp, float* params, float* grads, float* state1, float* state2,
-                            const float* norm_part, int n_norm_ctas, float* grad_norms, const double* stats,
-                            const long long* opt_counters) {
+// `norm_final`: per-module sum of squares of the gradient (K_wgrad / K_grad_norm), or with peers: the per-rank slice sums
+// that K_peer_reduce_scatter published (added in rank order after the slices have arrived).
+MMG_DEVICE void update_body(const SegInfo& seg, const OptHyper& hp, float* params, const float* grads_in, float* grads_out,
+                            float* state1, float* state2, const double* norm_final, float* grad_norms, const double* stats,
+                            const long long* opt_counters, const PeerView& pv) {
     MMG_SHARED float coef[4];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (warp < 4) {   // global L2 norm per module, partials summed in a fixed order
-        // per-CTA partials of this module: all loads in flight together (a plain accumulate loop would pay one L2 round
-        // trip per element), added in a fixed order
+    MMG_SHARED int s_err;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_err = 0;
+    if (pv.world > 1) {
+        if (tid < pv.world && !peer_wait(pv.flags[pv.rank] + 2 * MMG_MAX_PEERS + tid, pv.iter, pv.error)) *pv.error = 3;
+        MMG_SYNCTHREADS();
+        if (tid == 0) s_err = *reinterpret_cast<volatile int*>(pv.error);
+    }
+    if (tid < 4) {   // global L2 norm per module
         double v = 0.0;
-        for (int c0 = 0; c0 < n_norm_ctas; c0 += 32 * 8) {
-            float pv[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int c = c0 + u * 32 + lane;
-                pv[u] = c < n_norm_ctas ? norm_part[warp * n_norm_ctas + c] : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v += (double)pv[u];
-        }
-        v = warp_sum_d(v);
-        if (lane == 0) {
-            const float total = (float)sqrt(v);
-            const float cc = hp.max_norm / (total + 1e-6f);       // clip_grad_norm: scale only when coef < 1
-            coef[warp] = cc < 1.f ? cc : 1.f;
-            if (blockIdx.x == 0) grad_norms[warp] = total;
-        }
+        if (pv.world > 1) for (int r = 0; r < pv.world; ++r) v += peer_load_d(pv.norms[pv.rank] + 4 * r + tid);
+        else v = norm_final[tid];
+        const float total = (float)sqrt(v);
+        const float cc = hp.max_norm / (total + 1e-6f);       // clip_grad_norm: scale only when coef < 1
+        coef[tid] = cc < 1.f ? cc : 1.f;
+        if (blockIdx.x == 0) grad_norms[tid] = total;
     }
     MMG_SYNCTHREADS();
+    if (s_err != 0) return;      // a peer wait timed out (sticky): no update from stale or partial sums; the host raises
     const long long total = seg.begin[4];
     float bc1 = 1.f, bc2s = 1.f, bc1w = 1.f, bc2sw = 1.f;
     const bool whead_active = stats[seg.whead_stat] > 0.0;
@@ -300,7 +598,7 @@ MMG_DEVICE void update_body(const SegInfo& seg, const OptHyper& hp, float* param
         const bool in_whead = i >= seg.whead_begin && i < seg.whead_end;
         if (in_whead && !whead_active) continue;
         if (i >= seg.shead_begin && i < seg.shead_end && !seg.shead_active) continue;
-        float4 g4 = *reinterpret_cast<const float4*>(grads + i);
+        float4 g4 = *reinterpret_cast<const float4*>(grads_in + i);
         float4 p4 = *reinterpret_cast<const float4*>(params + i);
         const float cf = coef[sg];
         float g[4] = {g4.x * cf, g4.y * cf, g4.z * cf, g4.w * cf};
@@ -330,45 +628,18 @@ MMG_DEVICE void update_body(const SegInfo& seg, const OptHyper& hp, float* param
 #pragma unroll
             for (int c = 0; c < 4; ++c) p[c] -= hp.lr * g[c];
         }
-        *reinterpret_cast<float4*>(grads + i) = make_float4(g[0], g[1], g[2], g[3]);
+        *reinterpret_cast<float4*>(grads_out + i) = make_float4(g[0], g[1], g[2], g[3]);
         *reinterpret_cast<float4*>(params + i) = make_float4(p[0], p[1], p[2], p[3]);
     }
 }
 
 MMG_GLOBAL void __launch_bounds__(kUpdThreads)
-k_update(SegInfo seg, OptHyper hp, float* params, float* grads, float* state1, float* state2, const float* norm_part,
-         int n_norm_ctas, float* grad_norms, const double* stats, const long long* opt_counters) {
+k_update(SegInfo seg, OptHyper hp, float* params, const float* grads_in, float* grads_out, float* state1, float* state2,
+         const double* norm_final, float* grad_norms, const double* stats, const long long* opt_counters, PeerView pv) {
     pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
     pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
-    update_body(seg, hp, params, grads, state1, state2, norm_part, n_norm_ctas, grad_norms, stats, opt_counters);
+    update_body(seg, hp, params, grads_in, grads_out, state1, state2, norm_final, grad_norms, stats, opt_counters, pv);
 }
-
-#ifndef MMG_CPU_EMU
-// Single-GPU fusion of K_reduce_norm and K_update: the global gradient norm is a grid-wide dependency, resolved by a
-// software grid barrier (arrival counter + spin).  Legal because the host launches at most as many CTAs as are
-// co-resident (occupancy x SM count), so every CTA is running when the first one starts to wait.
-MMG_DEVICE void grid_barrier(unsigned* ctr, unsigned n) {     // ctr[0] arrivals, ctr[1] departures; self-resetting
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1u);
-        for (int spin = 0; spin < (1 << 26) && *reinterpret_cast<volatile unsigned*>(ctr) < n; ++spin) { }   // bounded
-        __threadfence();
-        if (atomicAdd(ctr + 1, 1u) == n - 1) { ctr[0] = 0; ctr[1] = 0; __threadfence(); }
-    }
-    __syncthreads();
-}
-MMG_GLOBAL void __launch_bounds__(kUpdThreads)
-k_reduce_update(SegInfo seg, SplitTable st, const float* arena, long long slab_stride, OptHyper hp, float* params,
-                float* grads, float* state1, float* state2, float* norm_part, float* grad_norms, const double* stats,
-                const long long* opt_counters, unsigned* barrier_ctr) {
-    pdl_wait();
-    pdl_launch_dependents();
-    reduce_norm_body(seg, st, arena, slab_stride, grads, 1.0f, 1, norm_part);
-    grid_barrier(barrier_ctr, gridDim.x);
-    update_body(seg, hp, params, grads, state1, state2, norm_part, (int)gridDim.x, grad_norms, stats, opt_counters);
-}
-#endif
 
 MMG_GLOBAL void k_init_rng(unsigned long long* st, unsigned long long seed) {
     pdl_wait();

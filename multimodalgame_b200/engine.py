@@ -263,8 +263,9 @@ class GameEngine(object):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         group = group if group is not None else dist.group.WORLD
-        tot, so, sto, fo = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
-        self.lib.call("mmg_peer_buffer_layout", C.byref(self.cfg), C.byref(tot), C.byref(so), C.byref(sto), C.byref(fo))
+        tot, so, ro, sto, no, fo = [C.c_int64() for _ in range(6)]
+        self.lib.call("mmg_peer_buffer_layout", C.byref(self.cfg), C.byref(tot), C.byref(so), C.byref(ro), C.byref(sto),
+                      C.byref(no), C.byref(fo))
         buf = symm_mem.empty(int(tot.value), dtype=torch.uint8, device=self.device)
         buf.zero_()
         hdl = symm_mem.rendezvous(buf, group)
@@ -275,10 +276,12 @@ class GameEngine(object):
         p.world, p.rank = world, rank
         for r in range(world):
             base = int(hdl.buffer_ptrs[r])
-            p.d_send[r], p.d_stats[r], p.d_flags[r] = base + so.value, base + sto.value, base + fo.value
+            p.d_send[r], p.d_recv[r], p.d_stats[r] = base + so.value, base + ro.value, base + sto.value
+            p.d_norms[r], p.d_flags[r] = base + no.value, base + fo.value
         self._peer_err = torch.zeros(1, dtype=torch.int32, device=self.device)
         p.d_error = self._peer_err.data_ptr()
         self._peers, self._peer_buf, self._peer_hdl = p, buf, hdl
+        self.peer_check_every = 1024
         torch.cuda.synchronize(self.device)
         hdl.barrier()                      # every rank's buffer is zeroed before anyone's first flag lands
         torch.cuda.synchronize(self.device)
@@ -291,6 +294,10 @@ class GameEngine(object):
         self._peer_iteration(self._inp)
 
     def _peer_iteration(self, inp):
+        # a timed-out peer wait is sticky on the device (updates are skipped from then on): surface it regularly
+        if self.step and self.step % self.peer_check_every == 0 and self.peer_error():
+            raise capi.MmgError("a peer wait timed out (error %d): the ranks lost lockstep; parameters were left untouched "
+                                "from that iteration on" % self.peer_error())
         self.step += 1
         s2 = None if self.state2 is None else self.state2.data_ptr()
         self.lib.call("mmg_train_step_peer", C.byref(self.cfg), self.params.data_ptr(), self.grads.data_ptr(),

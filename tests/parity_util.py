@@ -295,6 +295,7 @@ def run_synth_case(cfg, lib, device, iters=1, seed=0, check_grads=True, tag="syn
         for name in ("nll_loss", "loss_rec", "loss_sen", "loss_bas_rec", "loss_bas_sen"):
             worst[name] = assert_close(t_ + name, L[name], float(res[name].detach()), rtol=1e-4, atol=1e-4)
         assert int(L["active_steps"]) == Tp
+        assert abs(L["topk_correct"] / B - res["accuracy"]) < 1e-6, (t_, L["topk_correct"], res["accuracy"])
         if check_grads:
             gv = e.named_views(e.grads)
             for a in grads:
