@@ -352,6 +352,11 @@ int mmg_baseline_forward(const mmg_config* cfg, const float* d_params, int32_t w
 /* Number of kernels the last call of each entry point enqueued (for launch accounting). */
 int mmg_launch_count(void);
 void mmg_launch_count_reset(void);
+/* Diagnostic.  With MMG_KTIME=1 in the environment every kernel launch is bracketed by CUDA events on its own stream (and
+ * launched without programmatic dependent launch); this call synchronises the device, writes one line per kernel
+ * ("name launches mean_us") into `out` (NUL-terminated, at most `cap` bytes), clears the records and returns how many
+ * launches were recorded.  Without MMG_KTIME it writes an empty string and returns 0. */
+int mmg_debug_kernel_times(char* out, int32_t cap);
 
 #ifdef __cplusplus
 }

@@ -19,6 +19,33 @@ static thread_local char g_err[512] = "";
 static thread_local int g_launches = 0;
 void count_launch() { ++g_launches; }
 
+#ifndef MMG_CPU_EMU
+// ---- MMG_KTIME=1: in-situ per-kernel device times (diagnostic; mmg_debug_kernel_times reads and clears them) -------------
+struct KTimeRec { const char* name; cudaEvent_t a, b; };
+static const int kKTimeMax = 1 << 16;
+static KTimeRec* g_ktime = nullptr;
+static int g_ktime_n = 0;
+int ktime_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MMG_KTIME"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v;
+}
+void ktime_begin(const char* name, cudaStream_t st) {
+    if (!g_ktime) g_ktime = (KTimeRec*)calloc(kKTimeMax, sizeof(KTimeRec));
+    if (g_ktime_n >= kKTimeMax) return;
+    KTimeRec& r = g_ktime[g_ktime_n];
+    r.name = name;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+}
+void ktime_end(cudaStream_t st) {
+    if (g_ktime_n >= kKTimeMax) return;
+    cudaEventRecord(g_ktime[g_ktime_n].b, st);
+    ++g_ktime_n;
+}
+#endif
+
 static int fail(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -379,14 +406,14 @@ struct FastFwdArgs { const float* b_img; const float* bs_w1; const float* bs_b1;
 template <int BT, int M, bool SS, bool PERF>
 static int launch_fwd_fast_mode(const Dims& d, const WsPtrs& W, const ExchangeInputs& in, const FastFwdArgs& fa, const Plan& pl,
                                 cudaStream_t st) {
-    auto kern = k_exchange_fwd_fast<BT, M, SS, PERF>;
-    int rc = set_smem(kern, pl.fwd_smem_bytes);
+    auto k_exchange_fwd_fast_ = k_exchange_fwd_fast<BT, M, SS, PERF>;
+    int rc = set_smem(k_exchange_fwd_fast_, pl.fwd_smem_bytes);
     if (rc) return rc;
     const int n_conv = cdiv(d.B, BT);
     const int n_side = in.train ? cdiv(d.B, kTile) * cdiv(d.Hb, kTile) : 0;     // baseline pre-activation tiles
     AttnArgs none;
     memset(&none, 0, sizeof(none));
-    MMG_LAUNCH(kern, n_conv + n_side, kFastThreads, pl.fwd_smem_bytes, st, d, W, in, fa.b_img, d.row0, fa.bs_w1, fa.bs_b1, n_conv, none, fa.epilogue);
+    MMG_LAUNCH(k_exchange_fwd_fast_, n_conv + n_side, kFastThreads, pl.fwd_smem_bytes, st, d, W, in, fa.b_img, d.row0, fa.bs_w1, fa.bs_b1, n_conv, none, fa.epilogue);
     return check_cuda("k_exchange_fwd_fast");
 }
 template <int BT, int M, bool SS>
@@ -414,13 +441,13 @@ static int launch_fwd_fast_attn(const Dims& d, const WsPtrs& W, const ExchangeIn
     int rc;
     const int n_side = in.train ? cdiv(d.B, kTile) * cdiv(d.Hb, kTile) : 0;     // baseline pre-activation tiles (U[b])
     if (perf) {
-        auto kern = k_exchange_fwd_fast<1, 32, true, true, true>;
-        if ((rc = set_smem(kern, pl.fast_fwd_smem_bytes))) return rc;
-        MMG_LAUNCH(kern, d.B + n_side, kFastThreads, pl.fast_fwd_smem_bytes, st, d, W, in, fa.b_img, d.row0, fa.bs_w1, fa.bs_b1, d.B, aa, fa.epilogue);
+        auto k_exchange_fwd_fast_attn_ = k_exchange_fwd_fast<1, 32, true, true, true>;
+        if ((rc = set_smem(k_exchange_fwd_fast_attn_, pl.fast_fwd_smem_bytes))) return rc;
+        MMG_LAUNCH(k_exchange_fwd_fast_attn_, d.B + n_side, kFastThreads, pl.fast_fwd_smem_bytes, st, d, W, in, fa.b_img, d.row0, fa.bs_w1, fa.bs_b1, d.B, aa, fa.epilogue);
     } else {
-        auto kern = k_exchange_fwd_fast<1, 32, true, false, true>;
-        if ((rc = set_smem(kern, pl.fast_fwd_smem_bytes))) return rc;
-        MMG_LAUNCH(kern, d.B + n_side, kFastThreads, pl.fast_fwd_smem_bytes, st, d, W, in, fa.b_img, d.row0, fa.bs_w1, fa.bs_b1, d.B, aa, fa.epilogue);
+        auto k_exchange_fwd_fast_attn_ = k_exchange_fwd_fast<1, 32, true, false, true>;
+        if ((rc = set_smem(k_exchange_fwd_fast_attn_, pl.fast_fwd_smem_bytes))) return rc;
+        MMG_LAUNCH(k_exchange_fwd_fast_attn_, d.B + n_side, kFastThreads, pl.fast_fwd_smem_bytes, st, d, W, in, fa.b_img, d.row0, fa.bs_w1, fa.bs_b1, d.B, aa, fa.epilogue);
     }
     return check_cuda("k_exchange_fwd_fast<attn>");
 }
@@ -435,11 +462,11 @@ static int launch_bwd_fast_m(const Dims& d, const WsPtrs& W, const float* bin_w,
     const int loss_off = (pl.bwd_smem_bytes + 15) / 16 * 4;          // floats; the coefficient scratch follows the state
     const int smem = FUSE ? loss_off * 4 + loss_smem_bytes(d, pv.world) : pl.bwd_smem_bytes;
     if (smem > kMaxSmem) return fail(MMG_ERR_UNSUPPORTED, "fused backward: %d bytes of shared memory", smem);
-    auto kern = k_exchange_bwd_fast<M, FUSE>;
-    int rc = set_smem(kern, smem);
+    auto k_exchange_bwd_fast_ = k_exchange_bwd_fast<M, FUSE>;
+    int rc = set_smem(k_exchange_bwd_fast_, smem);
     if (rc) return rc;
     const int n_rec = d.B, n_sen = d.use_binary ? d.B : 0;
-    MMG_LAUNCH(kern, n_rec + n_sen, kFastBwdThreads, smem, st, d, W, bin_w, code_w, n_rec, cfg, pv, loss_off);
+    MMG_LAUNCH(k_exchange_bwd_fast_, n_rec + n_sen, kFastBwdThreads, smem, st, d, W, bin_w, code_w, n_rec, cfg, pv, loss_off);
     return check_cuda("k_exchange_bwd_fast");
 }
 
@@ -637,6 +664,37 @@ int mmg_abi_version(void) { return MMG_ABI_VERSION; }
 const char* mmg_last_error(void) { return g_err; }
 int mmg_launch_count(void) { return g_launches; }
 void mmg_launch_count_reset(void) { g_launches = 0; }
+
+int mmg_debug_kernel_times(char* out, int32_t cap) {
+    if (!out || cap < 1) return fail(MMG_ERR_INVALID, "null output");
+    out[0] = 0;
+#ifndef MMG_CPU_EMU
+    if (!ktime_enabled()) return 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return check_cuda("cudaDeviceSynchronize");
+    struct Agg { const char* name; double us; int n; };
+    Agg agg[64];
+    int na = 0;
+    for (int i = 0; i < g_ktime_n; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, g_ktime[i].a, g_ktime[i].b);
+        cudaEventDestroy(g_ktime[i].a);
+        cudaEventDestroy(g_ktime[i].b);
+        int j = 0;
+        while (j < na && agg[j].name != g_ktime[i].name) ++j;
+        if (j == na) { if (na == 64) continue; agg[na++] = Agg{g_ktime[i].name, 0.0, 0}; }
+        agg[j].us += 1e3 * ms;
+        agg[j].n += 1;
+    }
+    const int n = g_ktime_n;
+    g_ktime_n = 0;
+    int pos = 0;
+    for (int j = 0; j < na && pos < cap - 1; ++j)
+        pos += snprintf(out + pos, (size_t)(cap - pos), "%s %d %.3f\n", agg[j].name, agg[j].n, agg[j].us / agg[j].n);
+    return n;
+#else
+    return 0;
+#endif
+}
 
 int mmg_device_count(void) {
 #ifndef MMG_CPU_EMU

@@ -81,22 +81,31 @@ inline int pdl_enabled() {
     if (v < 0) { const char* e = getenv("MMG_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
     return v;
 }
+// MMG_KTIME=1 (diagnostic, see mmg_debug_kernel_times): every launch is bracketed by two CUDA events on its stream, without
+// PDL, so that per-kernel device times can be read IN SITU (inside the caller's own cache / flush protocol) instead of
+// from a profiler's serialised cold-cache replays.
+int ktime_enabled();
+void ktime_begin(const char* name, cudaStream_t st);
+void ktime_end(cudaStream_t st);
 template <typename... KArgs, typename... Args>
-inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+inline void launch(const char* name, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    const int kt = ktime_enabled();
+    cfg.numAttrs = (pdl_enabled() && !kt) ? 1 : 0;
+    if (kt) ktime_begin(name, st);
     cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+    if (kt) ktime_end(st);
 }
 }  // namespace host
 }  // namespace mmg
 #define MMG_LAUNCH(kernel, grid, block, smem, stream, ...)                                          \
     do {                                                                                             \
-        mmg::host::launch(kernel, dim3(grid), dim3(block), (size_t)(smem), (stream), __VA_ARGS__);  \
+        mmg::host::launch(#kernel, kernel, dim3(grid), dim3(block), (size_t)(smem), (stream), __VA_ARGS__);  \
         mmg::host::count_launch();                                                                   \
     } while (0)
 #else

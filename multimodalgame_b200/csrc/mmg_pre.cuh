@@ -71,6 +71,16 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
     pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
     MMG_SHARED __attribute__((aligned(16))) float gs[kGemmSmemFloats];
     const int tid = threadIdx.x;
+    if (blockIdx.x == 0 && tid == 0) {
+        W.tickets[1] = 0;      // "h_x rows ready" counter of the next forward kernel
+        // Every exchange that consumes on-device draws (Bernoulli samples without injected uniforms, flipout noise) gets a
+        // fresh Philox stream: the iteration counter advances HERE, before the conversation kernel of this launch sequence
+        // reads it (this grid has fully completed by then), so forward-only callers (model.exchange, eval with -flipout_dev)
+        // never see the same stream twice.
+        const bool flips = (d.flip_sen >= 0.f && in.u_flip_sen == nullptr) || (d.flip_rec >= 0.f && in.u_flip_rec == nullptr);
+        if ((in.train && in.u_sen == nullptr) || (flips && d.use_binary && (in.train || d.flipout_dev)))
+            W.rng_state[1] += 1ull;
+    }
 #ifndef MMG_CPU_EMU
     if (use_umma && (int)blockIdx.x < n_hx_tiles) {
         // ---- role A on the tensor cores (tcgen05, 3xTF32): 128 hidden units x 64 batch rows x one K-slice per CTA --------------
@@ -86,16 +96,6 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
         return;
     }
 #endif
-    if (blockIdx.x == 0 && tid == 0) {
-        W.tickets[1] = 0;      // "h_x rows ready" counter of the next forward kernel
-        // Every exchange that consumes on-device draws (Bernoulli samples without injected uniforms, flipout noise) gets a
-        // fresh Philox stream: the iteration counter advances HERE, before the conversation kernel of this launch sequence
-        // reads it (this grid has fully completed by then), so forward-only callers (model.exchange, eval with -flipout_dev)
-        // never see the same stream twice.
-        const bool flips = (d.flip_sen >= 0.f && in.u_flip_sen == nullptr) || (d.flip_rec >= 0.f && in.u_flip_rec == nullptr);
-        if ((in.train && in.u_sen == nullptr) || (flips && d.use_binary && (in.train || d.flipout_dev)))
-            W.rng_state[1] += 1ull;
-    }
     if ((int)blockIdx.x < n_hx_tiles) {
         // ---- role A: h_x split-K tile -------------------------------------------------------------------
         const int ntn = cdiv(d.Hi, kTile), ntm = cdiv(d.B, kTile);

@@ -54,6 +54,27 @@ def check_margin(u, p, name, margin=2e-6):
         name, margin, gap)
 
 
+def relu_knife_edge_units(params, ex, cfg, agent, margin=2e-6):
+    """Hidden units of a baseline's linear1 whose pre-activation lies within `margin` of zero for some (step, example) row of
+    the oracle run: fp32 rounding decides on which side of the relu kink such a unit falls, so its gradient row is only
+    comparable up to that one row's contribution (the same knife-edge rule as a uniform within rounding distance of a
+    probability, see check_margin).  Returns a boolean mask over the hidden units."""
+    P = params[agent]
+    Tp = len(ex["y"])
+    w1, b1 = P["linear1.weight"].detach().double(), P["linear1.bias"].detach().double()
+    edge = torch.zeros(w1.shape[0], dtype=torch.bool)
+    z_r = torch.full((ex["h_x"].shape[0], cfg.rec_w_dim), float(cfg.first_rec), dtype=torch.float64)
+    for t in range(Tp):
+        if agent == "baseline_sen":
+            feats = torch.cat([ex["h_x"].detach().double(), z_r], 1)
+        else:
+            feats = torch.cat([ex["sen_feats"][t].detach().double(), ex["h_z"][t].detach().double()], 1)
+        pre = feats @ w1.t() + b1
+        edge |= (pre.abs() < margin).any(0)
+        z_r = ex["rec_feats"][t].detach().double()
+    return edge.numpy()
+
+
 def run_train_case(case, lib, device, report=None, grad_rtol=2e-3):
     """Returns dict of max errors.  `report` (list) receives human-readable lines."""
     z, cfg = gu.load(case)
@@ -81,6 +102,7 @@ def run_train_case(case, lib, device, report=None, grad_rtol=2e-3):
                 e.ws("opt_counters", (4,), torch.int64).copy_(state[3])
         if words:
             e.set_desc_set(**words)
+        oparams_before = go.clone_params(oparams)
         ex, res, grads = go.train_iteration(oparams, ostate, x, target, desc, cfg, us, return_grads=True, **words)
         Tp = len(ex["y"])     # steps the reference executed (early break)
         stacked = stack_uniforms(us, cfg, B)
@@ -129,6 +151,7 @@ def run_train_case(case, lib, device, report=None, grad_rtol=2e-3):
         assert abs(L["topk_correct"] / B - res["accuracy"]) < 1e-6, (tag, L["topk_correct"], res["accuracy"])
         # --- gradients (pre-clip) against autograd of the oracle ---
         gv = e.named_views(e.grads)
+        edge_units = {}
         for a in grads:
             gmax = max([float(g.abs().max()) for g in grads[a].values() if g is not None] + [1e-12])
             for k, g in grads[a].items():
@@ -139,8 +162,20 @@ def run_train_case(case, lib, device, report=None, grad_rtol=2e-3):
                 if (a, k) in (("receiver", "y2.bias"), ("receiver", "d_attn.bias")):     # mathematically zero (shift invariance)
                     assert abs(float(got.reshape(-1)[0])) < 1e-5
                     continue
+                want = g.numpy()
+                if a in ("baseline_sen", "baseline_rec") and k in ("linear1.weight", "linear1.bias", "linear2.weight") and cfg.use_binary:
+                    # units sitting on the relu kink in the oracle run are excluded (and counted): see relu_knife_edge_units
+                    edge = edge_units.setdefault(a, relu_knife_edge_units(oparams_before, ex, cfg, a))
+                    if edge.any():
+                        errs["relu_knife_edge_units"] = max(errs.get("relu_knife_edge_units", 0), int(edge.sum()))
+                        assert edge.sum() <= 4, tag + "%d hidden units on the relu kink: pick another seed" % edge.sum()
+                        got, want = got.copy(), want.copy()
+                        if k == "linear2.weight":
+                            got[:, edge] = want[:, edge]
+                        else:
+                            got[edge] = want[edge]
                 errs["grad_" + a] = max(errs.get("grad_" + a, 0.0), assert_close(
-                    tag + "grad %s.%s" % (a, k), got, g.numpy(), rtol=grad_rtol, atol=2e-5 * gmax + 1e-9))
+                    tag + "grad %s.%s" % (a, k), got, want, rtol=grad_rtol, atol=2e-5 * gmax + 1e-9))
         # --- clip + optimizer step ---
         e.update()
         gn = e.outputs()["grad_norms"].detach().cpu().numpy()
@@ -161,6 +196,9 @@ def run_train_case(case, lib, device, report=None, grad_rtol=2e-3):
                     # elements whose gradient is at rounding-noise level: the normalised step is noise too
                     tiny = (grads[a][k].abs() < 1e-5).numpy()
                     atol = np.where(tiny, 12 * lr * (it + 1), atol)
+                    if a in edge_units and edge_units[a].any() and k in ("linear1.weight", "linear1.bias", "linear2.weight"):
+                        rows = edge_units[a] if k != "linear2.weight" else edge_units[a][None, :]
+                        atol = np.where(rows.reshape(rows.shape + (1,) * (atol.ndim - rows.ndim)), 12 * lr * (it + 1), atol)
                 errs["param_" + a] = max(errs.get("param_" + a, 0.0), assert_close(
                     tag + "param %s.%s" % (a, k), got, v.numpy(), rtol=1e-5, atol=atol))
         # keep both trajectories glued together: continue from the oracle's parameters
