@@ -94,7 +94,7 @@ class Library(object):
                "mmg_workspace_layout_get", "mmg_workspace_init", "mmg_exchange_forward", "mmg_loss", "mmg_backward",
                "mmg_grad_norm", "mmg_clip_update", "mmg_train_step", "mmg_train_step_host", "mmg_host_prefetch", "mmg_train_step_staged", "mmg_peer_buffer_layout", "mmg_train_step_peer", "mmg_launch_count",
                "mmg_launch_count_reset", "mmg_sender_forward", "mmg_receiver_forward", "mmg_baseline_forward",
-               "mmg_debug_kernel_times")
+               "mmg_debug_kernel_times", "mmg_debug_trace")
 
     def __init__(self, path):
         self.path = path
@@ -129,6 +129,7 @@ class Library(object):
                                            vp, vp, vp, vp, vp, vp, vp]
         d.mmg_baseline_forward.argtypes = [cfgp, vp, i32, i32, vp, i32, vp, i32, vp, i32, vp, vp]
         d.mmg_debug_kernel_times.argtypes = [C.c_char_p, i32]
+        d.mmg_debug_trace.argtypes = [vp, i32]
         for name in self.SYMBOLS:
             fn = getattr(d, name)
             if name not in ("mmg_last_error", "mmg_launch_count_reset"):

@@ -200,7 +200,7 @@ static void ws_layout(const Dims& d, Ws* w) {
     w->wgrad_split = kWgradSplitMax;
     w->slabs = take(c, (int64_t)(kWgradSplitMax - 1) * L.total * f);
     w->norm_part = take(c, 4 * kNormCtasMax * f);
-    w->tile_norm = take(c, kMaxOutTiles * f);
+    w->tile_norm = take(c, 2 * kMaxOutTiles * f);      // sums of squares | module of each tile
     w->tile_tickets = take(c, kMaxOutTiles * 4);
     w->norm_final = take(c, 4 * 8);
     w->hit = take(c, B * f);
@@ -665,6 +665,20 @@ const char* mmg_last_error(void) { return g_err; }
 int mmg_launch_count(void) { return g_launches; }
 void mmg_launch_count_reset(void) { g_launches = 0; }
 
+int mmg_debug_trace(unsigned long long* out, int32_t count) {
+#if defined(MMG_TRACE) && !defined(MMG_CPU_EMU)
+    if (!out || count < 6 * 1024 * 8) return fail(MMG_ERR_INVALID, "trace buffer too small");
+    if (cudaDeviceSynchronize() != cudaSuccess) return check_cuda("cudaDeviceSynchronize");
+    if (cudaMemcpyFromSymbol(out, g_trace, sizeof(g_trace)) != cudaSuccess) return check_cuda("cudaMemcpyFromSymbol");
+    static unsigned long long zero[6 * 1024 * 8];
+    cudaMemcpyToSymbol(g_trace, zero, sizeof(g_trace));
+    return 6 * 1024 * 8;
+#else
+    (void)out; (void)count;
+    return 0;
+#endif
+}
+
 int mmg_debug_kernel_times(char* out, int32_t cap) {
     if (!out || cap < 1) return fail(MMG_ERR_INVALID, "null output");
     out[0] = 0;
@@ -786,8 +800,11 @@ static int exchange_forward_impl(const mmg_config* cfg, const float* d_params, c
     }
 #endif
     // image formats: bit 0 = fast forward image, bit 1 = fast backward image
+    // the class / word tables run on the small-K row tile when the word-vector width allows (dynamic shared memory)
+    const int cls_dyn = d.WV <= kRowsKMax ? rows_tile_smem_floats(d.WV) * 4 : 0;
+    if (cls_dyn > pre_smem) { pre_smem = cls_dyn; if ((rc = set_smem(k_pre, pre_smem))) return rc; }
     MMG_LAUNCH(k_pre, n_hx_l + n_cls + n_pack, kGemmThreads, pre_smem, st, d, P, W, ei, n_hx_l, hx_kslice, pl.fast_fwd | (pl.fast << 1), n_cls,
-               use_umma);
+               use_umma, pre_smem / 4);
     if ((rc = check_cuda("k_pre"))) return rc;
     // K_exchange_fwd
     const AttnArgs aa = attn_args(d, P, ei, pl);
@@ -807,8 +824,12 @@ static int exchange_forward_impl(const mmg_config* cfg, const float* d_params, c
         const int tiles = 2 * cdiv(d.R, kTile) * W.ntb;
         // wd rows as GEMM tiles (fast path and -desc_attn); otherwise the generic kernel writes wd itself
         const int wd_tiles = (pl.fast || d.A) ? cdiv(d.R, kTile) * cdiv(d.WV, kTile) : 0;
-        MMG_LAUNCH(k_baseline_fwd, tiles + wd_tiles, kGemmThreads, 0, st, d, P, W, d.A ? ei.desc_set : ei.desc, tiles, pl.fast_fwd, epi, ei,
-                   epi ? *fuse : no_peers(), *cfg);
+        // the small-K row tile stages [sen_feats ; h_z] x baseline_rec.linear1 rows whole: 2 x 64 rows x (M + Hr, padded) floats
+        const int bas_k = d.M + d.Hr;
+        const int bas_dyn = bas_k <= kRowsKMax ? rows_tile_smem_floats(bas_k) : 0;
+        if ((rc = set_smem(k_baseline_fwd, bas_dyn * 4))) return rc;
+        MMG_LAUNCH(k_baseline_fwd, tiles + wd_tiles, kGemmThreads, bas_dyn * 4, st, d, P, W, d.A ? ei.desc_set : ei.desc, tiles, pl.fast_fwd, epi, ei,
+                   epi ? *fuse : no_peers(), *cfg, bas_dyn);
         if ((rc = check_cuda("k_baseline_fwd"))) return rc;
         if (finish_baselines) {     // standalone forward: bs / br must be final on return (mmg_loss re-derives them anyway)
             MMG_LAUNCH(k_baseline_finish, cdiv(d.R, 256), 256, 0, st, d, P, W);
@@ -858,8 +879,11 @@ int mmg_loss(const mmg_config* cfg, const float* d_params, const mmg_inputs* in,
 
 // `fuse_loss`: the loss gradients (K_lossgrad) are evaluated inside the fast backward kernel; needs the batch statistics in
 // the workspace (fused forward sequence) and use_binary (both backward roles run).
+// `norm_tiles` (optional): the caller's K_update adds the per-tile sums of squares (and the loss partials) itself, so K_wgrad
+// runs without a finishing CTA; receives the number of output tiles.
 static int backward_impl(const mmg_config* cfg, const float* d_params, const mmg_inputs* in, void* d_workspace,
-                         float* d_grads, void* stream, const PeerView& pv, bool fuse_loss = false) {
+                         float* d_grads, void* stream, const PeerView& pv, bool fuse_loss = false, int* norm_tiles = nullptr,
+                         int* loss_parts = nullptr) {
     int rc = validate(cfg);
     if (rc) return rc;
     if (!d_params || !in || !d_workspace || !d_grads) return fail(MMG_ERR_INVALID, "null pointer argument");
@@ -901,8 +925,11 @@ static int backward_impl(const mmg_config* cfg, const float* d_params, const mmg
     // tensors of untrained modules keep a zero gradient: their problems are not in the table, so they are cleared there
     const WgSync sy{W.tile_tickets, W.tile_norm, W.tickets + 3, W.norm_final};
     if ((rc = set_smem(k_wgrad, wgrad_smem_bytes()))) return rc;
+    const int n_loss_parts = (fuse_loss && pl.fast) ? (d.use_binary ? 2 * d.B : d.B) : 0;
+    const int defer = norm_tiles != nullptr && pv.world <= 1 ? 1 : 0;
+    if (norm_tiles != nullptr) { *norm_tiles = defer ? tab.total_out : 0; *loss_parts = defer ? n_loss_parts : 0; }
     MMG_LAUNCH(k_wgrad, tab.total_tiles, kGemmThreads, wgrad_smem_bytes(), st, d, tab, d_grads, W.slabs, P.p[MMG_P_SEN_CODE_W],
-               P.p[MMG_P_SEN_CODE_BIAS], W.d_as, sy, pv, W, (fuse_loss && pl.fast) ? (d.use_binary ? 2 * d.B : d.B) : 0);
+               P.p[MMG_P_SEN_CODE_BIAS], W.d_as, sy, pv, W, n_loss_parts, defer);
     return check_cuda("k_wgrad");
 }
 
@@ -927,8 +954,8 @@ int mmg_grad_norm(const mmg_config* cfg, float* d_grads, void* d_workspace, void
     return check_cuda("k_grad_norm");
 }
 
-int mmg_clip_update(const mmg_config* cfg, float* d_params, float* d_grads, float* d_state1, float* d_state2,
-                    int64_t step, float grad_scale, void* d_workspace, void* stream) {
+static int clip_update_impl(const mmg_config* cfg, float* d_params, float* d_grads, float* d_state1, float* d_state2,
+                            int64_t step, float grad_scale, void* d_workspace, void* stream, int norm_tiles, int loss_parts) {
     int rc = validate(cfg);
     if (rc) return rc;
     if (!d_params || !d_grads || !d_workspace) return fail(MMG_ERR_INVALID, "null pointer argument");
@@ -945,9 +972,14 @@ int mmg_clip_update(const mmg_config* cfg, float* d_params, float* d_grads, floa
     OptHyper hp;
     hp.optim = cfg->optim_type; hp.lr = cfg->learning_rate; hp.max_norm = cfg->max_norm; hp.step = step;
     MMG_LAUNCH(k_update, upd_ctas(L.total), kUpdThreads, 0, (cudaStream_t)stream, seg, hp, d_params, (const float*)d_grads, d_grads,
-               d_state1, d_state2, (const double*)W.norm_final, W.grad_norms, (const double*)W.stats,
-               (const long long*)W.opt_counters, no_peers());
+               d_state1, d_state2, W.norm_final, W.grad_norms, (const double*)W.stats,
+               (const long long*)W.opt_counters, no_peers(), (const float*)W.tile_norm, norm_tiles, loss_parts, d, W);
     return check_cuda("k_update");
+}
+
+int mmg_clip_update(const mmg_config* cfg, float* d_params, float* d_grads, float* d_state1, float* d_state2,
+                    int64_t step, float grad_scale, void* d_workspace, void* stream) {
+    return clip_update_impl(cfg, d_params, d_grads, d_state1, d_state2, step, grad_scale, d_workspace, stream, 0, 0);
 }
 
 int mmg_train_step(const mmg_config* cfg, float* d_params, float* d_grads, float* d_state1, float* d_state2,
@@ -959,8 +991,9 @@ int mmg_train_step(const mmg_config* cfg, float* d_params, float* d_grads, float
     if ((rc = exchange_forward_impl(cfg, d_params, in, d_workspace, stream, false, &none, &fused))) return rc;
     const bool fuse_loss = fused && fuse_loss_ok(cfg);
     if (!fuse_loss && (rc = loss_impl(cfg, d_params, in, d_workspace, -1, stream, none, fused))) return rc;
-    if ((rc = backward_impl(cfg, d_params, in, d_workspace, d_grads, stream, none, fuse_loss))) return rc;
-    return mmg_clip_update(cfg, d_params, d_grads, d_state1, d_state2, step, 1.0f, d_workspace, stream);
+    int norm_tiles = 0, loss_parts = 0;
+    if ((rc = backward_impl(cfg, d_params, in, d_workspace, d_grads, stream, none, fuse_loss, &norm_tiles, &loss_parts))) return rc;
+    return clip_update_impl(cfg, d_params, d_grads, d_state1, d_state2, step, 1.0f, d_workspace, stream, norm_tiles, loss_parts);
 }
 
 int mmg_train_step_host(const mmg_config* cfg, float* d_params, float* d_grads, float* d_state1, float* d_state2,
@@ -1050,7 +1083,8 @@ int mmg_train_step_peer(const mmg_config* cfg, float* d_params, float* d_grads, 
     OptHyper hp;
     hp.optim = cfg->optim_type; hp.lr = cfg->learning_rate; hp.max_norm = cfg->max_norm; hp.step = step;
     MMG_LAUNCH(k_update, upd_ctas(L.total), kUpdThreads, 0, st, seg, hp, d_params, (const float*)pv.recv[pv.rank], d_grads, d_state1,
-               d_state2, (const double*)W.norm_final, W.grad_norms, (const double*)W.stats, (const long long*)W.opt_counters, pv);
+               d_state2, W.norm_final, W.grad_norms, (const double*)W.stats, (const long long*)W.opt_counters, pv,
+               (const float*)W.tile_norm, 0, 0, d, W);
     return check_cuda("k_update");
 }
 

@@ -22,7 +22,7 @@
 #define MMG_BSTAMP(slot) do { if (threadIdx.x == 0 && (blockIdx.x == 0 || (int)blockIdx.x == n_rec_ctas)) reinterpret_cast<unsigned*>(W.g_bs)[((int)blockIdx.x == 0 ? 0 : 32) + (slot)] = (unsigned)clock64(); } while (0)
 #else
 #define MMG_STAMP(p) do { } while (0)
-#define MMG_BSTAMP(slot) do { } while (0)
+#define MMG_BSTAMP(slot) MMG_TRACE_AT(3, slot)
 #endif
 
 namespace mmg {
@@ -145,11 +145,13 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
         // (model.py:835-836).  h_x is the same for all T steps of an example, so this 9/10 of the sender-side baseline
         // GEMM is done once per example, concurrently with the exchange loop.
         pdl_wait(); pdl_launch_dependents();
+        MMG_TRACE_AT(1, 4);
         const int ntn = cdiv(d.Hb, kTile);
         const int tile = (int)blockIdx.x - n_conv_ctas, nt = tile % ntn, mt = tile / ntn;
         // h_x rows are finalised by the conversation CTAs in their prologue (lower block indices, never blocked)
         if (threadIdx.x == 0) flag_wait(W.tickets + 1, (unsigned)n_conv_ctas);
         MMG_SYNCTHREADS();
+        MMG_TRACE_AT(1, 5);
         Operand A = Operand{W.h_x, nullptr, nullptr, nullptr, HI, 0, 0, 0, 0, OP_PLAIN};
         Operand Bo = Operand{bs_w1, nullptr, nullptr, nullptr, HI + M, 0, 0, 0, 0, OP_PLAIN};
         float acc[4][4];
@@ -164,6 +166,7 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
                 if (b < d.B && n < d.Hb) W.ubs[(size_t)b * d.Hb + n] = acc[a][c] + ldg(bs_b1 + n);
             }
         }
+        MMG_TRACE_AT(1, 6);
         return;
     }
     const FastFwdImage im = make_fast_fwd_image(M, d.D);
@@ -242,6 +245,7 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     MMG_SYNCTHREADS();
     pdl_wait(); pdl_launch_dependents();
+    MMG_TRACE_AT(1, 0);
     if (tid == 0) tma_stage2(sm, gimg, (uint32_t)snd * 4u, sm + snd, gimg + im.b_ih, (uint32_t)(im.total - im.b_ih) * 4u, bar);
     // this thread's slice of every loop matrix -> registers (coalesced 16-byte loads from the L2-resident image)
     float4 rc[kRegSend ? M4 : 1], rb[kRegSend ? KB / 4 : 1], ri[3 * MQ], rh[8], rg[12], rw[KPT / 4];
@@ -379,6 +383,7 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
 
     gh_phase();                                   // gates' recurrent half for step 0 from the initial state
     MMG_SYNCTHREADS();
+    MMG_TRACE_AT(1, 1);
     // prediction step of every example (model.py:893-896): the first step whose outgoing stop mask is 0, else the last one.
     // Every thread tracks it in registers (smask only changes between barriers), so the scores can be kept when they appear.
     int ystep_r[BT];
@@ -791,6 +796,7 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
         MMG_STAMP(7);
         MMG_SYNCTHREADS();
     }
+    MMG_TRACE_AT(1, 2);
     if (epilogue) {
         // ---- per-example results (get_rec_outp, model.py:879-904; log_softmax / NLL / loglikelihood / argmax, 1264-1275;
         //      top-k, 1333-1338; d nll / d outp): one warp per example, lanes over the classes.  This is the per-example half
@@ -833,6 +839,7 @@ k_exchange_fwd_fast(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int
 #if defined(MMG_PHASE_TIMING) && !defined(MMG_CPU_EMU)
     if (blockIdx.x == 0) for (int i = tid; i < T * 64; i += NT) reinterpret_cast<unsigned*>(W.g_sen_probs)[i] = stamps[i];
 #endif
+    MMG_TRACE_AT(1, 3);
 }
 
 // ---- backward ------------------------------------------------------------------------------------------------------

@@ -269,4 +269,73 @@ MMG_DEVICE void gemm_tile_deep(const Operand& A, const Operand& Bm, int Mdim, in
     }
 }
 
+// ---- small-K tile for operands whose reduction index is contiguous in memory (rows of activations x rows of a Linear weight) ----
+// C[i][j] = sum_k A_i[k] * B_j[k], k < ka1 + ka2 <= kRowsKMax, where row i of A is the concatenation [a1[i * lda1 + 0..ka1) ;
+// a2[i * lda2 + 0..ka2)] and row j of B is b[j * ldb + 0..K).  The whole K range of both operands is staged with asynchronous
+// 16-byte copies (every load of the CTA in flight at once, no register round trip), rows kept k-contiguous in shared memory
+// with the 16-byte group index XOR-ed by (row / 4) % 8 so that the float4 reads of 8 consecutive thread columns hit 32 distinct
+// banks; then ONE rolled loop of 8 LDS.128 + 32 packed FMAs per 4 k.  The code is a few hundred instructions: these tiles run
+// once per CTA, and the fully unrolled generic tile spent 65 % of its stall samples waiting for instructions (ncu, r02).
+enum { kRowsKMax = 128 };
+MMG_HOST_DEVICE int rows_tile_kp(int K) { return (K + 31) & ~31; }                        // padded row length (floats)
+MMG_HOST_DEVICE int rows_tile_smem_floats(int K) { return 2 * kTile * rows_tile_kp(K); }
+MMG_HOST_DEVICE bool rows_tile_ok(const float* a1, int lda1, int ka1, const float* a2, int lda2, int ka2, const float* b, int ldb) {
+    const size_t bits = (size_t)a1 | (size_t)b | (ka2 > 0 ? (size_t)a2 : 0);
+    return (bits & 15) == 0 && ((lda1 | ka1 | ldb | (ka2 > 0 ? (lda2 | ka2) : 0)) & 3) == 0 && ka1 + ka2 <= kRowsKMax && ka1 > 0;
+}
+MMG_DEVICE void gemm_rows_tile(const float* a1, int lda1, int ka1, const float* a2, int lda2, int ka2, const float* b, int ldb,
+                               int Mdim, int Ndim, int m0, int n0, float (&acc)[4][4], float* smem) {
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int K = ka1 + ka2, K4 = K >> 2, KP = rows_tile_kp(K);
+    float* As = smem;
+    float* Bs = smem + kTile * KP;
+    // staging: thread -> (row = tid / 4 + 64 p?, groups tid % 4, + 4, ...): rows advance by kGemmThreads / 4 = 64 -> one pass per operand
+    {
+        const int row = tid >> 2;
+        const int sw = (row >> 2) & 7;
+        const bool oka = m0 + row < Mdim, okb = n0 + row < Ndim;
+        const float* ar1 = a1 + (size_t)(m0 + row) * lda1;
+        const float* ar2 = ka2 > 0 ? a2 + (size_t)(m0 + row) * lda2 - ka1 : ar1;
+        const float* br = b + (size_t)(n0 + row) * ldb;
+        for (int g = tid & 3; g < K4; g += 4) {
+            float* da = As + row * KP + 4 * (g ^ sw);
+            float* db = Bs + row * KP + 4 * (g ^ sw);
+            if (oka) cp_async16(da, 4 * g < ka1 ? ar1 + 4 * g : ar2 + 4 * g);
+            else *reinterpret_cast<float4*>(da) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (okb) cp_async16(db, br + 4 * g);
+            else *reinterpret_cast<float4*>(db) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    cp_async_wait_all();
+    MMG_SYNCTHREADS();
+    float2 s2[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s2[a][c] = make_float2(0.f, 0.f);
+    const float* arow = As + (ty * 4) * KP;
+    const float* brow = Bs + (tx * 4) * KP;
+    const int swa = ty & 7, swb = tx & 7;            // (row / 4) % 8 of this thread's four A rows / four B rows
+#pragma unroll 2
+    for (int g = 0; g < K4; ++g) {
+        float4 av[4], bv[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) av[a] = *reinterpret_cast<const float4*>(arow + a * KP + 4 * (g ^ swa));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bv[c] = *reinterpret_cast<const float4*>(brow + c * KP + 4 * (g ^ swb));
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {       // (even k, odd k) partial sums ride in one packed register pair
+                s2[a][c] = ffma2(make_float2(av[a].x, av[a].y), make_float2(bv[c].x, bv[c].y), s2[a][c]);
+                s2[a][c] = ffma2(make_float2(av[a].z, av[a].w), make_float2(bv[c].z, bv[c].w), s2[a][c]);
+            }
+    }
+    MMG_SYNCTHREADS();              // the caller may reuse `smem`
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = s2[a][c].x + s2[a][c].y;
+}
+
 }  // namespace mmg

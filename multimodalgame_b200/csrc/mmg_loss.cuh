@@ -14,7 +14,9 @@
 
 namespace mmg {
 
-MMG_DEVICE void baseline_fwd_tile(const Dims& d, const ParamPtrs& P, const WsPtrs& W, const float* desc, int n_bas_tiles, int use_u) {
+// `dyn` / `dyn_floats`: dynamic shared memory for the small-K row tile (gemm_rows_tile); the generic tile is the fallback.
+MMG_DEVICE void baseline_fwd_tile(const Dims& d, const ParamPtrs& P, const WsPtrs& W, const float* desc, int n_bas_tiles, int use_u,
+                                  float* dyn, int dyn_floats) {
     MMG_SHARED __attribute__((aligned(16))) float gs[kGemmSmemFloats];
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
     const int ntm = cdiv(d.R, kTile), ntn = W.ntb;
@@ -63,18 +65,62 @@ MMG_DEVICE void baseline_fwd_tile(const Dims& d, const ParamPtrs& P, const WsPtr
         b1 = P.p[MMG_P_BR_L1_B]; w2 = P.p[MMG_P_BR_L2_W]; hid = W.h1r; part = W.br_part; K = d.M + d.Hr;
     }
     float acc[4][4];
-    gemm_tile_deep(A, Bo, d.R, d.Hb, mt * kTile, nt * kTile, 0, K, acc, gs);
+    {
+        // rows with the reduction index contiguous on both sides: the staged small-K tile when shapes and alignment allow
+        const float *a1 = nullptr, *a2 = nullptr, *bw = nullptr;
+        int lda1 = 0, ka1 = 0, lda2 = 0, ka2 = 0, ldb = 0;
+        if (which == 0 && use_u) { a1 = W.rec_feats; lda1 = d.M; ka1 = d.M; bw = P.p[MMG_P_BS_L1_W] + d.Hi; ldb = d.Hi + d.M; }
+        else if (which == 1) { a1 = W.sen_feats; lda1 = d.M; ka1 = d.M; a2 = W.h_z + (size_t)d.B * d.Hr; lda2 = d.Hr; ka2 = d.Hr;
+                               bw = P.p[MMG_P_BR_L1_W]; ldb = d.M + d.Hr; }
+        if (a1 != nullptr && rows_tile_ok(a1, lda1, ka1, a2, lda2, ka2, bw, ldb) && rows_tile_smem_floats(ka1 + ka2) <= dyn_floats)
+            gemm_rows_tile(a1, lda1, ka1, a2, lda2, ka2, bw, ldb, d.R, d.Hb, mt * kTile, nt * kTile, acc, dyn);
+        else
+            gemm_tile_deep(A, Bo, d.R, d.Hb, mt * kTile, nt * kTile, 0, K, acc, gs);
+    }
+    MMG_TRACE_AT(2, 5);
+    // epilogue: every load (bias or U row, linear2 weights) is issued before the first store, through the read-only path, so the
+    // 16 elements of a thread cost one memory round trip instead of one per element (the stores may alias ordinary loads)
+    const int n0 = nt * kTile + tx * 4;
+    const bool vec = (d.Hb & 3) == 0 && n0 + 3 < d.Hb;
+    float add[4][4], w2v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) w2v[c] = n0 + c < d.Hb ? ldg(w2 + n0 + c) : 0.f;
+    if (u == nullptr) {
+        float bv[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bv[c] = n0 + c < d.Hb ? ldg(b1 + n0 + c) : 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) add[a][c] = bv[c];
+    } else {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int r = mt * kTile + ty * 4 + a;
+            const float* ur = u + (size_t)((r < d.R ? r : 0) % d.B) * d.Hb + n0;
+            if (vec) {
+                const float4 t4 = ldg4(reinterpret_cast<const float4*>(ur));
+                add[a][0] = t4.x; add[a][1] = t4.y; add[a][2] = t4.z; add[a][3] = t4.w;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) add[a][c] = n0 + c < d.Hb ? ldg(ur + c) : 0.f;
+            }
+        }
+    }
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const int r = mt * kTile + ty * 4 + a;
-        float dot = 0.f;
+        float v[4], dot = 0.f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const int n = nt * kTile + tx * 4 + c;
-            if (r < d.R && n < d.Hb) {
-                const float v = fmaxf(0.f, acc[a][c] + (u != nullptr ? u[(size_t)(r % d.B) * d.Hb + n] : ldg(b1 + n)));
-                hid[(size_t)r * d.Hb + n] = v;
-                dot = fmaf(v, ldg(w2 + n), dot);
+            v[c] = fmaxf(0.f, acc[a][c] + add[a][c]);
+            if (n0 + c < d.Hb) dot = fmaf(v[c], w2v[c], dot);
+        }
+        if (r < d.R) {
+            if (vec) *reinterpret_cast<float4*>(hid + (size_t)r * d.Hb + n0) = make_float4(v[0], v[1], v[2], v[3]);
+            else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) if (n0 + c < d.Hb) hid[(size_t)r * d.Hb + n0 + c] = v[c];
             }
         }
         dot = half_warp_sum(dot);
@@ -308,16 +354,123 @@ MMG_DEVICE void loss_coefs_store(const Dims& d, const mmg_config& cfg, const WsP
     }
 }
 
+// ---- fused statistics, two levels (B a multiple of the tile height, so a 64-row tile lies inside one exchange step) -------------
+// Level 1, by the last of the 2 * ntb CTAs that finish row tile `mt`: baseline scores of its 64 rows (per-tile partial dots added
+// in tile order) and the rows' share of the 12 per-step sums -> loss_part[mt][12] (double; the array is free until the backward).
+MMG_DEVICE void row_tile_stats(const Dims& d, const ParamPtrs& P, const WsPtrs& W, int mt) {
+    MMG_SHARED double red[12][2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < kTile) {
+        const int r = mt * kTile + tid;
+        const int t = r / d.B, b = r - t * d.B;
+        float s = ldg(P.p[MMG_P_BS_L2_B]), q = ldg(P.p[MMG_P_BR_L2_B]);
+        for (int j0 = 0; j0 < W.ntb; j0 += 8) {
+            float ps[8], pq[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool ok = j0 + u < W.ntb;
+                ps[u] = ok ? ld_cg(W.bs_part + (size_t)r * W.ntb + j0 + u) : 0.f;
+                pq[u] = ok ? ld_cg(W.br_part + (size_t)r * W.ntb + j0 + u) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { s += ps[u]; q += pq[u]; }
+        }
+        W.bs[r] = s; W.br[r] = q;
+        const float lg = W.logs[b];
+        const bool m_in = mask_at(d, W, t, b) != 0, m_out = mask_at(d, W, t + 1, b) != 0;
+        const double ws = (double)(lg - s), wr = (double)(lg - q);
+        double v[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};     // n0 a0 c0 | n1 a1 c1 | n2 a2 c2 | er2 es2 nm  (see stats_body)
+        if (m_in) {
+            v[0] = 1.0; v[1] = ws; v[2] = ws * ws;
+            if (!d.fixed) { v[6] = 1.0; v[7] = wr; v[8] = wr * wr; }
+            v[9] = wr * wr; v[10] = ws * ws;
+        }
+        if (m_out && t < d.T - 1) { v[3] = 1.0; v[4] = wr; v[5] = wr * wr; }
+        if (d.fixed || m_out) v[11] = 1.0;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const double sum = warp_sum_d(v[i]);
+            if (lane == 0) red[i][warp] = sum;
+        }
+    }
+    MMG_SYNCTHREADS();
+    if (tid < 12) W.loss_part[(size_t)mt * 12 + tid] = red[tid][0] + red[tid][1];
+}
+
+// Level 2, by the last row tile to finish: per step, the row tiles' shares added in tile order; the batch sums of the
+// per-example results; then the peers are told (data-parallel) or the loss coefficients derived (single rank).
+MMG_DEVICE void final_stats(const Dims& d, const WsPtrs& W, const PeerView& pv, const mmg_config& cfg) {
+    MMG_SHARED double red2[2][kGemmThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per_step = d.B / kTile;
+    for (int i = tid; i < d.T * 12; i += kGemmThreads) {
+        const int t = i / 12, k = i - 12 * t;
+        double s = 0.0;
+        for (int j = 0; j < per_step; ++j) s += ld_cg_d(W.loss_part + (size_t)(t * per_step + j) * 12 + k);
+        W.stats[k < 9 ? stat_idx(d, k / 3, t, k % 3) : stat_bas(d, t, k - 9)] = s;
+    }
+    double nl = 0.0, co = 0.0;
+    for (int b = tid; b < d.B; b += kGemmThreads) { nl -= (double)W.logs[b]; co += (double)W.hit[b]; }
+    nl = warp_sum_d(nl); co = warp_sum_d(co);
+    if (lane == 0) { red2[0][warp] = nl; red2[1][warp] = co; }
+    MMG_SYNCTHREADS();
+    if (tid == 0) {
+        double a = 0, c = 0;
+        for (int w = 0; w < kGemmThreads / 32; ++w) { a += red2[0][w]; c += red2[1][w]; }
+        W.stats[stat_scalar(d, 0)] = a;
+        W.stats[stat_scalar(d, 1)] = c;
+        W.stats[stat_scalar(d, 2)] = 0.0;
+        W.stats[stat_scalar(d, 3)] = 0.0;
+    }
+    MMG_SYNCTHREADS();
+    if (pv.world > 1) {
+        for (int i = tid; i < stats_count(d); i += kGemmThreads) pv.stats[pv.rank][i] = W.stats[i];
+        fence_system();
+        MMG_SYNCTHREADS();
+        if (tid < pv.world) peer_signal(pv.flags[tid] + pv.rank, pv.iter);
+    } else {
+        loss_coefs_store(d, cfg, W, kGemmThreads);
+    }
+}
+
 // `fuse_stats`: the last CTA to finish its tile (ticket) also runs the batch statistics, so K_stats is not launched: the
 // per-example half was done by the conversation kernel's epilogue.
 MMG_GLOBAL void __launch_bounds__(kGemmThreads)
 k_baseline_fwd(Dims d, ParamPtrs P, WsPtrs W, const float* desc, int n_bas_tiles, int use_u, int fuse_stats, ExchangeInputs in,
-               PeerView pv, mmg_config cfg) {
+               PeerView pv, mmg_config cfg, int dyn_floats) {
     pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
     pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
-    baseline_fwd_tile(d, P, W, desc, n_bas_tiles, use_u);
+    MMG_TRACE_AT(2, 0);
+    MMG_DYN_SMEM(dyn_raw);
+    baseline_fwd_tile(d, P, W, desc, n_bas_tiles, use_u, reinterpret_cast<float*>(dyn_raw), dyn_floats);
+    MMG_TRACE_AT(2, 1);
     if (!fuse_stats) return;
     MMG_SHARED int s_last;
+    {
+        const int ntm = cdiv(d.R, kTile), ntn = W.ntb;
+        if (d.B % kTile == 0 && ntm * 12 <= kLossCtasMax * 8) {
+            if ((int)blockIdx.x >= n_bas_tiles) return;                   // the wd tiles take no part in the statistics
+            const int mt = ((int)blockIdx.x % (ntm * ntn)) / ntn;
+            MMG_SYNCTHREADS();                                             // the barrier orders every thread's stores before thread 0's fence + ticket
+            if (threadIdx.x == 0) s_last = (ticket_take(W.tile_tickets + mt) == 2u * ntn - 1) ? 1 : 0;
+            MMG_SYNCTHREADS();
+            if (!s_last) return;
+            fence_acquire();
+            if (threadIdx.x == 0) W.tile_tickets[mt] = 0;                 // zero between launches (K_wgrad uses the same counters)
+            MMG_TRACE_AT(2, 2);
+            row_tile_stats(d, P, W, mt);
+            MMG_SYNCTHREADS();
+            if (threadIdx.x == 0) s_last = (ticket_take(W.tickets + 7) == (unsigned)ntm - 1) ? 1 : 0;
+            MMG_SYNCTHREADS();
+            if (!s_last) return;
+            fence_acquire();
+            if (threadIdx.x == 0) W.tickets[7] = 0;
+            MMG_TRACE_AT(2, 3);
+            final_stats(d, W, pv, cfg);
+            MMG_TRACE_AT(2, 4);
+            return;
+        }
+    }
     fence_acquire();            // every thread: its tile results are visible device-wide before the CTA is counted
     MMG_SYNCTHREADS();
     if (threadIdx.x == 0) s_last = (ticket_take(W.tickets + 7) == gridDim.x - 1) ? 1 : 0;
@@ -325,11 +478,14 @@ k_baseline_fwd(Dims d, ParamPtrs P, WsPtrs W, const float* desc, int n_bas_tiles
     if (!s_last) return;
     fence_acquire();
     if (threadIdx.x == 0) W.tickets[7] = 0;
+    MMG_TRACE_AT(2, 2);
     stats_body<kGemmThreads>(d, P, W, in, pv, true);
+    MMG_TRACE_AT(2, 3);
     if (pv.world <= 1) {
         MMG_SYNCTHREADS();
         loss_coefs_store(d, cfg, W, kGemmThreads);
     }
+    MMG_TRACE_AT(2, 4);
 }
 
 MMG_GLOBAL void __launch_bounds__(kStatsThreadsMax)

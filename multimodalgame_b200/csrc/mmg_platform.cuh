@@ -108,6 +108,7 @@ MMG_DEVICE double peer_load_d(const double* p) { return __ldcg(p); }
 // L1-bypassing loads for data another CTA of the SAME grid has just written (split-K partial tiles)
 MMG_DEVICE float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 MMG_DEVICE float ld_cg(const float* p) { return __ldcg(p); }
+MMG_DEVICE double ld_cg_d(const double* p) { return __ldcg(p); }
 
 // ---- mbarrier + TMA bulk copy (cp.async.bulk, SASS UBLKCP) ------------------------------------------
 MMG_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -170,6 +171,21 @@ MMG_DEVICE void cp_async16(void* smem_dst, const void* gmem_src) {
 }
 MMG_DEVICE void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // Programmatic dependent launch: wait for the producer grid's memory to be visible / let dependents start.
+// -DMMG_TRACE (debug build only, scripts/trace.py): thread 0 of every CTA stamps the global nanosecond timer at a few points;
+// mmg_debug_trace copies the table out.  kid: 0 pre, 1 fwd, 2 baseline, 3 bwd, 4 wgrad, 5 update.
+#ifdef MMG_TRACE
+__device__ unsigned long long g_trace[6][1024][8];
+#define MMG_TRACE_AT(kid, slot)                                                                  \
+    do {                                                                                         \
+        if (threadIdx.x == 0 && blockIdx.x < 1024) {                                             \
+            unsigned long long t_;                                                               \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                               \
+            g_trace[kid][blockIdx.x][slot] = t_;                                                 \
+        }                                                                                        \
+    } while (0)
+#else
+#define MMG_TRACE_AT(kid, slot) do { } while (0)
+#endif
 MMG_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 MMG_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -294,6 +310,7 @@ MMG_DEVICE float4 peer_load4(const float* p) { return *reinterpret_cast<const fl
 MMG_DEVICE double peer_load_d(const double* p) { return *p; }
 MMG_DEVICE float4 ld_cg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 MMG_DEVICE float ld_cg(const float* p) { return *p; }
+MMG_DEVICE double ld_cg_d(const double* p) { return *p; }
 MMG_DEVICE void mbar_init(uint64_t* bar, int) { *bar = 0; }
 MMG_DEVICE void mbar_fence_init() {}
 MMG_DEVICE void mbar_wait(uint64_t*, uint32_t) {}
@@ -309,6 +326,7 @@ MMG_DEVICE void cp_async16(void* smem_dst, const void* gmem_src) { memcpy(smem_d
 MMG_DEVICE void cp_async_wait_all() {}
 MMG_DEVICE void pdl_wait() {}
 MMG_DEVICE void pdl_launch_dependents() {}
+#define MMG_TRACE_AT(kid, slot) do { } while (0)
 MMG_DEVICE float ldg(const float* p) { return *p; }
 MMG_DEVICE float4 ldg4(const float4* p) { return *p; }
 }  // namespace mmg

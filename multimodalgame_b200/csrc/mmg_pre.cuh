@@ -66,11 +66,13 @@ MMG_DEVICE float bwd_image_elem(const Dims& d, const BwdImage& im, const ParamPt
 }
 
 MMG_GLOBAL void __launch_bounds__(kGemmThreads)
-k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_kslice, int fast, int n_cls_tiles, int use_umma) {
+k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_kslice, int fast, int n_cls_tiles, int use_umma,
+      int dyn_floats) {
     pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
     pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
     MMG_SHARED __attribute__((aligned(16))) float gs[kGemmSmemFloats];
     const int tid = threadIdx.x;
+    MMG_TRACE_AT(0, 0);
     if (blockIdx.x == 0 && tid == 0) {
         W.tickets[1] = 0;      // "h_x rows ready" counter of the next forward kernel
         // Every exchange that consumes on-device draws (Bernoulli samples without injected uniforms, flipout noise) gets a
@@ -119,6 +121,7 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
                 if (n < d.Hi) W.hx_part[((size_t)s * d.B + b) * d.Hi + n] = acc[a][c];
             }
         }
+        MMG_TRACE_AT(0, 6);
         return;
     }
     const FwdImage fim = make_fwd_image(d);
@@ -141,6 +144,10 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
                    : which == 1 ? Operand{P.p[MMG_P_REC_WD_W], nullptr, nullptr, nullptr, d.WV, 0, 0, 0, 0, OP_PLAIN}
                                 : Operand{P.p[MMG_P_REC_DD_W], nullptr, nullptr, nullptr, d.WV, 0, 0, 0, 0, OP_PLAIN};
         float acc[4][4];
+        if (rows_tile_ok(A.p, A.ld, d.WV, nullptr, 0, 0, Bo.p, Bo.ld) && rows_tile_smem_floats(d.WV) <= dyn_floats) {
+            MMG_DYN_SMEM(dyn_raw);
+            gemm_rows_tile(A.p, A.ld, d.WV, nullptr, 0, 0, Bo.p, Bo.ld, d.NW, N, mt * kTile, nt * kTile, acc, reinterpret_cast<float*>(dyn_raw));
+        } else
         gemm_tile_deep(A, Bo, d.NW, N, mt * kTile, nt * kTile, 0, d.WV, acc, gs);
         const int tx = tid % 16, ty = tid / 16;
         float* out = which == 0 ? W.wtab_y1 : (which == 1 ? W.wtab_wd : W.wtab_dd);
@@ -170,6 +177,10 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
         Operand Bo = which == 0 ? Operand{P.p[MMG_P_REC_Y1_W] + d.Hr, nullptr, nullptr, nullptr, d.Hr + d.WV, 0, 0, 0, 0, OP_PLAIN}
                                 : Operand{P.p[MMG_P_REC_WD_W], nullptr, nullptr, nullptr, d.WV, 0, 0, 0, 0, OP_PLAIN};
         float acc[4][4];
+        if (rows_tile_ok(A.p, A.ld, d.WV, nullptr, 0, 0, Bo.p, Bo.ld) && rows_tile_smem_floats(d.WV) <= dyn_floats) {
+            MMG_DYN_SMEM(dyn_raw);
+            gemm_rows_tile(A.p, A.ld, d.WV, nullptr, 0, 0, Bo.p, Bo.ld, d.D, d.Hr, mt * kTile, nt * kTile, acc, reinterpret_cast<float*>(dyn_raw));
+        } else
         gemm_tile_deep(A, Bo, d.D, d.Hr, mt * kTile, nt * kTile, 0, d.WV, acc, gs);
         const int tx = tid % 16, ty = tid / 16;
 #pragma unroll
@@ -196,6 +207,7 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
                 }
             }
         }
+        MMG_TRACE_AT(0, 5);
         return;
     }
     // ---- role B: images + the step-0 code term -------------------------------------------------------------
@@ -261,6 +273,7 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
         }
     }
     if (!fb) for (int e = gtid + bim.y1d + n_y1d_w; e < bim.total; e += gthreads) W.bwd_image[e] = 0.f;
+    MMG_TRACE_AT(0, 4);
 }
 
 }  // namespace mmg

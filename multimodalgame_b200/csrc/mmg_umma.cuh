@@ -127,6 +127,7 @@ MMG_DEVICE void image_layer_tile(const float* w_img, const float* x, int F, int 
     if (warp == 0) tmem_alloc(&s_tmem);
     stage_split<NT>(a_hi, a_lo, w_img + (size_t)n0 * F + k0, (size_t)F, kM, Hi - n0, nk, tid);
     stage_split<NT>(b_hi, b_lo, x + (size_t)b0 * F + k0, (size_t)F, kN, B - b0, nk, tid);
+    MMG_TRACE_AT(0, 1);
     fence_proxy_async();            // the staged operands (generic-proxy writes) become visible to the tensor-core (async) proxy
     tc_fence_before();
     __syncthreads();
@@ -150,6 +151,7 @@ MMG_DEVICE void image_layer_tile(const float* w_img, const float* x, int F, int 
     }
     mbar_wait(&s_bar, 0);
     tc_fence_after();
+    MMG_TRACE_AT(0, 2);
     // epilogue: warp w reads TMEM lanes 32 (w % 4) .. + 31 (hidden units), columns 16-wide groups (batch rows); warps 0-3 take
     // the even groups, warps 4-7 the odd ones.  For a fixed batch row the 32 lanes store 128 contiguous bytes.
     const int n = n0 + 32 * (warp & 3) + lane;
@@ -167,6 +169,7 @@ MMG_DEVICE void image_layer_tile(const float* w_img, const float* x, int F, int 
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_free(tmem);
+    MMG_TRACE_AT(0, 7);
 }
 
 }  // namespace umma

@@ -66,10 +66,23 @@ MMG_DEVICE void wg_stage(const Operand& op, int k0, int k1, int i0, int ilim, fl
         if (vec && i + 3 < ilim) {
             if (op.kind == OP_RELUGRAD_TSUM) {
                 float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int t = 0; t < op.mod; ++t) {
-                    const float4 h = ldg4(reinterpret_cast<const float4*>(op.p + ((size_t)t * op.ld2 + k) * op.ld + i));
-                    const float gg = ldg(op.g + (size_t)t * op.ld2 + k);
-                    r.x += h.x > 0.f ? gg : 0.f; r.y += h.y > 0.f ? gg : 0.f; r.z += h.z > 0.f ? gg : 0.f; r.w += h.w > 0.f ? gg : 0.f;
+                for (int t0 = 0; t0 < op.mod; t0 += 8) {        // 8 steps' loads in flight at once, summed in step order
+                    float4 h[8];
+                    float gg[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int t = t0 + u;
+                        h[u] = make_float4(0.f, 0.f, 0.f, 0.f); gg[u] = 0.f;
+                        if (t < op.mod) {
+                            h[u] = ldg4(reinterpret_cast<const float4*>(op.p + ((size_t)t * op.ld2 + k) * op.ld + i));
+                            gg[u] = ldg(op.g + (size_t)t * op.ld2 + k);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        r.x += h[u].x > 0.f ? gg[u] : 0.f; r.y += h[u].y > 0.f ? gg[u] : 0.f;
+                        r.z += h[u].z > 0.f ? gg[u] : 0.f; r.w += h[u].w > 0.f ? gg[u] : 0.f;
+                    }
                 }
                 const float4 w = ldg4(reinterpret_cast<const float4*>(op.w2 + i));
                 *reinterpret_cast<float4*>(dst) = make_float4(r.x * w.x, r.y * w.y, r.z * w.z, r.w * w.w);
@@ -125,9 +138,10 @@ MMG_DEVICE float block_sum_256(float v, float* red) {
 
 MMG_GLOBAL void __launch_bounds__(kGemmThreads, 3)
 k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, const float* code_bias, const float* d_as,
-        WgSync sy, PeerView pv, WsPtrs W, int n_loss_parts) {
+        WgSync sy, PeerView pv, WsPtrs W, int n_loss_parts, int defer_tail) {
     pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
     pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
+    MMG_TRACE_AT(4, 0);
     MMG_DYN_SMEM(smem_raw);
     float* As = reinterpret_cast<float*>(smem_raw);
     float* Bs = As + kWgradKSlice * kWgLd;
@@ -168,6 +182,7 @@ k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, co
         wg_stage(pr.B, kb, ke, n0, pr.N, Bs, rows_pad, tid);
         cp_async_wait_all();
         MMG_SYNCTHREADS();
+        MMG_TRACE_AT(4, 1);
         if (pr.A.kind == OP_RELUGRAD) { wg_relu_pass(pr.A, kb, ke, As, gk, tid); MMG_SYNCTHREADS(); }
 #pragma unroll 8
         for (int kk = 0; kk < rows_pad; ++kk) {
@@ -199,6 +214,7 @@ k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, co
             if (q == 0) csum_sm[c] += part + gk[c];
         }
         }
+        MMG_TRACE_AT(4, 2);
         // row factors: w2[i] of a relu-gradient operand, d sigmoid(code_bias)
         auto row_scale = [&](int i) {
             float r = 1.f;
@@ -242,28 +258,58 @@ k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, co
             for (int a = 0; a < 4; ++a) if (m0 + ty * 4 + a < pr.M) slab[pr.bias_off + m0 + ty * 4 + a] = csa[a];
         }
         if (pr.nsplit > 1) {
-            fence_acquire();             // every thread: its partial is visible device-wide before the ticket is taken
+            // the CTA's partial tile is published by ONE fence: the barrier orders every thread's stores before thread 0's
+            // device-scope fence + ticket (the grid-barrier pattern); the finishing CTA reads with L1-bypassing loads
             MMG_SYNCTHREADS();
-            if (tid == 0) s_flag = (ticket_take(sy.tile_tickets + out_tile) == (unsigned)pr.nsplit - 1) ? 1 : 0;
+            if (tid == 0) {
+                fence_acquire();
+                s_flag = (ticket_take(sy.tile_tickets + out_tile) == (unsigned)pr.nsplit - 1) ? 1 : 0;
+                fence_acquire();
+            }
             MMG_SYNCTHREADS();
             fin = s_flag != 0;
+            MMG_TRACE_AT(4, 3);
             if (fin) {
-                fence_acquire();
-                // last split to arrive: sum all partials in split order and write the final tile
+                // last split to arrive: sum all partials in split order (this CTA's own share from its registers would change the
+                // order with the arrival order, so every share is re-read) and write the final tile
+                if (vec) {
+                    // the splits' partials of this thread's 4 rows: 2 slabs x 4 rows in flight at once
+                    float4 v[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const int i = m0 + ty * 4 + a;
+                        v[a] = i < pr.M ? ld_cg4(grads + (size_t)pr.c_off + (size_t)i * pr.ldc + j0) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    for (int q0 = 1; q0 < pr.nsplit; q0 += 2) {
+                        float4 t4[2][4];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u)
+#pragma unroll
+                            for (int a = 0; a < 4; ++a) {
+                                const int i = m0 + ty * 4 + a;
+                                t4[u][a] = (q0 + u < pr.nsplit && i < pr.M)
+                                    ? ld_cg4(arena + (size_t)(q0 + u - 1) * tab.slab_stride + (size_t)pr.c_off + (size_t)i * pr.ldc + j0)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+#pragma unroll
+                        for (int u = 0; u < 2; ++u)
+#pragma unroll
+                            for (int a = 0; a < 4; ++a) { v[a].x += t4[u][a].x; v[a].y += t4[u][a].y; v[a].z += t4[u][a].z; v[a].w += t4[u][a].w; }
+                    }
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const int i = m0 + ty * 4 + a;
+                        if (i >= pr.M) continue;
+                        *reinterpret_cast<float4*>(grads + (size_t)pr.c_off + (size_t)i * pr.ldc + j0) = v[a];
+                        acc[a][0] = v[a].x; acc[a][1] = v[a].y; acc[a][2] = v[a].z; acc[a][3] = v[a].w;
+                    }
+                }
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
                     const int i = m0 + ty * 4 + a;
-                    if (i >= pr.M) continue;
+                    if (i >= pr.M || vec) continue;
                     const size_t off = (size_t)pr.c_off + (size_t)i * pr.ldc + j0;
-                    if (vec) {
-                        float4 v = ld_cg4(grads + off);
-                        for (int q = 1; q < pr.nsplit; ++q) {
-                            const float4 t4 = ld_cg4(arena + (size_t)(q - 1) * tab.slab_stride + off);
-                            v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w;
-                        }
-                        *reinterpret_cast<float4*>(grads + off) = v;
-                        acc[a][0] = v.x; acc[a][1] = v.y; acc[a][2] = v.z; acc[a][3] = v.w;
-                    } else {
+                    {
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             if (j0 + c >= pr.N) continue;
@@ -346,13 +392,15 @@ k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, co
         if (j < pr.N) slab[pr.c_off + j] = v;
         if (want_bias) slab[pr.bias_off] = bv;
         if (pr.nsplit > 1) {
-            fence_acquire();
             MMG_SYNCTHREADS();
-            if (tid == 0) s_flag = (ticket_take(sy.tile_tickets + out_tile) == (unsigned)pr.nsplit - 1) ? 1 : 0;
+            if (tid == 0) {
+                fence_acquire();
+                s_flag = (ticket_take(sy.tile_tickets + out_tile) == (unsigned)pr.nsplit - 1) ? 1 : 0;
+                fence_acquire();
+            }
             MMG_SYNCTHREADS();
             fin = s_flag != 0;
             if (fin) {
-                fence_acquire();
                 if (j < pr.N) {
                     v = ld_cg(grads + pr.c_off + j);
                     for (int q = 1; q < pr.nsplit; ++q) v += ld_cg(arena + (size_t)(q - 1) * tab.slab_stride + pr.c_off + j);
@@ -402,16 +450,20 @@ k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, co
             }
         }
     }
+    MMG_TRACE_AT(4, 4);
     if (!fin) return;
     if (pv.world > 1) fence_system();     // the tile lives in the symmetric send buffer: visible to the peers before it is counted
     // ---- finished output tile: its sum of squares; the CTA that finishes the LAST tile adds them up per module --------------
     const float tile_ss = block_sum_256(ss, red);
     if (tid == 0) {
         sy.tile_norm[out_tile] = tile_ss;
+        sy.tile_norm[kMaxOutTiles + out_tile] = (float)pr.seg;          // the module the tile belongs to (K_update's per-module sums)
         if (pr.nsplit > 1) sy.tile_tickets[out_tile] = 0;                // ready for the next launch
-        s_flag = (ticket_take(sy.done) == (unsigned)tab.total_out - 1) ? 1 : 0;
+        if (!defer_tail) s_flag = (ticket_take(sy.done) == (unsigned)tab.total_out - 1) ? 1 : 0;
     }
+    if (defer_tail) return;      // single-rank fused iteration: K_update adds the tile sums itself, no finishing CTA
     MMG_SYNCTHREADS();
+    MMG_TRACE_AT(4, 5);
     if (!s_flag) return;
     fence_acquire();
     {
@@ -441,6 +493,7 @@ k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, co
             if (tid < pv.world) peer_signal(pv.flags[tid] + MMG_MAX_PEERS + pv.rank, pv.iter);
         }
     }
+    MMG_TRACE_AT(4, 6);
 }
 
 enum { kUpdThreads = 256 };
@@ -558,13 +611,41 @@ struct OptHyper { int optim; float lr, max_norm; long long step; };
 
 // `norm_final`: per-module sum of squares of the gradient (K_wgrad / K_grad_norm), or with peers: the per-rank slice sums
 // that K_peer_reduce_scatter published (added in rank order after the slices have arrived).
+// `norm_tiles` > 0 (single-rank fused iteration): K_wgrad left one sum of squares per finished output tile (+ the tile's module)
+// and no finishing CTA; every CTA adds them up itself, in tile order (the same numbers in every CTA).
 MMG_DEVICE void update_body(const SegInfo& seg, const OptHyper& hp, float* params, const float* grads_in, float* grads_out,
-                            float* state1, float* state2, const double* norm_final, float* grad_norms, const double* stats,
-                            const long long* opt_counters, const PeerView& pv) {
+                            float* state1, float* state2, double* norm_final, float* grad_norms, const double* stats,
+                            const long long* opt_counters, const PeerView& pv, const float* tile_norm = nullptr, int norm_tiles = 0) {
     MMG_SHARED float coef[4];
     MMG_SHARED int s_err;
+    MMG_SHARED double tsum[4][kUpdThreads / 32];
     const int tid = threadIdx.x;
     if (tid == 0) s_err = 0;
+    if (norm_tiles > 0) {
+        double s4[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int o0 = 0; o0 < norm_tiles; o0 += 4 * kUpdThreads) {      // 8 loads in flight per thread
+            float nv[4], sv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int o = o0 + u * kUpdThreads + tid;
+                nv[u] = o < norm_tiles ? tile_norm[o] : 0.f;
+                sv[u] = o < norm_tiles ? tile_norm[kMaxOutTiles + o] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int sg = (int)sv[u];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) s4[k] += sg == k ? (double)nv[u] : 0.0;
+            }
+        }
+        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double v = warp_sum_d(s4[k]);
+            if (lane == 0) tsum[k][warp] = v;
+        }
+        MMG_SYNCTHREADS();
+    }
     if (pv.world > 1) {
         if (tid < pv.world && !peer_wait(pv.flags[pv.rank] + 2 * MMG_MAX_PEERS + tid, pv.iter, pv.error)) *pv.error = 3;
         MMG_SYNCTHREADS();
@@ -573,6 +654,10 @@ MMG_DEVICE void update_body(const SegInfo& seg, const OptHyper& hp, float* param
     if (tid < 4) {   // global L2 norm per module
         double v = 0.0;
         if (pv.world > 1) for (int r = 0; r < pv.world; ++r) v += peer_load_d(pv.norms[pv.rank] + 4 * r + tid);
+        else if (norm_tiles > 0) {
+            for (int w = 0; w < kUpdThreads / 32; ++w) v += tsum[tid][w];
+            if (blockIdx.x == 0) norm_final[tid] = v;
+        }
         else v = norm_final[tid];
         const float total = (float)sqrt(v);
         const float cc = hp.max_norm / (total + 1e-6f);       // clip_grad_norm: scale only when coef < 1
@@ -635,10 +720,17 @@ MMG_DEVICE void update_body(const SegInfo& seg, const OptHyper& hp, float* param
 
 MMG_GLOBAL void __launch_bounds__(kUpdThreads)
 k_update(SegInfo seg, OptHyper hp, float* params, const float* grads_in, float* grads_out, float* state1, float* state2,
-         const double* norm_final, float* grad_norms, const double* stats, const long long* opt_counters, PeerView pv) {
+         double* norm_final, float* grad_norms, const double* stats, const long long* opt_counters, PeerView pv,
+         const float* tile_norm, int norm_tiles, int n_loss_parts, Dims d, WsPtrs W) {
     pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
     pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
-    update_body(seg, hp, params, grads_in, grads_out, state1, state2, norm_final, grad_norms, stats, opt_counters, pv);
+    MMG_TRACE_AT(5, 0);
+    update_body(seg, hp, params, grads_in, grads_out, state1, state2, norm_final, grad_norms, stats, opt_counters, pv, tile_norm,
+                norm_tiles);
+    // fused iteration: the backward kernel left per-CTA partials of the five loss values; one CTA adds them up here, off every
+    // critical path (the values are only reported)
+    if (n_loss_parts > 0 && blockIdx.x == gridDim.x - 1) { MMG_SYNCTHREADS(); loss_finalize(d, W, n_loss_parts); }
+    MMG_TRACE_AT(5, 7);
 }
 
 MMG_GLOBAL void k_init_rng(unsigned long long* st, unsigned long long seed) {

@@ -206,7 +206,7 @@ def run_train_step_case(case, device):
             if cfg.optim_type == "SGD":
                 atol = lr * 1e-3 + 1e-7
             elif g is not None:
-                atol = np.where((g.abs() < 1e-6).numpy(), 12 * lr, atol)
+                atol = np.where((g.abs() < 1e-5).numpy(), 12 * lr, atol)     # same noise-level rule as parity_util
             pu.assert_close("%s/param %s.%s" % (case, a, k), p.detach().cpu().numpy(), oparams[a][k].numpy(), rtol=1e-5,
                             atol=atol)
     return eng
