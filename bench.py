@@ -299,7 +299,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=None, choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--no-flush", action="store_true", help="skip the secondary measurement that flushes L2 between steps")
+    ap.add_argument("--ring-mib", type=int, default=160, help="size of the ring of distinct input batches (must exceed L2)")
     ap.add_argument("--no-dp-check", action="store_true", help="N>1: skip the global-batch oracle check before timing")
     ap.add_argument("--dp", default="peer", choices=["peer", "nccl"],
                     help="N>1: in-kernel NVLink peer-memory reduction (default) or torch.distributed NCCL all-reduce")
@@ -337,14 +338,18 @@ def main():
     e.load_params(syn.init_params(fl, seed=0))
     if words:
         e.set_desc_set(**words)
-    # synthetic inputs: a ring of distinct batches, resident in HBM for `value`, in pinned host memory for `e2e`
-    nb = 8
-    batches = [syn.batch(fl, seed=100 * rank + i) for i in range(nb)]
+    # synthetic inputs: a ring of distinct batches LARGER THAN L2 (126 MB), resident in HBM for `value`, in pinned host memory
+    # for `e2e`: every timed step reads a batch that cannot be cache resident, while parameters / optimizer state / workspace
+    # stay wherever the previous step left them, as in a real training loop
+    x_bytes = B * fl.img_feat_dim * 4
+    nb = max(8, -(-args.ring_mib * (1 << 20) // x_bytes))
+    gen = torch.Generator().manual_seed(1000 + rank)
     desc = syn.batch(fl, seed=0)[1].to(dev)             # class descriptions are shared by all ranks
-    xs = [b[0].to(dev) for b in batches]
-    ts = [b[2].to(dev) for b in batches]
-    hx = [b[0].pin_memory() for b in batches]
-    ht = [b[2].pin_memory() for b in batches]
+    hx_all = torch.randn(nb, B, fl.img_feat_dim, generator=gen).pin_memory()           # x ~ N(0,1), SURVEY.md 8(d)
+    ht_all = torch.randint(0, fl.n_classes, (nb, B), generator=gen, dtype=torch.int64).pin_memory()
+    xs_all, ts_all = hx_all.to(dev), ht_all.to(dev)
+    xs, ts = list(xs_all.unbind(0)), list(ts_all.unbind(0))
+    hx, ht = list(hx_all.unbind(0)), list(ht_all.unbind(0))
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     dp_mode = "none"
@@ -410,31 +415,35 @@ def main():
         if dist is not None:
             dist.all_reduce(kk, op=dist.ReduceOp.MAX)
         K = int(kk)
+    # ---- primary measurement: EXACTLY K steps back to back over the input ring (inputs larger than L2), one pair of CUDA
+    #      events on the launching stream, barrier + synchronize on both sides
     lib.dll.mmg_launch_count_reset()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     t_wall = time.perf_counter()
+    a0.record()
     for i in range(K):
-        if flush is not None:
-            flush.zero_()                      # evict L2 (126 MB) between timed steps; outside the per-step events
-        ev[i][0].record()
-        step(i)
-        ev[i][1].record()
+        step(W + i)
+    a1.record()
     sync_all()
     t_wall = time.perf_counter() - t_wall
     launches = lib.dll.mmg_launch_count()
-    ms = [a.elapsed_time(b) for a, b in ev]
-    tot_ms = float(sum(ms))
+    tot_ms = a0.elapsed_time(a1)
     active = e.losses()["active_steps"]
-    # back-to-back (L2-warm) run of the same K steps, one pair of events
-    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    a0.record()
-    for i in range(K):
-        step(i)
-    a1.record()
-    sync_all()
-    warm_ms = a0.elapsed_time(a1)
+    # ---- secondary: the round-1 protocol, L2 flushed by a 256 MiB memset before every step (outside the per-step events);
+    #      the memset leaves L2 full of dirty lines, so this also charges their write-back to the step
+    flushed_ms = None
+    if flush is not None:
+        Kf = min(K, 400)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kf)]
+        sync_all()
+        for i in range(Kf):
+            flush.zero_()
+            ev[i][0].record()
+            step(i)
+            ev[i][1].record()
+        sync_all()
+        flushed_ms = float(sum(a.elapsed_time(b) for a, b in ev)) / Kf
     sampler.mark_end()
     clocks = sampler.stop()
     steps_per_iter = T if fl.fixed_exchange else float(active)
@@ -459,6 +468,7 @@ def main():
     h0.record()
     run_host(K)
     h1.record()
+    e2e_enqueue_ms = 1e3 * (time.perf_counter() - t0)         # host time to enqueue the K steps (before any synchronisation)
     torch.cuda.synchronize(dev)
     e2e_wall_ms = 1e3 * (time.perf_counter() - t0)
     e2e_ms = max(h0.elapsed_time(h1), 0.0)
@@ -466,7 +476,7 @@ def main():
 
     # ---- N>1: the replicas must still be bit-identical and no peer wait may have timed out ----------------------------------
     replicas = None
-    t = torch.tensor([tot_ms, warm_ms, e2e_ms, e2e_wall_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([tot_ms, flushed_ms if flushed_ms is not None else 0.0, e2e_ms, e2e_wall_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if dp_mode == "peer":
@@ -477,7 +487,7 @@ def main():
         same = all(bool(torch.equal(alld[0], d_)) for d_ in alld)
         assert same, "parameter replicas diverged across ranks: %s" % [d_.tolist() for d_ in alld]
         replicas = "bit-identical on %d ranks (int32 checksum + sum of squares of the flat parameter buffer)" % world
-    tot_ms, warm_ms, e2e_ms, e2e_wall_ms = [float(v) for v in t]
+    tot_ms, flushed_ms_max, e2e_ms, e2e_wall_ms = [float(v) for v in t]
 
     if rank != 0:
         if dist is not None:
@@ -486,7 +496,8 @@ def main():
     e2e = {"value": world * steps_per_iter * K / (e2e_ms * 1e-3), "unit": "exchange-steps/s",
            "h2d_bytes_per_step": int(world * (B * fl.img_feat_dim * 4 + B * 8)),
            "d2h_bytes_per_step": int(world * capi.MMG_LOSS_COUNT * 4), "ms_per_step": e2e_ms / K,
-           "ms_per_step_host_wall": e2e_wall_ms / K,
+           "ms_per_step_host_wall": e2e_wall_ms / K, "ms_per_step_host_enqueue": e2e_enqueue_ms / K,
+           "launch": "CUDA graph replay per staging slot" if getattr(e, "_hp", {}).get("graphs") else "eager launches",
            "note": "mmg_host_prefetch + mmg_train_step_staged (N>1: the same staging slots feeding mmg_train_step_peer): pinned "
                    "host x/target -> device on a copy stream (double-buffered, overlaps the previous step), losses -> pinned "
                    "host every step; bytes are the whole job's (all ranks); device-timed, max over ranks"}
@@ -500,7 +511,7 @@ def main():
     bytes_iter = algorithmic_bytes_per_iteration(cfgd, world)
     # DRAM traffic per iteration from the committed ncu capture of this same command (profiles/)
     traffic, traffic_src, traffic_protocol = None, None, None
-    if name in ("C2", "C2A") and world == 1 and flush is not None:
+    if name in ("C2", "C2A") and world == 1:
         try:
             import glob
             pat = "*_dram_traffic.json" if name == "C2" else "*_c2a_desc_attn_dram.json"
@@ -526,10 +537,14 @@ def main():
                 "dp_reduction": {"peer": "in-kernel sums over NVLink peer memory (statistics + gradient); no collective call",
                                  "nccl": "torch.distributed NCCL all-reduce (statistics + flat gradient)",
                                  "none": "single GPU"}[dp_mode],
-                "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA events)" if flush is not None
-                else "not flushed (working set ~25 MB stays L2 resident)",
+                "l2": "inputs larger than L2: ring of %d distinct batches (%.0f MiB of features per rank) cycled through the timed "
+                      "steps, no flush; parameters, optimizer state and workspace stay cache resident as in a training loop"
+                      % (nb, nb * x_bytes / float(1 << 20)),
                 "preconditioning_iterations": n_burst, "dp_oracle_check": dp_check, "replicas": replicas},
-        "value_l2_warm": world * steps_per_iter * K / (warm_ms * 1e-3), "ms_per_step_l2_warm": warm_ms / K,
+        "value_l2_flushed": (world * steps_per_iter / (flushed_ms_max * 1e-3)) if flush is not None else None,
+        "ms_per_step_l2_flushed": flushed_ms_max if flush is not None else None,
+        "l2_flushed_protocol": "secondary, round-1 protocol: 256 MiB memset before every step, per-step CUDA events (the memset's dirty "
+                               "lines are written back while the step runs)",
         "gpu_launches": int(launches), "launches_per_step": launches / float(K),
         "wall_s_timed_region": t_wall, "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

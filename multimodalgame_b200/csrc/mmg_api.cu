@@ -55,6 +55,47 @@ static int fail(int code, const char* fmt, ...) {
 }
 
 #ifndef MMG_CPU_EMU
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda).  Returns false when the
+// driver does not offer it or an encode fails: the caller then stages the operands with asynchronous 16-byte copies.
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmapEncodeFn tmap_encoder() {
+    static TmapEncodeFn fn = nullptr;
+    static int tried = 0;
+    if (!tried) {
+        tried = 1;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (TmapEncodeFn)p;
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+// K-major fp32 matrix (rows x cols, row stride cols * 4 bytes): boxes of 32 floats (one 128-byte swizzle span) x box_rows rows
+static bool encode_kmajor_tmap(CUtensorMap* tm, const float* base, int rows, int cols, int box_rows) {
+    TmapEncodeFn enc = tmap_encoder();
+    if (!enc) return false;
+    // small cache: the weight matrix and the (two) staging slots of the host pipeline come back every step
+    struct Slot { const float* base; int rows, cols, box; CUtensorMap tm; };
+    static thread_local Slot cache[8];
+    static thread_local int next = 0;
+    for (int i = 0; i < 8; ++i)
+        if (cache[i].base == base && cache[i].rows == rows && cache[i].cols == cols && cache[i].box == box_rows) { *tm = cache[i].tm; return true; }
+    Slot& sl = cache[next];
+    next = (next + 1) & 7;
+    sl.base = nullptr;
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)cols * 4};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    if (enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    sl.base = base; sl.rows = rows; sl.cols = cols; sl.box = box_rows; sl.tm = *tm;
+    return true;
+}
 static int check_cuda(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(MMG_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
@@ -376,6 +417,18 @@ static int make_plan(const Dims& d, Plan* pl) {
 #ifndef MMG_CPU_EMU
 template <typename K>
 static int set_smem(K kernel, int bytes) {
+    // one driver call per (kernel instantiation, device) and size change, not per launch: the attribute is sticky
+    // (kernels of different instantiations can share one function-pointer TYPE, so the cache is keyed by the pointer value)
+    struct Ent { const void* fn; int bytes, dev; };
+    static thread_local Ent cache[64];
+    static thread_local int n_ent = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    Ent* hit = nullptr;
+    for (int i = 0; i < n_ent; ++i) if (cache[i].fn == (const void*)kernel && cache[i].dev == dev) { hit = &cache[i]; break; }
+    if (hit != nullptr && hit->bytes == bytes) return MMG_OK;
+    if (hit == nullptr && n_ent < 64) { hit = &cache[n_ent++]; hit->fn = (const void*)kernel; hit->dev = dev; }
+    if (hit != nullptr) hit->bytes = bytes;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return fail(MMG_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", bytes, cudaGetErrorString(e));
     return MMG_OK;
@@ -786,16 +839,23 @@ static int exchange_forward_impl(const mmg_config* cfg, const float* d_params, c
     // image-layer GEMM on the tensor cores (tcgen05, 3xTF32) when the shapes allow: 128-row tiles of hidden units, K-slices of
     // whole 32-float swizzle atoms, 16-byte aligned rows (MMG_UMMA=0 keeps the FFMA tiles)
     int use_umma = 0, pre_smem = 0, n_hx_l = n_hx;
+    ImageTmaps tmaps;
+    memset(&tmaps, 0, sizeof(tmaps));
 #ifndef MMG_CPU_EMU
     {
-        static int umma_off = -1;
+        static int umma_off = -1, tma_off = -1;
         if (umma_off < 0) { const char* e = getenv("MMG_UMMA"); umma_off = (e && e[0] == '0') ? 1 : 0; }
+        if (tma_off < 0) { const char* e = getenv("MMG_UMMA_TMA"); tma_off = (e && e[0] == '0') ? 1 : 0; }   // =0: cp.async staging
         if (!umma_off && d.Hi % umma::kM == 0 && d.F % 32 == 0 && hx_kslice % 32 == 0 && hx_kslice <= umma::kMaxSliceK &&
             (((size_t)in->d_x | (size_t)P.p[MMG_P_SEN_IMG_W]) & 15) == 0) {
             use_umma = 1;
             pre_smem = umma::tile_smem_bytes(hx_kslice);
             n_hx_l = (d.Hi / umma::kM) * cdiv(d.B, umma::kN) * W.hx_split;
             if ((rc = set_smem(k_pre, pre_smem))) return rc;
+            // operands staged by the TMA unit (tensor maps: box = 32 floats x tile rows, 128-byte swizzle, zero fill past the batch)
+            if (!tma_off && encode_kmajor_tmap(&tmaps.w, P.p[MMG_P_SEN_IMG_W], d.Hi, d.F, umma::kM) &&
+                encode_kmajor_tmap(&tmaps.x, in->d_x, d.B, d.F, umma::kN))
+                use_umma = 2;
         }
     }
 #endif
@@ -804,7 +864,7 @@ static int exchange_forward_impl(const mmg_config* cfg, const float* d_params, c
     const int cls_dyn = d.WV <= kRowsKMax ? rows_tile_smem_floats(d.WV) * 4 : 0;
     if (cls_dyn > pre_smem) { pre_smem = cls_dyn; if ((rc = set_smem(k_pre, pre_smem))) return rc; }
     MMG_LAUNCH(k_pre, n_hx_l + n_cls + n_pack, kGemmThreads, pre_smem, st, d, P, W, ei, n_hx_l, hx_kslice, pl.fast_fwd | (pl.fast << 1), n_cls,
-               use_umma, pre_smem / 4);
+               use_umma, pre_smem / 4, tmaps);
     if ((rc = check_cuda("k_pre"))) return rc;
     // K_exchange_fwd
     const AttnArgs aa = attn_args(d, P, ei, pl);

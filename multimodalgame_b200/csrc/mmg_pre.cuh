@@ -67,7 +67,7 @@ MMG_DEVICE float bwd_image_elem(const Dims& d, const BwdImage& im, const ParamPt
 
 MMG_GLOBAL void __launch_bounds__(kGemmThreads)
 k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_kslice, int fast, int n_cls_tiles, int use_umma,
-      int dyn_floats) {
+      int dyn_floats, const MMG_GRID_CONSTANT ImageTmaps tmaps) {
     pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
     pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
     MMG_SHARED __attribute__((aligned(16))) float gs[kGemmSmemFloats];
@@ -94,7 +94,7 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
         const int s = t;
         const int k0 = s * hx_kslice, nk = min(hx_kslice, d.F - k0);
         umma::image_layer_tile(P.p[MMG_P_SEN_IMG_W], in.x, d.F, d.Hi, d.B, mt * umma::kM, bt * umma::kN, k0, nk,
-                               W.hx_part + (size_t)s * d.B * d.Hi, umma_smem);
+                               W.hx_part + (size_t)s * d.B * d.Hi, umma_smem, use_umma == 2 ? &tmaps : nullptr);
         return;
     }
 #endif
@@ -177,9 +177,11 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
         Operand Bo = which == 0 ? Operand{P.p[MMG_P_REC_Y1_W] + d.Hr, nullptr, nullptr, nullptr, d.Hr + d.WV, 0, 0, 0, 0, OP_PLAIN}
                                 : Operand{P.p[MMG_P_REC_WD_W], nullptr, nullptr, nullptr, d.WV, 0, 0, 0, 0, OP_PLAIN};
         float acc[4][4];
+        MMG_TRACE_AT(0, 3);
         if (rows_tile_ok(A.p, A.ld, d.WV, nullptr, 0, 0, Bo.p, Bo.ld) && rows_tile_smem_floats(d.WV) <= dyn_floats) {
             MMG_DYN_SMEM(dyn_raw);
             gemm_rows_tile(A.p, A.ld, d.WV, nullptr, 0, 0, Bo.p, Bo.ld, d.D, d.Hr, mt * kTile, nt * kTile, acc, reinterpret_cast<float*>(dyn_raw));
+            MMG_TRACE_AT(0, 6);
         } else
         gemm_tile_deep(A, Bo, d.D, d.Hr, mt * kTile, nt * kTile, 0, d.WV, acc, gs);
         const int tx = tid % 16, ty = tid / 16;

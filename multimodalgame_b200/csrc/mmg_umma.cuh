@@ -17,7 +17,12 @@
 #include "mmg_platform.cuh"
 
 #ifndef MMG_CPU_EMU
+#include <cuda.h>        // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 namespace mmg {
+// TMA descriptors of the two operands of the image layer (K-major, fp32, box = 32 floats x tile rows, SWIZZLE_128B): the
+// tensor-map unit writes a tile straight into the canonical UMMA shared-memory layout, out-of-range rows arrive as zeros.
+struct ImageTmaps { CUtensorMap w, x; };
+#define MMG_GRID_CONSTANT __grid_constant__
 namespace umma {
 
 enum { kM = 128, kN = 64, kAtomK = 32, kMaxSliceK = 128, kTmemCols = 64 };
@@ -109,13 +114,25 @@ MMG_DEVICE void stage_split(unsigned char* hi, unsigned char* lo, const float* s
     }
 }
 
+// 2-D tensor-map load of one box (32 floats of K x `rows` rows) into shared memory; completion is counted in bytes on `bar`.
+MMG_DEVICE void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int k, int row, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tm), "r"(k), "r"(row), "r"(smem_u32(bar))
+        : "memory");
+}
+
 // One split-K tile of the image layer, transposed:  D^T[n][b] = sum_{f in slice} W_img[n0 + n][f] * x[b0 + b][f]
 // (M = 128 hidden units on the TMEM lanes, N = 64 batch rows on the columns).  256 threads.  Partial sums go to
 // part[(b0 + b) * Hi + n0 + n] for b0 + b < B.
+// `tm` != nullptr: the operands are staged by the TMA unit (cp.async.bulk.tensor, one box per 32-float atom and operand) and
+// only split (hi / lo) by the threads; nullptr: asynchronous 16-byte copies issued by the threads.
 MMG_DEVICE void image_layer_tile(const float* w_img, const float* x, int F, int Hi, int B, int n0, int b0, int k0, int nk,
-                                 float* part, unsigned char* smem_raw) {
+                                 float* part, unsigned char* smem_raw, const ImageTmaps* tm) {
     constexpr int NT = 256;
     MMG_SHARED uint64_t s_bar;
+    MMG_SHARED uint64_t s_ld;
     MMG_SHARED uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // SWIZZLE_128B atoms: 1024-byte aligned
@@ -123,10 +140,39 @@ MMG_DEVICE void image_layer_tile(const float* w_img, const float* x, int F, int 
     unsigned char* a_lo = a_hi + (size_t)kM * nk * 4;
     unsigned char* b_hi = a_lo + (size_t)kM * nk * 4;
     unsigned char* b_lo = b_hi + (size_t)kN * nk * 4;
-    if (tid == 0) { mbar_init(&s_bar, 1); mbar_fence_init(); }
-    if (warp == 0) tmem_alloc(&s_tmem);
-    stage_split<NT>(a_hi, a_lo, w_img + (size_t)n0 * F + k0, (size_t)F, kM, Hi - n0, nk, tid);
-    stage_split<NT>(b_hi, b_lo, x + (size_t)b0 * F + k0, (size_t)F, kN, B - b0, nk, tid);
+    if (tid == 0) { mbar_init(&s_bar, 1); mbar_init(&s_ld, 1); mbar_fence_init(); }
+    if (tm != nullptr) {
+        __syncthreads();                 // the barrier is initialised before the TMA unit may signal it
+        if (tid == 0) {
+            const int atoms = nk / kAtomK;
+            mbar_expect_tx(&s_ld, (uint32_t)((kM + kN) * nk * 4));
+            for (int a = 0; a < atoms; ++a) {
+                tma_load_2d(a_hi + (size_t)a * kM * 128, &tm->w, k0 + a * kAtomK, n0, &s_ld);
+                tma_load_2d(b_hi + (size_t)a * kN * 128, &tm->x, k0 + a * kAtomK, b0, &s_ld);
+            }
+        }
+        if (warp == 0) tmem_alloc(&s_tmem);
+        mbar_wait(&s_ld, 0);
+        // split in place: hi keeps the TF32 head, lo = x - hi at the same (swizzled) offset of the lo buffer; A | lo A | B | lo B
+        // are contiguous, every thread walks 16-byte chunks of the raw tiles
+        const int chunks_a = kM * nk / 4, chunks_b = kN * nk / 4;
+        for (int idx = tid; idx < chunks_a + chunks_b; idx += NT) {
+            unsigned char* h = idx < chunks_a ? a_hi + (size_t)idx * 16 : b_hi + (size_t)(idx - chunks_a) * 16;
+            unsigned char* l = idx < chunks_a ? a_lo + (size_t)idx * 16 : b_lo + (size_t)(idx - chunks_a) * 16;
+            const float4 v = *reinterpret_cast<const float4*>(h);
+            float4 hh, ll;
+            hh.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); ll.x = v.x - hh.x;
+            hh.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); ll.y = v.y - hh.y;
+            hh.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); ll.z = v.z - hh.z;
+            hh.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); ll.w = v.w - hh.w;
+            *reinterpret_cast<float4*>(h) = hh;
+            *reinterpret_cast<float4*>(l) = ll;
+        }
+    } else {
+        if (warp == 0) tmem_alloc(&s_tmem);
+        stage_split<NT>(a_hi, a_lo, w_img + (size_t)n0 * F + k0, (size_t)F, kM, Hi - n0, nk, tid);
+        stage_split<NT>(b_hi, b_lo, x + (size_t)b0 * F + k0, (size_t)F, kN, B - b0, nk, tid);
+    }
     MMG_TRACE_AT(0, 1);
     fence_proxy_async();            // the staged operands (generic-proxy writes) become visible to the tensor-core (async) proxy
     tc_fence_before();
@@ -174,4 +220,9 @@ MMG_DEVICE void image_layer_tile(const float* w_img, const float* x, int F, int 
 
 }  // namespace umma
 }  // namespace mmg
+#else
+namespace mmg {
+struct ImageTmaps { int unused; };
+}
+#define MMG_GRID_CONSTANT
 #endif

@@ -7,6 +7,7 @@ views into one flat fp32 buffer so that clip + optimizer step is one kernel and 
 contiguous gradient buffer.
 """
 import ctypes as C
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -205,8 +206,11 @@ class GameEngine(object):
                       self._stream())
 
     # ---- host-buffer pipeline (the end-to-end path: pinned host batches in, loss values out) -------------------------
-    def enable_host_pipeline(self, desc):
-        """Two device staging slots + a copy stream: the H2D copy of batch i+1 overlaps the training of batch i."""
+    def enable_host_pipeline(self, desc, graphs=True):
+        """Two device staging slots + a copy stream: the H2D copy of batch i+1 overlaps the training of batch i.
+        `graphs`: capture the launch sequence of one iteration per slot in a CUDA graph and replay it (single GPU, RMSprop / SGD:
+        nothing in the sequence changes from step to step; Adam's bias correction takes the step number as a kernel argument
+        and the data-parallel paths use it as the flag value, so those keep the eager launches)."""
         d = self.dims
         dev = self.device
         self._hp = dict(
@@ -218,16 +222,47 @@ class GameEngine(object):
         self._hp["inp"] = [self._inputs(self._hp["x"][i], self._hp["desc"], self._hp["t"][i], True, None, None, None, 6)
                            for i in range(2)]
         self._keep = None
+        # everything that does not change from step to step is marshalled ONCE: the per-step Python work of the host
+        # pipeline is two foreign calls with prebuilt arguments (at ~0.1 ms of device time per step the host must stay ahead)
+        hp = self._hp
+        cur = torch.cuda.current_stream(dev)
+        for i in range(2):                       # materialise the event handles before the C calls re-record them
+            hp["ready"][i].record(hp["copy_stream"]); hp["free"][i].record(cur)
+        cs = C.c_void_p(hp["copy_stream"].cuda_stream)
+        vp = lambda t: C.c_void_p(t.data_ptr())
+        hp["pf_args"] = [(vp(hp["x"][i]), vp(hp["t"][i]), cs, C.c_void_p(hp["free"][i].cuda_event),
+                          C.c_void_p(hp["ready"][i].cuda_event)) for i in range(2)]
+        s2 = None if self.state2 is None else vp(self.state2)
+        hp["ts_args"] = [(C.byref(self.cfg), vp(self.params), vp(self.grads), vp(self.state1), s2, C.byref(hp["inp"][i]),
+                          vp(self.workspace), C.c_void_p(hp["ready"][i].cuda_event), C.c_void_p(hp["free"][i].cuda_event))
+                         for i in range(2)]
+        hp["cfg_ref"] = C.byref(self.cfg)
+        hp["stream"] = cur
+        hp["stream_ptr"] = C.c_void_p(cur.cuda_stream)
+        hp["fn_pf"] = self.lib.dll.mmg_host_prefetch
+        hp["fn_ts"] = self.lib.dll.mmg_train_step_staged
+        hp["graphs"] = None
+        hp["losses_dev"] = self.ws("losses", (capi.MMG_LOSS_COUNT,))
+        if (graphs and self.device.type == "cuda" and getattr(self, "_peers", None) is None
+                and int(self.cfg.optim_type) != capi.OPTIM["Adam"] and os.environ.get("MMG_GRAPHS", "1") != "0"):
+            gs = []
+            for i in range(2):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    cfg, p, gr, s1, s2_, inp, ws, _, _ = hp["ts_args"][i]
+                    self.lib.call("mmg_train_step", cfg, p, gr, s1, s2_, C.c_int64(1), inp, ws,
+                                  C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+                gs.append(g)
+            hp["graphs"] = gs
 
     def host_prefetch(self, h_x, h_target):
         """Enqueue the H2D copy of the NEXT batch (pinned host tensors) into the free staging slot."""
         hp = self._hp
-        slot = hp["n"] % 2
-        free = C.c_void_p(hp["free"][slot].cuda_event) if hp["used"][slot] else None
-        hp["ready"][slot].record(hp["copy_stream"])      # materialise the event handle before the C call re-records it
-        self.lib.call("mmg_host_prefetch", C.byref(self.cfg), h_x.data_ptr(), h_target.data_ptr(),
-                      hp["x"][slot].data_ptr(), hp["t"][slot].data_ptr(), C.c_void_p(hp["copy_stream"].cuda_stream), free,
-                      C.c_void_p(hp["ready"][slot].cuda_event))
+        slot = hp["n"] & 1
+        dx, dt, cs, free, ready = hp["pf_args"][slot]
+        rc = hp["fn_pf"](hp["cfg_ref"], h_x.data_ptr(), h_target.data_ptr(), dx, dt, cs, free if hp["used"][slot] else None, ready)
+        if rc < 0:
+            self.lib.check(rc, "mmg_host_prefetch")
         hp["n"] += 1
         hp["pending"] = slot
 
@@ -248,12 +283,18 @@ class GameEngine(object):
             h_losses.copy_(self.ws("losses", (capi.MMG_LOSS_COUNT,)), non_blocking=True)
             return
         self.step += 1
-        s2 = None if self.state2 is None else self.state2.data_ptr()
-        hp["free"][slot].record(torch.cuda.current_stream(self.device))
-        self.lib.call("mmg_train_step_staged", C.byref(self.cfg), self.params.data_ptr(), self.grads.data_ptr(),
-                      self.state1.data_ptr(), s2, C.c_int64(self.step), C.byref(hp["inp"][slot]), self.workspace.data_ptr(),
-                      h_losses.data_ptr(), self._stream(), C.c_void_p(hp["ready"][slot].cuda_event),
-                      C.c_void_p(hp["free"][slot].cuda_event))
+        if hp["graphs"] is not None:
+            st = hp["stream"]
+            st.wait_event(hp["ready"][slot])
+            hp["graphs"][slot].replay()
+            hp["free"][slot].record(st)
+            h_losses.copy_(hp["losses_dev"], non_blocking=True)
+            hp["used"][slot] = True
+            return
+        cfg, p, g, s1, s2, inp, ws, ready, free = hp["ts_args"][slot]
+        rc = hp["fn_ts"](cfg, p, g, s1, s2, self.step, inp, ws, h_losses.data_ptr(), hp["stream_ptr"], ready, free)
+        if rc < 0:
+            self.lib.check(rc, "mmg_train_step_staged")
         hp["used"][slot] = True
 
     # ---- data parallel over NVLink peer memory (no collective call, no extra launch) ---------------------------------

@@ -307,6 +307,49 @@ def _find_seed(cfg, seed, iters, margin=1e-6, tries=40):
     raise AssertionError("no seed with sampling margin found")
 
 
+def run_flip_rate_case(cfg, lib, device, seeds, margin=1e-6, max_events=5):
+    """UNFILTERED seeds (no search for a comfortable sampling margin): the forward conversation with injected uniforms against
+    the oracle.  The kernels evaluate sigmoid with MUFU-based exp / reciprocal (abs. error ~2e-7 on a probability), so a draw
+    within that distance of its probability may come out the other way; from that step on the example's conversation
+    legitimately differs.  Per example the FIRST differing draw (time order: sender bits, stop bit, receiver bits) must have
+    |u - p| < `margin` in the oracle run, and the number of such events over all seeds must stay within `max_events`
+    (expected: draws x 2 x 2e-7, well below one per 1e6 draws).  Returns (events, draws)."""
+    B, T, M = cfg.batch_size, cfg.max_exchange, cfg.rec_w_dim
+    events, draws = [], 0
+    for s in seeds:
+        params = go.init_params(cfg, seed=s)
+        x, desc, target = go.synthetic_batch(cfg, seed=7 * s + 1)
+        us = go.draw_uniforms(np.random.RandomState(s), cfg)
+        ex = go.exchange(params, x, desc, cfg, True, uniforms=us)
+        e = eng.GameEngine(config_from(cfg), device=device, lib=lib)
+        e.load_params(params)
+        e.forward(x, desc, target, train=True, uniforms=stack_uniforms(us, cfg, B))
+        out = {k: v.detach().cpu().numpy() for k, v in e.outputs().items()}
+        Tp = len(ex["y"])
+        st = lambda key: np.stack([t.detach().numpy() for t in ex[key]], 0)
+        ref = {"sen": (st("sen_feats"), st("sen_probs"), np.stack([u[0] for u in us[:Tp]], 0)),
+               "stop": (st("stop_feat").reshape(Tp, B, 1), st("stop_prob").reshape(Tp, B, 1), np.stack([u[1] for u in us[:Tp]], 0).reshape(Tp, B, 1)),
+               "rec": (st("rec_feats"), st("rec_probs"), np.stack([u[2] for u in us[:Tp]], 0))}
+        got = {"sen": out["sen_feats"][:Tp], "stop": out["stop_feat"][:Tp].reshape(Tp, B, 1), "rec": out["rec_feats"][:Tp]}
+        draws += Tp * B * (2 * M + 1)
+        for b in range(B):
+            first = None
+            for t in range(Tp):
+                for kind in ("sen", "stop", "rec"):
+                    bits, probs, u = ref[kind]
+                    diff = np.nonzero(bits[t, b] != got[kind][t, b])[0]
+                    if diff.size:
+                        first = (s, b, t, kind, int(diff[0]), float(np.abs(u[t, b] - probs[t, b])[diff].max()))
+                        break
+                if first:
+                    break
+            if first:
+                assert first[5] < margin, "seed %d example %d step %d %s bit %d differs with |u - p| = %.3g (not a rounding flip)" % first
+                events.append(first)
+    assert len(events) <= max_events, "%d rounding flips in %d draws: %s" % (len(events), draws, events)
+    return events, draws
+
+
 def run_synth_case(cfg, lib, device, iters=1, seed=0, check_grads=True, tag="synth"):
     """Synthetic inputs (oracle's init, N(0,1) features/descriptions) at arbitrary — including BASELINE.json's full —
     sizes: fused `train_step` through the C-ABI vs the oracle, iteration by iteration."""
