@@ -357,8 +357,8 @@ void mmg_launch_count_reset(void);
  * ("name launches mean_us") into `out` (NUL-terminated, at most `cap` bytes), clears the records and returns how many
  * launches were recorded.  Without MMG_KTIME it writes an empty string and returns 0. */
 int mmg_debug_kernel_times(char* out, int32_t cap);
-/* Diagnostic, debug builds only (-DMMG_TRACE): copies the per-CTA time stamps [6 kernels][1024 CTAs][8 slots] (global timer,
- * ns) of the launches since the last call into `out` (count >= 6*1024*8) and clears them.  Release builds return 0. */
+/* Diagnostic, debug builds only (-DMMG_TRACE): copies the per-CTA time stamps [7 kernels][1024 CTAs][8 slots] (global timer,
+ * ns) of the launches since the last call into `out` (count >= 7*1024*8) and clears them.  Release builds return 0. */
 int mmg_debug_trace(unsigned long long* out, int32_t count);
 
 #ifdef __cplusplus

@@ -720,12 +720,12 @@ void mmg_launch_count_reset(void) { g_launches = 0; }
 
 int mmg_debug_trace(unsigned long long* out, int32_t count) {
 #if defined(MMG_TRACE) && !defined(MMG_CPU_EMU)
-    if (!out || count < 6 * 1024 * 8) return fail(MMG_ERR_INVALID, "trace buffer too small");
+    if (!out || count < 7 * 1024 * 8) return fail(MMG_ERR_INVALID, "trace buffer too small");
     if (cudaDeviceSynchronize() != cudaSuccess) return check_cuda("cudaDeviceSynchronize");
     if (cudaMemcpyFromSymbol(out, g_trace, sizeof(g_trace)) != cudaSuccess) return check_cuda("cudaMemcpyFromSymbol");
-    static unsigned long long zero[6 * 1024 * 8];
+    static unsigned long long zero[7 * 1024 * 8];
     cudaMemcpyToSymbol(g_trace, zero, sizeof(g_trace));
-    return 6 * 1024 * 8;
+    return 7 * 1024 * 8;
 #else
     (void)out; (void)count;
     return 0;
@@ -987,7 +987,8 @@ static int backward_impl(const mmg_config* cfg, const float* d_params, const mmg
     if ((rc = set_smem(k_wgrad, wgrad_smem_bytes()))) return rc;
     const int n_loss_parts = (fuse_loss && pl.fast) ? (d.use_binary ? 2 * d.B : d.B) : 0;
     const int defer = norm_tiles != nullptr && pv.world <= 1 ? 1 : 0;
-    if (norm_tiles != nullptr) { *norm_tiles = defer ? tab.total_out : 0; *loss_parts = defer ? n_loss_parts : 0; }
+    // data-parallel: the finishing CTA only raises the "send buffer complete" flags; K_update adds up the loss partials there too
+    if (norm_tiles != nullptr) { *norm_tiles = defer ? tab.total_out : 0; *loss_parts = (defer || pv.world > 1) ? n_loss_parts : 0; }
     MMG_LAUNCH(k_wgrad, tab.total_tiles, kGemmThreads, wgrad_smem_bytes(), st, d, tab, d_grads, W.slabs, P.p[MMG_P_SEN_CODE_W],
                P.p[MMG_P_SEN_CODE_BIAS], W.d_as, sy, pv, W, n_loss_parts, defer);
     return check_cuda("k_wgrad");
@@ -1104,8 +1105,8 @@ int mmg_peer_buffer_layout(const mmg_config* cfg, int64_t* total_bytes, int64_t*
     *send_off = 0;
     *recv_off = align256(L.total * 4);
     *stats_off = *recv_off + align256(L.total * 4);
-    *norms_off = *stats_off + align256((int64_t)stats_count(d) * 8);
-    *flags_off = *norms_off + align256(4 * MMG_MAX_PEERS * 8);
+    *norms_off = *stats_off + align256((int64_t)MMG_MAX_PEERS * stats_count(d) * 16);    // one slot per pushing rank, 2 packets per value
+    *flags_off = *norms_off + align256(4 * MMG_MAX_PEERS * 16);
     *total_bytes = *flags_off + align256(3 * MMG_MAX_PEERS * 8);
     return MMG_OK;
 }
@@ -1126,7 +1127,8 @@ int mmg_train_step_peer(const mmg_config* cfg, float* d_params, float* d_grads, 
     const bool fuse_loss = fused && fuse_loss_ok(cfg);
     if (!fuse_loss && (rc = loss_impl(cfg, d_params, in, d_workspace, -1, stream, pv, fused))) return rc;
     // local gradient -> this rank's symmetric send buffer (K_wgrad raises flag row 1 when it is complete)
-    if ((rc = backward_impl(cfg, d_params, in, d_workspace, pv.send[pv.rank], stream, pv, fuse_loss))) return rc;
+    int norm_tiles = 0, loss_parts = 0;
+    if ((rc = backward_impl(cfg, d_params, in, d_workspace, pv.send[pv.rank], stream, pv, fuse_loss, &norm_tiles, &loss_parts))) return rc;
     const Dims d = make_dims(*cfg);
     mmg_param_layout L;
     param_layout(d, &L);
@@ -1135,16 +1137,16 @@ int mmg_train_step_peer(const mmg_config* cfg, float* d_params, float* d_grads, 
     const WsPtrs W = resolve(w, d_workspace);
     const SegInfo seg = seg_info(L, d);
     cudaStream_t st = (cudaStream_t)stream;
-    // two-shot sum: this rank reduces its 1/G slice of all send buffers into every rank's receive buffer ...
+    // two-shot sum: this rank reduces its 1/G slice of all send buffers into its own receive buffer (+ the slice's norms to all) ...
     MMG_LAUNCH(k_peer_reduce_scatter, upd_ctas(cdiv64(L.total, pv.world)), kUpdThreads, 0, st, seg, pv, W.norm_part, W.tickets + 6,
                W.norm_final);
     if ((rc = check_cuda("k_peer_reduce_scatter"))) return rc;
-    // ... and the update waits for all slices (flag row 2), then clips and steps from the local receive buffer
+    // ... and the update waits for all slices (flag row 2), then clips and steps, pulling every slice from its owner
     OptHyper hp;
     hp.optim = cfg->optim_type; hp.lr = cfg->learning_rate; hp.max_norm = cfg->max_norm; hp.step = step;
     MMG_LAUNCH(k_update, upd_ctas(L.total), kUpdThreads, 0, st, seg, hp, d_params, (const float*)pv.recv[pv.rank], d_grads, d_state1,
                d_state2, W.norm_final, W.grad_norms, (const double*)W.stats, (const long long*)W.opt_counters, pv,
-               (const float*)W.tile_norm, 0, 0, d, W);
+               (const float*)W.tile_norm, 0, loss_parts, d, W);
     return check_cuda("k_update");
 }
 

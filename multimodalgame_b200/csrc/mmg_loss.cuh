@@ -289,12 +289,12 @@ MMG_DEVICE void stats_body(const Dims& d, const ParamPtrs& P, const WsPtrs& W, c
         }
     }
     if (pv.world > 1) {
-        // publish this rank's statistics: copy into the symmetric slot, then raise flag row 0 on every peer
         MMG_SYNCTHREADS();
-        for (int i = tid; i < stats_count(d); i += kStatsThreads) pv.stats[pv.rank][i] = W.stats[i];
-        fence_system();
-        MMG_SYNCTHREADS();
-        if (tid < pv.world) peer_signal(pv.flags[tid] + pv.rank, pv.iter);
+        // PUSH as self-validating packets (ll_store): this rank's statistics go into slot `rank` of EVERY rank's symmetric statistics
+        // area; no flag and no fence, the consumers spin on the packets' tags in their own memory
+        const int cnt = stats_count(d);
+        for (int i = tid; i < cnt * pv.world; i += kStatsThreads)
+            ll_store(pv.stats[i / cnt] + 2 * (size_t)pv.rank * cnt, i % cnt, W.stats[i % cnt], pv.iter);
     }
 }
 
@@ -424,10 +424,11 @@ MMG_DEVICE void final_stats(const Dims& d, const WsPtrs& W, const PeerView& pv, 
     }
     MMG_SYNCTHREADS();
     if (pv.world > 1) {
-        for (int i = tid; i < stats_count(d); i += kGemmThreads) pv.stats[pv.rank][i] = W.stats[i];
-        fence_system();
-        MMG_SYNCTHREADS();
-        if (tid < pv.world) peer_signal(pv.flags[tid] + pv.rank, pv.iter);
+        // PUSH as self-validating packets (ll_store): this rank's statistics go into slot `rank` of EVERY rank's symmetric statistics
+        // area; no flag and no fence, the consumers spin on the packets' tags in their own memory
+        const int cnt = stats_count(d);
+        for (int i = tid; i < cnt * pv.world; i += kGemmThreads)
+            ll_store(pv.stats[i / cnt] + 2 * (size_t)pv.rank * cnt, i % cnt, W.stats[i % cnt], pv.iter);
     } else {
         loss_coefs_store(d, cfg, W, kGemmThreads);
     }
@@ -508,13 +509,12 @@ MMG_DEVICE const double* loss_prologue(const Dims& d, const mmg_config& cfg, con
     const int tid = threadIdx.x;
     const double* st = W.stats;
     if (pv.world > 1) {
-        // global batch statistics = sum over ranks, read straight from the peers' symmetric slots (rank order)
+        // global batch statistics = sum over ranks (rank order) of the slots the peers pushed into THIS rank's memory
         double* st_s = reinterpret_cast<double*>(bas_scale + 4);
-        if (tid < pv.world && !peer_wait(pv.flags[pv.rank] + tid, pv.iter, pv.error)) *pv.error = 1;
-        MMG_SYNCTHREADS();
-        for (int i = tid; i < stats_count(d); i += kLossThreads) {
+        const int cnt = stats_count(d);
+        for (int i = tid; i < cnt; i += kLossThreads) {
             double v = 0.0;
-            for (int r = 0; r < pv.world; ++r) v += peer_load_d(pv.stats[r] + i);
+            for (int r = 0; r < pv.world; ++r) v += ll_load(pv.stats[pv.rank] + 2 * (size_t)r * cnt, i, pv.iter, pv.error);
             st_s[i] = v;
             if (blockIdx.x == 0) W.stats[i] = v;      // later kernels (K_update) read the global numbers from here
         }

@@ -86,23 +86,50 @@ MMG_DEVICE void flag_wait(const unsigned* counter, unsigned target) {
 }
 
 // ---- cross-GPU flags over peer-mapped memory (NVLink) ----------------------------------------------------------------
+// Protocol rule: everything a flag announces lives in the SIGNALLING rank's own memory (send buffer, reduced slice) and is
+// PULLED by the peers over NVLink, whose loads are served by the owner's L2 (the owner's point of coherence; peer addresses are
+// never cached in the reader's L2 and the readers bypass L1).  A device-scope fence therefore orders the data (at the owner's
+// L2) before the remote flag store leaves; the system-scope fence the first version used here cost 5-12 us per signal because it
+// also waits for every outstanding write to leave the GPU.  Small values that are PUSHED (statistics, slice norms) travel as
+// self-validating packets instead (ll_store / ll_load below): no flag, no fence.
 MMG_DEVICE void peer_signal(unsigned long long* remote_flag, unsigned long long value) {
-    __threadfence_system();                                   // this rank's prior writes are visible system-wide first
+    __threadfence();
     *reinterpret_cast<volatile unsigned long long*>(remote_flag) = value;
 }
 // Bounded wait (~15 s: ranks must run in lockstep within that window; a dead peer must not hang the GPU for good).  `err`
 // is the rank's sticky error word: once a wait has timed out every later wait gives up at once, the update kernels skip
 // their work and the host raises (GameEngine.peer_error()).
 MMG_DEVICE bool peer_wait(const unsigned long long* local_flag, unsigned long long target, const int* err) {
-    if (*reinterpret_cast<const volatile unsigned long long*>(local_flag) >= target) { __threadfence_system(); return true; }
+    if (*reinterpret_cast<const volatile unsigned long long*>(local_flag) >= target) { __threadfence(); return true; }
     if (*reinterpret_cast<const volatile int*>(err) != 0) return false;
     for (int spin = 0; spin < (1 << 26); ++spin) {
-        if (*reinterpret_cast<const volatile unsigned long long*>(local_flag) >= target) { __threadfence_system(); return true; }
+        if (*reinterpret_cast<const volatile unsigned long long*>(local_flag) >= target) { __threadfence(); return true; }
         __nanosleep(spin < 4096 ? 32 : 256);
     }
     return false;
 }
 MMG_DEVICE void fence_system() { __threadfence_system(); }
+// Self-validating packets for small pushed values (the LL idea of NCCL): a double travels as two 8-byte words
+// {float bits | tag << 32} (head and remainder, ~48 bits of mantissa), each written by ONE 8-byte store, which NVLink delivers
+// whole; the reader spins until both words carry the expected tag (the step number: monotonic, never 0, buffers start zeroed).
+MMG_DEVICE void ll_store(double* remote_area, int idx, double v, unsigned long long tag) {
+    const float hi = (float)v, lo = (float)(v - (double)hi);
+    volatile unsigned long long* q = reinterpret_cast<volatile unsigned long long*>(remote_area) + 2 * (size_t)idx;
+    q[0] = (unsigned long long)__float_as_uint(hi) | (tag << 32);
+    q[1] = (unsigned long long)__float_as_uint(lo) | (tag << 32);
+}
+MMG_DEVICE double ll_load(const double* local_area, int idx, unsigned long long tag, int* err) {
+    const volatile unsigned long long* q = reinterpret_cast<const volatile unsigned long long*>(local_area) + 2 * (size_t)idx;
+    const unsigned t32 = (unsigned)tag;
+    unsigned long long a = q[0], b = q[1];
+    for (int spin = 0; ((unsigned)(a >> 32) != t32 || (unsigned)(b >> 32) != t32) && spin < (1 << 26); ++spin) {
+        if (*reinterpret_cast<const volatile int*>(err) != 0) break;
+        __nanosleep(spin < 4096 ? 32 : 256);
+        a = q[0]; b = q[1];
+    }
+    if ((unsigned)(a >> 32) != t32 || (unsigned)(b >> 32) != t32) { *err = 4; return 0.0; }
+    return (double)__uint_as_float((unsigned)a) + (double)__uint_as_float((unsigned)b);
+}
 MMG_DEVICE float4 peer_load4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }   // L1 bypass
 MMG_DEVICE double peer_load_d(const double* p) { return __ldcg(p); }
 // L1-bypassing loads for data another CTA of the SAME grid has just written (split-K partial tiles)
@@ -172,9 +199,9 @@ MMG_DEVICE void cp_async16(void* smem_dst, const void* gmem_src) {
 MMG_DEVICE void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // Programmatic dependent launch: wait for the producer grid's memory to be visible / let dependents start.
 // -DMMG_TRACE (debug build only, scripts/trace.py): thread 0 of every CTA stamps the global nanosecond timer at a few points;
-// mmg_debug_trace copies the table out.  kid: 0 pre, 1 fwd, 2 baseline, 3 bwd, 4 wgrad, 5 update.
+// mmg_debug_trace copies the table out.  kid: 0 pre, 1 fwd, 2 baseline, 3 bwd, 4 wgrad, 5 update, 6 peer reduce-scatter.
 #ifdef MMG_TRACE
-__device__ unsigned long long g_trace[6][1024][8];
+__device__ unsigned long long g_trace[7][1024][8];
 #define MMG_TRACE_AT(kid, slot)                                                                  \
     do {                                                                                         \
         if (threadIdx.x == 0 && blockIdx.x < 1024) {                                             \
@@ -306,6 +333,8 @@ MMG_DEVICE void flag_wait(const unsigned* counter, unsigned target) {   // block
 MMG_DEVICE void peer_signal(unsigned long long* f, unsigned long long v) { __atomic_store_n(f, v, __ATOMIC_SEQ_CST); }
 MMG_DEVICE bool peer_wait(const unsigned long long* f, unsigned long long target, const int*) { return __atomic_load_n(f, __ATOMIC_SEQ_CST) >= target; }
 MMG_DEVICE void fence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+MMG_DEVICE void ll_store(double* area, int idx, double v, unsigned long long) { area[2 * (size_t)idx] = v; }
+MMG_DEVICE double ll_load(const double* area, int idx, unsigned long long, int*) { return area[2 * (size_t)idx]; }
 MMG_DEVICE float4 peer_load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 MMG_DEVICE double peer_load_d(const double* p) { return *p; }
 MMG_DEVICE float4 ld_cg4(const float* p) { return *reinterpret_cast<const float4*>(p); }

@@ -452,7 +452,6 @@ k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, co
     }
     MMG_TRACE_AT(4, 4);
     if (!fin) return;
-    if (pv.world > 1) fence_system();     // the tile lives in the symmetric send buffer: visible to the peers before it is counted
     // ---- finished output tile: its sum of squares; the CTA that finishes the LAST tile adds them up per module --------------
     const float tile_ss = block_sum_256(ss, red);
     if (tid == 0) {
@@ -466,6 +465,15 @@ k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, co
     MMG_TRACE_AT(4, 5);
     if (!s_flag) return;
     fence_acquire();
+    if (pv.world > 1) {
+        // data-parallel: `grads` is this rank's symmetric send buffer and it is complete: raise flag row 1 on every peer.  The
+        // per-module norms come out of the cross-rank sum, the loss values are added up by K_update: nothing else to do here.
+        if (tid == 0) *sy.done = 0;
+        MMG_SYNCTHREADS();
+        if (tid < pv.world) peer_signal(pv.flags[tid] + MMG_MAX_PEERS + pv.rank, pv.iter);      // device-scope fence inside: the data is local
+        MMG_TRACE_AT(4, 6);
+        return;
+    }
     {
         MMG_SHARED double dred[4][kGemmThreads / 32];
         double s4[4] = {0.0, 0.0, 0.0, 0.0};
@@ -486,12 +494,6 @@ k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, co
         // fused iteration: the backward kernel left per-CTA partials of the five loss values; they are added up here, off
         // every critical path (the values are only reported)
         if (n_loss_parts > 0) { MMG_SYNCTHREADS(); loss_finalize(d, W, n_loss_parts); }
-        if (pv.world > 1) {
-            // `grads` is this rank's symmetric send buffer and it is complete: raise flag row 1 on every peer
-            fence_system();
-            MMG_SYNCTHREADS();
-            if (tid < pv.world) peer_signal(pv.flags[tid] + MMG_MAX_PEERS + pv.rank, pv.iter);
-        }
     }
     MMG_TRACE_AT(4, 6);
 }
@@ -569,18 +571,21 @@ k_grad_norm(SegInfo seg, const float* grads, float* norm_part, unsigned* ticket,
     finish_norms(ss, norm_part, ticket, norm_final);
 }
 
-// Data-parallel gradient sum over NVLink peer memory, two-shot.  Rank r owns the r-th 1/G slice of the flat gradient:
-// it waits until every rank has published its send buffer, sums the slice over all send buffers (rank order => the result
-// is the same number whoever computes it), stores it into EVERY rank's receive buffer together with the slice's per-module
-// sums of squares, and raises flag row 2 on every rank.  Per rank and iteration: (G-1)/G of the gradient in over NVLink and
-// the same amount out, instead of (G-1) whole gradients in with a one-shot read.
+// Data-parallel gradient sum over NVLink peer memory, two-shot, PULL on both legs.  Rank r owns the r-th 1/G slice of the flat
+// gradient: it waits until every rank has published its send buffer, sums the slice over all send buffers (peer loads, rank
+// order => the result is the same number whoever computes it) into its OWN receive buffer, pushes only the slice's four
+// per-module sums of squares to every rank and raises flag row 2 everywhere; K_update then pulls each slice from its owner.
+// Per rank and iteration: (G-1)/G of the gradient in over NVLink on each leg, no bulk remote stores (a system-scope fence
+// behind bulk remote stores cost 5-12 us per CTA in the push variant, profiles/r02_trace_2gpu_push.txt).
 MMG_GLOBAL void __launch_bounds__(kUpdThreads)
 k_peer_reduce_scatter(SegInfo seg, PeerView pv, float* norm_part, unsigned* ticket, double* norm_scratch) {
     pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
     pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
     const int tid = threadIdx.x;
+    MMG_TRACE_AT(6, 0);
     if (tid < pv.world && !peer_wait(pv.flags[pv.rank] + MMG_MAX_PEERS + tid, pv.iter, pv.error)) *pv.error = 2;
     MMG_SYNCTHREADS();
+    MMG_TRACE_AT(6, 1);
     const long long n4 = seg.begin[4] / 4;
     const long long per = cdiv64(n4, pv.world);
     const long long lo = per * pv.rank, hi = min(n4, lo + per);
@@ -593,17 +598,17 @@ k_peer_reduce_scatter(SegInfo seg, PeerView pv, float* norm_part, unsigned* tick
             const float4 a = peer_load4(pv.send[r] + i);
             g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
         }
-        for (int r = 0; r < pv.world; ++r) *reinterpret_cast<float4*>(pv.recv[r] + i) = g;
+        *reinterpret_cast<float4*>(pv.recv[pv.rank] + i) = g;       // the owner keeps the slice: the peers PULL it in K_update
         ss[sg] = fmaf(g.x, g.x, ss[sg]); ss[sg] = fmaf(g.y, g.y, ss[sg]);
         ss[sg] = fmaf(g.z, g.z, ss[sg]); ss[sg] = fmaf(g.w, g.w, ss[sg]);
     }
-    fence_system();             // this CTA's remote stores are visible system-wide before it is counted as finished
+    MMG_TRACE_AT(6, 2);
     if (finish_norms(ss, norm_part, ticket, norm_scratch)) {
         // the whole slice is reduced and stored: publish its sums of squares and raise flag row 2 everywhere
-        if (tid < 4 * pv.world) pv.norms[tid >> 2][4 * pv.rank + (tid & 3)] = norm_scratch[tid & 3];
-        fence_system();
+        if (tid < 4 * pv.world) ll_store(pv.norms[tid >> 2], 4 * pv.rank + (tid & 3), norm_scratch[tid & 3], pv.iter);
         MMG_SYNCTHREADS();
         if (tid < pv.world) peer_signal(pv.flags[tid] + 2 * MMG_MAX_PEERS + pv.rank, pv.iter);
+        MMG_TRACE_AT(6, 4);
     }
 }
 
@@ -649,11 +654,12 @@ MMG_DEVICE void update_body(const SegInfo& seg, const OptHyper& hp, float* param
     if (pv.world > 1) {
         if (tid < pv.world && !peer_wait(pv.flags[pv.rank] + 2 * MMG_MAX_PEERS + tid, pv.iter, pv.error)) *pv.error = 3;
         MMG_SYNCTHREADS();
+        MMG_TRACE_AT(5, 1);
         if (tid == 0) s_err = *reinterpret_cast<volatile int*>(pv.error);
     }
     if (tid < 4) {   // global L2 norm per module
         double v = 0.0;
-        if (pv.world > 1) for (int r = 0; r < pv.world; ++r) v += peer_load_d(pv.norms[pv.rank] + 4 * r + tid);
+        if (pv.world > 1) for (int r = 0; r < pv.world; ++r) v += ll_load(pv.norms[pv.rank], 4 * r + tid, pv.iter, pv.error);
         else if (norm_tiles > 0) {
             for (int w = 0; w < kUpdThreads / 32; ++w) v += tsum[tid][w];
             if (blockIdx.x == 0) norm_final[tid] = v;
@@ -683,7 +689,11 @@ MMG_DEVICE void update_body(const SegInfo& seg, const OptHyper& hp, float* param
         const bool in_whead = i >= seg.whead_begin && i < seg.whead_end;
         if (in_whead && !whead_active) continue;
         if (i >= seg.shead_begin && i < seg.shead_end && !seg.shead_active) continue;
-        float4 g4 = *reinterpret_cast<const float4*>(grads_in + i);
+        float4 g4;
+        if (pv.world > 1) {       // the reduced slice lives in its owner's receive buffer (NVLink peer load, L1 bypass)
+            const long long per4 = cdiv64(total / 4, pv.world) * 4;
+            g4 = peer_load4(pv.recv[(int)(i / per4)] + i);
+        } else g4 = *reinterpret_cast<const float4*>(grads_in + i);
         float4 p4 = *reinterpret_cast<const float4*>(params + i);
         const float cf = coef[sg];
         float g[4] = {g4.x * cf, g4.y * cf, g4.z * cf, g4.w * cf};

@@ -16,7 +16,7 @@ import torch
 import bench
 import __graft_entry__ as ge
 
-NAMES = ["k_pre", "k_exchange_fwd", "k_baseline_fwd", "k_exchange_bwd", "k_wgrad", "k_update"]
+NAMES = ["k_pre", "k_exchange_fwd", "k_baseline_fwd", "k_exchange_bwd", "k_wgrad", "k_update", "k_peer_reduce_scatter"]
 
 
 def build_trace_lib():
@@ -39,18 +39,27 @@ def main():
         return
     from multimodalgame_b200 import capi, engine as eng, synthetic as syn
     lib = capi.Library(path)
-    dev = torch.device("cuda", 0)
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     fl = syn.GameFlags(**bench.CONFIGS[args.config])
     words = syn.desc_set(fl, seed=0)
-    e = eng.GameEngine(syn.config_from_flags(fl, n_words=int(words["desc_set"].shape[0]) if words else 0), device=dev, lib=lib, seed=1)
+    B = fl.batch_size
+    e = eng.GameEngine(syn.config_from_flags(fl, batch_global=B * world, batch_offset=rank * B,
+                                             n_words=int(words["desc_set"].shape[0]) if words else 0), device=dev, lib=lib, seed=1)
     e.load_params(syn.init_params(fl, seed=0))
+    if world > 1:       # torchrun: the NVLink peer-memory data-parallel iteration, rank 0 prints its timeline
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        e.enable_peer_dp()
+        e.train_step = lambda x, d, t: e.train_step_peer(x, d, t)
     if words:
         e.set_desc_set(**words)
-    batches = [syn.batch(fl, seed=i) for i in range(4)]
+    batches = [syn.batch(fl, seed=10 * rank + i) for i in range(4)]
     desc = batches[0][1].to(dev)
     xs = [b[0].to(dev) for b in batches]
     ts = [b[2].to(dev) for b in batches]
-    buf = np.zeros(6 * 1024 * 8, dtype=np.uint64)
+    buf = np.zeros(7 * 1024 * 8, dtype=np.uint64)
     for i in range(30):
         e.train_step(xs[i % 4], desc, ts[i % 4])
     lib.dll.mmg_debug_trace(buf.ctypes.data_as(C.c_void_p), buf.size)
@@ -58,10 +67,12 @@ def main():
         e.train_step(xs[rep % 4], desc, ts[rep % 4])
         n = lib.dll.mmg_debug_trace(buf.ctypes.data_as(C.c_void_p), buf.size)
         assert n == buf.size, "not a -DMMG_TRACE build"
-        tr = buf.reshape(6, 1024, 8).astype(np.float64)
+        tr = buf.reshape(7, 1024, 8).astype(np.float64)
         t0 = tr[tr > 0].min()
+        if rank != 0:
+            continue
         print("== iteration %d (us relative to the first stamp)" % rep)
-        for k in range(6):
+        for k in range(7):
             tk = tr[k]
             used = (tk > 0).any(1)
             if not used.any():

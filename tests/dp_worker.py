@@ -2,8 +2,8 @@
 
 Every rank drives its batch shard through the NVLink peer-memory iteration (mmg_train_step_peer) and, on a second engine,
 through the NCCL all-reduce variant; rank 0 runs the single-process GLOBAL-batch CPU oracle.  Checked per iteration:
-no peer wait timed out, the parameter replicas are bit-identical across ranks, peer == NCCL (bit for bit with 2 ranks, where
-a + b is order-free; within the optimizer's step size otherwise), and both == oracle.
+no peer wait timed out, the parameter replicas are bit-identical across ranks, peer == NCCL (within 0.25 lr with 2 ranks: the two
+paths sum the batch statistics in different orders since the fused two-level statistics; within the optimizer step size otherwise), and both == oracle.
 
     torchrun --nproc-per-node N tests/dp_worker.py [small] [C4] [C5]
 
@@ -73,7 +73,7 @@ def compare(name, it, e_peer, e_nccl, oparams, lr, extra_ok=True):
     ref = e_peer.params.clone()
     dist.broadcast(ref, 0)
     rep = torch.equal(ref, e_peer.params)                    # replicas must agree bit for bit across ranks
-    good = (err == 0 and rep and dmax <= (1e-7 if world <= 2 else 12 * lr) and worst < 3e-3 * lr * (it + 1) + 12 * lr and extra_ok)
+    good = (err == 0 and rep and dmax <= (0.25 * lr if world <= 2 else 12 * lr) and worst < 3e-3 * lr * (it + 1) + 12 * lr and extra_ok)
     ok = ok and good
     say("%s it%d: peer_error=%d replicas_identical=%s peer==nccl bitwise=%s (max diff %.2e) max|param - oracle|=%.3e -> %s" % (
         name, it, err, rep, same, dmax, worst, "ok" if good else "BAD"))
