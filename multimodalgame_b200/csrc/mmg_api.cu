@@ -1138,6 +1138,7 @@ int mmg_train_step_peer(const mmg_config* cfg, float* d_params, float* d_grads, 
     const SegInfo seg = seg_info(L, d);
     cudaStream_t st = (cudaStream_t)stream;
     // two-shot sum: this rank reduces its 1/G slice of all send buffers into its own receive buffer (+ the slice's norms to all) ...
+    // one float4 per thread: every load of the slice is in flight at once
     MMG_LAUNCH(k_peer_reduce_scatter, upd_ctas(cdiv64(L.total, pv.world)), kUpdThreads, 0, st, seg, pv, W.norm_part, W.tickets + 6,
                W.norm_final);
     if ((rc = check_cuda("k_peer_reduce_scatter"))) return rc;

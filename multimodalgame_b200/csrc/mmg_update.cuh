@@ -593,11 +593,13 @@ k_peer_reduce_scatter(SegInfo seg, PeerView pv, float* norm_part, unsigned* tick
     for (long long q = lo + (long long)blockIdx.x * kUpdThreads + tid; q < hi; q += (long long)gridDim.x * kUpdThreads) {
         const long long i = 4 * q;
         const int sg = seg_of(seg.begin, i);
-        float4 g = peer_load4(pv.send[0] + i);
-        for (int r = 1; r < pv.world; ++r) {
-            const float4 a = peer_load4(pv.send[r] + i);
-            g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
-        }
+        // every rank's share of this float4 in flight at once (one NVLink round trip, not one per rank), added in rank order
+        float4 sh[MMG_MAX_PEERS];
+#pragma unroll
+        for (int r = 0; r < MMG_MAX_PEERS; ++r) sh[r] = r < pv.world ? peer_load4(pv.send[r] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 g = sh[0];
+#pragma unroll
+        for (int r = 1; r < MMG_MAX_PEERS; ++r) if (r < pv.world) { g.x += sh[r].x; g.y += sh[r].y; g.z += sh[r].z; g.w += sh[r].w; }
         *reinterpret_cast<float4*>(pv.recv[pv.rank] + i) = g;       // the owner keeps the slice: the peers PULL it in K_update
         ss[sg] = fmaf(g.x, g.x, ss[sg]); ss[sg] = fmaf(g.y, g.y, ss[sg]);
         ss[sg] = fmaf(g.z, g.z, ss[sg]); ss[sg] = fmaf(g.w, g.w, ss[sg]);

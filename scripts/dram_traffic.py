@@ -1,12 +1,13 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv` launch list of
 `bench.py` into per-iteration DRAM traffic and per-kernel averages (profiles/*_dram_traffic.json).
-usage: python scripts/dram_traffic.py <launches.csv> <config description> > profiles/rNN_dram_traffic.json"""
+usage: python scripts/dram_traffic.py <launches.csv> <config description> [<protocol note>] > profiles/rNN_dram_traffic.json"""
 import collections
 import csv
 import json
 import sys
 
 path, desc = sys.argv[1], sys.argv[2]
+protocol = sys.argv[3] if len(sys.argv) > 3 else None
 rows = [r for r in csv.reader(open(path)) if len(r) > 14 and r[0].isdigit() and "mmg::" in r[4]]
 per = collections.OrderedDict()
 for r in rows:
@@ -28,4 +29,6 @@ for k, v in per.items():
     tot_r += rd; tot_w += wr; tot_t += t
 out["per_iteration"] = {"dram_read_bytes": tot_r, "dram_write_bytes": tot_w, "total_bytes": tot_r + tot_w,
                         "kernel_time_us_ncu": round(tot_t, 1)}
+if protocol:
+    out["protocol"] = protocol
 print(json.dumps(out, indent=1))
