@@ -290,18 +290,20 @@ int mmg_train_step_staged(const mmg_config* cfg, float* d_params, float* d_grads
  * New capability (the reference is single-process).  Each rank owns one SYMMETRIC buffer (peer-mapped on every other
  * rank, e.g. torch.distributed._symmetric_memory) holding, in this order:
  *   send   : float[param_layout.total]      this rank's local gradient, read by every peer
- *   recv   : float[param_layout.total]      the GLOBAL gradient: slice r is written here by rank r (two-shot reduction)
- *   stats  : double[workspace.stats_count]  this rank's batch statistics, read by every peer
- *   norms  : double[MMG_MAX_PEERS][4]       per-module sums of squares of slice r of the global gradient, written by rank r
- *   flags  : uint64[3][MMG_MAX_PEERS]       arrival counters written REMOTELY by the peers (row 0: statistics published,
- *                                           row 1: send buffer published, row 2: reduced slice stored); value = training
- *                                           step, monotonic
- * No collective library call sits on the path: the producing kernels publish with a system-scope fence + remote flag store,
- * the consuming kernels spin on their LOCAL flag row and then read the peers' buffers directly (rank order, so every rank
- * computes bit-identical sums).  Gradient: rank r sums ITS 1/G slice over all send buffers and stores the result into every
- * rank's recv buffer — (G-1)/G of a gradient in and out per rank over NVLink.  Waits are bounded (~15 s: ranks must run in
+ *   recv   : float[param_layout.total]      slice `rank` of the GLOBAL gradient, reduced HERE by this rank and PULLED by the peers
+ *   stats  : packets[MMG_MAX_PEERS][2 * workspace.stats_count]   slot r = rank r's batch statistics, PUSHED by rank r
+ *   norms  : packets[MMG_MAX_PEERS][2 * 4]  slot r = per-module sums of squares of slice r of the global gradient, PUSHED by rank r
+ *   flags  : uint64[3][MMG_MAX_PEERS]       arrival counters written REMOTELY by the peers (row 1: send buffer complete,
+ *                                           row 2: reduced slice stored; row 0 unused); value = training step, monotonic
+ * A packet is one 8-byte word {float bits | step << 32}; a double travels as two (head, remainder) and is valid once both carry
+ * the current step, so pushed values need neither a flag nor a fence.  Bulk data is only written to the writer's OWN memory and
+ * pulled by the peers behind a device-scope fence + remote flag store (the peers' loads are served by the owner's L2).
+ * No collective library call sits on the path; every sum runs in rank order, so every rank computes bit-identical numbers.
+ * Gradient: rank r sums ITS 1/G slice over all send buffers into its recv buffer; the update kernel of every rank pulls each slice
+ * from its owner — (G-1)/G of a gradient over NVLink on each leg.  Waits are bounded (~15 s: ranks must run in
  * lockstep within that window); a timeout sets *d_error, which is STICKY: later waits give up at once and the update kernel
- * leaves parameters and optimizer state untouched, so the caller must poll it (GameEngine.peer_error()) and abort. */
+ * leaves parameters and optimizer state untouched, so the caller must poll it (GameEngine.peer_error()) and abort.
+ * The buffer must start zeroed. */
 #define MMG_MAX_PEERS 8
 typedef struct mmg_peers {
     int32_t world, rank;

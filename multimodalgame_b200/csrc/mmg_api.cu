@@ -511,7 +511,7 @@ static int launch_fwd_fast(const Dims& d, const WsPtrs& W, const ExchangeInputs&
 }
 template <int M, bool FUSE>
 static int launch_bwd_fast_m(const Dims& d, const WsPtrs& W, const float* bin_w, const float* code_w, const Plan& pl,
-                             cudaStream_t st, const mmg_config& cfg, const PeerView& pv) {
+                             cudaStream_t st, const mmg_config& cfg, const PeerView& pv, const float* bs_w2) {
     const int loss_off = (pl.bwd_smem_bytes + 15) / 16 * 4;          // floats; the coefficient scratch follows the state
     const int smem = FUSE ? loss_off * 4 + loss_smem_bytes(d, pv.world) : pl.bwd_smem_bytes;
     if (smem > kMaxSmem) return fail(MMG_ERR_UNSUPPORTED, "fused backward: %d bytes of shared memory", smem);
@@ -519,7 +519,7 @@ static int launch_bwd_fast_m(const Dims& d, const WsPtrs& W, const float* bin_w,
     int rc = set_smem(k_exchange_bwd_fast_, smem);
     if (rc) return rc;
     const int n_rec = d.B, n_sen = d.use_binary ? d.B : 0;
-    MMG_LAUNCH(k_exchange_bwd_fast_, n_rec + n_sen, kFastBwdThreads, smem, st, d, W, bin_w, code_w, n_rec, cfg, pv, loss_off);
+    MMG_LAUNCH(k_exchange_bwd_fast_, n_rec + n_sen, kFastBwdThreads, smem, st, d, W, bin_w, code_w, n_rec, cfg, pv, loss_off, bs_w2);
     return check_cuda("k_exchange_bwd_fast");
 }
 
@@ -607,9 +607,11 @@ static int build_wgrad_table(const Dims& d, const mmg_param_layout& L, const Par
         bw.mod = d.NW;                                       // row (cta, n) -> desc_set[n]
         b.add(km(W.ddd_part, align4(d.A)), bw, d.A, d.WV, d.NW, MMG_P_REC_DD_W, 0, MMG_P_REC_DD_B);   // slab 0 = sum over CTAs (K_attn_reduce)
     } else {
-        Operand bd = km(in.desc, d.WV);
-        bd.mod = d.D;                                        // row (b, d) -> desc[d]
-        b.add(km(W.dy1, Hr), bd, Hr, d.WV, B * d.D, MMG_P_REC_Y1_W, d.y1_dcol, MMG_P_REC_Y1_B);
+        // rows (b, d) of dy1 meet the same description row for every example: sum over the examples while staging (K = D instead
+        // of B * D: one K-slice per tile, no split-K round trip for what was the longest reduction of the launch)
+        Operand ad = km(W.dy1, Hr);
+        ad.kind = OP_BSUM; ad.mod = B; ad.ld2 = d.D;
+        b.add(ad, km(in.desc, d.WV), Hr, d.WV, d.D, MMG_P_REC_Y1_W, d.y1_dcol, MMG_P_REC_Y1_B);
     }
     b.add(km(W.dw2p, Hr), ones(), Hr, 1, B, MMG_P_REC_Y2_W, 0, -1);          // y2.weight (1, Hr): sum over examples
     b.add(km(W.g_outp, 1), ones(), 1, 1, B * d.D, MMG_P_REC_Y2_B, 0, -1);
@@ -628,9 +630,11 @@ static int build_wgrad_table(const Dims& d, const mmg_param_layout& L, const Par
             a.kind = OP_RELUGRAD; a.g = W.g_bs; a.w2 = P.p[MMG_P_BS_L2_W];
             if (fast_bs) {
                 // h_x is shared by the T rows of an example: sum the relu-gradient over t first (K = B instead of T*B),
-                // the z_r columns keep the full row range
+                // the z_r columns keep the full row range.  The fast backward kernel has already left the t-summed matrix S (B, Hb)
+                // in the U[b] array (a plain operand); behind the generic backward kernel the sum is formed while staging.
                 Operand at = a;
                 at.kind = OP_RELUGRAD_TSUM; at.mod = d.T; at.ld2 = B;
+                if (fast) at = km(W.ubs, d.Hb);
                 b.add(at, km(W.h_x, Hi), d.Hb, Hi, B, MMG_P_BS_L1_W, 0, MMG_P_BS_L1_B);
                 b.add(a, km(W.rec_feats, M), d.Hb, M, R, MMG_P_BS_L1_W, Hi, -1);
             } else {
@@ -962,8 +966,9 @@ static int backward_impl(const mmg_config* cfg, const float* d_params, const mmg
     const AttnArgs aa = attn_args(d, P, ei, pl);
     if (pl.fast) {
         const float *bw = P.p[MMG_P_SEN_BIN_W], *cw = P.p[MMG_P_SEN_CODE_W];
-        if (fuse_loss) rc = d.M == 32 ? launch_bwd_fast_m<32, true>(d, W, bw, cw, pl, st, *cfg, pv) : launch_bwd_fast_m<64, true>(d, W, bw, cw, pl, st, *cfg, pv);
-        else           rc = d.M == 32 ? launch_bwd_fast_m<32, false>(d, W, bw, cw, pl, st, *cfg, pv) : launch_bwd_fast_m<64, false>(d, W, bw, cw, pl, st, *cfg, pv);
+        const float* w2 = P.p[MMG_P_BS_L2_W];
+        if (fuse_loss) rc = d.M == 32 ? launch_bwd_fast_m<32, true>(d, W, bw, cw, pl, st, *cfg, pv, w2) : launch_bwd_fast_m<64, true>(d, W, bw, cw, pl, st, *cfg, pv, w2);
+        else           rc = d.M == 32 ? launch_bwd_fast_m<32, false>(d, W, bw, cw, pl, st, *cfg, pv, w2) : launch_bwd_fast_m<64, false>(d, W, bw, cw, pl, st, *cfg, pv, w2);
     }
     else switch (pl.BT) {
         case 1: rc = launch_bwd<1>(d, W, pl, st, aa); break;
@@ -1032,7 +1037,7 @@ static int clip_update_impl(const mmg_config* cfg, float* d_params, float* d_gra
     const SegInfo seg = seg_info(L, d);
     OptHyper hp;
     hp.optim = cfg->optim_type; hp.lr = cfg->learning_rate; hp.max_norm = cfg->max_norm; hp.step = step;
-    MMG_LAUNCH(k_update, upd_ctas(L.total), kUpdThreads, 0, (cudaStream_t)stream, seg, hp, d_params, (const float*)d_grads, d_grads,
+    MMG_LAUNCH(k_update, upd_ctas(L.total) + (loss_parts > 0 ? 1 : 0), kUpdThreads, 0, (cudaStream_t)stream, seg, hp, d_params, (const float*)d_grads, d_grads,
                d_state1, d_state2, W.norm_final, W.grad_norms, (const double*)W.stats,
                (const long long*)W.opt_counters, no_peers(), (const float*)W.tile_norm, norm_tiles, loss_parts, d, W);
     return check_cuda("k_update");
@@ -1145,7 +1150,7 @@ int mmg_train_step_peer(const mmg_config* cfg, float* d_params, float* d_grads, 
     // ... and the update waits for all slices (flag row 2), then clips and steps, pulling every slice from its owner
     OptHyper hp;
     hp.optim = cfg->optim_type; hp.lr = cfg->learning_rate; hp.max_norm = cfg->max_norm; hp.step = step;
-    MMG_LAUNCH(k_update, upd_ctas(L.total), kUpdThreads, 0, st, seg, hp, d_params, (const float*)pv.recv[pv.rank], d_grads, d_state1,
+    MMG_LAUNCH(k_update, upd_ctas(L.total) + (loss_parts > 0 ? 1 : 0), kUpdThreads, 0, st, seg, hp, d_params, (const float*)pv.recv[pv.rank], d_grads, d_state1,
                d_state2, W.norm_final, W.grad_norms, (const double*)W.stats, (const long long*)W.opt_counters, pv,
                (const float*)W.tile_norm, 0, loss_parts, d, W);
     return check_cuda("k_update");

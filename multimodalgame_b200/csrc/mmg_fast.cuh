@@ -848,7 +848,7 @@ MMG_HOST_DEVICE int fast_bwd_rec_state_floats(int T, int M, int D) {
     // dlw (T,M) | dhw (T,64) | inj (T,64) | gat (T,5,64) | hws, y1hs (T,64 each) | dgh (2,192) | gv (64) | gout (DP) | dls (T) | barrier
     return T * (M + 4) + 2 * T * (kFastHr + 4) + 5 * T * kFastHr + 2 * T * kFastHr + 4 * T * kFastHr + 2 * 3 * kFastHr + kFastHr + align4(D) + align4(T) + 8;
 }
-MMG_HOST_DEVICE int fast_bwd_sen_state_floats(int T, int M) { return T * M + 2 * kFastHi + T * kFastHi + 8; }
+MMG_HOST_DEVICE int fast_bwd_sen_state_floats(int T, int M) { return T * M + 2 * kFastHi + T * kFastHi + align4(T) + 8; }
 
 // Loss coefficients for the fused backward: single rank -> the table K_baseline_fwd's last CTA derived (one load per thread);
 // with peers -> the full prologue (wait for the peers' statistics, sum them in rank order, derive the coefficients).
@@ -869,7 +869,7 @@ MMG_DEVICE void fused_loss_coefs(const Dims& d, const mmg_config& cfg, const WsP
 template <int M, bool kFuse>
 MMG_GLOBAL void __launch_bounds__(kFastBwdThreads, 1)
 k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, int n_rec_ctas, mmg_config cfg, PeerView pv,
-                    int loss_off) {
+                    int loss_off, const float* bs_w2) {
     constexpr int HI = kFastHi, HR = kFastHr, NT = kFastBwdThreads, M4 = M / 4;
     MMG_DYN_SMEM(smem_raw);
     float* sm = reinterpret_cast<float*>(smem_raw);
@@ -893,6 +893,7 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
         float* das0 = sm + T * M;                                     // (256) d a at t = 0
         float* cred = das0 + HI;                                      // (256 / M, M) partial sums
         float* as_s = cred + HI;                                      // (T, 256) saved tanh outputs of this example
+        float* gbs_s = as_s + T * HI;                                 // (T) d loss / d bs[t, b]
 #pragma unroll 4
         for (int t = 0; t < T; ++t) as_s[t * HI + n] = W.a_s[((size_t)t * B + b) * HI + n];
         for (int idx = tid; idx < T * M; idx += NT) {
@@ -914,9 +915,10 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
                     g = binary_grad(p, f, (lg - bsv) * c0.cA, c0.cE);
                     if (j == 0) lacc[4] += (double)(bsv - lg) * (double)(bsv - lg) * bas_scale[0];
                 }
-                if (j == 0) W.g_bs[row] = m_in ? 2.f * (bsv - lg) * bas_scale[0] : 0.f;     // model.py:971-988
+                if (j == 0) { const float gb = m_in ? 2.f * (bsv - lg) * bas_scale[0] : 0.f; W.g_bs[row] = gb; gbs_s[t] = gb; }   // model.py:971-988
             } else {
                 g = W.g_sen_probs[i];
+                if (j == 0) gbs_s[t] = W.g_bs[(size_t)t * B + b];
             }
             const float dl = g * p * (1.f - p);                       // through the sigmoid (model.py:223)
             W.d_lz[i] = dl;
@@ -964,6 +966,22 @@ k_exchange_bwd_fast(Dims d, WsPtrs W, const float* bin_w, const float* code_w, i
 #pragma unroll
             for (int p = 0; p < NT / M; ++p) v += cred[p * M + tid];
             W.dcode_part[(size_t)b * M + tid] = v;
+        }
+        // t-summed relu gradient of the sender-side baseline's hidden layer for this example:
+        //   S[b][n] = linear2.weight[n] * sum_t g_bs[t, b] * (h1s[t, b, n] > 0)
+        // h_x is shared by the T rows of an example, so the h_x half of d linear1.weight is S^T . h_x with K = B (and the bias
+        // gradient its column sum).  Done HERE, on CTAs that are idle while the receiver CTAs walk the BPTT chain, so that K_wgrad
+        // stages a plain matrix (the array U[b] of the forward pass is free by now and has the right shape).
+        for (int n2 = tid; n2 < d.Hb; n2 += NT) {
+            float acc = 0.f;
+            for (int t0 = 0; t0 < T; t0 += 8) {           // 8 steps' loads in flight, added in step order
+                float hv8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) hv8[u] = t0 + u < T ? ldg(W.h1s + ((size_t)(t0 + u) * B + b) * d.Hb + n2) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if (t0 + u < T && hv8[u] > 0.f) acc += gbs_s[t0 + u];
+            }
+            W.ubs[(size_t)b * d.Hb + n2] = acc * ldg(bs_w2 + n2);
         }
         if constexpr (kFuse) loss_partials(W, lacc);     // this CTA's share of the loss values (summed by K_wgrad's last CTA)
         MMG_BSTAMP(3);

@@ -12,7 +12,7 @@ namespace mmg {
 
 enum { kTile = 64, kChunk = 16, kLd = kTile + 4, kGemmThreads = 256 };
 enum { kGemmSmemFloats = 4 * kChunk * kLd };     // [buffer 0/1][A, B][kChunk][kLd]
-enum { OP_PLAIN = 0, OP_RELUGRAD = 1, OP_ONES = 2, OP_RELUGRAD_TSUM = 4 };
+enum { OP_PLAIN = 0, OP_RELUGRAD = 1, OP_ONES = 2, OP_RELUGRAD_TSUM = 4, OP_BSUM = 8 };
 
 // Operand descriptor.  Element (k, i): k = reduction index, i = output index (row of C for A, column for B).
 struct Operand {
@@ -28,10 +28,16 @@ struct Operand {
                         //                         : (k >= split -> p2[i * ld2 + k - split]); 0 = none
     int kind;           // OP_PLAIN; OP_RELUGRAD: (p > 0) ? g[k] * w2[i] : 0; OP_ONES: 1 (column sums as a GEMM);
                         // OP_RELUGRAD_TSUM (k-major, k = example): w2[i] * sum_{t < mod} g[t * ld2 + k] * (p[(t * ld2 + k) * ld + i] > 0)
+                        // OP_BSUM (k-major, k = class): sum_{b < mod} p[(b * ld2 + k) * ld + i]   (rows (example, class) summed over the examples)
 };
 
 MMG_DEVICE float operand_load(const Operand& op, int k, int i) {
     if (op.kind == OP_ONES) return 1.f;
+    if (op.kind == OP_BSUM) {
+        float v = 0.f;
+        for (int b = 0; b < op.mod; ++b) v += ldg(op.p + ((size_t)b * op.ld2 + k) * op.ld + i);
+        return v;
+    }
     if (op.kind == OP_RELUGRAD_TSUM) {
         float v = 0.f;
         for (int t = 0; t < op.mod; ++t)
@@ -68,6 +74,7 @@ MMG_DEVICE bool aligned16(const void* p) { return (((size_t)p) & 15) == 0; }
 MMG_DEVICE int operand_mode(const Operand& op, int k0) {
     if (op.kind == OP_ONES) return 0;
     if (op.kind == OP_RELUGRAD_TSUM) return ((op.ld & 3) == 0 && aligned16(op.p) && aligned16(op.w2)) ? 2 : 0;
+    if (op.kind == OP_BSUM) return 0;
     const bool ok2 = op.p2 == nullptr || op.split == 0 || ((op.split & 3) == 0 && (op.ld2 & 3) == 0 && aligned16(op.p2));
     if ((op.ld & 3) != 0 || !aligned16(op.p) || !ok2) return op.kmajor ? 0 : 1;
     if (op.kmajor) {

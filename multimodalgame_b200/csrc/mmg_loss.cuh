@@ -358,8 +358,10 @@ MMG_DEVICE void loss_coefs_store(const Dims& d, const mmg_config& cfg, const WsP
 // Level 1, by the last of the 2 * ntb CTAs that finish row tile `mt`: baseline scores of its 64 rows (per-tile partial dots added
 // in tile order) and the rows' share of the 12 per-step sums -> loss_part[mt][12] (double; the array is free until the backward).
 MMG_DEVICE void row_tile_stats(const Dims& d, const ParamPtrs& P, const WsPtrs& W, int mt) {
-    MMG_SHARED double red[12][2];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // compact on purpose: this runs once per row tile, and straight-line code executes at instruction-fetch speed (12 unrolled
+    // double-precision shuffle trees were ~400 instructions); the 64 rows meet in shared memory and 12 threads add them in row order
+    MMG_SHARED double red[12][kTile + 1];
+    const int tid = threadIdx.x;
     if (tid < kTile) {
         const int r = mt * kTile + tid;
         const int t = r / d.B, b = r - t * d.B;
@@ -379,22 +381,20 @@ MMG_DEVICE void row_tile_stats(const Dims& d, const ParamPtrs& P, const WsPtrs& 
         const float lg = W.logs[b];
         const bool m_in = mask_at(d, W, t, b) != 0, m_out = mask_at(d, W, t + 1, b) != 0;
         const double ws = (double)(lg - s), wr = (double)(lg - q);
-        double v[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};     // n0 a0 c0 | n1 a1 c1 | n2 a2 c2 | er2 es2 nm  (see stats_body)
-        if (m_in) {
-            v[0] = 1.0; v[1] = ws; v[2] = ws * ws;
-            if (!d.fixed) { v[6] = 1.0; v[7] = wr; v[8] = wr * wr; }
-            v[9] = wr * wr; v[10] = ws * ws;
-        }
-        if (m_out && t < d.T - 1) { v[3] = 1.0; v[4] = wr; v[5] = wr * wr; }
-        if (d.fixed || m_out) v[11] = 1.0;
-#pragma unroll
-        for (int i = 0; i < 12; ++i) {
-            const double sum = warp_sum_d(v[i]);
-            if (lane == 0) red[i][warp] = sum;
-        }
+        const double on_in = m_in ? 1.0 : 0.0, on_rec = (m_out && t < d.T - 1) ? 1.0 : 0.0, on_s = (m_in && !d.fixed) ? 1.0 : 0.0;
+        // n0 a0 c0 | n1 a1 c1 | n2 a2 c2 | er2 es2 nm  (see stats_body)
+        red[0][tid] = on_in;  red[1][tid] = on_in * ws;   red[2][tid] = on_in * ws * ws;
+        red[3][tid] = on_rec; red[4][tid] = on_rec * wr;  red[5][tid] = on_rec * wr * wr;
+        red[6][tid] = on_s;   red[7][tid] = on_s * wr;    red[8][tid] = on_s * wr * wr;
+        red[9][tid] = on_in * wr * wr; red[10][tid] = on_in * ws * ws; red[11][tid] = (d.fixed || m_out) ? 1.0 : 0.0;
     }
     MMG_SYNCTHREADS();
-    if (tid < 12) W.loss_part[(size_t)mt * 12 + tid] = red[tid][0] + red[tid][1];
+    if (tid < 12) {
+        double sum = 0.0;
+#pragma unroll 4
+        for (int i = 0; i < kTile; ++i) sum += red[tid][i];
+        W.loss_part[(size_t)mt * 12 + tid] = sum;
+    }
 }
 
 // Level 2, by the last row tile to finish: per step, the row tiles' shares added in tile order; the batch sums of the
@@ -564,7 +564,10 @@ MMG_DEVICE void loss_partials(const WsPtrs& W, const double (&acc)[5]) {
 
 // The loss values from `nparts` per-CTA partials (added in CTA order: deterministic) and the global statistics in W.stats;
 // one CTA of 256 threads, after every partial is visible.
-MMG_DEVICE void loss_finalize(const Dims& d, const WsPtrs& W, int nparts) {
+// `bump_counter`: count this iteration in the receiver message head's own update counter (torch.optim.Adam keeps one step count
+// per parameter, and that head only steps when it received a gradient).  False when an earlier kernel of the fused sequence has
+// already done it (K_wgrad), so that K_update reads a value nobody writes while it runs.
+MMG_DEVICE void loss_finalize(const Dims& d, const WsPtrs& W, int nparts, bool bump_counter = true) {
     MMG_SHARED double red[5][kLossThreads / 32];
     MMG_SHARED double nll_red[kLossThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -604,7 +607,7 @@ MMG_DEVICE void loss_finalize(const Dims& d, const WsPtrs& W, int nparts) {
         int tp = d.T;
         if (!d.fixed) for (int t = 0; t < d.T; ++t) if (st[stat_bas(d, t, 2)] <= 0.0) { tp = t + 1; break; }
         L[MMG_LOSS_ACTIVE_STEPS] = (float)tp;
-        if (st[stat_idx(d, 1, 0, 0)] > 0.0) W.opt_counters[0] += 1;   // updates seen by the receiver message head
+        if (bump_counter && st[stat_idx(d, 1, 0, 0)] > 0.0) W.opt_counters[0] += 1;   // updates seen by the receiver message head
         for (int i = MMG_LOSS_ACTIVE_STEPS + 1; i < MMG_LOSS_COUNT; ++i) L[i] = 0.f;
     }
 }

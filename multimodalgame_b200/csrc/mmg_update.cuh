@@ -64,7 +64,19 @@ MMG_DEVICE void wg_stage(const Operand& op, int k0, int k1, int i0, int ilim, fl
         float* dst = S + kk * kWgLd + 4 * g;
         if (k >= k1 || i >= ilim) { *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
         if (vec && i + 3 < ilim) {
-            if (op.kind == OP_RELUGRAD_TSUM) {
+            if (op.kind == OP_BSUM) {
+                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int b0 = 0; b0 < op.mod; b0 += 8) {        // 8 examples' rows in flight at once, added in example order
+                    float4 h[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        h[u] = b0 + u < op.mod ? ldg4(reinterpret_cast<const float4*>(op.p + ((size_t)(b0 + u) * op.ld2 + k) * op.ld + i))
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { r.x += h[u].x; r.y += h[u].y; r.z += h[u].z; r.w += h[u].w; }
+                }
+                *reinterpret_cast<float4*>(dst) = r;
+            } else if (op.kind == OP_RELUGRAD_TSUM) {
                 float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int t0 = 0; t0 < op.mod; t0 += 8) {        // 8 steps' loads in flight at once, summed in step order
                     float4 h[8];
@@ -142,6 +154,11 @@ k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, co
     pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
     pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
     MMG_TRACE_AT(4, 0);
+    // fused iteration: the loss values are added up beside K_update (its extra CTA); the receiver message head's update counter is
+    // advanced HERE, one kernel earlier, so that K_update reads a stable value (the statistics are final since the backward kernel)
+    if (n_loss_parts > 0 && defer_tail + (pv.world > 1) > 0 && blockIdx.x == 0 && threadIdx.x == 0 &&
+        W.stats[stat_idx(d, 1, 0, 0)] > 0.0)
+        W.opt_counters[0] += 1;
     MMG_DYN_SMEM(smem_raw);
     float* As = reinterpret_cast<float*>(smem_raw);
     float* Bs = As + kWgradKSlice * kWgLd;
@@ -273,34 +290,42 @@ k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, co
                 // last split to arrive: sum all partials in split order (this CTA's own share from its registers would change the
                 // order with the arrival order, so every share is re-read) and write the final tile
                 if (vec) {
-                    // the splits' partials of this thread's 4 rows: 2 slabs x 4 rows in flight at once
-                    float4 v[4];
+                    // ROLLED over the slabs (this block runs once per output tile: straight-line code would be fetched at L2 speed),
+                    // the next slab's four rows in flight while the current ones are added; split order => reproducible sums
+                    const size_t off0 = (size_t)pr.c_off + (size_t)(m0 + ty * 4) * pr.ldc + j0;
+                    const int nrow = min(4, pr.M - (m0 + ty * 4));
+                    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 v[4], nx[2][4];
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
-                        const int i = m0 + ty * 4 + a;
-                        v[a] = i < pr.M ? ld_cg4(grads + (size_t)pr.c_off + (size_t)i * pr.ldc + j0) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[a] = a < nrow ? ld_cg4(grads + off0 + (size_t)a * pr.ldc) : z4;
+                        nx[0][a] = a < nrow ? ld_cg4(arena + off0 + (size_t)a * pr.ldc) : z4;          // slab 1 (nsplit > 1 here)
+                        nx[1][a] = (a < nrow && pr.nsplit > 2) ? ld_cg4(arena + tab.slab_stride + off0 + (size_t)a * pr.ldc) : z4;
                     }
-                    for (int q0 = 1; q0 < pr.nsplit; q0 += 2) {
-                        float4 t4[2][4];
+#pragma unroll 1
+                    for (int q = 1; q < pr.nsplit; q += 2) {           // slabs q, q + 1 are in nx; q + 2, q + 3 go in flight
+                        float4 cur[2][4];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u)
+#pragma unroll
+                            for (int a = 0; a < 4; ++a) cur[u][a] = nx[u][a];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const bool more = q + 2 + u < pr.nsplit;
+                            const float* nb = arena + (size_t)(q + 1 + u) * tab.slab_stride + off0;
+#pragma unroll
+                            for (int a = 0; a < 4; ++a) nx[u][a] = (more && a < nrow) ? ld_cg4(nb + (size_t)a * pr.ldc) : z4;
+                        }
 #pragma unroll
                         for (int u = 0; u < 2; ++u)
 #pragma unroll
                             for (int a = 0; a < 4; ++a) {
-                                const int i = m0 + ty * 4 + a;
-                                t4[u][a] = (q0 + u < pr.nsplit && i < pr.M)
-                                    ? ld_cg4(arena + (size_t)(q0 + u - 1) * tab.slab_stride + (size_t)pr.c_off + (size_t)i * pr.ldc + j0)
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                                v[a].x += cur[u][a].x; v[a].y += cur[u][a].y; v[a].z += cur[u][a].z; v[a].w += cur[u][a].w;
                             }
-#pragma unroll
-                        for (int u = 0; u < 2; ++u)
-#pragma unroll
-                            for (int a = 0; a < 4; ++a) { v[a].x += t4[u][a].x; v[a].y += t4[u][a].y; v[a].z += t4[u][a].z; v[a].w += t4[u][a].w; }
                     }
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
-                        const int i = m0 + ty * 4 + a;
-                        if (i >= pr.M) continue;
-                        *reinterpret_cast<float4*>(grads + (size_t)pr.c_off + (size_t)i * pr.ldc + j0) = v[a];
+                        if (a < nrow) *reinterpret_cast<float4*>(grads + off0 + (size_t)a * pr.ldc) = v[a];
                         acc[a][0] = v[a].x; acc[a][1] = v[a].y; acc[a][2] = v[a].z; acc[a][3] = v[a].w;
                     }
                 }
@@ -622,7 +647,9 @@ struct OptHyper { int optim; float lr, max_norm; long long step; };
 // and no finishing CTA; every CTA adds them up itself, in tile order (the same numbers in every CTA).
 MMG_DEVICE void update_body(const SegInfo& seg, const OptHyper& hp, float* params, const float* grads_in, float* grads_out,
                             float* state1, float* state2, double* norm_final, float* grad_norms, const double* stats,
-                            const long long* opt_counters, const PeerView& pv, const float* tile_norm = nullptr, int norm_tiles = 0) {
+                            const long long* opt_counters, const PeerView& pv, const float* tile_norm = nullptr, int norm_tiles = 0,
+                            int nb = 0) {
+    if (nb <= 0) nb = (int)gridDim.x;          // CTAs that share the update (the grid may carry one extra CTA for the loss values)
     MMG_SHARED float coef[4];
     MMG_SHARED int s_err;
     MMG_SHARED double tsum[4][kUpdThreads / 32];
@@ -685,7 +712,7 @@ MMG_DEVICE void update_body(const SegInfo& seg, const OptHyper& hp, float* param
         bc2sw = sqrtf(1.f - powf(0.999f, ws));
     }
     // all range boundaries are multiples of 4 floats, so a float4 group never straddles a module or a head
-    for (long long i = 4 * ((long long)blockIdx.x * kUpdThreads + tid); i < total; i += 4ll * gridDim.x * kUpdThreads) {
+    for (long long i = 4 * ((long long)blockIdx.x * kUpdThreads + tid); i < total; i += 4ll * nb * kUpdThreads) {
         const int sg = seg_of(seg.begin, i);
         if (!seg.trained[sg]) continue;
         const bool in_whead = i >= seg.whead_begin && i < seg.whead_end;
@@ -737,11 +764,11 @@ k_update(SegInfo seg, OptHyper hp, float* params, const float* grads_in, float* 
     pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
     pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
     MMG_TRACE_AT(5, 0);
+    // fused iteration: the backward kernel left per-CTA partials of the five loss values; ONE EXTRA CTA adds them up beside the
+    // update (the values are only reported; as a tail of an update CTA this once-executed code lengthened the kernel by 3 us)
+    if (n_loss_parts > 0 && blockIdx.x == gridDim.x - 1) { loss_finalize(d, W, n_loss_parts, false); MMG_TRACE_AT(5, 6); return; }
     update_body(seg, hp, params, grads_in, grads_out, state1, state2, norm_final, grad_norms, stats, opt_counters, pv, tile_norm,
-                norm_tiles);
-    // fused iteration: the backward kernel left per-CTA partials of the five loss values; one CTA adds them up here, off every
-    // critical path (the values are only reported)
-    if (n_loss_parts > 0 && blockIdx.x == gridDim.x - 1) { MMG_SYNCTHREADS(); loss_finalize(d, W, n_loss_parts); }
+                norm_tiles, n_loss_parts > 0 ? (int)gridDim.x - 1 : (int)gridDim.x);
     MMG_TRACE_AT(5, 7);
 }
 

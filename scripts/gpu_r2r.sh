@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | grep -E "passed|failed|BAD|FAIL|Error" | head -10 > gpurun_out/r2r_pytest.log; cat gpurun_out/r2r_pytest.log
+python scripts/trace.py --dump 4 2>&1 | awk '/iteration 2/{p=1} p' > gpurun_out/r2r_trace.txt; grep -B1 -A8 "k_baseline_fwd\|k_update" gpurun_out/r2r_trace.txt | grep -v " cta " | head -30; grep "span" gpurun_out/r2r_trace.txt
+timeout 300 python bench.py --steps 3000 --warmup 20 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; j=json.loads(sys.stdin.read()); print('N=1', {k:j[k] for k in ('value','ms_per_step','value_l2_flushed')}, 'e2e', j['e2e']['value'])"

@@ -21,7 +21,7 @@ def test_reference_update_block_on_mirrored_surface(case):
     su.run_surface_case(case, "cpu")
 
 
-@pytest.mark.parametrize("case", ["fixed_small", "adaptive_sgd", "desc_attn_small"])
+@pytest.mark.parametrize("case", ["fixed_small", "adaptive_sgd", "adaptive_b1_adam", "desc_attn_small"])
 def test_fused_train_step_behind_the_modules(case):
     su.run_train_step_case(case, "cpu")
 
