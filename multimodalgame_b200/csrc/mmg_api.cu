@@ -691,6 +691,15 @@ static int upd_ctas(int64_t total) {
     return (int)n;
 }
 
+// K_update: one float4 per thread (no per-CTA scratch limits its grid): every load of the pass — with peers, every NVLink pull —
+// is in flight at once instead of one round trip per loop iteration
+static int update_ctas(int64_t total) {
+    int64_t n = cdiv64(total / 4, kUpdThreads);
+    if (n > 4096) n = 4096;
+    if (n < 1) n = 1;
+    return (int)n;
+}
+
 static SegInfo seg_info(const mmg_param_layout& L, const Dims& d) {
     SegInfo s;
     for (int i = 0; i < 5; ++i) s.begin[i] = L.seg_begin[i];
@@ -1037,7 +1046,7 @@ static int clip_update_impl(const mmg_config* cfg, float* d_params, float* d_gra
     const SegInfo seg = seg_info(L, d);
     OptHyper hp;
     hp.optim = cfg->optim_type; hp.lr = cfg->learning_rate; hp.max_norm = cfg->max_norm; hp.step = step;
-    MMG_LAUNCH(k_update, upd_ctas(L.total) + (loss_parts > 0 ? 1 : 0), kUpdThreads, 0, (cudaStream_t)stream, seg, hp, d_params, (const float*)d_grads, d_grads,
+    MMG_LAUNCH(k_update, update_ctas(L.total) + (loss_parts > 0 ? 1 : 0), kUpdThreads, 0, (cudaStream_t)stream, seg, hp, d_params, (const float*)d_grads, d_grads,
                d_state1, d_state2, W.norm_final, W.grad_norms, (const double*)W.stats,
                (const long long*)W.opt_counters, no_peers(), (const float*)W.tile_norm, norm_tiles, loss_parts, d, W);
     return check_cuda("k_update");
@@ -1150,7 +1159,7 @@ int mmg_train_step_peer(const mmg_config* cfg, float* d_params, float* d_grads, 
     // ... and the update waits for all slices (flag row 2), then clips and steps, pulling every slice from its owner
     OptHyper hp;
     hp.optim = cfg->optim_type; hp.lr = cfg->learning_rate; hp.max_norm = cfg->max_norm; hp.step = step;
-    MMG_LAUNCH(k_update, upd_ctas(L.total) + (loss_parts > 0 ? 1 : 0), kUpdThreads, 0, st, seg, hp, d_params, (const float*)pv.recv[pv.rank], d_grads, d_state1,
+    MMG_LAUNCH(k_update, update_ctas(L.total) + (loss_parts > 0 ? 1 : 0), kUpdThreads, 0, st, seg, hp, d_params, (const float*)pv.recv[pv.rank], d_grads, d_state1,
                d_state2, W.norm_final, W.grad_norms, (const double*)W.stats, (const long long*)W.opt_counters, pv,
                (const float*)W.tile_norm, 0, loss_parts, d, W);
     return check_cuda("k_update");
