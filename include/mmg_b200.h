@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MMG_ABI_VERSION 3
+#define MMG_ABI_VERSION 4
 
 typedef enum mmg_status {
     MMG_OK = 0,
@@ -41,7 +41,7 @@ typedef enum mmg_status {
 } mmg_status;
 
 enum { MMG_OPT_RMSPROP = 0, MMG_OPT_ADAM = 1, MMG_OPT_SGD = 2 }; /* model.py:1111-1137 */
-enum { MMG_MIX_SUM = 0, MMG_MIX_PROD = 1 };
+enum { MMG_MIX_SUM = 0, MMG_MIX_PROD = 1, MMG_MIX_MOU = 2 };
 
 /* Flags that shape the path.  Field names follow the reference's gflags (model.py:1641-1741). */
 typedef struct mmg_config {
@@ -68,7 +68,7 @@ typedef struct mmg_config {
     int32_t has_flipout_sen, has_flipout_rec; /* 0 when the flag is None (model.py:1710-1711) */
     int32_t flipout_dev;     /* model.py:1712: flip in eval mode too */
     float flipout_sen, flipout_rec;           /* bit-flip probabilities (model.py:233-234,467-468,554-568) */
-    int32_t sender_mix;      /* MMG_MIX_SUM: tanh(h_x + h_w); MMG_MIX_PROD: tanh(h_x * h_w)  (model.py:1692,208-221); "mou" unsupported */
+    int32_t sender_mix;      /* MMG_MIX_SUM: tanh(h_x + h_w); MMG_MIX_PROD: tanh(h_x * h_w); MMG_MIX_MOU: tanh([h_x ; h_w ; h_x - h_w ; h_x * h_w]), binary_layer 4 Hi wide (model.py:1692,71-76,208-221) */
     int32_t ignore_code;     /* model.py:1704,208-213: the sender ignores the receiver's message, hidden = tanh(h_x) */
     int32_t desc_attn;       /* model.py:1719,344-410: the receiver attends over the words of each class description */
     int32_t desc_attn_dim;   /* A   model.py:1720 */
@@ -108,11 +108,12 @@ enum {
     MMG_P_REC_DA_W,         /* receiver.d_attn.weight   (1, A)    */
     MMG_P_REC_DA_B,         /* receiver.d_attn.bias     (1)       */
     MMG_P_SEN_CODE_BIAS,    /* sender.code_bias         (M)        model.py:69 */
+    MMG_P_SEN_CODE_BIAS_MOU,/* sender.code_bias_mou     (M)        model.py:73-74; only with sender_mix mou AND ignore_code, zero-sized otherwise */
     MMG_P_SEN_IMG_W,        /* sender.image_layer.weight (Hi, F)   model.py:67 */
     MMG_P_SEN_IMG_B,        /* sender.image_layer.bias  (Hi)      */
     MMG_P_SEN_CODE_W,       /* sender.code_layer.weight (Hi, M)    model.py:68 */
     MMG_P_SEN_CODE_B,       /* sender.code_layer.bias   (Hi)      */
-    MMG_P_SEN_BIN_W,        /* sender.binary_layer.weight (M, Hi)  model.py:76 */
+    MMG_P_SEN_BIN_W,        /* sender.binary_layer.weight (M, Hi), (M, 4 Hi) with sender_mix mou  model.py:72,76 */
     MMG_P_SEN_BIN_B,        /* sender.binary_layer.bias (M)       */
     MMG_P_BR_L1_W,          /* baseline_rec.linear1.weight (Hb, M+Hr) columns [z ; h_z]  model.py:492,842 */
     MMG_P_BR_L1_B,          /* baseline_rec.linear1.bias   (Hb)   */
@@ -329,7 +330,7 @@ int mmg_train_step_peer(const mmg_config* cfg, float* d_params, float* d_grads, 
  * everywhere else; no activations are saved (no backward).  Training draws use the injected float64 uniforms when given,
  * else the Philox stream (seed, counter) — the caller advances `counter` per call.
  *
- * mmg_sender_forward: Sender.forward(x, w, g, t) default path, model.py:144-238 (sender_mix sum/prod, ignore_code,
+ * mmg_sender_forward: Sender.forward(x, w, g, t) default path, model.py:144-238 (sender_mix sum/prod/mou, ignore_code,
  *   flipout_sen).  d_w (rows,M) may be NULL when t == 0 (the code is sigmoid(code_bias), model.py:199-200).
  *   Outputs: d_msg (rows,M) message {0,1} or raw scores (continuous), d_probs (rows,M) (untouched when !use_binary),
  *   d_h_x (rows,Hi) = sender.h_x (model.py:195). */

@@ -11,8 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libmmg_b200.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 
-MMG_ABI_VERSION = 3          # include/mmg_b200.h; a library built from other headers is refused at load time
-MMG_P_COUNT = 36
+MMG_ABI_VERSION = 4          # include/mmg_b200.h; a library built from other headers is refused at load time
+MMG_P_COUNT = 37
 MMG_SEG_COUNT = 4
 MMG_LOSS_COUNT = 16
 
@@ -24,7 +24,8 @@ PARAM_NAMES = [
     ("receiver", "y2.weight"), ("receiver", "y2.bias"), ("receiver", "s.weight"), ("receiver", "s.bias"),
     ("receiver", "d_d.weight"), ("receiver", "d_d.bias"), ("receiver", "d_h.weight"), ("receiver", "d_h.bias"),
     ("receiver", "d_attn.weight"), ("receiver", "d_attn.bias"),      # -desc_attn only, zero-sized otherwise
-    ("sender", "code_bias"), ("sender", "image_layer.weight"), ("sender", "image_layer.bias"),
+    ("sender", "code_bias"), ("sender", "code_bias_mou"),            # code_bias_mou: -sender_mix mou -ignore_code only, zero-sized otherwise
+    ("sender", "image_layer.weight"), ("sender", "image_layer.bias"),
     ("sender", "code_layer.weight"), ("sender", "code_layer.bias"), ("sender", "binary_layer.weight"),
     ("sender", "binary_layer.bias"),
     ("baseline_rec", "linear1.weight"), ("baseline_rec", "linear1.bias"), ("baseline_rec", "linear2.weight"),
@@ -36,7 +37,7 @@ SEGMENTS = ("receiver", "sender", "baseline_rec", "baseline_sen")
 LOSS_NAMES = ("nll_loss", "loss_rec", "loss_sen", "loss_bas_rec", "loss_bas_sen", "loss_binary_s", "loss_binary_rec",
               "loss_binary_sen", "topk_correct", "active_steps")
 OPTIM = {"RMSprop": 0, "Adam": 1, "SGD": 2}
-SENDER_MIX = {"sum": 0, "prod": 1}
+SENDER_MIX = {"sum": 0, "prod": 1, "mou": 2}
 
 
 class Config(C.Structure):

@@ -119,7 +119,7 @@ static int validate(const mmg_config* c) {
     if (c->msg_dim > 256) return fail(MMG_ERR_UNSUPPORTED, "msg_dim=%d > 256 not supported by the fused path", c->msg_dim);
     if (c->img_h_dim > (int)kGemmSmemFloats * 64) return fail(MMG_ERR_UNSUPPORTED, "img_h_dim=%d too large", c->img_h_dim);
     if (c->optim_type < 0 || c->optim_type > 2) return fail(MMG_ERR_INVALID, "optim_type=%d", c->optim_type);
-    if (c->sender_mix != MMG_MIX_SUM && c->sender_mix != MMG_MIX_PROD) return fail(MMG_ERR_UNSUPPORTED, "sender_mix=%d (mou is not built)", c->sender_mix);
+    if (c->sender_mix != MMG_MIX_SUM && c->sender_mix != MMG_MIX_PROD && c->sender_mix != MMG_MIX_MOU) return fail(MMG_ERR_INVALID, "sender_mix=%d", c->sender_mix);
     if ((long long)c->max_exchange * c->batch > (1ll << 24)) return fail(MMG_ERR_UNSUPPORTED, "T*B too large");
     if (c->desc_attn) {
         if (c->desc_attn_dim < 1 || c->desc_attn_dim > 256) return fail(MMG_ERR_INVALID, "desc_attn_dim=%d", c->desc_attn_dim);
@@ -131,6 +131,7 @@ static int validate(const mmg_config* c) {
 
 static void param_layout(const Dims& d, mmg_param_layout* L) {
     const int Hr = d.Hr, M = d.M, WV = d.WV, Hi = d.Hi, F = d.F, Hb = d.Hb, A = d.A, on = d.A ? 1 : 0;
+    const int mo = (d.mix_mou && d.ignore_code) ? 1 : 0;      // code_bias_mou exists (model.py:73-74)
     struct E { int id, rows, cols, seg; };
     const E tab[MMG_P_COUNT] = {
         {MMG_P_REC_RNN_WIH, 3 * Hr, M, 0}, {MMG_P_REC_RNN_WHH, 3 * Hr, Hr, 0}, {MMG_P_REC_RNN_BIH, 3 * Hr, 1, 0},
@@ -140,8 +141,8 @@ static void param_layout(const Dims& d, mmg_param_layout* L) {
         {MMG_P_REC_Y2_B, 1, 1, 0}, {MMG_P_REC_S_W, 1, Hr, 0}, {MMG_P_REC_S_B, 1, 1, 0},
         {MMG_P_REC_DD_W, A, on * WV, 0}, {MMG_P_REC_DD_B, A, on, 0}, {MMG_P_REC_DH_W, A, on * Hr, 0}, {MMG_P_REC_DH_B, A, on, 0},
         {MMG_P_REC_DA_W, on, A, 0}, {MMG_P_REC_DA_B, on, on, 0},
-        {MMG_P_SEN_CODE_BIAS, M, 1, 1}, {MMG_P_SEN_IMG_W, Hi, F, 1}, {MMG_P_SEN_IMG_B, Hi, 1, 1},
-        {MMG_P_SEN_CODE_W, Hi, M, 1}, {MMG_P_SEN_CODE_B, Hi, 1, 1}, {MMG_P_SEN_BIN_W, M, Hi, 1},
+        {MMG_P_SEN_CODE_BIAS, M, 1, 1}, {MMG_P_SEN_CODE_BIAS_MOU, mo * M, mo, 1}, {MMG_P_SEN_IMG_W, Hi, F, 1}, {MMG_P_SEN_IMG_B, Hi, 1, 1},
+        {MMG_P_SEN_CODE_W, Hi, M, 1}, {MMG_P_SEN_CODE_B, Hi, 1, 1}, {MMG_P_SEN_BIN_W, M, d.Ha, 1},
         {MMG_P_SEN_BIN_B, M, 1, 1},
         {MMG_P_BR_L1_W, Hb, M + Hr, 2}, {MMG_P_BR_L1_B, Hb, 1, 2}, {MMG_P_BR_L2_W, 1, Hb, 2}, {MMG_P_BR_L2_B, 1, 1, 2},
         {MMG_P_BS_L1_W, Hb, Hi + M, 3}, {MMG_P_BS_L1_B, Hb, 1, 3}, {MMG_P_BS_L2_W, 1, Hb, 3}, {MMG_P_BS_L2_B, 1, 1, 3}};
@@ -200,8 +201,8 @@ static void ws_layout(const Dims& d, Ws* w) {
     p.g_br = take(c, R * f);
     p.rng_state = take(c, 16);
     w->code_in = take(c, R * d.M * f);
-    w->a_s = take(c, R * d.Hi * f);
-    w->hw_s = take(c, d.mix_prod ? R * d.Hi * f : 16);
+    w->a_s = take(c, R * d.Ha * f);
+    w->hw_s = take(c, (d.mix_prod || d.mix_mou) ? R * d.Hi * f : 16);
     w->gates = take(c, R * 4 * d.Hr * f);
     w->y1h = take(c, R * d.Hr * f);
     w->q = take(c, R * d.D * f);
@@ -617,11 +618,21 @@ static int build_wgrad_table(const Dims& d, const mmg_param_layout& L, const Par
     b.add(km(W.g_outp, 1), ones(), 1, 1, B * d.D, MMG_P_REC_Y2_B, 0, -1);
     if (d.use_binary) {
         // sender
-        b.add(km(W.d_lz, M), km(W.a_s, Hi), M, Hi, R, MMG_P_SEN_BIN_W, 0, MMG_P_SEN_BIN_B);
-        if (!d.ignore_code) {      // -ignore_code: code_layer / code_bias receive no gradient (model.py:208-213); they stay zero
+        b.add(km(W.d_lz, M), km(W.a_s, d.Ha), M, d.Ha, R, MMG_P_SEN_BIN_W, 0, MMG_P_SEN_BIN_B);
+        if (!d.ignore_code || d.mix_mou) {      // -ignore_code without mou: code_layer / code_bias receive no gradient (model.py:208-210); they stay zero
             b.add(km(W.d_as, Hi), km(W.code_in, M), Hi, M, R, MMG_P_SEN_CODE_W, 0, MMG_P_SEN_CODE_B);
             if (fast) b.add(km(W.dcode_part, M), ones(), M, 1, B, MMG_P_SEN_CODE_BIAS, 0, -1, WG_GEMM, P.p[MMG_P_SEN_CODE_BIAS]);
-            else      b.add(km(W.d_as, Hi), km(W.d_as, Hi), M, 1, 1, MMG_P_SEN_CODE_BIAS, 0, -1, WG_CODEBIAS);
+            else {
+                // d code_bias from the rows of step 0; with mou + ignore_code, d code_bias_mou from the rows of the later steps
+                Operand rows0 = km(W.d_as, Hi);
+                rows0.ld2 = 0; rows0.mod = B;
+                b.add(rows0, km(W.d_as, Hi), M, 1, 1, MMG_P_SEN_CODE_BIAS, 0, -1, WG_CODEBIAS, P.p[MMG_P_SEN_CODE_BIAS]);
+                if (d.mix_mou && d.ignore_code && R > B) {
+                    Operand rows1 = km(W.d_as, Hi);
+                    rows1.ld2 = B; rows1.mod = R;
+                    b.add(rows1, km(W.d_as, Hi), M, 1, 1, MMG_P_SEN_CODE_BIAS_MOU, 0, -1, WG_CODEBIAS, P.p[MMG_P_SEN_CODE_BIAS_MOU]);
+                }
+            }
         }
         b.add(km(W.dhx, Hi), km(in.x, d.F), Hi, d.F, B, MMG_P_SEN_IMG_W, 0, MMG_P_SEN_IMG_B);
         // baseline_sen: d pre = g_bs * linear2.weight * (hidden > 0); rows [h_x[b] ; z_r[t,b]]

@@ -25,7 +25,7 @@ MMG_HOST_DEVICE int bwd_rec_state_floats(const Dims& d, int BT) {
 }
 MMG_HOST_DEVICE int bwd_sen_state_floats(const Dims& d, int BT) {
     const int MP = d.M4 * 4, HiP = align4(d.Hi);
-    int pmax = round_up(d.Hi, 32);
+    int pmax = round_up(d.Ha, 32);
     if (pmax < kLoopThreads) pmax = kLoopThreads;
     return BT * (MP + HiP) + BT * pmax + 8;
 }
@@ -46,7 +46,7 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
         int o = im.sender_end;
         float* dlz = sm + o; o += BT * MP;
         float* dhx = sm + o; o += BT * HiP;
-        int pmax = round_up(d.Hi, 32);
+        int pmax = round_up(d.Ha, 32);
         if (pmax < kLoopThreads) pmax = kLoopThreads;
         float* part = sm + o; o += BT * pmax;
         o = align4(o); o += (o & 1);
@@ -63,7 +63,7 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
         mbar_wait(bar, 0);
         MMG_SYNCTHREADS();
         const float* WbT = sm + im.wbT;
-        const SplitPlan sp = make_split(d.Hi, d.M4);
+        const SplitPlan sp = make_split(d.Ha, d.M4);
         for (int t = 0; t < d.T; ++t) {
             for (int idx = tid; idx < BT * d.M; idx += kLoopThreads) {
                 const int bt = idx / d.M, j = idx % d.M, b = b0 + bt;
@@ -77,11 +77,21 @@ k_exchange_bwd(Dims d, WsPtrs W, int n_rec_ctas, AttnArgs aa) {
                 dlz[bt * MP + j] = dl;
             }
             MMG_SYNCTHREADS();
-            split_matvec<BT, false>(WbT, d.Hi, d.M4, dlz, MP, part, sp);   // d a = W_b^T . d logits
+            split_matvec<BT, false>(WbT, d.Ha, d.M4, dlz, MP, part, sp);   // d a = W_b^T . d logits
             MMG_SYNCTHREADS();
             for (int idx = tid; idx < BT * d.Hi; idx += kLoopThreads) {
                 const int bt = idx / d.Hi, n = idx % d.Hi, b = b0 + bt;
-                if (b < d.B) {
+                if (b < d.B && d.mix_mou) {
+                    // four blocks a = tanh([h_x ; h_w ; h_x - h_w ; h_x * h_w]): d h_x = d0 + d2 + d3 h_w, d h_w = d1 - d2 + d3 h_x
+                    const size_t i = ((size_t)t * d.B + b) * d.Hi + n;
+                    const float* as = W.a_s + ((size_t)t * d.B + b) * d.Ha;
+                    float dp[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { const float a = as[k * d.Hi + n]; dp[k] = gather_part<BT>(part, sp, bt, k * d.Hi + n) * (1.f - a * a); }
+                    const float hxv = W.h_x[(size_t)b * d.Hi + n], hwv = W.hw_s[i];
+                    W.d_as[i] = dp[1] - dp[2] + dp[3] * hxv;
+                    dhx[bt * HiP + n] += dp[0] + dp[2] + dp[3] * hwv;
+                } else if (b < d.B) {
                     const size_t i = ((size_t)t * d.B + b) * d.Hi + n;
                     const float a = W.a_s[i];
                     const float dpre = gather_part<BT>(part, sp, bt, n) * (1.f - a * a);  // through tanh (model.py:216)

@@ -90,8 +90,8 @@ MMG_DEVICE float flip_bit(float bit, float p_flip, const double* u, size_t uidx,
 
 MMG_HOST_DEVICE int fwd_state_floats(const Dims& d, int BT) {
     // hx, a, win, z, pz, h, head, yv, q, hwr, partA, partB, misc
-    const int HiP = align4(d.Hi), MP = d.M4 * 4, HrP = d.Hr4 * 4;
-    int n = BT * HiP * 2 + BT * MP * 3 + BT * HrP * 2 + BT * align4(d.NH) + BT * align4(d.D) * 2;
+    const int HiP = align4(d.Hi), HaP = align4(d.Ha), MP = d.M4 * 4, HrP = d.Hr4 * 4;
+    int n = BT * (HiP + HaP) + BT * MP * 3 + BT * HrP * 2 + BT * align4(d.NH) + BT * align4(d.D) * 2;
     int pmax = round_up(d.Hi, 32);
     if (round_up(d.G3, 32) > pmax) pmax = round_up(d.G3, 32);
     if (round_up(d.NH, 32) > pmax) pmax = round_up(d.NH, 32);
@@ -110,13 +110,13 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
     const FwdImage im = make_fwd_image(d);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b0 = blockIdx.x * BT;
-    const int HiP = align4(d.Hi), MP = d.M4 * 4, HrP = d.Hr4 * 4, NHP = align4(d.NH), DP = align4(d.D);
+    const int HiP = align4(d.Hi), HaP = align4(d.Ha), MP = d.M4 * 4, HrP = d.Hr4 * 4, NHP = align4(d.NH), DP = align4(d.D);
     const int img0 = sender_smem ? 0 : im.sender_end;
     // ---- shared-memory carve-up ---------------------------------------------------------------------------
     float* img = sm - img0;                       // img[off] valid for off >= img0
     int o = im.total - img0;
     float* hx = sm + o;   o += BT * HiP;
-    float* av = sm + o;   o += BT * HiP;
+    float* av = sm + o;   o += BT * HaP;
     float* win = sm + o;  o += BT * MP;
     float* zv = sm + o;   o += BT * MP;
     float* pv = sm + o;   o += BT * MP;
@@ -151,6 +151,8 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
     const float* Wb = sender_smem ? img + im.wb : gimg + im.wb;
     const float* b_code = sender_smem ? img + im.b_code : gimg + im.b_code;
     const float* hw0 = sender_smem ? img + im.hw0 : gimg + im.hw0;
+    const float* hw0m = sender_smem ? img + im.hw0m : gimg + im.hw0m;
+    const bool code_const = d.mix_mou && d.ignore_code;     // the code term after step 0 is a constant vector (model.py:201-205)
     const float* b_b = sender_smem ? img + im.b_b : gimg + im.b_b;
     const float* Wih = img + im.wih;
     const float* Whh = img + im.whh;
@@ -164,7 +166,7 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
     const float* y1d = img + im.y1d;
     const float* wdd = img + im.wdd;
 
-    const SplitPlan sp_code = make_split(d.Hi, d.M4), sp_bin = make_split(d.M, d.Hi4), sp_gi = make_split(d.G3, d.M4),
+    const SplitPlan sp_code = make_split(d.Hi, d.M4), sp_bin = make_split(d.M, d.Ha4), sp_gi = make_split(d.G3, d.M4),
                     sp_gh = make_split(d.G3, d.Hr4), sp_head = make_split(d.NH, d.Hr4), sp_w = make_split(d.M, d.Hr4);
     const bool train = in.train != 0;
     const bool binary = d.use_binary != 0;
@@ -202,7 +204,7 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
         if (b < d.B && j < d.M) W.rec_feats[(size_t)b * d.M + j] = v;  // slot 0
     }
     if (tid < BT) { sprod[tid] = 1.f; smask[tid] = 1.f; if (b0 + tid < d.B) W.stop_mask[b0 + tid] = 1; }
-    for (int idx = tid; idx < BT * HiP; idx += kLoopThreads) av[idx] = 0.f;
+    for (int idx = tid; idx < BT * HaP; idx += kLoopThreads) av[idx] = 0.f;
     if (d.A) {
         for (int idx = tid; idx < AP; idx += kLoopThreads) vas[idx] = idx < d.A ? ldg(aa.va + idx) : 0.f;
         for (int idx = tid; idx < HrP; idx += kLoopThreads) b1s[idx] = idx < d.Hr ? ldg(aa.b1 + idx) : 0.f;
@@ -219,7 +221,7 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
 
     for (int t = 0; t < d.T; ++t) {
         // ---- S1: sender code term W_code . w_prev (model.py:207); step 0 uses the constant hw0 (199-200) ----
-        if (t > 0) {
+        if (t > 0 && !code_const) {
             if (sender_smem) split_matvec<BT, false>(Wc, d.Hi, d.M4, win, MP, partA, sp_code);
             else             split_matvec<BT, true>(Wc, d.Hi, d.M4, win, MP, partA, sp_code);
             MMG_SYNCTHREADS();
@@ -227,16 +229,27 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
         // ---- S2: a = tanh(h_x + h_w) (model.py:216) -------------------------------------------------------
         for (int idx = tid; idx < BT * d.Hi; idx += kLoopThreads) {
             const int bt = idx / d.Hi, n = idx % d.Hi, b = b0 + bt;
-            const float hw = (t == 0) ? hw0[n] : b_code[n] + gather_part<BT>(partA, sp_code, bt, n);
+            const float hw = (t == 0) ? hw0[n] : (code_const ? hw0m[n] : b_code[n] + gather_part<BT>(partA, sp_code, bt, n));
             const float hxv = hx[bt * HiP + n];
+            if (d.mix_mou) {      // a = tanh([h_x ; h_w ; h_x - h_w ; h_x * h_w]) (model.py:211-213, 219-221)
+                const float a0 = tanhf(hxv), a1 = tanhf(hw), a2 = tanhf(hxv - hw), a3 = tanhf(hxv * hw);
+                float* ab = av + bt * HaP;
+                ab[n] = a0; ab[d.Hi + n] = a1; ab[2 * d.Hi + n] = a2; ab[3 * d.Hi + n] = a3;
+                if (b < d.B) {
+                    float* as = W.a_s + ((size_t)t * d.B + b) * d.Ha;
+                    as[n] = a0; as[d.Hi + n] = a1; as[2 * d.Hi + n] = a2; as[3 * d.Hi + n] = a3;
+                    W.hw_s[((size_t)t * d.B + b) * d.Hi + n] = hw;
+                }
+                continue;
+            }
             const float a = tanhf(d.ignore_code ? hxv : (d.mix_prod ? hxv * hw : hxv + hw));     // model.py:208-221
-            av[bt * HiP + n] = a;
+            av[bt * HaP + n] = a;
             if (b < d.B) {
                 W.a_s[((size_t)t * d.B + b) * d.Hi + n] = a;
                 if (d.mix_prod) W.hw_s[((size_t)t * d.B + b) * d.Hi + n] = hw;
             }
         }
-        if (t > 0) {
+        if (t > 0 && !code_const) {
             for (int idx = tid; idx < BT * d.M; idx += kLoopThreads) {
                 const int bt = idx / d.M, j = idx % d.M, b = b0 + bt;
                 if (b < d.B) W.code_in[((size_t)t * d.B + b) * d.M + j] = win[bt * MP + j];
@@ -244,8 +257,8 @@ k_exchange_fwd(Dims d, WsPtrs W, ExchangeInputs in, const float* b_img, int send
         }
         MMG_SYNCTHREADS();
         // ---- S3: binary_layer (model.py:216) -----------------------------------------------------------------
-        if (sender_smem) split_matvec<BT, false>(Wb, d.M, d.Hi4, av, HiP, partA, sp_bin);
-        else             split_matvec<BT, true>(Wb, d.M, d.Hi4, av, HiP, partA, sp_bin);
+        if (sender_smem) split_matvec<BT, false>(Wb, d.M, d.Ha4, av, HaP, partA, sp_bin);
+        else             split_matvec<BT, true>(Wb, d.M, d.Ha4, av, HaP, partA, sp_bin);
         MMG_SYNCTHREADS();
         // ---- S4: sender message (model.py:222-238, 814-820) ------------------------------------------------
         for (int idx = tid; idx < BT * d.M; idx += kLoopThreads) {

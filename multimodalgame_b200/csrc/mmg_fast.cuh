@@ -111,7 +111,7 @@ MMG_HOST_DEVICE int fast_fwd_attn_floats(int D, int NW) {
 }
 MMG_HOST_DEVICE bool fast_fwd_attn_dims(const Dims& d) {
     // any batch: one example per CTA, in waves when B exceeds the SM count (conversation CTAs never wait on anything)
-    return d.Hi == kFastHi && d.Hr == kFastHr && d.M == 32 && d.T <= kFastMaxT && d.A == kFastAttnA;
+    return d.Hi == kFastHi && d.Hr == kFastHr && d.M == 32 && d.T <= kFastMaxT && d.A == kFastAttnA && !d.mix_mou;
 }
 
 MMG_DEVICE void fma4(const float4& w, const float4& x, float4& acc) {      // two packed fp32x2 FMAs (FFMA2)

@@ -11,12 +11,15 @@ struct Dims {
     int R;        // T * B rows, step-major
     int G3;       // 3 * Hr
     int M4, Hr4, Hi4;   // ceil(x / 4): float4 groups along a reduction dimension
+    int Ha, Ha4;        // width of the sender's hidden vector a: Hi, or 4 Hi with sender_mix mou ([h_x ; h_w ; h_x - h_w ; h_x * h_w])
     int NH;       // stacked head rows: [y1.weight[:, h cols] ; w_h.weight ; s.weight ; d_h.weight (desc_attn)] = 2*Hr + 1 + A
     int use_binary, fixed, s_prob_prod, ignore_receiver;
     float first_rec;
     float flip_sen, flip_rec;   // flipout probabilities, < 0 = off (model.py:233-234,467-468)
     int flipout_dev;
     int mix_prod, ignore_code;  // sender hidden: tanh(h_x * h_w) instead of the sum / tanh(h_x) alone (model.py:208-221)
+    int mix_mou;                // sender hidden: the 4-block mixture (model.py:211-213, 219-221); with ignore_code the code term after
+                                // step 0 is code_layer(sigmoid(code_bias_mou)) (model.py:201-205)
     // -desc_attn (model.py:344-410): A = attention width (0 = off), NW = words of all class descriptions.
     // y1.weight columns are [h_z ; desc] without and [desc ; h_z] with attention (model.py:408-410 vs 548).
     int A, NW, y1_hcol, y1_dcol;
@@ -36,6 +39,8 @@ MMG_HOST_DEVICE Dims make_dims(const mmg_config& c) {
     d.flip_rec = c.has_flipout_rec ? c.flipout_rec : -1.f;
     d.flipout_dev = c.flipout_dev;
     d.mix_prod = c.sender_mix == MMG_MIX_PROD; d.ignore_code = c.ignore_code;
+    d.mix_mou = c.sender_mix == MMG_MIX_MOU;
+    d.Ha = d.mix_mou ? 4 * d.Hi : d.Hi; d.Ha4 = cdiv(d.Ha, 4);
     d.A = c.desc_attn ? c.desc_attn_dim : 0; d.NW = c.desc_attn ? c.n_words : 0;
     d.y1_hcol = d.A ? d.WV : 0; d.y1_dcol = d.A ? 0 : d.Hr;
     d.NH = 2 * d.Hr + 1 + d.A;
@@ -54,6 +59,7 @@ struct FwdImage {
     int wb;      // binary_layer.weight out=M   red=Hi
     int b_code;  // [Hi]
     int hw0;     // [Hi] code_layer(sigmoid(code_bias)) incl. bias: the step-0 code term (model.py:199-200)
+    int hw0m;    // [Hi] code_layer(sigmoid(code_bias_mou)) incl. bias: the code term after step 0 with mou + ignore_code (201-205)
     int b_b;     // [M]
     int sender_end;
     // receiver part
@@ -87,9 +93,10 @@ MMG_HOST_DEVICE int align4(int x) { return (x + 3) & ~3; }
 MMG_HOST_DEVICE FwdImage make_fwd_image(const Dims& d) {
     FwdImage im; int o = 0;
     im.wc = o; o += d.M4 * d.Hi * 4;
-    im.wb = o; o += d.Hi4 * d.M * 4;
+    im.wb = o; o += d.Ha4 * d.M * 4;
     im.b_code = o; o += align4(d.Hi);
     im.hw0 = o; o += align4(d.Hi);
+    im.hw0m = o; o += align4(d.Hi);
     im.b_b = o; o += align4(d.M);
     im.sender_end = o;
     im.wih = o; o += d.M4 * d.G3 * 4;
@@ -109,7 +116,7 @@ MMG_HOST_DEVICE FwdImage make_fwd_image(const Dims& d) {
 }
 MMG_HOST_DEVICE BwdImage make_bwd_image(const Dims& d) {
     BwdImage im; int o = 0;
-    im.wbT = o; o += d.M4 * d.Hi * 4;
+    im.wbT = o; o += d.M4 * d.Ha * 4;
     im.sender_end = o;
     im.wwT = o; o += d.M4 * d.Hr * 4;
     im.headT = o; o += cdiv(2 * d.Hr + d.A, 4) * d.Hr * 4;
@@ -190,7 +197,7 @@ MMG_HOST_DEVICE FastBwdImage make_fast_bwd_image(int M, int D) {
     return im;
 }
 MMG_HOST_DEVICE bool fast_dims(const Dims& d) {
-    return d.Hi == kFastHi && d.Hr == kFastHr && (d.M == 32 || d.M == 64) && d.T <= kFastMaxT && d.A == 0;
+    return d.Hi == kFastHi && d.Hr == kFastHr && (d.M == 32 || d.M == 64) && d.T <= kFastMaxT && d.A == 0 && !d.mix_mou;
 }
 
 // ---- workspace ------------------------------------------------------------------------------------------

@@ -19,7 +19,7 @@ MMG_DEVICE float fwd_image_elem(const Dims& d, const FwdImage& im, const ParamPt
     if (e < im.wb) { int q = e - im.wc; int r = (q / (d.Hi * 4)) * 4 + (q & 3), o = (q >> 2) % d.Hi;
         return packed_src(P.p[MMG_P_SEN_CODE_W], d.M, o, r, d.M); }
     if (e < im.b_code) { int q = e - im.wb; int r = (q / (d.M * 4)) * 4 + (q & 3), o = (q >> 2) % d.M;
-        return packed_src(P.p[MMG_P_SEN_BIN_W], d.Hi, o, r, d.Hi); }
+        return packed_src(P.p[MMG_P_SEN_BIN_W], d.Ha, o, r, d.Ha); }
     if (e < im.hw0) { int i = e - im.b_code; return i < d.Hi ? ldg(P.p[MMG_P_SEN_CODE_B] + i) : 0.f; }
     if (e < im.b_b) return 0.f;  // hw0: dot role
     if (e < im.sender_end) { int i = e - im.b_b; return i < d.M ? ldg(P.p[MMG_P_SEN_BIN_B] + i) : 0.f; }
@@ -49,8 +49,8 @@ MMG_DEVICE float fwd_image_elem(const Dims& d, const FwdImage& im, const ParamPt
 }
 
 MMG_DEVICE float bwd_image_elem(const Dims& d, const BwdImage& im, const ParamPtrs& P, int e) {
-    if (e < im.wwT) { int q = e - im.wbT; int r = (q / (d.Hi * 4)) * 4 + (q & 3), o = (q >> 2) % d.Hi;   // W(o=n, r=j) = bin_w[j][n]
-        return r < d.M ? ldg(P.p[MMG_P_SEN_BIN_W] + (size_t)r * d.Hi + o) : 0.f; }
+    if (e < im.wwT) { int q = e - im.wbT; int r = (q / (d.Ha * 4)) * 4 + (q & 3), o = (q >> 2) % d.Ha;   // W(o=n, r=j) = bin_w[j][n]
+        return r < d.M ? ldg(P.p[MMG_P_SEN_BIN_W] + (size_t)r * d.Ha + o) : 0.f; }
     if (e < im.headT) { int q = e - im.wwT; int r = (q / (d.Hr * 4)) * 4 + (q & 3), o = (q >> 2) % d.Hr;  // w_w[j][k]
         return r < d.M ? ldg(P.p[MMG_P_REC_W_W] + (size_t)r * d.Hr + o) : 0.f; }
     if (e < im.whhT) { int q = e - im.headT; int r = (q / (d.Hr * 4)) * 4 + (q & 3), o = (q >> 2) % d.Hr;
@@ -259,6 +259,19 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
             for (int b = lane; b < d.B; b += 32) W.code_in[(size_t)b * d.M + j] = c0;
         }
     }
+    if (d.mix_mou && d.ignore_code) {
+        // -sender_mix mou -ignore_code: after step 0 the code is sigmoid(code_bias_mou) for every example (model.py:201-205):
+        // hw0m[n] = code_layer(that code)[n], and the code rows of steps >= 1 (the code_layer weight-gradient operand)
+        for (int n = gwarp; n < d.Hi; n += nwarps) {
+            float s = 0.f;
+            for (int j = lane; j < d.M; j += 32)
+                s = fmaf(sigmoidf_(ldg(P.p[MMG_P_SEN_CODE_BIAS_MOU] + j)), ldg(P.p[MMG_P_SEN_CODE_W] + (size_t)n * d.M + j), s);
+            s = warp_sum(s);
+            if (lane == 0) W.fwd_image[fim.hw0m + n] = s + ldg(P.p[MMG_P_SEN_CODE_B] + n);
+        }
+        for (long long e = (long long)d.B * d.M + gtid; e < (long long)d.R * d.M; e += gthreads)
+            W.code_in[e] = sigmoidf_(ldg(P.p[MMG_P_SEN_CODE_BIAS_MOU] + (int)(e % d.M)));
+    }
     // pad tails of dot sections (keep the images fully defined for the bulk copies)
     const int dpad = ((d.D + 3) / 4) * 4;
     if (ff || fb) {
@@ -270,7 +283,8 @@ k_pre(Dims d, ParamPtrs P, WsPtrs W, ExchangeInputs in, int n_hx_tiles, int hx_k
     }
     if (!ff) {
         for (int e = gtid; e < fim.total; e += gthreads) {
-            if ((e >= fim.hw0 + d.Hi && e < fim.b_b) || (e >= fim.y1d + n_y1d_w && e < fim.wdd) || (e >= fim.wdd + n_y1d_w))
+            if ((e >= fim.hw0 + d.Hi && e < fim.hw0m) || (e >= fim.hw0m + ((d.mix_mou && d.ignore_code) ? d.Hi : 0) && e < fim.b_b) ||
+                (e >= fim.y1d + n_y1d_w && e < fim.wdd) || (e >= fim.wdd + n_y1d_w))
                 W.fwd_image[e] = 0.f;
         }
     }

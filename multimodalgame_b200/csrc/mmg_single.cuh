@@ -25,7 +25,7 @@ MMG_DEVICE void block_matvec(float* out, const float* Wm, int ld, int rows, cons
     }
 }
 
-MMG_HOST_DEVICE int sender_step_smem_floats(const Dims& d) { return align4(d.F) + 2 * align4(d.Hi) + 2 * align4(d.M); }
+MMG_HOST_DEVICE int sender_step_smem_floats(const Dims& d) { return align4(d.F) + align4(d.Hi) + align4(d.Ha) + 2 * align4(d.M); }
 
 // Sender.forward default path (model.py:195-238): h_x = image_layer(x); code = sigmoid(code_bias) at t == 0 else w;
 // a = tanh(mix(h_x, code_layer(code))); logits = binary_layer(a); binary: p = sigmoid, message = 1[u < p] (train) or
@@ -38,24 +38,29 @@ k_sender_step(Dims d, ParamPtrs P, const float* x, const float* w, int t, int tr
     float* xs = sm;
     float* hx = xs + align4(d.F);
     float* av = hx + align4(d.Hi);
-    float* code = av + align4(d.Hi);
+    float* code = av + align4(d.Ha);
     float* lg = code + align4(d.M);
     const int tid = threadIdx.x, b = blockIdx.x;
     for (int f = tid; f < d.F; f += kSingleThreads) xs[f] = x[(size_t)b * d.F + f];
     for (int j = tid; j < d.M; j += kSingleThreads)
-        code[j] = (t == 0) ? sigmoidf_(ldg(P.p[MMG_P_SEN_CODE_BIAS] + j)) : w[(size_t)b * d.M + j];   // model.py:199-207
+        code[j] = (t == 0) ? sigmoidf_(ldg(P.p[MMG_P_SEN_CODE_BIAS] + j))                              // model.py:199-207
+                : ((d.mix_mou && d.ignore_code) ? sigmoidf_(ldg(P.p[MMG_P_SEN_CODE_BIAS_MOU] + j)) : w[(size_t)b * d.M + j]);
     MMG_SYNCTHREADS();
     block_matvec(hx, P.p[MMG_P_SEN_IMG_W], d.F, d.Hi, xs, d.F, P.p[MMG_P_SEN_IMG_B]);                 // model.py:195
     block_matvec(av, P.p[MMG_P_SEN_CODE_W], d.M, d.Hi, code, d.M, P.p[MMG_P_SEN_CODE_B]);
     MMG_SYNCTHREADS();
     for (int n = tid; n < d.Hi; n += kSingleThreads) {
         const float hxv = hx[n], hwv = av[n];
+        h_x[(size_t)b * d.Hi + n] = hxv;
+        if (d.mix_mou) {                                                                            // model.py:211-213, 219-221
+            av[n] = tanhf(hxv); av[d.Hi + n] = tanhf(hwv); av[2 * d.Hi + n] = tanhf(hxv - hwv); av[3 * d.Hi + n] = tanhf(hxv * hwv);
+            continue;
+        }
         const float pre = d.ignore_code ? hxv : (d.mix_prod ? hxv * hwv : hxv + hwv);               // model.py:208-221
         av[n] = tanhf(pre);
-        h_x[(size_t)b * d.Hi + n] = hxv;
     }
     MMG_SYNCTHREADS();
-    block_matvec(lg, P.p[MMG_P_SEN_BIN_W], d.Hi, d.M, av, d.Hi, P.p[MMG_P_SEN_BIN_B]);
+    block_matvec(lg, P.p[MMG_P_SEN_BIN_W], d.Ha, d.M, av, d.Ha, P.p[MMG_P_SEN_BIN_B]);
     MMG_SYNCTHREADS();
     for (int j = tid; j < d.M; j += kSingleThreads) {
         const size_t i = (size_t)b * d.M + j;

@@ -451,6 +451,7 @@ k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, co
     } else {
         // generic-path only (the fast backward kernel emits per-example partials instead):
         // d code_bias[j] = c0 (1 - c0) sum_n code_layer.weight[n][j] * (sum_b d_as[t=0][b][n])   (model.py:199-200)
+        // rows [A.ld2, A.mod) of d_as: step 0 for code_bias, the later steps for code_bias_mou (model.py:201-205); sig_rows = the bias
         float* v = As;
         const int vcap = 2 * kWgradKSlice * kWgLd;
         for (int j0 = 0; j0 < d.M; j0 += kGemmThreads) {
@@ -461,14 +462,14 @@ k_wgrad(Dims d, WgTable tab, float* grads, float* arena, const float* code_w, co
                 MMG_SYNCTHREADS();
                 for (int n = tid; n < nlim; n += kGemmThreads) {
                     float sv = 0.f;
-                    for (int b = 0; b < d.B; ++b) sv += d_as[(size_t)b * d.Hi + nb + n];
+                    for (int b = pr.A.ld2; b < pr.A.mod; ++b) sv += d_as[(size_t)b * d.Hi + nb + n];
                     v[n] = sv;
                 }
                 MMG_SYNCTHREADS();
                 if (j < d.M) for (int n = 0; n < nlim; ++n) accj = fmaf(ldg(code_w + (size_t)(nb + n) * d.M + j), v[n], accj);
             }
             if (j < d.M) {
-                const float c0 = sigmoidf_(ldg(code_bias + j));
+                const float c0 = sigmoidf_(ldg((pr.sig_rows != nullptr ? pr.sig_rows : code_bias) + j));
                 const float r = accj * c0 * (1.f - c0);
                 grads[pr.c_off + j] = r;
                 ss = fmaf(r, r, ss);

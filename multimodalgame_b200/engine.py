@@ -44,7 +44,7 @@ def make_config(batch, n_classes, img_feat_dim=4096, img_h_dim=100, baseline_hid
     c.has_flipout_rec, c.flipout_rec = int(flipout_rec is not None), float(flipout_rec or 0.0)
     c.flipout_dev = int(bool(flipout_dev))
     if sender_mix not in capi.SENDER_MIX:
-        raise NotImplementedError("sender_mix=%s is outside the fused B200 path" % sender_mix)        # 'mou', model.py:219-221
+        raise NotImplementedError("sender_mix=%s (model.py:1692 knows sum, prod, mou)" % sender_mix)
     c.sender_mix, c.ignore_code = capi.SENDER_MIX[sender_mix], int(bool(ignore_code))
     c.desc_attn = int(bool(desc_attn))                                                               # model.py:1719-1720
     c.desc_attn_dim, c.n_words = (int(desc_attn_dim), int(n_words)) if desc_attn else (0, 0)
@@ -53,7 +53,7 @@ def make_config(batch, n_classes, img_feat_dim=4096, img_h_dim=100, baseline_hid
 
 
 def _is_vector(key):
-    return key.endswith("bias") or key.endswith("bias_ih") or key.endswith("bias_hh")
+    return key.endswith("bias") or key.endswith("bias_ih") or key.endswith("bias_hh") or key == "code_bias_mou"
 
 
 class GameEngine(object):

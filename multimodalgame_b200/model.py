@@ -190,12 +190,15 @@ class Sender(nn.Module):
         self.attn_dim, self.attn_extra_context, self.attn_context_dim = attn_dim, attn_extra_context, attn_context_dim
         if use_attn:
             _unsupported("-visual_attn (Sender visual attention, model.py:80-86,114-191)")
-        if _flag("sender_mix", "sum") == "mou":
-            _unsupported("-sender_mix mou (4 x h_dim mixture, model.py:73-76,213-221)")
         self.image_layer = nn.Linear(self.feat_dim, self.h_dim)
         self.code_layer = nn.Linear(self.w_dim, self.h_dim)
         self.code_bias = Parameter(torch.Tensor(self.bin_dim_out))
-        self.binary_layer = nn.Linear(self.h_dim, self.bin_dim_out)
+        if _flag("sender_mix", "sum") == "mou":           # model.py:71-76: binary_layer reads [h_x ; h_w ; h_x - h_w ; h_x * h_w]
+            self.binary_layer = nn.Linear(self.h_dim * 4, self.bin_dim_out)
+            if _flag("ignore_code", False):
+                self.code_bias_mou = Parameter(torch.Tensor(self.bin_dim_out))
+        else:
+            self.binary_layer = nn.Linear(self.h_dim, self.bin_dim_out)
         self.reset_parameters()
         self.reset_state()
 
@@ -206,6 +209,10 @@ class Sender(nn.Module):
                 if m.bias is not None:
                     m.bias.data.zero_()
         self.code_bias.data.normal_()
+        if hasattr(self, "code_bias_mou"):
+            # the reference leaves this parameter as torch.Tensor(n) allocated it (uninitialised memory, model.py:73-74, 90-97);
+            # N(0, 1) like code_bias keeps runs reproducible
+            self.code_bias_mou.data.normal_()
 
     def reset_state(self):        # model.py:99-112
         self.h_x = None

@@ -69,8 +69,11 @@ def init_params(flags, seed=0):
                             flags.baseline_hid_dim)
     snd = OrderedDict()
     snd["code_bias"] = torch.zeros(M).normal_(generator=g)                         # model.py:97
-    for name, r, c in (("image_layer", Hi, F), ("code_layer", Hi, M), ("binary_layer", M, Hi)):
+    mou = getattr(flags, "sender_mix", "sum") == "mou"
+    for name, r, c in (("image_layer", Hi, F), ("code_layer", Hi, M), ("binary_layer", M, 4 * Hi if mou else Hi)):   # model.py:71-76
         snd[name + ".weight"], snd[name + ".bias"] = _xavier_normal(r, c, g), torch.zeros(r)
+    if mou and getattr(flags, "ignore_code", False):
+        snd["code_bias_mou"] = torch.zeros(M).normal_(generator=g)                 # model.py:73-74
     rec = OrderedDict()
     rec["rnn.weight_ih"], rec["rnn.weight_hh"] = _xavier_normal(3 * Hr, M, g), _xavier_normal(3 * Hr, Hr, g)
     rec["rnn.bias_ih"], rec["rnn.bias_hh"] = torch.zeros(3 * Hr), torch.zeros(3 * Hr)

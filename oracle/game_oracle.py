@@ -64,7 +64,7 @@ class GameConfig(object):
         self.ignore_receiver = ignore_receiver
         self.flipout_sen = flipout_sen      # model.py:1710-1711 (None = off)
         self.flipout_rec = flipout_rec
-        self.sender_mix = sender_mix        # 'sum' | 'prod' (model.py:1692); 'mou' is not restated
+        self.sender_mix = sender_mix        # 'sum' | 'prod' | 'mou' (model.py:1692)
         self.ignore_code = ignore_code      # model.py:1704
         self.desc_attn = desc_attn          # model.py:1719-1720: the receiver attends over the words of every class description
         self.desc_attn_dim = desc_attn_dim
@@ -106,8 +106,13 @@ def init_params(cfg, seed=0):
     snd["image_layer.bias"] = z(Hi)
     snd["code_layer.weight"] = _xavier_normal_(z(Hi, M), g)
     snd["code_layer.bias"] = z(Hi)
-    snd["binary_layer.weight"] = _xavier_normal_(z(M, Hi), g)
+    mou = cfg.sender_mix == "mou"
+    snd["binary_layer.weight"] = _xavier_normal_(z(M, 4 * Hi if mou else Hi), g)   # model.py:71-76
     snd["binary_layer.bias"] = z(M)
+    if mou and cfg.ignore_code:
+        # model.py:73-74 creates the parameter and reset_parameters (model.py:90-97) leaves it uninitialised (torch.Tensor(n));
+        # N(0, 1) like code_bias is this package's choice, any finite value is equally "reference"
+        snd["code_bias_mou"] = z(M).normal_(generator=g)
     rec = OrderedDict()
     rec["rnn.weight_ih"] = _xavier_normal_(z(3 * Hr, M), g)
     rec["rnn.weight_hh"] = _xavier_normal_(z(3 * Hr, Hr), g)
@@ -181,10 +186,15 @@ def sender_forward(P, x, w, t, cfg, train, u=None, u_flip=None):
     if t == 0:
         first_code = torch.sigmoid(P["code_bias"].view(1, -1))                  # :199
         h_w = F.linear(first_code, P["code_layer.weight"], P["code_layer.bias"]).expand(x.shape[0], -1)
+    elif cfg.ignore_code and cfg.sender_mix == "mou":
+        code_mou = torch.sigmoid(P["code_bias_mou"].view(1, -1))               # :201-205: the same learned code for every example
+        h_w = F.linear(code_mou, P["code_layer.weight"], P["code_layer.bias"]).expand(x.shape[0], -1)
     else:
         h_w = F.linear(w, P["code_layer.weight"], P["code_layer.bias"])        # :207
-    assert cfg.sender_mix in ("sum", "prod")
-    if cfg.ignore_code:
+    assert cfg.sender_mix in ("sum", "prod", "mou")
+    if cfg.sender_mix == "mou":
+        mixed = torch.cat([h_x, h_w, h_x - h_w, h_x * h_w], 1)                   # :211-213, 219-221 (with and without ignore_code)
+    elif cfg.ignore_code:
         mixed = h_x                                                             # :208-210
     elif cfg.sender_mix == "prod":
         mixed = h_x * h_w                                                       # :217-218

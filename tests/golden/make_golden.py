@@ -83,6 +83,19 @@ CASES = {
                               max_exchange=4, fixed_exchange=False, use_binary=True, entropy_sen=0.01,
                               entropy_rec=0.02, entropy_s=0.05, top_k_train=2, sender_mix="prod"),
                      iters=2, seed=25),
+    # -sender_mix mou: binary_layer reads tanh([h_x ; h_w ; h_x - h_w ; h_x * h_w]) (4 x h_dim, model.py:71-76, 219-221)
+    "mix_mou": dict(cfg=dict(batch_size=6, img_feat_dim=40, img_h_dim=24, baseline_hid_dim=20,
+                             sender_out_dim=12, rec_hidden=16, rec_w_dim=12, wv_dim=20, n_classes=7,
+                             max_exchange=4, fixed_exchange=False, use_binary=True, entropy_sen=0.01,
+                             entropy_rec=0.02, entropy_s=0.05, top_k_train=2, sender_mix="mou"),
+                    iters=2, seed=31),
+    # -sender_mix mou -ignore_code: after step 0 the code term is code_layer(sigmoid(code_bias_mou)), a second learned code
+    # (model.py:73-74, 201-205, 211-213)
+    "mix_mou_ignore": dict(cfg=dict(batch_size=6, img_feat_dim=40, img_h_dim=24, baseline_hid_dim=20,
+                                    sender_out_dim=12, rec_hidden=16, rec_w_dim=12, wv_dim=20, n_classes=7,
+                                    max_exchange=3, fixed_exchange=True, use_binary=True, entropy_sen=0.01,
+                                    entropy_rec=0.02, top_k_train=2, sender_mix="mou", ignore_code=True),
+                           iters=2, seed=32),
     # -ignore_code: the sender never sees the receiver's message (model.py:208-210); code_layer / code_bias get no gradient
     "ignore_code": dict(cfg=dict(batch_size=6, img_feat_dim=40, img_h_dim=24, baseline_hid_dim=20,
                                  sender_out_dim=12, rec_hidden=16, rec_w_dim=12, wv_dim=20, n_classes=7,

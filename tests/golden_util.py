@@ -12,7 +12,7 @@ from oracle import game_oracle as go
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 TRAIN_CASES = ["c1_continuous", "continuous_t3", "fixed_small", "fixed_t1_noent", "adaptive_small",
-               "adaptive_b1_adam", "headline_mid", "adaptive_sgd", "flipout_small", "ignore_rec_first1", "mix_prod", "ignore_code"]
+               "adaptive_b1_adam", "headline_mid", "adaptive_sgd", "flipout_small", "ignore_rec_first1", "mix_prod", "ignore_code", "mix_mou", "mix_mou_ignore"]
 ATTN_TRAIN_CASES = ["desc_attn_small", "desc_attn_mid"]      # -desc_attn (model.py:344-410)
 ATTN_EVAL_CASES = ["eval_desc_attn"]
 EVAL_CASES = ["eval_adaptive", "eval_adaptive_noprod", "eval_fixed_corrupt", "eval_continuous"]

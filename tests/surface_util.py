@@ -62,7 +62,10 @@ def build_modules(cfg, params, device):
     baseline_sen = M.Baseline(cfg.baseline_hid_dim, cfg.img_h_dim, cfg.rec_w_dim, 0)
     baseline_rec = M.Baseline(cfg.baseline_hid_dim, 0, cfg.sender_out_dim, cfg.rec_hidden)
     mods = dict(sender=sender, receiver=receiver, baseline_sen=baseline_sen, baseline_rec=baseline_rec)
-    assert list(sender.state_dict().keys()) == REF_KEYS["sender"]
+    want = list(REF_KEYS["sender"])
+    if getattr(cfg, "sender_mix", "sum") == "mou" and getattr(cfg, "ignore_code", False):
+        want.insert(1, "code_bias_mou")                  # direct parameters come first in state_dict order (model.py:73-74)
+    assert list(sender.state_dict().keys()) == want
     assert list(receiver.state_dict().keys()) == REF_KEYS["receiver"] + (ATTN_KEYS if getattr(cfg, "desc_attn", False) else [])
     assert list(baseline_sen.state_dict().keys()) == REF_KEYS["baseline"]
     for a, m in mods.items():

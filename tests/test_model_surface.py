@@ -16,7 +16,8 @@ def emulated_library():
     M._BINDINGS.clear(); M._LAST_BINDING.clear()
 
 
-@pytest.mark.parametrize("case", ["fixed_small", "adaptive_small", "continuous_t3", "fixed_t1_noent", "desc_attn_small"])
+@pytest.mark.parametrize("case", ["fixed_small", "adaptive_small", "continuous_t3", "fixed_t1_noent", "desc_attn_small", "mix_mou",
+                                  "mix_mou_ignore"])
 def test_reference_update_block_on_mirrored_surface(case):
     su.run_surface_case(case, "cpu")
 
@@ -45,7 +46,7 @@ def test_unsupported_flags_raise():
 
 
 @pytest.mark.parametrize("case,train", [("fixed_small", True), ("adaptive_small", True), ("continuous_t3", True),
-                                        ("mix_prod", True), ("desc_attn_small", True), ("flipout_small", True), ("ignore_code", True),
+                                        ("mix_prod", True), ("mix_mou", True), ("mix_mou_ignore", True), ("desc_attn_small", True), ("flipout_small", True), ("ignore_code", True),
                                         ("ignore_rec_first1", True), ("eval_adaptive", False),
                                         ("eval_desc_attn", False)])
 def test_module_forwards_turn_by_turn(case, train):
