@@ -25,7 +25,7 @@ def test_every_declared_symbol_is_exported(lib):
     for name in declared:
         assert hasattr(lib.dll, name), "symbol %s declared in include/mmg_b200.h but not exported" % name
     assert set(capi.Library.SYMBOLS) <= declared
-    assert lib.dll.mmg_abi_version() == capi.MMG_ABI_VERSION == 3
+    assert lib.dll.mmg_abi_version() == capi.MMG_ABI_VERSION == 4
 
 
 def test_layouts_and_validation(lib):
@@ -35,7 +35,7 @@ def test_layouts_and_validation(lib):
     lib.call("mmg_param_layout_get", C.byref(cfg), C.byref(L))
     # parameter counts of SURVEY.md §8a: sender 541 248, receiver 42 146, baselines 145 001 + 49 001
     n = lambda a, b: sum(L.rows[i] * L.cols[i] for i in range(a, b))
-    assert n(0, 21) == 42146 and n(21, 28) == 541248 and n(28, 32) == 49001 and n(32, 36) == 145001
+    assert n(0, 21) == 42146 and n(21, 29) == 541248 and n(29, 33) == 49001 and n(33, 37) == 145001
     assert all(L.offset[i] % 4 == 0 for i in range(capi.MMG_P_COUNT))
     assert [capi.PARAM_NAMES[i][0] for i in range(capi.MMG_P_COUNT)] == [capi.SEGMENTS[L.segment[i]] for i in range(capi.MMG_P_COUNT)]
     W = capi.WorkspaceLayout()
