@@ -451,7 +451,6 @@ def main():
     # ---- e2e: host buffers through the public API: every step copies its batch from pinned host memory (H2D, on a copy
     #      stream, double-buffered: overlaps the previous step) and its loss values back (D2H).  Timed on the device with
     #      one pair of events around the K steps (plus the host wall clock), max over ranks.
-    hl = torch.zeros(K, capi.MMG_LOSS_COUNT, dtype=torch.float32).pin_memory()
     e.enable_host_pipeline(desc)
 
     def run_host(n):
@@ -460,7 +459,9 @@ def main():
             slot = i % 2
             if i + 1 < n:
                 e.host_prefetch(hx[(i + 1) % nb], ht[(i + 1) % nb])
-            e.train_step_staged(hl[i % K], slot, dp_group=dist.group.WORLD if dp_mode == "nccl" else None)
+            # loss values -> pinned host memory every step: written by the update kernel itself into the slot's mapped pinned
+            # buffer (single GPU), or copied device-to-host behind the step (data-parallel paths)
+            e.train_step_staged(None, slot, dp_group=dist.group.WORLD if dp_mode == "nccl" else None)
     run_host(6)
     sync_all()
     h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -472,7 +473,10 @@ def main():
     torch.cuda.synchronize(dev)
     e2e_wall_ms = 1e3 * (time.perf_counter() - t0)
     e2e_ms = max(h0.elapsed_time(h1), 0.0)
-    assert float(hl[K - 1][0]) != 0.0          # the loss values really arrived on the host
+    last_losses = e.staged_losses((K - 1) % 2).clone()
+    assert float(last_losses[0]) != 0.0 and bool(torch.isfinite(last_losses).all())     # the loss values really arrived on the host
+    dev_losses = e.ws("losses", (capi.MMG_LOSS_COUNT,)).cpu()
+    assert torch.equal(last_losses, dev_losses), "host copy of the loss values differs from the device's"
 
     # ---- N>1: the replicas must still be bit-identical and no peer wait may have timed out ----------------------------------
     replicas = None
@@ -500,7 +504,7 @@ def main():
            "launch": "CUDA graph replay per staging slot" if getattr(e, "_hp", {}).get("graphs") else "eager launches",
            "note": "mmg_host_prefetch + mmg_train_step_staged (N>1: the same staging slots feeding mmg_train_step_peer): pinned "
                    "host x/target -> device on a copy stream (double-buffered, overlaps the previous step), losses -> pinned "
-                   "host every step; bytes are the whole job's (all ranks); device-timed, max over ranks"}
+                   "host every step (single GPU: written by the update kernel into mapped pinned memory; N>1: async copy); bytes are the whole job's (all ranks); device-timed, max over ranks"}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

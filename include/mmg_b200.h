@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MMG_ABI_VERSION 4
+#define MMG_ABI_VERSION 5
 
 typedef enum mmg_status {
     MMG_OK = 0,
@@ -214,6 +214,10 @@ typedef struct mmg_inputs {
      * words of each class; every class has at least one word */
     const float* d_desc_set;        /* (NW,WV) exchange_args["desc_set"] */
     const int32_t* d_desc_set_lens; /* (D)     exchange_args["desc_set_lens"] */
+    /* optional, fused training entry points only: MMG_LOSS_COUNT floats of MAPPED PINNED HOST memory (cudaHostAlloc; with unified
+     * addressing the host pointer is the device pointer).  The update kernel writes the iteration's loss values there itself, so no
+     * device-to-host copy has to sit between two iterations; they are valid once the iteration has completed on the stream. */
+    float* h_losses_out;
 } mmg_inputs;
 
 int mmg_abi_version(void);
@@ -279,7 +283,8 @@ int mmg_train_step_host(const mmg_config* cfg, float* d_params, float* d_grads, 
  * mmg_host_prefetch: waits (on copy_stream) for `ev_free` (the staging slot's previous consumer), copies x (B,F) and
  *   target (B) from pinned host memory into the slot and records `ev_ready`.
  * mmg_train_step_staged: `stream` waits for `ev_ready`, runs mmg_train_step on the slot (in->d_x / in->d_target point
- *   at it), records `ev_free` and copies the MMG_LOSS_COUNT loss floats to `h_losses` (pinned).  Streams and events are
+ *   at it), records `ev_free` and copies the MMG_LOSS_COUNT loss floats to `h_losses` (pinned); `h_losses` may be NULL
+ *   when in->h_losses_out is set (the update kernel then delivers them, no copy is enqueued).  Streams and events are
  *   caller-owned handles (cudaStream_t / cudaEvent_t passed as void*); nothing synchronises the host. */
 int mmg_host_prefetch(const mmg_config* cfg, const float* h_x, const int64_t* h_target, float* d_x_stage,
                       int64_t* d_target_stage, void* copy_stream, void* ev_free, void* ev_ready);

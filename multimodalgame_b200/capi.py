@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libmmg_b200.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 
-MMG_ABI_VERSION = 4          # include/mmg_b200.h; a library built from other headers is refused at load time
+MMG_ABI_VERSION = 5          # include/mmg_b200.h; a library built from other headers is refused at load time
 MMG_P_COUNT = 37
 MMG_SEG_COUNT = 4
 MMG_LOSS_COUNT = 16
@@ -72,7 +72,8 @@ class Inputs(C.Structure):
     _fields_ = [("d_x", C.c_void_p), ("d_desc", C.c_void_p), ("d_target", C.c_void_p), ("d_u_sen", C.c_void_p),
                 ("d_u_stop", C.c_void_p), ("d_u_rec", C.c_void_p), ("d_corrupt_mask", C.c_void_p),
                 ("d_h0", C.c_void_p), ("top_k", C.c_int32), ("train", C.c_int32), ("d_u_flip_sen", C.c_void_p),
-                ("d_u_flip_rec", C.c_void_p), ("d_desc_set", C.c_void_p), ("d_desc_set_lens", C.c_void_p)]
+                ("d_u_flip_rec", C.c_void_p), ("d_desc_set", C.c_void_p), ("d_desc_set_lens", C.c_void_p),
+                ("h_losses_out", C.c_void_p)]
 
 
 MMG_MAX_PEERS = 8

@@ -1041,7 +1041,8 @@ int mmg_grad_norm(const mmg_config* cfg, float* d_grads, void* d_workspace, void
 }
 
 static int clip_update_impl(const mmg_config* cfg, float* d_params, float* d_grads, float* d_state1, float* d_state2,
-                            int64_t step, float grad_scale, void* d_workspace, void* stream, int norm_tiles, int loss_parts) {
+                            int64_t step, float grad_scale, void* d_workspace, void* stream, int norm_tiles, int loss_parts,
+                            float* h_losses_out = nullptr) {
     int rc = validate(cfg);
     if (rc) return rc;
     if (!d_params || !d_grads || !d_workspace) return fail(MMG_ERR_INVALID, "null pointer argument");
@@ -1059,7 +1060,8 @@ static int clip_update_impl(const mmg_config* cfg, float* d_params, float* d_gra
     hp.optim = cfg->optim_type; hp.lr = cfg->learning_rate; hp.max_norm = cfg->max_norm; hp.step = step;
     MMG_LAUNCH(k_update, update_ctas(L.total) + (loss_parts > 0 ? 1 : 0), kUpdThreads, 0, (cudaStream_t)stream, seg, hp, d_params, (const float*)d_grads, d_grads,
                d_state1, d_state2, W.norm_final, W.grad_norms, (const double*)W.stats,
-               (const long long*)W.opt_counters, no_peers(), (const float*)W.tile_norm, norm_tiles, loss_parts, d, W);
+               (const long long*)W.opt_counters, no_peers(), (const float*)W.tile_norm, norm_tiles, loss_parts, d, W,
+               loss_parts > 0 ? h_losses_out : nullptr);
     return check_cuda("k_update");
 }
 
@@ -1079,7 +1081,20 @@ int mmg_train_step(const mmg_config* cfg, float* d_params, float* d_grads, float
     if (!fuse_loss && (rc = loss_impl(cfg, d_params, in, d_workspace, -1, stream, none, fused))) return rc;
     int norm_tiles = 0, loss_parts = 0;
     if ((rc = backward_impl(cfg, d_params, in, d_workspace, d_grads, stream, none, fuse_loss, &norm_tiles, &loss_parts))) return rc;
-    return clip_update_impl(cfg, d_params, d_grads, d_state1, d_state2, step, 1.0f, d_workspace, stream, norm_tiles, loss_parts);
+    if ((rc = clip_update_impl(cfg, d_params, d_grads, d_state1, d_state2, step, 1.0f, d_workspace, stream, norm_tiles, loss_parts,
+                               in->h_losses_out))) return rc;
+#ifndef MMG_CPU_EMU
+    if (in->h_losses_out != nullptr && loss_parts == 0) {
+        // the loss values were finalised by an earlier kernel of this sequence (no fused loss path for this configuration):
+        // deliver them with an ordinary copy
+        Ws w;
+        ws_layout(make_dims(*cfg), &w);
+        if (cudaMemcpyAsync(in->h_losses_out, (char*)d_workspace + w.pub.losses, MMG_LOSS_COUNT * sizeof(float), cudaMemcpyDeviceToHost,
+                            (cudaStream_t)stream) != cudaSuccess)
+            return check_cuda("D2H losses");
+    }
+#endif
+    return MMG_OK;
 }
 
 int mmg_train_step_host(const mmg_config* cfg, float* d_params, float* d_grads, float* d_state1, float* d_state2,
@@ -1172,8 +1187,14 @@ int mmg_train_step_peer(const mmg_config* cfg, float* d_params, float* d_grads, 
     hp.optim = cfg->optim_type; hp.lr = cfg->learning_rate; hp.max_norm = cfg->max_norm; hp.step = step;
     MMG_LAUNCH(k_update, update_ctas(L.total) + (loss_parts > 0 ? 1 : 0), kUpdThreads, 0, st, seg, hp, d_params, (const float*)pv.recv[pv.rank], d_grads, d_state1,
                d_state2, W.norm_final, W.grad_norms, (const double*)W.stats, (const long long*)W.opt_counters, pv,
-               (const float*)W.tile_norm, 0, loss_parts, d, W);
-    return check_cuda("k_update");
+               (const float*)W.tile_norm, 0, loss_parts, d, W, loss_parts > 0 ? in->h_losses_out : nullptr);
+    if ((rc = check_cuda("k_update"))) return rc;
+#ifndef MMG_CPU_EMU
+    if (in->h_losses_out != nullptr && loss_parts == 0 &&
+        cudaMemcpyAsync(in->h_losses_out, (char*)d_workspace + w.pub.losses, MMG_LOSS_COUNT * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        return check_cuda("D2H losses");
+#endif
+    return MMG_OK;
 }
 
 int mmg_host_prefetch(const mmg_config* cfg, const float* h_x, const int64_t* h_target, float* d_x_stage,
@@ -1202,7 +1223,7 @@ int mmg_train_step_staged(const mmg_config* cfg, float* d_params, float* d_grads
                           void* ev_ready, void* ev_free) {
     int rc = validate(cfg);
     if (rc) return rc;
-    if (!in || !h_losses || !ev_ready || !ev_free) return fail(MMG_ERR_INVALID, "null pointer argument");
+    if (!in || (!h_losses && !in->h_losses_out) || !ev_ready || !ev_free) return fail(MMG_ERR_INVALID, "null pointer argument");
 #ifndef MMG_CPU_EMU
     cudaStream_t st = (cudaStream_t)stream;
     if (cudaStreamWaitEvent(st, (cudaEvent_t)ev_ready, 0) != cudaSuccess) return check_cuda("wait ev_ready");
@@ -1210,7 +1231,8 @@ int mmg_train_step_staged(const mmg_config* cfg, float* d_params, float* d_grads
     if (cudaEventRecord((cudaEvent_t)ev_free, st) != cudaSuccess) return check_cuda("record ev_free");
     Ws w;
     ws_layout(make_dims(*cfg), &w);
-    if (cudaMemcpyAsync(h_losses, (char*)d_workspace + w.pub.losses, MMG_LOSS_COUNT * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+    if (h_losses != nullptr &&
+        cudaMemcpyAsync(h_losses, (char*)d_workspace + w.pub.losses, MMG_LOSS_COUNT * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess)
         return check_cuda("D2H losses");
     return MMG_OK;
 #else

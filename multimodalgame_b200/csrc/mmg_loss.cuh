@@ -567,7 +567,7 @@ MMG_DEVICE void loss_partials(const WsPtrs& W, const double (&acc)[5]) {
 // `bump_counter`: count this iteration in the receiver message head's own update counter (torch.optim.Adam keeps one step count
 // per parameter, and that head only steps when it received a gradient).  False when an earlier kernel of the fused sequence has
 // already done it (K_wgrad), so that K_update reads a value nobody writes while it runs.
-MMG_DEVICE void loss_finalize(const Dims& d, const WsPtrs& W, int nparts, bool bump_counter = true) {
+MMG_DEVICE void loss_finalize(const Dims& d, const WsPtrs& W, int nparts, bool bump_counter = true, float* host_out = nullptr) {
     MMG_SHARED double red[5][kLossThreads / 32];
     MMG_SHARED double nll_red[kLossThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -609,6 +609,11 @@ MMG_DEVICE void loss_finalize(const Dims& d, const WsPtrs& W, int nparts, bool b
         L[MMG_LOSS_ACTIVE_STEPS] = (float)tp;
         if (bump_counter && st[stat_idx(d, 1, 0, 0)] > 0.0) W.opt_counters[0] += 1;   // updates seen by the receiver message head
         for (int i = MMG_LOSS_ACTIVE_STEPS + 1; i < MMG_LOSS_COUNT; ++i) L[i] = 0.f;
+        if (host_out != nullptr) {        // mapped pinned host memory (mmg_inputs.h_losses_out): four 16-byte stores over PCIe
+#pragma unroll
+            for (int i = 0; i < MMG_LOSS_COUNT; i += 4)
+                *reinterpret_cast<float4*>(host_out + i) = make_float4(L[i], L[i + 1], L[i + 2], L[i + 3]);
+        }
     }
 }
 

@@ -761,13 +761,13 @@ MMG_DEVICE void update_body(const SegInfo& seg, const OptHyper& hp, float* param
 MMG_GLOBAL void __launch_bounds__(kUpdThreads)
 k_update(SegInfo seg, OptHyper hp, float* params, const float* grads_in, float* grads_out, float* state1, float* state2,
          double* norm_final, float* grad_norms, const double* stats, const long long* opt_counters, PeerView pv,
-         const float* tile_norm, int norm_tiles, int n_loss_parts, Dims d, WsPtrs W) {
+         const float* tile_norm, int norm_tiles, int n_loss_parts, Dims d, WsPtrs W, float* h_losses_out) {
     pdl_wait();                 // PDL: the previous kernel of the stream has completed and flushed
     pdl_launch_dependents();    // let the next kernel's CTAs be scheduled behind this grid
     MMG_TRACE_AT(5, 0);
     // fused iteration: the backward kernel left per-CTA partials of the five loss values; ONE EXTRA CTA adds them up beside the
     // update (the values are only reported; as a tail of an update CTA this once-executed code lengthened the kernel by 3 us)
-    if (n_loss_parts > 0 && blockIdx.x == gridDim.x - 1) { loss_finalize(d, W, n_loss_parts, false); MMG_TRACE_AT(5, 6); return; }
+    if (n_loss_parts > 0 && blockIdx.x == gridDim.x - 1) { loss_finalize(d, W, n_loss_parts, false, h_losses_out); MMG_TRACE_AT(5, 6); return; }
     update_body(seg, hp, params, grads_in, grads_out, state1, state2, norm_final, grad_norms, stats, opt_counters, pv, tile_norm,
                 norm_tiles, n_loss_parts > 0 ? (int)gridDim.x - 1 : (int)gridDim.x);
     MMG_TRACE_AT(5, 7);

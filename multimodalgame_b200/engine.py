@@ -243,6 +243,11 @@ class GameEngine(object):
         hp["fn_ts"] = self.lib.dll.mmg_train_step_staged
         hp["graphs"] = None
         hp["losses_dev"] = self.ws("losses", (capi.MMG_LOSS_COUNT,))
+        # loss values of the iteration on staging slot i land here (mapped pinned memory written by the update kernel itself:
+        # no device-to-host copy between two iterations); valid once that iteration has completed
+        hp["h_losses"] = torch.zeros(2, capi.MMG_LOSS_COUNT, dtype=torch.float32).pin_memory()
+        for i in range(2):
+            hp["inp"][i].h_losses_out = C.c_void_p(hp["h_losses"][i].data_ptr())
         if (graphs and self.device.type == "cuda" and getattr(self, "_peers", None) is None
                 and int(self.cfg.optim_type) != capi.OPTIM["Adam"] and os.environ.get("MMG_GRAPHS", "1") != "0"):
             gs = []
@@ -267,7 +272,9 @@ class GameEngine(object):
         hp["pending"] = slot
 
     def train_step_staged(self, h_losses, slot, dp_group=None):
-        """Train on staging slot `slot` (its prefetch was enqueued earlier); loss values land in pinned `h_losses`.
+        """Train on staging slot `slot` (its prefetch was enqueued earlier).  `h_losses` (pinned tensor) receives the loss values
+        through a device-to-host copy; pass None to read them from `staged_losses(slot)` instead — pinned memory the update kernel
+        writes itself, valid once the iteration has completed and until that slot trains again (no copy between iterations).
         Data-parallel engines (enable_peer_dp, or `dp_group` for the NCCL variant) run their own iteration on the slot."""
         hp = self._hp
         if getattr(self, "_peers", None) is not None or dp_group is not None:
@@ -280,7 +287,8 @@ class GameEngine(object):
                 self._peer_iteration(hp["inp"][slot])
             hp["free"][slot].record(st)
             hp["used"][slot] = True
-            h_losses.copy_(self.ws("losses", (capi.MMG_LOSS_COUNT,)), non_blocking=True)
+            if h_losses is not None or dp_group is not None:       # the peer iteration delivers into staged_losses(slot) itself
+                (h_losses if h_losses is not None else hp["h_losses"][slot]).copy_(hp["losses_dev"], non_blocking=True)
             return
         self.step += 1
         if hp["graphs"] is not None:
@@ -288,14 +296,20 @@ class GameEngine(object):
             st.wait_event(hp["ready"][slot])
             hp["graphs"][slot].replay()
             hp["free"][slot].record(st)
-            h_losses.copy_(hp["losses_dev"], non_blocking=True)
+            if h_losses is not None:
+                h_losses.copy_(hp["losses_dev"], non_blocking=True)
             hp["used"][slot] = True
             return
         cfg, p, g, s1, s2, inp, ws, ready, free = hp["ts_args"][slot]
-        rc = hp["fn_ts"](cfg, p, g, s1, s2, self.step, inp, ws, h_losses.data_ptr(), hp["stream_ptr"], ready, free)
+        rc = hp["fn_ts"](cfg, p, g, s1, s2, self.step, inp, ws, None if h_losses is None else h_losses.data_ptr(), hp["stream_ptr"],
+                         ready, free)
         if rc < 0:
             self.lib.check(rc, "mmg_train_step_staged")
         hp["used"][slot] = True
+
+    def staged_losses(self, slot):
+        """Loss values (capi.LOSS_NAMES order) of the last iteration trained on staging slot `slot` (pinned host tensor)."""
+        return self._hp["h_losses"][slot]
 
     # ---- data parallel over NVLink peer memory (no collective call, no extra launch) ---------------------------------
     def enable_peer_dp(self, group=None):
