@@ -250,15 +250,19 @@ class GameEngine(object):
             hp["inp"][i].h_losses_out = C.c_void_p(hp["h_losses"][i].data_ptr())
         if (graphs and self.device.type == "cuda" and getattr(self, "_peers", None) is None
                 and int(self.cfg.optim_type) != capi.OPTIM["Adam"] and os.environ.get("MMG_GRAPHS", "1") != "0"):
-            gs = []
-            for i in range(2):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    cfg, p, gr, s1, s2_, inp, ws, _, _ = hp["ts_args"][i]
-                    self.lib.call("mmg_train_step", cfg, p, gr, s1, s2_, C.c_int64(1), inp, ws,
-                                  C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
-                gs.append(g)
-            hp["graphs"] = gs
+            try:
+                gs = []
+                for i in range(2):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        cfg, p, gr, s1, s2_, inp, ws, _, _ = hp["ts_args"][i]
+                        self.lib.call("mmg_train_step", cfg, p, gr, s1, s2_, C.c_int64(1), inp, ws,
+                                      C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+                    gs.append(g)
+                hp["graphs"] = gs
+            except Exception:           # capture refused (driver / runtime restriction): the eager launch sequence does the same work
+                hp["graphs"] = None
+                torch.cuda.synchronize(dev)
 
     def host_prefetch(self, h_x, h_target):
         """Enqueue the H2D copy of the NEXT batch (pinned host tensors) into the free staging slot."""
