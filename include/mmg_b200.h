@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MMG_ABI_VERSION 5
+#define MMG_ABI_VERSION 6
 
 typedef enum mmg_status {
     MMG_OK = 0,
@@ -319,6 +319,10 @@ typedef struct mmg_peers {
     double* d_norms[MMG_MAX_PEERS];
     unsigned long long* d_flags[MMG_MAX_PEERS];
     int32_t* d_error;      /* local device int, set non-zero when a peer wait timed out */
+    /* optional: MULTICAST address of the `send` region (one address that the NVSwitch resolves to every rank's send buffer,
+     * e.g. torch symmetric memory's multicast_ptr + send_off), or NULL.  With it the owner of a slice sums it with one
+     * multimem.ld_reduce per float4 (the switch reduces in flight) instead of one peer load per rank. */
+    float* d_send_mc;
 } mmg_peers;
 /* Bytes of the symmetric buffer and the offsets of its five sections. */
 int mmg_peer_buffer_layout(const mmg_config* cfg, int64_t* total_bytes, int64_t* send_off, int64_t* recv_off, int64_t* stats_off,

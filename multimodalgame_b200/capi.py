@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libmmg_b200.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 
-MMG_ABI_VERSION = 5          # include/mmg_b200.h; a library built from other headers is refused at load time
+MMG_ABI_VERSION = 6          # include/mmg_b200.h; a library built from other headers is refused at load time
 MMG_P_COUNT = 37
 MMG_SEG_COUNT = 4
 MMG_LOSS_COUNT = 16
@@ -82,7 +82,8 @@ MMG_MAX_PEERS = 8
 class Peers(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("d_send", C.c_void_p * MMG_MAX_PEERS),
                 ("d_recv", C.c_void_p * MMG_MAX_PEERS), ("d_stats", C.c_void_p * MMG_MAX_PEERS),
-                ("d_norms", C.c_void_p * MMG_MAX_PEERS), ("d_flags", C.c_void_p * MMG_MAX_PEERS), ("d_error", C.c_void_p)]
+                ("d_norms", C.c_void_p * MMG_MAX_PEERS), ("d_flags", C.c_void_p * MMG_MAX_PEERS), ("d_error", C.c_void_p),
+                ("d_send_mc", C.c_void_p)]
 
 
 class MmgError(RuntimeError):

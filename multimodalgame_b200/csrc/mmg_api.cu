@@ -686,6 +686,7 @@ static int resolve_peers(const mmg_peers* p, int64_t step, PeerView* pv) {
         return fail(MMG_ERR_INVALID, "bad mmg_peers");
     memset(pv, 0, sizeof(*pv));
     pv->world = p->world; pv->rank = p->rank; pv->error = p->d_error; pv->iter = (unsigned long long)step;
+    pv->send_mc = p->d_send_mc;
     for (int r = 0; r < p->world; ++r) {
         if (!p->d_send[r] || !p->d_recv[r] || !p->d_stats[r] || !p->d_norms[r] || !p->d_flags[r])
             return fail(MMG_ERR_INVALID, "null peer pointer (rank %d)", r);

@@ -34,6 +34,7 @@ struct WsPtrs {               // resolved workspace arrays (device pointers)
 struct PeerView {             // mmg_peers resolved for the kernels; world <= 1: single-rank run, nothing is touched
     int world, rank;
     float* send[MMG_MAX_PEERS];     // local gradients (read by the peers)
+    float* send_mc;                 // multicast address of the send buffers (in-switch reduction), or nullptr
     float* recv[MMG_MAX_PEERS];     // global gradient, written slice by slice by the rank that owns the slice
     double* stats[MMG_MAX_PEERS];
     double* norms[MMG_MAX_PEERS];   // [world][4] per-slice sums of squares of the global gradient

@@ -131,6 +131,13 @@ MMG_DEVICE double ll_load(const double* local_area, int idx, unsigned long long 
     return (double)__uint_as_float((unsigned)a) + (double)__uint_as_float((unsigned)b);
 }
 MMG_DEVICE float4 peer_load4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }   // L1 bypass
+// One float4 summed over every rank's copy by the NVSwitch (NVLS): `mc` is a multicast address.
+MMG_DEVICE float4 multimem_sum4(const float* mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
 MMG_DEVICE double peer_load_d(const double* p) { return __ldcg(p); }
 // L1-bypassing loads for data another CTA of the SAME grid has just written (split-K partial tiles)
 MMG_DEVICE float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
@@ -336,6 +343,7 @@ MMG_DEVICE void fence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 MMG_DEVICE void ll_store(double* area, int idx, double v, unsigned long long) { area[2 * (size_t)idx] = v; }
 MMG_DEVICE double ll_load(const double* area, int idx, unsigned long long, int*) { return area[2 * (size_t)idx]; }
 MMG_DEVICE float4 peer_load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+MMG_DEVICE float4 multimem_sum4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 MMG_DEVICE double peer_load_d(const double* p) { return *p; }
 MMG_DEVICE float4 ld_cg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 MMG_DEVICE float ld_cg(const float* p) { return *p; }

@@ -619,6 +619,15 @@ k_peer_reduce_scatter(SegInfo seg, PeerView pv, float* norm_part, unsigned* tick
     for (long long q = lo + (long long)blockIdx.x * kUpdThreads + tid; q < hi; q += (long long)gridDim.x * kUpdThreads) {
         const long long i = 4 * q;
         const int sg = seg_of(seg.begin, i);
+        if (pv.send_mc != nullptr) {
+            // in-switch reduction: ONE multimem load returns the sum over all ranks (1/G of the inbound bytes); the slice has a
+            // single reducer, so every replica still receives the same numbers
+            const float4 g = multimem_sum4(pv.send_mc + i);
+            *reinterpret_cast<float4*>(pv.recv[pv.rank] + i) = g;
+            ss[sg] = fmaf(g.x, g.x, ss[sg]); ss[sg] = fmaf(g.y, g.y, ss[sg]);
+            ss[sg] = fmaf(g.z, g.z, ss[sg]); ss[sg] = fmaf(g.w, g.w, ss[sg]);
+            continue;
+        }
         // every rank's share of this float4 in flight at once (one NVLink round trip, not one per rank), added in rank order
         float4 sh[MMG_MAX_PEERS];
 #pragma unroll

@@ -337,6 +337,11 @@ class GameEngine(object):
             base = int(hdl.buffer_ptrs[r])
             p.d_send[r], p.d_recv[r], p.d_stats[r] = base + so.value, base + ro.value, base + sto.value
             p.d_norms[r], p.d_flags[r] = base + no.value, base + fo.value
+        # in-switch reduction of the gradient slices when the symmetric buffer has a multicast mapping (NVSwitch, NVLS); MMG_NVLS=0:
+        # one peer load per rank instead
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        p.d_send_mc = C.c_void_p(mc + so.value) if (mc and os.environ.get("MMG_NVLS", "1") != "0") else None
+        self.peer_nvls = bool(p.d_send_mc)
         self._peer_err = torch.zeros(1, dtype=torch.int32, device=self.device)
         p.d_error = self._peer_err.data_ptr()
         self._peers, self._peer_buf, self._peer_hdl = p, buf, hdl

@@ -10,7 +10,7 @@ try:
     h = symm_mem.rendezvous(t, dist.group.WORLD)
     if rank == 0:
         print("handle attrs:", [a for a in dir(h) if not a.startswith("_")])
-        print("buffer_ptrs", h.buffer_ptrs, "signal_pad_ptrs", h.signal_pad_ptrs, "rank", h.rank, "world", h.world_size)
+        print("multicast_ptr", getattr(h, "multicast_ptr", None)); print("buffer_ptrs", h.buffer_ptrs, "signal_pad_ptrs", h.signal_pad_ptrs, "rank", h.rank, "world", h.world_size)
     t.fill_(rank + 1)
     h.barrier()
     peer = h.get_buffer((rank + 1) % world, (1024,), torch.float32)

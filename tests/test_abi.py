@@ -25,7 +25,7 @@ def test_every_declared_symbol_is_exported(lib):
     for name in declared:
         assert hasattr(lib.dll, name), "symbol %s declared in include/mmg_b200.h but not exported" % name
     assert set(capi.Library.SYMBOLS) <= declared
-    assert lib.dll.mmg_abi_version() == capi.MMG_ABI_VERSION == 5
+    assert lib.dll.mmg_abi_version() == capi.MMG_ABI_VERSION == 6
 
 
 def test_layouts_and_validation(lib):
