@@ -170,6 +170,23 @@ def run_train_case(case, lib, device, report=None, grad_rtol=2e-3):
                 errs[name] = assert_close(tag + name, L[name], float(res[name]), rtol=1e-4, atol=1e-4)
         assert int(L["active_steps"]) == Tp, (tag, L["active_steps"], Tp)
         assert abs(L["topk_correct"] / B - res["accuracy"]) < 1e-6, (tag, L["topk_correct"], res["accuracy"])
+        # --- the same outputs DIRECTLY against the vectors the reference's own code produced (tests/golden/make_golden.py), no
+        #     oracle in between: sampled bits and arg-max exact, probabilities / scores / baselines / losses within 1e-4 ---
+        pre = "it%d/" % it
+        if pre + "y" in z.files:
+            gy = z[pre + "y"]
+            Tg = gy.shape[0]
+            assert Tg == Tp, (tag, Tg, Tp)
+            for key in ("sen_feats", "rec_feats", "stop_feat"):
+                if cfg.use_binary or key == "stop_feat":
+                    assert np.array_equal(out[key][:Tg].reshape(z[pre + key].shape), z[pre + key]), tag + key + " differs from the reference's vector"
+            for key in ("y", "sen_probs", "rec_probs", "stop_prob", "bs", "br"):
+                if pre + key in z.files:
+                    assert_close(tag + "golden " + key, out[key][:Tg].reshape(z[pre + key].shape), z[pre + key])
+            assert np.array_equal(out["argmax"].reshape(-1), z[pre + "argmax"].reshape(-1)), tag + "argmax differs from the reference's vector"
+            for name in ("nll_loss", "loss_rec", "loss_sen", "loss_bas_rec", "loss_bas_sen", "loss_binary_rec", "loss_binary_sen"):
+                if pre + name in z.files:
+                    assert_close(tag + "golden " + name, L[name], float(z[pre + name]), rtol=1e-4, atol=1e-4)
         # --- gradients (pre-clip) against autograd of the oracle ---
         gv = e.named_views(e.grads)
         for a in grads:
